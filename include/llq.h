@@ -1,0 +1,158 @@
+/* llq.h -- C-ABI of the batched legged-quadruped rollout engine ("llq").
+ *
+ * This is the drop-in boundary for the hot path named in BASELINE.json: the
+ * TLeague actor's env.reset()/env.step() on the reference's PyBullet envs.
+ * The reference has no FFI of its own for this path (it is pure Python over the
+ * pybullet wheel), so every entry point cites the reference Python interface it
+ * replaces.  Citations are relative to /root/reference/src/lifelike/sim_envs/pybullet_envs/:
+ *   LR  = legged_robot/legged_robot.py
+ *   PLE = primitive_level_env/primitive_level_env.py
+ *   ML  = primitive_level_env/motion_lib.py
+ *   CPE = create_pybullet_envs.py
+ *
+ * Two shared libraries implement this header with identical semantics:
+ *   oracle/libllq_cpu.so                                  fp64 CPU restatement (test oracle only)
+ *   lifelike_agility_and_play_b200/csrc/libllq_cuda.so    fp32 sm_100a CUDA engine (the product)
+ *
+ * Conventions: plain C types only; all array arguments are caller-owned;
+ * every function returns 0 on success and a negative LLQ_E* code on failure,
+ * never aborts; llq_last_error() gives a human-readable message for the last
+ * failure on the calling thread.  A handle is single-owner and not re-entrant;
+ * several handles (one per GPU) may coexist in one process.
+ */
+#ifndef LLQ_H
+#define LLQ_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLQ_ABI_VERSION 1
+
+/* per-env sizes (PMC env, reference PLE:102-124 with the shipped prop_type) */
+#define LLQ_STATE_DIM   37   /* base_pos3 base_orn4(xyzw) base_lin_vel3 base_ang_vel3 joint_pos12 joint_vel12 (LR:86-106) */
+#define LLQ_ACTION_DIM  12   /* residual joint-position targets (PLE:198-200) */
+#define LLQ_PROP_DIM    33   /* joint_pos12 joint_vel12 ang_vel_loc3 lin_vel_loc3 e_g3 (PLE:247-260) */
+#define LLQ_OBS_DIM     207  /* prop 3x33 | prop_a 3x12 | future 4x18 (PLE:117-121,276-297) */
+#define LLQ_MOCAP_FRAME 19   /* x y z qx qy qz qw + 12 joint angles (ML:88-96) */
+#define LLQ_NUM_FEET    4
+
+/* error codes */
+#define LLQ_OK            0
+#define LLQ_EINVAL      (-1)
+#define LLQ_ENOMEM      (-2)
+#define LLQ_ECUDA       (-3)
+#define LLQ_ESTATE      (-4)  /* call order violated (e.g. step before load_model / load_mocap / reset) */
+#define LLQ_EUNSUPPORTED (-5)
+
+/* pointer-space flags for llq_step_ex / llq_reset_ex */
+#define LLQ_IO_HOST    0   /* pointers are host memory (pageable or pinned); copies happen inside the call */
+#define LLQ_IO_DEVICE  1   /* pointers are device memory on the handle's GPU; no host round trip, no sync */
+
+/* field ids for llq_get_field / llq_set_field (host pointers, row-major, [n_envs, width]) */
+#define LLQ_F_STATE       0  /* float   [N,37]  robot state, pybullet base-inertial-frame convention (LR:86-106) */
+#define LLQ_F_CLIP        1  /* int32   [N]     sampled mocap clip id (ML:59-63) */
+#define LLQ_F_TIME        2  /* double  [N]     env clock PLE.time (PLE:208-210,271) */
+#define LLQ_F_REWARD_SUM  3  /* float   [N]     PLE.reward_sum (PLE:231) */
+#define LLQ_F_EPISODE_STEPS 4 /* int32  [N]     PLE._episode_steps (PLE:197) */
+#define LLQ_F_WARMSTART   5  /* float   [N,4]   previous sub-step's normal impulse per foot (contact warm start) */
+#define LLQ_F_OBS         6  /* float   [N,207] last observation (carries the 3-frame prop / action history) */
+#define LLQ_F_KIN_STATE   7  /* float   [N,37]  kinematic (mocap) robot state (PLE:217-218) -- get only */
+#define LLQ_F_SAMPLE_PROB 8  /* double  [n_clips] prioritized sampling probabilities (PLE:239-240) */
+#define LLQ_F_AVG_REWARD  9  /* double  [n_clips] PLE._avg_reward_sum (PLE:236) */
+#define LLQ_F_EPISODE_ID  10 /* int64   [N]     per-env episode counter (RNG stream position) */
+#define LLQ_F_FOOT_POS    11 /* float   [N,12]  world positions of the 4 foot links after the last step (LR:199-205) -- get only */
+
+typedef struct llq_config {
+  int32_t struct_size;        /* = sizeof(llq_config), for ABI checking */
+  int32_t n_envs;             /* environments stepped in lock-step by this handle */
+  int32_t device;             /* CUDA device ordinal (ignored by the CPU oracle) */
+  int32_t substeps;           /* physics sub-steps per env step: int(policy_step/time_step) = 10 (PLE:52) */
+  int32_t solver_iters;       /* PGS iterations, numSolverIterations=10 (LR:261) */
+  int32_t auto_reset;         /* 1: envs that finish are re-sampled inside llq_step (vector-env convention) */
+  int32_t num_threads;        /* CPU oracle: OpenMP threads over envs (0 = all cores); ignored by CUDA */
+  int32_t reserved0;
+  int64_t global_env_offset;  /* global id of env 0 (RNG streams are keyed by global id => result independent of sharding) */
+  uint64_t seed;
+  double sim_dt;              /* 1/sim_freq = 0.002 (PLE:49) */
+  double kp, kd, max_tau;     /* PD gains and torque clip (LR:138-141; train cfg 50, 0.5, 18) */
+  double gravity_z;           /* -9.80665 (LR:260) */
+  double ground_friction;     /* plane.urdf lateral_friction 0.9 (legged_robot/data/urdf/plane.urdf:5) */
+  double foot_friction;       /* foot_lateral_friction 0.5 (LR:304-308) */
+  double contact_erp;         /* Bullet m_erp2 as set by pybullet */
+  double joint_erp;           /* Bullet m_erp (joint-limit rows) */
+  double linear_slop;         /* Bullet m_linearSlop as set by pybullet (1e-5) */
+  double warmstart;           /* Bullet m_warmstartingFactor as set by pybullet (0.1) */
+  double contact_breaking;    /* relative contact breaking threshold: 0.02 * sphere radius */
+  double lin_damping;         /* btMultiBody m_linearDamping 0.04 */
+  double ang_damping;         /* btMultiBody m_angularDamping 0.04 */
+  double max_coord_vel;       /* btMultiBody m_maxCoordinateVelocity 100 */
+  double max_applied_impulse; /* btMultiBody m_maxAppliedImpulse 1000 (joint-limit rows) */
+  double w_joint_pos, w_joint_vel, w_end_effector, w_root_pose, w_root_vel; /* reward weights (PLE:352-370) */
+  double prioritized_sample_factor; /* (PLE:136,239) */
+  double policy_dt;           /* 1/control_freq = 0.02 (PLE:47) -- used for MotionLib margin / max_steps (ML:35,45) */
+} llq_config;
+
+typedef struct llq_engine* llq_handle;
+
+/* ABI / build info: returns LLQ_ABI_VERSION; *is_cuda = 1 for the CUDA engine, 0 for the CPU oracle. */
+int llq_abi_version(int* is_cuda);
+
+/* Fill cfg with the reference's training configuration (train_scripts/example_pmc_train.sh:67-79,
+ * PLE:27-43 defaults, Bullet/pybullet solver defaults of SURVEY appendix A). */
+int llq_default_config(llq_config* cfg);
+
+/* Replaces: PrimitiveLevelEnv.__init__ (PLE:27-148) -- allocate an engine for cfg->n_envs environments. */
+int llq_create(const llq_config* cfg, llq_handle* out);
+
+/* Replaces: PrimitiveLevelEnv.close (PLE:428-431). */
+int llq_destroy(llq_handle h);
+
+/* Replaces: LeggedRobot._init_dynamic_model / loadURDF (LR:207-264).  blob: float64 table produced by
+ * model/compile_model.py, layout in llq_model_layout.h. */
+int llq_load_model(llq_handle h, const double* blob, int64_t n_doubles);
+
+/* Replaces: MotionLib._open_all_mocap_datas (ML:19-46).  frames: [total_frames,19] float64 (clips back to
+ * back, file order = sorted names), clip_offsets: [n_clips+1] prefix offsets, frame_dt = "FrameDuration". */
+int llq_load_mocap(llq_handle h, const double* frames, const int32_t* clip_offsets, int32_t n_clips, double frame_dt);
+
+/* Replaces: PrimitiveLevelEnv.reset (PLE:150-171) for every env with mask[i] != 0 (mask == NULL: all).
+ * Clip ~ prioritized_sample_probability, phase ~ U(0,1) (ML:48-63), drawn from Philox4x32-10 keyed by
+ * (seed, global env id, episode counter).  obs (nullable): [N,207] host buffer receiving the reset obs. */
+int llq_reset(llq_handle h, const uint8_t* mask, float* obs);
+
+/* Deterministic variant used by tests and by the gym adaptor's "reset to clip/time": same as llq_reset but
+ * clip[i] / time[i] are given instead of sampled (ML:50-57 with sampled_time = time[i]). */
+int llq_reset_to(llq_handle h, const uint8_t* mask, const int32_t* clip, const double* time, float* obs);
+
+/* Replaces: PrimitiveLevelEnv.step (PLE:195-245) for all envs, minus the real-time sleep (PLE:241-244).
+ * actions [N,12] -> obs [N,207], reward [N], done [N].  Host pointers; H2D/D2H copies are inside the call. */
+int llq_step(llq_handle h, const float* actions, float* obs, float* reward, uint8_t* done);
+
+/* Same, with explicit pointer space, observation row stride (floats, >= 207; lets the engine write straight
+ * into a [T,N,ld] trajectory slab) and, for LLQ_IO_DEVICE, the CUDA stream (cudaStream_t as void*, NULL =
+ * the handle's own stream) on which the step is enqueued without synchronising. Any of obs/reward/done may be
+ * NULL. */
+int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, float* reward, uint8_t* done,
+                int io_mode, void* stream);
+
+/* State access for parity tests and checkpoint/resume (replaces LR.get_states_info / set_states_info,
+ * LR:62-113, and the env bookkeeping fields).  Host pointers. */
+int llq_get_field(llq_handle h, int field, void* dst);
+int llq_set_field(llq_handle h, int field, const void* src);
+
+/* counters: [0] env steps, [1] episodes finished, [2] contact rows solved, [3] joint-limit rows solved,
+ * [4] kernel launches issued by the engine (CUDA) / 0 (CPU). n <= 8. */
+int llq_get_counters(llq_handle h, int64_t* out, int32_t n);
+
+/* Block until all work enqueued by this handle has finished (no-op for the CPU oracle). */
+int llq_sync(llq_handle h);
+
+const char* llq_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LLQ_H */

@@ -1,0 +1,218 @@
+"""ctypes binding of the C-ABI declared in ``include/llq.h``.
+
+This module is host plumbing only: it marshals numpy buffers (or raw device
+pointers) into the ``llq_*`` entry points.  It never computes anything itself
+and has no CPU fallback -- :func:`load_cuda_library` raises if the CUDA engine
+has not been built.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+STATE_DIM, ACTION_DIM, PROP_DIM, OBS_DIM, MOCAP_FRAME = 37, 12, 33, 207, 19
+
+LLQ_IO_HOST, LLQ_IO_DEVICE = 0, 1
+(F_STATE, F_CLIP, F_TIME, F_REWARD_SUM, F_EPISODE_STEPS, F_WARMSTART, F_OBS, F_KIN_STATE, F_SAMPLE_PROB,
+ F_AVG_REWARD, F_EPISODE_ID, F_FOOT_POS) = range(12)
+
+# field id -> (dtype, per-env width or None for per-clip tables)
+_FIELDS = {
+    F_STATE: (np.float32, STATE_DIM), F_CLIP: (np.int32, 1), F_TIME: (np.float64, 1),
+    F_REWARD_SUM: (np.float32, 1), F_EPISODE_STEPS: (np.int32, 1), F_WARMSTART: (np.float32, 4),
+    F_OBS: (np.float32, OBS_DIM), F_KIN_STATE: (np.float32, STATE_DIM), F_SAMPLE_PROB: (np.float64, None),
+    F_AVG_REWARD: (np.float64, None), F_EPISODE_ID: (np.int64, 1), F_FOOT_POS: (np.float32, 12),
+}
+
+
+class LlqConfig(C.Structure):
+    """Mirror of ``struct llq_config`` (include/llq.h) -- field order and types must match."""
+    _fields_ = [
+        ("struct_size", C.c_int32), ("n_envs", C.c_int32), ("device", C.c_int32), ("substeps", C.c_int32),
+        ("solver_iters", C.c_int32), ("auto_reset", C.c_int32), ("num_threads", C.c_int32), ("reserved0", C.c_int32),
+        ("global_env_offset", C.c_int64), ("seed", C.c_uint64),
+        ("sim_dt", C.c_double), ("kp", C.c_double), ("kd", C.c_double), ("max_tau", C.c_double),
+        ("gravity_z", C.c_double), ("ground_friction", C.c_double), ("foot_friction", C.c_double),
+        ("contact_erp", C.c_double), ("joint_erp", C.c_double), ("linear_slop", C.c_double), ("warmstart", C.c_double),
+        ("contact_breaking", C.c_double), ("lin_damping", C.c_double), ("ang_damping", C.c_double),
+        ("max_coord_vel", C.c_double), ("max_applied_impulse", C.c_double),
+        ("w_joint_pos", C.c_double), ("w_joint_vel", C.c_double), ("w_end_effector", C.c_double),
+        ("w_root_pose", C.c_double), ("w_root_vel", C.c_double),
+        ("prioritized_sample_factor", C.c_double), ("policy_dt", C.c_double),
+    ]
+
+
+class LlqError(RuntimeError):
+    def __init__(self, code, msg):
+        super().__init__("llq error %d: %s" % (code, msg))
+        self.code = code
+
+
+_EXPORTS = ["llq_abi_version", "llq_default_config", "llq_create", "llq_destroy", "llq_load_model", "llq_load_mocap",
+            "llq_reset", "llq_reset_to", "llq_step", "llq_step_ex", "llq_get_field", "llq_set_field",
+            "llq_get_counters", "llq_sync", "llq_last_error"]
+
+
+class LlqLibrary:
+    """A loaded implementation of include/llq.h (CUDA engine or CPU oracle)."""
+
+    def __init__(self, path):
+        if not os.path.exists(path):
+            raise FileNotFoundError(path)
+        self.path = path
+        self.lib = C.CDLL(path, mode=C.RTLD_GLOBAL if False else C.RTLD_LOCAL)
+        for name in _EXPORTS:
+            if not hasattr(self.lib, name):
+                raise AttributeError("%s does not export %s" % (path, name))
+        L = self.lib
+        vp = C.c_void_p
+        L.llq_abi_version.argtypes = [C.POINTER(C.c_int)]
+        L.llq_default_config.argtypes = [C.POINTER(LlqConfig)]
+        L.llq_create.argtypes = [C.POINTER(LlqConfig), C.POINTER(vp)]
+        L.llq_destroy.argtypes = [vp]
+        L.llq_load_model.argtypes = [vp, vp, C.c_int64]
+        L.llq_load_mocap.argtypes = [vp, vp, vp, C.c_int32, C.c_double]
+        L.llq_reset.argtypes = [vp, vp, vp]
+        L.llq_reset_to.argtypes = [vp, vp, vp, vp, vp]
+        L.llq_step.argtypes = [vp, vp, vp, vp, vp]
+        L.llq_step_ex.argtypes = [vp, vp, vp, C.c_int64, vp, vp, C.c_int, vp]
+        L.llq_get_field.argtypes = [vp, C.c_int, vp]
+        L.llq_set_field.argtypes = [vp, C.c_int, vp]
+        L.llq_get_counters.argtypes = [vp, vp, C.c_int32]
+        L.llq_sync.argtypes = [vp]
+        L.llq_last_error.restype = C.c_char_p
+        for name in _EXPORTS[:-1]:
+            getattr(L, name).restype = C.c_int
+        is_cuda = C.c_int(0)
+        self.abi = L.llq_abi_version(C.byref(is_cuda))
+        self.is_cuda = bool(is_cuda.value)
+
+    def check(self, rc):
+        if rc != 0:
+            raise LlqError(rc, (self.lib.llq_last_error() or b"").decode())
+
+    def default_config(self) -> LlqConfig:
+        cfg = LlqConfig()
+        self.check(self.lib.llq_default_config(C.byref(cfg)))
+        return cfg
+
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+CUDA_LIB_PATH = os.path.join(_HERE, "csrc", "libllq_cuda.so")
+_cuda_lib = None
+
+
+def load_cuda_library() -> LlqLibrary:
+    """Load the sm_100a engine.  No fallback: a missing build is a hard error."""
+    global _cuda_lib
+    if _cuda_lib is None:
+        if not os.path.exists(CUDA_LIB_PATH):
+            raise RuntimeError("CUDA engine %s is not built; run `python -c 'import __graft_entry__ as g; g.build()'` "
+                               "(there is no CPU fallback on the product path)" % CUDA_LIB_PATH)
+        lib = LlqLibrary(CUDA_LIB_PATH)
+        if not lib.is_cuda:
+            raise RuntimeError("%s is not the CUDA engine" % CUDA_LIB_PATH)
+        _cuda_lib = lib
+    return _cuda_lib
+
+
+def _ptr(a):
+    return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+class VecEngine:
+    """N lock-step environments behind one ``llq_handle``.
+
+    Array arguments are numpy (host) arrays; ``step_device`` takes raw device
+    pointers (e.g. ``torch.Tensor.data_ptr()``) for the zero-copy path.
+    """
+
+    def __init__(self, lib: LlqLibrary, n_envs, model_blob, mocap, **overrides):
+        self.lib = lib
+        cfg = lib.default_config()
+        cfg.n_envs = int(n_envs)
+        for k, v in overrides.items():
+            if not hasattr(cfg, k):
+                raise TypeError("unknown llq_config field %r" % k)
+            setattr(cfg, k, v)
+        self.cfg = cfg
+        self.n = int(n_envs)
+        self._h = C.c_void_p()
+        lib.check(lib.lib.llq_create(C.byref(cfg), C.byref(self._h)))
+        blob = np.ascontiguousarray(model_blob, dtype=np.float64)
+        lib.check(lib.lib.llq_load_model(self._h, _ptr(blob), blob.size))
+        frames = np.ascontiguousarray(mocap.frames, dtype=np.float64)
+        offs = np.ascontiguousarray(mocap.offsets, dtype=np.int32)
+        self.n_clips = offs.size - 1
+        lib.check(lib.lib.llq_load_mocap(self._h, _ptr(frames), _ptr(offs), self.n_clips, float(mocap.frame_dt)))
+
+    # -- lifecycle
+    def close(self):
+        if self._h:
+            self.lib.lib.llq_destroy(self._h)
+            self._h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    # -- stepping
+    def _mask(self, mask):
+        return None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
+
+    def reset(self, mask=None):
+        obs = np.empty((self.n, OBS_DIM), np.float32)
+        m = self._mask(mask)
+        self.lib.check(self.lib.lib.llq_reset(self._h, _ptr(m), _ptr(obs)))
+        return obs
+
+    def reset_to(self, clip, time, mask=None):
+        obs = np.empty((self.n, OBS_DIM), np.float32)
+        clip = np.ascontiguousarray(np.broadcast_to(clip, (self.n,)), dtype=np.int32)
+        time = np.ascontiguousarray(np.broadcast_to(time, (self.n,)), dtype=np.float64)
+        m = self._mask(mask)
+        self.lib.check(self.lib.lib.llq_reset_to(self._h, _ptr(m), _ptr(clip), _ptr(time), _ptr(obs)))
+        return obs
+
+    def step(self, actions, out=None):
+        a = np.ascontiguousarray(actions, dtype=np.float32)
+        if a.shape != (self.n, ACTION_DIM):
+            raise ValueError("actions must have shape (%d, %d)" % (self.n, ACTION_DIM))
+        if out is None:
+            obs = np.empty((self.n, OBS_DIM), np.float32)
+            rew = np.empty((self.n,), np.float32)
+            done = np.empty((self.n,), np.uint8)
+        else:
+            obs, rew, done = out
+        self.lib.check(self.lib.lib.llq_step(self._h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done)))
+        return obs, rew, done
+
+    def step_device(self, actions_ptr, obs_ptr, reward_ptr, done_ptr, obs_ld=OBS_DIM, stream=None):
+        self.lib.check(self.lib.lib.llq_step_ex(self._h, C.c_void_p(actions_ptr), C.c_void_p(obs_ptr), obs_ld,
+                                                 C.c_void_p(reward_ptr), C.c_void_p(done_ptr), LLQ_IO_DEVICE,
+                                                 C.c_void_p(stream) if stream else None))
+
+    def sync(self):
+        self.lib.check(self.lib.lib.llq_sync(self._h))
+
+    # -- state access
+    def get(self, field):
+        dt, w = _FIELDS[field]
+        arr = np.empty((self.n_clips,) if w is None else ((self.n,) if w == 1 else (self.n, w)), dt)
+        self.lib.check(self.lib.lib.llq_get_field(self._h, field, _ptr(arr)))
+        return arr
+
+    def set(self, field, value):
+        dt, w = _FIELDS[field]
+        shape = (self.n_clips,) if w is None else ((self.n,) if w == 1 else (self.n, w))
+        arr = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), shape), dtype=dt)
+        self.lib.check(self.lib.lib.llq_set_field(self._h, field, _ptr(arr)))
+
+    def counters(self):
+        out = np.zeros(8, np.int64)
+        self.lib.check(self.lib.lib.llq_get_counters(self._h, _ptr(out), 8))
+        return out

@@ -1,0 +1,971 @@
+// llq_kernels.cuh -- sm_100a kernels of the batched quadruped rollout engine.
+//
+// Mapping: one environment = 4 adjacent lanes of a warp, one lane per leg (FR, FL, HR, HL);
+// a warp therefore advances 8 environments.  Base quantities are replicated on the 4 lanes, the per-leg
+// 3-joint chain recursion runs lane-local, and the only cross-lane traffic is
+//   * the reduction of the legs' articulated inertia / bias force into the base (27 floats, xor-shuffles),
+//   * broadcast of unit-impulse base responses and of each Gauss-Seidel row's impulse (shfl, width 4).
+// All ten 2 ms sub-steps of one 50 Hz policy step run inside one launch with the state in registers.
+//
+// Replaces (reference, relative to src/lifelike/sim_envs/pybullet_envs/):
+//   PrimitiveLevelEnv.step                     primitive_level_env/primitive_level_env.py:195-245
+//   LeggedRobot.apply_action                   legged_robot/legged_robot.py:119-148
+//   pybullet stepSimulation (Bullet btMultiBody ABA + PGS)
+//   MotionLib.step/get_states_info(_future)    primitive_level_env/motion_lib.py:65-166
+//   _prepare_obs/_compute_reward/_check_terminate   primitive_level_env.py:276-426
+#pragma once
+#include "llq_math.cuh"
+#include <stdint.h>
+
+namespace llq {
+
+constexpr int kObsDim = 207, kPropDim = 33, kActDim = 12, kStateDim = 37;
+constexpr int kNewObs = 120;  // floats staged per env: prop 33 | action 12 | future 72 (+3 pad)
+
+struct DampItem { float m; float c[3]; float Ic[6]; };
+struct JointConst {
+  float r[3];
+  float m; float h[3]; float I[6];
+  int nd; DampItem d[2];
+  float lower, upper, jdamp; int haslim;
+};
+struct LegConst { JointConst j[3]; float foot[3]; float foot_r; float pad[4]; };
+struct BaseConst { float qI[4]; float m; float h[3]; float I[6]; int nd; DampItem d[3]; };
+struct ModelConst { BaseConst base; LegConst leg[4]; };
+
+struct MocapFrame { double x, y, z, pad; float quat[4]; float q[12]; };  // 96 B, 16-byte aligned
+
+struct StepParams {
+  int n_envs, substeps, solver_iters;
+  float dt, kp, kd, max_tau, gz, mu, erp, jerp, slop, warm, breaking, kl, ka, vmax, max_imp;
+  float w_jp, w_jv, w_ee, w_pose, w_vel;   // already normalised to sum 1
+  double sim_dt, frame_dt;
+  int margin;
+};
+
+struct EnvArrays {      // SoA device arrays, N envs
+  double* pos;          // [3][N]
+  float* st;            // [34][N]: quat4 lin3 ang3 q12 qd12
+  double* time;         // [N]
+  int* clip;            // [N]
+  float* reward_sum;    // [N]
+  int* episode_steps;   // [N]
+  long long* episode;   // [N]
+  float* warm;          // [4][N]
+  float* obs;           // [N][207] (history carry)
+  float* kin;           // [37][N]
+  float* foot_pos;      // [12][N]
+  float* done_reward;   // [N] reward_sum at termination
+  unsigned char* done;  // [N]
+  float* reward;        // [N]
+  unsigned long long* counters;  // [8]
+};
+
+struct MocapDev { const MocapFrame* frames; const int* clip_off; int n_clips; };
+
+#define FULL 0xffffffffu
+
+LLQ_DI float clampf(float v, float lo, float hi) { return fminf(fmaxf(v, lo), hi); }
+LLQ_DI float gsum4(float v) {  // sum over the 4 lanes of an env, result on all 4
+  v += __shfl_xor_sync(FULL, v, 1);
+  v += __shfl_xor_sync(FULL, v, 2);
+  return v;
+}
+LLQ_DI V3 ld3(const float* p) { return V3{p[0], p[1], p[2]}; }
+LLQ_DI Sym3 ldsym(const float* p) { return Sym3{p[0], p[1], p[2], p[3], p[4], p[5]}; }
+
+// spatial motion / force vectors (angular, linear) at a link origin, link coordinates
+struct SV { V3 a, l; };
+
+// bias force of a rigid body (composite m, h, I about the frame origin) moving with (w, v):  v x* (I v)  plus
+// Bullet's per-link damping  m v_c (k + k|v_c|),  I_c w (k + k|w|)  for each original URDF link in the composite.
+template <int ND> LLQ_DI SV bias_force(float m, V3 h, Sym3 I, int nd, const DampItem* d, V3 w, V3 v, float kl, float ka) {
+  V3 hl = fma3(m, v, cross(w, h));
+  V3 ha = mul(I, w) + cross(h, v);
+  SV p;
+  p.a = cross(w, ha) + cross(v, hl);
+  p.l = cross(w, hl);
+  float wn = norm3(w);
+#pragma unroll
+  for (int t = 0; t < ND; t++) {
+    if (t < nd) {
+      V3 c = ld3(d[t].c);
+      V3 vc = v + cross(w, c);
+      V3 f = (d[t].m * (kl + kl * norm3(vc))) * vc;
+      V3 n = (ka + ka * wn) * mul(ldsym(d[t].Ic), w);
+      p.l = p.l + f;
+      p.a = p.a + n + cross(c, f);
+    }
+  }
+  return p;
+}
+
+// articulated inertia blocks: f_ang = A w + B v ; f_lin = B^T w + C v
+struct ABI { Sym3 A; M3 B; Sym3 C; };
+
+LLQ_DI ABI rigid_abi(float m, V3 h, Sym3 I) {
+  ABI r; r.A = I; r.B = skew(h); r.C = Sym3{m, 0.f, 0.f, m, 0.f, m};
+  return r;
+}
+
+// per-joint cache kept for the whole sub-step
+struct JC { float c, s; V3 Ua, Ul; float Dinv, u; };
+
+// Reduce a 1-dof joint about coordinate axis AX (sign SG) out of (I, p), then express the result in the parent frame
+// (rotation E = Rot(AX, angle) with (c, s), origin offset r).  cor = velocity-product acceleration of the link.
+template <int AX, int SG> LLQ_DI void joint_reduce(ABI& I, SV& p, SV cor, float tau, V3 r, JC& jc) {
+  const float sg = (float)SG;
+  V3 Ua = sg * col(I.A, AX), Ul = sg * row(I.B, AX);
+  float D = diag(I.A, AX), Dinv = 1.0f / D;
+  float u = tau - sg * comp(p.a, AX);
+  jc.Ua = Ua; jc.Ul = Ul; jc.Dinv = Dinv; jc.u = u;
+  I.A = sub_outer(I.A, Ua, Dinv);
+  I.B = sub_outer(I.B, Ua, Ul, Dinv);
+  I.C = sub_outer(I.C, Ul, Dinv);
+  float ud = u * Dinv;
+  V3 pa = p.a + mul(I.A, cor.a) + mul(I.B, cor.l) + ud * Ua;
+  V3 pl = p.l + tmul(I.B, cor.a) + mul(I.C, cor.l) + ud * Ul;
+  // rotate into parent axes
+  Sym3 Ar = rot_sym<AX>(I.A, jc.c, jc.s), Cr = rot_sym<AX>(I.C, jc.c, jc.s);
+  M3 Br = rot_mat<AX>(I.B, jc.c, jc.s);
+  V3 par = rot<AX>(pa, jc.c, jc.s), plr = rot<AX>(pl, jc.c, jc.s);
+  // translate by r:  C' = C ; B' = B + rx C ; A' = A - K - K^T - (rx C) rx,  K = B rx (rows of B crossed with r)
+  V3 g0 = cross(r, col(Cr, 0)), g1 = cross(r, col(Cr, 1)), g2 = cross(r, col(Cr, 2));   // columns of G = rx C
+  M3 G = M3{g0.x, g1.x, g2.x, g0.y, g1.y, g2.y, g0.z, g1.z, g2.z};
+  V3 k0 = cross(row(Br, 0), r), k1 = cross(row(Br, 1), r), k2 = cross(row(Br, 2), r);   // rows of K
+  V3 h0 = cross(row(G, 0), r), h1 = cross(row(G, 1), r), h2 = cross(row(G, 2), r);      // rows of G rx (symmetric)
+  I.A = Sym3{Ar.xx - 2.f * k0.x - h0.x, Ar.xy - k0.y - k1.x - h0.y, Ar.xz - k0.z - k2.x - h0.z,
+             Ar.yy - 2.f * k1.y - h1.y, Ar.yz - k1.z - k2.y - h1.z, Ar.zz - 2.f * k2.z - h2.z};
+  I.B = Br + G;
+  I.C = Cr;
+  p.a = par + cross(r, plr);
+  p.l = plr;
+}
+
+// motion transform parent -> child:  a_c = E^T a_p ; l_c = E^T (l_p + a_p x r)
+template <int AX> LLQ_DI SV xmotion(SV vp, V3 r, float c, float s) {
+  SV o; o.a = rotT<AX>(vp.a, c, s); o.l = rotT<AX>(vp.l + cross(vp.a, r), c, s);
+  return o;
+}
+// force transform child -> parent:  n_p = E n_c + r x (E f_c) ; f_p = E f_c
+template <int AX> LLQ_DI SV xforce(SV fc, V3 r, float c, float s) {
+  SV o; o.l = rot<AX>(fc.l, c, s); o.a = rot<AX>(fc.a, c, s) + cross(r, o.l);
+  return o;
+}
+
+// Unit-impulse response (Bullet calcAccelerationDeltasMultiDof): up pass on the owning lane.
+// F3: spatial force applied at the shank origin (shank coords); t1..t3: joint torques.  Returns -Z0 (the force the
+// base sees, base coords) and the per-joint u's.
+LLQ_DI SV response_up(const JC (&jc)[3], const V3 (&r)[3], SV F3, float t1, float t2, float t3, float (&u)[3]) {
+  SV Z = SV{neg(F3.a), neg(F3.l)};
+  u[2] = t3 - (-1.f) * Z.a.y;                               // S3 = (0,-1,0 | 0)
+  float ud = u[2] * jc[2].Dinv;
+  Z.a = fma3(ud, jc[2].Ua, Z.a); Z.l = fma3(ud, jc[2].Ul, Z.l);
+  Z = xforce<1>(Z, r[2], jc[2].c, jc[2].s);
+  u[1] = t2 - (-1.f) * Z.a.y;
+  ud = u[1] * jc[1].Dinv;
+  Z.a = fma3(ud, jc[1].Ua, Z.a); Z.l = fma3(ud, jc[1].Ul, Z.l);
+  Z = xforce<1>(Z, r[1], jc[1].c, jc[1].s);
+  u[0] = t1 - Z.a.x;                                        // S1 = (1,0,0 | 0)
+  ud = u[0] * jc[0].Dinv;
+  Z.a = fma3(ud, jc[0].Ua, Z.a); Z.l = fma3(ud, jc[0].Ul, Z.l);
+  Z = xforce<0>(Z, r[0], jc[0].c, jc[0].s);
+  return SV{neg(Z.a), neg(Z.l)};
+}
+// down pass on every lane: base acceleration a0 (base coords) -> joint accelerations of this lane's leg
+LLQ_DI void response_down(const JC (&jc)[3], const V3 (&r)[3], SV a0, float u1, float u2, float u3, float (&qdd)[3]) {
+  SV a = xmotion<0>(a0, r[0], jc[0].c, jc[0].s);
+  qdd[0] = (u1 - dot(jc[0].Ua, a.a) - dot(jc[0].Ul, a.l)) * jc[0].Dinv;
+  a.a.x += qdd[0];
+  a = xmotion<1>(a, r[1], jc[1].c, jc[1].s);
+  qdd[1] = (u2 - dot(jc[1].Ua, a.a) - dot(jc[1].Ul, a.l)) * jc[1].Dinv;
+  a.a.y -= qdd[1];
+  a = xmotion<1>(a, r[2], jc[2].c, jc[2].s);
+  qdd[2] = (u3 - dot(jc[2].Ua, a.a) - dot(jc[2].Ul, a.l)) * jc[2].Dinv;
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Mocap interpolation (motion_lib.py:88-166), fp32 except positions/time (fp64)
+struct KinBase { double px, py, pz; Q4 q; V3 lin, ang; };
+
+LLQ_DI Q4 ldq(const float* p) { float4 v = *reinterpret_cast<const float4*>(p); return Q4{v.x, v.y, v.z, v.w}; }
+
+LLQ_DI KinBase mocap_base(const MocapFrame* fc, const MocapFrame* fn, double frac, double frame_dt) {
+  KinBase k;
+  double cx = fc->x, cy = fc->y, cz = fc->z, nx = fn->x, ny = fn->y, nz = fn->z;
+  k.px = cx + frac * (nx - cx); k.py = cy + frac * (ny - cy); k.pz = cz + frac * (nz - cz);
+  float inv = (float)(1.0 / frame_dt);
+  k.lin = V3{(float)(nx - cx) * inv, (float)(ny - cy) * inv, (float)(nz - cz) * inv};
+  Q4 qc = qnormalize(ldq(fc->quat)), qn = qnormalize(ldq(fn->quat));
+  V3 rv = q_rotvec(qmul(qconj(qc), qn));
+  k.q = qmul(qc, rotvec_q((float)frac * rv));
+  V3 rw = q_rotvec(qmul(qn, qconj(qc)));
+  float angle = norm3(rw);
+  float sc = angle / (angle + 1e-8f) * inv;
+  k.ang = sc * rw;
+  return k;
+}
+
+// Foot (link *4) world position for a robot state given in the pybullet base-inertial convention:
+// R_bp = world <- B' (URDF body axes), p = base CoM.  q = this leg's joint angles.
+LLQ_DI V3 foot_in_base(const LegConst& L, float q1, float q2, float q3) {
+  float c1, s1, c2, s2, c3, s3;
+  sincosf(q1, &s1, &c1); sincosf(-q2, &s2, &c2); sincosf(-q3, &s3, &c3);
+  V3 p = rot<1>(ld3(L.foot), c3, s3) + ld3(L.j[2].r);
+  p = rot<1>(p, c2, s2) + ld3(L.j[1].r);
+  p = rot<0>(p, c1, s1) + ld3(L.j[0].r);
+  return p;
+}
+
+// Philox4x32-10
+LLQ_DI void philox4x32_10(unsigned (&c)[4], unsigned k0, unsigned k1) {
+#pragma unroll
+  for (int r = 0; r < 10; r++) {
+    unsigned hi0 = __umulhi(0xD2511F53u, c[0]), lo0 = 0xD2511F53u * c[0];
+    unsigned hi1 = __umulhi(0xCD9E8D57u, c[2]), lo1 = 0xCD9E8D57u * c[2];
+    unsigned n0 = hi1 ^ c[1] ^ k0, n1 = lo1, n2 = hi0 ^ c[3] ^ k1, n3 = lo0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Shared tail: given the dynamic robot state (pybullet convention) and the mocap cursor, build the new prop / future
+// into the staging row `snew` (120 floats per env) and return the pieces the reward needs.
+struct ObsCtx {
+  KinBase kb;          // kinematic (mocap) base
+  float kq[3], kqd[3]; // kinematic joints of this lane's leg
+};
+
+LLQ_DI ObsCtx build_obs_new(const MocapDev& mc, const StepParams& P, const ModelConst& M, int lane4, int clip, int frame_id,
+                            double frac, double px, double py, double pz, Q4 qb, V3 lin, V3 ang, const float (&q)[3],
+                            const float (&qd)[3], float* snew) {
+  ObsCtx o;
+  const MocapFrame* f0 = mc.frames + mc.clip_off[clip] + frame_id;
+  o.kb = mocap_base(f0, f0 + 1, frac, P.frame_dt);
+  float inv = (float)(1.0 / P.frame_dt), fr = (float)frac;
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float c = f0->q[3 * lane4 + i], n = f0[1].q[3 * lane4 + i];
+    o.kq[i] = fmaf(fr, n - c, c);
+    o.kqd[i] = (n - c) * inv;
+  }
+  qb = qnormalize(qb);
+  M3 Rb = qmat(qb);
+  // prop (PLE:247-260): joint_pos | joint_vel | R^T w | R^T v | R[2,:]
+#pragma unroll
+  for (int i = 0; i < 3; i++) { snew[3 * lane4 + i] = q[i]; snew[12 + 3 * lane4 + i] = qd[i]; }
+  if (lane4 == 0) {
+    V3 wl = tmul(Rb, ang), vl = tmul(Rb, lin);
+    snew[24] = wl.x; snew[25] = wl.y; snew[26] = wl.z;
+    snew[27] = vl.x; snew[28] = vl.y; snew[29] = vl.z;
+    snew[30] = Rb.a20; snew[31] = Rb.a21; snew[32] = Rb.a22;
+  }
+  // future target `lane4` (ML:75-86, PLE:299-317)
+  {
+    const double tf = lane4 == 0 ? 1. / 30. : (lane4 == 1 ? 1. / 15. : (lane4 == 2 ? 1. / 3. : 1.));
+    double t = P.frame_dt * frac + tf;
+    int fid = (int)floor(t / P.frame_dt);
+    double ffrac = t / P.frame_dt - fid;
+    const MocapFrame* g0 = f0 + fid;
+    KinBase kf = mocap_base(g0, g0 + 1, ffrac, P.frame_dt);
+    V3 dp = tmul(Rb, V3{(float)(kf.px - px), (float)(kf.py - py), (float)(kf.pz - pz)});
+    V3 rv = q_rotvec(qnormalize(qmul(qconj(qb), qnormalize(kf.q))));
+    float angle = norm3(rv);
+    float sc = angle / (angle + 1e-8f);
+    float* o18 = snew + 45 + 18 * lane4;
+    o18[0] = dp.x; o18[1] = dp.y; o18[2] = dp.z;
+    o18[3] = sc * rv.x; o18[4] = sc * rv.y; o18[5] = sc * rv.z;
+    float ff = (float)ffrac;
+#pragma unroll
+    for (int j = 0; j < 12; j++) { float c = g0->q[j], n = g0[1].q[j]; o18[6 + j] = fmaf(ff, n - c, c); }
+  }
+  return o;
+}
+
+// Cooperative, coalesced emission of the 8 observation rows owned by this warp.
+// mode 0 (step):  prop = [old[33:99], new] ; prop_a = [old[12:36], act] ; future = new
+// mode 1 (reset): prop = [new, new, new]  ; prop_a = 0                 ; future = new      (PLE:282-290)
+// `do_row` (bit e of a warp-uniform mask) selects which of the 8 rows are written.
+LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const float* snew_warp, int env0, int n_envs, int mode,
+                          unsigned row_mask) {
+  const int lane = threadIdx.x & 31;
+  for (int base = 0; base < 8 * kObsDim; base += 32) {
+    int idx = base + lane;
+    int e = idx / kObsDim, j = idx - e * kObsDim;
+    bool ok = idx < 8 * kObsDim && (env0 + e) < n_envs && ((row_mask >> e) & 1u);
+    float v = 0.f;
+    if (ok) {
+      const float* sn = snew_warp + e * kNewObs;
+      float* row = obs + (size_t)(env0 + e) * kObsDim;
+      if (j < 99) {
+        if (mode == 1) v = sn[j % kPropDim];
+        else v = j < 66 ? row[j + kPropDim] : sn[j - 66];
+      } else if (j < 135) {
+        int a = j - 99;
+        if (mode == 1) v = 0.f;
+        else v = a < 24 ? row[j + kActDim] : sn[kPropDim + a - 24];
+      } else {
+        v = sn[45 + (j - 135)];
+      }
+    }
+    __syncwarp();
+    if (ok) {
+      obs[(size_t)(env0 + e) * kObsDim + j] = v;
+      if (obs2) obs2[(size_t)(env0 + e) * obs2_ld + j] = v;
+    }
+    __syncwarp();
+  }
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// The fused policy-step kernel.
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev mc, StepParams P, const ModelConst* __restrict__ gmodel,
+                                                         const float* __restrict__ actions, float* obs2, long long obs2_ld,
+                                                         int* __restrict__ winner) {
+  __shared__ ModelConst M;
+  __shared__ __align__(16) float s_new[BLOCK / 4][kNewObs];
+  {
+    const int* src = reinterpret_cast<const int*>(gmodel);
+    int* dst = reinterpret_cast<int*>(&M);
+    for (int i = threadIdx.x; i < (int)(sizeof(ModelConst) / 4); i += BLOCK) dst[i] = src[i];
+  }
+  __syncthreads();
+
+  const int N = P.n_envs;
+  const int gtid = blockIdx.x * BLOCK + threadIdx.x;
+  const int env_raw = gtid >> 2;
+  const int env = env_raw < N ? env_raw : N - 1;   // surplus lanes shadow the last env (they must join the shuffles)
+  const bool valid = env_raw < N;
+  const int k = threadIdx.x & 3;                   // leg
+  const LegConst& L = M.leg[k];
+  const V3 r[3] = {ld3(L.j[0].r), ld3(L.j[1].r), ld3(L.j[2].r)};
+
+  // ---- load state (SoA, coalesced over envs; base entries are broadcast within the 4 lanes)
+  double px = E.pos[env], py = E.pos[N + env], pz = E.pos[2 * N + env];
+  const float* st = E.st;
+  Q4 qb = Q4{st[env], st[N + env], st[2 * N + env], st[3 * N + env]};
+  V3 vw = V3{st[4 * N + env], st[5 * N + env], st[6 * N + env]};
+  V3 ww = V3{st[7 * N + env], st[8 * N + env], st[9 * N + env]};
+  float q[3], qd[3], act[3], tgt[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    q[i] = st[(10 + 3 * k + i) * N + env];
+    qd[i] = st[(22 + 3 * k + i) * N + env];
+    act[i] = actions[(size_t)env * kActDim + 3 * k + i];
+    tgt[i] = clampf(q[i] + act[i], -3.0f, 3.0f);           // PLE:200, LR:126-127
+  }
+  float warm = E.warm[k * N + env];
+  double time = E.time[env];
+  const int clip = E.clip[env];
+  int frame_id = 0; double frame_frac = 0.0;
+  // base orientation: pybullet speaks in the base inertial frame; dynamics run in URDF body axes B' = inertial * qI^-1
+  const Q4 qI = Q4{M.base.qI[0], M.base.qI[1], M.base.qI[2], M.base.qI[3]};
+  Q4 qp = qmul(qnormalize(qb), qconj(qI));
+  unsigned long long n_contact_rows = 0, n_limit_rows = 0;
+  bool bad = false;
+
+  const V3 bh = ld3(M.base.h); const Sym3 bI = ldsym(M.base.I); const float bm = M.base.m;
+
+  for (int sub = 0; sub < P.substeps; sub++) {
+    const float dt = P.dt;
+    // ---------------- PD actuator (LR:138-141) + joint damping (pybullet applyJointDamping)
+    float tau[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      float t = fmaf(P.kp, tgt[i] - q[i], P.kd * (0.f - qd[i]));
+      tau[i] = clampf(t, -P.max_tau, P.max_tau) - L.j[i].jdamp * qd[i];
+    }
+    // ---------------- kinematics
+    const M3 R = qmat(qp);                       // world <- B'
+    JC jc[3];
+    sincosf(q[0], &jc[0].s, &jc[0].c);
+    sincosf(-q[1], &jc[1].s, &jc[1].c);
+    sincosf(-q[2], &jc[2].s, &jc[2].c);
+    // ---------------- ABA pass 1: velocities, velocity products, bias forces (link coords, link origins)
+    SV v0; v0.a = tmul(R, ww); v0.l = tmul(R, vw);
+    SV v1 = xmotion<0>(v0, r[0], jc[0].c, jc[0].s);
+    SV vj = SV{V3{qd[0], 0.f, 0.f}, V3{0.f, 0.f, 0.f}};
+    v1.a.x += qd[0];
+    SV c1 = SV{cross(v1.a, vj.a), cross(v1.l, vj.a)};
+    SV v2 = xmotion<1>(v1, r[1], jc[1].c, jc[1].s);
+    vj.a = V3{0.f, -qd[1], 0.f};
+    v2.a.y -= qd[1];
+    SV c2 = SV{cross(v2.a, vj.a), cross(v2.l, vj.a)};
+    SV v3 = xmotion<1>(v2, r[2], jc[2].c, jc[2].s);
+    vj.a = V3{0.f, -qd[2], 0.f};
+    v3.a.y -= qd[2];
+    SV c3 = SV{cross(v3.a, vj.a), cross(v3.l, vj.a)};
+    // ---------------- ABA pass 2: articulated inertia, leaf -> root inside the lane
+    ABI IA = rigid_abi(L.j[2].m, ld3(L.j[2].h), ldsym(L.j[2].I));
+    SV pA = bias_force<2>(L.j[2].m, ld3(L.j[2].h), ldsym(L.j[2].I), L.j[2].nd, L.j[2].d, v3.a, v3.l, P.kl, P.ka);
+    joint_reduce<1, -1>(IA, pA, c3, tau[2], r[2], jc[2]);
+    {
+      ABI I2 = rigid_abi(L.j[1].m, ld3(L.j[1].h), ldsym(L.j[1].I));
+      SV p2 = bias_force<2>(L.j[1].m, ld3(L.j[1].h), ldsym(L.j[1].I), L.j[1].nd, L.j[1].d, v2.a, v2.l, P.kl, P.ka);
+      IA.A = IA.A + I2.A; IA.B = IA.B + I2.B; IA.C = IA.C + I2.C; pA.a = pA.a + p2.a; pA.l = pA.l + p2.l;
+    }
+    joint_reduce<1, -1>(IA, pA, c2, tau[1], r[1], jc[1]);
+    {
+      ABI I1 = rigid_abi(L.j[0].m, ld3(L.j[0].h), ldsym(L.j[0].I));
+      SV p1 = bias_force<2>(L.j[0].m, ld3(L.j[0].h), ldsym(L.j[0].I), L.j[0].nd, L.j[0].d, v1.a, v1.l, P.kl, P.ka);
+      IA.A = IA.A + I1.A; IA.B = IA.B + I1.B; IA.C = IA.C + I1.C; pA.a = pA.a + p1.a; pA.l = pA.l + p1.l;
+    }
+    joint_reduce<0, 1>(IA, pA, c1, tau[0], r[0], jc[0]);
+    // ---------------- base: sum the four legs (xor shuffles), add the base body, factorise
+    float m6[21], z0[6];
+    {
+      // packed lower triangle of [[A, B], [B^T, C]] : rows 0-2 = A, rows 3-5 = [B^T, C]
+      m6[tri(0, 0)] = IA.A.xx; m6[tri(1, 0)] = IA.A.xy; m6[tri(1, 1)] = IA.A.yy;
+      m6[tri(2, 0)] = IA.A.xz; m6[tri(2, 1)] = IA.A.yz; m6[tri(2, 2)] = IA.A.zz;
+      m6[tri(3, 0)] = IA.B.a00; m6[tri(3, 1)] = IA.B.a10; m6[tri(3, 2)] = IA.B.a20;
+      m6[tri(4, 0)] = IA.B.a01; m6[tri(4, 1)] = IA.B.a11; m6[tri(4, 2)] = IA.B.a21;
+      m6[tri(5, 0)] = IA.B.a02; m6[tri(5, 1)] = IA.B.a12; m6[tri(5, 2)] = IA.B.a22;
+      m6[tri(3, 3)] = IA.C.xx; m6[tri(4, 3)] = IA.C.xy; m6[tri(4, 4)] = IA.C.yy;
+      m6[tri(5, 3)] = IA.C.xz; m6[tri(5, 4)] = IA.C.yz; m6[tri(5, 5)] = IA.C.zz;
+      z0[0] = pA.a.x; z0[1] = pA.a.y; z0[2] = pA.a.z; z0[3] = pA.l.x; z0[4] = pA.l.y; z0[5] = pA.l.z;
+#pragma unroll
+      for (int i = 0; i < 21; i++) m6[i] = gsum4(m6[i]);
+#pragma unroll
+      for (int i = 0; i < 6; i++) z0[i] = gsum4(z0[i]);
+      SV pb = bias_force<3>(bm, bh, bI, M.base.nd, M.base.d, v0.a, v0.l, P.kl, P.ka);
+      M3 hx = skew(bh);
+      m6[tri(0, 0)] += bI.xx; m6[tri(1, 0)] += bI.xy; m6[tri(1, 1)] += bI.yy;
+      m6[tri(2, 0)] += bI.xz; m6[tri(2, 1)] += bI.yz; m6[tri(2, 2)] += bI.zz;
+      m6[tri(3, 0)] += hx.a00; m6[tri(3, 1)] += hx.a10; m6[tri(3, 2)] += hx.a20;
+      m6[tri(4, 0)] += hx.a01; m6[tri(4, 1)] += hx.a11; m6[tri(4, 2)] += hx.a21;
+      m6[tri(5, 0)] += hx.a02; m6[tri(5, 1)] += hx.a12; m6[tri(5, 2)] += hx.a22;
+      m6[tri(3, 3)] += bm; m6[tri(4, 4)] += bm; m6[tri(5, 5)] += bm;
+      z0[0] += pb.a.x; z0[1] += pb.a.y; z0[2] += pb.a.z; z0[3] += pb.l.x; z0[4] += pb.l.y; z0[5] += pb.l.z;
+    }
+    const Chol6 ch = chol6(m6);
+    float a0[6];
+    {
+      float b[6];
+#pragma unroll
+      for (int i = 0; i < 6; i++) b[i] = -z0[i];
+      chol6_solve(ch, b, a0);                   // acceleration relative to free fall (gravity as a fictitious base acceleration)
+    }
+    // ---------------- ABA pass 3
+    float qdd[3];
+    {
+      SV a = xmotion<0>(SV{V3{a0[0], a0[1], a0[2]}, V3{a0[3], a0[4], a0[5]}}, r[0], jc[0].c, jc[0].s);
+      a.a = a.a + c1.a; a.l = a.l + c1.l;
+      qdd[0] = (jc[0].u - dot(jc[0].Ua, a.a) - dot(jc[0].Ul, a.l)) * jc[0].Dinv;
+      a.a.x += qdd[0];
+      a = xmotion<1>(a, r[1], jc[1].c, jc[1].s);
+      a.a = a.a + c2.a; a.l = a.l + c2.l;
+      qdd[1] = (jc[1].u - dot(jc[1].Ua, a.a) - dot(jc[1].Ul, a.l)) * jc[1].Dinv;
+      a.a.y -= qdd[1];
+      a = xmotion<1>(a, r[2], jc[2].c, jc[2].s);
+      a.a = a.a + c3.a; a.l = a.l + c3.l;
+      qdd[2] = (jc[2].u - dot(jc[2].Ua, a.a) - dot(jc[2].Ul, a.l)) * jc[2].Dinv;
+    }
+    // ---------------- velocity prediction  v* = clamp(v + a dt)   (btMultiBody::applyDeltaVeeMultiDof)
+    {
+      V3 wd = mul(R, V3{a0[0], a0[1], a0[2]});
+      V3 vd = mul(R, V3{a0[3], a0[4], a0[5]} + cross(v0.a, v0.l));
+      vd.z += P.gz;
+      ww = V3{clampf(fmaf(wd.x, dt, ww.x), -P.vmax, P.vmax), clampf(fmaf(wd.y, dt, ww.y), -P.vmax, P.vmax), clampf(fmaf(wd.z, dt, ww.z), -P.vmax, P.vmax)};
+      vw = V3{clampf(fmaf(vd.x, dt, vw.x), -P.vmax, P.vmax), clampf(fmaf(vd.y, dt, vw.y), -P.vmax, P.vmax), clampf(fmaf(vd.z, dt, vw.z), -P.vmax, P.vmax)};
+#pragma unroll
+      for (int i = 0; i < 3; i++) qd[i] = clampf(fmaf(qdd[i], dt, qd[i]), -P.vmax, P.vmax);
+    }
+    // predicted velocity in base coordinates (generalised velocity used by the constraint rows)
+    const V3 wbs = tmul(R, ww), vbs = tmul(R, vw);
+
+    // ---------------- collision: foot sphere vs plane z = 0 on the pre-step pose
+    const V3 fb = foot_in_base(L, q[0], q[1], q[2]);     // foot centre, base coords (same trig as jc; recomputed for clarity)
+    const V3 nb = V3{R.a20, R.a21, R.a22};               // world z in base coords
+    const float dist = (float)pz + dot(nb, fb) - L.foot_r;
+    const bool contact = dist < P.breaking;
+    if (!contact) warm = 0.f;
+    const unsigned cmask_w = __ballot_sync(FULL, contact);
+    const unsigned cmask = (cmask_w >> (threadIdx.x & 28)) & 0xFu;     // contact bits of this env's 4 feet
+    // joint-limit rows (btMultiBodyJointLimitConstraint: only when violated)
+    int limdir[3];
+    unsigned mylim = 0;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      limdir[i] = 0;
+      if (L.j[i].haslim) {
+        if (q[i] - L.j[i].lower <= 0.f) limdir[i] = 1;
+        else if (L.j[i].upper - q[i] <= 0.f) limdir[i] = -1;
+      }
+      if (limdir[i]) mylim |= 1u << i;
+    }
+    const bool any_lim_warp = __any_sync(FULL, mylim != 0);
+
+    // ---------------- constraint rows of this lane's own foot: Jacobians + unit-impulse responses
+    // directions (world): n = +z, t1 = -y, t2 = +x   (btPlaneSpace1 of the plane normal)
+    float Jb[3][6], Jl[3][3], Wb[4][3][6], Wl[4][3][3], rhs[3], invd[3], lam[3];
+    float ur[3][3];      // up-pass u's of own rows
+    float A0[3][6];      // base response of own rows
+    float den[3] = {1.f, 1.f, 1.f};
+    {
+      const V3 dirs[3] = {nb, neg(V3{R.a10, R.a11, R.a12}), V3{R.a00, R.a01, R.a02}};
+      // contact point on the sphere surface (base coords) and the same in shank coords
+      const V3 Pb = fb - L.foot_r * nb;
+#pragma unroll
+      for (int d = 0; d < 3; d++) {
+        V3 db = dirs[d];
+        // direction in shank coordinates
+        V3 d3 = rotT<1>(rotT<1>(rotT<0>(db, jc[0].c, jc[0].s), jc[1].c, jc[1].s), jc[2].c, jc[2].s);
+        V3 n3 = rotT<1>(rotT<1>(rotT<0>(nb, jc[0].c, jc[0].s), jc[1].c, jc[1].s), jc[2].c, jc[2].s);
+        V3 P3 = ld3(L.foot) - L.foot_r * n3;
+        SV F3 = SV{cross(P3, d3), d3};
+        // rigid force transport for the Jacobian row: J_i = S_i . F_i
+        SV F = F3;
+        Jl[d][2] = -F.a.y;
+        F = xforce<1>(F, r[2], jc[2].c, jc[2].s);
+        Jl[d][1] = -F.a.y;
+        F = xforce<1>(F, r[1], jc[1].c, jc[1].s);
+        Jl[d][0] = F.a.x;
+        V3 jw = cross(Pb, db);
+        Jb[d][0] = jw.x; Jb[d][1] = jw.y; Jb[d][2] = jw.z; Jb[d][3] = db.x; Jb[d][4] = db.y; Jb[d][5] = db.z;
+        // articulated up pass and base solve
+        SV Fb = response_up(jc, r, F3, 0.f, 0.f, 0.f, ur[d]);
+        float b[6] = {Fb.a.x, Fb.a.y, Fb.a.z, Fb.l.x, Fb.l.y, Fb.l.z};
+        chol6_solve(ch, b, A0[d]);
+      }
+    }
+    // exchange: every lane gets every foot's base response and runs the down pass for its own leg
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+      if (__any_sync(FULL, (cmask >> j) & 1u)) {
+#pragma unroll
+        for (int d = 0; d < 3; d++) {
+          float a[6];
+#pragma unroll
+          for (int t = 0; t < 6; t++) a[t] = __shfl_sync(FULL, A0[d][t], j, 4);
+          const bool own = (j == k);
+          float qd3[3];
+          response_down(jc, r, SV{V3{a[0], a[1], a[2]}, V3{a[3], a[4], a[5]}}, own ? ur[d][0] : 0.f, own ? ur[d][1] : 0.f,
+                        own ? ur[d][2] : 0.f, qd3);
+#pragma unroll
+          for (int t = 0; t < 6; t++) Wb[j][d][t] = a[t];
+#pragma unroll
+          for (int t = 0; t < 3; t++) Wl[j][d][t] = qd3[t];
+          if (own) {
+            float dn = 0.f;
+#pragma unroll
+            for (int t = 0; t < 6; t++) dn = fmaf(Jb[d][t], a[t], dn);
+#pragma unroll
+            for (int t = 0; t < 3; t++) dn = fmaf(Jl[d][t], qd3[t], dn);
+            den[d] = dn;
+          }
+        }
+      }
+    }
+    // own rows: effective mass, right-hand sides (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint)
+    const float mu = P.mu;
+#pragma unroll
+    for (int d = 0; d < 3; d++) {
+      float rel = Jb[d][0] * wbs.x + Jb[d][1] * wbs.y + Jb[d][2] * wbs.z + Jb[d][3] * vbs.x + Jb[d][4] * vbs.y + Jb[d][5] * vbs.z +
+            Jl[d][0] * qd[0] + Jl[d][1] * qd[1] + Jl[d][2] * qd[2];
+      invd[d] = contact ? 1.0f / den[d] : 0.f;
+      if (d == 0) {
+        float pen = dist + P.slop, poserr = 0.f, velerr = -rel;
+        if (pen > 0.f) velerr -= pen / dt; else poserr = -pen * P.erp / dt;
+        rhs[0] = (poserr + velerr) * invd[0];
+        lam[0] = contact ? P.warm * warm : 0.f;
+      } else {
+        rhs[d] = -rel * invd[d];
+        lam[d] = 0.f;
+      }
+    }
+    if (contact) n_contact_rows += 3;
+
+    // joint-limit rows (rare): W for each active (leg j, joint i) row lives in local memory
+    float WLb[4][3][6], WLl[4][3][3], lrhs[3], linvd[3], llam[3];
+    unsigned limmask = 0;   // 12 bits: bit (3*j+i) = row active in this env
+    if (any_lim_warp) {
+      unsigned m0 = __shfl_sync(FULL, mylim, 0, 4), m1 = __shfl_sync(FULL, mylim, 1, 4), m2 = __shfl_sync(FULL, mylim, 2, 4),
+               m3 = __shfl_sync(FULL, mylim, 3, 4);
+      limmask = m0 | (m1 << 3) | (m2 << 6) | (m3 << 9);
+#pragma unroll 1
+      for (int j = 0; j < 4; j++) {
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+          if (!__any_sync(FULL, (limmask >> (3 * j + i)) & 1u)) continue;
+          float uu[3], a[6], b[6];
+          float dirf = (float)limdir[i];
+          SV Fb = response_up(jc, r, SV{V3{0.f, 0.f, 0.f}, V3{0.f, 0.f, 0.f}}, i == 0 ? dirf : 0.f, i == 1 ? dirf : 0.f,
+                              i == 2 ? dirf : 0.f, uu);
+          b[0] = Fb.a.x; b[1] = Fb.a.y; b[2] = Fb.a.z; b[3] = Fb.l.x; b[4] = Fb.l.y; b[5] = Fb.l.z;
+          chol6_solve(ch, b, a);
+#pragma unroll
+          for (int t = 0; t < 6; t++) a[t] = __shfl_sync(FULL, a[t], j, 4);
+          const bool own = (j == k);
+          float qd3[3];
+          response_down(jc, r, SV{V3{a[0], a[1], a[2]}, V3{a[3], a[4], a[5]}}, own ? uu[0] : 0.f, own ? uu[1] : 0.f, own ? uu[2] : 0.f, qd3);
+#pragma unroll
+          for (int t = 0; t < 6; t++) WLb[j][i][t] = a[t];
+#pragma unroll
+          for (int t = 0; t < 3; t++) WLl[j][i][t] = qd3[t];
+          if (own) {
+            // J = dir * e_i  ->  denom = dir * W[i],  rel = dir * qd[i]
+            float den = dirf * qd3[i], rel = dirf * qd[i];
+            float pen = limdir[i] > 0 ? q[i] - L.j[i].lower : L.j[i].upper - q[i];
+            linvd[i] = limdir[i] ? 1.0f / den : 0.f;
+            float poserr = pen > -0.04f ? -pen * P.jerp / dt : 0.f;   // split-impulse threshold quirk
+            lrhs[i] = (poserr - rel) * linvd[i];
+            llam[i] = 0.f;
+            if (limdir[i]) n_limit_rows += 1;
+          }
+        }
+      }
+    }
+
+    // ---------------- projected Gauss-Seidel on delta velocities (base coords + own leg)
+    float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dvl[3] = {0.f, 0.f, 0.f};
+    if (cmask_w) {
+      // warm start (normal rows only)
+#pragma unroll
+      for (int j = 0; j < 4; j++) {
+        float l0 = __shfl_sync(FULL, lam[0], j, 4);
+        if ((cmask >> j) & 1u) {
+#pragma unroll
+          for (int t = 0; t < 6; t++) dvb[t] = fmaf(Wb[j][0][t], l0, dvb[t]);
+#pragma unroll
+          for (int t = 0; t < 3; t++) dvl[t] = fmaf(Wl[j][0][t], l0, dvl[t]);
+        }
+      }
+    }
+    if (cmask_w || any_lim_warp) {
+      for (int it = 0; it < P.solver_iters; it++) {
+        if (any_lim_warp) {
+#pragma unroll 1
+          for (int j = 0; j < 4; j++) {
+#pragma unroll
+            for (int i = 0; i < 3; i++) {
+              if (!__any_sync(FULL, (limmask >> (3 * j + i)) & 1u)) continue;
+              float dl = 0.f;
+              if (j == k && limdir[i]) {
+                float jd = (float)limdir[i] * dvl[i];
+                dl = lrhs[i] - jd * linvd[i];
+                float sum = llam[i] + dl;
+                if (sum < 0.f) { dl = -llam[i]; llam[i] = 0.f; }
+                else if (sum > P.max_imp) { dl = P.max_imp - llam[i]; llam[i] = P.max_imp; }
+                else llam[i] = sum;
+              }
+              dl = __shfl_sync(FULL, dl, j, 4);
+              if ((limmask >> (3 * j + i)) & 1u) {
+#pragma unroll
+                for (int t = 0; t < 6; t++) dvb[t] = fmaf(WLb[j][i][t], dl, dvb[t]);
+#pragma unroll
+                for (int t = 0; t < 3; t++) dvl[t] = fmaf(WLl[j][i][t], dl, dvl[t]);
+              }
+            }
+          }
+        }
+        // normal rows, feet in order FR FL HR HL
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (!__any_sync(FULL, (cmask >> j) & 1u)) continue;
+          float dl = 0.f;
+          if (j == k && contact) {
+            float jd = Jb[0][0] * dvb[0] + Jb[0][1] * dvb[1] + Jb[0][2] * dvb[2] + Jb[0][3] * dvb[3] + Jb[0][4] * dvb[4] + Jb[0][5] * dvb[5] +
+                       Jl[0][0] * dvl[0] + Jl[0][1] * dvl[1] + Jl[0][2] * dvl[2];
+            dl = rhs[0] - jd * invd[0];
+            float sum = lam[0] + dl;
+            if (sum < 0.f) { dl = -lam[0]; lam[0] = 0.f; }
+            else if (sum > 1e10f) { dl = 1e10f - lam[0]; lam[0] = 1e10f; }
+            else lam[0] = sum;
+          }
+          dl = __shfl_sync(FULL, dl, j, 4);
+          if ((cmask >> j) & 1u) {
+#pragma unroll
+            for (int t = 0; t < 6; t++) dvb[t] = fmaf(Wb[j][0][t], dl, dvb[t]);
+#pragma unroll
+            for (int t = 0; t < 3; t++) dvl[t] = fmaf(Wl[j][0][t], dl, dvl[t]);
+          }
+        }
+        // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
+#pragma unroll
+        for (int j = 0; j < 4; j++) {
+          if (!__any_sync(FULL, (cmask >> j) & 1u)) continue;
+          float da = 0.f, db = 0.f;
+          if (j == k && contact) {
+            float ja = Jb[1][0] * dvb[0] + Jb[1][1] * dvb[1] + Jb[1][2] * dvb[2] + Jb[1][3] * dvb[3] + Jb[1][4] * dvb[4] + Jb[1][5] * dvb[5] +
+                       Jl[1][0] * dvl[0] + Jl[1][1] * dvl[1] + Jl[1][2] * dvl[2];
+            float jb = Jb[2][0] * dvb[0] + Jb[2][1] * dvb[1] + Jb[2][2] * dvb[2] + Jb[2][3] * dvb[3] + Jb[2][4] * dvb[4] + Jb[2][5] * dvb[5] +
+                       Jl[2][0] * dvl[0] + Jl[2][1] * dvl[1] + Jl[2][2] * dvl[2];
+            float sa = lam[1] + (rhs[1] - ja * invd[1]), sb = lam[2] + (rhs[2] - jb * invd[2]);
+            float limit = mu * lam[0];
+            float r2 = sa * sa + sb * sb;
+            if (r2 >= limit * limit && r2 > 0.f) {
+              float sc = limit / sqrtf(r2);
+              sa *= sc; sb *= sc;
+            }
+            da = sa - lam[1]; db = sb - lam[2];
+            lam[1] = sa; lam[2] = sb;
+          }
+          da = __shfl_sync(FULL, da, j, 4);
+          db = __shfl_sync(FULL, db, j, 4);
+          if ((cmask >> j) & 1u) {
+#pragma unroll
+            for (int t = 0; t < 6; t++) dvb[t] = fmaf(Wb[j][1][t], da, fmaf(Wb[j][2][t], db, dvb[t]));
+#pragma unroll
+            for (int t = 0; t < 3; t++) dvl[t] = fmaf(Wl[j][1][t], da, fmaf(Wl[j][2][t], db, dvl[t]));
+          }
+        }
+      }
+    }
+    if (contact) warm = lam[0];
+
+    // ---------------- apply the impulses, clamp, integrate (btMultiBody::stepPositionsMultiDof)
+    {
+      V3 dw = mul(R, V3{dvb[0], dvb[1], dvb[2]}), dv = mul(R, V3{dvb[3], dvb[4], dvb[5]});
+      ww = V3{clampf(ww.x + dw.x, -P.vmax, P.vmax), clampf(ww.y + dw.y, -P.vmax, P.vmax), clampf(ww.z + dw.z, -P.vmax, P.vmax)};
+      vw = V3{clampf(vw.x + dv.x, -P.vmax, P.vmax), clampf(vw.y + dv.y, -P.vmax, P.vmax), clampf(vw.z + dv.z, -P.vmax, P.vmax)};
+#pragma unroll
+      for (int i = 0; i < 3; i++) {
+        qd[i] = clampf(qd[i] + dvl[i], -P.vmax, P.vmax);
+        q[i] = fmaf(qd[i], dt, q[i]);
+      }
+      px += (double)vw.x * P.sim_dt; py += (double)vw.y * P.sim_dt; pz += (double)vw.z * P.sim_dt;
+      float fa = norm3(ww);
+      float sc;
+      if (fa < 0.001f) sc = 0.5f * dt - dt * dt * dt * 0.020833333333f * fa * fa;
+      else sc = sinf(0.5f * fa * dt) / fa;
+      Q4 dq = Q4{sc * ww.x, sc * ww.y, sc * ww.z, cosf(0.5f * fa * dt)};
+      qp = qnormalize(qmul(dq, qp));
+    }
+    bad = bad || !(fabsf(qd[0]) <= P.vmax) || !(fabsf(ww.x) <= P.vmax) || !(fabsf(vw.x) <= P.vmax);
+    // ---------------- mocap clock (PLE:208-210): sampled with the time *before* the increment
+    frame_id = (int)floor(time / P.frame_dt);
+    frame_frac = (time - frame_id * P.frame_dt) / P.frame_dt;
+    time += P.sim_dt;
+  }
+
+  // ================= end of the policy step: observation, reward, termination =================
+  qb = qmul(qp, qI);                                 // back to the pybullet (inertial-frame) convention
+  float* snew = &s_new[threadIdx.x >> 2][0];
+  ObsCtx oc = build_obs_new(mc, P, M, k, clip, frame_id, frame_frac, px, py, pz, qb, vw, ww, q, qd, snew);
+#pragma unroll
+  for (int i = 0; i < 3; i++) snew[kPropDim + 3 * k + i] = act[i];
+
+  // reward (PLE:350-426)
+  float djp = 0.f, djv = 0.f;
+#pragma unroll
+  for (int i = 0; i < 3; i++) { float a = q[i] - oc.kq[i], b = qd[i] - oc.kqd[i]; djp = fmaf(a, a, djp); djv = fmaf(b, b, djv); }
+  V3 fd, fk;
+  {
+    M3 Rp = qmat(qp);
+    V3 f = mul(Rp, foot_in_base(L, q[0], q[1], q[2]));
+    fd = V3{(float)px + f.x, (float)py + f.y, (float)pz + f.z};
+    Q4 kqp = qmul(qnormalize(oc.kb.q), qconj(qI));
+    V3 g = mul(qmat(kqp), foot_in_base(L, oc.kq[0], oc.kq[1], oc.kq[2]));
+    // difference of foot positions, formed in double for the base offset
+    fk = V3{(float)(oc.kb.px - px) + g.x - f.x, (float)(oc.kb.py - py) + g.y - f.y, (float)(oc.kb.pz - pz) + g.z - f.z};
+  }
+  float dee = dot(fk, fk);
+  djp = gsum4(djp); djv = gsum4(djv); dee = gsum4(dee);
+  float dpx = (float)(px - oc.kb.px), dpy = (float)(py - oc.kb.py), dpz = (float)(pz - oc.kb.pz);
+  float dp = dpx * dpx + dpy * dpy + dpz * dpz;
+  V3 dvl3 = vw - oc.kb.lin, dva3 = ww - oc.kb.ang;
+  Q4 q1 = qnormalize(qb), q2 = qnormalize(oc.kb.q);
+  float angle = norm3(q_rotvec(qnormalize(qmul(q2, qconj(q1)))));
+  float rew = P.w_jp * expf(-1.0f * djp) + P.w_jv * expf(-0.1f * djv) + P.w_ee * expf(-40.0f * dee) +
+              P.w_pose * expf(-20.0f * dp - 10.0f * angle * angle) + P.w_vel * expf(-2.0f * dot(dvl3, dvl3) - 0.2f * dot(dva3, dva3));
+  // termination (PLE:337-348, LR:158-179, ML:168-172)
+  M3 Rq = qmat(q1);
+  float left_z = Rq.a02 * Rq.a10 - Rq.a12 * Rq.a00;
+  bool fall = left_z > 0.70710678118654752f || left_z < -0.70710678118654752f || Rq.a22 < 0.5f;
+  int nf = mc.clip_off[clip + 1] - mc.clip_off[clip];
+  bool ended = frame_id >= nf - P.margin - 1;
+  bool diff = fabsf(angle) > 1.0f || dp > 1.0f;
+  {
+    int bi = bad ? 1 : 0;
+    bi |= __shfl_xor_sync(FULL, bi, 1);
+    bi |= __shfl_xor_sync(FULL, bi, 2);
+    bad = bi != 0;
+  }
+  if (bad || !isfinite(rew)) { rew = 0.f; bad = true; }
+  bool done = fall || ended || diff || bad;
+
+  // ---- write back state (SoA)
+  if (valid) {
+    float* sw = E.st;
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      sw[(10 + 3 * k + i) * N + env] = q[i];
+      sw[(22 + 3 * k + i) * N + env] = qd[i];
+      E.kin[(13 + 3 * k + i) * N + env] = oc.kq[i];
+      E.kin[(25 + 3 * k + i) * N + env] = oc.kqd[i];
+    }
+    E.warm[k * N + env] = warm;
+    E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
+    if (k == 0) {
+      E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
+      sw[env] = qb.x; sw[N + env] = qb.y; sw[2 * N + env] = qb.z; sw[3 * N + env] = qb.w;
+      sw[4 * N + env] = vw.x; sw[5 * N + env] = vw.y; sw[6 * N + env] = vw.z;
+      sw[7 * N + env] = ww.x; sw[8 * N + env] = ww.y; sw[9 * N + env] = ww.z;
+      E.time[env] = time;
+      float rs = E.reward_sum[env] + rew;
+      E.reward_sum[env] = rs;
+      E.episode_steps[env] += 1;
+      E.reward[env] = rew;
+      E.done[env] = done ? 1 : 0;
+      E.kin[env] = (float)oc.kb.px; E.kin[N + env] = (float)oc.kb.py; E.kin[2 * N + env] = (float)oc.kb.pz;
+      E.kin[3 * N + env] = oc.kb.q.x; E.kin[4 * N + env] = oc.kb.q.y; E.kin[5 * N + env] = oc.kb.q.z; E.kin[6 * N + env] = oc.kb.q.w;
+      E.kin[7 * N + env] = oc.kb.lin.x; E.kin[8 * N + env] = oc.kb.lin.y; E.kin[9 * N + env] = oc.kb.lin.z;
+      E.kin[10 * N + env] = oc.kb.ang.x; E.kin[11 * N + env] = oc.kb.ang.y; E.kin[12 * N + env] = oc.kb.ang.z;
+      if (done) {
+        E.done_reward[env] = rs;
+        atomicMax(&winner[clip], env);       // highest finished env index owns the clip's slot this step (PLE:236)
+      }
+    }
+  }
+  // counters: one atomic per warp
+  {
+    unsigned long long cr = n_contact_rows, lr = n_limit_rows;
+    if (!valid) { cr = 0; lr = 0; }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) { cr += __shfl_xor_sync(FULL, cr, o); lr += __shfl_xor_sync(FULL, lr, o); }
+    unsigned dm = __ballot_sync(FULL, valid && k == 0 && done);
+    if ((threadIdx.x & 31) == 0) {
+      if (cr) atomicAdd(&E.counters[2], cr);
+      if (lr) atomicAdd(&E.counters[3], lr);
+      if (dm) atomicAdd(&E.counters[1], (unsigned long long)__popc(dm));
+    }
+  }
+  // ---- observation rows of this warp (history shift + new prop / action / future), coalesced
+  __syncwarp();
+  const int warp_env0 = (blockIdx.x * BLOCK + (threadIdx.x & ~31)) >> 2;
+  emit_obs_rows(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], warp_env0, N, 0, 0xFFu);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// Reset kernel (PLE:150-171, ML:48-63): also owns the prioritized-sampling table update (PLE:235-240).
+// mode 0: reset envs with done[i] != 0 (auto-reset after a step), sampling clip/phase
+// mode 1: reset envs with mask[i] != 0 (mask == null: all), sampling
+// mode 2: like mode 1 but clip/time given
+// mode 3: no env is reset (table update only; auto_reset off)
+struct ResetParams {
+  int mode; const unsigned char* mask; const int* clip_in; const double* time_in;
+  unsigned long long seed; long long gid0;
+  int* winner_cur; int* winner_next;          // [n_clips]
+  const double* avg_old; double* avg_new;     // [n_clips]
+  double* prob;                               // [n_clips]  (written by block 0)
+  const double* max_steps;                    // [n_clips]
+  double factor;
+  int update_table;                           // 1 after a step
+};
+
+template <int BLOCK>
+__global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev mc, StepParams P, const ModelConst* __restrict__ gmodel,
+                                                          ResetParams RP, float* obs2, long long obs2_ld) {
+  extern __shared__ double s_cdf[];            // [n_clips]
+  __shared__ ModelConst M;
+  __shared__ __align__(16) float s_new[BLOCK / 4][kNewObs];
+  {
+    const int* src = reinterpret_cast<const int*>(gmodel);
+    int* dst = reinterpret_cast<int*>(&M);
+    for (int i = threadIdx.x; i < (int)(sizeof(ModelConst) / 4); i += BLOCK) dst[i] = src[i];
+  }
+  const int C = mc.n_clips;
+  // ---- prioritized sampling table: every block recomputes it identically; block 0 publishes it
+  for (int c = threadIdx.x; c < C; c += BLOCK) {
+    double avg = RP.avg_old[c];
+    if (RP.update_table) {
+      int w = RP.winner_cur[c];
+      if (w >= 0) avg = (double)E.done_reward[w] / RP.max_steps[c];
+    }
+    s_cdf[c] = avg;
+  }
+  __syncthreads();
+  if (RP.update_table && blockIdx.x == 0)
+    for (int c = threadIdx.x; c < C; c += BLOCK) { RP.avg_new[c] = s_cdf[c]; RP.winner_next[c] = -1; }
+  __syncthreads();
+  for (int c = threadIdx.x; c < C; c += BLOCK) s_cdf[c] = pow(1.0 - s_cdf[c], RP.factor);
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    double tot = 0;
+    for (int c = 0; c < C; c++) tot += s_cdf[c];
+    double acc = 0;
+    for (int c = 0; c < C; c++) { s_cdf[c] = s_cdf[c] / tot; }
+    if (blockIdx.x == 0) for (int c = 0; c < C; c++) RP.prob[c] = s_cdf[c];
+    // cumulative, normalised by the final sum like np.random.choice
+    for (int c = 0; c < C; c++) { acc += s_cdf[c]; s_cdf[c] = acc; }
+    double last = s_cdf[C - 1];
+    for (int c = 0; c < C; c++) s_cdf[c] = s_cdf[c] / last;
+  }
+  __syncthreads();
+
+  const int N = P.n_envs;
+  const int gtid = blockIdx.x * BLOCK + threadIdx.x;
+  const int env_raw = gtid >> 2;
+  const int env = env_raw < N ? env_raw : N - 1;
+  const bool valid = env_raw < N;
+  const int k = threadIdx.x & 3;
+  bool doit = valid;
+  if (RP.mode == 3) doit = false;
+  else if (RP.mode == 0) doit = doit && E.done[env] != 0;
+  else if (RP.mask) doit = doit && RP.mask[env] != 0;
+  const unsigned wm = __ballot_sync(FULL, doit);
+  if (wm == 0) return;                                   // warp-uniform: nothing to reset in these 8 envs
+  const LegConst& L = M.leg[k];
+
+  int clip; double t0;
+  long long ep = E.episode[env];
+  if (RP.mode == 2) { clip = RP.clip_in[env]; t0 = RP.time_in[env]; }
+  else {
+    long long gid = RP.gid0 + env;
+    unsigned c4[4] = {(unsigned)gid, (unsigned)((unsigned long long)gid >> 32), (unsigned)ep, (unsigned)((unsigned long long)ep >> 32)};
+    philox4x32_10(c4, (unsigned)RP.seed, (unsigned)(RP.seed >> 32));
+    double u1 = ((double)c4[0] + 0.5) * (1.0 / 4294967296.0), u2 = ((double)c4[1] + 0.5) * (1.0 / 4294967296.0);
+    clip = C - 1;
+    for (int c = 0; c < C; c++) if (s_cdf[c] > u1) { clip = c; break; }
+    int nf = mc.clip_off[clip + 1] - mc.clip_off[clip];
+    t0 = u2 * (P.frame_dt * (double)(nf - P.margin - 1));
+    ep += 1;
+  }
+  int frame_id = (int)floor(t0 / P.frame_dt);
+  double frac = (t0 - frame_id * P.frame_dt) / P.frame_dt;
+  const MocapFrame* f0 = mc.frames + mc.clip_off[clip] + frame_id;
+  KinBase kb = mocap_base(f0, f0 + 1, frac, P.frame_dt);
+  float inv = (float)(1.0 / P.frame_dt), fr = (float)frac;
+  float q[3], qd[3];
+#pragma unroll
+  for (int i = 0; i < 3; i++) {
+    float c = f0->q[3 * k + i], n = f0[1].q[3 * k + i];
+    q[i] = fmaf(fr, n - c, c);
+    qd[i] = (n - c) * inv;
+  }
+  float* snew = &s_new[threadIdx.x >> 2][0];
+  build_obs_new(mc, P, M, k, clip, frame_id, frac, kb.px, kb.py, kb.pz, kb.q, kb.lin, kb.ang, q, qd, snew);
+  if (doit) {
+    float* sw = E.st;
+    const Q4 qI = Q4{M.base.qI[0], M.base.qI[1], M.base.qI[2], M.base.qI[3]};
+    V3 f = mul(qmat(qmul(qnormalize(kb.q), qconj(qI))), foot_in_base(L, q[0], q[1], q[2]));
+#pragma unroll
+    for (int i = 0; i < 3; i++) {
+      sw[(10 + 3 * k + i) * N + env] = q[i]; sw[(22 + 3 * k + i) * N + env] = qd[i];
+      E.kin[(13 + 3 * k + i) * N + env] = q[i]; E.kin[(25 + 3 * k + i) * N + env] = qd[i];
+    }
+    E.warm[k * N + env] = 0.f;
+    E.foot_pos[(3 * k) * N + env] = (float)kb.px + f.x; E.foot_pos[(3 * k + 1) * N + env] = (float)kb.py + f.y;
+    E.foot_pos[(3 * k + 2) * N + env] = (float)kb.pz + f.z;
+    if (k == 0) {
+      E.pos[env] = kb.px; E.pos[N + env] = kb.py; E.pos[2 * N + env] = kb.pz;
+      float b[13] = {kb.q.x, kb.q.y, kb.q.z, kb.q.w, kb.lin.x, kb.lin.y, kb.lin.z, kb.ang.x, kb.ang.y, kb.ang.z, 0.f, 0.f, 0.f};
+#pragma unroll
+      for (int i = 0; i < 10; i++) sw[i * N + env] = b[i];
+      E.kin[env] = (float)kb.px; E.kin[N + env] = (float)kb.py; E.kin[2 * N + env] = (float)kb.pz;
+#pragma unroll
+      for (int i = 0; i < 10; i++) E.kin[(3 + i) * N + env] = b[i];
+      E.time[env] = t0; E.clip[env] = clip; E.reward_sum[env] = 0.f; E.episode_steps[env] = 0; E.episode[env] = ep;
+    }
+  }
+  __syncwarp();
+  unsigned rows = 0;
+#pragma unroll
+  for (int e = 0; e < 8; e++) if ((wm >> (4 * e)) & 1u) rows |= 1u << e;
+  const int warp_env0 = (blockIdx.x * BLOCK + (threadIdx.x & ~31)) >> 2;
+  emit_obs_rows(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], warp_env0, N, 1, rows);
+}
+
+}  // namespace llq

@@ -1,0 +1,1079 @@
+// llq_oracle.cpp -- CPU restatement ("oracle") of the reference env.step() hot path.
+//
+//  *** TEST INFRASTRUCTURE ONLY ***  Only tests/, __graft_entry__.smoke() and bench.py's
+//  cpu_baseline / --impl reference legs may load libllq_cpu.so.  The product path
+//  (lifelike_agility_and_play_b200/) never links, imports or calls anything in oracle/.
+//
+//  PARITY STATUS: the *environment logic* (mocap interpolation, observation, reward,
+//  termination, clocks, sampling) is pinned against the reference's own Python code run in
+//  this container (tests/golden/gen_golden_from_reference.py imports MotionLib /
+//  PrimitiveLevelEnv from /root/reference with pybullet replaced by a shim).  The *physics*
+//  (Bullet btMultiBody step) is "parity unpinned": PyBullet/Bullet3 is an un-vendored,
+//  un-pinned dependency (setup.py:20) that is absent from /root/reference and from this
+//  image, and the reference's tests hold no golden vectors.  The physics
+//  below restates Bullet's published algorithm as listed in SURVEY.md appendix A.
+//
+//  fp64 throughout; one environment at a time; OpenMP over environments.
+//  Citations: LR/PLE/ML/CPE as in include/llq.h.
+//
+//  Formulation (deliberately different from the CUDA engine so that the two cross-check):
+//  generic kinematic tree read from the model blob (23 links, fixed joints kept as 0-dof
+//  links like Bullet without URDF_MERGE_FIXED_LINKS), spatial quantities in each link's
+//  inertial (CoM, principal-axes) frame, dense 6x6 articulated inertias, generalized
+//  velocity (omega_world, v_world, qdot) exactly as btMultiBody stores it.
+#include "../include/llq.h"
+#include "../include/llq_model_layout.h"
+
+#include <algorithm>
+#include <cmath>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <vector>
+#ifdef _OPENMP
+#include <omp.h>
+#endif
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) { g_err = msg; return code; }
+
+// ------------------------------------------------------------------ small linear algebra
+struct V3 { double x, y, z; };
+struct M3 { double m[3][3]; };
+inline V3 operator+(V3 a, V3 b) { return {a.x + b.x, a.y + b.y, a.z + b.z}; }
+inline V3 operator-(V3 a, V3 b) { return {a.x - b.x, a.y - b.y, a.z - b.z}; }
+inline V3 operator*(double s, V3 a) { return {s * a.x, s * a.y, s * a.z}; }
+inline double dot(V3 a, V3 b) { return a.x * b.x + a.y * b.y + a.z * b.z; }
+inline V3 cross(V3 a, V3 b) { return {a.y * b.z - a.z * b.y, a.z * b.x - a.x * b.z, a.x * b.y - a.y * b.x}; }
+inline double norm(V3 a) { return std::sqrt(dot(a, a)); }
+inline V3 mul(const M3& A, V3 v) {
+  return {A.m[0][0] * v.x + A.m[0][1] * v.y + A.m[0][2] * v.z, A.m[1][0] * v.x + A.m[1][1] * v.y + A.m[1][2] * v.z,
+          A.m[2][0] * v.x + A.m[2][1] * v.y + A.m[2][2] * v.z};
+}
+inline V3 tmul(const M3& A, V3 v) {  // A^T v
+  return {A.m[0][0] * v.x + A.m[1][0] * v.y + A.m[2][0] * v.z, A.m[0][1] * v.x + A.m[1][1] * v.y + A.m[2][1] * v.z,
+          A.m[0][2] * v.x + A.m[1][2] * v.y + A.m[2][2] * v.z};
+}
+inline M3 mul(const M3& A, const M3& B) {
+  M3 C;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C.m[i][j] = A.m[i][0] * B.m[0][j] + A.m[i][1] * B.m[1][j] + A.m[i][2] * B.m[2][j];
+  return C;
+}
+inline M3 transpose(const M3& A) {
+  M3 C;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) C.m[i][j] = A.m[j][i];
+  return C;
+}
+inline M3 ident() { return {{{1, 0, 0}, {0, 1, 0}, {0, 0, 1}}}; }
+inline M3 from9(const double* p) {
+  M3 A;
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) A.m[i][j] = p[3 * i + j];
+  return A;
+}
+inline M3 axis_angle(V3 a, double q) {  // Rodrigues, |a| = 1
+  double c = std::cos(q), s = std::sin(q), t = 1 - c;
+  return {{{t * a.x * a.x + c, t * a.x * a.y - s * a.z, t * a.x * a.z + s * a.y},
+           {t * a.x * a.y + s * a.z, t * a.y * a.y + c, t * a.y * a.z - s * a.x},
+           {t * a.x * a.z - s * a.y, t * a.y * a.z + s * a.x, t * a.z * a.z + c}}};
+}
+
+// quaternions are (x, y, z, w), scalar last, as scipy / pybullet
+struct Q4 { double x, y, z, w; };
+inline Q4 qnormalize(Q4 q) {
+  double n = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z + q.w * q.w);
+  return {q.x / n, q.y / n, q.z / n, q.w / n};
+}
+inline Q4 qmul(Q4 a, Q4 b) {  // Hamilton product; scipy R1*R2 == qmul(q1, q2)
+  return {a.w * b.x + a.x * b.w + a.y * b.z - a.z * b.y, a.w * b.y - a.x * b.z + a.y * b.w + a.z * b.x,
+          a.w * b.z + a.x * b.y - a.y * b.x + a.z * b.w, a.w * b.w - a.x * b.x - a.y * b.y - a.z * b.z};
+}
+inline Q4 qconj(Q4 q) { return {-q.x, -q.y, -q.z, q.w}; }
+inline M3 qmat(Q4 q) {  // scipy Rotation.from_quat(q).as_matrix(), q unit
+  double x = q.x, y = q.y, z = q.z, w = q.w;
+  return {{{1 - 2 * (y * y + z * z), 2 * (x * y - z * w), 2 * (x * z + y * w)},
+           {2 * (x * y + z * w), 1 - 2 * (x * x + z * z), 2 * (y * z - x * w)},
+           {2 * (x * z - y * w), 2 * (y * z + x * w), 1 - 2 * (x * x + y * y)}}};
+}
+// scipy Rotation.as_rotvec: angle in [0, pi]
+inline V3 q_rotvec(Q4 q) {
+  if (q.w < 0) q = {-q.x, -q.y, -q.z, -q.w};
+  double s = std::sqrt(q.x * q.x + q.y * q.y + q.z * q.z);
+  double angle = 2 * std::atan2(s, q.w);
+  double scale;
+  if (angle <= 1e-3) {
+    double a2 = angle * angle;
+    scale = 2 + a2 / 12 + 7 * a2 * a2 / 2880;
+  } else {
+    scale = angle / std::sin(angle / 2);
+  }
+  return {scale * q.x, scale * q.y, scale * q.z};
+}
+// scipy Rotation.from_rotvec
+inline Q4 rotvec_q(V3 r) {
+  double angle = norm(r), scale;
+  if (angle <= 1e-3) {
+    double a2 = angle * angle;
+    scale = 0.5 - a2 / 48 + a2 * a2 / 3840;
+  } else {
+    scale = std::sin(angle / 2) / angle;
+  }
+  return {scale * r.x, scale * r.y, scale * r.z, std::cos(angle / 2)};
+}
+
+// ------------------------------------------------------------------ 6-vectors / 6x6 (angular first)
+struct S6 { double v[6]; };
+struct M6 { double m[6][6]; };
+inline S6 s6(V3 a, V3 l) { return {{a.x, a.y, a.z, l.x, l.y, l.z}}; }
+inline V3 ang(const S6& s) { return {s.v[0], s.v[1], s.v[2]}; }
+inline V3 lin(const S6& s) { return {s.v[3], s.v[4], s.v[5]}; }
+inline double dot6(const S6& a, const S6& b) {
+  double r = 0;
+  for (int i = 0; i < 6; i++) r += a.v[i] * b.v[i];
+  return r;
+}
+inline S6 mul6(const M6& A, const S6& x) {
+  S6 y;
+  for (int i = 0; i < 6; i++) {
+    double r = 0;
+    for (int j = 0; j < 6; j++) r += A.m[i][j] * x.v[j];
+    y.v[i] = r;
+  }
+  return y;
+}
+inline S6 tmul6(const M6& A, const S6& x) {  // A^T x
+  S6 y;
+  for (int i = 0; i < 6; i++) {
+    double r = 0;
+    for (int j = 0; j < 6; j++) r += A.m[j][i] * x.v[j];
+    y.v[i] = r;
+  }
+  return y;
+}
+// motion transform parent(CoM frame) -> child(CoM frame): ang_c = R ang_p ; lin_c = R lin_p - r x (R ang_p)
+inline M6 motion_xform(const M3& R, V3 r) {
+  M6 X;
+  std::memset(&X, 0, sizeof(X));
+  M3 rx = {{{0, -r.z, r.y}, {r.z, 0, -r.x}, {-r.y, r.x, 0}}};
+  M3 rxR = mul(rx, R);
+  for (int i = 0; i < 3; i++)
+    for (int j = 0; j < 3; j++) {
+      X.m[i][j] = R.m[i][j];
+      X.m[i + 3][j + 3] = R.m[i][j];
+      X.m[i + 3][j] = -rxR.m[i][j];
+    }
+  return X;
+}
+// solve A x = b for symmetric positive definite 6x6 (Cholesky)
+inline bool chol6(const M6& A, double L[6][6]) {
+  for (int i = 0; i < 6; i++)
+    for (int j = 0; j <= i; j++) {
+      double s = A.m[i][j];
+      for (int k = 0; k < j; k++) s -= L[i][k] * L[j][k];
+      if (i == j) {
+        if (!(s > 0)) return false;
+        L[i][i] = std::sqrt(s);
+      } else {
+        L[i][j] = s / L[j][j];
+      }
+    }
+  return true;
+}
+inline S6 chol6_solve(const double L[6][6], const S6& b) {
+  double y[6];
+  for (int i = 0; i < 6; i++) {
+    double s = b.v[i];
+    for (int k = 0; k < i; k++) s -= L[i][k] * y[k];
+    y[i] = s / L[i][i];
+  }
+  S6 x;
+  for (int i = 5; i >= 0; i--) {
+    double s = y[i];
+    for (int k = i + 1; k < 6; k++) s -= L[k][i] * x.v[k];
+    x.v[i] = s / L[i][i];
+  }
+  return x;
+}
+
+// ------------------------------------------------------------------ Philox4x32-10 (counter-based RNG)
+inline void philox4x32_10(uint32_t c[4], uint32_t k0, uint32_t k1) {
+  for (int r = 0; r < 10; r++) {
+    uint64_t p0 = (uint64_t)0xD2511F53u * c[0], p1 = (uint64_t)0xCD9E8D57u * c[2];
+    uint32_t n0 = (uint32_t)(p1 >> 32) ^ c[1] ^ k0, n1 = (uint32_t)p1;
+    uint32_t n2 = (uint32_t)(p0 >> 32) ^ c[3] ^ k1, n3 = (uint32_t)p0;
+    c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
+    k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+  }
+}
+// two uniforms in (0,1) for (seed, global env id, episode counter)
+inline void reset_uniforms(uint64_t seed, int64_t gid, int64_t episode, double* u_clip, double* u_phase) {
+  uint32_t c[4] = {(uint32_t)gid, (uint32_t)((uint64_t)gid >> 32), (uint32_t)episode, (uint32_t)((uint64_t)episode >> 32)};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  *u_clip = ((double)c[0] + 0.5) * (1.0 / 4294967296.0);
+  *u_phase = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
+}
+
+// ------------------------------------------------------------------ model
+struct LinkM {
+  int parent, jtype, dof;
+  V3 jxyz; M3 jrot; V3 axis;
+  double mass; V3 com; M3 Rin; V3 idiag;
+  double lower, upper, jdamp; bool haslim;
+};
+struct SphereM { int link; V3 c; double r, mu; };
+struct Model {
+  std::vector<LinkM> links;
+  std::vector<SphereM> spheres;
+  int ndof = 0;
+  std::vector<int> dof_link;  // dof -> link
+};
+
+constexpr int MAXL = 32;   // max links
+constexpr int MAXD = 6 + 16;
+
+struct Env {
+  double pos[3], quat[4], linv[3], angv[3], q[12], qd[12];
+  double kin[LLQ_STATE_DIM];
+  double time; int clip; double reward_sum; int episode_steps; int64_t episode;
+  int frame_id; double frame_frac;
+  double warm[8];
+  double prop_hist[3][LLQ_PROP_DIM]; double act_hist[3][LLQ_ACTION_DIM];
+  double foot_pos[12];
+  float obs[LLQ_OBS_DIM];
+};
+
+}  // namespace
+
+struct llq_engine {
+  llq_config cfg;
+  Model model; bool has_model = false;
+  std::vector<double> frames; std::vector<int32_t> clip_off; int n_clips = 0; double frame_dt = 0; bool has_mocap = false;
+  int frame_rate = 0, margin = 0;
+  std::vector<double> max_steps, sample_prob, avg_reward;
+  std::vector<Env> envs; bool was_reset = false;
+  int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+};
+
+namespace {
+
+// ------------------------------------------------------------------ kinematics of the tree
+struct Kin {
+  M3 Rl[MAXL]; V3 pl[MAXL];   // link frames in world
+  M3 Rc[MAXL]; V3 pc[MAXL];   // inertial (CoM) frames in world
+};
+void kinematics(const Model& md, const double pos[3], const double quat[4], const double* q, Kin& k) {
+  Q4 qb = qnormalize({quat[0], quat[1], quat[2], quat[3]});
+  M3 Rb = qmat(qb);
+  const LinkM& b = md.links[0];
+  k.Rl[0] = mul(Rb, transpose(b.Rin));           // base state is the pose of the base inertial frame
+  k.pl[0] = V3{pos[0], pos[1], pos[2]} - mul(k.Rl[0], b.com);
+  k.Rc[0] = Rb; k.pc[0] = {pos[0], pos[1], pos[2]};
+  for (size_t i = 1; i < md.links.size(); i++) {
+    const LinkM& l = md.links[i];
+    M3 R = mul(k.Rl[l.parent], l.jrot);
+    if (l.jtype == 1) R = mul(R, axis_angle(l.axis, q[l.dof]));
+    k.Rl[i] = R;
+    k.pl[i] = k.pl[l.parent] + mul(k.Rl[l.parent], l.jxyz);
+    k.Rc[i] = mul(R, l.Rin);
+    k.pc[i] = k.pl[i] + mul(R, l.com);
+  }
+}
+
+// ------------------------------------------------------------------ articulated-body algorithm (Bullet layout)
+struct AbaCache {
+  M6 X[MAXL];        // motion transform parent CoM frame -> link CoM frame
+  S6 S[MAXL];        // joint motion subspace (revolute) in link CoM frame
+  S6 U[MAXL]; double Dinv[MAXL];
+  double L0[6][6];   // Cholesky factor of the base articulated inertia
+  M3 Rb;
+};
+
+// Forward dynamics: returns generalized acceleration (omegadot_world, vdot_world, qdd) in acc[6+ndof].
+// ext_f / ext_n: optional per-link external force / torque about the CoM, world frame (may be null).
+bool aba(const llq_engine& E, const Kin& k, const double* gv /*omega_w, v_w, qd*/, const double* tau,
+         const V3* ext_f, const V3* ext_n, double* acc, AbaCache& c) {
+  const Model& md = E.model;
+  const int n = (int)md.links.size();
+  const double kl = E.cfg.lin_damping, ka = E.cfg.ang_damping;
+  S6 v[MAXL], cor[MAXL], Z[MAXL], a[MAXL]; M6 IA[MAXL]; double u[MAXL];
+  V3 g = {0, 0, E.cfg.gravity_z};
+  c.Rb = k.Rc[0];
+  for (int i = 0; i < n; i++) {
+    const LinkM& l = md.links[i];
+    if (i == 0) {
+      v[0] = s6(tmul(k.Rc[0], V3{gv[0], gv[1], gv[2]}), tmul(k.Rc[0], V3{gv[3], gv[4], gv[5]}));
+      std::memset(&cor[0], 0, sizeof(S6));
+    } else {
+      M3 R = mul(transpose(k.Rc[i]), k.Rc[l.parent]);
+      V3 r = tmul(k.Rc[i], k.pc[i] - k.pc[l.parent]);
+      c.X[i] = motion_xform(R, r);
+      v[i] = mul6(c.X[i], v[l.parent]);
+      if (l.jtype == 1) {
+        V3 sa = tmul(l.Rin, l.axis);
+        V3 d = tmul(l.Rin, l.com);           // joint pivot (link origin) -> CoM, inertial coords
+        c.S[i] = s6(sa, cross(sa, d));
+        double qd = gv[6 + l.dof];
+        S6 vj;
+        for (int t = 0; t < 6; t++) vj.v[t] = c.S[i].v[t] * qd;
+        for (int t = 0; t < 6; t++) v[i].v[t] += vj.v[t];
+        // velocity-product acceleration  c = v x vj  (motion cross product)
+        V3 w = ang(v[i]), vl = lin(v[i]), wj = ang(vj), vjl = lin(vj);
+        cor[i] = s6(cross(w, wj), cross(w, vjl) + cross(vl, wj));
+      } else {
+        std::memset(&cor[i], 0, sizeof(S6));
+      }
+    }
+    // zero-acceleration (bias) force, Bullet order: -external, +damping, +gyroscopic
+    V3 w = ang(v[i]), vl = lin(v[i]);
+    V3 Iw = {l.idiag.x * w.x, l.idiag.y * w.y, l.idiag.z * w.z};
+    V3 f_ext = l.mass * g;
+    V3 n_ext = {0, 0, 0};
+    if (ext_f) f_ext = f_ext + ext_f[i];
+    if (ext_n) n_ext = n_ext + ext_n[i];
+    V3 zn = (-1.0) * tmul(k.Rc[i], n_ext), zf = (-1.0) * tmul(k.Rc[i], f_ext);
+    zn = zn + (ka + ka * norm(w)) * Iw;
+    zf = zf + (l.mass * (kl + kl * norm(vl))) * vl;
+    zn = zn + cross(w, Iw);
+    zf = zf + l.mass * cross(w, vl);
+    Z[i] = s6(zn, zf);
+    std::memset(&IA[i], 0, sizeof(M6));
+    IA[i].m[0][0] = l.idiag.x; IA[i].m[1][1] = l.idiag.y; IA[i].m[2][2] = l.idiag.z;
+    IA[i].m[3][3] = IA[i].m[4][4] = IA[i].m[5][5] = l.mass;
+  }
+  for (int i = n - 1; i >= 1; i--) {
+    const LinkM& l = md.links[i];
+    M6 Ia = IA[i]; S6 pa = Z[i];
+    if (l.jtype == 1) {
+      c.U[i] = mul6(IA[i], c.S[i]);
+      double D = dot6(c.S[i], c.U[i]);
+      if (!(D > 0)) return false;
+      c.Dinv[i] = 1.0 / D;
+      u[i] = tau[l.dof] - dot6(c.S[i], Z[i]);
+      for (int r = 0; r < 6; r++)
+        for (int s = 0; s < 6; s++) Ia.m[r][s] -= c.U[i].v[r] * c.U[i].v[s] * c.Dinv[i];
+      S6 Iac = mul6(Ia, cor[i]);
+      for (int t = 0; t < 6; t++) pa.v[t] += Iac.v[t] + c.U[i].v[t] * (u[i] * c.Dinv[i]);
+    }
+    // IA[parent] += X^T Ia X ; Z[parent] += X^T pa
+    const M6& X = c.X[i];
+    M6 T;
+    for (int r = 0; r < 6; r++)
+      for (int s = 0; s < 6; s++) {
+        double acc2 = 0;
+        for (int t = 0; t < 6; t++) acc2 += Ia.m[r][t] * X.m[t][s];
+        T.m[r][s] = acc2;
+      }
+    for (int r = 0; r < 6; r++)
+      for (int s = 0; s < 6; s++) {
+        double acc2 = 0;
+        for (int t = 0; t < 6; t++) acc2 += X.m[t][r] * T.m[t][s];
+        IA[l.parent].m[r][s] += acc2;
+      }
+    S6 zp = tmul6(X, pa);
+    for (int t = 0; t < 6; t++) Z[l.parent].v[t] += zp.v[t];
+  }
+  if (!chol6(IA[0], c.L0)) return false;
+  S6 mz;
+  for (int t = 0; t < 6; t++) mz.v[t] = -Z[0].v[t];
+  a[0] = chol6_solve(c.L0, mz);
+  for (int i = 1; i < n; i++) {
+    const LinkM& l = md.links[i];
+    a[i] = mul6(c.X[i], a[l.parent]);
+    for (int t = 0; t < 6; t++) a[i].v[t] += cor[i].v[t];
+    if (l.jtype == 1) {
+      double qdd = (u[i] - dot6(c.U[i], a[i])) * c.Dinv[i];
+      acc[6 + l.dof] = qdd;
+      for (int t = 0; t < 6; t++) a[i].v[t] += c.S[i].v[t] * qdd;
+    }
+  }
+  // base acceleration back to world; classical linear acceleration = spatial + omega x v
+  V3 wb = ang(v[0]), vb = lin(v[0]);
+  V3 od = mul(k.Rc[0], ang(a[0]));
+  V3 vd = mul(k.Rc[0], lin(a[0]) + cross(wb, vb));
+  acc[0] = od.x; acc[1] = od.y; acc[2] = od.z; acc[3] = vd.x; acc[4] = vd.y; acc[5] = vd.z;
+  return true;
+}
+
+// Response of the generalized velocity to a unit generalized impulse F (torque_w, force_w on the base CoM, joint
+// torques): out = M^-1 F, using the quantities cached by aba() (Bullet: calcAccelerationDeltasMultiDof).
+void aba_delta(const Model& md, const AbaCache& c, const double* F, double* out) {
+  const int n = (int)md.links.size();
+  S6 Z[MAXL], a[MAXL]; double u[MAXL];
+  for (int i = 0; i < n; i++) std::memset(&Z[i], 0, sizeof(S6));
+  Z[0] = s6((-1.0) * tmul(c.Rb, V3{F[0], F[1], F[2]}), (-1.0) * tmul(c.Rb, V3{F[3], F[4], F[5]}));
+  for (int i = n - 1; i >= 1; i--) {
+    const LinkM& l = md.links[i];
+    S6 pa = Z[i];
+    if (l.jtype == 1) {
+      u[i] = F[6 + l.dof] - dot6(c.S[i], Z[i]);
+      for (int t = 0; t < 6; t++) pa.v[t] += c.U[i].v[t] * (u[i] * c.Dinv[i]);
+    }
+    S6 zp = tmul6(c.X[i], pa);
+    for (int t = 0; t < 6; t++) Z[l.parent].v[t] += zp.v[t];
+  }
+  S6 mz;
+  for (int t = 0; t < 6; t++) mz.v[t] = -Z[0].v[t];
+  a[0] = chol6_solve(c.L0, mz);
+  for (int i = 1; i < n; i++) {
+    const LinkM& l = md.links[i];
+    a[i] = mul6(c.X[i], a[l.parent]);
+    if (l.jtype == 1) {
+      double qdd = (u[i] - dot6(c.U[i], a[i])) * c.Dinv[i];
+      out[6 + l.dof] = qdd;
+      for (int t = 0; t < 6; t++) a[i].v[t] += c.S[i].v[t] * qdd;
+    }
+  }
+  V3 od = mul(c.Rb, ang(a[0])), vd = mul(c.Rb, lin(a[0]));
+  out[0] = od.x; out[1] = od.y; out[2] = od.z; out[3] = vd.x; out[4] = vd.y; out[5] = vd.z;
+}
+
+// Jacobian row of "velocity of world point P fixed on link li, along world direction d" w.r.t. (omega_w, v_w, qd)
+void point_jacobian(const Model& md, const Kin& k, int li, V3 P, V3 d, double* J) {
+  for (int t = 0; t < 6 + md.ndof; t++) J[t] = 0;
+  V3 rb = P - k.pc[0];
+  V3 jw = cross(rb, d);
+  J[0] = jw.x; J[1] = jw.y; J[2] = jw.z; J[3] = d.x; J[4] = d.y; J[5] = d.z;
+  for (int i = li; i > 0; i = md.links[i].parent) {
+    const LinkM& l = md.links[i];
+    if (l.jtype != 1) continue;
+    V3 aw = mul(k.Rl[i], l.axis);
+    J[6 + l.dof] = dot(cross(aw, P - k.pl[i]), d);
+  }
+}
+
+// btPlaneSpace1
+void plane_space(V3 n, V3& p, V3& q) {
+  if (std::fabs(n.z) > 0.7071067811865475244008443621048490) {
+    double a = n.y * n.y + n.z * n.z, kk = 1.0 / std::sqrt(a);
+    p = {0, -n.z * kk, n.y * kk};
+    q = {a * kk, -n.x * p.z, n.x * p.y};
+  } else {
+    double a = n.x * n.x + n.y * n.y, kk = 1.0 / std::sqrt(a);
+    p = {-n.y * kk, n.x * kk, 0};
+    q = {-n.z * p.y, n.z * p.x, a * kk};
+  }
+}
+
+struct Row {
+  double J[MAXD], W[MAXD];
+  double rhs, invd, lam, lo, hi;
+};
+
+inline double clampd(double v, double lo, double hi) { return std::max(lo, std::min(v, hi)); }
+
+// One Bullet stepSimulation() with numSubSteps=1 for one robot on the infinite plane z=0.
+// tau: motor torques (12).  Returns false if the dynamics became singular / non-finite.
+bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contact_rows, int64_t* n_limit_rows) {
+  const Model& md = E.model;
+  const llq_config& cf = E.cfg;
+  const int nd = 6 + md.ndof;
+  const double dt = cf.sim_dt;
+  Kin k;
+  kinematics(md, e.pos, e.quat, e.q, k);
+
+  // (a) collision detection on pre-step poses: foot spheres vs plane z = 0
+  struct Contact { int link, sphere; V3 P; double dist, mu; };
+  Contact contacts[8]; int nc = 0;
+  for (size_t s = 0; s < md.spheres.size(); s++) {
+    const SphereM& sp = md.spheres[s];
+    V3 cw = k.pl[sp.link] + mul(k.Rl[sp.link], sp.c);
+    double dist = cw.z - sp.r;
+    if (dist < cf.contact_breaking) {
+      contacts[nc++] = {sp.link, (int)s, V3{cw.x, cw.y, cw.z - sp.r}, dist, cf.ground_friction * sp.mu};
+    } else {
+      e.warm[s] = 0.0;  // manifold point removed
+    }
+  }
+
+  // (b) joint damping (pybullet applyJointDamping) + motor torque, forward dynamics, velocity prediction
+  double gv[MAXD], tt[16], acc[MAXD];
+  for (int t = 0; t < 3; t++) { gv[t] = e.angv[t]; gv[3 + t] = e.linv[t]; }
+  for (int j = 0; j < md.ndof; j++) {
+    gv[6 + j] = e.qd[j];
+    tt[j] = tau[j] - md.links[md.dof_link[j]].jdamp * e.qd[j];
+  }
+  AbaCache c;
+  if (!aba(E, k, gv, tt, nullptr, nullptr, acc, c)) return false;
+  for (int t = 0; t < nd; t++) gv[t] = clampd(gv[t] + acc[t] * dt, -cf.max_coord_vel, cf.max_coord_vel);
+
+  // (c) constraint rows
+  std::vector<Row> lim, nrm, fr;
+  for (int j = 0; j < md.ndof; j++) {
+    const LinkM& l = md.links[md.dof_link[j]];
+    if (!l.haslim) continue;
+    for (int side = 0; side < 2; side++) {
+      double pen = side == 0 ? e.q[j] - l.lower : l.upper - e.q[j];
+      if (pen > 0) continue;                       // btMultiBodyJointLimitConstraint: row only when violated
+      double dir = side == 0 ? 1.0 : -1.0;
+      Row r; std::memset(&r, 0, sizeof(r));
+      r.J[6 + j] = dir;
+      aba_delta(md, c, r.J, r.W);
+      double denom = 0, rel = 0;
+      for (int t = 0; t < nd; t++) { denom += r.J[t] * r.W[t]; rel += r.J[t] * gv[t]; }
+      r.invd = 1.0 / denom;
+      // split-impulse quirk: positional term only while the violation is shallower than 0.04 (m_splitImpulsePenetrationThreshold)
+      double poserr = pen > -0.04 ? -pen * cf.joint_erp / dt : 0.0;
+      r.rhs = (poserr - rel) * r.invd;
+      r.lo = 0; r.hi = cf.max_applied_impulse; r.lam = 0;
+      lim.push_back(r);
+    }
+  }
+  for (int ci = 0; ci < nc; ci++) {
+    const Contact& ct = contacts[ci];
+    V3 nrml = {0, 0, 1}, t1, t2;
+    plane_space(nrml, t1, t2);
+    V3 dirs[3] = {nrml, t1, t2};
+    for (int d = 0; d < 3; d++) {
+      Row r; std::memset(&r, 0, sizeof(r));
+      point_jacobian(md, k, ct.link, ct.P, dirs[d], r.J);
+      aba_delta(md, c, r.J, r.W);
+      double denom = 0, rel = 0;
+      for (int t = 0; t < nd; t++) { denom += r.J[t] * r.W[t]; rel += r.J[t] * gv[t]; }
+      r.invd = 1.0 / denom;
+      if (d == 0) {
+        double pen = ct.dist + cf.linear_slop;
+        double poserr = 0, velerr = -rel;
+        if (pen > 0) velerr -= pen / dt; else poserr = -pen * cf.contact_erp / dt;
+        r.rhs = (poserr + velerr) * r.invd;
+        r.lo = 0; r.hi = 1e10;
+        r.lam = cf.warmstart * e.warm[ct.sphere];
+        nrm.push_back(r);
+      } else {
+        r.rhs = -rel * r.invd;
+        r.lam = 0;
+        fr.push_back(r);
+      }
+    }
+  }
+  *n_contact_rows += (int64_t)nrm.size() * 3;
+  *n_limit_rows += (int64_t)lim.size();
+
+  // (d) projected Gauss-Seidel on delta velocities
+  double dv[MAXD];
+  for (int t = 0; t < nd; t++) dv[t] = 0;
+  for (auto& r : nrm)
+    if (r.lam != 0)
+      for (int t = 0; t < nd; t++) dv[t] += r.W[t] * r.lam;   // warm start
+  auto solve_row = [&](Row& r) {
+    double jd = 0;
+    for (int t = 0; t < nd; t++) jd += r.J[t] * dv[t];
+    double dl = r.rhs - jd * r.invd;
+    double sum = r.lam + dl;
+    if (sum < r.lo) { dl = r.lo - r.lam; r.lam = r.lo; }
+    else if (sum > r.hi) { dl = r.hi - r.lam; r.lam = r.hi; }
+    else r.lam = sum;
+    for (int t = 0; t < nd; t++) dv[t] += r.W[t] * dl;
+  };
+  for (int it = 0; it < cf.solver_iters; it++) {
+    for (auto& r : lim) solve_row(r);
+    for (auto& r : nrm) solve_row(r);
+    for (size_t ci = 0; ci < nrm.size(); ci++) {   // implicit cone friction on the row pair (t1, t2)
+      Row& a = fr[2 * ci]; Row& b = fr[2 * ci + 1];
+      double limit = contacts[ci].mu * nrm[ci].lam;
+      double ja = 0, jb = 0;
+      for (int t = 0; t < nd; t++) { ja += a.J[t] * dv[t]; jb += b.J[t] * dv[t]; }
+      double sa = a.lam + (a.rhs - ja * a.invd), sb = b.lam + (b.rhs - jb * b.invd);
+      double r2 = sa * sa + sb * sb;
+      if (r2 >= limit * limit && r2 > 0) {
+        double sc = limit / std::sqrt(r2);
+        sa *= sc; sb *= sc;
+      }
+      double da = sa - a.lam, db = sb - b.lam;
+      a.lam = sa; b.lam = sb;
+      for (int t = 0; t < nd; t++) dv[t] += a.W[t] * da + b.W[t] * db;
+    }
+  }
+  for (int t = 0; t < nd; t++) gv[t] = clampd(gv[t] + dv[t], -cf.max_coord_vel, cf.max_coord_vel);
+  for (int ci = 0; ci < nc; ci++) e.warm[contacts[ci].sphere] = nrm[ci].lam;
+
+  // (e) integrate (btMultiBody::stepPositionsMultiDof): explicit positions from the new velocities
+  for (int t = 0; t < 3; t++) { e.angv[t] = gv[t]; e.linv[t] = gv[3 + t]; e.pos[t] += gv[3 + t] * dt; }
+  {
+    V3 w = {gv[0], gv[1], gv[2]};
+    double fa = norm(w);
+    V3 ax;
+    if (fa < 0.001) ax = (0.5 * dt - dt * dt * dt * 0.020833333333 * fa * fa) * w;
+    else ax = (std::sin(0.5 * fa * dt) / fa) * w;
+    Q4 dq = {ax.x, ax.y, ax.z, std::cos(fa * dt * 0.5)};
+    Q4 qn = qnormalize(qmul(dq, Q4{e.quat[0], e.quat[1], e.quat[2], e.quat[3]}));
+    e.quat[0] = qn.x; e.quat[1] = qn.y; e.quat[2] = qn.z; e.quat[3] = qn.w;
+  }
+  for (int j = 0; j < md.ndof; j++) { e.qd[j] = gv[6 + j]; e.q[j] += gv[6 + j] * dt; }
+  for (int t = 0; t < nd; t++)
+    if (!std::isfinite(gv[t])) return false;
+  return true;
+}
+
+// ------------------------------------------------------------------ MotionLib restatement (ML:11-172)
+inline const double* frame_ptr(const llq_engine& E, int clip, int f) {
+  return &E.frames[(size_t)(E.clip_off[clip] + f) * LLQ_MOCAP_FRAME];
+}
+// ML:88-166 _get_states_info_by_interpolation -> 37 doubles in LLQ_F_STATE order
+void mocap_state(const llq_engine& E, const double* fc, const double* fn, double frac, double* st) {
+  const double dt = E.frame_dt;
+  for (int i = 0; i < 3; i++) {
+    st[i] = fc[i] + frac * (fn[i] - fc[i]);          // ML:118-124
+    st[7 + i] = (fn[i] - fc[i]) / dt;                // ML:137-140
+  }
+  Q4 qc = qnormalize({fc[3], fc[4], fc[5], fc[6]}), qn = qnormalize({fn[3], fn[4], fn[5], fn[6]});
+  V3 rv = q_rotvec(qmul(qconj(qc), qn));             // scipy Slerp: rotvec of R_c^-1 R_n
+  Q4 qi = qmul(qc, rotvec_q(frac * rv));             // ML:127-134
+  st[3] = qi.x; st[4] = qi.y; st[5] = qi.z; st[6] = qi.w;
+  V3 rw = q_rotvec(qmul(qn, qconj(qc)));             // ML:143-149
+  double angle = norm(rw);
+  V3 axis = (1.0 / (angle + 1e-8)) * rw;
+  st[10] = axis.x * angle / dt; st[11] = axis.y * angle / dt; st[12] = axis.z * angle / dt;
+  for (int j = 0; j < 12; j++) {                     // ML:152-160
+    st[13 + j] = fc[7 + j] + frac * (fn[7 + j] - fc[7 + j]);
+    st[25 + j] = (fn[7 + j] - fc[7 + j]) / dt;
+  }
+}
+const double kTimeFuture[4] = {1. / 30., 1. / 15., 1. / 3., 1.};  // ML:44
+
+void foot_positions(const llq_engine& E, const double* st, double* out12) {
+  Kin k;
+  kinematics(E.model, st, st + 3, st + 13, k);
+  for (size_t s = 0; s < E.model.spheres.size() && s < 4; s++) {
+    int li = E.model.spheres[s].link;
+    out12[3 * s] = k.pc[li].x; out12[3 * s + 1] = k.pc[li].y; out12[3 * s + 2] = k.pc[li].z;  // getLinkState()[0]
+  }
+}
+
+inline void pack_state(const Env& e, double* st) {
+  for (int i = 0; i < 3; i++) { st[i] = e.pos[i]; st[7 + i] = e.linv[i]; st[10 + i] = e.angv[i]; }
+  for (int i = 0; i < 4; i++) st[3 + i] = e.quat[i];
+  for (int j = 0; j < 12; j++) { st[13 + j] = e.q[j]; st[25 + j] = e.qd[j]; }
+}
+inline void unpack_state(Env& e, const double* st) {
+  for (int i = 0; i < 3; i++) { e.pos[i] = st[i]; e.linv[i] = st[7 + i]; e.angv[i] = st[10 + i]; }
+  for (int i = 0; i < 4; i++) e.quat[i] = st[3 + i];
+  for (int j = 0; j < 12; j++) { e.q[j] = st[13 + j]; e.qd[j] = st[25 + j]; }
+}
+
+// PLE:247-260 with the shipped prop_type order
+void make_prop(const double* st, double* prop) {
+  M3 R = qmat(qnormalize({st[3], st[4], st[5], st[6]}));
+  for (int j = 0; j < 12; j++) { prop[j] = st[13 + j]; prop[12 + j] = st[25 + j]; }
+  V3 wl = tmul(R, V3{st[10], st[11], st[12]}), vl = tmul(R, V3{st[7], st[8], st[9]});
+  prop[24] = wl.x; prop[25] = wl.y; prop[26] = wl.z;
+  prop[27] = vl.x; prop[28] = vl.y; prop[29] = vl.z;
+  prop[30] = R.m[2][0]; prop[31] = R.m[2][1]; prop[32] = R.m[2][2];
+}
+
+// PLE:299-317 + ML:75-86
+void make_future(const llq_engine& E, const Env& e, const double* st, double* fut72) {
+  Q4 qb = qnormalize({st[3], st[4], st[5], st[6]});
+  M3 Rb = qmat(qb);
+  for (int i = 0; i < 4; i++) {
+    double t = E.frame_dt * e.frame_frac + kTimeFuture[i];           // ML:80
+    int fid = (int)std::floor(t / E.frame_dt);                        // ML:81
+    double ffrac = t / E.frame_dt - fid;                              // ML:82
+    double fs[LLQ_STATE_DIM];
+    mocap_state(E, frame_ptr(E, e.clip, e.frame_id + fid), frame_ptr(E, e.clip, e.frame_id + fid + 1), ffrac, fs);
+    Q4 qi = qnormalize({fs[3], fs[4], fs[5], fs[6]});
+    Q4 qd = qmul(qconj(qb), qi);                                      // PLE:307
+    V3 rv = q_rotvec(qnormalize(qd));
+    double angle = norm(rv);
+    V3 axis = (1.0 / (angle + 1e-8)) * rv;                            // PLE:19-23
+    V3 dp = tmul(Rb, V3{fs[0] - st[0], fs[1] - st[1], fs[2] - st[2]}); // PLE:310-311
+    double* o = fut72 + 18 * i;
+    o[0] = dp.x; o[1] = dp.y; o[2] = dp.z;
+    o[3] = axis.x * angle; o[4] = axis.y * angle; o[5] = axis.z * angle;
+    for (int j = 0; j < 12; j++) o[6 + j] = fs[13 + j];
+  }
+}
+
+void write_obs(const llq_engine& E, Env& e, const double* st) {
+  double fut[72];
+  make_future(E, e, st, fut);
+  int o = 0;
+  for (int h = 0; h < 3; h++)
+    for (int t = 0; t < LLQ_PROP_DIM; t++) e.obs[o++] = (float)e.prop_hist[h][t];
+  for (int h = 0; h < 3; h++)
+    for (int t = 0; t < LLQ_ACTION_DIM; t++) e.obs[o++] = (float)e.act_hist[h][t];
+  for (int t = 0; t < 72; t++) e.obs[o++] = (float)fut[t];
+}
+
+void motion_set_time(const llq_engine& E, Env& e, double t) {  // ML:65-67
+  e.frame_id = (int)std::floor(t / E.frame_dt);
+  e.frame_frac = (t - e.frame_id * E.frame_dt) / E.frame_dt;
+}
+
+// PLE:150-171 with (clip, sampled_time) given
+void reset_env(llq_engine& E, Env& e, int clip, double sampled_time) {
+  e.clip = clip;
+  e.time = sampled_time;
+  motion_set_time(E, e, sampled_time);                                   // ML:52-53 (same arithmetic as ML:65-67)
+  mocap_state(E, frame_ptr(E, clip, e.frame_id), frame_ptr(E, clip, e.frame_id + 1), e.frame_frac, e.kin);
+  unpack_state(e, e.kin);                                                // PLE:162-163
+  e.reward_sum = 0; e.episode_steps = 0;
+  for (int s = 0; s < 8; s++) e.warm[s] = 0;
+  double prop[LLQ_PROP_DIM];
+  make_prop(e.kin, prop);
+  for (int h = 0; h < 3; h++) {                                          // PLE:282-290
+    std::memcpy(e.prop_hist[h], prop, sizeof(prop));
+    for (int t = 0; t < 12; t++) e.act_hist[h][t] = 0;
+  }
+  foot_positions(E, e.kin, e.foot_pos);
+  write_obs(E, e, e.kin);
+}
+
+void sample_reset(llq_engine& E, Env& e, int64_t gid) {
+  double u1, u2;
+  reset_uniforms(E.cfg.seed, gid, e.episode, &u1, &u2);
+  e.episode++;
+  // np.random.choice(p): cdf = cumsum(p); cdf /= cdf[-1]; searchsorted(cdf, u, side='right')   (ML:60)
+  double tot = 0;
+  for (int c = 0; c < E.n_clips; c++) tot += E.sample_prob[c];
+  double acc = 0; int clip = E.n_clips - 1;
+  for (int c = 0; c < E.n_clips; c++) {
+    acc += E.sample_prob[c];
+    if (acc / tot > u1) { clip = c; break; }
+  }
+  int nf = E.clip_off[clip + 1] - E.clip_off[clip];
+  double duration = E.frame_dt * (nf - E.margin - 1);                    // ML:50
+  reset_env(E, e, clip, u2 * duration);                                  // ML:51
+}
+
+// PLE:195-245 for one env; returns reward, sets *done
+double step_env(llq_engine& E, Env& e, const float* action, bool* done, int64_t* ncr, int64_t* nlr) {
+  const llq_config& cf = E.cfg;
+  e.episode_steps += 1;
+  double act[12], tgt[12], tau[12];
+  for (int j = 0; j < 12; j++) { act[j] = (double)action[j]; tgt[j] = e.q[j] + act[j]; }   // PLE:198-200
+  bool ok = true;
+  for (int s = 0; s < cf.substeps; s++) {
+    for (int j = 0; j < 12; j++) {                                                          // LR:126-141
+      double tg = clampd(tgt[j], -3.0, 3.0);
+      double t = cf.kp * (tg - e.q[j]) + cf.kd * (0.0 - e.qd[j]);
+      tau[j] = clampd(t, -cf.max_tau, cf.max_tau);
+    }
+    if (ok) ok = physics_substep(E, e, tau, ncr, nlr);                                       // PLE:206
+    motion_set_time(E, e, e.time);                                                           // PLE:208
+    e.time += cf.sim_dt;                                                                     // PLE:210
+  }
+  // PLE:217-222
+  mocap_state(E, frame_ptr(E, e.clip, e.frame_id), frame_ptr(E, e.clip, e.frame_id + 1), e.frame_frac, e.kin);
+  double st[LLQ_STATE_DIM];
+  pack_state(e, st);
+  // PLE:276-297 history update
+  double prop[LLQ_PROP_DIM];
+  make_prop(st, prop);
+  std::memmove(e.prop_hist[0], e.prop_hist[1], 2 * sizeof(e.prop_hist[0]));
+  std::memcpy(e.prop_hist[2], prop, sizeof(prop));
+  std::memmove(e.act_hist[0], e.act_hist[1], 2 * sizeof(e.act_hist[0]));
+  std::memcpy(e.act_hist[2], act, sizeof(act));
+  write_obs(E, e, st);
+  // reward PLE:350-426
+  double sw = cf.w_joint_pos + cf.w_joint_vel + cf.w_end_effector + cf.w_root_pose + cf.w_root_vel;
+  double djp = 0, djv = 0;
+  for (int j = 0; j < 12; j++) {
+    double a = st[13 + j] - e.kin[13 + j], b = st[25 + j] - e.kin[25 + j];
+    djp += a * a; djv += b * b;
+  }
+  double fd[12], fk[12], dee = 0;
+  foot_positions(E, st, fd);
+  foot_positions(E, e.kin, fk);
+  for (int t = 0; t < 12; t++) { dee += (fd[t] - fk[t]) * (fd[t] - fk[t]); e.foot_pos[t] = fd[t]; }
+  double dp = 0, dvl = 0, dva = 0;
+  for (int t = 0; t < 3; t++) {
+    dp += (st[t] - e.kin[t]) * (st[t] - e.kin[t]);
+    dvl += (st[7 + t] - e.kin[7 + t]) * (st[7 + t] - e.kin[7 + t]);
+    dva += (st[10 + t] - e.kin[10 + t]) * (st[10 + t] - e.kin[10 + t]);
+  }
+  Q4 q1 = qnormalize({st[3], st[4], st[5], st[6]}), q2 = qnormalize({e.kin[3], e.kin[4], e.kin[5], e.kin[6]});
+  double angle = norm(q_rotvec(qnormalize(qmul(q2, qconj(q1)))));                           // PLE:410-411
+  double r = (cf.w_joint_pos / sw) * std::exp(-1.0 * djp) + (cf.w_joint_vel / sw) * std::exp(-0.1 * djv) +
+             (cf.w_end_effector / sw) * std::exp(-40.0 * dee) +
+             (cf.w_root_pose / sw) * std::exp(-20.0 * dp - 10.0 * angle * angle) +
+             (cf.w_root_vel / sw) * std::exp(-2.0 * dvl - 0.2 * dva);
+  e.reward_sum += r;
+  // termination PLE:337-348
+  M3 R = qmat(q1);
+  double left_z = R.m[0][2] * R.m[1][0] - R.m[1][2] * R.m[0][0];                             // LR:171-172
+  bool fall = left_z > std::sin(45.0 * M_PI / 180.0) || left_z < std::sin(-45.0 * M_PI / 180.0) ||
+              R.m[2][2] < std::cos(60.0 * M_PI / 180.0);                                     // LR:173-178
+  int nf = E.clip_off[e.clip + 1] - E.clip_off[e.clip];
+  bool ended = e.frame_id >= nf - E.margin - 1;                                              // ML:168-172
+  bool diff = std::fabs(angle) > 1.0 || dp > 1.0;                                            // PLE:319-335
+  *done = fall || ended || diff || !ok;
+  if (!ok || !std::isfinite(r)) { r = 0.0; *done = true; }
+  return r;
+}
+
+void update_sampling(llq_engine& E) {  // PLE:239-240
+  double tot = 0;
+  for (int c = 0; c < E.n_clips; c++) {
+    E.sample_prob[c] = std::pow(1.0 - E.avg_reward[c], E.cfg.prioritized_sample_factor);
+    tot += E.sample_prob[c];
+  }
+  for (int c = 0; c < E.n_clips; c++) E.sample_prob[c] /= tot;
+}
+
+int check_ready(llq_handle h, bool need_reset) {
+  if (!h) return fail(LLQ_EINVAL, "null handle");
+  if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
+  if (!h->has_mocap) return fail(LLQ_ESTATE, "llq_load_mocap has not been called");
+  if (need_reset && !h->was_reset) return fail(LLQ_ESTATE, "llq_reset has not been called");
+  return LLQ_OK;
+}
+
+}  // namespace
+
+// ====================================================================== C ABI
+extern "C" {
+
+int llq_abi_version(int* is_cuda) {
+  if (is_cuda) *is_cuda = 0;
+  return LLQ_ABI_VERSION;
+}
+
+int llq_default_config(llq_config* c) {
+  if (!c) return fail(LLQ_EINVAL, "null config");
+  std::memset(c, 0, sizeof(*c));
+  c->struct_size = (int32_t)sizeof(llq_config);
+  c->n_envs = 1; c->device = 0; c->substeps = 10; c->solver_iters = 10; c->auto_reset = 0; c->num_threads = 0;
+  c->global_env_offset = 0; c->seed = 0;
+  c->sim_dt = 1.0 / 500.0; c->policy_dt = 1.0 / 50.0;
+  c->kp = 50.0; c->kd = 0.5; c->max_tau = 18.0;
+  c->gravity_z = -9.80665; c->ground_friction = 0.9; c->foot_friction = 0.5;
+  c->contact_erp = 0.08; c->joint_erp = 0.2; c->linear_slop = 1e-5; c->warmstart = 0.1;
+  c->contact_breaking = 0.02 * 0.025;
+  c->lin_damping = 0.04; c->ang_damping = 0.04; c->max_coord_vel = 100.0; c->max_applied_impulse = 1000.0;
+  c->w_joint_pos = 0.3; c->w_joint_vel = 0.05; c->w_end_effector = 0.1; c->w_root_pose = 0.5; c->w_root_vel = 0.05;
+  c->prioritized_sample_factor = 3.0;
+  return LLQ_OK;
+}
+
+int llq_create(const llq_config* cfg, llq_handle* out) {
+  if (!cfg || !out) return fail(LLQ_EINVAL, "null argument");
+  if (cfg->struct_size != (int32_t)sizeof(llq_config)) return fail(LLQ_EINVAL, "llq_config size mismatch (ABI)");
+  if (cfg->n_envs <= 0) return fail(LLQ_EINVAL, "n_envs must be positive");
+  if (cfg->substeps <= 0 || cfg->solver_iters < 0 || !(cfg->sim_dt > 0)) return fail(LLQ_EINVAL, "bad step configuration");
+  llq_engine* e = new (std::nothrow) llq_engine();
+  if (!e) return fail(LLQ_ENOMEM, "out of memory");
+  e->cfg = *cfg;
+  e->envs.resize(cfg->n_envs);
+  for (auto& en : e->envs) std::memset(&en, 0, sizeof(Env));
+  *out = e;
+  return LLQ_OK;
+}
+
+int llq_destroy(llq_handle h) {
+  delete h;
+  return LLQ_OK;
+}
+
+int llq_load_model(llq_handle h, const double* b, int64_t n) {
+  if (!h || !b) return fail(LLQ_EINVAL, "null argument");
+  if (n < LLQ_HDR || (int64_t)b[LLQ_H_MAGIC] != LLQ_MODEL_MAGIC || (int64_t)b[LLQ_H_TOTAL] != n)
+    return fail(LLQ_EINVAL, "bad model blob (magic/size)");
+  Model md;
+  int nl = (int)b[LLQ_H_NLINKS];
+  if (nl < 1 || nl > MAXL) return fail(LLQ_EINVAL, "unsupported link count");
+  md.ndof = (int)b[LLQ_H_NDOF];
+  if (md.ndof != 12) return fail(LLQ_EUNSUPPORTED, "oracle env logic expects 12 actuated joints");
+  md.dof_link.assign(md.ndof, -1);
+  const double* g = b + (int64_t)b[LLQ_H_OFF_GENERIC];
+  for (int i = 0; i < nl; i++, g += LLQ_GL) {
+    LinkM l;
+    l.parent = (int)g[LLQ_G_PARENT]; l.jtype = (int)g[LLQ_G_JTYPE]; l.dof = (int)g[LLQ_G_DOF];
+    l.jxyz = {g[LLQ_G_JXYZ], g[LLQ_G_JXYZ + 1], g[LLQ_G_JXYZ + 2]};
+    l.jrot = from9(g + LLQ_G_JROT);
+    l.axis = {g[LLQ_G_AXIS], g[LLQ_G_AXIS + 1], g[LLQ_G_AXIS + 2]};
+    l.mass = g[LLQ_G_MASS];
+    l.com = {g[LLQ_G_COM], g[LLQ_G_COM + 1], g[LLQ_G_COM + 2]};
+    l.Rin = from9(g + LLQ_G_RIN);
+    l.idiag = {g[LLQ_G_IDIAG], g[LLQ_G_IDIAG + 1], g[LLQ_G_IDIAG + 2]};
+    l.lower = g[LLQ_G_LOWER]; l.upper = g[LLQ_G_UPPER]; l.jdamp = g[LLQ_G_JDAMP]; l.haslim = g[LLQ_G_HASLIM] != 0;
+    if (i > 0 && (l.parent < 0 || l.parent >= i)) return fail(LLQ_EINVAL, "links must be parent-first");
+    if (l.jtype == 1) {
+      if (l.dof < 0 || l.dof >= md.ndof) return fail(LLQ_EINVAL, "bad dof index");
+      md.dof_link[l.dof] = i;
+    }
+    md.links.push_back(l);
+  }
+  const double* s = b + (int64_t)b[LLQ_H_OFF_SPHERES];
+  int ns = (int)b[LLQ_H_NSPHERES];
+  if (ns > 8) return fail(LLQ_EINVAL, "too many contact spheres");
+  for (int i = 0; i < ns; i++, s += LLQ_SPH) md.spheres.push_back({(int)s[0], V3{s[1], s[2], s[3]}, s[4], h->cfg.foot_friction});
+  h->model = md;
+  h->has_model = true;
+  return LLQ_OK;
+}
+
+int llq_load_mocap(llq_handle h, const double* frames, const int32_t* off, int32_t n_clips, double frame_dt) {
+  if (!h || !frames || !off || n_clips <= 0 || !(frame_dt > 0)) return fail(LLQ_EINVAL, "bad mocap arguments");
+  h->frame_dt = frame_dt;
+  h->frame_rate = (int)(1.0 / frame_dt);                                                           // ML:34
+  h->margin = (int)std::ceil(h->cfg.policy_dt / frame_dt) + h->frame_rate + 2;                     // ML:35
+  h->n_clips = n_clips;
+  h->clip_off.assign(off, off + n_clips + 1);
+  for (int c = 0; c < n_clips; c++)
+    if (off[c + 1] - off[c] < h->margin + 3) return fail(LLQ_EINVAL, "mocap clip shorter than margin + 3 frames");
+  h->frames.assign(frames, frames + (size_t)off[n_clips] * LLQ_MOCAP_FRAME);
+  for (int p = 0; p < 128; p++)   // replicated tail frames: a stale cursor never reads past the table
+    for (int t = 0; t < LLQ_MOCAP_FRAME; t++) h->frames.push_back(frames[((size_t)off[n_clips] - 1) * LLQ_MOCAP_FRAME + t]);
+  h->max_steps.resize(n_clips);
+  for (int c = 0; c < n_clips; c++) h->max_steps[c] = (off[c + 1] - off[c] - h->margin) * frame_dt / h->cfg.policy_dt;  // ML:45
+  h->sample_prob.assign(n_clips, 1.0 / n_clips);                                                   // ML:46
+  h->avg_reward.assign(n_clips, 0.0);                                                              // PLE:133
+  h->has_mocap = true;
+  return LLQ_OK;
+}
+
+int llq_reset(llq_handle h, const uint8_t* mask, float* obs) {
+  int rc = check_ready(h, false);
+  if (rc) return rc;
+  for (int i = 0; i < h->cfg.n_envs; i++) {
+    if (mask && !mask[i]) continue;
+    sample_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
+  }
+  h->was_reset = true;
+  if (obs)
+    for (int i = 0; i < h->cfg.n_envs; i++) std::memcpy(obs + (size_t)i * LLQ_OBS_DIM, h->envs[i].obs, sizeof(float) * LLQ_OBS_DIM);
+  return LLQ_OK;
+}
+
+int llq_reset_to(llq_handle h, const uint8_t* mask, const int32_t* clip, const double* time, float* obs) {
+  int rc = check_ready(h, false);
+  if (rc) return rc;
+  if (!clip || !time) return fail(LLQ_EINVAL, "null clip/time");
+  for (int i = 0; i < h->cfg.n_envs; i++) {
+    if (mask && !mask[i]) continue;
+    if (clip[i] < 0 || clip[i] >= h->n_clips) return fail(LLQ_EINVAL, "clip id out of range");
+    int nf = h->clip_off[clip[i] + 1] - h->clip_off[clip[i]];
+    if (!(time[i] >= 0) || time[i] >= h->frame_dt * (nf - h->margin - 1)) return fail(LLQ_EINVAL, "reset time outside clip");
+    reset_env(*h, h->envs[i], clip[i], time[i]);
+  }
+  h->was_reset = true;
+  if (obs)
+    for (int i = 0; i < h->cfg.n_envs; i++) std::memcpy(obs + (size_t)i * LLQ_OBS_DIM, h->envs[i].obs, sizeof(float) * LLQ_OBS_DIM);
+  return LLQ_OK;
+}
+
+int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, float* reward, uint8_t* done, int io_mode,
+                void* stream) {
+  (void)stream;
+  int rc = check_ready(h, true);
+  if (rc) return rc;
+  if (!actions) return fail(LLQ_EINVAL, "null actions");
+  if (io_mode != LLQ_IO_HOST) return fail(LLQ_EUNSUPPORTED, "CPU oracle only takes host pointers");
+  if (obs && obs_ld < LLQ_OBS_DIM) return fail(LLQ_EINVAL, "obs_ld < 207");
+  const int n = h->cfg.n_envs;
+  std::vector<double> rew(n); std::vector<uint8_t> dn(n);
+  int64_t ncr = 0, nlr = 0;
+#ifdef _OPENMP
+  int nt = h->cfg.num_threads > 0 ? h->cfg.num_threads : omp_get_max_threads();
+#pragma omp parallel for schedule(dynamic, 4) num_threads(nt) reduction(+ : ncr, nlr)
+#endif
+  for (int i = 0; i < n; i++) {
+    bool d = false;
+    rew[i] = step_env(*h, h->envs[i], actions + (size_t)i * LLQ_ACTION_DIM, &d, &ncr, &nlr);
+    dn[i] = d ? 1 : 0;
+  }
+  // prioritized-sampling bookkeeping (PLE:235-240).  Batched rule: envs are applied in index order, so the
+  // highest finished env index owning a clip wins that clip's slot -- same rule as the CUDA engine.
+  bool any = false;
+  for (int i = 0; i < n; i++)
+    if (dn[i]) {
+      Env& e = h->envs[i];
+      h->avg_reward[e.clip] = e.reward_sum / h->max_steps[e.clip];
+      any = true;
+      h->counters[1]++;
+    }
+  if (any) update_sampling(*h);
+  for (int i = 0; i < n; i++) {
+    if (reward) reward[i] = (float)rew[i];
+    if (done) done[i] = dn[i];
+  }
+  if (h->cfg.auto_reset)
+    for (int i = 0; i < n; i++)
+      if (dn[i]) sample_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
+  if (obs)
+    for (int i = 0; i < n; i++) std::memcpy(obs + (size_t)i * obs_ld, h->envs[i].obs, sizeof(float) * LLQ_OBS_DIM);
+  h->counters[0] += n; h->counters[2] += ncr; h->counters[3] += nlr;
+  return LLQ_OK;
+}
+
+int llq_step(llq_handle h, const float* actions, float* obs, float* reward, uint8_t* done) {
+  return llq_step_ex(h, actions, obs, LLQ_OBS_DIM, reward, done, LLQ_IO_HOST, nullptr);
+}
+
+int llq_get_field(llq_handle h, int field, void* dst) {
+  if (!h || !dst) return fail(LLQ_EINVAL, "null argument");
+  const int n = h->cfg.n_envs;
+  for (int i = 0; i < n; i++) {
+    const Env& e = h->envs[i];
+    switch (field) {
+      case LLQ_F_STATE: { double st[LLQ_STATE_DIM]; pack_state(e, st); for (int t = 0; t < LLQ_STATE_DIM; t++) ((float*)dst)[(size_t)i * LLQ_STATE_DIM + t] = (float)st[t]; break; }
+      case LLQ_F_KIN_STATE: for (int t = 0; t < LLQ_STATE_DIM; t++) ((float*)dst)[(size_t)i * LLQ_STATE_DIM + t] = (float)e.kin[t]; break;
+      case LLQ_F_CLIP: ((int32_t*)dst)[i] = e.clip; break;
+      case LLQ_F_TIME: ((double*)dst)[i] = e.time; break;
+      case LLQ_F_REWARD_SUM: ((float*)dst)[i] = (float)e.reward_sum; break;
+      case LLQ_F_EPISODE_STEPS: ((int32_t*)dst)[i] = e.episode_steps; break;
+      case LLQ_F_WARMSTART: for (int t = 0; t < 4; t++) ((float*)dst)[(size_t)i * 4 + t] = (float)e.warm[t]; break;
+      case LLQ_F_OBS: std::memcpy((float*)dst + (size_t)i * LLQ_OBS_DIM, e.obs, sizeof(float) * LLQ_OBS_DIM); break;
+      case LLQ_F_EPISODE_ID: ((int64_t*)dst)[i] = e.episode; break;
+      case LLQ_F_FOOT_POS: for (int t = 0; t < 12; t++) ((float*)dst)[(size_t)i * 12 + t] = (float)e.foot_pos[t]; break;
+      case LLQ_F_SAMPLE_PROB: case LLQ_F_AVG_REWARD: break;
+      default: return fail(LLQ_EINVAL, "unknown field");
+    }
+  }
+  if (field == LLQ_F_SAMPLE_PROB || field == LLQ_F_AVG_REWARD) {
+    if (!h->has_mocap) return fail(LLQ_ESTATE, "no mocap loaded");
+    const std::vector<double>& v = field == LLQ_F_SAMPLE_PROB ? h->sample_prob : h->avg_reward;
+    std::memcpy(dst, v.data(), sizeof(double) * v.size());
+  }
+  return LLQ_OK;
+}
+
+int llq_set_field(llq_handle h, int field, const void* src) {
+  if (!h || !src) return fail(LLQ_EINVAL, "null argument");
+  const int n = h->cfg.n_envs;
+  if (field == LLQ_F_SAMPLE_PROB || field == LLQ_F_AVG_REWARD) {
+    if (!h->has_mocap) return fail(LLQ_ESTATE, "no mocap loaded");
+    std::vector<double>& v = field == LLQ_F_SAMPLE_PROB ? h->sample_prob : h->avg_reward;
+    std::memcpy(v.data(), src, sizeof(double) * v.size());
+    return LLQ_OK;
+  }
+  for (int i = 0; i < n; i++) {
+    Env& e = h->envs[i];
+    switch (field) {
+      case LLQ_F_STATE: { double st[LLQ_STATE_DIM]; for (int t = 0; t < LLQ_STATE_DIM; t++) st[t] = ((const float*)src)[(size_t)i * LLQ_STATE_DIM + t]; unpack_state(e, st); break; }
+      case LLQ_F_CLIP: e.clip = ((const int32_t*)src)[i]; if (e.clip < 0 || e.clip >= h->n_clips) return fail(LLQ_EINVAL, "clip id out of range"); break;
+      case LLQ_F_TIME: e.time = ((const double*)src)[i]; if (h->has_mocap) motion_set_time(*h, e, e.time); break;
+      case LLQ_F_REWARD_SUM: e.reward_sum = ((const float*)src)[i]; break;
+      case LLQ_F_EPISODE_STEPS: e.episode_steps = ((const int32_t*)src)[i]; break;
+      case LLQ_F_WARMSTART: for (int t = 0; t < 4; t++) e.warm[t] = ((const float*)src)[(size_t)i * 4 + t]; break;
+      case LLQ_F_EPISODE_ID: e.episode = ((const int64_t*)src)[i]; break;
+      case LLQ_F_OBS: {
+        const float* o = (const float*)src + (size_t)i * LLQ_OBS_DIM;
+        std::memcpy(e.obs, o, sizeof(float) * LLQ_OBS_DIM);
+        for (int hh = 0; hh < 3; hh++) {
+          for (int t = 0; t < LLQ_PROP_DIM; t++) e.prop_hist[hh][t] = o[hh * LLQ_PROP_DIM + t];
+          for (int t = 0; t < LLQ_ACTION_DIM; t++) e.act_hist[hh][t] = o[3 * LLQ_PROP_DIM + hh * LLQ_ACTION_DIM + t];
+        }
+        break;
+      }
+      default: return fail(LLQ_EINVAL, "field is not settable");
+    }
+  }
+  return LLQ_OK;
+}
+
+int llq_get_counters(llq_handle h, int64_t* out, int32_t n) {
+  if (!h || !out || n < 0 || n > 8) return fail(LLQ_EINVAL, "bad arguments");
+  for (int i = 0; i < n; i++) out[i] = h->counters[i];
+  return LLQ_OK;
+}
+
+int llq_sync(llq_handle h) { return h ? LLQ_OK : fail(LLQ_EINVAL, "null handle"); }
+
+const char* llq_last_error(void) { return g_err.c_str(); }
+
+}  // extern "C"
