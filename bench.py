@@ -1,0 +1,317 @@
+#!/usr/bin/env python
+"""bench.py -- env-steps/sec of the batched PMC mocap-tracking rollout (BASELINE.json configs[1]).
+
+One "step" = one policy step (10 physics sub-steps + mocap + observation + reward + termination + auto-reset)
+of every environment of the batch.  Contract: see the task statement / DESIGN.md 7.
+
+    python bench.py --gpus 1 --steps 512 --warmup 32            # our CUDA engine
+    python bench.py --impl reference --steps 20 --warmup 3      # CPU arm (oracle port)
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29500 \
+        bench.py --gpus 8 ...                                    # env shards, one process per GPU
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+ALGO_BYTES_PER_ENV_STEP = 1676          # 157 words read + 262 words written, fp32
+MU_A = np.array([.0124, -.011, -.0793, -.0125, -.0108, -.0806, .0402, -.0505, -.1956, -.0433, -.0515, -.2156], np.float32)
+SIGMA_A = np.array([.0853, .1525, .1747, .0847, .1503, .1766, .1025, .2023, .3701, .1021, .2035, .426], np.float32)
+TRAJ_WIDTH = 223                        # obs 207 | action 12 | reward | done | neglogp | value  
+UNROLL = 128                            # example_pmc_train.sh:145
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=512)
+    ap.add_argument("--warmup", type=int, default=32)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--envs", type=int, default=4096, help="environments per GPU (BASELINE configs[1]: 4096)")
+    ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL trajectory gather to rank 0")
+    ap.add_argument("--block", type=int, default=0, help="CUDA block size override (32/64/128)")
+    ap.add_argument("--cpu-envs", type=int, default=256, help="CPU arm: environments per step (bounded sample)")
+    return ap.parse_args()
+
+
+def synthetic_inputs(n_clips=66):
+    from lifelike_agility_and_play_b200.model.compile_model import load_model_blob
+    from lifelike_agility_and_play_b200.mocap import synthetic_mocap
+    return load_model_blob(), synthetic_mocap(n_clips, seed=0)
+
+
+def action_pool_np(n, count, seed):
+    rng = np.random.default_rng(seed)
+    a = MU_A + SIGMA_A * rng.standard_normal((count, n, 12)).astype(np.float32)
+    return np.clip(a, -1.0, 1.0).astype(np.float32)
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.rows, self._stop_evt, self.proc = index, [], threading.Event(), None
+
+    def run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits",
+                                          "-lms", "100"], stdout=subprocess.PIPE, text=True)
+            for line in self.proc.stdout:
+                if self._stop_evt.is_set():
+                    break
+                self.rows.append([c.strip() for c in line.split(",")])
+        except Exception:
+            pass
+
+    def stop(self):
+        self._stop_evt.set()
+        if self.proc:
+            self.proc.terminate()
+
+    def summary(self):
+        sm, mx, reasons = [], 0, set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for r in self.rows:
+            try:
+                sm.append(float(r[0])); mx = max(mx, float(r[1]))
+                for nme, v in zip(names, r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(nme)
+            except Exception:
+                continue
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx or None, "reasons": sorted(reasons),
+                "samples": len(sm)}
+
+
+def time_cpu_arm(n_envs, steps, warmup, threads=0):
+    """Oracle port of the reference step on the host cores (kind 'port': the reference itself is Python over the
+    pybullet wheel, which is not installable here -- DESIGN.md 6)."""
+    from oracle import oracle
+    blob, mocap = synthetic_inputs()
+    eng = oracle.make_engine(n_envs, blob, mocap, seed=1234, auto_reset=1, num_threads=threads)
+    eng.reset()
+    pool = action_pool_np(n_envs, 8, 5678)
+    for i in range(warmup):
+        eng.step(pool[i % 8])
+    t0 = time.perf_counter()
+    for i in range(steps):
+        eng.step(pool[i % 8])
+    dt = time.perf_counter() - t0
+    cores = threads if threads > 0 else (os.cpu_count() or 1)
+    return n_envs * steps / dt, dt, cores
+
+
+def run_reference(args, rank):
+    if rank != 0:
+        return
+    n = args.cpu_envs
+    val, dt, cores = time_cpu_arm(n, args.steps, args.warmup)
+    sample = "%d envs x %d steps of the 4096-env workload, oracle/libllq_cpu.so, OpenMP over envs" % (n, args.steps)
+    line = {
+        "impl": "reference", "metric": "env-steps/sec PMC mocap-tracking", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": "4096-env batched PMC mocap-tracking, flat ground (BASELINE configs[1]); CPU arm steps a %d-env sample" % n,
+                   "envs_per_step": n},
+        "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+def main():
+    args = parse()
+    rank = int(os.environ.get("RANK", 0))
+    local_rank = int(os.environ.get("LOCAL_RANK", 0))
+    world = int(os.environ.get("WORLD_SIZE", 1))
+    if args.impl == "reference":
+        return run_reference(args, rank)
+
+    import torch
+    import torch.distributed as dist
+    from lifelike_agility_and_play_b200 import _capi as capi
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    n = args.envs
+    blob, mocap = synthetic_inputs()
+    eng = capi.VecEngine(capi.load_cuda_library(), n, blob, mocap, device=local_rank, seed=1234, auto_reset=1,
+                         global_env_offset=rank * n)
+    if args.block:
+        eng.set_option("block", args.block)
+    eng.reset()
+
+    POOL = 16
+    pool = torch.from_numpy(action_pool_np(n, POOL, 5678 + rank)).to(dev)
+    do_gather = world > 1 and not args.no_gather
+    slab = torch.zeros((UNROLL, n, TRAJ_WIDTH), device=dev, dtype=torch.float32)     # [T, N_local, 223] send slab
+    reward = torch.zeros((n,), device=dev, dtype=torch.float32)
+    done = torch.zeros((n,), device=dev, dtype=torch.uint8)
+    recv = None
+    if do_gather and rank == 0:
+        recv = [torch.empty_like(slab) for _ in range(world)]
+    flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)          # > 126 MB L2
+    stream = torch.cuda.current_stream().cuda_stream
+
+    def one_step(i):
+        t = i % UNROLL
+        row = slab[t]
+        # the fused kernel writes the observation straight into the trajectory slab (row stride 223 floats)
+        eng.step_device(pool[i % POOL].data_ptr(), row.data_ptr(), reward.data_ptr(), done.data_ptr(), obs_ld=TRAJ_WIDTH, stream=stream)
+        row[:, 207:219] = pool[i % POOL]
+        row[:, 219] = reward
+        row[:, 220] = done
+
+    def gather():
+        dist.gather(slab, recv, dst=0)
+
+    for i in range(args.warmup):
+        one_step(i)
+    if do_gather:
+        gather()
+    torch.cuda.synchronize()
+
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    time.sleep(0.3)
+    c0 = eng.counters()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    ev0 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    ev1 = [torch.cuda.Event(enable_timing=True) for _ in range(args.steps)]
+    gev = []
+    wall0 = time.perf_counter()
+    for i in range(args.steps):
+        flush.fill_(i & 0xFF)                       # L2 flush between timed steps (not timed)
+        ev0[i].record()
+        one_step(args.warmup + i)
+        ev1[i].record()
+        if do_gather and (i + 1) % UNROLL == 0:
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(); gather(); b.record()
+            gev.append((a, b))
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    torch.cuda.synchronize()
+    wall = time.perf_counter() - wall0
+    step_ms = sum(a.elapsed_time(b) for a, b in zip(ev0, ev1))
+    gather_ms = sum(a.elapsed_time(b) for a, b in gev)
+    c1 = eng.counters()
+
+    # hot (no flush, back-to-back) variant: what a resident rollout loop sees
+    torch.cuda.synchronize()
+    h0, h1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    h0.record()
+    for i in range(args.steps):
+        one_step(args.warmup + args.steps + i)
+    h1.record()
+    torch.cuda.synchronize()
+    hot_ms = h0.elapsed_time(h1)
+    sampler.stop()
+
+    # dominant kernel alone (events inside the engine, on the launching stream), L2 flushed
+    eng.set_option("profile", 1)
+    ks, kr = [], []
+    for i in range(min(args.steps, 64)):
+        flush.fill_(i & 0xFF)
+        one_step(i)
+        torch.cuda.synchronize()
+        a, b = eng.timing()
+        ks.append(a); kr.append(b)
+    eng.set_option("profile", 0)
+    kern_ms = float(np.mean(ks))
+
+    tot = torch.tensor([step_ms, gather_ms, hot_ms, kern_ms], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(tot, op=dist.ReduceOp.MAX)
+    step_ms, gather_ms, hot_ms, kern_ms = [float(x) for x in tot.tolist()]
+    total_ms = step_ms + gather_ms
+    total_env_steps = n * world * args.steps
+    value = total_env_steps / (total_ms * 1e-3)
+
+    # end-to-end through the public host API (numpy in, numpy out; H2D + D2H inside the timed region)
+    e2e_steps = min(args.steps, 128)
+    host_pool = action_pool_np(n, 4, 999 + rank)
+    out = (np.empty((n, capi.OBS_DIM), np.float32), np.empty((n,), np.float32), np.empty((n,), np.uint8))
+    for i in range(4):
+        eng.step(host_pool[i % 4], out=out)
+    eng.sync()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    for i in range(e2e_steps):
+        eng.step(host_pool[i % 4], out=out)
+    eng.sync()
+    e2e_s = time.perf_counter() - t0
+    e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
+    e2e_val = n * world * e2e_steps / float(e2e_t.item())
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    peaks = {}
+    try:
+        peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except Exception:
+        pass
+    peak = float(peaks.get("hbm_gbs", 6650.0))
+    peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
+    achieved = ALGO_BYTES_PER_ENV_STEP * n / (kern_ms * 1e-3) / 1e9
+    traffic = None
+    try:
+        traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("pmc_step_kernel_dram_bytes_per_launch")
+    except Exception:
+        pass
+    line = {
+        "metric": "env-steps/sec PMC mocap-tracking", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": "4096-env batched PMC mocap-tracking, flat ground, per GPU (BASELINE configs[1]%s)"
+                   % ("; configs[3] sharding" if world > 1 else ""),
+                   "envs_per_gpu": n, "global_envs": n * world, "substeps": 10, "solver_iters": 10, "mocap": "66 synthetic clips, 229k frames",
+                   "auto_reset": True, "prioritized_sample_factor": 3.0, "actions": "N(mu_a, sigma_a) clipped +-1, device resident",
+                   "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events summed",
+                   "parallelism": "env shards x%d%s" % (world, ", NCCL gather of [128,N,223] slabs to rank 0 every 128 steps" if do_gather else "")},
+        "value_hot_l2": n * world * args.steps / (hot_ms * 1e-3),
+        "value_no_gather": n * world * args.steps / (step_ms * 1e-3),
+        "gather_ms_total": gather_ms, "wall_s_timed_region": wall,
+        "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": n * 12 * 4, "d2h_bytes_per_step": n * (207 * 4 + 4 + 1),
+                "steps": e2e_steps, "api": "VecEngine.step(numpy) -> llq_step (host buffers, pinned staging)"},
+        "gpu_launches": int(c1[4] - c0[4]),
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
+                     "kernel": "pmc_step_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "peak_source": peak_src,
+                     "note": "latency/issue bound by design (SURVEY 7): ~2e5 flop per 1.7 kB; see profiles/"},
+        "clocks": sampler.summary(),
+    }
+    if world == 1:
+        cval, cdt, cores = time_cpu_arm(args.cpu_envs, 24, 2)
+        line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": cores, "kind": "port",
+                                "sample": "%d envs x 24 steps of the same workload on the host cores (oracle/libllq_cpu.so, OpenMP)" % args.cpu_envs}
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

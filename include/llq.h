@@ -64,6 +64,9 @@ extern "C" {
 #define LLQ_F_AVG_REWARD  9  /* double  [n_clips] PLE._avg_reward_sum (PLE:236) */
 #define LLQ_F_EPISODE_ID  10 /* int64   [N]     per-env episode counter (RNG stream position) */
 #define LLQ_F_FOOT_POS    11 /* float   [N,12]  world positions of the 4 foot links after the last step (LR:199-205) -- get only */
+#define LLQ_F_DECISION_MARGIN 12 /* float [N]   CPU oracle only, get only: smallest distance to a discontinuous branch taken during
+                                   the last step: min(|q-limit|) over joints [rad], min(|dist-contact_breaking|) over feet [m].
+                                   Parity tests use it to tell rounding noise from a flipped joint-limit / contact decision. */
 
 typedef struct llq_config {
   int32_t struct_size;        /* = sizeof(llq_config), for ABI checking */
@@ -146,6 +149,12 @@ int llq_set_field(llq_handle h, int field, const void* src);
 /* counters: [0] env steps, [1] episodes finished, [2] contact rows solved, [3] joint-limit rows solved,
  * [4] kernel launches issued by the engine (CUDA) / 0 (CPU). n <= 8. */
 int llq_get_counters(llq_handle h, int64_t* out, int32_t n);
+
+/* Per-kernel device timing of the most recent llq_step*: out[0] = fused step kernel ms, out[1] = reset/table kernel ms
+ * (CUDA events on the launching stream; valid after llq_sync).  Enabled by llq_set_option(h, "profile", 1).
+ * Other options: "block" = CUDA block size (32, 64, 128).  The CPU oracle returns LLQ_EUNSUPPORTED. */
+int llq_set_option(llq_handle h, const char* name, double value);
+int llq_get_timing(llq_handle h, double* out, int32_t n);
 
 /* Block until all work enqueued by this handle has finished (no-op for the CPU oracle). */
 int llq_sync(llq_handle h);

@@ -16,7 +16,7 @@ STATE_DIM, ACTION_DIM, PROP_DIM, OBS_DIM, MOCAP_FRAME = 37, 12, 33, 207, 19
 
 LLQ_IO_HOST, LLQ_IO_DEVICE = 0, 1
 (F_STATE, F_CLIP, F_TIME, F_REWARD_SUM, F_EPISODE_STEPS, F_WARMSTART, F_OBS, F_KIN_STATE, F_SAMPLE_PROB,
- F_AVG_REWARD, F_EPISODE_ID, F_FOOT_POS) = range(12)
+ F_AVG_REWARD, F_EPISODE_ID, F_FOOT_POS, F_DECISION_MARGIN) = range(13)
 
 # field id -> (dtype, per-env width or None for per-clip tables)
 _FIELDS = {
@@ -24,6 +24,7 @@ _FIELDS = {
     F_REWARD_SUM: (np.float32, 1), F_EPISODE_STEPS: (np.int32, 1), F_WARMSTART: (np.float32, 4),
     F_OBS: (np.float32, OBS_DIM), F_KIN_STATE: (np.float32, STATE_DIM), F_SAMPLE_PROB: (np.float64, None),
     F_AVG_REWARD: (np.float64, None), F_EPISODE_ID: (np.int64, 1), F_FOOT_POS: (np.float32, 12),
+    F_DECISION_MARGIN: (np.float32, 1),
 }
 
 
@@ -52,7 +53,7 @@ class LlqError(RuntimeError):
 
 _EXPORTS = ["llq_abi_version", "llq_default_config", "llq_create", "llq_destroy", "llq_load_model", "llq_load_mocap",
             "llq_reset", "llq_reset_to", "llq_step", "llq_step_ex", "llq_get_field", "llq_set_field",
-            "llq_get_counters", "llq_sync", "llq_last_error"]
+            "llq_get_counters", "llq_set_option", "llq_get_timing", "llq_sync", "llq_last_error"]
 
 
 class LlqLibrary:
@@ -82,6 +83,8 @@ class LlqLibrary:
         L.llq_set_field.argtypes = [vp, C.c_int, vp]
         L.llq_get_counters.argtypes = [vp, vp, C.c_int32]
         L.llq_sync.argtypes = [vp]
+        L.llq_set_option.argtypes = [vp, C.c_char_p, C.c_double]
+        L.llq_get_timing.argtypes = [vp, vp, C.c_int32]
         L.llq_last_error.restype = C.c_char_p
         for name in _EXPORTS[:-1]:
             getattr(L, name).restype = C.c_int
@@ -211,6 +214,15 @@ class VecEngine:
         shape = (self.n_clips,) if w is None else ((self.n,) if w == 1 else (self.n, w))
         arr = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), shape), dtype=dt)
         self.lib.check(self.lib.lib.llq_set_field(self._h, field, _ptr(arr)))
+
+    def set_option(self, name, value):
+        self.lib.check(self.lib.lib.llq_set_option(self._h, name.encode(), float(value)))
+
+    def timing(self):
+        """(step kernel ms, reset kernel ms) of the last step; needs set_option("profile", 1)."""
+        out = np.zeros(2, np.float64)
+        self.lib.check(self.lib.lib.llq_get_timing(self._h, _ptr(out), 2))
+        return float(out[0]), float(out[1])
 
     def counters(self):
         out = np.zeros(8, np.int64)

@@ -55,6 +55,7 @@ struct llq_engine {
   void* d_scratch = nullptr; size_t d_scratch_bytes = 0;
   int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   llq::StepParams P{};
+  bool profile = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool ev_valid = false;
 };
 
 namespace {
@@ -244,6 +245,7 @@ int llq_destroy(llq_handle h) {
   for (void* p : dptrs) if (p) cudaFree(p);
   void* hptrs[] = {h->h_actions, h->h_obs, h->h_reward, h->h_done, h->h_scratch};
   for (void* p : hptrs) if (p) cudaFreeHost(p);
+  for (int i = 0; i < 3; i++) if (h->ev[i]) cudaEventDestroy(h->ev[i]);
   if (h->stream) cudaStreamDestroy(h->stream);
   delete h;
   return LLQ_OK;
@@ -406,10 +408,13 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
   } else {
     return fail(LLQ_EINVAL, "bad io_mode");
   }
+  if (h->profile) CK(cudaEventRecord(h->ev[0], s));
   launch_step(h, E, d_act, obs2, (long long)obs_ld, s);
+  if (h->profile) CK(cudaEventRecord(h->ev[1], s));
   // prioritized-sampling table update (PLE:235-240) + auto reset of finished envs
   llq::ResetParams RP = reset_params(h, h->cfg.auto_reset ? 0 : 3, true);
   launch_reset(h, E, RP, obs2, (long long)obs_ld, s);
+  if (h->profile) { CK(cudaEventRecord(h->ev[2], s)); h->ev_valid = true; }
   h->parity ^= 1;
   CK(cudaGetLastError());
   h->counters[0] += (int64_t)n;
@@ -526,6 +531,37 @@ int llq_get_counters(llq_handle h, int64_t* out, int32_t n) {
   for (int i = 0; i < 8; i++) c[i] = h->counters[i];
   c[1] = (int64_t)dc[1]; c[2] = (int64_t)dc[2]; c[3] = (int64_t)dc[3];
   for (int i = 0; i < n; i++) out[i] = c[i];
+  return LLQ_OK;
+}
+
+int llq_set_option(llq_handle h, const char* name, double value) {
+  if (!h || !name) return fail(LLQ_EINVAL, "null argument");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (!std::strcmp(name, "profile")) {
+    h->profile = value != 0;
+    if (h->profile && !h->ev[0]) for (int i = 0; i < 3; i++) CK(cudaEventCreate(&h->ev[i]));
+    return LLQ_OK;
+  }
+  if (!std::strcmp(name, "block")) {
+    int v = (int)value;
+    if (v != 32 && v != 64 && v != 128) return fail(LLQ_EINVAL, "block must be 32, 64 or 128");
+    h->block = v;
+    return LLQ_OK;
+  }
+  return fail(LLQ_EINVAL, std::string("unknown option ") + name);
+}
+
+int llq_get_timing(llq_handle h, double* out, int32_t n) {
+  if (!h || !out || n < 2) return fail(LLQ_EINVAL, "bad arguments");
+  if (!h->profile || !h->ev_valid) return fail(LLQ_ESTATE, "profiling is off or no step has run");
+  int rc = set_device(h);
+  if (rc) return rc;
+  CK(cudaEventSynchronize(h->ev[2]));
+  float a = 0, b = 0;
+  CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
+  CK(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
+  out[0] = a; out[1] = b;
   return LLQ_OK;
 }
 

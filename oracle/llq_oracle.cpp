@@ -243,6 +243,7 @@ struct Env {
   double warm[8];
   double prop_hist[3][LLQ_PROP_DIM]; double act_hist[3][LLQ_ACTION_DIM];
   double foot_pos[12];
+  double margin;   // LLQ_F_DECISION_MARGIN
   float obs[LLQ_OBS_DIM];
 };
 
@@ -482,6 +483,7 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
     const SphereM& sp = md.spheres[s];
     V3 cw = k.pl[sp.link] + mul(k.Rl[sp.link], sp.c);
     double dist = cw.z - sp.r;
+    e.margin = std::min(e.margin, std::fabs(dist - cf.contact_breaking));
     if (dist < cf.contact_breaking) {
       contacts[nc++] = {sp.link, (int)s, V3{cw.x, cw.y, cw.z - sp.r}, dist, cf.ground_friction * sp.mu};
     } else {
@@ -507,6 +509,7 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
     if (!l.haslim) continue;
     for (int side = 0; side < 2; side++) {
       double pen = side == 0 ? e.q[j] - l.lower : l.upper - e.q[j];
+      e.margin = std::min(e.margin, std::fabs(pen));
       if (pen > 0) continue;                       // btMultiBodyJointLimitConstraint: row only when violated
       double dir = side == 0 ? 1.0 : -1.0;
       Row r; std::memset(&r, 0, sizeof(r));
@@ -743,6 +746,7 @@ void sample_reset(llq_engine& E, Env& e, int64_t gid) {
 double step_env(llq_engine& E, Env& e, const float* action, bool* done, int64_t* ncr, int64_t* nlr) {
   const llq_config& cf = E.cfg;
   e.episode_steps += 1;
+  e.margin = 1e30;
   double act[12], tgt[12], tau[12];
   for (int j = 0; j < 12; j++) { act[j] = (double)action[j]; tgt[j] = e.q[j] + act[j]; }   // PLE:198-200
   bool ok = true;
@@ -1020,6 +1024,7 @@ int llq_get_field(llq_handle h, int field, void* dst) {
       case LLQ_F_OBS: std::memcpy((float*)dst + (size_t)i * LLQ_OBS_DIM, e.obs, sizeof(float) * LLQ_OBS_DIM); break;
       case LLQ_F_EPISODE_ID: ((int64_t*)dst)[i] = e.episode; break;
       case LLQ_F_FOOT_POS: for (int t = 0; t < 12; t++) ((float*)dst)[(size_t)i * 12 + t] = (float)e.foot_pos[t]; break;
+      case LLQ_F_DECISION_MARGIN: ((float*)dst)[i] = (float)e.margin; break;
       case LLQ_F_SAMPLE_PROB: case LLQ_F_AVG_REWARD: break;
       default: return fail(LLQ_EINVAL, "unknown field");
     }
@@ -1073,6 +1078,9 @@ int llq_get_counters(llq_handle h, int64_t* out, int32_t n) {
 }
 
 int llq_sync(llq_handle h) { return h ? LLQ_OK : fail(LLQ_EINVAL, "null handle"); }
+
+int llq_set_option(llq_handle, const char*, double) { return fail(LLQ_EUNSUPPORTED, "the CPU oracle has no options"); }
+int llq_get_timing(llq_handle, double*, int32_t) { return fail(LLQ_EUNSUPPORTED, "the CPU oracle has no device timing"); }
 
 const char* llq_last_error(void) { return g_err.c_str(); }
 
