@@ -165,7 +165,12 @@ def main():
     if do_gather and rank == 0:
         recv = [torch.empty_like(slab) for _ in range(world)]
     flush = torch.empty(256 * 1024 * 1024, dtype=torch.uint8, device=dev)          # > 126 MB L2
-    stream = torch.cuda.current_stream().cuda_stream
+    # everything below runs on one explicit (non-default) stream: the engine launches on it, the CUDA events are
+    # recorded on it (torch.cuda.Event only sees torch's current stream)
+    bench_stream = torch.cuda.Stream(device=dev)
+    torch.cuda.set_stream(bench_stream)
+    stream = bench_stream.cuda_stream
+    assert stream != 0
 
     def one_step(i):
         t = i % UNROLL

@@ -35,7 +35,7 @@ constexpr int kPadFrames = 128;  // replicated tail frames so that a stale curso
 
 struct llq_engine {
   llq_config cfg;
-  int block = 128;
+  int block = 32;
   cudaStream_t stream = nullptr;
   bool has_model = false, has_mocap = false, was_reset = false;
   // device
@@ -104,7 +104,10 @@ template <int BLOCK>
 void launch_step_t(llq_handle h, const llq::EnvArrays& E, const float* d_actions, float* obs2, long long ld, cudaStream_t s) {
   int threads = 4 * h->cfg.n_envs;
   int grid = (threads + BLOCK - 1) / BLOCK;
-  llq::pmc_step_kernel<BLOCK><<<grid, BLOCK, 0, s>>>(E, mocap_dev(h), h->P, h->d_model, d_actions, obs2, ld, h->d_winner[h->parity]);
+  const size_t smem = sizeof(float) * llq::kRowFloats * BLOCK;
+  static bool attr_set = false;   // per template instance
+  if (!attr_set) { cudaFuncSetAttribute(llq::pmc_step_kernel<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  llq::pmc_step_kernel<BLOCK><<<grid, BLOCK, smem, s>>>(E, mocap_dev(h), h->P, h->d_model, d_actions, obs2, ld, h->d_winner[h->parity]);
 }
 template <int BLOCK>
 void launch_reset_t(llq_handle h, const llq::EnvArrays& E, const llq::ResetParams& RP, float* obs2, long long ld, cudaStream_t s) {

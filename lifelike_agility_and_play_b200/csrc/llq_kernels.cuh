@@ -20,7 +20,8 @@
 namespace llq {
 
 constexpr int kObsDim = 207, kPropDim = 33, kActDim = 12, kStateDim = 37;
-constexpr int kNewObs = 120;  // floats staged per env: prop 33 | action 12 | future 72 (+3 pad)
+constexpr int kNewObs = 120;
+constexpr int kRowFloats = 36 + 18 + 144;  // per-lane floats of the constraint-row workspace in shared memory  // floats staged per env: prop 33 | action 12 | future 72 (+3 pad)
 
 struct DampItem { float m; float c[3]; float Ic[6]; };
 struct JointConst {
@@ -326,6 +327,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
                                                          int* __restrict__ winner) {
   __shared__ ModelConst M;
   __shared__ __align__(16) float s_new[BLOCK / 4][kNewObs];
+  extern __shared__ float rows_sm[];     // kRowFloats * BLOCK floats: per-lane constraint-row workspace (Y 36 | U 18 | A 144)
   {
     const int* src = reinterpret_cast<const int*>(gmodel);
     int* dst = reinterpret_cast<int*>(&M);
@@ -333,6 +335,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
   }
   __syncthreads();
 
+  const int tid = threadIdx.x;
   const int N = P.n_envs;
   const int gtid = blockIdx.x * BLOCK + threadIdx.x;
   const int env_raw = gtid >> 2;
@@ -475,245 +478,266 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     // predicted velocity in base coordinates (generalised velocity used by the constraint rows)
     const V3 wbs = tmul(R, ww), vbs = tmul(R, vw);
 
+    // ---------------- leg kinematics and the ABA's per-joint vectors, re-expressed in base coordinates about the base origin
+    const float kc1 = jc[0].c, ks1 = jc[0].s, kc2 = jc[1].c, ks2 = jc[1].s;
+    const float kc23 = kc2 * jc[2].c - ks2 * jc[2].s, ks23 = ks2 * jc[2].c + kc2 * jc[2].s;
+    const V3 p1 = r[0];
+    const V3 p2 = p1 + rot<0>(r[1], kc1, ks1);
+    const V3 p3 = p2 + rot<0>(rot<1>(r[2], kc2, ks2), kc1, ks1);
+    const V3 fb = p3 + rot<0>(rot<1>(ld3(L.foot), kc23, ks23), kc1, ks1);     // foot centre
+    const V3 n2 = V3{0.f, -kc1, -ks1};                                       // axis of joints 2, 3 (= -E1 e_y)
+    V3 Sa[3], Sl[3], Ua[3], Ul[3];
+    Sa[0] = V3{1.f, 0.f, 0.f}; Sl[0] = cross(p1, Sa[0]);
+    Sa[1] = n2; Sl[1] = cross(p2, n2);
+    Sa[2] = n2; Sl[2] = cross(p3, n2);
+    Ul[0] = rot<0>(jc[0].Ul, kc1, ks1); Ua[0] = rot<0>(jc[0].Ua, kc1, ks1) + cross(p1, Ul[0]);
+    Ul[1] = rot<0>(rot<1>(jc[1].Ul, kc2, ks2), kc1, ks1); Ua[1] = rot<0>(rot<1>(jc[1].Ua, kc2, ks2), kc1, ks1) + cross(p2, Ul[1]);
+    Ul[2] = rot<0>(rot<1>(jc[2].Ul, kc23, ks23), kc1, ks1); Ua[2] = rot<0>(rot<1>(jc[2].Ua, kc23, ks23), kc1, ks1) + cross(p3, Ul[2]);
+    const float Di[3] = {jc[0].Dinv, jc[1].Dinv, jc[2].Dinv};
+
     // ---------------- collision: foot sphere vs plane z = 0 on the pre-step pose
-    const V3 fb = foot_in_base(L, q[0], q[1], q[2]);     // foot centre, base coords (same trig as jc; recomputed for clarity)
     const V3 nb = V3{R.a20, R.a21, R.a22};               // world z in base coords
     const float dist = (float)pz + dot(nb, fb) - L.foot_r;
     const bool contact = dist < P.breaking;
     if (!contact) warm = 0.f;
-    const unsigned cmask_w = __ballot_sync(FULL, contact);
-    const unsigned cmask = (cmask_w >> (threadIdx.x & 28)) & 0xFu;     // contact bits of this env's 4 feet
-    // joint-limit rows (btMultiBodyJointLimitConstraint: only when violated)
-    int limdir[3];
-    unsigned mylim = 0;
+    // joint-limit rows (btMultiBodyJointLimitConstraint: a row exists only while the limit is violated)
+    float limdir[3];
+    unsigned mymask = contact ? 7u : 0u;   // bits 0-2: contact rows n,t1,t2 ; bits 3-5: limit rows of joints 0-2
 #pragma unroll
     for (int i = 0; i < 3; i++) {
-      limdir[i] = 0;
+      limdir[i] = 0.f;
       if (L.j[i].haslim) {
-        if (q[i] - L.j[i].lower <= 0.f) limdir[i] = 1;
-        else if (L.j[i].upper - q[i] <= 0.f) limdir[i] = -1;
+        if (q[i] - L.j[i].lower <= 0.f) limdir[i] = 1.f;
+        else if (L.j[i].upper - q[i] <= 0.f) limdir[i] = -1.f;
       }
-      if (limdir[i]) mylim |= 1u << i;
+      if (limdir[i] != 0.f) mymask |= 8u << i;
     }
-    const bool any_lim_warp = __any_sync(FULL, mylim != 0);
+    const unsigned envmask = __shfl_sync(FULL, mymask, 0, 4) | (__shfl_sync(FULL, mymask, 1, 4) << 6) |
+                             (__shfl_sync(FULL, mymask, 2, 4) << 12) | (__shfl_sync(FULL, mymask, 3, 4) << 18);
+    const unsigned warpmask = __reduce_or_sync(FULL, envmask);
+    const bool any_con_warp = (warpmask & 0x1C71C7u) != 0;   // bits 0-2 of each 6-bit group
+    const bool any_lim_warp = (warpmask & 0xE38E38u) != 0;   // bits 3-5 of each 6-bit group
+    float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dvl[3] = {0.f, 0.f, 0.f};
 
-    // ---------------- constraint rows of this lane's own foot: Jacobians + unit-impulse responses
-    // directions (world): n = +z, t1 = -y, t2 = +x   (btPlaneSpace1 of the plane normal)
-    float Jb[3][6], Jl[3][3], Wb[4][3][6], Wl[4][3][3], rhs[3], invd[3], lam[3];
-    float ur[3][3];      // up-pass u's of own rows
-    float A0[3][6];      // base response of own rows
-    float den[3] = {1.f, 1.f, 1.f};
-    {
-      const V3 dirs[3] = {nb, neg(V3{R.a10, R.a11, R.a12}), V3{R.a00, R.a01, R.a02}};
-      // contact point on the sphere surface (base coords) and the same in shank coords
-      const V3 Pb = fb - L.foot_r * nb;
+    if (warpmask) {
+      // own rows 0..2 = contact (n, t1, t2), 3..5 = joint limits.  For each row we keep its image under the ABA's
+      // L^-1 factor: y = L0^-1 Fhat (base part, 6) and u (joint part, 3).  Then  J_r M^-1 J_s^T = y_r.y_s + sum_i u_ri u_si / D_i
+      // (second term only for rows on the same leg) -- no per-row down passes are needed.
+      float bq[6], rhs[6], invd[6], lam[6];
 #pragma unroll
-      for (int d = 0; d < 3; d++) {
-        V3 db = dirs[d];
-        // direction in shank coordinates
-        V3 d3 = rotT<1>(rotT<1>(rotT<0>(db, jc[0].c, jc[0].s), jc[1].c, jc[1].s), jc[2].c, jc[2].s);
-        V3 n3 = rotT<1>(rotT<1>(rotT<0>(nb, jc[0].c, jc[0].s), jc[1].c, jc[1].s), jc[2].c, jc[2].s);
-        V3 P3 = ld3(L.foot) - L.foot_r * n3;
-        SV F3 = SV{cross(P3, d3), d3};
-        // rigid force transport for the Jacobian row: J_i = S_i . F_i
-        SV F = F3;
-        Jl[d][2] = -F.a.y;
-        F = xforce<1>(F, r[2], jc[2].c, jc[2].s);
-        Jl[d][1] = -F.a.y;
-        F = xforce<1>(F, r[1], jc[1].c, jc[1].s);
-        Jl[d][0] = F.a.x;
-        V3 jw = cross(Pb, db);
-        Jb[d][0] = jw.x; Jb[d][1] = jw.y; Jb[d][2] = jw.z; Jb[d][3] = db.x; Jb[d][4] = db.y; Jb[d][5] = db.z;
-        // articulated up pass and base solve
-        SV Fb = response_up(jc, r, F3, 0.f, 0.f, 0.f, ur[d]);
-        float b[6] = {Fb.a.x, Fb.a.y, Fb.a.z, Fb.l.x, Fb.l.y, Fb.l.z};
-        chol6_solve(ch, b, A0[d]);
-      }
-    }
-    // exchange: every lane gets every foot's base response and runs the down pass for its own leg
-#pragma unroll
-    for (int j = 0; j < 4; j++) {
-      if (__any_sync(FULL, (cmask >> j) & 1u)) {
+      for (int t = 0; t < 6; t++) { bq[t] = 0.f; rhs[t] = 0.f; invd[t] = 0.f; lam[t] = 0.f; }
+      float* Ysm = rows_sm + tid;                         // Y[r][t] at Ysm[(r*6+t)*BLOCK]
+      float* Usm = rows_sm + 36 * BLOCK + tid;            // U[r][i] at Usm[(r*3+i)*BLOCK]
+      float* Asm = rows_sm + 54 * BLOCK + tid;            // A[r][s] at Asm[(r*24+s)*BLOCK]
+      if (any_con_warp) {
+        // directions (world): n = +z, t1 = -y, t2 = +x   (btPlaneSpace1 of the plane normal), in base coords
+        const V3 dirs[3] = {nb, neg(V3{R.a10, R.a11, R.a12}), V3{R.a00, R.a01, R.a02}};
+        const V3 Pc = fb - L.foot_r * nb;                 // contact point on the sphere surface
 #pragma unroll
         for (int d = 0; d < 3; d++) {
-          float a[6];
+          const V3 db = dirs[d];
+          V3 Ga = cross(Pc, db), Gl = db;                 // spatial force of a unit impulse, about the base origin
+          const float rel0 = dot(Ga, wbs) + dot(Gl, vbs);
+          float u[3];
+          u[2] = dot(Sa[2], Ga) + dot(Sl[2], Gl);
+          const float j2 = dot(Sa[1], Ga) + dot(Sl[1], Gl), j1 = dot(Sa[0], Ga) + dot(Sl[0], Gl);
+          const float rel = rel0 + j1 * qd[0] + j2 * qd[1] + u[2] * qd[2];
+          float g = u[2] * Di[2];
+          Ga = fma3(-g, Ua[2], Ga); Gl = fma3(-g, Ul[2], Gl);
+          u[1] = dot(Sa[1], Ga) + dot(Sl[1], Gl);
+          g = u[1] * Di[1];
+          Ga = fma3(-g, Ua[1], Ga); Gl = fma3(-g, Ul[1], Gl);
+          u[0] = dot(Sa[0], Ga) + dot(Sl[0], Gl);
+          g = u[0] * Di[0];
+          Ga = fma3(-g, Ua[0], Ga); Gl = fma3(-g, Ul[0], Gl);
+          float y[6];
+          { const float bb[6] = {Ga.x, Ga.y, Ga.z, Gl.x, Gl.y, Gl.z}; chol6_fwd(ch, bb, y); }
+          float dg = u[0] * u[0] * Di[0] + u[1] * u[1] * Di[1] + u[2] * u[2] * Di[2];
 #pragma unroll
-          for (int t = 0; t < 6; t++) a[t] = __shfl_sync(FULL, A0[d][t], j, 4);
-          const bool own = (j == k);
-          float qd3[3];
-          response_down(jc, r, SV{V3{a[0], a[1], a[2]}, V3{a[3], a[4], a[5]}}, own ? ur[d][0] : 0.f, own ? ur[d][1] : 0.f,
-                        own ? ur[d][2] : 0.f, qd3);
+          for (int t = 0; t < 6; t++) { dg = fmaf(y[t], y[t], dg); Ysm[(d * 6 + t) * BLOCK] = y[t]; }
 #pragma unroll
-          for (int t = 0; t < 6; t++) Wb[j][d][t] = a[t];
-#pragma unroll
-          for (int t = 0; t < 3; t++) Wl[j][d][t] = qd3[t];
-          if (own) {
-            float dn = 0.f;
-#pragma unroll
-            for (int t = 0; t < 6; t++) dn = fmaf(Jb[d][t], a[t], dn);
-#pragma unroll
-            for (int t = 0; t < 3; t++) dn = fmaf(Jl[d][t], qd3[t], dn);
-            den[d] = dn;
+          for (int i = 0; i < 3; i++) Usm[(d * 3 + i) * BLOCK] = u[i];
+          invd[d] = contact ? 1.0f / dg : 0.f;
+          if (d == 0) {   // btMultiBodyConstraintSolver::setupMultiBodyContactConstraint
+            float pen = dist + P.slop, poserr = 0.f, velerr = -rel;
+            if (pen > 0.f) velerr -= pen / dt; else poserr = -pen * P.erp / dt;
+            rhs[0] = (poserr + velerr) * invd[0];
+            lam[0] = contact ? P.warm * warm : 0.f;
+          } else {
+            rhs[d] = -rel * invd[d];
           }
         }
+        if (contact) n_contact_rows += 3;
       }
-    }
-    // own rows: effective mass, right-hand sides (btMultiBodyConstraintSolver::setupMultiBodyContactConstraint)
-    const float mu = P.mu;
-#pragma unroll
-    for (int d = 0; d < 3; d++) {
-      float rel = Jb[d][0] * wbs.x + Jb[d][1] * wbs.y + Jb[d][2] * wbs.z + Jb[d][3] * vbs.x + Jb[d][4] * vbs.y + Jb[d][5] * vbs.z +
-            Jl[d][0] * qd[0] + Jl[d][1] * qd[1] + Jl[d][2] * qd[2];
-      invd[d] = contact ? 1.0f / den[d] : 0.f;
-      if (d == 0) {
-        float pen = dist + P.slop, poserr = 0.f, velerr = -rel;
-        if (pen > 0.f) velerr -= pen / dt; else poserr = -pen * P.erp / dt;
-        rhs[0] = (poserr + velerr) * invd[0];
-        lam[0] = contact ? P.warm * warm : 0.f;
-      } else {
-        rhs[d] = -rel * invd[d];
-        lam[d] = 0.f;
-      }
-    }
-    if (contact) n_contact_rows += 3;
-
-    // joint-limit rows (rare): W for each active (leg j, joint i) row lives in local memory
-    float WLb[4][3][6], WLl[4][3][3], lrhs[3], linvd[3], llam[3];
-    unsigned limmask = 0;   // 12 bits: bit (3*j+i) = row active in this env
-    if (any_lim_warp) {
-      unsigned m0 = __shfl_sync(FULL, mylim, 0, 4), m1 = __shfl_sync(FULL, mylim, 1, 4), m2 = __shfl_sync(FULL, mylim, 2, 4),
-               m3 = __shfl_sync(FULL, mylim, 3, 4);
-      limmask = m0 | (m1 << 3) | (m2 << 6) | (m3 << 9);
-#pragma unroll 1
-      for (int j = 0; j < 4; j++) {
+      if (any_lim_warp) {
 #pragma unroll
         for (int i = 0; i < 3; i++) {
-          if (!__any_sync(FULL, (limmask >> (3 * j + i)) & 1u)) continue;
-          float uu[3], a[6], b[6];
-          float dirf = (float)limdir[i];
-          SV Fb = response_up(jc, r, SV{V3{0.f, 0.f, 0.f}, V3{0.f, 0.f, 0.f}}, i == 0 ? dirf : 0.f, i == 1 ? dirf : 0.f,
-                              i == 2 ? dirf : 0.f, uu);
-          b[0] = Fb.a.x; b[1] = Fb.a.y; b[2] = Fb.a.z; b[3] = Fb.l.x; b[4] = Fb.l.y; b[5] = Fb.l.z;
-          chol6_solve(ch, b, a);
+          const float dir = limdir[i];
+          float u[3] = {0.f, 0.f, 0.f};
+          u[i] = dir;
+          float g = dir * Di[i];
+          V3 Ga = (-g) * Ua[i], Gl = (-g) * Ul[i];
 #pragma unroll
-          for (int t = 0; t < 6; t++) a[t] = __shfl_sync(FULL, a[t], j, 4);
-          const bool own = (j == k);
-          float qd3[3];
-          response_down(jc, r, SV{V3{a[0], a[1], a[2]}, V3{a[3], a[4], a[5]}}, own ? uu[0] : 0.f, own ? uu[1] : 0.f, own ? uu[2] : 0.f, qd3);
+          for (int m = i - 1; m >= 0; m--) {
+            u[m] = dot(Sa[m], Ga) + dot(Sl[m], Gl);
+            g = u[m] * Di[m];
+            Ga = fma3(-g, Ua[m], Ga); Gl = fma3(-g, Ul[m], Gl);
+          }
+          float y[6];
+          { const float bb[6] = {Ga.x, Ga.y, Ga.z, Gl.x, Gl.y, Gl.z}; chol6_fwd(ch, bb, y); }
+          float dg = u[0] * u[0] * Di[0] + u[1] * u[1] * Di[1] + u[2] * u[2] * Di[2];
 #pragma unroll
-          for (int t = 0; t < 6; t++) WLb[j][i][t] = a[t];
+          for (int t = 0; t < 6; t++) { dg = fmaf(y[t], y[t], dg); Ysm[((3 + i) * 6 + t) * BLOCK] = y[t]; }
 #pragma unroll
-          for (int t = 0; t < 3; t++) WLl[j][i][t] = qd3[t];
-          if (own) {
-            // J = dir * e_i  ->  denom = dir * W[i],  rel = dir * qd[i]
-            float den = dirf * qd3[i], rel = dirf * qd[i];
-            float pen = limdir[i] > 0 ? q[i] - L.j[i].lower : L.j[i].upper - q[i];
-            linvd[i] = limdir[i] ? 1.0f / den : 0.f;
-            float poserr = pen > -0.04f ? -pen * P.jerp / dt : 0.f;   // split-impulse threshold quirk
-            lrhs[i] = (poserr - rel) * linvd[i];
-            llam[i] = 0.f;
-            if (limdir[i]) n_limit_rows += 1;
+          for (int m = 0; m < 3; m++) Usm[((3 + i) * 3 + m) * BLOCK] = u[m];
+          if (dir != 0.f) {
+            const float rel = dir * qd[i];
+            const float pen = dir > 0.f ? q[i] - L.j[i].lower : L.j[i].upper - q[i];
+            invd[3 + i] = 1.0f / dg;
+            const float poserr = pen > -0.04f ? -pen * P.jerp / dt : 0.f;   // split-impulse threshold quirk
+            rhs[3 + i] = (poserr - rel) * invd[3 + i];
+            n_limit_rows += 1;
           }
         }
       }
-    }
-
-    // ---------------- projected Gauss-Seidel on delta velocities (base coords + own leg)
-    float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dvl[3] = {0.f, 0.f, 0.f};
-    if (cmask_w) {
-      // warm start (normal rows only)
+      __syncwarp();
+      // ---- Delassus block of the own rows against every active row of the env (y's of the other legs come through smem)
+      const int nrows = any_lim_warp ? 6 : 3;
+      const int g0 = tid & ~3;
+      const unsigned ownmask_w = __reduce_or_sync(FULL, mymask);   // own-row slots that are active on some lane of the warp
+#pragma unroll 1
+      for (int rr = 0; rr < nrows; rr++) {
+        if (!((ownmask_w >> rr) & 1u)) continue;
+        float yo[6], uo[3];
 #pragma unroll
-      for (int j = 0; j < 4; j++) {
-        float l0 = __shfl_sync(FULL, lam[0], j, 4);
-        if ((cmask >> j) & 1u) {
+        for (int t = 0; t < 6; t++) yo[t] = Ysm[(rr * 6 + t) * BLOCK];
 #pragma unroll
-          for (int t = 0; t < 6; t++) dvb[t] = fmaf(Wb[j][0][t], l0, dvb[t]);
+        for (int i = 0; i < 3; i++) uo[i] = Usm[(rr * 3 + i) * BLOCK] * Di[i];
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+          const float* Yj = rows_sm + g0 + j;
+          const float* Uj = rows_sm + 36 * BLOCK + g0 + j;
+          const float own = (j == k) ? 1.f : 0.f;
+#pragma unroll 1
+          for (int rs = 0; rs < nrows; rs++) {
+            if (!((warpmask >> (6 * j + rs)) & 1u)) continue;
+            float acc = own * (uo[0] * Uj[(rs * 3 + 0) * BLOCK] + uo[1] * Uj[(rs * 3 + 1) * BLOCK] + uo[2] * Uj[(rs * 3 + 2) * BLOCK]);
 #pragma unroll
-          for (int t = 0; t < 3; t++) dvl[t] = fmaf(Wl[j][0][t], l0, dvl[t]);
+            for (int t = 0; t < 6; t++) acc = fmaf(yo[t], Yj[(rs * 6 + t) * BLOCK], acc);
+            Asm[(rr * 24 + 6 * j + rs) * BLOCK] = acc;
+          }
         }
       }
-    }
-    if (cmask_w || any_lim_warp) {
+      // ---- projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration order: limits, normals, friction)
+      // bq[r] tracks J_r . (delta velocity) for the own rows; every applied impulse updates it through the Delassus column.
+#define LLQ_APPLY(col, dl_)                                                              \
+      {                                                                                  \
+        const float* Ac_ = Asm + (col) * BLOCK;                                          \
+        bq[0] = fmaf(Ac_[0 * 24 * BLOCK], dl_, bq[0]);                                   \
+        bq[1] = fmaf(Ac_[1 * 24 * BLOCK], dl_, bq[1]);                                   \
+        bq[2] = fmaf(Ac_[2 * 24 * BLOCK], dl_, bq[2]);                                   \
+        if (any_lim_warp) {                                                              \
+          bq[3] = fmaf(Ac_[3 * 24 * BLOCK], dl_, bq[3]);                                 \
+          bq[4] = fmaf(Ac_[4 * 24 * BLOCK], dl_, bq[4]);                                 \
+          bq[5] = fmaf(Ac_[5 * 24 * BLOCK], dl_, bq[5]);                                 \
+        }                                                                                \
+      }
+      if (any_con_warp) {   // warm start of the normal rows
+#pragma unroll 1
+        for (int j = 0; j < 4; j++) {
+          if (!((warpmask >> (6 * j)) & 1u)) continue;
+          const float l0 = __shfl_sync(FULL, lam[0], j, 4);
+          if ((envmask >> (6 * j)) & 1u) LLQ_APPLY(6 * j, l0)
+        }
+      }
+      const float mu = P.mu;
+#pragma unroll 1
       for (int it = 0; it < P.solver_iters; it++) {
         if (any_lim_warp) {
 #pragma unroll 1
           for (int j = 0; j < 4; j++) {
 #pragma unroll
             for (int i = 0; i < 3; i++) {
-              if (!__any_sync(FULL, (limmask >> (3 * j + i)) & 1u)) continue;
+              if (!((warpmask >> (6 * j + 3 + i)) & 1u)) continue;
               float dl = 0.f;
-              if (j == k && limdir[i]) {
-                float jd = (float)limdir[i] * dvl[i];
-                dl = lrhs[i] - jd * linvd[i];
-                float sum = llam[i] + dl;
-                if (sum < 0.f) { dl = -llam[i]; llam[i] = 0.f; }
-                else if (sum > P.max_imp) { dl = P.max_imp - llam[i]; llam[i] = P.max_imp; }
-                else llam[i] = sum;
+              if (j == k && limdir[i] != 0.f) {
+                dl = rhs[3 + i] - bq[3 + i] * invd[3 + i];
+                const float sum = lam[3 + i] + dl;
+                if (sum < 0.f) { dl = -lam[3 + i]; lam[3 + i] = 0.f; }
+                else if (sum > P.max_imp) { dl = P.max_imp - lam[3 + i]; lam[3 + i] = P.max_imp; }
+                else lam[3 + i] = sum;
               }
               dl = __shfl_sync(FULL, dl, j, 4);
-              if ((limmask >> (3 * j + i)) & 1u) {
-#pragma unroll
-                for (int t = 0; t < 6; t++) dvb[t] = fmaf(WLb[j][i][t], dl, dvb[t]);
-#pragma unroll
-                for (int t = 0; t < 3; t++) dvl[t] = fmaf(WLl[j][i][t], dl, dvl[t]);
+              if ((envmask >> (6 * j + 3 + i)) & 1u) LLQ_APPLY(6 * j + 3 + i, dl)
+            }
+          }
+        }
+        if (any_con_warp) {
+#pragma unroll 1
+          for (int j = 0; j < 4; j++) {   // normal rows, feet in order FR FL HR HL
+            if (!((warpmask >> (6 * j)) & 1u)) continue;
+            float dl = 0.f;
+            if (j == k && contact) {
+              dl = rhs[0] - bq[0] * invd[0];
+              const float sum = lam[0] + dl;
+              if (sum < 0.f) { dl = -lam[0]; lam[0] = 0.f; }
+              else if (sum > 1e10f) { dl = 1e10f - lam[0]; lam[0] = 1e10f; }
+              else lam[0] = sum;
+            }
+            dl = __shfl_sync(FULL, dl, j, 4);
+            if ((envmask >> (6 * j)) & 1u) LLQ_APPLY(6 * j, dl)
+          }
+#pragma unroll 1
+          for (int j = 0; j < 4; j++) {   // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
+            if (!((warpmask >> (6 * j)) & 1u)) continue;
+            float da = 0.f, db = 0.f;
+            if (j == k && contact) {
+              float sa = lam[1] + (rhs[1] - bq[1] * invd[1]), sb = lam[2] + (rhs[2] - bq[2] * invd[2]);
+              const float limit = mu * lam[0];
+              const float r2 = sa * sa + sb * sb;
+              if (r2 >= limit * limit && r2 > 0.f) {
+                const float sc = limit * rsqrtf(r2);
+                sa *= sc; sb *= sc;
               }
+              da = sa - lam[1]; db = sb - lam[2];
+              lam[1] = sa; lam[2] = sb;
             }
-          }
-        }
-        // normal rows, feet in order FR FL HR HL
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          if (!__any_sync(FULL, (cmask >> j) & 1u)) continue;
-          float dl = 0.f;
-          if (j == k && contact) {
-            float jd = Jb[0][0] * dvb[0] + Jb[0][1] * dvb[1] + Jb[0][2] * dvb[2] + Jb[0][3] * dvb[3] + Jb[0][4] * dvb[4] + Jb[0][5] * dvb[5] +
-                       Jl[0][0] * dvl[0] + Jl[0][1] * dvl[1] + Jl[0][2] * dvl[2];
-            dl = rhs[0] - jd * invd[0];
-            float sum = lam[0] + dl;
-            if (sum < 0.f) { dl = -lam[0]; lam[0] = 0.f; }
-            else if (sum > 1e10f) { dl = 1e10f - lam[0]; lam[0] = 1e10f; }
-            else lam[0] = sum;
-          }
-          dl = __shfl_sync(FULL, dl, j, 4);
-          if ((cmask >> j) & 1u) {
-#pragma unroll
-            for (int t = 0; t < 6; t++) dvb[t] = fmaf(Wb[j][0][t], dl, dvb[t]);
-#pragma unroll
-            for (int t = 0; t < 3; t++) dvl[t] = fmaf(Wl[j][0][t], dl, dvl[t]);
-          }
-        }
-        // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
-#pragma unroll
-        for (int j = 0; j < 4; j++) {
-          if (!__any_sync(FULL, (cmask >> j) & 1u)) continue;
-          float da = 0.f, db = 0.f;
-          if (j == k && contact) {
-            float ja = Jb[1][0] * dvb[0] + Jb[1][1] * dvb[1] + Jb[1][2] * dvb[2] + Jb[1][3] * dvb[3] + Jb[1][4] * dvb[4] + Jb[1][5] * dvb[5] +
-                       Jl[1][0] * dvl[0] + Jl[1][1] * dvl[1] + Jl[1][2] * dvl[2];
-            float jb = Jb[2][0] * dvb[0] + Jb[2][1] * dvb[1] + Jb[2][2] * dvb[2] + Jb[2][3] * dvb[3] + Jb[2][4] * dvb[4] + Jb[2][5] * dvb[5] +
-                       Jl[2][0] * dvl[0] + Jl[2][1] * dvl[1] + Jl[2][2] * dvl[2];
-            float sa = lam[1] + (rhs[1] - ja * invd[1]), sb = lam[2] + (rhs[2] - jb * invd[2]);
-            float limit = mu * lam[0];
-            float r2 = sa * sa + sb * sb;
-            if (r2 >= limit * limit && r2 > 0.f) {
-              float sc = limit / sqrtf(r2);
-              sa *= sc; sb *= sc;
+            da = __shfl_sync(FULL, da, j, 4);
+            db = __shfl_sync(FULL, db, j, 4);
+            if ((envmask >> (6 * j)) & 1u) {
+              LLQ_APPLY(6 * j + 1, da)
+              LLQ_APPLY(6 * j + 2, db)
             }
-            da = sa - lam[1]; db = sb - lam[2];
-            lam[1] = sa; lam[2] = sb;
-          }
-          da = __shfl_sync(FULL, da, j, 4);
-          db = __shfl_sync(FULL, db, j, 4);
-          if ((cmask >> j) & 1u) {
-#pragma unroll
-            for (int t = 0; t < 6; t++) dvb[t] = fmaf(Wb[j][1][t], da, fmaf(Wb[j][2][t], db, dvb[t]));
-#pragma unroll
-            for (int t = 0; t < 3; t++) dvl[t] = fmaf(Wl[j][1][t], da, fmaf(Wl[j][2][t], db, dvl[t]));
           }
         }
       }
+#undef LLQ_APPLY
+      if (contact) warm = lam[0];
+      // ---- total impulse -> velocity change: one back substitution and one down pass (base coordinates)
+      float Yt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, wt[3] = {0.f, 0.f, 0.f};
+#pragma unroll
+      for (int rr = 0; rr < 6; rr++) {
+        if ((mymask >> rr) & 1u) {
+          const float l = lam[rr];
+#pragma unroll
+          for (int t = 0; t < 6; t++) Yt[t] = fmaf(l, Ysm[(rr * 6 + t) * BLOCK], Yt[t]);
+#pragma unroll
+          for (int i = 0; i < 3; i++) wt[i] = fmaf(l, Usm[(rr * 3 + i) * BLOCK], wt[i]);
+        }
+      }
+#pragma unroll
+      for (int t = 0; t < 6; t++) Yt[t] = gsum4(Yt[t]);
+      chol6_bwd(ch, Yt, dvb);
+      {
+        V3 aa = V3{dvb[0], dvb[1], dvb[2]}, al = V3{dvb[3], dvb[4], dvb[5]};
+        dvl[0] = (wt[0] - dot(Ua[0], aa) - dot(Ul[0], al)) * Di[0];
+        aa = fma3(dvl[0], Sa[0], aa); al = fma3(dvl[0], Sl[0], al);
+        dvl[1] = (wt[1] - dot(Ua[1], aa) - dot(Ul[1], al)) * Di[1];
+        aa = fma3(dvl[1], Sa[1], aa); al = fma3(dvl[1], Sl[1], al);
+        dvl[2] = (wt[2] - dot(Ua[2], aa) - dot(Ul[2], al)) * Di[2];
+      }
+      __syncwarp();
     }
-    if (contact) warm = lam[0];
 
     // ---------------- apply the impulses, clamp, integrate (btMultiBody::stepPositionsMultiDof)
     {

@@ -165,4 +165,25 @@ LLQ_DI void chol6_solve(const Chol6& c, const float (&b)[6], float (&x)[6]) {
   }
 }
 
+// forward substitution only: y = L^-1 b
+LLQ_DI void chol6_fwd(const Chol6& c, const float (&b)[6], float (&y)[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s = fmaf(-c.l[tri(i, k)], y[k], s);
+    y[i] = s * c.l[tri(i, i)];
+  }
+}
+// backward substitution only: x = L^-T y
+LLQ_DI void chol6_bwd(const Chol6& c, const float (&y)[6], float (&x)[6]) {
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    float s = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) s = fmaf(-c.l[tri(k, i)], x[k], s);
+    x[i] = s * c.l[tri(i, i)];
+  }
+}
+
 }  // namespace llq

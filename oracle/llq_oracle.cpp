@@ -1084,4 +1084,32 @@ int llq_get_timing(llq_handle, double*, int32_t) { return fail(LLQ_EUNSUPPORTED,
 
 const char* llq_last_error(void) { return g_err.c_str(); }
 
+// ---- oracle-only hooks (not part of include/llq.h): fp64 state access and a bare physics sub-step with caller-supplied
+// joint torques.  tests/golden/pybullet_shim.py builds a stand-in `pybullet` module on these so that the *unmodified*
+// reference PrimitiveLevelEnv / LeggedRobot / MotionLib can be executed here and their outputs frozen as golden vectors.
+int llq_oracle_get_state64(llq_handle h, int32_t env, double* st37) {
+  if (!h || !st37 || env < 0 || env >= h->cfg.n_envs) return fail(LLQ_EINVAL, "bad arguments");
+  pack_state(h->envs[env], st37);
+  return LLQ_OK;
+}
+int llq_oracle_set_state64(llq_handle h, int32_t env, const double* st37) {
+  if (!h || !st37 || env < 0 || env >= h->cfg.n_envs) return fail(LLQ_EINVAL, "bad arguments");
+  unpack_state(h->envs[env], st37);
+  for (int s = 0; s < 8; s++) h->envs[env].warm[s] = 0;   // resetBasePositionAndOrientation drops the contact cache
+  return LLQ_OK;
+}
+int llq_oracle_substep(llq_handle h, int32_t env, const double* tau12) {
+  if (!h || !tau12 || env < 0 || env >= h->cfg.n_envs) return fail(LLQ_EINVAL, "bad arguments");
+  if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
+  int64_t a = 0, b = 0;
+  h->envs[env].margin = 1e30;
+  return physics_substep(*h, h->envs[env], tau12, &a, &b) ? LLQ_OK : fail(LLQ_ESTATE, "physics sub-step failed");
+}
+int llq_oracle_foot_positions(llq_handle h, const double* st37, double* out12) {
+  if (!h || !st37 || !out12) return fail(LLQ_EINVAL, "bad arguments");
+  if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
+  foot_positions(*h, st37, out12);
+  return LLQ_OK;
+}
+
 }  // extern "C"

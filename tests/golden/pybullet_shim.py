@@ -1,0 +1,189 @@
+"""Stand-ins for the reference's missing third-party modules (pybullet, pybullet_utils, gym, tleague) so that the
+*unmodified* reference classes (LeggedRobot, MotionLib, PrimitiveLevelEnv, create_tracking_game) can be imported and
+executed in this container.  Only used by gen_golden_from_reference.py (which needs /root/reference) -- never at test
+time, never on the GPU box.
+
+`pybullet` is the interesting one: every call the reference makes (legged_robot.py, primitive_level_env.py) is mapped
+onto oracle/libllq_cpu.so's fp64 physics through the oracle-only hooks llq_oracle_{get,set}_state64 /
+llq_oracle_substep / llq_oracle_foot_positions.  What the resulting golden vectors pin is therefore the reference's
+*environment logic* (call order, sub-step loop, mocap clock, interpolation, observation, reward, termination,
+prioritized sampling) on top of the oracle's physics; Bullet's own numerics stay unpinned (no Bullet here)."""
+import ctypes as C
+import sys
+import types
+from collections import OrderedDict
+
+import numpy as np
+
+LEG_LINKS = [0, 1, 2, 5, 6, 7, 10, 11, 12, 15, 16, 17]
+FOOT_LINKS = [3, 8, 13, 18]
+JOINT_NAMES = []
+for leg in ("FR", "FL", "HR", "HL"):
+    JOINT_NAMES += ["joint_%s1" % leg, "joint_%s2" % leg, "joint_%s3" % leg, "joint_%s4" % leg, "joint_%sW" % leg]
+JOINT_NAMES += ["joint_front_handle", "joint_hind_handle"]
+
+
+class _Body:
+    def __init__(self, kind):
+        self.kind = kind
+        self.state = np.zeros(37)
+        self.state[6] = 1.0
+        self.dirty = True
+        self.tau = np.zeros(12)
+
+
+class FakeBulletClient:
+    # constants the reference touches
+    GUI, DIRECT = 1, 2
+    URDF_MAINTAIN_LINK_ORDER, URDF_USE_SELF_COLLISION, URDF_ENABLE_CACHED_GRAPHICS_SHAPES = 1, 2, 4
+    URDF_USE_SELF_COLLISION_EXCLUDE_ALL_PARENTS = 8
+    POSITION_CONTROL, TORQUE_CONTROL = 2, 3
+    ACTIVATION_STATE_SLEEP, ACTIVATION_STATE_ENABLE_SLEEPING, ACTIVATION_STATE_DISABLE_WAKEUP = 1, 2, 4
+    COV_ENABLE_RENDERING, COV_ENABLE_GUI, COV_ENABLE_SINGLE_STEP_RENDERING = 1, 2, 3
+    GEOM_BOX, STATE_LOGGING_VIDEO_MP4 = 3, 4
+
+    oracle_engine = None      # VecEngine over libllq_cpu.so with n_envs = 1, set by the generator
+    call_log = None
+
+    def __init__(self, connection_mode=None):
+        self.bodies = []
+        self.connected = True
+        eng = FakeBulletClient.oracle_engine
+        self._lib = eng.lib.lib
+        self._h = eng._h
+        for f in ("llq_oracle_get_state64", "llq_oracle_set_state64", "llq_oracle_substep", "llq_oracle_foot_positions"):
+            getattr(self._lib, f).restype = C.c_int
+
+    # ---- model loading
+    def loadURDF(self, path, basePosition=None, baseOrientation=None, flags=0, globalScaling=1.0, useFixedBase=False):
+        if path.endswith("max.urdf"):
+            b = _Body("kinematic" if useFixedBase else "dynamic")
+            if basePosition is not None:
+                b.state[0:3] = basePosition
+            if baseOrientation is not None:
+                b.state[3:7] = baseOrientation
+        else:
+            b = _Body("static")
+        self.bodies.append(b)
+        return len(self.bodies) - 1
+
+    def getNumJoints(self, uid):
+        return 22
+
+    def getJointInfo(self, uid, j):
+        return (j, JOINT_NAMES[j].encode("utf-8"))
+
+    def _noop(self, *a, **k):
+        return None
+    setCollisionFilterGroupMask = changeVisualShape = changeDynamics = setGravity = _noop
+    setPhysicsEngineParameter = setTimeStep = configureDebugVisualizer = resetDebugVisualizerCamera = _noop
+
+    def setJointMotorControlArray(self, bodyUniqueId, jointIndices, controlMode, forces=None, **kw):
+        if controlMode == self.TORQUE_CONTROL:
+            assert list(jointIndices) == LEG_LINKS
+            self.bodies[bodyUniqueId].tau = np.asarray(forces, dtype=np.float64).copy()
+
+    # ---- state access
+    def resetBasePositionAndOrientation(self, uid, pos, orn):
+        b = self.bodies[uid]
+        b.state[0:3], b.state[3:7], b.dirty = pos, orn, True
+
+    def resetBaseVelocity(self, uid, lin, ang):
+        b = self.bodies[uid]
+        b.state[7:10], b.state[10:13], b.dirty = lin, ang, True
+
+    def resetJointState(self, uid, jointIndex, pos, vel=0.0):
+        b = self.bodies[uid]
+        d = LEG_LINKS.index(jointIndex)
+        b.state[13 + d], b.state[25 + d], b.dirty = pos, vel, True
+
+    def getBasePositionAndOrientation(self, uid):
+        s = self.bodies[uid].state
+        return tuple(s[0:3]), tuple(s[3:7])
+
+    def getBaseVelocity(self, uid):
+        s = self.bodies[uid].state
+        return tuple(s[7:10]), tuple(s[10:13])
+
+    def getJointStates(self, uid, indices):
+        s = self.bodies[uid].state
+        return [(s[13 + LEG_LINKS.index(j)], s[25 + LEG_LINKS.index(j)], (0.0,) * 6, 0.0) for j in indices]
+
+    def getLinkStates(self, uid, indices, computeForwardKinematics=False, computeLinkVelocity=False):
+        assert list(indices) == FOOT_LINKS
+        st = np.ascontiguousarray(self.bodies[uid].state, dtype=np.float64)
+        out = np.zeros(12)
+        rc = self._lib.llq_oracle_foot_positions(self._h, st.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+        assert rc == 0
+        z3 = (0.0, 0.0, 0.0)
+        return [(tuple(out[3 * i:3 * i + 3]), (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, z3) for i in range(4)]
+
+    def getContactPoints(self, **kw):
+        return []
+
+    # ---- the physics step
+    def stepSimulation(self):
+        for b in self.bodies:
+            if b.kind != "dynamic":
+                continue
+            if b.dirty:
+                st = np.ascontiguousarray(b.state, dtype=np.float64)
+                assert self._lib.llq_oracle_set_state64(self._h, 0, st.ctypes.data_as(C.c_void_p)) == 0
+                b.dirty = False
+            tau = np.ascontiguousarray(b.tau, dtype=np.float64)
+            assert self._lib.llq_oracle_substep(self._h, 0, tau.ctypes.data_as(C.c_void_p)) == 0
+            out = np.zeros(37)
+            assert self._lib.llq_oracle_get_state64(self._h, 0, out.ctypes.data_as(C.c_void_p)) == 0
+            b.state = out
+            b.tau = np.zeros(12)          # Bullet clears applied torques after every step
+
+    def isConnected(self):
+        return 0
+
+    def disconnect(self):
+        self.connected = False
+
+
+def install():
+    """Register the fake modules; returns the FakeBulletClient class."""
+    from lifelike_agility_and_play_b200 import spaces as myspaces
+
+    pb = types.ModuleType("pybullet")
+    for k in dir(FakeBulletClient):
+        if k.isupper():
+            setattr(pb, k, getattr(FakeBulletClient, k))
+    sys.modules["pybullet"] = pb
+    pbu = types.ModuleType("pybullet_utils")
+    bc = types.ModuleType("pybullet_utils.bullet_client")
+    bc.BulletClient = FakeBulletClient
+    pbu.bullet_client = bc
+    sys.modules["pybullet_utils"], sys.modules["pybullet_utils.bullet_client"] = pbu, bc
+
+    gym = types.ModuleType("gym")
+
+    class Env:
+        pass
+
+    class Wrapper:
+        def __init__(self, env):
+            self.env = env
+
+        def step(self, action):
+            return self.env.step(action)
+
+        def __getattr__(self, name):
+            return getattr(self.env, name)
+    gym.Env, gym.Wrapper = Env, Wrapper
+    sp = types.ModuleType("gym.spaces")
+    sp.Box, sp.Dict, sp.Tuple, sp.Discrete = myspaces.Box, myspaces.Dict, myspaces.Tuple, myspaces.Discrete
+    gym.spaces = sp
+    sys.modules["gym"], sys.modules["gym.spaces"] = gym, sp
+
+    tl = types.ModuleType("tleague")
+    tlu = types.ModuleType("tleague.utils")
+    lg = types.ModuleType("tleague.utils.logger")
+    lg.log = lambda *a, **k: None
+    tlu.logger = lg
+    tl.utils = tlu
+    sys.modules["tleague"], sys.modules["tleague.utils"], sys.modules["tleague.utils.logger"] = tl, tlu, lg
+    return FakeBulletClient
