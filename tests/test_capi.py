@@ -1,0 +1,146 @@
+"""The C-ABI boundary: exported symbols, loud failure without a GPU, call-order errors, gym surface."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from lifelike_agility_and_play_b200 import _capi as capi
+from conftest import HAVE_CUDA, ROOT
+
+
+def _declared():
+    txt = open(os.path.join(ROOT, "include", "llq.h")).read()
+    return sorted(set(re.findall(r"\b(llq_\w+)\s*\(", txt)) - {"llq_config", "llq_engine"})
+
+
+def test_both_libraries_export_every_declared_symbol(built):
+    names = _declared()
+    assert len(names) >= 17
+    from oracle import oracle
+    for path in (capi.CUDA_LIB_PATH, oracle.LIB_PATH):
+        lib = ctypes.CDLL(path)
+        for n in names:
+            assert hasattr(lib, n), "%s does not export %s" % (path, n)
+
+
+def test_config_struct_matches_header(built, oracle_lib):
+    cfg = oracle_lib.default_config()
+    assert cfg.struct_size == ctypes.sizeof(capi.LlqConfig)
+    cuda = capi.LlqLibrary(capi.CUDA_LIB_PATH)
+    c2 = cuda.default_config()
+    assert cuda.is_cuda and not oracle_lib.is_cuda and cuda.abi == oracle_lib.abi == 1
+    for f, _ in capi.LlqConfig._fields_:
+        assert getattr(cfg, f) == getattr(c2, f), f
+    assert (cfg.substeps, cfg.solver_iters, cfg.kp, cfg.kd, cfg.max_tau) == (10, 10, 50.0, 0.5, 18.0)
+    assert cfg.gravity_z == -9.80665 and cfg.sim_dt == 1 / 500.0
+
+
+@pytest.mark.skipif(HAVE_CUDA, reason="needs a host without a GPU")
+def test_cuda_engine_fails_loudly_without_gpu(built, blob, small_mocap):
+    """No silent CPU fallback on the product path."""
+    with pytest.raises(capi.LlqError) as ei:
+        capi.VecEngine(capi.load_cuda_library(), 4, blob, small_mocap)
+    assert ei.value.code == -3 and "CUDA" in str(ei.value)
+
+
+def test_call_order_and_argument_errors(make_oracle, oracle_lib, blob, small_mocap):
+    eng = make_oracle(2)
+    with pytest.raises(capi.LlqError) as ei:
+        eng.step(np.zeros((2, 12), np.float32))            # step before reset
+    assert ei.value.code == -4
+    eng.reset()
+    with pytest.raises(ValueError):
+        eng.step(np.zeros((3, 12), np.float32))
+    with pytest.raises(capi.LlqError):
+        eng.reset_to(99, 0.1)
+    with pytest.raises(capi.LlqError):
+        eng.reset_to(0, 1e9)
+    with pytest.raises(capi.LlqError):
+        capi.VecEngine(oracle_lib, 0, blob, small_mocap)
+    with pytest.raises(capi.LlqError):
+        capi.VecEngine(oracle_lib, 1, blob[:-3], small_mocap)
+
+
+def test_state_roundtrip_and_counters(make_oracle):
+    eng = make_oracle(5, seed=1)
+    eng.reset()
+    st = eng.get(capi.F_STATE)
+    eng.set(capi.F_STATE, st)
+    assert np.array_equal(eng.get(capi.F_STATE), st)
+    o, r, d = eng.step(np.zeros((5, 12), np.float32))
+    assert o.shape == (5, 207) and r.shape == (5,) and d.dtype == np.uint8
+    assert eng.counters()[0] == 5
+    assert np.all(eng.get(capi.F_EPISODE_STEPS) == 1)
+
+
+def _tracking_cfg(mocap):
+    return {'arena_id': 'LeggedRobotTracking', 'render': False, 'data_path': '', 'mocap': mocap, 'control_freq': 50.0,
+            'prop_type': ['joint_pos', 'joint_vel', 'root_ang_vel_loc', 'root_lin_vel_loc', 'e_g'],
+            'prioritized_sample_factor': 3.0, 'set_obstacle': False, 'kp': 50.0, 'kd': 0.5, 'max_tau': 18,
+            'reward_weights': {'joint_pos': 0.3, 'joint_vel': 0.05, 'end_effector': 0.1, 'root_pose': 0.5, 'root_vel': 0.05}}
+
+
+def _drive(env):
+    """The loop of test_scripts/primitive_level/test_primitive_level_env.py:61-96, head-less, random policy."""
+    ob_space, ac_space = env.observation_space, env.action_space
+    obs = env.reset(inter_kwargs={})
+    assert isinstance(obs, tuple) and list(obs[0].keys()) == ['prop', 'prop_a', 'future']
+    assert [obs[0][k].shape for k in obs[0]] == [(99,), (36,), (72,)]
+    rng = np.random.default_rng(0)
+    n_done = 0
+    for t in range(120):
+        act = (0.1 * rng.standard_normal(12)).astype(np.float32)
+        obs, rwd, done, info = env.step([act])
+        assert isinstance(rwd, tuple) and isinstance(done, bool) and isinstance(info, dict)
+        assert 0.0 <= rwd[0] <= 1.0 + 1e-6
+        if done:
+            n_done += 1
+            obs = env.reset()
+    return ob_space, ac_space, n_done
+
+
+def test_gym_surface_on_oracle(monkeypatch, oracle_lib, small_mocap):
+    """Host logic of the drop-in factories (CPE:21-64,143-147), exercised on the CPU by swapping the engine factory."""
+    from lifelike_agility_and_play_b200.sim_envs import create_envs, primitive_level_env as ple
+    monkeypatch.setattr(ple, "engine_factory", lambda n, blob, mocap, **cfg: capi.VecEngine(oracle_lib, n, blob, mocap, **{k: v for k, v in cfg.items() if k != "device"}))
+    env = create_envs.create_tracking_game(**_tracking_cfg(small_mocap))
+    ob, ac, _ = _drive(env)
+    assert len(ob.spaces) == 1 and list(ob.spaces[0].spaces.keys()) == ['prop', 'prop_a', 'future']
+    assert ob.spaces[0].spaces['prop'].shape == (99,) and ac.spaces[0].shape == (12,)
+    env.close()
+    env2 = create_envs.create_tracking_env(**_tracking_cfg(small_mocap))
+    assert list(env2.observation_space.spaces.keys()) == ['prop', 'prop_a', 'future'] and env2.action_space.shape == (12,)
+    env2.close()
+    with pytest.raises(AssertionError):
+        create_envs.create_tracking_game(**dict(_tracking_cfg(small_mocap), arena_id="nope"))          # CPE:22-25
+    with pytest.raises(TypeError):
+        create_envs.create_tracking_game(**dict(_tracking_cfg(small_mocap), prop_type=""))             # PLE:112-113
+    with pytest.raises(NotImplementedError):
+        create_envs.create_playground_game(arena_id="Playground")
+
+
+@pytest.mark.gpu
+def test_gym_surface_on_cuda(small_mocap):
+    from lifelike_agility_and_play_b200.sim_envs import create_envs
+    env = create_envs.create_tracking_game(**_tracking_cfg(small_mocap))
+    _drive(env)
+    env.close()
+
+
+def test_mocap_loader_roundtrip(tmp_path, small_mocap):
+    """Reference on-disk format (ML:19-46): JSON per clip, sorted file order."""
+    import json
+    from lifelike_agility_and_play_b200.mocap import load_mocap
+    for i in (2, 0, 1):
+        with open(tmp_path / ("clip_%02d.txt" % i), "w") as f:
+            json.dump({"FrameDuration": small_mocap.frame_dt, "LegOrder": ["FR", "FL", "HR", "HL"], "Frames": small_mocap.clip(i).tolist()}, f)
+    (tmp_path / "notes.md").write_text("ignored")
+    t = load_mocap(str(tmp_path))
+    assert t.n_clips == 3 and t.names == ["clip_00.txt", "clip_01.txt", "clip_02.txt"]
+    assert np.array_equal(t.clip(1), small_mocap.clip(1)) and t.margin() == 125
+    rep = t.validation_report(lower=np.full(12, -5.0), upper=np.full(12, 5.0))
+    assert rep[0]["limit_violations"] == 0 and rep[0]["quat_norm_err"] < 1e-9
+    with pytest.raises(FileNotFoundError):
+        load_mocap(str(tmp_path / "missing"))

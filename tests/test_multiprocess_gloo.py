@@ -1,0 +1,68 @@
+"""N>1 host path on CPU: two gloo ranks shard the envs (oracle engines standing in for the per-GPU engines), fill
+trajectory slabs and gather them to the learner rank; the result must equal one process stepping the whole batch."""
+import os
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+T, N_PER, WORLD = 5, 6, 2
+
+
+def _actions(t, n_global):
+    rng = np.random.default_rng(100 + t)
+    return (0.1 * rng.standard_normal((n_global, 12))).astype(np.float32)
+
+
+def _rollout(rank, world, n_per, slab):
+    from lifelike_agility_and_play_b200.model.compile_model import load_model_blob
+    from lifelike_agility_and_play_b200.mocap import synthetic_mocap
+    from lifelike_agility_and_play_b200.parallel import shard_offset
+    from oracle import oracle
+    eng = oracle.make_engine(n_per, load_model_blob(), synthetic_mocap(6, seed=3, min_frames=380, max_frames=700),
+                             seed=99, global_env_offset=shard_offset(rank, n_per if world > 1 else 0), num_threads=1)
+    eng.reset()
+    for t in range(T):
+        a = _actions(t, N_PER * WORLD)[rank * n_per:(rank + 1) * n_per] if world > 1 else _actions(t, N_PER * WORLD)
+        obs, rew, done = eng.step(a)
+        slab.record(t, torch.from_numpy(a), torch.from_numpy(rew), torch.from_numpy(done.astype(np.float32)), obs=torch.from_numpy(obs))
+    eng.close()
+
+
+def _worker(rank, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from lifelike_agility_and_play_b200.parallel import TrajectorySlab
+    slab = TrajectorySlab(T, N_PER, "cpu")
+    _rollout(rank, WORLD, N_PER, slab)
+    out = slab.gather_to_learner(dst=0)
+    if rank == 0:
+        q.put(torch.cat(out, dim=1).numpy())
+    else:
+        assert out is None
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_two_rank_shards_gather_equals_single_process(built):
+    from lifelike_agility_and_play_b200.parallel import TrajectorySlab, TRAJ_WIDTH
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 29500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_worker, args=(r, port, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    gathered = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    ref = TrajectorySlab(T, N_PER * WORLD, "cpu")
+    _rollout(0, 1, N_PER * WORLD, ref)
+    assert gathered.shape == (T, N_PER * WORLD, TRAJ_WIDTH)
+    assert np.array_equal(gathered, ref.buf.numpy()), "sharded rollout differs from the single-process rollout"
