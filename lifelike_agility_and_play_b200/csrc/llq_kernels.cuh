@@ -497,7 +497,23 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
 
     // ---------------- collision: foot sphere vs plane z = 0 on the pre-step pose
     const V3 nb = V3{R.a20, R.a21, R.a22};               // world z in base coords
-    const float dist = (float)pz + dot(nb, fb) - L.foot_r;
+    // The foot clearance feeds Bullet's speculative-contact target (-penetration/dt): a 1e-7 m rounding error becomes
+    // 5e-5 m/s.  Evaluate just this scalar (height of the foot centre) in fp64 from the fp32 joint sines/cosines.
+    float dist;
+    {
+      const double qx = qp.x, qy = qp.y, qz = qp.z, qw = qp.w;
+      const double nx = 2.0 * (qx * qz - qy * qw), ny = 2.0 * (qy * qz + qx * qw), nz = 1.0 - 2.0 * (qx * qx + qy * qy);
+      const double dc1 = kc1, ds1 = ks1, dc2 = kc2, ds2 = ks2, dc3 = jc[2].c, ds3 = jc[2].s;
+      // foot in shank frame -> thigh frame -> hip frame -> base (same chain as fb, in double)
+      double x = L.foot[0], y = L.foot[1], z = L.foot[2], t;
+      t = dc3 * x + ds3 * z; z = -ds3 * x + dc3 * z; x = t;            // Ry(theta3)
+      x += (double)r[2].x; y += (double)r[2].y; z += (double)r[2].z;
+      t = dc2 * x + ds2 * z; z = -ds2 * x + dc2 * z; x = t;            // Ry(theta2)
+      x += (double)r[1].x; y += (double)r[1].y; z += (double)r[1].z;
+      t = dc1 * y - ds1 * z; z = ds1 * y + dc1 * z; y = t;             // Rx(q1)
+      x += (double)r[0].x; y += (double)r[0].y; z += (double)r[0].z;
+      dist = (float)(pz + nx * x + ny * y + nz * z - (double)L.foot_r);
+    }
     const bool contact = dist < P.breaking;
     if (!contact) warm = 0.f;
     // joint-limit rows (btMultiBodyJointLimitConstraint: a row exists only while the limit is violated)

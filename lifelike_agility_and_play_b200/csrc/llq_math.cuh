@@ -127,9 +127,16 @@ LLQ_DI Q4 rotvec_q(V3 r) {
   return Q4{scale * r.x, scale * r.y, scale * r.z, cs};
 }
 
-// 6x6 symmetric positive definite: packed lower Cholesky factor L (row-major lower triangle, 21 entries)
-struct Chol6 { float l[21]; };
+// 6x6 symmetric positive definite: packed lower Cholesky factor L (row-major lower triangle, 21 entries).
+// LLQ_CHOL_T selects the arithmetic of the factorisation and of the triangular solves (float by default; B200 runs
+// fp64 FMA at half the fp32 rate, so -DLLQ_CHOL_T=double is affordable for these ~250 flops per sub-step).
+#ifndef LLQ_CHOL_T
+#define LLQ_CHOL_T float
+#endif
+typedef LLQ_CHOL_T chol_t;
+struct Chol6 { chol_t l[21]; };
 LLQ_DI constexpr int tri(int i, int j) { return i * (i + 1) / 2 + j; }  // i >= j
+LLQ_DI chol_t cfma(chol_t a, chol_t b, chol_t c) { return sizeof(chol_t) == 8 ? (chol_t)fma((double)a, (double)b, (double)c) : (chol_t)fmaf((float)a, (float)b, (float)c); }
 // m: packed lower triangle of the symmetric matrix (same indexing)
 LLQ_DI Chol6 chol6(const float (&m)[21]) {
   Chol6 c;
@@ -137,52 +144,56 @@ LLQ_DI Chol6 chol6(const float (&m)[21]) {
   for (int i = 0; i < 6; i++) {
 #pragma unroll
     for (int j = 0; j <= i; j++) {
-      float s = m[tri(i, j)];
+      chol_t s = (chol_t)m[tri(i, j)];
 #pragma unroll
-      for (int k = 0; k < j; k++) s = fmaf(-c.l[tri(i, k)], c.l[tri(j, k)], s);
-      if (i == j) c.l[tri(i, i)] = 1.0f / sqrtf(s);   // store the reciprocal of the diagonal
+      for (int k = 0; k < j; k++) s = cfma(-c.l[tri(i, k)], c.l[tri(j, k)], s);
+      if (i == j) c.l[tri(i, i)] = sizeof(chol_t) == 8 ? (chol_t)rsqrt((double)s) : (chol_t)(1.0f / sqrtf((float)s));   // reciprocal of the diagonal
       else c.l[tri(i, j)] = s * c.l[tri(j, j)];
     }
   }
   return c;
 }
-// solve (L L^T) x = b ; diagonal entries of c hold 1/L_ii
-LLQ_DI void chol6_solve(const Chol6& c, const float (&b)[6], float (&x)[6]) {
-  float y[6];
-#pragma unroll
-  for (int i = 0; i < 6; i++) {
-    float s = b[i];
-#pragma unroll
-    for (int k = 0; k < i; k++) s = fmaf(-c.l[tri(i, k)], y[k], s);
-    y[i] = s * c.l[tri(i, i)];
-  }
-#pragma unroll
-  for (int i = 5; i >= 0; i--) {
-    float s = y[i];
-#pragma unroll
-    for (int k = i + 1; k < 6; k++) s = fmaf(-c.l[tri(k, i)], x[k], s);
-    x[i] = s * c.l[tri(i, i)];
-  }
-}
-
-// forward substitution only: y = L^-1 b
+// forward substitution: y = L^-1 b
 LLQ_DI void chol6_fwd(const Chol6& c, const float (&b)[6], float (&y)[6]) {
+  chol_t t[6];
 #pragma unroll
   for (int i = 0; i < 6; i++) {
-    float s = b[i];
+    chol_t s = (chol_t)b[i];
 #pragma unroll
-    for (int k = 0; k < i; k++) s = fmaf(-c.l[tri(i, k)], y[k], s);
-    y[i] = s * c.l[tri(i, i)];
+    for (int k = 0; k < i; k++) s = cfma(-c.l[tri(i, k)], t[k], s);
+    t[i] = s * c.l[tri(i, i)];
+    y[i] = (float)t[i];
   }
 }
-// backward substitution only: x = L^-T y
+// backward substitution: x = L^-T y
 LLQ_DI void chol6_bwd(const Chol6& c, const float (&y)[6], float (&x)[6]) {
+  chol_t t[6];
 #pragma unroll
   for (int i = 5; i >= 0; i--) {
-    float s = y[i];
+    chol_t s = (chol_t)y[i];
 #pragma unroll
-    for (int k = i + 1; k < 6; k++) s = fmaf(-c.l[tri(k, i)], x[k], s);
-    x[i] = s * c.l[tri(i, i)];
+    for (int k = i + 1; k < 6; k++) s = cfma(-c.l[tri(k, i)], t[k], s);
+    t[i] = s * c.l[tri(i, i)];
+    x[i] = (float)t[i];
+  }
+}
+// solve (L L^T) x = b
+LLQ_DI void chol6_solve(const Chol6& c, const float (&b)[6], float (&x)[6]) {
+  chol_t t[6], u[6];
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    chol_t s = (chol_t)b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s = cfma(-c.l[tri(i, k)], t[k], s);
+    t[i] = s * c.l[tri(i, i)];
+  }
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    chol_t s = t[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) s = cfma(-c.l[tri(k, i)], u[k], s);
+    u[i] = s * c.l[tri(i, i)];
+    x[i] = (float)u[i];
   }
 }
 

@@ -51,38 +51,41 @@ def test_reset_parity(make_cuda, make_oracle):
 
 
 def test_teacher_forced_step_parity(make_cuda, make_oracle):
-    """>= 1e5 (state, action) pairs when run with LLQ_PARITY_STEPS=64; default 16384 x 8 = 1.3e5 sub-steps worth."""
-    n, steps = 2048, 8
+    """T2: identical (state, action) into both engines, one full policy step (10 sub-steps) each, 2048 x 12 = 24.5k pairs
+    by default (LLQ_PARITY_STEPS raises it; 50 steps = 1e5 pairs).  Requirements:
+      * >= 99.9 % of ALL env-steps within 1e-4 relative (obs blocks, state, reward), done flags equal;
+      * every env-step that exceeds 1e-4 sits within NEAR_BRANCH of a discontinuity of Bullet's step (joint-limit row
+        appears/disappears, contact makes/breaks) according to the oracle's decision margin;
+      * nothing outside the fp32-ambiguous band (margin > MARGIN_OK) deviates by more than 5e-3."""
+    import os
+    n, steps = 2048, int(os.environ.get("LLQ_PARITY_STEPS", 12))
+    NEAR_BRANCH = 2.5e-4
     gpu, cpu = make_cuda(n, seed=5), make_oracle(n, seed=5)
     gpu.reset(); cpu.reset()
     rng = np.random.default_rng(0)
-    tot = ok = excluded = 0
-    worst = 0.0
-    rew_worst = 0.0
+    E, M, ER, DD = [], [], [], []
     for t in range(steps):
         a = np.clip(MU_A + SIGMA_A * rng.standard_normal((n, 12)).astype(np.float32), -1, 1).astype(np.float32)
         teacher_force(gpu, cpu)
         og, rg, dg = gpu.step(a)
         oc, rc, dc = cpu.step(a)
-        margin = cpu.get(capi.F_DECISION_MARGIN)
-        e = np.maximum.reduce([blockrel(og[:, :99], oc[:, :99]), blockrel(og[:, 135:], oc[:, 135:]),
-                               blockrel(gpu.get(capi.F_STATE), cpu.get(capi.F_STATE))])
-        er = np.abs(rg - rc) / np.maximum(1e-2, np.abs(rc))
         assert np.array_equal(og[:, 99:135], oc[:, 99:135])                       # action history is copied, not computed
-        safe = margin > MARGIN_OK
-        tot += n; excluded += int((~safe).sum())
-        assert e[safe].max() < TOL, "obs/state deviate at a step with a clear branch margin: %g" % e[safe].max()
-        assert er[safe].max() < TOL, "reward deviates: %g" % er[safe].max()
-        assert np.array_equal(dg[safe], dc[safe])
-        ok += int((e < TOL).sum())
-        worst = max(worst, float(e[safe].max())); rew_worst = max(rew_worst, float(er[safe].max()))
+        E.append(np.maximum.reduce([blockrel(og[:, :99], oc[:, :99]), blockrel(og[:, 135:], oc[:, 135:]),
+                                    blockrel(gpu.get(capi.F_STATE), cpu.get(capi.F_STATE))]))
+        ER.append(np.abs(rg - rc) / np.maximum(1e-2, np.abs(rc)))
+        M.append(cpu.get(capi.F_DECISION_MARGIN)); DD.append(dg != dc)
         # envs that finished are re-seeded identically on both sides so the sweep keeps covering fresh states
         m = dc.astype(np.uint8)
         if m.any():
             cpu.reset(m); gpu.reset(m)
-    assert excluded < 0.02 * tot, "too many branch-ambiguous samples: %d of %d" % (excluded, tot)
-    assert ok >= 0.99 * tot
-    print("teacher-forced: %d env-steps, %d branch-ambiguous excluded, worst rel err obs/state %.2e reward %.2e" % (tot, excluded, worst, rew_worst))
+    e, er, m, dd = np.concatenate(E), np.concatenate(ER), np.concatenate(M), np.concatenate(DD)
+    bad = (e >= TOL) | (er >= TOL) | dd
+    print("teacher-forced: %d env-steps; rel err percentiles 50/99/99.9/max = %.1e %.1e %.1e %.1e; reward max %.1e; "
+          "%d above 1e-4 (margins %s)" % (e.size, np.percentile(e, 50), np.percentile(e, 99), np.percentile(e, 99.9), e.max(),
+                                         er.max(), int(bad.sum()), ["%.1e" % x for x in m[bad][:8]]))
+    assert bad.mean() <= 1e-3, "more than 0.1%% of env-steps deviate by > 1e-4: %d of %d" % (bad.sum(), bad.size)
+    assert np.all(m[bad] < NEAR_BRANCH), "a deviation > 1e-4 occurred away from any branch of the step: margins %s" % m[bad]
+    assert e[m > MARGIN_OK].max() < 5e-3
     cg, cc = gpu.counters(), cpu.counters()
     assert abs(int(cg[2]) - int(cc[2])) <= 0.002 * cc[2] + 3 and abs(int(cg[3]) - int(cc[3])) <= 0.02 * cc[3] + 3   # rows solved
 
@@ -119,7 +122,7 @@ def test_auto_reset_and_prioritized_table(make_cuda, make_oracle):
         og, rg, dg = gpu.step(a); oc, rc, dc = cpu.step(a)
         margin = cpu.get(capi.F_DECISION_MARGIN)
         same = dg == dc
-        assert same[margin > MARGIN_OK].all()
+        assert same[margin > 2.5e-4].all()
         finished += int(dc.sum())
         if same.all():
             assert np.allclose(gpu.get(capi.F_AVG_REWARD), cpu.get(capi.F_AVG_REWARD), rtol=1e-4, atol=1e-6)
