@@ -15,13 +15,14 @@
 //   _prepare_obs/_compute_reward/_check_terminate   primitive_level_env.py:276-426
 #pragma once
 #include "llq_math.cuh"
+#include <cuda_pipeline.h>
 #include <stdint.h>
 
 namespace llq {
 
 constexpr int kObsDim = 207, kPropDim = 33, kActDim = 12, kStateDim = 37;
 constexpr int kNewObs = 120;
-constexpr int kRowFloats = 36 + 18 + 144;  // per-lane floats of the constraint-row workspace in shared memory  // floats staged per env: prop 33 | action 12 | future 72 (+3 pad)
+constexpr int kRowFloats = 153;  // per-lane floats of the constraint-row workspace in shared memory (Yc 18 | Yl 18 | Ul 9 | Acl 36 | Alc 36 | All 36)  // floats staged per env: prop 33 | action 12 | future 72 (+3 pad)
 
 struct DampItem { float m; float c[3]; float Ic[6]; };
 struct JointConst {
@@ -32,7 +33,7 @@ struct JointConst {
 };
 struct LegConst { JointConst j[3]; float foot[3]; float foot_r; float pad[4]; };
 struct BaseConst { float qI[4]; float m; float h[3]; float I[6]; int nd; DampItem d[3]; };
-struct ModelConst { BaseConst base; LegConst leg[4]; };
+struct alignas(16) ModelConst { BaseConst base; LegConst leg[4]; };
 
 struct MocapFrame { double x, y, z, pad; float quat[4]; float q[12]; };  // 96 B, 16-byte aligned
 
@@ -288,9 +289,12 @@ LLQ_DI ObsCtx build_obs_new(const MocapDev& mc, const StepParams& P, const Model
 // mode 0 (step):  prop = [old[33:99], new] ; prop_a = [old[12:36], act] ; future = new
 // mode 1 (reset): prop = [new, new, new]  ; prop_a = 0                 ; future = new      (PLE:282-290)
 // `do_row` (bit e of a warp-uniform mask) selects which of the 8 rows are written.
-LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const float* snew_warp, int env0, int n_envs, int mode,
-                          unsigned row_mask) {
+constexpr int kHist = 90;   // per-env history carry: prop[33:99] (66) | prop_a[12:36] (24)
+
+LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const float* snew_warp, const float* hist_warp, int env0, int n_envs,
+                          int mode, unsigned row_mask) {
   const int lane = threadIdx.x & 31;
+#pragma unroll 4
   for (int base = 0; base < 8 * kObsDim; base += 32) {
     int idx = base + lane;
     int e = idx / kObsDim, j = idx - e * kObsDim;
@@ -298,25 +302,38 @@ LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const floa
     float v = 0.f;
     if (ok) {
       const float* sn = snew_warp + e * kNewObs;
-      float* row = obs + (size_t)(env0 + e) * kObsDim;
+      const float* hs = hist_warp + e * kHist;
       if (j < 99) {
         if (mode == 1) v = sn[j % kPropDim];
-        else v = j < 66 ? row[j + kPropDim] : sn[j - 66];
+        else v = j < 66 ? hs[j] : sn[j - 66];
       } else if (j < 135) {
         int a = j - 99;
         if (mode == 1) v = 0.f;
-        else v = a < 24 ? row[j + kActDim] : sn[kPropDim + a - 24];
+        else v = a < 24 ? hs[66 + a] : sn[kPropDim + a - 24];
       } else {
         v = sn[45 + (j - 135)];
       }
-    }
-    __syncwarp();
-    if (ok) {
       obs[(size_t)(env0 + e) * kObsDim + j] = v;
       if (obs2) obs2[(size_t)(env0 + e) * obs2_ld + j] = v;
     }
-    __syncwarp();
   }
+}
+
+// Asynchronous (cp.async) prefetch issued at kernel start; consumed after the ten sub-steps, so DRAM latency is hidden.
+LLQ_DI void prefetch_history(const float* obs, float* hist_warp, int env0, int n_envs) {
+  const int lane = threadIdx.x & 31;
+  for (int idx = lane; idx < 8 * kHist; idx += 32) {
+    int e = idx / kHist, t = idx - e * kHist;
+    int env = env0 + e < n_envs ? env0 + e : n_envs - 1;
+    int j = t < 66 ? 33 + t : 99 + 12 + (t - 66);
+    __pipeline_memcpy_async(hist_warp + idx, obs + (size_t)env * kObsDim + j, 4);
+  }
+}
+LLQ_DI void prefetch_model(const ModelConst* gmodel, ModelConst* smodel, int nthreads) {
+  static_assert(sizeof(ModelConst) % 16 == 0, "ModelConst must be a multiple of 16 bytes");
+  const float4* src = reinterpret_cast<const float4*>(gmodel);
+  float4* dst = reinterpret_cast<float4*>(smodel);
+  for (int i = threadIdx.x; i < (int)(sizeof(ModelConst) / 16); i += nthreads) __pipeline_memcpy_async(dst + i, src + i, 16);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -325,18 +342,19 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev mc, StepParams P, const ModelConst* __restrict__ gmodel,
                                                          const float* __restrict__ actions, float* obs2, long long obs2_ld,
                                                          int* __restrict__ winner) {
-  __shared__ ModelConst M;
+  __shared__ __align__(16) ModelConst M;
   __shared__ __align__(16) float s_new[BLOCK / 4][kNewObs];
-  extern __shared__ float rows_sm[];     // kRowFloats * BLOCK floats: per-lane constraint-row workspace (Y 36 | U 18 | A 144)
-  {
-    const int* src = reinterpret_cast<const int*>(gmodel);
-    int* dst = reinterpret_cast<int*>(&M);
-    for (int i = threadIdx.x; i < (int)(sizeof(ModelConst) / 4); i += BLOCK) dst[i] = src[i];
-  }
-  __syncthreads();
-
+  __shared__ __align__(16) float s_hist[BLOCK / 4][kHist];
+  extern __shared__ float rows_sm[];     // kRowFloats * BLOCK floats: per-lane constraint-row workspace
   const int tid = threadIdx.x;
   const int N = P.n_envs;
+  prefetch_model(gmodel, &M, BLOCK);
+  __pipeline_commit();
+  prefetch_history(E.obs, &s_hist[(tid & ~31) >> 2][0], (blockIdx.x * BLOCK + (tid & ~31)) >> 2, N);
+  __pipeline_commit();
+  __pipeline_wait_prior(1);              // model constants have landed; the history copy stays in flight
+  __syncthreads();
+
   const int gtid = blockIdx.x * BLOCK + threadIdx.x;
   const int env_raw = gtid >> 2;
   const int env = env_raw < N ? env_raw : N - 1;   // surplus lanes shadow the last env (they must join the shuffles)
@@ -536,15 +554,18 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dvl[3] = {0.f, 0.f, 0.f};
 
     if (warpmask) {
-      // own rows 0..2 = contact (n, t1, t2), 3..5 = joint limits.  For each row we keep its image under the ABA's
-      // L^-1 factor: y = L0^-1 Fhat (base part, 6) and u (joint part, 3).  Then  J_r M^-1 J_s^T = y_r.y_s + sum_i u_ri u_si / D_i
-      // (second term only for rows on the same leg) -- no per-row down passes are needed.
-      float bq[6], rhs[6], invd[6], lam[6];
-#pragma unroll
-      for (int t = 0; t < 6; t++) { bq[t] = 0.f; rhs[t] = 0.f; invd[t] = 0.f; lam[t] = 0.f; }
-      float* Ysm = rows_sm + tid;                         // Y[r][t] at Ysm[(r*6+t)*BLOCK]
-      float* Usm = rows_sm + 36 * BLOCK + tid;            // U[r][i] at Usm[(r*3+i)*BLOCK]
-      float* Asm = rows_sm + 54 * BLOCK + tid;            // A[r][s] at Asm[(r*24+s)*BLOCK]
+      // Own rows: 0..2 = contact (n, t1, t2) -- hot path, kept in registers, loops unrolled;
+      //           3..5 = violated joint limits -- rare path, kept in shared memory, loops rolled.
+      // For each row we keep its image under the ABA's L^-1 factor: y = L0^-1 Fhat (base part, 6) and u (joint part, 3).
+      // Then  J_r M^-1 J_s^T = y_r.y_s + sum_i u_ri u_si / D_i  (second term only for rows on the same leg), so no
+      // per-row down passes are needed; PGS only tracks b_r = J_r . (delta v) of the own rows.
+      float yc[3][6], uc[3][3], Ac[3][12];
+      float bq[3] = {0.f, 0.f, 0.f}, rhs[3] = {0.f, 0.f, 0.f}, invd[3] = {0.f, 0.f, 0.f}, lam[3] = {0.f, 0.f, 0.f};
+      float bl[3] = {0.f, 0.f, 0.f}, rhsl[3] = {0.f, 0.f, 0.f}, invdl[3] = {0.f, 0.f, 0.f}, laml[3] = {0.f, 0.f, 0.f};
+      // shared-memory workspace of this lane (element e of lane tid at ws[e * BLOCK])
+      float* ws = rows_sm + tid;
+      constexpr int W_YC = 0, W_YL = 18, W_UL = 36, W_ACL = 45, W_ALC = 81, W_ALL = 117;   // kRowFloats = 153
+      const int g0 = tid & ~3;
       if (any_con_warp) {
         // directions (world): n = +z, t1 = -y, t2 = +x   (btPlaneSpace1 of the plane normal), in base coords
         const V3 dirs[3] = {nb, neg(V3{R.a10, R.a11, R.a12}), V3{R.a00, R.a01, R.a02}};
@@ -554,25 +575,21 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           const V3 db = dirs[d];
           V3 Ga = cross(Pc, db), Gl = db;                 // spatial force of a unit impulse, about the base origin
           const float rel0 = dot(Ga, wbs) + dot(Gl, vbs);
-          float u[3];
-          u[2] = dot(Sa[2], Ga) + dot(Sl[2], Gl);
+          uc[d][2] = dot(Sa[2], Ga) + dot(Sl[2], Gl);
           const float j2 = dot(Sa[1], Ga) + dot(Sl[1], Gl), j1 = dot(Sa[0], Ga) + dot(Sl[0], Gl);
-          const float rel = rel0 + j1 * qd[0] + j2 * qd[1] + u[2] * qd[2];
-          float g = u[2] * Di[2];
+          const float rel = rel0 + j1 * qd[0] + j2 * qd[1] + uc[d][2] * qd[2];
+          float g = uc[d][2] * Di[2];
           Ga = fma3(-g, Ua[2], Ga); Gl = fma3(-g, Ul[2], Gl);
-          u[1] = dot(Sa[1], Ga) + dot(Sl[1], Gl);
-          g = u[1] * Di[1];
+          uc[d][1] = dot(Sa[1], Ga) + dot(Sl[1], Gl);
+          g = uc[d][1] * Di[1];
           Ga = fma3(-g, Ua[1], Ga); Gl = fma3(-g, Ul[1], Gl);
-          u[0] = dot(Sa[0], Ga) + dot(Sl[0], Gl);
-          g = u[0] * Di[0];
+          uc[d][0] = dot(Sa[0], Ga) + dot(Sl[0], Gl);
+          g = uc[d][0] * Di[0];
           Ga = fma3(-g, Ua[0], Ga); Gl = fma3(-g, Ul[0], Gl);
-          float y[6];
-          { const float bb[6] = {Ga.x, Ga.y, Ga.z, Gl.x, Gl.y, Gl.z}; chol6_fwd(ch, bb, y); }
-          float dg = u[0] * u[0] * Di[0] + u[1] * u[1] * Di[1] + u[2] * u[2] * Di[2];
+          { const float bb[6] = {Ga.x, Ga.y, Ga.z, Gl.x, Gl.y, Gl.z}; chol6_fwd(ch, bb, yc[d]); }
+          float dg = uc[d][0] * uc[d][0] * Di[0] + uc[d][1] * uc[d][1] * Di[1] + uc[d][2] * uc[d][2] * Di[2];
 #pragma unroll
-          for (int t = 0; t < 6; t++) { dg = fmaf(y[t], y[t], dg); Ysm[(d * 6 + t) * BLOCK] = y[t]; }
-#pragma unroll
-          for (int i = 0; i < 3; i++) Usm[(d * 3 + i) * BLOCK] = u[i];
+          for (int t = 0; t < 6; t++) { dg = fmaf(yc[d][t], yc[d][t], dg); ws[(W_YC + d * 6 + t) * BLOCK] = yc[d][t]; }
           invd[d] = contact ? 1.0f / dg : 0.f;
           if (d == 0) {   // btMultiBodyConstraintSolver::setupMultiBodyContactConstraint
             float pen = dist + P.slop, poserr = 0.f, velerr = -rel;
@@ -603,67 +620,114 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           { const float bb[6] = {Ga.x, Ga.y, Ga.z, Gl.x, Gl.y, Gl.z}; chol6_fwd(ch, bb, y); }
           float dg = u[0] * u[0] * Di[0] + u[1] * u[1] * Di[1] + u[2] * u[2] * Di[2];
 #pragma unroll
-          for (int t = 0; t < 6; t++) { dg = fmaf(y[t], y[t], dg); Ysm[((3 + i) * 6 + t) * BLOCK] = y[t]; }
+          for (int t = 0; t < 6; t++) { dg = fmaf(y[t], y[t], dg); ws[(W_YL + i * 6 + t) * BLOCK] = y[t]; }
 #pragma unroll
-          for (int m = 0; m < 3; m++) Usm[((3 + i) * 3 + m) * BLOCK] = u[m];
+          for (int m = 0; m < 3; m++) ws[(W_UL + i * 3 + m) * BLOCK] = u[m];
           if (dir != 0.f) {
             const float rel = dir * qd[i];
             const float pen = dir > 0.f ? q[i] - L.j[i].lower : L.j[i].upper - q[i];
-            invd[3 + i] = 1.0f / dg;
+            invdl[i] = 1.0f / dg;
             const float poserr = pen > -0.04f ? -pen * P.jerp / dt : 0.f;   // split-impulse threshold quirk
-            rhs[3 + i] = (poserr - rel) * invd[3 + i];
+            rhsl[i] = (poserr - rel) * invdl[i];
             n_limit_rows += 1;
           }
         }
       }
       __syncwarp();
-      // ---- Delassus block of the own rows against every active row of the env (y's of the other legs come through smem)
-      const int nrows = any_lim_warp ? 6 : 3;
-      const int g0 = tid & ~3;
-      const unsigned ownmask_w = __reduce_or_sync(FULL, mymask);   // own-row slots that are active on some lane of the warp
-#pragma unroll 1
-      for (int rr = 0; rr < nrows; rr++) {
-        if (!((ownmask_w >> rr) & 1u)) continue;
-        float yo[6], uo[3];
+      // ---- Delassus blocks.  contact x contact: registers, unrolled (the y's of the other legs come through smem)
+      if (any_con_warp) {
+        float ut[3][3];   // same-leg joint term  sum_i u_ri u_si / D_i  of the own contact rows
 #pragma unroll
-        for (int t = 0; t < 6; t++) yo[t] = Ysm[(rr * 6 + t) * BLOCK];
+        for (int rr = 0; rr < 3; rr++)
 #pragma unroll
-        for (int i = 0; i < 3; i++) uo[i] = Usm[(rr * 3 + i) * BLOCK] * Di[i];
-#pragma unroll 1
+          for (int sr = 0; sr < 3; sr++)
+            ut[rr][sr] = uc[rr][0] * uc[sr][0] * Di[0] + uc[rr][1] * uc[sr][1] * Di[1] + uc[rr][2] * uc[sr][2] * Di[2];
+#pragma unroll
         for (int j = 0; j < 4; j++) {
-          const float* Yj = rows_sm + g0 + j;
-          const float* Uj = rows_sm + 36 * BLOCK + g0 + j;
-          const float own = (j == k) ? 1.f : 0.f;
-#pragma unroll 1
-          for (int rs = 0; rs < nrows; rs++) {
-            if (!((warpmask >> (6 * j + rs)) & 1u)) continue;
-            float acc = own * (uo[0] * Uj[(rs * 3 + 0) * BLOCK] + uo[1] * Uj[(rs * 3 + 1) * BLOCK] + uo[2] * Uj[(rs * 3 + 2) * BLOCK]);
+          if ((warpmask >> (6 * j)) & 1u) {
+            const float* Yj = rows_sm + g0 + j;
+            const bool own = (j == k);
 #pragma unroll
-            for (int t = 0; t < 6; t++) acc = fmaf(yo[t], Yj[(rs * 6 + t) * BLOCK], acc);
-            Asm[(rr * 24 + 6 * j + rs) * BLOCK] = acc;
+            for (int sr = 0; sr < 3; sr++) {
+              float ys[6];
+#pragma unroll
+              for (int t = 0; t < 6; t++) ys[t] = Yj[(W_YC + sr * 6 + t) * BLOCK];
+#pragma unroll
+              for (int rr = 0; rr < 3; rr++) {
+                float acc = own ? ut[rr][sr] : 0.f;
+#pragma unroll
+                for (int t = 0; t < 6; t++) acc = fmaf(yc[rr][t], ys[t], acc);
+                Ac[rr][3 * j + sr] = acc;
+              }
+            }
+          }
+        }
+      }
+      // blocks that involve limit rows: shared memory, rolled loops (rare path)
+      if (any_lim_warp) {
+#pragma unroll 1
+        for (int jl = 0; jl < 4; jl++) {
+          const bool own = (jl == k);
+#pragma unroll 1
+          for (int il = 0; il < 3; il++) {
+            if (!((warpmask >> (6 * jl + 3 + il)) & 1u)) continue;       // source: limit row (jl, il)
+            float ys[6], us[3];
+#pragma unroll
+            for (int t = 0; t < 6; t++) ys[t] = rows_sm[(W_YL + il * 6 + t) * BLOCK + g0 + jl];
+#pragma unroll
+            for (int m = 0; m < 3; m++) us[m] = own ? rows_sm[(W_UL + il * 3 + m) * BLOCK + g0 + jl] * Di[m] : 0.f;
+#pragma unroll
+            for (int rr = 0; rr < 3; rr++) {                              // targets: own contact rows, own limit rows
+              float a1 = uc[rr][0] * us[0] + uc[rr][1] * us[1] + uc[rr][2] * us[2];
+              float a2 = ws[(W_UL + rr * 3 + 0) * BLOCK] * us[0] + ws[(W_UL + rr * 3 + 1) * BLOCK] * us[1] + ws[(W_UL + rr * 3 + 2) * BLOCK] * us[2];
+#pragma unroll
+              for (int t = 0; t < 6; t++) { a1 = fmaf(yc[rr][t], ys[t], a1); a2 = fmaf(ws[(W_YL + rr * 6 + t) * BLOCK], ys[t], a2); }
+              ws[(W_ACL + rr * 12 + 3 * jl + il) * BLOCK] = any_con_warp ? a1 : 0.f;
+              ws[(W_ALL + rr * 12 + 3 * jl + il) * BLOCK] = a2;
+            }
+          }
+          if (any_con_warp && ((warpmask >> (6 * jl)) & 1u)) {            // sources: contact rows of leg jl, targets: own limit rows
+#pragma unroll 1
+            for (int sr = 0; sr < 3; sr++) {
+              float ys[6];
+#pragma unroll
+              for (int t = 0; t < 6; t++) ys[t] = rows_sm[(W_YC + sr * 6 + t) * BLOCK + g0 + jl];
+              // u of the source contact row is only needed on its own leg, where it is uc[sr] (sr rolled -> select)
+              const float u0 = sr == 0 ? uc[0][0] : (sr == 1 ? uc[1][0] : uc[2][0]);
+              const float u1 = sr == 0 ? uc[0][1] : (sr == 1 ? uc[1][1] : uc[2][1]);
+              const float u2 = sr == 0 ? uc[0][2] : (sr == 1 ? uc[1][2] : uc[2][2]);
+#pragma unroll
+              for (int rr = 0; rr < 3; rr++) {
+                float a2 = own ? (ws[(W_UL + rr * 3 + 0) * BLOCK] * u0 * Di[0] + ws[(W_UL + rr * 3 + 1) * BLOCK] * u1 * Di[1] +
+                                  ws[(W_UL + rr * 3 + 2) * BLOCK] * u2 * Di[2]) : 0.f;
+#pragma unroll
+                for (int t = 0; t < 6; t++) a2 = fmaf(ws[(W_YL + rr * 6 + t) * BLOCK], ys[t], a2);
+                ws[(W_ALC + rr * 12 + 3 * jl + sr) * BLOCK] = a2;
+              }
+            }
           }
         }
       }
       // ---- projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration order: limits, normals, friction)
-      // bq[r] tracks J_r . (delta velocity) for the own rows; every applied impulse updates it through the Delassus column.
-#define LLQ_APPLY(col, dl_)                                                              \
-      {                                                                                  \
-        const float* Ac_ = Asm + (col) * BLOCK;                                          \
-        bq[0] = fmaf(Ac_[0 * 24 * BLOCK], dl_, bq[0]);                                   \
-        bq[1] = fmaf(Ac_[1 * 24 * BLOCK], dl_, bq[1]);                                   \
-        bq[2] = fmaf(Ac_[2 * 24 * BLOCK], dl_, bq[2]);                                   \
-        if (any_lim_warp) {                                                              \
-          bq[3] = fmaf(Ac_[3 * 24 * BLOCK], dl_, bq[3]);                                 \
-          bq[4] = fmaf(Ac_[4 * 24 * BLOCK], dl_, bq[4]);                                 \
-          bq[5] = fmaf(Ac_[5 * 24 * BLOCK], dl_, bq[5]);                                 \
-        }                                                                                \
+      // an impulse dl_ on contact column (j_, d_) of the env: own contact rows from registers, own limit rows from smem
+#define LLQ_APPLY_C(j_, d_, dl_)                                                                   \
+      {                                                                                            \
+        bq[0] = fmaf(Ac[0][3 * (j_) + (d_)], dl_, bq[0]);                                          \
+        bq[1] = fmaf(Ac[1][3 * (j_) + (d_)], dl_, bq[1]);                                          \
+        bq[2] = fmaf(Ac[2][3 * (j_) + (d_)], dl_, bq[2]);                                          \
+        if (any_lim_warp) {                                                                        \
+          bl[0] = fmaf(ws[(W_ALC + 0 * 12 + 3 * (j_) + (d_)) * BLOCK], dl_, bl[0]);                \
+          bl[1] = fmaf(ws[(W_ALC + 1 * 12 + 3 * (j_) + (d_)) * BLOCK], dl_, bl[1]);                \
+          bl[2] = fmaf(ws[(W_ALC + 2 * 12 + 3 * (j_) + (d_)) * BLOCK], dl_, bl[2]);                \
+        }                                                                                          \
       }
       if (any_con_warp) {   // warm start of the normal rows
-#pragma unroll 1
+#pragma unroll
         for (int j = 0; j < 4; j++) {
-          if (!((warpmask >> (6 * j)) & 1u)) continue;
-          const float l0 = __shfl_sync(FULL, lam[0], j, 4);
-          if ((envmask >> (6 * j)) & 1u) LLQ_APPLY(6 * j, l0)
+          if ((warpmask >> (6 * j)) & 1u) {
+            const float l0 = __shfl_sync(FULL, lam[0], j, 4);
+            if ((envmask >> (6 * j)) & 1u) LLQ_APPLY_C(j, 0, l0)
+          }
         }
       }
       const float mu = P.mu;
@@ -677,68 +741,90 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
               if (!((warpmask >> (6 * j + 3 + i)) & 1u)) continue;
               float dl = 0.f;
               if (j == k && limdir[i] != 0.f) {
-                dl = rhs[3 + i] - bq[3 + i] * invd[3 + i];
-                const float sum = lam[3 + i] + dl;
-                if (sum < 0.f) { dl = -lam[3 + i]; lam[3 + i] = 0.f; }
-                else if (sum > P.max_imp) { dl = P.max_imp - lam[3 + i]; lam[3 + i] = P.max_imp; }
-                else lam[3 + i] = sum;
+                dl = rhsl[i] - bl[i] * invdl[i];
+                const float sum = laml[i] + dl;
+                if (sum < 0.f) { dl = -laml[i]; laml[i] = 0.f; }
+                else if (sum > P.max_imp) { dl = P.max_imp - laml[i]; laml[i] = P.max_imp; }
+                else laml[i] = sum;
               }
               dl = __shfl_sync(FULL, dl, j, 4);
-              if ((envmask >> (6 * j + 3 + i)) & 1u) LLQ_APPLY(6 * j + 3 + i, dl)
+              if ((envmask >> (6 * j + 3 + i)) & 1u) {
+                const int col = 3 * j + i;
+                bl[0] = fmaf(ws[(W_ALL + 0 * 12 + col) * BLOCK], dl, bl[0]);
+                bl[1] = fmaf(ws[(W_ALL + 1 * 12 + col) * BLOCK], dl, bl[1]);
+                bl[2] = fmaf(ws[(W_ALL + 2 * 12 + col) * BLOCK], dl, bl[2]);
+                if (any_con_warp) {
+                  bq[0] = fmaf(ws[(W_ACL + 0 * 12 + col) * BLOCK], dl, bq[0]);
+                  bq[1] = fmaf(ws[(W_ACL + 1 * 12 + col) * BLOCK], dl, bq[1]);
+                  bq[2] = fmaf(ws[(W_ACL + 2 * 12 + col) * BLOCK], dl, bq[2]);
+                }
+              }
             }
           }
         }
         if (any_con_warp) {
-#pragma unroll 1
+#pragma unroll
           for (int j = 0; j < 4; j++) {   // normal rows, feet in order FR FL HR HL
-            if (!((warpmask >> (6 * j)) & 1u)) continue;
-            float dl = 0.f;
-            if (j == k && contact) {
-              dl = rhs[0] - bq[0] * invd[0];
-              const float sum = lam[0] + dl;
-              if (sum < 0.f) { dl = -lam[0]; lam[0] = 0.f; }
-              else if (sum > 1e10f) { dl = 1e10f - lam[0]; lam[0] = 1e10f; }
-              else lam[0] = sum;
-            }
-            dl = __shfl_sync(FULL, dl, j, 4);
-            if ((envmask >> (6 * j)) & 1u) LLQ_APPLY(6 * j, dl)
-          }
-#pragma unroll 1
-          for (int j = 0; j < 4; j++) {   // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
-            if (!((warpmask >> (6 * j)) & 1u)) continue;
-            float da = 0.f, db = 0.f;
-            if (j == k && contact) {
-              float sa = lam[1] + (rhs[1] - bq[1] * invd[1]), sb = lam[2] + (rhs[2] - bq[2] * invd[2]);
-              const float limit = mu * lam[0];
-              const float r2 = sa * sa + sb * sb;
-              if (r2 >= limit * limit && r2 > 0.f) {
-                const float sc = limit * rsqrtf(r2);
-                sa *= sc; sb *= sc;
+            if ((warpmask >> (6 * j)) & 1u) {
+              float dl = 0.f;
+              if (j == k && contact) {
+                dl = rhs[0] - bq[0] * invd[0];
+                const float sum = lam[0] + dl;
+                if (sum < 0.f) { dl = -lam[0]; lam[0] = 0.f; }
+                else if (sum > 1e10f) { dl = 1e10f - lam[0]; lam[0] = 1e10f; }
+                else lam[0] = sum;
               }
-              da = sa - lam[1]; db = sb - lam[2];
-              lam[1] = sa; lam[2] = sb;
+              dl = __shfl_sync(FULL, dl, j, 4);
+              if ((envmask >> (6 * j)) & 1u) LLQ_APPLY_C(j, 0, dl)
             }
-            da = __shfl_sync(FULL, da, j, 4);
-            db = __shfl_sync(FULL, db, j, 4);
-            if ((envmask >> (6 * j)) & 1u) {
-              LLQ_APPLY(6 * j + 1, da)
-              LLQ_APPLY(6 * j + 2, db)
+          }
+#pragma unroll
+          for (int j = 0; j < 4; j++) {   // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
+            if ((warpmask >> (6 * j)) & 1u) {
+              float da = 0.f, db = 0.f;
+              if (j == k && contact) {
+                float sa = lam[1] + (rhs[1] - bq[1] * invd[1]), sb = lam[2] + (rhs[2] - bq[2] * invd[2]);
+                const float limit = mu * lam[0];
+                const float r2 = sa * sa + sb * sb;
+                if (r2 >= limit * limit && r2 > 0.f) {
+                  const float sc = limit * rsqrtf(r2);
+                  sa *= sc; sb *= sc;
+                }
+                da = sa - lam[1]; db = sb - lam[2];
+                lam[1] = sa; lam[2] = sb;
+              }
+              da = __shfl_sync(FULL, da, j, 4);
+              db = __shfl_sync(FULL, db, j, 4);
+              if ((envmask >> (6 * j)) & 1u) {
+                LLQ_APPLY_C(j, 1, da)
+                LLQ_APPLY_C(j, 2, db)
+              }
             }
           }
         }
       }
-#undef LLQ_APPLY
+#undef LLQ_APPLY_C
       if (contact) warm = lam[0];
       // ---- total impulse -> velocity change: one back substitution and one down pass (base coordinates)
       float Yt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, wt[3] = {0.f, 0.f, 0.f};
+      if (contact) {
 #pragma unroll
-      for (int rr = 0; rr < 6; rr++) {
-        if ((mymask >> rr) & 1u) {
-          const float l = lam[rr];
+        for (int rr = 0; rr < 3; rr++) {
 #pragma unroll
-          for (int t = 0; t < 6; t++) Yt[t] = fmaf(l, Ysm[(rr * 6 + t) * BLOCK], Yt[t]);
+          for (int t = 0; t < 6; t++) Yt[t] = fmaf(lam[rr], yc[rr][t], Yt[t]);
 #pragma unroll
-          for (int i = 0; i < 3; i++) wt[i] = fmaf(l, Usm[(rr * 3 + i) * BLOCK], wt[i]);
+          for (int i = 0; i < 3; i++) wt[i] = fmaf(lam[rr], uc[rr][i], wt[i]);
+        }
+      }
+      if (any_lim_warp) {
+#pragma unroll
+        for (int rr = 0; rr < 3; rr++) {
+          if (limdir[rr] != 0.f) {
+#pragma unroll
+            for (int t = 0; t < 6; t++) Yt[t] = fmaf(laml[rr], ws[(W_YL + rr * 6 + t) * BLOCK], Yt[t]);
+#pragma unroll
+            for (int i = 0; i < 3; i++) wt[i] = fmaf(laml[rr], ws[(W_UL + rr * 3 + i) * BLOCK], wt[i]);
+          }
         }
       }
 #pragma unroll
@@ -873,9 +959,10 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     }
   }
   // ---- observation rows of this warp (history shift + new prop / action / future), coalesced
+  __pipeline_wait_prior(0);
   __syncwarp();
   const int warp_env0 = (blockIdx.x * BLOCK + (threadIdx.x & ~31)) >> 2;
-  emit_obs_rows(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], warp_env0, N, 0, 0xFFu);
+  emit_obs_rows(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], &s_hist[(threadIdx.x & ~31) >> 2][0], warp_env0, N, 0, 0xFFu);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -899,13 +986,10 @@ template <int BLOCK>
 __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev mc, StepParams P, const ModelConst* __restrict__ gmodel,
                                                           ResetParams RP, float* obs2, long long obs2_ld) {
   extern __shared__ double s_cdf[];            // [n_clips]
-  __shared__ ModelConst M;
+  __shared__ __align__(16) ModelConst M;
   __shared__ __align__(16) float s_new[BLOCK / 4][kNewObs];
-  {
-    const int* src = reinterpret_cast<const int*>(gmodel);
-    int* dst = reinterpret_cast<int*>(&M);
-    for (int i = threadIdx.x; i < (int)(sizeof(ModelConst) / 4); i += BLOCK) dst[i] = src[i];
-  }
+  prefetch_model(gmodel, &M, BLOCK);
+  __pipeline_commit();
   const int C = mc.n_clips;
   // ---- prioritized sampling table: every block recomputes it identically; block 0 publishes it
   for (int c = threadIdx.x; c < C; c += BLOCK) {
@@ -935,6 +1019,8 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
   }
   __syncthreads();
 
+  __pipeline_wait_prior(0);
+  __syncthreads();
   const int N = P.n_envs;
   const int gtid = blockIdx.x * BLOCK + threadIdx.x;
   const int env_raw = gtid >> 2;
@@ -1005,7 +1091,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
 #pragma unroll
   for (int e = 0; e < 8; e++) if ((wm >> (4 * e)) & 1u) rows |= 1u << e;
   const int warp_env0 = (blockIdx.x * BLOCK + (threadIdx.x & ~31)) >> 2;
-  emit_obs_rows(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], warp_env0, N, 1, rows);
+  emit_obs_rows(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], &s_new[0][0], warp_env0, N, 1, rows);
 }
 
 }  // namespace llq
