@@ -1,7 +1,7 @@
 // llq_cuda.cu -- host side of the sm_100a rollout engine and its C-ABI (include/llq.h).
 //
 // Build (see __graft_entry__.build):
-//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -Xcompiler -fPIC -shared \
+//   nvcc -gencode arch=compute_100a,code=sm_100a -lineinfo -O3 -std=c++17 -prec-div=false -prec-sqrt=false -Xcompiler -fPIC -shared \
 //        -o libllq_cuda.so llq_cuda.cu
 //
 // This file holds no physics: it owns device memory (structure-of-arrays state, mocap table, model constants),
@@ -35,7 +35,7 @@ constexpr int kPadFrames = 128;  // replicated tail frames so that a stale curso
 
 struct llq_engine {
   llq_config cfg;
-  int block = 32;
+  int block = 128;   // 4 warps per CTA kept on the same code stretch by per-sub-step barriers (instruction-cache sharing)
   cudaStream_t stream = nullptr;
   bool has_model = false, has_mocap = false, was_reset = false;
   // device
@@ -128,7 +128,7 @@ void launch_reset(llq_handle h, const llq::EnvArrays& E, const llq::ResetParams&
   switch (h->block) {
     case 32: launch_reset_t<32>(h, E, RP, obs2, ld, s); break;
     case 64: launch_reset_t<64>(h, E, RP, obs2, ld, s); break;
-    default: launch_reset_t<128>(h, E, RP, obs2, ld, s); break;
+    default: launch_reset_t<128>(h, E, RP, obs2, ld, s); break;   // the reset kernel has no use for larger blocks
   }
   h->counters[4]++;
 }
