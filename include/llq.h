@@ -37,6 +37,14 @@ extern "C" {
 #define LLQ_PROP_DIM    33   /* joint_pos12 joint_vel12 ang_vel_loc3 lin_vel_loc3 e_g3 (PLE:247-260) */
 #define LLQ_OBS_DIM     207  /* prop 3x33 | prop_a 3x12 | future 4x18 (PLE:117-121,276-297) */
 #define LLQ_MOCAP_FRAME 19   /* x y z qx qy qz qw + 12 joint angles (ML:88-96) */
+#define LLQ_OBS_DIM_EPMC 916 /* prop 99 | prop_a 36 | percep_2d 25x13 | percep_1d 128 | percep_front 25x13 | target 3
+                                (max_game_elements/playground_env.py:129-144) */
+#define LLQ_ENV_PMC  0       /* PrimitiveLevelEnv  (primitive_level_env.py) */
+#define LLQ_ENV_EPMC 1       /* PlayGroundEnv, element_id 0 = flat-ground joystick task, the shipped script default
+                                (max_game_elements/playground_env.py, train_scripts/example_epmc_train.sh:100) */
+#define LLQ_AUX_DIM  18      /* LLQ_F_AUX: counter, cmd_vary_freq, target_x, target_y, target_spd, target_angle, last_pos_diff_len,
+                                total_spd, max_spd, push_count, push_fx, push_fy, push_fz, foot_friction, push_draws, cmd_draws,
+                                yaw_accum_deg (the reference mutates its module-level init-state dict, so reset yaws accumulate: PGE:181-189), reserved */
 #define LLQ_NUM_FEET    4
 
 /* error codes */
@@ -64,6 +72,7 @@ extern "C" {
 #define LLQ_F_AVG_REWARD  9  /* double  [n_clips] PLE._avg_reward_sum (PLE:236) */
 #define LLQ_F_EPISODE_ID  10 /* int64   [N]     per-env episode counter (RNG stream position) */
 #define LLQ_F_FOOT_POS    11 /* float   [N,12]  world positions of the 4 foot links after the last step (LR:199-205) -- get only */
+#define LLQ_F_AUX         13 /* double  [N,18]  EPMC bookkeeping (LLQ_AUX_DIM): counters, joystick target, push randomiser, friction */
 #define LLQ_F_DECISION_MARGIN 12 /* float [N]   CPU oracle only, get only: smallest distance to a discontinuous branch taken during
                                    the last step: min(|q-limit|) over joints [rad], min(|dist-contact_breaking|) over feet [m].
                                    Parity tests use it to tell rounding noise from a flipped joint-limit / contact decision. */
@@ -96,6 +105,17 @@ typedef struct llq_config {
   double w_joint_pos, w_joint_vel, w_end_effector, w_root_pose, w_root_vel; /* reward weights (PLE:352-370) */
   double prioritized_sample_factor; /* (PLE:136,239) */
   double policy_dt;           /* 1/control_freq = 0.02 (PLE:47) -- used for MotionLib margin / max_steps (ML:35,45) */
+  /* ---- environmental level (LLQ_ENV_EPMC); PGE = max_game_elements/playground_env.py, PR = randomizer/push_randomizer.py */
+  int32_t env_kind;           /* LLQ_ENV_PMC / LLQ_ENV_EPMC */
+  int32_t max_steps;          /* episode length cap, 1000 (PGE:66,364) */
+  int32_t cmd_freq_lo, cmd_freq_hi;   /* cmd_vary_freq ~ randint(lo, hi) (PGE:170,223) */
+  int32_t push_start_count;   /* -start_time // time_step  = -250 (PR:53)   -- computed by the host with Python float floor division */
+  int32_t push_interval_steps;/* interval_time // time_step = 499  (PR:46) */
+  int32_t push_duration_steps;/* duration_time // time_step = 100  (PR:45) */
+  int32_t push_enabled;       /* 'disturb_force_config' present (PGE:155-158) */
+  double friction_lo, friction_hi;    /* per-episode foot lateral friction ~ U (PGE:209) */
+  double push_h_lo, push_h_hi, push_v_lo, push_v_hi;   /* horizontal / vertical push force ranges (PR:89-99) */
+  double target_spd_lo, target_spd_hi;                 /* target_spd_range (PGE:317) */
 } llq_config;
 
 typedef struct llq_engine* llq_handle;
@@ -112,6 +132,13 @@ int llq_create(const llq_config* cfg, llq_handle* out);
 
 /* Replaces: PrimitiveLevelEnv.close (PLE:428-431). */
 int llq_destroy(llq_handle h);
+
+/* Observation row width of this handle: LLQ_OBS_DIM (PMC) or LLQ_OBS_DIM_EPMC. */
+int llq_obs_dim(llq_handle h);
+
+/* EPMC only. Replaces LeggedRobot.get_init_states_info (LR:115-117): the 37-float state every episode starts from
+ * (utils/constants.py:103-116 STATES_INFO_12_RUN_0) before the random yaw and z = 0.5 of PGE:181-189 are applied. */
+int llq_set_init_state(llq_handle h, const double* state37);
 
 /* Replaces: LeggedRobot._init_dynamic_model / loadURDF (LR:207-264).  blob: float64 table produced by
  * model/compile_model.py, layout in llq_model_layout.h. */

@@ -16,7 +16,8 @@ STATE_DIM, ACTION_DIM, PROP_DIM, OBS_DIM, MOCAP_FRAME = 37, 12, 33, 207, 19
 
 LLQ_IO_HOST, LLQ_IO_DEVICE = 0, 1
 (F_STATE, F_CLIP, F_TIME, F_REWARD_SUM, F_EPISODE_STEPS, F_WARMSTART, F_OBS, F_KIN_STATE, F_SAMPLE_PROB,
- F_AVG_REWARD, F_EPISODE_ID, F_FOOT_POS, F_DECISION_MARGIN) = range(13)
+ F_AVG_REWARD, F_EPISODE_ID, F_FOOT_POS, F_DECISION_MARGIN, F_AUX) = range(14)
+ENV_PMC, ENV_EPMC, OBS_DIM_EPMC, AUX_DIM = 0, 1, 916, 18
 
 # field id -> (dtype, per-env width or None for per-clip tables)
 _FIELDS = {
@@ -24,7 +25,7 @@ _FIELDS = {
     F_REWARD_SUM: (np.float32, 1), F_EPISODE_STEPS: (np.int32, 1), F_WARMSTART: (np.float32, 4),
     F_OBS: (np.float32, OBS_DIM), F_KIN_STATE: (np.float32, STATE_DIM), F_SAMPLE_PROB: (np.float64, None),
     F_AVG_REWARD: (np.float64, None), F_EPISODE_ID: (np.int64, 1), F_FOOT_POS: (np.float32, 12),
-    F_DECISION_MARGIN: (np.float32, 1),
+    F_DECISION_MARGIN: (np.float32, 1), F_AUX: (np.float64, AUX_DIM),
 }
 
 
@@ -42,6 +43,11 @@ class LlqConfig(C.Structure):
         ("w_joint_pos", C.c_double), ("w_joint_vel", C.c_double), ("w_end_effector", C.c_double),
         ("w_root_pose", C.c_double), ("w_root_vel", C.c_double),
         ("prioritized_sample_factor", C.c_double), ("policy_dt", C.c_double),
+        ("env_kind", C.c_int32), ("max_steps", C.c_int32), ("cmd_freq_lo", C.c_int32), ("cmd_freq_hi", C.c_int32),
+        ("push_start_count", C.c_int32), ("push_interval_steps", C.c_int32), ("push_duration_steps", C.c_int32),
+        ("push_enabled", C.c_int32),
+        ("friction_lo", C.c_double), ("friction_hi", C.c_double), ("push_h_lo", C.c_double), ("push_h_hi", C.c_double),
+        ("push_v_lo", C.c_double), ("push_v_hi", C.c_double), ("target_spd_lo", C.c_double), ("target_spd_hi", C.c_double),
     ]
 
 
@@ -53,7 +59,7 @@ class LlqError(RuntimeError):
 
 _EXPORTS = ["llq_abi_version", "llq_default_config", "llq_create", "llq_destroy", "llq_load_model", "llq_load_mocap",
             "llq_reset", "llq_reset_to", "llq_step", "llq_step_ex", "llq_get_field", "llq_set_field",
-            "llq_get_counters", "llq_set_option", "llq_get_timing", "llq_sync", "llq_last_error"]
+            "llq_get_counters", "llq_set_option", "llq_get_timing", "llq_obs_dim", "llq_set_init_state", "llq_sync", "llq_last_error"]
 
 
 class LlqLibrary:
@@ -83,6 +89,8 @@ class LlqLibrary:
         L.llq_set_field.argtypes = [vp, C.c_int, vp]
         L.llq_get_counters.argtypes = [vp, vp, C.c_int32]
         L.llq_sync.argtypes = [vp]
+        L.llq_obs_dim.argtypes = [vp]
+        L.llq_set_init_state.argtypes = [vp, vp]
         L.llq_set_option.argtypes = [vp, C.c_char_p, C.c_double]
         L.llq_get_timing.argtypes = [vp, vp, C.c_int32]
         L.llq_last_error.restype = C.c_char_p
@@ -146,10 +154,20 @@ class VecEngine:
         lib.check(lib.lib.llq_create(C.byref(cfg), C.byref(self._h)))
         blob = np.ascontiguousarray(model_blob, dtype=np.float64)
         lib.check(lib.lib.llq_load_model(self._h, _ptr(blob), blob.size))
-        frames = np.ascontiguousarray(mocap.frames, dtype=np.float64)
-        offs = np.ascontiguousarray(mocap.offsets, dtype=np.int32)
-        self.n_clips = offs.size - 1
-        lib.check(lib.lib.llq_load_mocap(self._h, _ptr(frames), _ptr(offs), self.n_clips, float(mocap.frame_dt)))
+        self.n_clips = 0
+        if mocap is not None:
+            frames = np.ascontiguousarray(mocap.frames, dtype=np.float64)
+            offs = np.ascontiguousarray(mocap.offsets, dtype=np.int32)
+            self.n_clips = offs.size - 1
+            lib.check(lib.lib.llq_load_mocap(self._h, _ptr(frames), _ptr(offs), self.n_clips, float(mocap.frame_dt)))
+        self.obs_dim = int(lib.lib.llq_obs_dim(self._h))
+        if self.obs_dim <= 0:
+            lib.check(self.obs_dim)
+
+    def set_init_state(self, state37):
+        st = np.ascontiguousarray(state37, dtype=np.float64)
+        assert st.shape == (STATE_DIM,)
+        self.lib.check(self.lib.lib.llq_set_init_state(self._h, _ptr(st)))
 
     # -- lifecycle
     def close(self):
@@ -168,13 +186,13 @@ class VecEngine:
         return None if mask is None else np.ascontiguousarray(mask, dtype=np.uint8)
 
     def reset(self, mask=None):
-        obs = np.empty((self.n, OBS_DIM), np.float32)
+        obs = np.empty((self.n, self.obs_dim), np.float32)
         m = self._mask(mask)
         self.lib.check(self.lib.lib.llq_reset(self._h, _ptr(m), _ptr(obs)))
         return obs
 
     def reset_to(self, clip, time, mask=None):
-        obs = np.empty((self.n, OBS_DIM), np.float32)
+        obs = np.empty((self.n, self.obs_dim), np.float32)
         clip = np.ascontiguousarray(np.broadcast_to(clip, (self.n,)), dtype=np.int32)
         time = np.ascontiguousarray(np.broadcast_to(time, (self.n,)), dtype=np.float64)
         m = self._mask(mask)
@@ -186,7 +204,7 @@ class VecEngine:
         if a.shape != (self.n, ACTION_DIM):
             raise ValueError("actions must have shape (%d, %d)" % (self.n, ACTION_DIM))
         if out is None:
-            obs = np.empty((self.n, OBS_DIM), np.float32)
+            obs = np.empty((self.n, self.obs_dim), np.float32)
             rew = np.empty((self.n,), np.float32)
             done = np.empty((self.n,), np.uint8)
         else:
@@ -194,7 +212,8 @@ class VecEngine:
         self.lib.check(self.lib.lib.llq_step(self._h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done)))
         return obs, rew, done
 
-    def step_device(self, actions_ptr, obs_ptr, reward_ptr, done_ptr, obs_ld=OBS_DIM, stream=None):
+    def step_device(self, actions_ptr, obs_ptr, reward_ptr, done_ptr, obs_ld=None, stream=None):
+        obs_ld = self.obs_dim if obs_ld is None else obs_ld
         self.lib.check(self.lib.lib.llq_step_ex(self._h, C.c_void_p(actions_ptr), C.c_void_p(obs_ptr), obs_ld,
                                                  C.c_void_p(reward_ptr), C.c_void_p(done_ptr), LLQ_IO_DEVICE,
                                                  C.c_void_p(stream) if stream else None))
@@ -205,12 +224,16 @@ class VecEngine:
     # -- state access
     def get(self, field):
         dt, w = _FIELDS[field]
+        if field == F_OBS:
+            w = self.obs_dim
         arr = np.empty((self.n_clips,) if w is None else ((self.n,) if w == 1 else (self.n, w)), dt)
         self.lib.check(self.lib.lib.llq_get_field(self._h, field, _ptr(arr)))
         return arr
 
     def set(self, field, value):
         dt, w = _FIELDS[field]
+        if field == F_OBS:
+            w = self.obs_dim
         shape = (self.n_clips,) if w is None else ((self.n,) if w == 1 else (self.n, w))
         arr = np.ascontiguousarray(np.broadcast_to(np.asarray(value, dtype=dt), shape), dtype=dt)
         self.lib.check(self.lib.lib.llq_set_field(self._h, field, _ptr(arr)))

@@ -217,6 +217,13 @@ inline void reset_uniforms(uint64_t seed, int64_t gid, int64_t episode, double* 
   *u_phase = ((double)c[1] + 0.5) * (1.0 / 4294967296.0);
 }
 
+// four uniforms of stream `stream` (1 = EPMC reset, 2 = push randomiser, 3 = joystick command), draw `index`
+inline void stream_uniforms(uint64_t seed, int64_t gid, int64_t episode, uint32_t stream, uint32_t index, double u[4]) {
+  uint32_t c[4] = {(uint32_t)gid, ((uint32_t)((uint64_t)gid >> 32) & 0x00FFFFFFu) | (stream << 24), (uint32_t)episode, index};
+  philox4x32_10(c, (uint32_t)seed, (uint32_t)(seed >> 32));
+  for (int i = 0; i < 4; i++) u[i] = ((double)c[i] + 0.5) * (1.0 / 4294967296.0);
+}
+
 // ------------------------------------------------------------------ model
 struct LinkM {
   int parent, jtype, dof;
@@ -244,7 +251,12 @@ struct Env {
   double prop_hist[3][LLQ_PROP_DIM]; double act_hist[3][LLQ_ACTION_DIM];
   double foot_pos[12];
   double margin;   // LLQ_F_DECISION_MARGIN
-  float obs[LLQ_OBS_DIM];
+  double foot_mu;  // per-episode foot lateral friction (PGE:209; PMC: cfg.foot_friction)
+  // EPMC bookkeeping (PGE:146-179, PR:40-54)
+  int counter, cmd_freq; double tgt_x, tgt_y, target_spd, target_angle, last_pos_diff_len, total_spd, max_spd;
+  int push_count, push_draws, cmd_draws; double push_f[3];
+  double yaw_accum_deg;   // PGE:181-189 mutates the shared init-state dict: every reset's yaw is applied on top of the previous ones
+  float obs[LLQ_OBS_DIM_EPMC];
 };
 
 }  // namespace
@@ -256,6 +268,8 @@ struct llq_engine {
   int frame_rate = 0, margin = 0;
   std::vector<double> max_steps, sample_prob, avg_reward;
   std::vector<Env> envs; bool was_reset = false;
+  double init_state[LLQ_STATE_DIM]; bool has_init_state = false;
+  int obs_dim() const { return cfg.env_kind == LLQ_ENV_EPMC ? LLQ_OBS_DIM_EPMC : LLQ_OBS_DIM; }
   int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -468,7 +482,8 @@ inline double clampd(double v, double lo, double hi) { return std::max(lo, std::
 
 // One Bullet stepSimulation() with numSubSteps=1 for one robot on the infinite plane z=0.
 // tau: motor torques (12).  Returns false if the dynamics became singular / non-finite.
-bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contact_rows, int64_t* n_limit_rows) {
+bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contact_rows, int64_t* n_limit_rows,
+                     const double* push_local = nullptr) {
   const Model& md = E.model;
   const llq_config& cf = E.cfg;
   const int nd = 6 + md.ndof;
@@ -485,7 +500,7 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
     double dist = cw.z - sp.r;
     e.margin = std::min(e.margin, std::fabs(dist - cf.contact_breaking));
     if (dist < cf.contact_breaking) {
-      contacts[nc++] = {sp.link, (int)s, V3{cw.x, cw.y, cw.z - sp.r}, dist, cf.ground_friction * sp.mu};
+      contacts[nc++] = {sp.link, (int)s, V3{cw.x, cw.y, cw.z - sp.r}, dist, cf.ground_friction * e.foot_mu};
     } else {
       e.warm[s] = 0.0;  // manifold point removed
     }
@@ -499,7 +514,14 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
     tt[j] = tau[j] - md.links[md.dof_link[j]].jdamp * e.qd[j];
   }
   AbaCache c;
-  if (!aba(E, k, gv, tt, nullptr, nullptr, acc, c)) return false;
+  V3 extf[MAXL];
+  if (push_local) {
+    // applyExternalForce(linkIndex=0, LINK_FRAME) (PR:73-77): pybullet link 0 = first child link (FR hip); force and position
+    // are expressed in that link's inertial frame; position (0,0,0) = its CoM => pure force, no torque
+    for (size_t i = 0; i < md.links.size(); i++) extf[i] = V3{0, 0, 0};
+    extf[1] = mul(k.Rc[1], V3{push_local[0], push_local[1], push_local[2]});
+  }
+  if (!aba(E, k, gv, tt, push_local ? extf : nullptr, nullptr, acc, c)) return false;
   for (int t = 0; t < nd; t++) gv[t] = clampd(gv[t] + acc[t] * dt, -cf.max_coord_vel, cf.max_coord_vel);
 
   // (c) constraint rows
@@ -714,6 +736,7 @@ void reset_env(llq_engine& E, Env& e, int clip, double sampled_time) {
   mocap_state(E, frame_ptr(E, clip, e.frame_id), frame_ptr(E, clip, e.frame_id + 1), e.frame_frac, e.kin);
   unpack_state(e, e.kin);                                                // PLE:162-163
   e.reward_sum = 0; e.episode_steps = 0;
+  e.foot_mu = E.cfg.foot_friction;
   for (int s = 0; s < 8; s++) e.warm[s] = 0;
   double prop[LLQ_PROP_DIM];
   make_prop(e.kin, prop);
@@ -809,6 +832,165 @@ double step_env(llq_engine& E, Env& e, const float* action, bool* done, int64_t*
   return r;
 }
 
+
+// ================================================================== EPMC (PlayGroundEnv, element_id 0: flat joystick task)
+// PGE = max_game_elements/playground_env.py, PR = randomizer/push_randomizer.py
+void epmc_randomize_push(llq_engine& E, Env& e, int64_t gid) {   // PR:89-99
+  double u[4];
+  stream_uniforms(E.cfg.seed, gid, e.episode - 1, 2, (uint32_t)e.push_draws++, u);   // e.episode was advanced by epmc_reset
+  double theta = 2.0 * M_PI * u[0];
+  double h = E.cfg.push_h_lo + u[1] * (E.cfg.push_h_hi - E.cfg.push_h_lo);
+  double v = E.cfg.push_v_lo + u[2] * (E.cfg.push_v_hi - E.cfg.push_v_lo);
+  e.push_f[0] = h * std::cos(theta); e.push_f[1] = h * std::sin(theta); e.push_f[2] = v;
+}
+
+// PGE:374-447 on the flat 200 x 200 ground slab (top face z = 0) -- the only static body of element 0 besides the
+// degenerate target marker (BSE:106-131 gives its collision box zero extents).
+void epmc_drill(const llq_engine& E, const Env& e, const double* st, float* percep /* 325 + 128 + 325 + 3 */) {
+  Q4 qb = qnormalize({st[3], st[4], st[5], st[6]});
+  M3 R = qmat(qb);
+  V3 pos = {st[0], st[1], st[2]};
+  // percep_2d: rays straight down from z = 10 over a 25 x 13 grid: every ray hits the slab top => hit z = 0 (PGE:431-447)
+  for (int i = 0; i < 325; i++) percep[i] = 0.0f;
+  // percep_1d: 128 horizontal rays of 20 m at the base height never reach the slab (z0 > 0): miss => hit_pos = (0,0,0) =>
+  // "distance" = |ray_from| = |base_pos| (PGE:49-53,388-394).  Below the surface the origin is inside the slab: miss too.
+  float d1 = (float)norm(pos);
+  for (int i = 0; i < 128; i++) percep[325 + i] = d1;
+  // percep_front: 25 x 13 rays along body +x, 3 m, starting at body (0, y, z), y in [-.25,.25], z in [-.3,.1] (PGE:409-429)
+  for (int i = 0; i < 25; i++) {
+    double y = i == 24 ? 0.25 : -0.25 + i * (0.5 / 24.0);
+    for (int j = 0; j < 13; j++) {
+      double z = j == 12 ? 0.1 : -0.3 + j * (0.4 / 12.0);
+      V3 from = mul(R, V3{0.0, y, z}) + pos;
+      V3 to = mul(R, V3{3.0, y, z}) + pos;
+      V3 hit = to;
+      if (from.z > 0.0 && to.z < 0.0) {            // enters the slab through its top face
+        double t = from.z / (from.z - to.z);
+        hit = from + t * (to - from);
+      }
+      percep[453 + i * 13 + j] = (float)norm(hit - from);
+    }
+  }
+  // target (PGE:396-400): unit xy of R^-1 (target - pos), then target_spd
+  V3 d = tmul(R, V3{e.tgt_x - pos.x, e.tgt_y - pos.y, 0.0 - pos.z});
+  double n2 = std::sqrt(d.x * d.x + d.y * d.y);
+  percep[778] = (float)(d.x / n2); percep[779] = (float)(d.y / n2); percep[780] = (float)e.target_spd;
+}
+
+void epmc_write_obs(const llq_engine& E, Env& e, const double* st) {
+  int o = 0;
+  for (int h = 0; h < 3; h++)
+    for (int t = 0; t < LLQ_PROP_DIM; t++) e.obs[o++] = (float)e.prop_hist[h][t];
+  for (int h = 0; h < 3; h++)
+    for (int t = 0; t < LLQ_ACTION_DIM; t++) e.obs[o++] = (float)e.act_hist[h][t];
+  epmc_drill(E, e, st, e.obs + 135);
+}
+
+void epmc_reset(llq_engine& E, Env& e, int64_t gid) {   // PGE:196-249
+  const llq_config& cf = E.cfg;
+  double u[4];
+  e.episode++;                                   // all streams of this episode are keyed by (episode - 1)
+  stream_uniforms(cf.seed, gid, e.episode - 1, 1, 0, u);
+  e.foot_mu = cf.friction_lo + u[0] * (cf.friction_hi - cf.friction_lo);                 // PGE:209-210
+  e.push_draws = 0; e.cmd_draws = 0;
+  e.push_count = cf.push_start_count;                                                    // PR:52-53
+  e.push_f[0] = e.push_f[1] = e.push_f[2] = 0;
+  if (cf.push_enabled) epmc_randomize_push(E, e, gid);                                   // PR:54
+  e.cmd_freq = cf.cmd_freq_lo + (int)std::floor(u[2] * (cf.cmd_freq_hi - cf.cmd_freq_lo));   // np.random.randint (PGE:223)
+  e.counter = 0; e.total_spd = 0; e.max_spd = 0; e.time = 0;
+  e.reward_sum = 0; e.episode_steps = 0;
+  // randomize_init_states (PGE:181-195): yaw about world z composed on the right of the stored tilt
+  double st[LLQ_STATE_DIM];
+  std::memcpy(st, E.init_state, sizeof(st));
+  e.yaw_accum_deg = std::fmod(e.yaw_accum_deg + 360.0 * u[1], 360.0);
+  double a = e.yaw_accum_deg * M_PI / 180.0;
+  Q4 qr = {0, 0, std::sin(a / 2), std::cos(a / 2)};
+  Q4 q0 = qnormalize({st[3], st[4], st[5], st[6]});
+  Q4 qn = qmul(q0, qr);
+  st[3] = qn.x; st[4] = qn.y; st[5] = qn.z; st[6] = qn.w;
+  st[0] = 0.0; st[1] = 0.0; st[2] = 0.5;
+  unpack_state(e, st);
+  for (int s = 0; s < 8; s++) e.warm[s] = 0;
+  e.tgt_x = 8.0; e.tgt_y = 0.0;                                                          // BSE:247-248, PGE:219
+  e.last_pos_diff_len = std::sqrt((st[0] - e.tgt_x) * (st[0] - e.tgt_x) + (st[1] - e.tgt_y) * (st[1] - e.tgt_y));
+  double prop[LLQ_PROP_DIM];
+  make_prop(st, prop);
+  for (int h = 0; h < 3; h++) {
+    std::memcpy(e.prop_hist[h], prop, sizeof(prop));
+    for (int t = 0; t < 12; t++) e.act_hist[h][t] = 0;
+  }
+  foot_positions(E, st, e.foot_pos);
+  epmc_write_obs(E, e, st);
+}
+
+double epmc_step(llq_engine& E, Env& e, int64_t gid, const float* action, bool* done, int64_t* ncr, int64_t* nlr) {   // PGE:301-358
+  const llq_config& cf = E.cfg;
+  e.episode_steps += 1;
+  e.margin = 1e30;
+  if (e.counter % e.cmd_freq == 0) {                                                     // PGE:302-317 (element_id == 0)
+    double u[4];
+    stream_uniforms(cf.seed, gid, e.episode - 1, 3, (uint32_t)e.cmd_draws++, u);
+    e.target_angle = 2.0 * M_PI * u[0];
+    e.tgt_x = e.pos[0] + std::cos(e.target_angle) * 100.0;
+    e.tgt_y = e.pos[1] + std::sin(e.target_angle) * 100.0;
+    e.last_pos_diff_len = std::sqrt((e.pos[0] - e.tgt_x) * (e.pos[0] - e.tgt_x) + (e.pos[1] - e.tgt_y) * (e.pos[1] - e.tgt_y));
+    e.target_spd = cf.target_spd_lo + u[1] * (cf.target_spd_hi - cf.target_spd_lo);
+  }
+  double act[12], tgt[12], tau[12];
+  for (int j = 0; j < 12; j++) { act[j] = (double)action[j]; tgt[j] = e.q[j] + act[j]; }   // PGE:323-324
+  bool ok = true;
+  for (int s = 0; s < cf.substeps; s++) {
+    for (int j = 0; j < 12; j++) {
+      double tg = clampd(tgt[j], -3.0, 3.0);
+      double t = cf.kp * (tg - e.q[j]) + cf.kd * (0.0 - e.qd[j]);
+      tau[j] = clampd(t, -cf.max_tau, cf.max_tau);
+    }
+    const double* push = nullptr;
+    if (cf.push_enabled) {                                                               // PR:56-87
+      e.push_count += 1;
+      if (e.push_count > 0) {
+        if (e.push_count % cf.push_interval_steps == 0) { epmc_randomize_push(E, e, gid); e.push_count = 0; }
+        if (e.push_count < cf.push_duration_steps) push = e.push_f;
+      }
+    }
+    if (ok) ok = physics_substep(E, e, tau, ncr, nlr, push);                             // PGE:295-299
+    e.time += cf.sim_dt;
+  }
+  double st[LLQ_STATE_DIM];
+  pack_state(e, st);
+  double prop[LLQ_PROP_DIM];
+  make_prop(st, prop);
+  std::memmove(e.prop_hist[0], e.prop_hist[1], 2 * sizeof(e.prop_hist[0]));
+  std::memcpy(e.prop_hist[2], prop, sizeof(prop));
+  std::memmove(e.act_hist[0], e.act_hist[1], 2 * sizeof(e.act_hist[0]));
+  std::memcpy(e.act_hist[2], act, sizeof(act));
+  foot_positions(E, st, e.foot_pos);
+  epmc_write_obs(E, e, st);
+  e.counter += 1;                                                                        // PGE:340
+  // termination (PGE:360-372)
+  Q4 q1 = qnormalize({st[3], st[4], st[5], st[6]});
+  M3 R = qmat(q1);
+  double left_z = R.m[0][2] * R.m[1][0] - R.m[1][2] * R.m[0][0];
+  bool fall = left_z > std::sin(45.0 * M_PI / 180.0) || left_z < std::sin(-45.0 * M_PI / 180.0) || R.m[2][2] < std::cos(60.0 * M_PI / 180.0);
+  double dx = e.tgt_x - st[0], dy = e.tgt_y - st[1];
+  double plen = std::sqrt(dx * dx + dy * dy);
+  bool reach = plen < 0.5;
+  bool timeup = e.counter >= cf.max_steps;
+  *done = fall || timeup || reach || !ok;
+  // joystick reward (PGE:479-502)
+  double ux = dx / plen, uy = dy / plen;
+  double spd = std::fabs(st[7] * ux + st[8] * uy);
+  e.total_spd += spd;
+  if (spd > e.max_spd) e.max_spd = spd;
+  double reward_vel = std::exp(-std::fabs(spd - e.target_spd));
+  double yaw = std::atan2(R.m[1][0], R.m[0][0]);
+  double reward_rot = std::exp((std::cos(yaw) * ux + std::sin(yaw) * uy - 1.0) * 5.0);
+  double r = reward_vel * reward_rot / (double)cf.max_steps;
+  if (!ok || !std::isfinite(r)) { r = 0.0; *done = true; }
+  e.reward_sum += r;
+  return r;
+}
+
 void update_sampling(llq_engine& E) {  // PLE:239-240
   double tot = 0;
   for (int c = 0; c < E.n_clips; c++) {
@@ -821,7 +1003,8 @@ void update_sampling(llq_engine& E) {  // PLE:239-240
 int check_ready(llq_handle h, bool need_reset) {
   if (!h) return fail(LLQ_EINVAL, "null handle");
   if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
-  if (!h->has_mocap) return fail(LLQ_ESTATE, "llq_load_mocap has not been called");
+  if (h->cfg.env_kind == LLQ_ENV_PMC && !h->has_mocap) return fail(LLQ_ESTATE, "llq_load_mocap has not been called");
+  if (h->cfg.env_kind == LLQ_ENV_EPMC && !h->has_init_state) return fail(LLQ_ESTATE, "llq_set_init_state has not been called");
   if (need_reset && !h->was_reset) return fail(LLQ_ESTATE, "llq_reset has not been called");
   return LLQ_OK;
 }
@@ -850,6 +1033,11 @@ int llq_default_config(llq_config* c) {
   c->lin_damping = 0.04; c->ang_damping = 0.04; c->max_coord_vel = 100.0; c->max_applied_impulse = 1000.0;
   c->w_joint_pos = 0.3; c->w_joint_vel = 0.05; c->w_end_effector = 0.1; c->w_root_pose = 0.5; c->w_root_vel = 0.05;
   c->prioritized_sample_factor = 3.0;
+  // EPMC defaults = train_scripts/example_epmc_train.sh:100-117 (only used when env_kind = LLQ_ENV_EPMC)
+  c->env_kind = LLQ_ENV_PMC; c->max_steps = 1000; c->cmd_freq_lo = 9999; c->cmd_freq_hi = 10000;
+  c->push_start_count = -250; c->push_interval_steps = 499; c->push_duration_steps = 100; c->push_enabled = 1;
+  c->friction_lo = 0.4; c->friction_hi = 3.0; c->push_h_lo = 0.0; c->push_h_hi = 50.0; c->push_v_lo = 0.0; c->push_v_hi = 10.0;
+  c->target_spd_lo = 0.5; c->target_spd_hi = 3.0;
   return LLQ_OK;
 }
 
@@ -858,6 +1046,10 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   if (cfg->struct_size != (int32_t)sizeof(llq_config)) return fail(LLQ_EINVAL, "llq_config size mismatch (ABI)");
   if (cfg->n_envs <= 0) return fail(LLQ_EINVAL, "n_envs must be positive");
   if (cfg->substeps <= 0 || cfg->solver_iters < 0 || !(cfg->sim_dt > 0)) return fail(LLQ_EINVAL, "bad step configuration");
+  if (cfg->env_kind != LLQ_ENV_PMC && cfg->env_kind != LLQ_ENV_EPMC) return fail(LLQ_EINVAL, "unknown env_kind");
+  if (cfg->env_kind == LLQ_ENV_EPMC && (cfg->max_steps <= 0 || cfg->cmd_freq_hi <= cfg->cmd_freq_lo || cfg->cmd_freq_lo <= 0 ||
+                                        cfg->push_interval_steps <= 0))
+    return fail(LLQ_EINVAL, "bad EPMC configuration");
   llq_engine* e = new (std::nothrow) llq_engine();
   if (!e) return fail(LLQ_ENOMEM, "out of memory");
   e->cfg = *cfg;
@@ -933,19 +1125,22 @@ int llq_load_mocap(llq_handle h, const double* frames, const int32_t* off, int32
 int llq_reset(llq_handle h, const uint8_t* mask, float* obs) {
   int rc = check_ready(h, false);
   if (rc) return rc;
+  const int od = h->obs_dim();
   for (int i = 0; i < h->cfg.n_envs; i++) {
     if (mask && !mask[i]) continue;
-    sample_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
+    if (h->cfg.env_kind == LLQ_ENV_EPMC) epmc_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
+    else sample_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
   }
   h->was_reset = true;
   if (obs)
-    for (int i = 0; i < h->cfg.n_envs; i++) std::memcpy(obs + (size_t)i * LLQ_OBS_DIM, h->envs[i].obs, sizeof(float) * LLQ_OBS_DIM);
+    for (int i = 0; i < h->cfg.n_envs; i++) std::memcpy(obs + (size_t)i * od, h->envs[i].obs, sizeof(float) * od);
   return LLQ_OK;
 }
 
 int llq_reset_to(llq_handle h, const uint8_t* mask, const int32_t* clip, const double* time, float* obs) {
   int rc = check_ready(h, false);
   if (rc) return rc;
+  if (h->cfg.env_kind != LLQ_ENV_PMC) return fail(LLQ_EUNSUPPORTED, "llq_reset_to is a PMC (mocap) entry point");
   if (!clip || !time) return fail(LLQ_EINVAL, "null clip/time");
   for (int i = 0; i < h->cfg.n_envs; i++) {
     if (mask && !mask[i]) continue;
@@ -967,8 +1162,10 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
   if (rc) return rc;
   if (!actions) return fail(LLQ_EINVAL, "null actions");
   if (io_mode != LLQ_IO_HOST) return fail(LLQ_EUNSUPPORTED, "CPU oracle only takes host pointers");
-  if (obs && obs_ld < LLQ_OBS_DIM) return fail(LLQ_EINVAL, "obs_ld < 207");
+  const int od = h->obs_dim();
+  if (obs && obs_ld < od) return fail(LLQ_EINVAL, "obs_ld smaller than the observation width");
   const int n = h->cfg.n_envs;
+  const bool epmc = h->cfg.env_kind == LLQ_ENV_EPMC;
   std::vector<double> rew(n); std::vector<uint8_t> dn(n);
   int64_t ncr = 0, nlr = 0;
 #ifdef _OPENMP
@@ -977,7 +1174,8 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
 #endif
   for (int i = 0; i < n; i++) {
     bool d = false;
-    rew[i] = step_env(*h, h->envs[i], actions + (size_t)i * LLQ_ACTION_DIM, &d, &ncr, &nlr);
+    if (epmc) rew[i] = epmc_step(*h, h->envs[i], h->cfg.global_env_offset + i, actions + (size_t)i * LLQ_ACTION_DIM, &d, &ncr, &nlr);
+    else rew[i] = step_env(*h, h->envs[i], actions + (size_t)i * LLQ_ACTION_DIM, &d, &ncr, &nlr);
     dn[i] = d ? 1 : 0;
   }
   // prioritized-sampling bookkeeping (PLE:235-240).  Batched rule: envs are applied in index order, so the
@@ -986,26 +1184,39 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
   for (int i = 0; i < n; i++)
     if (dn[i]) {
       Env& e = h->envs[i];
-      h->avg_reward[e.clip] = e.reward_sum / h->max_steps[e.clip];
+      if (!epmc) h->avg_reward[e.clip] = e.reward_sum / h->max_steps[e.clip];
       any = true;
       h->counters[1]++;
     }
-  if (any) update_sampling(*h);
+  if (any && !epmc) update_sampling(*h);
   for (int i = 0; i < n; i++) {
     if (reward) reward[i] = (float)rew[i];
     if (done) done[i] = dn[i];
   }
   if (h->cfg.auto_reset)
     for (int i = 0; i < n; i++)
-      if (dn[i]) sample_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
+      if (dn[i]) {
+        if (epmc) epmc_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
+        else sample_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
+      }
   if (obs)
-    for (int i = 0; i < n; i++) std::memcpy(obs + (size_t)i * obs_ld, h->envs[i].obs, sizeof(float) * LLQ_OBS_DIM);
+    for (int i = 0; i < n; i++) std::memcpy(obs + (size_t)i * obs_ld, h->envs[i].obs, sizeof(float) * od);
   h->counters[0] += n; h->counters[2] += ncr; h->counters[3] += nlr;
   return LLQ_OK;
 }
 
 int llq_step(llq_handle h, const float* actions, float* obs, float* reward, uint8_t* done) {
-  return llq_step_ex(h, actions, obs, LLQ_OBS_DIM, reward, done, LLQ_IO_HOST, nullptr);
+  if (!h) return fail(LLQ_EINVAL, "null handle");
+  return llq_step_ex(h, actions, obs, h->obs_dim(), reward, done, LLQ_IO_HOST, nullptr);
+}
+
+int llq_obs_dim(llq_handle h) { return h ? h->obs_dim() : fail(LLQ_EINVAL, "null handle"); }
+
+int llq_set_init_state(llq_handle h, const double* st) {
+  if (!h || !st) return fail(LLQ_EINVAL, "null argument");
+  std::memcpy(h->init_state, st, sizeof(h->init_state));
+  h->has_init_state = true;
+  return LLQ_OK;
 }
 
 int llq_get_field(llq_handle h, int field, void* dst) {
@@ -1021,7 +1232,15 @@ int llq_get_field(llq_handle h, int field, void* dst) {
       case LLQ_F_REWARD_SUM: ((float*)dst)[i] = (float)e.reward_sum; break;
       case LLQ_F_EPISODE_STEPS: ((int32_t*)dst)[i] = e.episode_steps; break;
       case LLQ_F_WARMSTART: for (int t = 0; t < 4; t++) ((float*)dst)[(size_t)i * 4 + t] = (float)e.warm[t]; break;
-      case LLQ_F_OBS: std::memcpy((float*)dst + (size_t)i * LLQ_OBS_DIM, e.obs, sizeof(float) * LLQ_OBS_DIM); break;
+      case LLQ_F_OBS: std::memcpy((float*)dst + (size_t)i * h->obs_dim(), e.obs, sizeof(float) * h->obs_dim()); break;
+      case LLQ_F_AUX: {
+        double* a = (double*)dst + (size_t)i * LLQ_AUX_DIM;
+        a[0] = e.counter; a[1] = e.cmd_freq; a[2] = e.tgt_x; a[3] = e.tgt_y; a[4] = e.target_spd; a[5] = e.target_angle;
+        a[6] = e.last_pos_diff_len; a[7] = e.total_spd; a[8] = e.max_spd; a[9] = e.push_count; a[10] = e.push_f[0];
+        a[11] = e.push_f[1]; a[12] = e.push_f[2]; a[13] = e.foot_mu; a[14] = e.push_draws; a[15] = e.cmd_draws;
+        a[16] = e.yaw_accum_deg; a[17] = 0;
+        break;
+      }
       case LLQ_F_EPISODE_ID: ((int64_t*)dst)[i] = e.episode; break;
       case LLQ_F_FOOT_POS: for (int t = 0; t < 12; t++) ((float*)dst)[(size_t)i * 12 + t] = (float)e.foot_pos[t]; break;
       case LLQ_F_DECISION_MARGIN: ((float*)dst)[i] = (float)e.margin; break;
@@ -1056,9 +1275,18 @@ int llq_set_field(llq_handle h, int field, const void* src) {
       case LLQ_F_EPISODE_STEPS: e.episode_steps = ((const int32_t*)src)[i]; break;
       case LLQ_F_WARMSTART: for (int t = 0; t < 4; t++) e.warm[t] = ((const float*)src)[(size_t)i * 4 + t]; break;
       case LLQ_F_EPISODE_ID: e.episode = ((const int64_t*)src)[i]; break;
+      case LLQ_F_AUX: {
+        const double* a = (const double*)src + (size_t)i * LLQ_AUX_DIM;
+        e.counter = (int)a[0]; e.cmd_freq = (int)a[1]; e.tgt_x = a[2]; e.tgt_y = a[3]; e.target_spd = a[4]; e.target_angle = a[5];
+        e.last_pos_diff_len = a[6]; e.total_spd = a[7]; e.max_spd = a[8]; e.push_count = (int)a[9]; e.push_f[0] = a[10];
+        e.push_f[1] = a[11]; e.push_f[2] = a[12]; e.foot_mu = a[13]; e.push_draws = (int)a[14]; e.cmd_draws = (int)a[15];
+        e.yaw_accum_deg = a[16];
+        if (e.cmd_freq <= 0) return fail(LLQ_EINVAL, "cmd_vary_freq must be positive");
+        break;
+      }
       case LLQ_F_OBS: {
-        const float* o = (const float*)src + (size_t)i * LLQ_OBS_DIM;
-        std::memcpy(e.obs, o, sizeof(float) * LLQ_OBS_DIM);
+        const float* o = (const float*)src + (size_t)i * h->obs_dim();
+        std::memcpy(e.obs, o, sizeof(float) * h->obs_dim());
         for (int hh = 0; hh < 3; hh++) {
           for (int t = 0; t < LLQ_PROP_DIM; t++) e.prop_hist[hh][t] = o[hh * LLQ_PROP_DIM + t];
           for (int t = 0; t < LLQ_ACTION_DIM; t++) e.act_hist[hh][t] = o[3 * LLQ_PROP_DIM + hh * LLQ_ACTION_DIM + t];
@@ -1103,7 +1331,16 @@ int llq_oracle_substep(llq_handle h, int32_t env, const double* tau12) {
   if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
   int64_t a = 0, b = 0;
   h->envs[env].margin = 1e30;
+  if (!(h->envs[env].foot_mu > 0)) h->envs[env].foot_mu = h->cfg.foot_friction;
   return physics_substep(*h, h->envs[env], tau12, &a, &b) ? LLQ_OK : fail(LLQ_ESTATE, "physics sub-step failed");
+}
+int llq_oracle_substep_push(llq_handle h, int32_t env, const double* tau12, const double* push_local3, double foot_mu) {
+  if (!h || !tau12 || env < 0 || env >= h->cfg.n_envs) return fail(LLQ_EINVAL, "bad arguments");
+  if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
+  int64_t a = 0, b = 0;
+  h->envs[env].margin = 1e30;
+  h->envs[env].foot_mu = foot_mu;
+  return physics_substep(*h, h->envs[env], tau12, &a, &b, push_local3) ? LLQ_OK : fail(LLQ_ESTATE, "physics sub-step failed");
 }
 int llq_oracle_foot_positions(llq_handle h, const double* st37, double* out12) {
   if (!h || !st37 || !out12) return fail(LLQ_EINVAL, "bad arguments");

@@ -30,6 +30,8 @@ class _Body:
         self.state[6] = 1.0
         self.dirty = True
         self.tau = np.zeros(12)
+        self.push = None          # pending applyExternalForce (link 0, LINK_FRAME), cleared after every step
+        self.foot_mu = 0.5
 
 
 class FakeBulletClient:
@@ -40,7 +42,8 @@ class FakeBulletClient:
     POSITION_CONTROL, TORQUE_CONTROL = 2, 3
     ACTIVATION_STATE_SLEEP, ACTIVATION_STATE_ENABLE_SLEEPING, ACTIVATION_STATE_DISABLE_WAKEUP = 1, 2, 4
     COV_ENABLE_RENDERING, COV_ENABLE_GUI, COV_ENABLE_SINGLE_STEP_RENDERING = 1, 2, 3
-    GEOM_BOX, STATE_LOGGING_VIDEO_MP4 = 3, 4
+    GEOM_BOX, STATE_LOGGING_VIDEO_MP4, GEOM_CYLINDER = 3, 4, 5
+    LINK_FRAME, WORLD_FRAME = 1, 2
 
     oracle_engine = None      # VecEngine over libllq_cpu.so with n_envs = 1, set by the generator
     call_log = None
@@ -51,7 +54,8 @@ class FakeBulletClient:
         eng = FakeBulletClient.oracle_engine
         self._lib = eng.lib.lib
         self._h = eng._h
-        for f in ("llq_oracle_get_state64", "llq_oracle_set_state64", "llq_oracle_substep", "llq_oracle_foot_positions"):
+        for f in ("llq_oracle_get_state64", "llq_oracle_set_state64", "llq_oracle_substep", "llq_oracle_substep_push",
+                  "llq_oracle_foot_positions"):
             getattr(self._lib, f).restype = C.c_int
 
     # ---- model loading
@@ -75,8 +79,54 @@ class FakeBulletClient:
 
     def _noop(self, *a, **k):
         return None
-    setCollisionFilterGroupMask = changeVisualShape = changeDynamics = setGravity = _noop
+    setCollisionFilterGroupMask = changeVisualShape = setGravity = _noop
     setPhysicsEngineParameter = setTimeStep = configureDebugVisualizer = resetDebugVisualizerCamera = _noop
+    createVisualShape = createCollisionShape = removeBody = _noop
+
+    def createMultiBody(self, *a, **k):
+        self.bodies.append(_Body("static"))
+        return len(self.bodies) - 1
+
+    def changeDynamics(self, uid, linkIndex=None, lateralFriction=None, **kw):
+        if lateralFriction is not None and linkIndex in FOOT_LINKS and self.bodies[uid].kind == "dynamic":
+            self.bodies[uid].foot_mu = float(lateralFriction)        # LR:304-308
+
+    def applyExternalForce(self, objectUniqueId, linkIndex, forceObj, posObj, flags):
+        assert linkIndex == 0 and flags == self.LINK_FRAME and not np.any(np.asarray(posObj))        # PR:73-77
+        self.bodies[objectUniqueId].push = np.asarray(forceObj, dtype=np.float64).copy()
+
+    def rayTestBatch(self, rayFromPositions, rayToPositions, collisionFilterMask=-1, **kw):
+        """Closest hit against the static world of EPMC element 0: the ground slab of max_game_elements/data/urdf/plane.urdf
+        (box 200 x 200 x 10 centred at z = -5).  Independent slab test (not the oracle's code).  Mask 6 => robots are invisible."""
+        lo, hi = np.array([-100.0, -100.0, -10.0]), np.array([100.0, 100.0, 0.0])
+        out = []
+        for a, b in zip(np.asarray(rayFromPositions, dtype=np.float64), np.asarray(rayToPositions, dtype=np.float64)):
+            d = b - a
+            t0, t1, axis_in = 0.0, 1.0, -1
+            inside = bool(np.all(a > lo) and np.all(a < hi))
+            hit = not inside
+            if hit:
+                for ax in range(3):
+                    if d[ax] == 0.0:
+                        if a[ax] < lo[ax] or a[ax] > hi[ax]:
+                            hit = False
+                            break
+                        continue
+                    ta, tb = (lo[ax] - a[ax]) / d[ax], (hi[ax] - a[ax]) / d[ax]
+                    if ta > tb:
+                        ta, tb = tb, ta
+                    if ta > t0:
+                        t0, axis_in = ta, ax
+                    t1 = min(t1, tb)
+                    if t0 > t1:
+                        hit = False
+                        break
+            if hit and axis_in >= 0:
+                n = np.zeros(3); n[axis_in] = -np.sign(d[axis_in])
+                out.append((len(self.bodies) - 1, -1, t0, tuple(a + t0 * d), tuple(n)))
+            else:
+                out.append((-1, -1, 1.0, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0)))
+        return out
 
     def setJointMotorControlArray(self, bodyUniqueId, jointIndices, controlMode, forces=None, **kw):
         if controlMode == self.TORQUE_CONTROL:
@@ -131,7 +181,11 @@ class FakeBulletClient:
                 assert self._lib.llq_oracle_set_state64(self._h, 0, st.ctypes.data_as(C.c_void_p)) == 0
                 b.dirty = False
             tau = np.ascontiguousarray(b.tau, dtype=np.float64)
-            assert self._lib.llq_oracle_substep(self._h, 0, tau.ctypes.data_as(C.c_void_p)) == 0
+            push = None if b.push is None else np.ascontiguousarray(b.push, dtype=np.float64)
+            self._lib.llq_oracle_substep_push.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double]
+            assert self._lib.llq_oracle_substep_push(self._h, 0, tau.ctypes.data_as(C.c_void_p),
+                                                      None if push is None else push.ctypes.data_as(C.c_void_p), C.c_double(b.foot_mu)) == 0
+            b.push = None                 # external forces last one step
             out = np.zeros(37)
             assert self._lib.llq_oracle_get_state64(self._h, 0, out.ctypes.data_as(C.c_void_p)) == 0
             b.state = out

@@ -1,0 +1,92 @@
+"""EPMC (PlayGroundEnv, element_id 0) -- the oracle against golden vectors produced by the reference's own code
+(tests/golden/gen_golden_epmc_from_reference.py: unmodified PlayGroundEnv / PushRandomizer / BulletStatics / LeggedRobot on
+the pybullet shim, consuming the engine's Philox streams).  The replay goes through the oracle's own reset()/step()
+*sampling* path, so friction / yaw / command / push draws, the push schedule and the joystick logic are all pinned."""
+import os
+
+import numpy as np
+import pytest
+
+from lifelike_agility_and_play_b200 import _capi as capi
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "epmc_reference_golden.npz")
+EPMC_CFG = dict(env_kind=1, kp=50.0, kd=0.5, max_tau=16.0, ground_friction=1.0, cmd_freq_lo=25, cmd_freq_hi=40,
+                friction_lo=0.4, friction_hi=3.0, push_h_lo=0.0, push_h_hi=50.0, push_v_lo=0.0, push_v_hi=10.0,
+                target_spd_lo=0.5, target_spd_hi=3.0, push_start_count=-250, push_interval_steps=499, push_duration_steps=100,
+                push_enabled=1)
+
+
+@pytest.fixture(scope="module")
+def gold():
+    return np.load(GOLD)
+
+
+def _obs_of(g, i):
+    return np.concatenate([g[k][i] for k in ("prop", "prop_a", "percep_2d", "percep_1d", "percep_front", "target")])
+
+
+def _replay(eng, g, tol_obs, tol_state, check_state=True):
+    eng.set_init_state(g["init_state"])
+    step = 0
+    worst = 0.0
+    for ep in range(len(g["reset_obs"])):
+        obs = eng.reset()
+        want = g["reset_obs"][ep]
+        err = np.max(np.abs(obs[0] - want) / (1 + np.abs(want)))
+        assert err < tol_obs, ("reset obs", ep, err)
+        aux = eng.get(capi.F_AUX)[0]
+        assert np.allclose(aux[[0, 1, 9, 14, 15]], g["reset_aux"][ep][[0, 1, 9, 14, 15]])          # counters: exact
+        assert np.allclose(aux[[2, 3, 4, 6, 10, 11, 12, 13]], g["reset_aux"][ep][[2, 3, 4, 6, 10, 11, 12, 13]], rtol=1e-6, atol=1e-9)
+        while step < len(g["episode"]) and g["episode"][step] == ep:
+            o, r, d = eng.step(g["action"][step][None])
+            want = _obs_of(g, step)
+            err = np.max(np.abs(o[0] - want) / (1 + np.abs(want)))
+            worst = max(worst, err)
+            assert err < tol_obs, ("obs", step, err, int(np.argmax(np.abs(o[0] - want))))
+            assert abs(r[0] - g["reward"][step]) < tol_obs * 1e-1 + 1e-7, ("reward", step, r[0], g["reward"][step])
+            assert bool(d[0]) == bool(g["done"][step]), ("done", step)
+            aux = eng.get(capi.F_AUX)[0]
+            assert np.allclose(aux[[0, 1, 9, 14, 15]], g["aux"][step][[0, 1, 9, 14, 15]]), ("counters", step, aux, g["aux"][step])
+            if check_state:
+                st = eng.get(capi.F_STATE)[0].astype(np.float64); ws = g["state"][step].copy()
+                if np.dot(st[3:7], ws[3:7]) < 0:
+                    ws[3:7] *= -1
+                assert np.max(np.abs(st - ws) / (1 + np.abs(ws))) < tol_state, ("state", step)
+                assert np.allclose(aux[[2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13]], g["aux"][step][[2, 3, 4, 5, 6, 7, 8, 10, 11, 12, 13]], rtol=1e-5, atol=1e-7)
+            step += 1
+    assert step == len(g["episode"])
+    return worst
+
+
+def test_oracle_replays_reference_epmc_golden(gold, oracle_lib, blob):
+    eng = capi.VecEngine(oracle_lib, 1, blob, None, seed=int(gold["seed"]), max_steps=int(gold["max_steps"]), **EPMC_CFG)
+    assert eng.obs_dim == 916
+    worst = _replay(eng, gold, 5e-7, 5e-7)
+    print("oracle vs reference EPMC golden: worst rel obs err %.2e" % worst)
+    eng.close()
+
+
+def test_epmc_push_schedule_k7(oracle_lib, blob, gold):
+    """silent for 250 sub-steps, first window = counts 1..99, then every 499 sub-steps a resample + 100 sub-steps."""
+    eng = capi.VecEngine(oracle_lib, 1, blob, None, seed=3, substeps=1, max_steps=5000, **EPMC_CFG)
+    eng.set_init_state(gold["init_state"])
+    eng.reset()
+    counts, draws = [], []
+    for t in range(1400):
+        eng.step(np.zeros((1, 12), np.float32))
+        a = eng.get(capi.F_AUX)[0]
+        counts.append(int(a[9])); draws.append(int(a[14]))
+    counts = np.array(counts); draws = np.array(draws)
+    assert counts[0] == -249 and counts[249] == 0 and counts[250] == 1
+    assert draws[0] == 1 and draws[250 + 497] == 1 and draws[250 + 498] == 2          # count reaches 499 -> resample, count := 0
+    assert counts[250 + 498] == 0 and counts[250 + 499] == 1
+
+
+@pytest.mark.gpu
+def test_cuda_replays_reference_epmc_golden(gold, built, blob):
+    eng = capi.VecEngine(capi.load_cuda_library(), 1, blob, None, seed=int(gold["seed"]), max_steps=int(gold["max_steps"]), **EPMC_CFG)
+    assert eng.obs_dim == 916
+    # open loop in fp32: the discrete bookkeeping must match exactly; continuous quantities within a drift allowance
+    worst = _replay(eng, gold, 2e-2, 1.0, check_state=False)
+    print("cuda vs reference EPMC golden (open loop): worst rel obs err %.2e" % worst)
+    eng.close()
