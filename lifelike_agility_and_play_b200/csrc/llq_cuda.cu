@@ -44,6 +44,7 @@ struct llq_engine {
   std::vector<int> clip_off;
   llq::EnvArrays E{};
   float* d_actions = nullptr;
+  int obs_dim = LLQ_OBS_DIM; bool has_init_state = false; llq::ModelConst h_model{};
   int* d_winner[2] = {nullptr, nullptr};
   double* d_avg[2] = {nullptr, nullptr};
   double* d_prob = nullptr; double* d_max_steps = nullptr;
@@ -78,6 +79,11 @@ void fill_params(llq_handle h) {
   P.w_jp = (float)(c.w_joint_pos / sw); P.w_jv = (float)(c.w_joint_vel / sw); P.w_ee = (float)(c.w_end_effector / sw);
   P.w_pose = (float)(c.w_root_pose / sw); P.w_vel = (float)(c.w_root_vel / sw);
   P.sim_dt = c.sim_dt; P.frame_dt = h->frame_dt; P.margin = h->margin;
+  P.max_steps = c.max_steps; P.cmd_freq_lo = c.cmd_freq_lo; P.cmd_freq_hi = c.cmd_freq_hi; P.push_start_count = c.push_start_count;
+  P.push_interval = c.push_interval_steps; P.push_duration = c.push_duration_steps; P.push_enabled = c.push_enabled;
+  P.mu_ground = (float)c.ground_friction; P.fr_lo = (float)c.friction_lo; P.fr_hi = (float)c.friction_hi;
+  P.ph_lo = (float)c.push_h_lo; P.ph_hi = (float)c.push_h_hi; P.pv_lo = (float)c.push_v_lo; P.pv_hi = (float)c.push_v_hi;
+  P.ts_lo = (float)c.target_spd_lo; P.ts_hi = (float)c.target_spd_hi;
 }
 
 template <typename T> int dalloc(T** p, size_t n) {
@@ -100,36 +106,35 @@ int ensure_scratch(llq_handle h, size_t bytes) {
 
 llq::MocapDev mocap_dev(llq_handle h) { return llq::MocapDev{h->d_frames, h->d_clip_off, h->n_clips}; }
 
-template <int BLOCK>
+template <int BLOCK, int ENV>
 void launch_step_t(llq_handle h, const llq::EnvArrays& E, const float* d_actions, float* obs2, long long ld, cudaStream_t s) {
   int threads = 4 * h->cfg.n_envs;
   int grid = (threads + BLOCK - 1) / BLOCK;
   const size_t smem = sizeof(float) * llq::kRowFloats * BLOCK;
   static bool attr_set = false;   // per template instance
-  if (!attr_set) { cudaFuncSetAttribute(llq::pmc_step_kernel<BLOCK>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
-  llq::pmc_step_kernel<BLOCK><<<grid, BLOCK, smem, s>>>(E, mocap_dev(h), h->P, h->d_model, d_actions, obs2, ld, h->d_winner[h->parity]);
+  if (!attr_set) { cudaFuncSetAttribute(llq::pmc_step_kernel<BLOCK, ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  llq::pmc_step_kernel<BLOCK, ENV><<<grid, BLOCK, smem, s>>>(E, mocap_dev(h), h->P, h->d_model, d_actions, obs2, ld, h->d_winner[h->parity],
+                                                             (unsigned long long)h->cfg.seed, (long long)h->cfg.global_env_offset);
 }
-template <int BLOCK>
+template <int BLOCK, int ENV>
 void launch_reset_t(llq_handle h, const llq::EnvArrays& E, const llq::ResetParams& RP, float* obs2, long long ld, cudaStream_t s) {
   int threads = 4 * h->cfg.n_envs;
   int grid = (threads + BLOCK - 1) / BLOCK;
-  size_t smem = sizeof(double) * (size_t)h->n_clips;
-  llq::pmc_reset_kernel<BLOCK><<<grid, BLOCK, smem, s>>>(E, mocap_dev(h), h->P, h->d_model, RP, obs2, ld);
+  size_t smem = sizeof(double) * (size_t)(h->n_clips > 0 ? h->n_clips : 1);
+  llq::pmc_reset_kernel<BLOCK, ENV><<<grid, BLOCK, smem, s>>>(E, mocap_dev(h), h->P, h->d_model, RP, obs2, ld);
 }
 void launch_step(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
+  const bool epmc = h->cfg.env_kind == LLQ_ENV_EPMC;
   switch (h->block) {
-    case 32: launch_step_t<32>(h, E, a, obs2, ld, s); break;
-    case 64: launch_step_t<64>(h, E, a, obs2, ld, s); break;
-    default: launch_step_t<128>(h, E, a, obs2, ld, s); break;
+    case 32: if (epmc) launch_step_t<32, 1>(h, E, a, obs2, ld, s); else launch_step_t<32, 0>(h, E, a, obs2, ld, s); break;
+    case 64: if (epmc) launch_step_t<64, 1>(h, E, a, obs2, ld, s); else launch_step_t<64, 0>(h, E, a, obs2, ld, s); break;
+    default: if (epmc) launch_step_t<128, 1>(h, E, a, obs2, ld, s); else launch_step_t<128, 0>(h, E, a, obs2, ld, s); break;
   }
   h->counters[4]++;
 }
 void launch_reset(llq_handle h, const llq::EnvArrays& E, const llq::ResetParams& RP, float* obs2, long long ld, cudaStream_t s) {
-  switch (h->block) {
-    case 32: launch_reset_t<32>(h, E, RP, obs2, ld, s); break;
-    case 64: launch_reset_t<64>(h, E, RP, obs2, ld, s); break;
-    default: launch_reset_t<128>(h, E, RP, obs2, ld, s); break;   // the reset kernel has no use for larger blocks
-  }
+  if (h->cfg.env_kind == LLQ_ENV_EPMC) launch_reset_t<128, 1>(h, E, RP, obs2, ld, s);
+  else launch_reset_t<128, 0>(h, E, RP, obs2, ld, s);
   h->counters[4]++;
 }
 
@@ -147,7 +152,8 @@ llq::ResetParams reset_params(llq_handle h, int mode, bool update_table) {
 int check_ready(llq_handle h, bool need_reset) {
   if (!h) return fail(LLQ_EINVAL, "null handle");
   if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
-  if (!h->has_mocap) return fail(LLQ_ESTATE, "llq_load_mocap has not been called");
+  if (h->cfg.env_kind == LLQ_ENV_PMC && !h->has_mocap) return fail(LLQ_ESTATE, "llq_load_mocap has not been called");
+  if (h->cfg.env_kind == LLQ_ENV_EPMC && !h->has_init_state) return fail(LLQ_ESTATE, "llq_set_init_state has not been called");
   if (need_reset && !h->was_reset) return fail(LLQ_ESTATE, "llq_reset has not been called");
   return set_device(h);
 }
@@ -194,6 +200,11 @@ int llq_default_config(llq_config* c) {
   c->lin_damping = 0.04; c->ang_damping = 0.04; c->max_coord_vel = 100.0; c->max_applied_impulse = 1000.0;
   c->w_joint_pos = 0.3; c->w_joint_vel = 0.05; c->w_end_effector = 0.1; c->w_root_pose = 0.5; c->w_root_vel = 0.05;
   c->prioritized_sample_factor = 3.0;
+  // EPMC defaults = train_scripts/example_epmc_train.sh:100-117 (only used when env_kind = LLQ_ENV_EPMC)
+  c->env_kind = LLQ_ENV_PMC; c->max_steps = 1000; c->cmd_freq_lo = 9999; c->cmd_freq_hi = 10000;
+  c->push_start_count = -250; c->push_interval_steps = 499; c->push_duration_steps = 100; c->push_enabled = 1;
+  c->friction_lo = 0.4; c->friction_hi = 3.0; c->push_h_lo = 0.0; c->push_h_hi = 50.0; c->push_v_lo = 0.0; c->push_v_hi = 10.0;
+  c->target_spd_lo = 0.5; c->target_spd_hi = 3.0;
   return LLQ_OK;
 }
 
@@ -202,6 +213,10 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   if (cfg->struct_size != (int32_t)sizeof(llq_config)) return fail(LLQ_EINVAL, "llq_config size mismatch (ABI)");
   if (cfg->n_envs <= 0) return fail(LLQ_EINVAL, "n_envs must be positive");
   if (cfg->substeps <= 0 || cfg->solver_iters < 0 || !(cfg->sim_dt > 0)) return fail(LLQ_EINVAL, "bad step configuration");
+  if (cfg->env_kind != LLQ_ENV_PMC && cfg->env_kind != LLQ_ENV_EPMC) return fail(LLQ_EINVAL, "unknown env_kind");
+  if (cfg->env_kind == LLQ_ENV_EPMC && (cfg->max_steps <= 0 || cfg->cmd_freq_hi <= cfg->cmd_freq_lo || cfg->cmd_freq_lo <= 0 ||
+                                        cfg->push_interval_steps <= 0))
+    return fail(LLQ_EINVAL, "bad EPMC configuration");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(LLQ_ECUDA, "no CUDA device visible (the CUDA engine has no CPU fallback)");
@@ -209,6 +224,7 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   llq_engine* h = new (std::nothrow) llq_engine();
   if (!h) return fail(LLQ_ENOMEM, "out of memory");
   h->cfg = *cfg;
+  h->obs_dim = cfg->env_kind == LLQ_ENV_EPMC ? LLQ_OBS_DIM_EPMC : LLQ_OBS_DIM;
   if (const char* b = std::getenv("LLQ_BLOCK")) {
     int v = std::atoi(b);
     if (v == 32 || v == 64 || v == 128) h->block = v;
@@ -222,17 +238,22 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   TRY(dalloc(&h->d_model, 1));
   TRY(dalloc(&h->E.pos, 3 * n)); TRY(dalloc(&h->E.st, 34 * n)); TRY(dalloc(&h->E.time, n)); TRY(dalloc(&h->E.clip, n));
   TRY(dalloc(&h->E.reward_sum, n)); TRY(dalloc(&h->E.episode_steps, n)); TRY(dalloc(&h->E.episode, n));
-  TRY(dalloc(&h->E.warm, 4 * n)); TRY(dalloc(&h->E.obs, (size_t)LLQ_OBS_DIM * n)); TRY(dalloc(&h->E.kin, 37 * n));
+  TRY(dalloc(&h->E.warm, 4 * n)); TRY(dalloc(&h->E.obs, (size_t)h->obs_dim * n)); TRY(dalloc(&h->E.kin, 37 * n));
   TRY(dalloc(&h->E.foot_pos, 12 * n)); TRY(dalloc(&h->E.done_reward, n)); TRY(dalloc(&h->E.done, n)); TRY(dalloc(&h->E.reward, n));
   TRY(dalloc(&h->E.counters, 8));
+  TRY(dalloc(&h->E.aux, (size_t)LLQ_AUX_DIM * n));
   TRY(dalloc(&h->d_actions, (size_t)LLQ_ACTION_DIM * n));
   TRY(dalloc(&h->d_mask, n)); TRY(dalloc(&h->d_clip_in, n)); TRY(dalloc(&h->d_time_in, n));
   ce = cudaMallocHost((void**)&h->h_actions, sizeof(float) * LLQ_ACTION_DIM * n);
-  if (ce == cudaSuccess) ce = cudaMallocHost((void**)&h->h_obs, sizeof(float) * LLQ_OBS_DIM * n);
+  if (ce == cudaSuccess) ce = cudaMallocHost((void**)&h->h_obs, sizeof(float) * h->obs_dim * n);
   if (ce == cudaSuccess) ce = cudaMallocHost((void**)&h->h_reward, sizeof(float) * n);
   if (ce == cudaSuccess) ce = cudaMallocHost((void**)&h->h_done, n);
   if (ce != cudaSuccess) { llq_destroy(h); return fail(LLQ_ECUDA, cudaGetErrorString(ce)); }
 #undef TRY
+  if (cfg->env_kind == LLQ_ENV_EPMC) {   // no mocap table: the winner/avg buffers are still passed to the kernels (unused)
+    h->frame_dt = 1.0 / 120.0; h->margin = 0;
+    fill_params(h);
+  }
   *out = h;
   return LLQ_OK;
 }
@@ -242,7 +263,7 @@ int llq_destroy(llq_handle h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* dptrs[] = {h->d_model, h->d_frames, h->d_clip_off, h->E.pos, h->E.st, h->E.time, h->E.clip, h->E.reward_sum, h->E.episode_steps,
-                   h->E.episode, h->E.warm, h->E.obs, h->E.kin, h->E.foot_pos, h->E.done_reward, h->E.done, h->E.reward, h->E.counters,
+                   h->E.episode, h->E.warm, h->E.obs, h->E.kin, h->E.foot_pos, h->E.done_reward, h->E.done, h->E.reward, h->E.counters, h->E.aux,
                    h->d_actions, h->d_winner[0], h->d_winner[1], h->d_avg[0], h->d_avg[1], h->d_prob, h->d_max_steps, h->d_mask,
                    h->d_clip_in, h->d_time_in, h->d_scratch};
   for (void* p : dptrs) if (p) cudaFree(p);
@@ -291,8 +312,27 @@ int llq_load_model(llq_handle h, const double* b, int64_t n) {
     for (int i = 0; i < 3; i++) M.leg[k].foot[i] = (float)lb[LLQ_L_FOOT + i];
     M.leg[k].foot_r = (float)lb[LLQ_L_FOOT + 3];
   }
+  {   // FR hip = generic link 1: inertial-frame rotation and CoM (for the EPMC push force)
+    const double* g = b + (int64_t)b[LLQ_H_OFF_GENERIC] + 1 * LLQ_GL;
+    for (int i = 0; i < 9; i++) M.push_R[i] = (float)g[LLQ_G_RIN + i];
+    for (int i = 0; i < 3; i++) M.push_c[i] = (float)g[LLQ_G_COM + i];
+  }
+  for (int i = 0; i < 37; i++) M.init_state[i] = h->h_model.init_state[i];
+  h->h_model = M;
   CK(cudaMemcpy(h->d_model, &M, sizeof(M), cudaMemcpyHostToDevice));
   h->has_model = true;
+  return LLQ_OK;
+}
+
+int llq_obs_dim(llq_handle h) { return h ? h->obs_dim : fail(LLQ_EINVAL, "null handle"); }
+
+int llq_set_init_state(llq_handle h, const double* st) {
+  if (!h || !st) return fail(LLQ_EINVAL, "null argument");
+  int rc = set_device(h);
+  if (rc) return rc;
+  for (int i = 0; i < 37; i++) h->h_model.init_state[i] = (float)st[i];
+  if (h->has_model) CK(cudaMemcpy(h->d_model, &h->h_model, sizeof(h->h_model), cudaMemcpyHostToDevice));
+  h->has_init_state = true;
   return LLQ_OK;
 }
 
@@ -365,11 +405,11 @@ static int do_reset(llq_handle h, const uint8_t* mask, const int32_t* clip, cons
     CK(cudaMemcpyAsync(h->d_clip_in, hc, n * sizeof(int), cudaMemcpyHostToDevice, h->stream));
     RP.clip_in = h->d_clip_in; RP.time_in = h->d_time_in;
   }
-  launch_reset(h, h->E, RP, nullptr, LLQ_OBS_DIM, h->stream);
+  launch_reset(h, h->E, RP, nullptr, h->obs_dim, h->stream);
   CK(cudaGetLastError());
-  if (obs) CK(cudaMemcpyAsync(h->h_obs, h->E.obs, sizeof(float) * LLQ_OBS_DIM * n, cudaMemcpyDeviceToHost, h->stream));
+  if (obs) CK(cudaMemcpyAsync(h->h_obs, h->E.obs, sizeof(float) * h->obs_dim * n, cudaMemcpyDeviceToHost, h->stream));
   CK(cudaStreamSynchronize(h->stream));
-  if (obs) std::memcpy(obs, h->h_obs, sizeof(float) * LLQ_OBS_DIM * n);
+  if (obs) std::memcpy(obs, h->h_obs, sizeof(float) * h->obs_dim * n);
   h->was_reset = true;
   return LLQ_OK;
 }
@@ -383,6 +423,7 @@ int llq_reset(llq_handle h, const uint8_t* mask, float* obs) {
 int llq_reset_to(llq_handle h, const uint8_t* mask, const int32_t* clip, const double* time, float* obs) {
   int rc = check_ready(h, false);
   if (rc) return rc;
+  if (h->cfg.env_kind != LLQ_ENV_PMC) return fail(LLQ_EUNSUPPORTED, "llq_reset_to is a PMC (mocap) entry point");
   if (!clip || !time) return fail(LLQ_EINVAL, "null clip/time");
   return do_reset(h, mask, clip, time, obs);
 }
@@ -392,7 +433,8 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
   int rc = check_ready(h, true);
   if (rc) return rc;
   if (!actions) return fail(LLQ_EINVAL, "null actions");
-  if (obs && obs_ld < LLQ_OBS_DIM) return fail(LLQ_EINVAL, "obs_ld < 207");
+  const size_t od = (size_t)h->obs_dim;
+  if (obs && obs_ld < (int64_t)od) return fail(LLQ_EINVAL, "obs_ld smaller than the observation width");
   const size_t n = (size_t)h->cfg.n_envs;
   llq::EnvArrays E = h->E;
   const float* d_act;
@@ -422,13 +464,13 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
   CK(cudaGetLastError());
   h->counters[0] += (int64_t)n;
   if (io_mode == LLQ_IO_HOST) {
-    if (obs) CK(cudaMemcpyAsync(h->h_obs, h->E.obs, sizeof(float) * LLQ_OBS_DIM * n, cudaMemcpyDeviceToHost, s));
+    if (obs) CK(cudaMemcpyAsync(h->h_obs, h->E.obs, sizeof(float) * od * n, cudaMemcpyDeviceToHost, s));
     if (reward) CK(cudaMemcpyAsync(h->h_reward, h->E.reward, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
     if (done) CK(cudaMemcpyAsync(h->h_done, h->E.done, n, cudaMemcpyDeviceToHost, s));
     CK(cudaStreamSynchronize(s));
     if (obs) {
-      if (obs_ld == LLQ_OBS_DIM) std::memcpy(obs, h->h_obs, sizeof(float) * LLQ_OBS_DIM * n);
-      else for (size_t i = 0; i < n; i++) std::memcpy(obs + i * obs_ld, h->h_obs + i * LLQ_OBS_DIM, sizeof(float) * LLQ_OBS_DIM);
+      if ((size_t)obs_ld == od) std::memcpy(obs, h->h_obs, sizeof(float) * od * n);
+      else for (size_t i = 0; i < n; i++) std::memcpy(obs + i * obs_ld, h->h_obs + i * od, sizeof(float) * od);
     }
     if (reward) std::memcpy(reward, h->h_reward, sizeof(float) * n);
     if (done) std::memcpy(done, h->h_done, n);
@@ -437,7 +479,8 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
 }
 
 int llq_step(llq_handle h, const float* actions, float* obs, float* reward, uint8_t* done) {
-  return llq_step_ex(h, actions, obs, LLQ_OBS_DIM, reward, done, LLQ_IO_HOST, nullptr);
+  if (!h) return fail(LLQ_EINVAL, "null handle");
+  return llq_step_ex(h, actions, obs, h->obs_dim, reward, done, LLQ_IO_HOST, nullptr);
 }
 
 int llq_get_field(llq_handle h, int field, void* dst) {
@@ -468,7 +511,17 @@ int llq_get_field(llq_handle h, int field, void* dst) {
     case LLQ_F_REWARD_SUM: CK(cudaMemcpy(dst, h->E.reward_sum, sizeof(float) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_EPISODE_STEPS: CK(cudaMemcpy(dst, h->E.episode_steps, sizeof(int) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_EPISODE_ID: CK(cudaMemcpy(dst, h->E.episode, sizeof(long long) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
-    case LLQ_F_OBS: CK(cudaMemcpy(dst, h->E.obs, sizeof(float) * LLQ_OBS_DIM * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
+    case LLQ_F_OBS: CK(cudaMemcpy(dst, h->E.obs, sizeof(float) * h->obs_dim * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
+    case LLQ_F_AUX: {
+      std::vector<double> tmp((size_t)LLQ_AUX_DIM * n);
+      CK(cudaMemcpy(tmp.data(), h->E.aux, sizeof(double) * LLQ_AUX_DIM * n, cudaMemcpyDeviceToHost));
+      double* o = (double*)dst;
+      for (size_t i = 0; i < n; i++) {
+        for (int t = 0; t < LLQ_AUX_DIM; t++) o[i * LLQ_AUX_DIM + t] = tmp[(size_t)t * n + i];
+        o[i * LLQ_AUX_DIM + 13] = tmp[13 * n + i];
+      }
+      return LLQ_OK;
+    }
     case LLQ_F_SAMPLE_PROB:
       if (!h->has_mocap) return fail(LLQ_ESTATE, "no mocap loaded");
       CK(cudaMemcpy(dst, h->d_prob, sizeof(double) * h->n_clips, cudaMemcpyDeviceToHost)); return LLQ_OK;
@@ -513,7 +566,17 @@ int llq_set_field(llq_handle h, int field, const void* src) {
     case LLQ_F_REWARD_SUM: CK(cudaMemcpy(h->E.reward_sum, src, sizeof(float) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
     case LLQ_F_EPISODE_STEPS: CK(cudaMemcpy(h->E.episode_steps, src, sizeof(int) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
     case LLQ_F_EPISODE_ID: CK(cudaMemcpy(h->E.episode, src, sizeof(long long) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
-    case LLQ_F_OBS: CK(cudaMemcpy(h->E.obs, src, sizeof(float) * LLQ_OBS_DIM * n, cudaMemcpyHostToDevice)); return LLQ_OK;
+    case LLQ_F_OBS: CK(cudaMemcpy(h->E.obs, src, sizeof(float) * h->obs_dim * n, cudaMemcpyHostToDevice)); return LLQ_OK;
+    case LLQ_F_AUX: {
+      const double* a = (const double*)src;
+      std::vector<double> tmp((size_t)LLQ_AUX_DIM * n);
+      for (size_t i = 0; i < n; i++) {
+        if (!(a[i * LLQ_AUX_DIM + 1] >= 1)) return fail(LLQ_EINVAL, "cmd_vary_freq must be positive");
+        for (int t = 0; t < LLQ_AUX_DIM; t++) tmp[(size_t)t * n + i] = a[i * LLQ_AUX_DIM + t];
+      }
+      CK(cudaMemcpy(h->E.aux, tmp.data(), sizeof(double) * LLQ_AUX_DIM * n, cudaMemcpyHostToDevice));
+      return LLQ_OK;
+    }
     case LLQ_F_SAMPLE_PROB:
       return fail(LLQ_EUNSUPPORTED, "sample probabilities are derived from LLQ_F_AVG_REWARD on the device; set that instead");
     case LLQ_F_AVG_REWARD:

@@ -20,7 +20,8 @@
 
 namespace llq {
 
-constexpr int kObsDim = 207, kPropDim = 33, kActDim = 12, kStateDim = 37;
+constexpr int kObsDim = 207, kObsDimEpmc = 916, kPropDim = 33, kActDim = 12, kStateDim = 37, kAuxDim = 18;
+template <int ENV> struct ObsW { static constexpr int value = ENV == 1 ? kObsDimEpmc : kObsDim; };
 constexpr int kNewObs = 120;
 constexpr int kRowFloats = 153;  // per-lane floats of the constraint-row workspace in shared memory (Yc 18 | Yl 18 | Ul 9 | Acl 36 | Alc 36 | All 36)  // floats staged per env: prop 33 | action 12 | future 72 (+3 pad)
 
@@ -33,7 +34,11 @@ struct JointConst {
 };
 struct LegConst { JointConst j[3]; float foot[3]; float foot_r; float pad[4]; };
 struct BaseConst { float qI[4]; float m; float h[3]; float I[6]; int nd; DampItem d[3]; };
-struct alignas(16) ModelConst { BaseConst base; LegConst leg[4]; };
+struct alignas(16) ModelConst {
+  BaseConst base; LegConst leg[4];
+  float push_R[9]; float push_c[3];   // FR hip link: inertial-frame rotation (link <- inertial) and CoM, for applyExternalForce(LINK_FRAME) (PR:73-77)
+  float init_state[37]; float pad_[3]; // EPMC episode start state (LR:115-117, utils/constants.py:103-116)
+};
 
 struct MocapFrame { double x, y, z, pad; float quat[4]; float q[12]; };  // 96 B, 16-byte aligned
 
@@ -43,6 +48,9 @@ struct StepParams {
   float w_jp, w_jv, w_ee, w_pose, w_vel;   // already normalised to sum 1
   double sim_dt, frame_dt;
   int margin;
+  // EPMC (PGE / PR)
+  int max_steps, cmd_freq_lo, cmd_freq_hi, push_start_count, push_interval, push_duration, push_enabled;
+  float mu_ground, fr_lo, fr_hi, ph_lo, ph_hi, pv_lo, pv_hi, ts_lo, ts_hi;
 };
 
 struct EnvArrays {      // SoA device arrays, N envs
@@ -61,6 +69,7 @@ struct EnvArrays {      // SoA device arrays, N envs
   unsigned char* done;  // [N]
   float* reward;        // [N]
   unsigned long long* counters;  // [8]
+  double* aux;          // [18][N] EPMC bookkeeping (include/llq.h LLQ_F_AUX)
 };
 
 struct MocapDev { const MocapFrame* frames; const int* clip_off; int n_clips; };
@@ -231,6 +240,22 @@ LLQ_DI void philox4x32_10(unsigned (&c)[4], unsigned k0, unsigned k1) {
   }
 }
 
+// four uniforms of stream `stream` (1 = EPMC reset, 2 = push randomiser, 3 = joystick command), draw `index` (matches the oracle)
+LLQ_DI void stream_uniforms(unsigned long long seed, long long gid, long long episode, unsigned stream, unsigned index, double (&u)[4]) {
+  unsigned c[4] = {(unsigned)gid, ((unsigned)((unsigned long long)gid >> 32) & 0x00FFFFFFu) | (stream << 24), (unsigned)episode, index};
+  philox4x32_10(c, (unsigned)seed, (unsigned)(seed >> 32));
+#pragma unroll
+  for (int i = 0; i < 4; i++) u[i] = ((double)c[i] + 0.5) * (1.0 / 4294967296.0);
+}
+LLQ_DI void epmc_randomize_push(const StepParams& P, unsigned long long seed, long long gid, long long ep, int& push_draws, float (&pf)[3]) {   // PR:89-99
+  double u[4];
+  stream_uniforms(seed, gid, ep, 2, (unsigned)push_draws++, u);
+  double sn, cs;
+  sincos(2.0 * 3.14159265358979323846 * u[0], &sn, &cs);
+  double h = (double)P.ph_lo + u[1] * ((double)P.ph_hi - (double)P.ph_lo);
+  pf[0] = (float)(h * cs); pf[1] = (float)(h * sn); pf[2] = (float)((double)P.pv_lo + u[2] * ((double)P.pv_hi - (double)P.pv_lo));
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Shared tail: given the dynamic robot state (pybullet convention) and the mocap cursor, build the new prop / future
 // into the staging row `snew` (120 floats per env) and return the pieces the reward needs.
@@ -291,14 +316,18 @@ LLQ_DI ObsCtx build_obs_new(const MocapDev& mc, const StepParams& P, const Model
 // `do_row` (bit e of a warp-uniform mask) selects which of the 8 rows are written.
 constexpr int kHist = 90;   // per-env history carry: prop[33:99] (66) | prop_a[12:36] (24)
 
+// staging row (kNewObs floats per env).  PMC: prop 33 | action 12 | future 72.
+// EPMC: prop 33 | action 12 | R (world<-base inertial, row major) 9 | pos 3 | target 3 | |base_pos| 1   (perception is evaluated while the row is written)
+template <int ENV>
 LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const float* snew_warp, const float* hist_warp, int env0, int n_envs,
                           int mode, unsigned row_mask) {
+  constexpr int OW = ObsW<ENV>::value;
   const int lane = threadIdx.x & 31;
 #pragma unroll 4
-  for (int base = 0; base < 8 * kObsDim; base += 32) {
+  for (int base = 0; base < 8 * OW; base += 32) {
     int idx = base + lane;
-    int e = idx / kObsDim, j = idx - e * kObsDim;
-    bool ok = idx < 8 * kObsDim && (env0 + e) < n_envs && ((row_mask >> e) & 1u);
+    int e = idx / OW, j = idx - e * OW;
+    bool ok = idx < 8 * OW && (env0 + e) < n_envs && ((row_mask >> e) & 1u);
     float v = 0.f;
     if (ok) {
       const float* sn = snew_warp + e * kNewObs;
@@ -310,23 +339,40 @@ LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const floa
         int a = j - 99;
         if (mode == 1) v = 0.f;
         else v = a < 24 ? hs[66 + a] : sn[kPropDim + a - 24];
-      } else {
+      } else if (ENV == 0) {
         v = sn[45 + (j - 135)];
+      } else if (j < 460) {
+        v = 0.f;                                   // percep_2d: every down-ray hits the slab top, hit z = 0 (PGE:431-447)
+      } else if (j < 588) {
+        v = sn[60];                                // percep_1d: horizontal rays miss => |ray_from| (PGE:49-53,388-394)
+      } else if (j < 913) {                        // percep_front (PGE:409-429) against the ground slab
+        int t = j - 588, i = t / 13, jj = t - i * 13;
+        float y = i == 24 ? 0.25f : -0.25f + (float)i * (0.5f / 24.0f);
+        float z = jj == 12 ? 0.1f : -0.3f + (float)jj * (0.4f / 12.0f);
+        float fz = fmaf(sn[52], y, fmaf(sn[53], z, sn[56]));          // from.z = R[2,1] y + R[2,2] z + pos.z
+        float dz = 3.0f * sn[51];                                     // (to - from).z = 3 R[2,0]
+        float len = 3.0f * sqrtf(sn[45] * sn[45] + sn[48] * sn[48] + sn[51] * sn[51]);
+        float tz = fz + dz;
+        v = (fz > 0.f && tz < 0.f) ? len * (fz / (fz - tz)) : len;
+      } else {
+        v = sn[57 + (j - 913)];
       }
-      obs[(size_t)(env0 + e) * kObsDim + j] = v;
+      obs[(size_t)(env0 + e) * OW + j] = v;
       if (obs2) obs2[(size_t)(env0 + e) * obs2_ld + j] = v;
     }
   }
 }
 
 // Asynchronous (cp.async) prefetch issued at kernel start; consumed after the ten sub-steps, so DRAM latency is hidden.
+template <int ENV>
 LLQ_DI void prefetch_history(const float* obs, float* hist_warp, int env0, int n_envs) {
+  constexpr int OW = ObsW<ENV>::value;
   const int lane = threadIdx.x & 31;
   for (int idx = lane; idx < 8 * kHist; idx += 32) {
     int e = idx / kHist, t = idx - e * kHist;
     int env = env0 + e < n_envs ? env0 + e : n_envs - 1;
     int j = t < 66 ? 33 + t : 99 + 12 + (t - 66);
-    __pipeline_memcpy_async(hist_warp + idx, obs + (size_t)env * kObsDim + j, 4);
+    __pipeline_memcpy_async(hist_warp + idx, obs + (size_t)env * OW + j, 4);
   }
 }
 LLQ_DI void prefetch_model(const ModelConst* gmodel, ModelConst* smodel, int nthreads) {
@@ -338,10 +384,10 @@ LLQ_DI void prefetch_model(const ModelConst* gmodel, ModelConst* smodel, int nth
 
 // ---------------------------------------------------------------------------------------------------------------
 // The fused policy-step kernel.
-template <int BLOCK>
+template <int BLOCK, int ENV>
 __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev mc, StepParams P, const ModelConst* __restrict__ gmodel,
                                                          const float* __restrict__ actions, float* obs2, long long obs2_ld,
-                                                         int* __restrict__ winner) {
+                                                         int* __restrict__ winner, unsigned long long seed, long long gid0) {
   __shared__ __align__(16) ModelConst M;
   __shared__ __align__(16) float s_new[BLOCK / 4][kNewObs];
   __shared__ __align__(16) float s_hist[BLOCK / 4][kHist];
@@ -350,7 +396,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
   const int N = P.n_envs;
   prefetch_model(gmodel, &M, BLOCK);
   __pipeline_commit();
-  prefetch_history(E.obs, &s_hist[(tid & ~31) >> 2][0], (blockIdx.x * BLOCK + (tid & ~31)) >> 2, N);
+  prefetch_history<ENV>(E.obs, &s_hist[(tid & ~31) >> 2][0], (blockIdx.x * BLOCK + (tid & ~31)) >> 2, N);
   __pipeline_commit();
   __pipeline_wait_prior(1);              // model constants have landed; the history copy stays in flight
   __syncthreads();
@@ -379,8 +425,32 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
   }
   float warm = E.warm[k * N + env];
   double time = E.time[env];
-  const int clip = E.clip[env];
+  const int clip = ENV == 0 ? E.clip[env] : 0;
   int frame_id = 0; double frame_frac = 0.0;
+  // ---- EPMC bookkeeping (replicated on the 4 lanes): joystick command, push randomiser, per-episode friction
+  int counter = 0, cmd_freq = 1, push_count = 0, push_draws = 0, cmd_draws = 0;
+  double tgx = 0.0, tgy = 0.0, total_spd = 0.0, max_spd = 0.0, target_angle = 0.0, last_len = 0.0;
+  float target_spd = 0.f, pf[3] = {0.f, 0.f, 0.f}, mu_env = P.mu;
+  long long epi = 0;
+  if (ENV == 1) {
+    const double* A = E.aux;
+    counter = (int)A[env]; cmd_freq = (int)A[N + env]; tgx = A[2 * N + env]; tgy = A[3 * N + env];
+    target_spd = (float)A[4 * N + env]; target_angle = A[5 * N + env]; last_len = A[6 * N + env]; total_spd = A[7 * N + env];
+    max_spd = A[8 * N + env]; push_count = (int)A[9 * N + env]; pf[0] = (float)A[10 * N + env]; pf[1] = (float)A[11 * N + env];
+    pf[2] = (float)A[12 * N + env]; mu_env = P.mu_ground * (float)A[13 * N + env]; push_draws = (int)A[14 * N + env];
+    cmd_draws = (int)A[15 * N + env];
+    epi = E.episode[env] - 1;                             // streams of the running episode (the reset advanced the counter)
+    if (counter % cmd_freq == 0) {                        // PGE:302-317, element_id 0
+      double u[4];
+      stream_uniforms(seed, gid0 + env, epi, 3, (unsigned)cmd_draws++, u);
+      target_angle = 2.0 * 3.14159265358979323846 * u[0];
+      double sn, cs;
+      sincos(target_angle, &sn, &cs);
+      tgx = px + cs * 100.0; tgy = py + sn * 100.0;
+      last_len = sqrt((px - tgx) * (px - tgx) + (py - tgy) * (py - tgy));
+      target_spd = (float)((double)P.ts_lo + u[1] * ((double)P.ts_hi - (double)P.ts_lo));
+    }
+  }
   // base orientation: pybullet speaks in the base inertial frame; dynamics run in URDF body axes B' = inertial * qI^-1
   const Q4 qI = Q4{M.base.qI[0], M.base.qI[1], M.base.qI[2], M.base.qI[3]};
   Q4 qp = qmul(qnormalize(qb), qconj(qI));
@@ -400,6 +470,15 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     for (int i = 0; i < 3; i++) {
       float t = fmaf(P.kp, tgt[i] - q[i], P.kd * (0.f - qd[i]));
       tau[i] = clampf(t, -P.max_tau, P.max_tau) - L.j[i].jdamp * qd[i];
+    }
+    // ---------------- EPMC push randomiser (PR:56-87): counters in sub-steps, force lasts one sub-step
+    bool push_on = false;
+    if (ENV == 1 && P.push_enabled) {
+      push_count += 1;
+      if (push_count > 0) {
+        if (push_count % P.push_interval == 0) { epmc_randomize_push(P, seed, gid0 + env, epi, push_draws, pf); push_count = 0; }
+        push_on = push_count < P.push_duration;
+      }
     }
     // ---------------- kinematics
     const M3 R = qmat(qp);                       // world <- B'
@@ -435,6 +514,13 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     {
       ABI I1 = rigid_abi(L.j[0].m, ld3(L.j[0].h), ldsym(L.j[0].I));
       SV p1 = bias_force<2>(L.j[0].m, ld3(L.j[0].h), ldsym(L.j[0].I), L.j[0].nd, L.j[0].d, v1.a, v1.l, P.kl, P.ka);
+      if (ENV == 1 && push_on && k == 0) {
+        // applyExternalForce(link 0 = FR hip, LINK_FRAME): force given in the hip's inertial frame, applied at its CoM
+        const V3 fl = V3{M.push_R[0] * pf[0] + M.push_R[1] * pf[1] + M.push_R[2] * pf[2], M.push_R[3] * pf[0] + M.push_R[4] * pf[1] + M.push_R[5] * pf[2],
+                         M.push_R[6] * pf[0] + M.push_R[7] * pf[1] + M.push_R[8] * pf[2]};
+        p1.a = p1.a - cross(ld3(M.push_c), fl);
+        p1.l = p1.l - fl;
+      }
       IA.A = IA.A + I1.A; IA.B = IA.B + I1.B; IA.C = IA.C + I1.C; pA.a = pA.a + p1.a; pA.l = pA.l + p1.l;
     }
     joint_reduce<0, 1>(IA, pA, c1, tau[0], r[0], jc[0]);
@@ -736,7 +822,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           }
         }
       }
-      const float mu = P.mu;
+      const float mu = ENV == 1 ? mu_env : P.mu;
 #pragma unroll 1
       for (int it = 0; it < P.solver_iters; it++) {
         if (any_lim_warp) {
@@ -868,12 +954,16 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     }
     bad = bad || !(fabsf(qd[0]) <= P.vmax) || !(fabsf(ww.x) <= P.vmax) || !(fabsf(vw.x) <= P.vmax);
     // ---------------- mocap clock (PLE:208-210): sampled with the time *before* the increment
-    frame_id = (int)floor(time / P.frame_dt);
-    frame_frac = (time - frame_id * P.frame_dt) / P.frame_dt;
+    if (ENV == 0) {
+      frame_id = (int)floor(time / P.frame_dt);
+      frame_frac = (time - frame_id * P.frame_dt) / P.frame_dt;
+    }
     time += P.sim_dt;
   }
 
   // ================= end of the policy step: observation, reward, termination =================
+  bool done = false;
+  if (ENV == 0) {
   qb = qmul(qp, qI);                                 // back to the pybullet (inertial-frame) convention
   float* snew = &s_new[threadIdx.x >> 2][0];
   ObsCtx oc = build_obs_new(mc, P, M, k, clip, frame_id, frame_frac, px, py, pz, qb, vw, ww, q, qd, snew);
@@ -917,7 +1007,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     bad = bi != 0;
   }
   if (bad || !isfinite(rew)) { rew = 0.f; bad = true; }
-  bool done = fall || ended || diff || bad;
+  done = fall || ended || diff || bad;
 
   // ---- write back state (SoA)
   if (valid) {
@@ -952,6 +1042,77 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       }
     }
   }
+  } else {
+    // ---------------- EPMC tail (PGE:334-358, 360-372, 479-502)
+    qb = qmul(qp, qI);
+    float* snew = &s_new[threadIdx.x >> 2][0];
+    const Q4 q1 = qnormalize(qb);
+    const M3 Rq = qmat(q1);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { snew[3 * k + i] = q[i]; snew[12 + 3 * k + i] = qd[i]; snew[kPropDim + 3 * k + i] = act[i]; }
+    counter += 1;
+    const double dx = tgx - px, dy = tgy - py;
+    const double plen = sqrt(dx * dx + dy * dy);
+    if (k == 0) {
+      V3 wl = tmul(Rq, ww), vl = tmul(Rq, vw);
+      snew[24] = wl.x; snew[25] = wl.y; snew[26] = wl.z; snew[27] = vl.x; snew[28] = vl.y; snew[29] = vl.z;
+      snew[30] = Rq.a20; snew[31] = Rq.a21; snew[32] = Rq.a22;
+      snew[45] = Rq.a00; snew[46] = Rq.a01; snew[47] = Rq.a02; snew[48] = Rq.a10; snew[49] = Rq.a11; snew[50] = Rq.a12;
+      snew[51] = Rq.a20; snew[52] = Rq.a21; snew[53] = Rq.a22;
+      snew[54] = (float)px; snew[55] = (float)py; snew[56] = (float)pz;
+      V3 d = tmul(Rq, V3{(float)dx, (float)dy, (float)(0.0 - pz)});
+      float n2 = sqrtf(d.x * d.x + d.y * d.y);
+      snew[57] = d.x / n2; snew[58] = d.y / n2; snew[59] = target_spd;
+      snew[60] = (float)sqrt(px * px + py * py + pz * pz);
+    }
+    const float left_z = Rq.a02 * Rq.a10 - Rq.a12 * Rq.a00;
+    const bool fall = left_z > 0.70710678118654752f || left_z < -0.70710678118654752f || Rq.a22 < 0.5f;
+    const bool reach = plen < 0.5, timeup = counter >= P.max_steps;
+    const float ux = (float)(dx / plen), uy = (float)(dy / plen);
+    const float spd = fabsf(vw.x * ux + vw.y * uy);
+    total_spd += (double)spd;
+    if ((double)spd > max_spd) max_spd = (double)spd;
+    const float yaw = atan2f(Rq.a10, Rq.a00);
+    float sy, cy;
+    sincosf(yaw, &sy, &cy);
+    float rew = expf(-fabsf(spd - target_spd)) * expf((cy * ux + sy * uy - 1.0f) * 5.0f) / (float)P.max_steps;
+    {
+      int bi = bad ? 1 : 0;
+      bi |= __shfl_xor_sync(FULL, bi, 1);
+      bi |= __shfl_xor_sync(FULL, bi, 2);
+      bad = bi != 0;
+    }
+    if (bad || !isfinite(rew)) { rew = 0.f; bad = true; }
+    done = fall || timeup || reach || bad;
+    V3 fd;
+    {
+      V3 f = mul(qmat(qp), foot_in_base(L, q[0], q[1], q[2]));
+      fd = V3{(float)px + f.x, (float)py + f.y, (float)pz + f.z};
+    }
+    if (valid) {
+      float* sw = E.st;
+#pragma unroll
+      for (int i = 0; i < 3; i++) { sw[(10 + 3 * k + i) * N + env] = q[i]; sw[(22 + 3 * k + i) * N + env] = qd[i]; }
+      E.warm[k * N + env] = warm;
+      E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
+      if (k == 0) {
+        E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
+        sw[env] = qb.x; sw[N + env] = qb.y; sw[2 * N + env] = qb.z; sw[3 * N + env] = qb.w;
+        sw[4 * N + env] = vw.x; sw[5 * N + env] = vw.y; sw[6 * N + env] = vw.z;
+        sw[7 * N + env] = ww.x; sw[8 * N + env] = ww.y; sw[9 * N + env] = ww.z;
+        E.time[env] = time;
+        E.reward_sum[env] += rew;
+        E.episode_steps[env] += 1;
+        E.reward[env] = rew;
+        E.done[env] = done ? 1 : 0;
+        double* A = E.aux;
+        A[env] = counter; A[N + env] = cmd_freq; A[2 * N + env] = tgx; A[3 * N + env] = tgy; A[4 * N + env] = target_spd;
+        A[5 * N + env] = target_angle; A[6 * N + env] = last_len; A[7 * N + env] = total_spd; A[8 * N + env] = max_spd;
+        A[9 * N + env] = push_count; A[10 * N + env] = pf[0]; A[11 * N + env] = pf[1]; A[12 * N + env] = pf[2];
+        A[14 * N + env] = push_draws; A[15 * N + env] = cmd_draws;
+      }
+    }
+  }
   // counters: one atomic per warp
   {
     unsigned long long cr = n_contact_rows, lr = n_limit_rows;
@@ -969,7 +1130,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
   __pipeline_wait_prior(0);
   __syncwarp();
   const int warp_env0 = (blockIdx.x * BLOCK + (threadIdx.x & ~31)) >> 2;
-  emit_obs_rows(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], &s_hist[(threadIdx.x & ~31) >> 2][0], warp_env0, N, 0, 0xFFu);
+  emit_obs_rows<ENV>(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], &s_hist[(threadIdx.x & ~31) >> 2][0], warp_env0, N, 0, 0xFFu);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -989,7 +1150,7 @@ struct ResetParams {
   int update_table;                           // 1 after a step
 };
 
-template <int BLOCK>
+template <int BLOCK, int ENV>
 __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev mc, StepParams P, const ModelConst* __restrict__ gmodel,
                                                           ResetParams RP, float* obs2, long long obs2_ld) {
   extern __shared__ double s_cdf[];            // [n_clips]
@@ -1013,7 +1174,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
   __syncthreads();
   for (int c = threadIdx.x; c < C; c += BLOCK) s_cdf[c] = pow(1.0 - s_cdf[c], RP.factor);
   __syncthreads();
-  if (threadIdx.x == 0) {
+  if (threadIdx.x == 0 && C > 0) {
     double tot = 0;
     for (int c = 0; c < C; c++) tot += s_cdf[c];
     double acc = 0;
@@ -1042,6 +1203,64 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
   if (wm == 0) return;                                   // warp-uniform: nothing to reset in these 8 envs
   const LegConst& L = M.leg[k];
 
+  if (ENV == 1) {
+    // ---------------- EPMC reset (PGE:196-249)
+    long long ep = E.episode[env];
+    const long long gid = RP.gid0 + env;
+    double u[4];
+    stream_uniforms(RP.seed, gid, ep, 1, 0, u);
+    const double foot_mu = (double)P.fr_lo + u[0] * ((double)P.fr_hi - (double)P.fr_lo);                   // PGE:209-210
+    int push_draws = 0;
+    float pf[3] = {0.f, 0.f, 0.f};
+    if (P.push_enabled) epmc_randomize_push(P, RP.seed, gid, ep, push_draws, pf);                          // PR:52-54
+    const int cmd_freq = P.cmd_freq_lo + (int)floor(u[2] * (double)(P.cmd_freq_hi - P.cmd_freq_lo));       // PGE:223
+    const double yaw_deg = fmod(E.aux[16 * N + env] + 360.0 * u[1], 360.0);                                // PGE:181-189 (accumulates)
+    double sn, cs;
+    sincos(0.5 * yaw_deg * (3.14159265358979323846 / 180.0), &sn, &cs);
+    const float* I0 = M.init_state;
+    const Q4 qn = qmul(qnormalize(Q4{I0[3], I0[4], I0[5], I0[6]}), Q4{0.f, 0.f, (float)sn, (float)cs});
+    float q[3], qd[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { q[i] = I0[13 + 3 * k + i]; qd[i] = I0[25 + 3 * k + i]; }
+    const V3 lin = V3{I0[7], I0[8], I0[9]}, ang = V3{I0[10], I0[11], I0[12]};
+    float* snew = &s_new[threadIdx.x >> 2][0];
+    const M3 Rq = qmat(qnormalize(qn));
+    const float target_spd = (float)E.aux[4 * N + env];            // persists across episodes (PGE:170-172)
+#pragma unroll
+    for (int i = 0; i < 3; i++) { snew[3 * k + i] = q[i]; snew[12 + 3 * k + i] = qd[i]; }
+    if (k == 0) {
+      V3 wl = tmul(Rq, ang), vl = tmul(Rq, lin);
+      snew[24] = wl.x; snew[25] = wl.y; snew[26] = wl.z; snew[27] = vl.x; snew[28] = vl.y; snew[29] = vl.z;
+      snew[30] = Rq.a20; snew[31] = Rq.a21; snew[32] = Rq.a22;
+      snew[45] = Rq.a00; snew[46] = Rq.a01; snew[47] = Rq.a02; snew[48] = Rq.a10; snew[49] = Rq.a11; snew[50] = Rq.a12;
+      snew[51] = Rq.a20; snew[52] = Rq.a21; snew[53] = Rq.a22;
+      snew[54] = 0.f; snew[55] = 0.f; snew[56] = 0.5f;
+      V3 d = tmul(Rq, V3{8.0f, 0.f, -0.5f});                        // target (8,0,0) - pos (0,0,0.5)  (BSE:247-248)
+      float n2 = sqrtf(d.x * d.x + d.y * d.y);
+      snew[57] = d.x / n2; snew[58] = d.y / n2; snew[59] = target_spd;
+      snew[60] = 0.5f;
+    }
+    if (doit) {
+      float* sw = E.st;
+      const Q4 qI = Q4{M.base.qI[0], M.base.qI[1], M.base.qI[2], M.base.qI[3]};
+      V3 f = mul(qmat(qmul(qnormalize(qn), qconj(qI))), foot_in_base(L, q[0], q[1], q[2]));
+#pragma unroll
+      for (int i = 0; i < 3; i++) { sw[(10 + 3 * k + i) * N + env] = q[i]; sw[(22 + 3 * k + i) * N + env] = qd[i]; }
+      E.warm[k * N + env] = 0.f;
+      E.foot_pos[(3 * k) * N + env] = f.x; E.foot_pos[(3 * k + 1) * N + env] = f.y; E.foot_pos[(3 * k + 2) * N + env] = 0.5f + f.z;
+      if (k == 0) {
+        E.pos[env] = 0.0; E.pos[N + env] = 0.0; E.pos[2 * N + env] = 0.5;
+        float b[10] = {qn.x, qn.y, qn.z, qn.w, lin.x, lin.y, lin.z, ang.x, ang.y, ang.z};
+#pragma unroll
+        for (int i = 0; i < 10; i++) sw[i * N + env] = b[i];
+        E.time[env] = 0.0; E.reward_sum[env] = 0.f; E.episode_steps[env] = 0; E.episode[env] = ep + 1;
+        double* A = E.aux;
+        A[env] = 0; A[N + env] = cmd_freq; A[2 * N + env] = 8.0; A[3 * N + env] = 0.0; A[6 * N + env] = 8.0; A[7 * N + env] = 0.0;
+        A[8 * N + env] = 0.0; A[9 * N + env] = P.push_start_count; A[10 * N + env] = pf[0]; A[11 * N + env] = pf[1]; A[12 * N + env] = pf[2];
+        A[13 * N + env] = foot_mu; A[14 * N + env] = push_draws; A[15 * N + env] = 0; A[16 * N + env] = yaw_deg;
+      }
+    }
+  } else {
   int clip; double t0;
   long long ep = E.episode[env];
   if (RP.mode == 2) { clip = RP.clip_in[env]; t0 = RP.time_in[env]; }
@@ -1093,12 +1312,13 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
       E.time[env] = t0; E.clip[env] = clip; E.reward_sum[env] = 0.f; E.episode_steps[env] = 0; E.episode[env] = ep;
     }
   }
+  }
   __syncwarp();
   unsigned rows = 0;
 #pragma unroll
   for (int e = 0; e < 8; e++) if ((wm >> (4 * e)) & 1u) rows |= 1u << e;
   const int warp_env0 = (blockIdx.x * BLOCK + (threadIdx.x & ~31)) >> 2;
-  emit_obs_rows(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], &s_new[0][0], warp_env0, N, 1, rows);
+  emit_obs_rows<ENV>(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], &s_new[0][0], warp_env0, N, 1, rows);
 }
 
 }  // namespace llq

@@ -84,9 +84,30 @@ def test_epmc_push_schedule_k7(oracle_lib, blob, gold):
 
 @pytest.mark.gpu
 def test_cuda_replays_reference_epmc_golden(gold, built, blob):
-    eng = capi.VecEngine(capi.load_cuda_library(), 1, blob, None, seed=int(gold["seed"]), max_steps=int(gold["max_steps"]), **EPMC_CFG)
+    """Open loop in fp32: trajectories separate chaotically once the robot flails, so the continuous quantities are only
+    compared over the first steps of every episode; resets (incl. the sampled friction / yaw / command frequency / push
+    force) are compared tightly.  Teacher-forced parity is in tests/test_parity_epmc_gpu.py."""
+    g = gold
+    eng = capi.VecEngine(capi.load_cuda_library(), 1, blob, None, seed=int(g["seed"]), max_steps=int(g["max_steps"]), **EPMC_CFG)
     assert eng.obs_dim == 916
-    # open loop in fp32: the discrete bookkeeping must match exactly; continuous quantities within a drift allowance
-    worst = _replay(eng, gold, 2e-2, 1.0, check_state=False)
-    print("cuda vs reference EPMC golden (open loop): worst rel obs err %.2e" % worst)
+    eng.set_init_state(g["init_state"])
+    first = {int(ep): int(np.argmax(g["episode"] == ep)) for ep in np.unique(g["episode"])}
+    for ep in range(len(g["reset_obs"])):
+        if ep > 0:   # the replay of the previous episode was truncated: carry over what persists across resets (target_spd)
+            aux = eng.get(capi.F_AUX); aux[0, 4] = g["aux"][first[ep] - 1][4]; eng.set(capi.F_AUX, aux)
+        obs = eng.reset()
+        want = g["reset_obs"][ep]
+        assert np.max(np.abs(obs[0] - want) / (1 + np.abs(want))) < 1e-5
+        aux = eng.get(capi.F_AUX)[0]
+        assert np.allclose(aux[[0, 1, 9, 14, 15]], g["reset_aux"][ep][[0, 1, 9, 14, 15]])
+        assert np.allclose(aux[[2, 3, 4, 6, 10, 11, 12, 13]], g["reset_aux"][ep][[2, 3, 4, 6, 10, 11, 12, 13]], rtol=1e-5, atol=1e-6)
+        for t in range(8):
+            step = first[ep] + t
+            o, r, d = eng.step(g["action"][step][None])
+            want = _obs_of(g, step)
+            assert np.max(np.abs(o[0] - want) / (1 + np.abs(want))) < 1e-3, ("obs", step)
+            assert abs(r[0] - g["reward"][step]) < 1e-6 and bool(d[0]) == bool(g["done"][step])
+            aux = eng.get(capi.F_AUX)[0]
+            assert np.allclose(aux[[0, 1, 9, 14, 15]], g["aux"][step][[0, 1, 9, 14, 15]])
+            assert np.allclose(aux[[2, 3, 4, 5, 10, 11, 12, 13]], g["aux"][step][[2, 3, 4, 5, 10, 11, 12, 13]], rtol=1e-4, atol=1e-4)
     eng.close()
