@@ -27,6 +27,13 @@ MU_A = np.array([.0124, -.011, -.0793, -.0125, -.0108, -.0806, .0402, -.0505, -.
 SIGMA_A = np.array([.0853, .1525, .1747, .0847, .1503, .1766, .1025, .2023, .3701, .1021, .2035, .426], np.float32)
 TRAJ_WIDTH = 223                        # obs 207 | action 12 | reward | done | neglogp | value  
 UNROLL = 128                            # example_pmc_train.sh:145
+METRIC = {"pmc": "env-steps/sec PMC mocap-tracking", "epmc": "env-steps/sec EPMC playground (element 0, flat joystick arena)"}
+WORKLOAD = {"pmc": "4096-env batched PMC mocap-tracking, flat ground, per GPU (BASELINE configs[1])",
+            "epmc": "8192-env batched EPMC playground, element_id 0 = flat joystick arena of example_epmc_train.sh (BASELINE configs[2] "
+                    "asks for box/heightfield terrain, which is not built yet), per GPU"}
+# algorithmic bytes per env-step: PMC 157 words read + 262 written; EPMC without a terrain box list: 177 read + 991 written
+ALGO_BYTES = {"pmc": 1676, "epmc": 4672}
+OBS_W = {"pmc": 207, "epmc": 916}
 
 
 def parse():
@@ -39,7 +46,12 @@ def parse():
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL trajectory gather to rank 0")
     ap.add_argument("--block", type=int, default=0, help="CUDA block size override (32/64/128)")
     ap.add_argument("--cpu-envs", type=int, default=256, help="CPU arm: environments per step (bounded sample)")
-    return ap.parse_args()
+    ap.add_argument("--env", default="pmc", choices=["pmc", "epmc"],
+                    help="pmc = BASELINE configs[1] (headline); epmc = configs[2] on the flat element-0 arena (8192 envs)")
+    a = ap.parse_args()
+    if a.env == "epmc" and a.envs == 4096:
+        a.envs = 8192
+    return a
 
 
 def synthetic_inputs(n_clips=66):
@@ -94,12 +106,28 @@ class ClockSampler(threading.Thread):
                 "samples": len(sm)}
 
 
-def time_cpu_arm(n_envs, steps, warmup, threads=0):
+def make_engine(lib_or_none, n, env, **over):
+    """Engine for the bench workload on the CUDA library (lib_or_none=None) or a given library (the oracle)."""
+    from lifelike_agility_and_play_b200 import _capi as capi
+    lib = lib_or_none if lib_or_none is not None else capi.load_cuda_library()
+    blob, mocap = synthetic_inputs()
+    if env == "epmc":
+        from lifelike_agility_and_play_b200.sim_envs.playground_env import INIT_STATE_RUN_0, epmc_engine_config
+        erc = {'element_id': 0, 'friction_range': [0.4, 3.0], 'cmd_vary_freq_range': [9999, 10000], 'target_spd_range': [0.5, 3.0],
+               'disturb_force_config': {'start_time': 0.5, 'interval_time': 1.0, 'duration_time': 0.2, 'horizontal_force': [0, 50], 'vertical_force': [0, 10]}}
+        cfg = epmc_engine_config(50.0, 50.0, 0.5, 16, 1000, erc)       # train_scripts/example_epmc_train.sh:88-117
+        cfg.update(over)
+        eng = capi.VecEngine(lib, n, blob, None, **cfg)
+        eng.set_init_state(INIT_STATE_RUN_0)
+        return eng
+    return capi.VecEngine(lib, n, blob, mocap, **over)
+
+
+def time_cpu_arm(n_envs, steps, warmup, threads=0, env="pmc"):
     """Oracle port of the reference step on the host cores (kind 'port': the reference itself is Python over the
     pybullet wheel, which is not installable here -- DESIGN.md 6)."""
     from oracle import oracle
-    blob, mocap = synthetic_inputs()
-    eng = oracle.make_engine(n_envs, blob, mocap, seed=1234, auto_reset=1, num_threads=threads)
+    eng = make_engine(oracle.load(), n_envs, env, seed=1234, auto_reset=1, num_threads=threads)
     eng.reset()
     pool = action_pool_np(n_envs, 8, 5678)
     for i in range(warmup):
@@ -116,14 +144,13 @@ def run_reference(args, rank):
     if rank != 0:
         return
     n = args.cpu_envs
-    val, dt, cores = time_cpu_arm(n, args.steps, args.warmup)
+    val, dt, cores = time_cpu_arm(n, args.steps, args.warmup, env=args.env)
     sample = "%d envs x %d steps of the 4096-env workload, oracle/libllq_cpu.so, OpenMP over envs" % (n, args.steps)
     line = {
-        "impl": "reference", "metric": "env-steps/sec PMC mocap-tracking", "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
+        "impl": "reference", "metric": METRIC[args.env], "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-        "config": {"workload": "4096-env batched PMC mocap-tracking, flat ground (BASELINE configs[1]); CPU arm steps a %d-env sample" % n,
-                   "envs_per_step": n},
+        "config": {"workload": WORKLOAD[args.env] + "; CPU arm steps a %d-env sample" % n, "envs_per_step": n},
         "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
         "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
@@ -148,9 +175,9 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     n = args.envs
-    blob, mocap = synthetic_inputs()
-    eng = capi.VecEngine(capi.load_cuda_library(), n, blob, mocap, device=local_rank, seed=1234, auto_reset=1,
-                         global_env_offset=rank * n)
+    ow = OBS_W[args.env]
+    traj_w = ow + 16                        # obs | action 12 | reward | done | neglogp | value
+    eng = make_engine(None, n, args.env, device=local_rank, seed=1234, auto_reset=1, global_env_offset=rank * n)
     if args.block:
         eng.set_option("block", args.block)
     eng.reset()
@@ -158,7 +185,7 @@ def main():
     POOL = 16
     pool = torch.from_numpy(action_pool_np(n, POOL, 5678 + rank)).to(dev)
     do_gather = world > 1 and not args.no_gather
-    slab = torch.zeros((UNROLL, n, TRAJ_WIDTH), device=dev, dtype=torch.float32)     # [T, N_local, 223] send slab
+    slab = torch.zeros((UNROLL, n, traj_w), device=dev, dtype=torch.float32)         # [T, N_local, obs+16] send slab
     reward = torch.zeros((n,), device=dev, dtype=torch.float32)
     done = torch.zeros((n,), device=dev, dtype=torch.uint8)
     recv = None
@@ -176,10 +203,10 @@ def main():
         t = i % UNROLL
         row = slab[t]
         # the fused kernel writes the observation straight into the trajectory slab (row stride 223 floats)
-        eng.step_device(pool[i % POOL].data_ptr(), row.data_ptr(), reward.data_ptr(), done.data_ptr(), obs_ld=TRAJ_WIDTH, stream=stream)
-        row[:, 207:219] = pool[i % POOL]
-        row[:, 219] = reward
-        row[:, 220] = done
+        eng.step_device(pool[i % POOL].data_ptr(), row.data_ptr(), reward.data_ptr(), done.data_ptr(), obs_ld=traj_w, stream=stream)
+        row[:, ow:ow + 12] = pool[i % POOL]
+        row[:, ow + 12] = reward
+        row[:, ow + 13] = done
 
     def gather():
         dist.gather(slab, recv, dst=0)
@@ -253,7 +280,7 @@ def main():
     # end-to-end through the public host API (numpy in, numpy out; H2D + D2H inside the timed region)
     e2e_steps = min(args.steps, 128)
     host_pool = action_pool_np(n, 4, 999 + rank)
-    out = (np.empty((n, capi.OBS_DIM), np.float32), np.empty((n,), np.float32), np.empty((n,), np.uint8))
+    out = (np.empty((n, ow), np.float32), np.empty((n,), np.float32), np.empty((n,), np.uint8))
     for i in range(4):
         eng.step(host_pool[i % 4], out=out)
     eng.sync()
@@ -281,36 +308,38 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    achieved = ALGO_BYTES_PER_ENV_STEP * n / (kern_ms * 1e-3) / 1e9
+    achieved = ALGO_BYTES[args.env] * n / (kern_ms * 1e-3) / 1e9
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("pmc_step_kernel_dram_bytes_per_launch")
     except Exception:
         pass
     line = {
-        "metric": "env-steps/sec PMC mocap-tracking", "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
+        "metric": METRIC[args.env], "value": value, "unit": "env-steps/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": "4096-env batched PMC mocap-tracking, flat ground, per GPU (BASELINE configs[1]%s)"
-                   % ("; configs[3] sharding" if world > 1 else ""),
-                   "envs_per_gpu": n, "global_envs": n * world, "substeps": 10, "solver_iters": 10, "mocap": "66 synthetic clips, 229k frames",
-                   "auto_reset": True, "prioritized_sample_factor": 3.0, "actions": "N(mu_a, sigma_a) clipped +-1, device resident",
+        "config": {"workload": WORKLOAD[args.env] + ("; sharded as in configs[3]" if world > 1 else ""),
+                   "envs_per_gpu": n, "global_envs": n * world, "substeps": 10, "solver_iters": 10,
+                   "mocap": "66 synthetic clips, 229k frames" if args.env == "pmc" else None,
+                   "auto_reset": True, "prioritized_sample_factor": 3.0 if args.env == "pmc" else None,
+                   "actions": "N(mu_a, sigma_a) clipped +-1, device resident",
                    "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events summed",
-                   "parallelism": "env shards x%d%s" % (world, ", NCCL gather of [128,N,223] slabs to rank 0 every 128 steps" if do_gather else "")},
+                   "parallelism": "env shards x%d%s" % (world, ", NCCL gather of [128,N,obs+16] slabs to rank 0 every 128 steps" if do_gather else "")},
         "value_hot_l2": n * world * args.steps / (hot_ms * 1e-3),
         "value_no_gather": n * world * args.steps / (step_ms * 1e-3),
         "gather_ms_total": gather_ms, "wall_s_timed_region": wall,
-        "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": n * 12 * 4, "d2h_bytes_per_step": n * (207 * 4 + 4 + 1),
+        "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": n * 12 * 4, "d2h_bytes_per_step": n * (ow * 4 + 4 + 1),
                 "steps": e2e_steps, "api": "VecEngine.step(numpy) -> llq_step (host buffers, pinned staging)"},
         "gpu_launches": int(c1[4] - c0[4]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "pmc_step_kernel", "kernel_ms": kern_ms, "algorithmic_bytes_per_env_step": ALGO_BYTES_PER_ENV_STEP,
+                     "kernel": "pmc_step_kernel<128,%d>" % (1 if args.env == "epmc" else 0), "kernel_ms": kern_ms,
+                     "algorithmic_bytes_per_env_step": ALGO_BYTES[args.env],
                      "peak_source": peak_src,
                      "note": "latency/issue bound by design (SURVEY 7): ~2e5 flop per 1.7 kB; see profiles/"},
         "clocks": sampler.summary(),
     }
     if world == 1:
-        cval, cdt, cores = time_cpu_arm(args.cpu_envs, 24, 2)
+        cval, cdt, cores = time_cpu_arm(args.cpu_envs, 24, 2, env=args.env)
         line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": cores, "kind": "port",
                                 "sample": "%d envs x 24 steps of the same workload on the host cores (oracle/libllq_cpu.so, OpenMP)" % args.cpu_envs}
     print(json.dumps(line), flush=True)

@@ -1,0 +1,123 @@
+"""Gym-style single-environment adaptor for the environmental-level (EPMC) playground env.
+
+Mirrors ``PlayGroundEnv`` (reference max_game_elements/playground_env.py:57-539) for ``element_id == 0`` -- the flat
+"joystick" arena that the shipped training script selects (train_scripts/example_epmc_train.sh:100): same constructor
+keywords, observation / action spaces (PGE:129-150), ``reset(**kwargs)``, ``step(rl_action)`` (dict with ``A_LLC`` or a
+bare 12-vector, PGE:323), ``info`` keys on termination (PGE:345-357).  Elements 1-3 (hurdles / holes / cubes: box terrain,
+BulletStatics) are SURVEY rows a19/a21 still to be built and raise ``NotImplementedError``.
+"""
+from collections import OrderedDict
+
+import numpy as np
+
+from .. import _capi as capi
+from .. import spaces
+from ..model.compile_model import load_model_blob
+from .primitive_level_env import SHIPPED_PROP_TYPE, _FULL_PROP_SIZE
+
+# LeggedRobot.get_init_states_info() (LR:115-117) -> utils/constants.py:103-116 STATES_INFO_12_RUN_0
+INIT_STATE_RUN_0 = np.array(
+    [0.0, 0.0, 0.3343530097022097,
+     0.013840790797843786, 0.023505515131419717, -0.0003254560394373679, 0.9996278394216837,
+     0.00809597744709567, -0.020893862693440735, -0.001824006727717542,
+     0.0838167925768054, -0.00447012899185979, 0.04114855957667429,
+     -0.02776715425087109, -0.7790427096234822, 1.687309016042587, -0.02761322597239251, -0.7777310768160954, 1.6837882482054838,
+     -0.02776264511056588, -0.7333994876717276, 1.5669191826863689, -0.027617718742577027, -0.7319111056361625, 1.5631584243808343,
+     -0.05228733284239881, -0.0686649273790696, 0.05668137846569721, -0.03640328999561543, -0.02286152438035316, 0.0029650694829541635,
+     0.010717179495497164, -0.09457474021233203, 0.10883376594280847, 0.023988549884502025, -0.055563832783516176, 0.03375014202679161])
+
+
+def _default_engine_factory(n_envs, model_blob, **cfg):
+    return capi.VecEngine(capi.load_cuda_library(), n_envs, model_blob, None, **cfg)
+
+
+engine_factory = _default_engine_factory      # tests swap this for the oracle
+
+
+def epmc_engine_config(control_freq=50, kp=50.0, kd=1.0, max_tau=16, max_steps=1000, env_randomize_config=None):
+    """llq_config fields for the EPMC env from the reference's kwargs (PGE:57-179, PR:7-54); the integer sub-step counts
+    use the reference's own float floor divisions (PR:45-46,53: 0.2 // 0.002 = 100, 1.0 // 0.002 = 499, -0.5 // 0.002 = -250)."""
+    erc = env_randomize_config
+    time_step = 1.0 / 500.0                                                                  # PGE:85
+    cfg = dict(env_kind=capi.ENV_EPMC, sim_dt=time_step, policy_dt=1.0 / control_freq, substeps=int((1.0 / control_freq) / time_step),
+               kp=kp, kd=kd, max_tau=float(max_tau), ground_friction=1.0,                   # max_game_elements plane.urdf:5
+               max_steps=int(max_steps), friction_lo=float(erc['friction_range'][0]), friction_hi=float(erc['friction_range'][1]),
+               target_spd_lo=float(erc['target_spd_range'][0]), target_spd_hi=float(erc['target_spd_range'][1]))
+    lo, hi = erc.get('cmd_vary_freq_range', [25, 200])                                        # PGE:170
+    cfg.update(cmd_freq_lo=int(lo), cmd_freq_hi=int(hi))
+    dfc = erc.get('disturb_force_config')
+    if dfc is not None:
+        d = dict(start_time=0., interval_time=5., duration_time=0.5, horizontal_force=20, vertical_force=5)
+        d.update(dfc)
+        assert d['duration_time'] <= d['interval_time']                                      # PR:35
+        assert isinstance(d['horizontal_force'], list) and isinstance(d['vertical_force'], list)   # PR:91-92
+        cfg.update(push_enabled=1, push_start_count=int(-d['start_time'] // time_step),
+                   push_interval_steps=int(d['interval_time'] // time_step), push_duration_steps=int(d['duration_time'] // time_step),
+                   push_h_lo=float(d['horizontal_force'][0]), push_h_hi=float(d['horizontal_force'][1]),
+                   push_v_lo=float(d['vertical_force'][0]), push_v_hi=float(d['vertical_force'][1]))
+    else:
+        cfg.update(push_enabled=0)
+    return cfg
+
+
+class PlayGroundEnv:
+    metadata = {}
+
+    def __init__(self, enable_render=False, control_freq=50, kp=50.0, kd=1.0, max_tau=16, prop_type=None, stack_frame_num=3,
+                 max_steps=1000, obs_randomization=None, env_randomize_config=None, seed=0, device=0):
+        if not isinstance(prop_type, list):
+            raise TypeError("Expected 'prop_type' to be a list.")                            # PGE:125-126
+        for e in prop_type:
+            if e not in _FULL_PROP_SIZE:
+                raise KeyError(e)
+        if list(prop_type) != SHIPPED_PROP_TYPE or stack_frame_num != 3:
+            raise NotImplementedError("the engine implements the shipped prop_type with stack_frame_num=3")
+        if env_randomize_config['element_id'] != 0:
+            raise NotImplementedError("EPMC element_id %r (box terrain, SURVEY rows a19/a21) is not built yet; element_id 0 is"
+                                      % (env_randomize_config['element_id'],))
+        if obs_randomization:
+            raise NotImplementedError("obs_randomization (episodic observation noise, PGE:174-179) is not built yet")
+        if isinstance(max_tau, (list, tuple)):
+            max_tau = float(np.random.uniform(*max_tau))                                     # LR:244 (PGE:236 writes a dead attribute)
+        self._max_steps = max_steps
+        self._engine = engine_factory(1, load_model_blob(), device=device, seed=seed, auto_reset=0,
+                                      **epmc_engine_config(control_freq, kp, kd, max_tau, max_steps, env_randomize_config))
+        self._engine.set_init_state(INIT_STATE_RUN_0)
+        self.observation_space = spaces.Dict(OrderedDict({                                   # PGE:129-137
+            'prop': spaces.Box(0, 0, shape=(99,)), 'prop_a': spaces.Box(0, 0, shape=(36,)),
+            'percep_2d': spaces.Box(0, 0, shape=(25, 13)), 'percep_1d': spaces.Box(0, 0, shape=(128,)),
+            'percep_front': spaces.Box(0, 0, shape=(25, 13)), 'target': spaces.Box(0, 0, shape=(3,)),
+        }))
+        self.action_space = spaces.Dict(OrderedDict({'A_Z': spaces.Discrete(256), 'A_LLC': spaces.Box(0, 0, shape=(12,))}))   # PGE:141-144
+        self.reward_type = 'joystick'
+        self.episodic_reward = OrderedDict({'reward_vel': 0.0, 'reward_rotation': 0.0, 'reward_dist': 0.0, 'reward_avg_spd': 0.0})
+
+    @staticmethod
+    def _split(row):
+        return OrderedDict({'prop': row[0:99].copy(), 'prop_a': row[99:135].copy(), 'percep_2d': row[135:460].reshape(25, 13).copy(),
+                            'percep_1d': row[460:588].copy(), 'percep_front': row[588:913].reshape(25, 13).copy(),
+                            'target': row[913:916].copy()})
+
+    def reset(self, **kwargs):
+        return self._split(self._engine.reset()[0])                                          # PGE:196-249
+
+    def step(self, rl_action):
+        a = rl_action['A_LLC'] if isinstance(rl_action, dict) and 'A_LLC' in rl_action else rl_action    # PGE:323
+        obs, reward, done = self._engine.step(np.asarray(a, dtype=np.float32).reshape(1, 12))
+        info = {}
+        if done[0]:                                                                           # PGE:345-357
+            aux = self._engine.get(capi.F_AUX)[0]
+            info['ave_spd'] = float(aux[7] / aux[0])
+            info['max_spd'] = float(aux[8])
+        return self._split(obs[0]), float(reward[0]), bool(done[0]), info
+
+    def close(self):
+        if self._engine is not None:
+            self._engine.close()
+            self._engine = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

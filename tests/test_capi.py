@@ -118,7 +118,60 @@ def test_gym_surface_on_oracle(monkeypatch, oracle_lib, small_mocap):
     with pytest.raises(TypeError):
         create_envs.create_tracking_game(**dict(_tracking_cfg(small_mocap), prop_type=""))             # PLE:112-113
     with pytest.raises(NotImplementedError):
-        create_envs.create_playground_game(arena_id="Playground")
+        create_envs.create_chase_tag_game(arena_id="CTG")
+
+
+EPMC_ENV_CONFIG = {
+    'arena_id': 'Playground', 'render': False, 'control_freq': 50.0,
+    'prop_type': ['joint_pos', 'joint_vel', 'root_ang_vel_loc', 'root_lin_vel_loc', 'e_g'],
+    'kp': 50.0, 'kd': 0.5, 'max_tau': 16, 'max_steps': 30, 'obs_randomization': {},
+    'env_randomize_config': {
+        'element_id': 0, 'height_range': [0.0, 0.0], 'friction_range': [0.4, 3.0],
+        'disturb_force_config': {'start_time': 0.5, 'interval_time': 1.0, 'duration_time': 0.2, 'horizontal_force': [0, 50], 'vertical_force': [0, 10]},
+        'cmd_vary_freq_range': [9999, 10000], 'target_spd_range': [0.5, 3.0], 'auxiliary_radius': 0.02,
+        'hole_config': {'min_gap_height': 0.25, 'max_gap_height': 0.25}},
+}
+
+
+def _drive_epmc(env):
+    """The loop of test_scripts/environmental_level/test_environmental_level_env.py, head-less, random policy."""
+    obs = env.reset(inter_kwargs={})
+    assert list(obs[0].keys()) == ['prop', 'prop_a', 'percep_2d', 'percep_1d', 'percep_front', 'target']
+    assert [obs[0][k].shape for k in obs[0]] == [(99,), (36,), (25, 13), (128,), (25, 13), (3,)]
+    assert np.all(obs[0]['percep_2d'] == 0) and np.allclose(obs[0]['percep_1d'], 0.5)          # flat ground; |base_pos| = 0.5 (K8)
+    rng = np.random.default_rng(0)
+    dones = 0
+    for t in range(70):
+        obs, rwd, done, info = env.step([{'A_Z': 0, 'A_LLC': (0.1 * rng.standard_normal(12)).astype(np.float32)}])
+        assert isinstance(done, bool) and 0.0 <= rwd[0] <= 1.0 / 30 + 1e-9
+        assert abs(np.linalg.norm(obs[0]['target'][:2]) - 1.0) < 1e-5 and 0.5 <= obs[0]['target'][2] <= 3.0
+        if done:
+            assert set(info) >= {'ave_spd', 'max_spd'}
+            dones += 1
+            obs = env.reset()
+    assert dones >= 2          # max_steps = 30
+
+
+def test_epmc_gym_surface_on_oracle(monkeypatch, oracle_lib):
+    from lifelike_agility_and_play_b200.sim_envs import create_envs, playground_env as pge
+    monkeypatch.setattr(pge, "engine_factory", lambda n, blob, **cfg: capi.VecEngine(oracle_lib, n, blob, None, **{k: v for k, v in cfg.items() if k != "device"}))
+    env = create_envs.create_playground_game(**EPMC_ENV_CONFIG)
+    assert list(env.action_space.spaces[0].spaces.keys()) == ['A_Z', 'A_LLC']
+    _drive_epmc(env)
+    env.close()
+    cfg = pge.epmc_engine_config(50.0, 50.0, 0.5, 16, 1000, EPMC_ENV_CONFIG['env_randomize_config'])
+    assert (cfg['push_start_count'], cfg['push_interval_steps'], cfg['push_duration_steps'], cfg['substeps']) == (-250, 499, 100, 10)   # K7
+    bad = dict(EPMC_ENV_CONFIG, env_randomize_config=dict(EPMC_ENV_CONFIG['env_randomize_config'], element_id=1))
+    with pytest.raises(NotImplementedError):
+        create_envs.create_playground_game(**bad)
+
+
+@pytest.mark.gpu
+def test_epmc_gym_surface_on_cuda():
+    from lifelike_agility_and_play_b200.sim_envs import create_envs
+    env = create_envs.create_playground_game(**EPMC_ENV_CONFIG)
+    _drive_epmc(env)
+    env.close()
 
 
 @pytest.mark.gpu
