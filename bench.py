@@ -278,19 +278,29 @@ def main():
     value = total_env_steps / (total_ms * 1e-3)
 
     # end-to-end through the public host API (numpy in, numpy out; H2D + D2H inside the timed region)
+    # (actions come from pinned host memory, results are read back into pinned host memory: VecEngine.step_pinned)
     e2e_steps = min(args.steps, 128)
     host_pool = action_pool_np(n, 4, 999 + rank)
-    out = (np.empty((n, ow), np.float32), np.empty((n,), np.float32), np.empty((n,), np.uint8))
+    act_p, obs_p, rew_p, done_p = eng.pinned_io()
     for i in range(4):
-        eng.step(host_pool[i % 4], out=out)
+        act_p[...] = host_pool[i % 4]
+        eng.step_pinned(act_p, obs_p, rew_p, done_p)
     eng.sync()
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
     for i in range(e2e_steps):
-        eng.step(host_pool[i % 4], out=out)
+        act_p[...] = host_pool[i % 4]               # the policy's output lands in the pinned action buffer
+        eng.step_pinned(act_p, obs_p, rew_p, done_p)
+        _ = float(rew_p[0])                         # host reads the step's result
     eng.sync()
     e2e_s = time.perf_counter() - t0
+    # the plain numpy API (pageable buffers, staging copies inside llq_step) for comparison
+    out = (np.empty((n, ow), np.float32), np.empty((n,), np.float32), np.empty((n,), np.uint8))
+    t1 = time.perf_counter()
+    for i in range(32):
+        eng.step(host_pool[i % 4], out=out)
+    e2e_pageable = n * 32 / (time.perf_counter() - t1)
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
@@ -329,7 +339,8 @@ def main():
         "value_no_gather": n * world * args.steps / (step_ms * 1e-3),
         "gather_ms_total": gather_ms, "wall_s_timed_region": wall,
         "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": n * 12 * 4, "d2h_bytes_per_step": n * (ow * 4 + 4 + 1),
-                "steps": e2e_steps, "api": "VecEngine.step(numpy) -> llq_step (host buffers, pinned staging)"},
+                "steps": e2e_steps, "api": "VecEngine.step_pinned(numpy over page-locked memory) -> llq_step_ex(LLQ_IO_PINNED)",
+                "value_pageable_numpy_api": e2e_pageable * world},
         "gpu_launches": int(c1[4] - c0[4]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                      "kernel": "pmc_step_kernel<128,%d>" % (1 if args.env == "epmc" else 0), "kernel_ms": kern_ms,

@@ -58,6 +58,8 @@ extern "C" {
 /* pointer-space flags for llq_step_ex / llq_reset_ex */
 #define LLQ_IO_HOST    0   /* pointers are host memory (pageable or pinned); copies happen inside the call */
 #define LLQ_IO_DEVICE  1   /* pointers are device memory on the handle's GPU; no host round trip, no sync */
+#define LLQ_IO_PINNED  2   /* pointers are page-locked host memory (llq_host_alloc / cudaHostAlloc / cudaHostRegister): the copies
+                              go straight between the caller's buffers and the device, no staging memcpy; synchronous like HOST */
 
 /* field ids for llq_get_field / llq_set_field (host pointers, row-major, [n_envs, width]) */
 #define LLQ_F_STATE       0  /* float   [N,37]  robot state, pybullet base-inertial-frame convention (LR:86-106) */
@@ -182,6 +184,10 @@ int llq_get_counters(llq_handle h, int64_t* out, int32_t n);
  * Other options: "block" = CUDA block size (32, 64, 128).  The CPU oracle returns LLQ_EUNSUPPORTED. */
 int llq_set_option(llq_handle h, const char* name, double value);
 int llq_get_timing(llq_handle h, double* out, int32_t n);
+
+/* Page-locked host buffers for LLQ_IO_PINNED (plain malloc/free in the CPU oracle). */
+int llq_host_alloc(void** out, int64_t bytes);
+int llq_host_free(void* p);
 
 /* Block until all work enqueued by this handle has finished (no-op for the CPU oracle). */
 int llq_sync(llq_handle h);

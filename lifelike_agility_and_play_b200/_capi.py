@@ -14,7 +14,7 @@ import numpy as np
 
 STATE_DIM, ACTION_DIM, PROP_DIM, OBS_DIM, MOCAP_FRAME = 37, 12, 33, 207, 19
 
-LLQ_IO_HOST, LLQ_IO_DEVICE = 0, 1
+LLQ_IO_HOST, LLQ_IO_DEVICE, LLQ_IO_PINNED = 0, 1, 2
 (F_STATE, F_CLIP, F_TIME, F_REWARD_SUM, F_EPISODE_STEPS, F_WARMSTART, F_OBS, F_KIN_STATE, F_SAMPLE_PROB,
  F_AVG_REWARD, F_EPISODE_ID, F_FOOT_POS, F_DECISION_MARGIN, F_AUX) = range(14)
 ENV_PMC, ENV_EPMC, OBS_DIM_EPMC, AUX_DIM = 0, 1, 916, 18
@@ -59,7 +59,7 @@ class LlqError(RuntimeError):
 
 _EXPORTS = ["llq_abi_version", "llq_default_config", "llq_create", "llq_destroy", "llq_load_model", "llq_load_mocap",
             "llq_reset", "llq_reset_to", "llq_step", "llq_step_ex", "llq_get_field", "llq_set_field",
-            "llq_get_counters", "llq_set_option", "llq_get_timing", "llq_obs_dim", "llq_set_init_state", "llq_sync", "llq_last_error"]
+            "llq_get_counters", "llq_set_option", "llq_get_timing", "llq_obs_dim", "llq_set_init_state", "llq_host_alloc", "llq_host_free", "llq_sync", "llq_last_error"]
 
 
 class LlqLibrary:
@@ -89,6 +89,8 @@ class LlqLibrary:
         L.llq_set_field.argtypes = [vp, C.c_int, vp]
         L.llq_get_counters.argtypes = [vp, vp, C.c_int32]
         L.llq_sync.argtypes = [vp]
+        L.llq_host_alloc.argtypes = [C.POINTER(vp), C.c_int64]
+        L.llq_host_free.argtypes = [vp]
         L.llq_obs_dim.argtypes = [vp]
         L.llq_set_init_state.argtypes = [vp, vp]
         L.llq_set_option.argtypes = [vp, C.c_char_p, C.c_double]
@@ -174,6 +176,9 @@ class VecEngine:
         if self._h:
             self.lib.lib.llq_destroy(self._h)
             self._h = C.c_void_p()
+            for p in getattr(self, "_pinned", []):
+                self.lib.lib.llq_host_free(p)
+            self._pinned = []
 
     def __del__(self):
         try:
@@ -211,6 +216,30 @@ class VecEngine:
             obs, rew, done = out
         self.lib.check(self.lib.lib.llq_step(self._h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done)))
         return obs, rew, done
+
+    # -- page-locked I/O (LLQ_IO_PINNED): no staging memcpy on either side
+    def pinned_array(self, shape, dtype):
+        """numpy array over page-locked host memory owned by this engine (freed on close)."""
+        dtype = np.dtype(dtype)
+        nbytes = int(np.prod(shape)) * dtype.itemsize
+        p = C.c_void_p()
+        self.lib.check(self.lib.lib.llq_host_alloc(C.byref(p), nbytes))
+        if not hasattr(self, "_pinned"):
+            self._pinned = []
+        self._pinned.append(p)
+        buf = (C.c_char * nbytes).from_address(p.value)
+        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+
+    def pinned_io(self):
+        """(actions, obs, reward, done) page-locked buffers for step_pinned."""
+        return (self.pinned_array((self.n, ACTION_DIM), np.float32), self.pinned_array((self.n, self.obs_dim), np.float32),
+                self.pinned_array((self.n,), np.float32), self.pinned_array((self.n,), np.uint8))
+
+    def step_pinned(self, actions, obs, reward, done):
+        """Like step(), but all four arrays must be page-locked (pinned_io()); results land in obs / reward / done."""
+        self.lib.check(self.lib.lib.llq_step_ex(self._h, _ptr(actions), _ptr(obs), self.obs_dim, _ptr(reward), _ptr(done),
+                                                 LLQ_IO_PINNED, None))
+        return obs, reward, done
 
     def step_device(self, actions_ptr, obs_ptr, reward_ptr, done_ptr, obs_ld=None, stream=None):
         obs_ld = self.obs_dim if obs_ld is None else obs_ld

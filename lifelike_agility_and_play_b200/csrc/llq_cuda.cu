@@ -450,6 +450,9 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
     std::memcpy(h->h_actions, actions, sizeof(float) * LLQ_ACTION_DIM * n);
     CK(cudaMemcpyAsync(h->d_actions, h->h_actions, sizeof(float) * LLQ_ACTION_DIM * n, cudaMemcpyHostToDevice, s));
     d_act = h->d_actions;
+  } else if (io_mode == LLQ_IO_PINNED) {
+    CK(cudaMemcpyAsync(h->d_actions, actions, sizeof(float) * LLQ_ACTION_DIM * n, cudaMemcpyHostToDevice, s));
+    d_act = h->d_actions;
   } else {
     return fail(LLQ_EINVAL, "bad io_mode");
   }
@@ -474,6 +477,14 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
     }
     if (reward) std::memcpy(reward, h->h_reward, sizeof(float) * n);
     if (done) std::memcpy(done, h->h_done, n);
+  } else if (io_mode == LLQ_IO_PINNED) {
+    if (obs) {
+      if ((size_t)obs_ld == od) CK(cudaMemcpyAsync(obs, h->E.obs, sizeof(float) * od * n, cudaMemcpyDeviceToHost, s));
+      else CK(cudaMemcpy2DAsync(obs, sizeof(float) * obs_ld, h->E.obs, sizeof(float) * od, sizeof(float) * od, n, cudaMemcpyDeviceToHost, s));
+    }
+    if (reward) CK(cudaMemcpyAsync(reward, h->E.reward, sizeof(float) * n, cudaMemcpyDeviceToHost, s));
+    if (done) CK(cudaMemcpyAsync(done, h->E.done, n, cudaMemcpyDeviceToHost, s));
+    CK(cudaStreamSynchronize(s));
   }
   return LLQ_OK;
 }
@@ -628,6 +639,16 @@ int llq_get_timing(llq_handle h, double* out, int32_t n) {
   CK(cudaEventElapsedTime(&a, h->ev[0], h->ev[1]));
   CK(cudaEventElapsedTime(&b, h->ev[1], h->ev[2]));
   out[0] = a; out[1] = b;
+  return LLQ_OK;
+}
+
+int llq_host_alloc(void** out, int64_t bytes) {
+  if (!out || bytes <= 0) return fail(LLQ_EINVAL, "bad arguments");
+  CK(cudaHostAlloc(out, (size_t)bytes, cudaHostAllocPortable));
+  return LLQ_OK;
+}
+int llq_host_free(void* p) {
+  if (p) CK(cudaFreeHost(p));
   return LLQ_OK;
 }
 

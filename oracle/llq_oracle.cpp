@@ -27,6 +27,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdint>
+#include <cstdlib>
 #include <cstring>
 #include <string>
 #include <vector>
@@ -846,7 +847,7 @@ void epmc_randomize_push(llq_engine& E, Env& e, int64_t gid) {   // PR:89-99
 
 // PGE:374-447 on the flat 200 x 200 ground slab (top face z = 0) -- the only static body of element 0 besides the
 // degenerate target marker (BSE:106-131 gives its collision box zero extents).
-void epmc_drill(const llq_engine& E, const Env& e, const double* st, float* percep /* 325 + 128 + 325 + 3 */) {
+void epmc_drill(const llq_engine& /*E*/, const Env& e, const double* st, float* percep /* 325 + 128 + 325 + 3 */) {
   Q4 qb = qnormalize({st[3], st[4], st[5], st[6]});
   M3 R = qmat(qb);
   V3 pos = {st[0], st[1], st[2]};
@@ -1161,7 +1162,7 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
   int rc = check_ready(h, true);
   if (rc) return rc;
   if (!actions) return fail(LLQ_EINVAL, "null actions");
-  if (io_mode != LLQ_IO_HOST) return fail(LLQ_EUNSUPPORTED, "CPU oracle only takes host pointers");
+  if (io_mode != LLQ_IO_HOST && io_mode != LLQ_IO_PINNED) return fail(LLQ_EUNSUPPORTED, "CPU oracle only takes host pointers");
   const int od = h->obs_dim();
   if (obs && obs_ld < od) return fail(LLQ_EINVAL, "obs_ld smaller than the observation width");
   const int n = h->cfg.n_envs;
@@ -1306,6 +1307,12 @@ int llq_get_counters(llq_handle h, int64_t* out, int32_t n) {
 }
 
 int llq_sync(llq_handle h) { return h ? LLQ_OK : fail(LLQ_EINVAL, "null handle"); }
+int llq_host_alloc(void** out, int64_t bytes) {
+  if (!out || bytes <= 0) return fail(LLQ_EINVAL, "bad arguments");
+  *out = std::malloc((size_t)bytes);
+  return *out ? LLQ_OK : fail(LLQ_ENOMEM, "out of memory");
+}
+int llq_host_free(void* p) { std::free(p); return LLQ_OK; }
 
 int llq_set_option(llq_handle, const char*, double) { return fail(LLQ_EUNSUPPORTED, "the CPU oracle has no options"); }
 int llq_get_timing(llq_handle, double*, int32_t) { return fail(LLQ_EUNSUPPORTED, "the CPU oracle has no device timing"); }

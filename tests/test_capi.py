@@ -197,3 +197,17 @@ def test_mocap_loader_roundtrip(tmp_path, small_mocap):
     assert rep[0]["limit_violations"] == 0 and rep[0]["quat_norm_err"] < 1e-9
     with pytest.raises(FileNotFoundError):
         load_mocap(str(tmp_path / "missing"))
+
+
+def test_pinned_io_path_matches_plain_step(make_oracle):
+    """LLQ_IO_PINNED entry (page-locked buffers, no staging copy) gives the same results as llq_step."""
+    a, b = make_oracle(6, seed=4), make_oracle(6, seed=4)
+    a.reset(); b.reset()
+    act_p, obs_p, rew_p, done_p = b.pinned_io()
+    rng = np.random.default_rng(1)
+    for _ in range(3):
+        act = (0.1 * rng.standard_normal((6, 12))).astype(np.float32)
+        o, r, d = a.step(act)
+        act_p[...] = act
+        b.step_pinned(act_p, obs_p, rew_p, done_p)
+        assert np.array_equal(o, obs_p) and np.array_equal(r, rew_p) and np.array_equal(d, done_p)
