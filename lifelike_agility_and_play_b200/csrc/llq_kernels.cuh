@@ -14,6 +14,9 @@
 //   MotionLib.step/get_states_info(_future)    primitive_level_env/motion_lib.py:65-166
 //   _prepare_obs/_compute_reward/_check_terminate   primitive_level_env.py:276-426
 #pragma once
+#ifndef LLQ_BARRIERS
+#define LLQ_BARRIERS 1   // CTA barriers per sub-step that keep the warps on the same code stretch (instruction-cache sharing)
+#endif
 #include "llq_math.cuh"
 #include <cuda_pipeline.h>
 #include <stdint.h>
@@ -500,7 +503,9 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     vj.a = V3{0.f, -qd[2], 0.f};
     v3.a.y -= qd[2];
     SV c3 = SV{cross(v3.a, vj.a), cross(v3.l, vj.a)};
+#if LLQ_BARRIERS >= 5
     if (BLOCK > 32) __syncthreads();
+#endif
     // ---------------- ABA pass 2: articulated inertia, leaf -> root inside the lane
     ABI IA = rigid_abi(L.j[2].m, ld3(L.j[2].h), ldsym(L.j[2].I));
     SV pA = bias_force<2>(L.j[2].m, ld3(L.j[2].h), ldsym(L.j[2].I), L.j[2].nd, L.j[2].d, v3.a, v3.l, P.kl, P.ka);
@@ -524,7 +529,9 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       IA.A = IA.A + I1.A; IA.B = IA.B + I1.B; IA.C = IA.C + I1.C; pA.a = pA.a + p1.a; pA.l = pA.l + p1.l;
     }
     joint_reduce<0, 1>(IA, pA, c1, tau[0], r[0], jc[0]);
+#if LLQ_BARRIERS >= 3
     if (BLOCK > 32) __syncthreads();
+#endif
     // ---------------- base: sum the four legs (xor shuffles), add the base body, factorise
     float m6[21], z0[6];
     {
@@ -587,7 +594,9 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     // predicted velocity in base coordinates (generalised velocity used by the constraint rows)
     const V3 wbs = tmul(R, ww), vbs = tmul(R, vw);
 
+#if LLQ_BARRIERS >= 2
     if (BLOCK > 32) __syncthreads();
+#endif
     // ---------------- leg kinematics and the ABA's per-joint vectors, re-expressed in base coordinates about the base origin
     const float kc1 = jc[0].c, ks1 = jc[0].s, kc2 = jc[1].c, ks2 = jc[1].s;
     const float kc23 = kc2 * jc[2].c - ks2 * jc[2].s, ks23 = ks2 * jc[2].c + kc2 * jc[2].s;
@@ -933,7 +942,9 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       __syncwarp();
     }
 
+#if LLQ_BARRIERS >= 4
     if (BLOCK > 32) __syncthreads();
+#endif
     // ---------------- apply the impulses, clamp, integrate (btMultiBody::stepPositionsMultiDof)
     {
       V3 dw = mul(R, V3{dvb[0], dvb[1], dvb[2]}), dv = mul(R, V3{dvb[3], dvb[4], dvb[5]});
