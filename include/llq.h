@@ -75,6 +75,7 @@ extern "C" {
 #define LLQ_F_EPISODE_ID  10 /* int64   [N]     per-env episode counter (RNG stream position) */
 #define LLQ_F_FOOT_POS    11 /* float   [N,12]  world positions of the 4 foot links after the last step (LR:199-205) -- get only */
 #define LLQ_F_AUX         13 /* double  [N,18]  EPMC bookkeeping (LLQ_AUX_DIM): counters, joystick target, push randomiser, friction */
+#define LLQ_F_OB_ID       14 /* int32   [N]     PMC hurdle: index of the active plate within the clip's plate list (PLE:179,264-265) */
 #define LLQ_F_DECISION_MARGIN 12 /* float [N]   CPU oracle only, get only: smallest distance to a discontinuous branch taken during
                                    the last step: min(|q-limit|) over joints [rad], min(|dist-contact_breaking|) over feet [m].
                                    Parity tests use it to tell rounding noise from a flipped joint-limit / contact decision. */
@@ -149,6 +150,16 @@ int llq_load_model(llq_handle h, const double* blob, int64_t n_doubles);
 /* Replaces: MotionLib._open_all_mocap_datas (ML:19-46).  frames: [total_frames,19] float64 (clips back to
  * back, file order = sorted names), clip_offsets: [n_clips+1] prefix offsets, frame_dt = "FrameDuration". */
 int llq_load_mocap(llq_handle h, const double* frames, const int32_t* clip_offsets, int32_t n_clips, double frame_dt);
+
+/* Replaces: MotionLib.obstacles_info + PrimitiveLevelEnv._create_obstacle / _update_obstacle (ML:38-42, PLE:173-193,262-268,
+ * utils/obstacle.py:6-33) -- set_obstacle=True.  table: [total,4] float64 rows (apex time [s], x, y, yaw) of every clip's
+ * hurdle plates back to back, offsets: [n_clips+1]; half extents of the plate (PLE:184: 0.025, 0.5, obstacle_height).
+ * An episode ends when the robot touches the active plate (PLE:341-346).  Contact is evaluated on the poses of the last
+ * sub-step (what getContactPoints reports after stepSimulation) with detection proxies: foot / wheel / hip spheres and the
+ * body box corners -- a coarse stand-in for Bullet's exact link shapes; the plate exerts no force (the episode ends anyway).
+ * Must be called after llq_load_mocap. */
+int llq_load_obstacles(llq_handle h, const double* table, const int32_t* offsets, int32_t n_clips, double half_x, double half_y,
+                       double half_z);
 
 /* Replaces: PrimitiveLevelEnv.reset (PLE:150-171) for every env with mask[i] != 0 (mask == NULL: all).
  * Clip ~ prioritized_sample_probability, phase ~ U(0,1) (ML:48-63), drawn from Philox4x32-10 keyed by

@@ -16,7 +16,7 @@ STATE_DIM, ACTION_DIM, PROP_DIM, OBS_DIM, MOCAP_FRAME = 37, 12, 33, 207, 19
 
 LLQ_IO_HOST, LLQ_IO_DEVICE, LLQ_IO_PINNED = 0, 1, 2
 (F_STATE, F_CLIP, F_TIME, F_REWARD_SUM, F_EPISODE_STEPS, F_WARMSTART, F_OBS, F_KIN_STATE, F_SAMPLE_PROB,
- F_AVG_REWARD, F_EPISODE_ID, F_FOOT_POS, F_DECISION_MARGIN, F_AUX) = range(14)
+ F_AVG_REWARD, F_EPISODE_ID, F_FOOT_POS, F_DECISION_MARGIN, F_AUX, F_OB_ID) = range(15)
 ENV_PMC, ENV_EPMC, OBS_DIM_EPMC, AUX_DIM = 0, 1, 916, 18
 
 # field id -> (dtype, per-env width or None for per-clip tables)
@@ -25,7 +25,7 @@ _FIELDS = {
     F_REWARD_SUM: (np.float32, 1), F_EPISODE_STEPS: (np.int32, 1), F_WARMSTART: (np.float32, 4),
     F_OBS: (np.float32, OBS_DIM), F_KIN_STATE: (np.float32, STATE_DIM), F_SAMPLE_PROB: (np.float64, None),
     F_AVG_REWARD: (np.float64, None), F_EPISODE_ID: (np.int64, 1), F_FOOT_POS: (np.float32, 12),
-    F_DECISION_MARGIN: (np.float32, 1), F_AUX: (np.float64, AUX_DIM),
+    F_DECISION_MARGIN: (np.float32, 1), F_AUX: (np.float64, AUX_DIM), F_OB_ID: (np.int32, 1),
 }
 
 
@@ -59,7 +59,7 @@ class LlqError(RuntimeError):
 
 _EXPORTS = ["llq_abi_version", "llq_default_config", "llq_create", "llq_destroy", "llq_load_model", "llq_load_mocap",
             "llq_reset", "llq_reset_to", "llq_step", "llq_step_ex", "llq_get_field", "llq_set_field",
-            "llq_get_counters", "llq_set_option", "llq_get_timing", "llq_obs_dim", "llq_set_init_state", "llq_host_alloc", "llq_host_free", "llq_sync", "llq_last_error"]
+            "llq_get_counters", "llq_set_option", "llq_get_timing", "llq_obs_dim", "llq_set_init_state", "llq_host_alloc", "llq_host_free", "llq_load_obstacles", "llq_sync", "llq_last_error"]
 
 
 class LlqLibrary:
@@ -89,6 +89,7 @@ class LlqLibrary:
         L.llq_set_field.argtypes = [vp, C.c_int, vp]
         L.llq_get_counters.argtypes = [vp, vp, C.c_int32]
         L.llq_sync.argtypes = [vp]
+        L.llq_load_obstacles.argtypes = [vp, vp, vp, C.c_int32, C.c_double, C.c_double, C.c_double]
         L.llq_host_alloc.argtypes = [C.POINTER(vp), C.c_int64]
         L.llq_host_free.argtypes = [vp]
         L.llq_obs_dim.argtypes = [vp]
@@ -165,6 +166,13 @@ class VecEngine:
         self.obs_dim = int(lib.lib.llq_obs_dim(self._h))
         if self.obs_dim <= 0:
             lib.check(self.obs_dim)
+
+    def load_obstacles(self, table, offsets, half_extents):
+        """PMC hurdle plates (mocap.obstacle_table) -- set_obstacle=True of the reference (PLE:173-193)."""
+        t = np.ascontiguousarray(table, dtype=np.float64).reshape(-1, 4)
+        o = np.ascontiguousarray(offsets, dtype=np.int32)
+        hx, hy, hz = [float(v) for v in half_extents]
+        self.lib.check(self.lib.lib.llq_load_obstacles(self._h, _ptr(t) if t.size else None, _ptr(o), o.size - 1, hx, hy, hz))
 
     def set_init_state(self, state37):
         st = np.ascontiguousarray(state37, dtype=np.float64)

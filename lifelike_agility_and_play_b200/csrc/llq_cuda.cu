@@ -49,6 +49,7 @@ struct llq_engine {
   double* d_avg[2] = {nullptr, nullptr};
   double* d_prob = nullptr; double* d_max_steps = nullptr;
   unsigned char* d_mask = nullptr; int* d_clip_in = nullptr; double* d_time_in = nullptr;
+  double* d_ob_table = nullptr; int* d_ob_off = nullptr; bool has_obstacles = false;
   int parity = 0;
   // pinned host staging
   float* h_actions = nullptr; float* h_obs = nullptr; float* h_reward = nullptr; unsigned char* h_done = nullptr;
@@ -84,6 +85,7 @@ void fill_params(llq_handle h) {
   P.mu_ground = (float)c.ground_friction; P.fr_lo = (float)c.friction_lo; P.fr_hi = (float)c.friction_hi;
   P.ph_lo = (float)c.push_h_lo; P.ph_hi = (float)c.push_h_hi; P.pv_lo = (float)c.push_v_lo; P.pv_hi = (float)c.push_v_hi;
   P.ts_lo = (float)c.target_spd_lo; P.ts_hi = (float)c.target_spd_hi;
+  if (!h->has_obstacles) { P.has_ob = 0; P.ob_hx = P.ob_hy = P.ob_hz = 0.f; }
 }
 
 template <typename T> int dalloc(T** p, size_t n) {
@@ -104,7 +106,7 @@ int ensure_scratch(llq_handle h, size_t bytes) {
   return LLQ_OK;
 }
 
-llq::MocapDev mocap_dev(llq_handle h) { return llq::MocapDev{h->d_frames, h->d_clip_off, h->n_clips}; }
+llq::MocapDev mocap_dev(llq_handle h) { return llq::MocapDev{h->d_frames, h->d_clip_off, h->n_clips, h->d_ob_table, h->d_ob_off}; }
 
 template <int BLOCK, int ENV>
 void launch_step_t(llq_handle h, const llq::EnvArrays& E, const float* d_actions, float* obs2, long long ld, cudaStream_t s) {
@@ -242,6 +244,7 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   TRY(dalloc(&h->E.foot_pos, 12 * n)); TRY(dalloc(&h->E.done_reward, n)); TRY(dalloc(&h->E.done, n)); TRY(dalloc(&h->E.reward, n));
   TRY(dalloc(&h->E.counters, 8));
   TRY(dalloc(&h->E.aux, (size_t)LLQ_AUX_DIM * n));
+  TRY(dalloc(&h->E.ob_id, n));
   TRY(dalloc(&h->d_actions, (size_t)LLQ_ACTION_DIM * n));
   TRY(dalloc(&h->d_mask, n)); TRY(dalloc(&h->d_clip_in, n)); TRY(dalloc(&h->d_time_in, n));
   ce = cudaMallocHost((void**)&h->h_actions, sizeof(float) * LLQ_ACTION_DIM * n);
@@ -263,7 +266,7 @@ int llq_destroy(llq_handle h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* dptrs[] = {h->d_model, h->d_frames, h->d_clip_off, h->E.pos, h->E.st, h->E.time, h->E.clip, h->E.reward_sum, h->E.episode_steps,
-                   h->E.episode, h->E.warm, h->E.obs, h->E.kin, h->E.foot_pos, h->E.done_reward, h->E.done, h->E.reward, h->E.counters, h->E.aux,
+                   h->E.episode, h->E.warm, h->E.obs, h->E.kin, h->E.foot_pos, h->E.done_reward, h->E.done, h->E.reward, h->E.counters, h->E.aux, h->E.ob_id, h->d_ob_table, h->d_ob_off,
                    h->d_actions, h->d_winner[0], h->d_winner[1], h->d_avg[0], h->d_avg[1], h->d_prob, h->d_max_steps, h->d_mask,
                    h->d_clip_in, h->d_time_in, h->d_scratch};
   for (void* p : dptrs) if (p) cudaFree(p);
@@ -316,6 +319,26 @@ int llq_load_model(llq_handle h, const double* b, int64_t n) {
     const double* g = b + (int64_t)b[LLQ_H_OFF_GENERIC] + 1 * LLQ_GL;
     for (int i = 0; i < 9; i++) M.push_R[i] = (float)g[LLQ_G_RIN + i];
     for (int i = 0; i < 3; i++) M.push_c[i] = (float)g[LLQ_G_COM + i];
+  }
+  {   // detection proxies for the hurdle plate
+    const double* pr = b + (int64_t)b[LLQ_H_OFF_PROXIES];
+    const double* gen = b + (int64_t)b[LLQ_H_OFF_GENERIC];
+    int nw = 0, nh = 0, nc = 0;
+    for (int i = 0; i < (int)b[LLQ_H_NPROXIES]; i++, pr += LLQ_PROXY) {
+      const int link = (int)pr[0], kind = (int)pr[5];
+      if (kind == 1 && nw < 4) {          // wheel: its (fixed) joint origin in the thigh frame + the shape offset (joint rpy only spins the symmetric cylinder)
+        const double* g = gen + (size_t)link * LLQ_GL;
+        for (int t = 0; t < 3; t++) M.wheel_off[nw][t] = (float)(g[LLQ_G_JXYZ + t] + pr[1 + t]);
+        M.wheel_r[nw++] = (float)pr[4];
+      } else if (kind == 2 && nh < 4) {
+        M.hip_r[nh++] = (float)pr[4];
+      } else if (kind == 3 && nc < 8) {   // body corner, relative to the base reference point (body CoM), body axes
+        const double* g0 = gen;
+        for (int t = 0; t < 3; t++) M.corner[nc][t] = (float)(pr[1 + t] - g0[LLQ_G_COM + t]);
+        nc++;
+      }
+    }
+    if ((int)b[LLQ_H_NPROXIES] > 0 && (nw != 4 || nh != 4 || nc != 8)) return fail(LLQ_EINVAL, "unexpected proxy table");
   }
   for (int i = 0; i < 37; i++) M.init_state[i] = h->h_model.init_state[i];
   h->h_model = M;
@@ -379,6 +402,26 @@ int llq_load_mocap(llq_handle h, const double* frames, const int32_t* off, int32
   h->parity = 0;
   h->has_mocap = true;
   fill_params(h);
+  return LLQ_OK;
+}
+
+int llq_load_obstacles(llq_handle h, const double* table, const int32_t* offsets, int32_t n_clips, double hx, double hy, double hz) {
+  if (!h || !offsets || n_clips <= 0) return fail(LLQ_EINVAL, "bad obstacle arguments");
+  if (!h->has_mocap || n_clips != h->n_clips) return fail(LLQ_ESTATE, "llq_load_obstacles needs the mocap table first (same clip count)");
+  if (offsets[0] != 0 || (offsets[n_clips] > 0 && !table)) return fail(LLQ_EINVAL, "bad obstacle table");
+  for (int c = 0; c < n_clips; c++) if (offsets[c + 1] < offsets[c]) return fail(LLQ_EINVAL, "obstacle offsets must be non-decreasing");
+  int rc = set_device(h);
+  if (rc) return rc;
+  if (h->d_ob_table) cudaFree(h->d_ob_table);
+  if (h->d_ob_off) cudaFree(h->d_ob_off);
+  h->d_ob_table = nullptr; h->d_ob_off = nullptr;
+  const size_t total = (size_t)offsets[n_clips];
+  CK(cudaMalloc((void**)&h->d_ob_table, sizeof(double) * 4 * (total ? total : 1)));
+  if (total) CK(cudaMemcpy(h->d_ob_table, table, sizeof(double) * 4 * total, cudaMemcpyHostToDevice));
+  CK(cudaMalloc((void**)&h->d_ob_off, sizeof(int) * (n_clips + 1)));
+  CK(cudaMemcpy(h->d_ob_off, offsets, sizeof(int) * (n_clips + 1), cudaMemcpyHostToDevice));
+  h->has_obstacles = true;
+  h->P.has_ob = 1; h->P.ob_hx = (float)hx; h->P.ob_hy = (float)hy; h->P.ob_hz = (float)hz;
   return LLQ_OK;
 }
 
@@ -522,6 +565,7 @@ int llq_get_field(llq_handle h, int field, void* dst) {
     case LLQ_F_REWARD_SUM: CK(cudaMemcpy(dst, h->E.reward_sum, sizeof(float) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_EPISODE_STEPS: CK(cudaMemcpy(dst, h->E.episode_steps, sizeof(int) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_EPISODE_ID: CK(cudaMemcpy(dst, h->E.episode, sizeof(long long) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
+    case LLQ_F_OB_ID: CK(cudaMemcpy(dst, h->E.ob_id, sizeof(int) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_OBS: CK(cudaMemcpy(dst, h->E.obs, sizeof(float) * h->obs_dim * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_AUX: {
       std::vector<double> tmp((size_t)LLQ_AUX_DIM * n);
@@ -577,6 +621,7 @@ int llq_set_field(llq_handle h, int field, const void* src) {
     case LLQ_F_REWARD_SUM: CK(cudaMemcpy(h->E.reward_sum, src, sizeof(float) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
     case LLQ_F_EPISODE_STEPS: CK(cudaMemcpy(h->E.episode_steps, src, sizeof(int) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
     case LLQ_F_EPISODE_ID: CK(cudaMemcpy(h->E.episode, src, sizeof(long long) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
+    case LLQ_F_OB_ID: CK(cudaMemcpy(h->E.ob_id, src, sizeof(int) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
     case LLQ_F_OBS: CK(cudaMemcpy(h->E.obs, src, sizeof(float) * h->obs_dim * n, cudaMemcpyHostToDevice)); return LLQ_OK;
     case LLQ_F_AUX: {
       const double* a = (const double*)src;

@@ -41,6 +41,8 @@ struct alignas(16) ModelConst {
   BaseConst base; LegConst leg[4];
   float push_R[9]; float push_c[3];   // FR hip link: inertial-frame rotation (link <- inertial) and CoM, for applyExternalForce(LINK_FRAME) (PR:73-77)
   float init_state[37]; float pad_[3]; // EPMC episode start state (LR:115-117, utils/constants.py:103-116)
+  // detection proxies for the PMC hurdle plate: wheel (knee) centre in the thigh frame + radius, hip radius, body-box corners (base coords)
+  float wheel_off[4][3]; float wheel_r[4]; float hip_r[4]; float corner[8][3];
 };
 
 struct MocapFrame { double x, y, z, pad; float quat[4]; float q[12]; };  // 96 B, 16-byte aligned
@@ -54,6 +56,8 @@ struct StepParams {
   // EPMC (PGE / PR)
   int max_steps, cmd_freq_lo, cmd_freq_hi, push_start_count, push_interval, push_duration, push_enabled;
   float mu_ground, fr_lo, fr_hi, ph_lo, ph_hi, pv_lo, pv_hi, ts_lo, ts_hi;
+  // PMC hurdle plates (PLE:173-193)
+  int has_ob; float ob_hx, ob_hy, ob_hz;
 };
 
 struct EnvArrays {      // SoA device arrays, N envs
@@ -73,9 +77,10 @@ struct EnvArrays {      // SoA device arrays, N envs
   float* reward;        // [N]
   unsigned long long* counters;  // [8]
   double* aux;          // [18][N] EPMC bookkeeping (include/llq.h LLQ_F_AUX)
+  int* ob_id;           // [N] active hurdle plate
 };
 
-struct MocapDev { const MocapFrame* frames; const int* clip_off; int n_clips; };
+struct MocapDev { const MocapFrame* frames; const int* clip_off; int n_clips; const double* ob_table; const int* ob_off; };
 
 #define FULL 0xffffffffu
 
@@ -241,6 +246,13 @@ LLQ_DI void philox4x32_10(unsigned (&c)[4], unsigned k0, unsigned k1) {
     c[0] = n0; c[1] = n1; c[2] = n2; c[3] = n3;
     k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
   }
+}
+
+// distance test of a sphere (centre w in world, radius r) against the yawed plate centred at (ox, oy, 0)
+LLQ_DI bool plate_hit(V3 w, float r, float cy, float sy, float hx, float hy, float hz, float thr) {
+  float bx = cy * w.x + sy * w.y, by = -sy * w.x + cy * w.y;
+  float qx = bx - clampf(bx, -hx, hx), qy = by - clampf(by, -hy, hy), qz = w.z - clampf(w.z, -hz, hz);
+  return sqrtf(qx * qx + qy * qy + qz * qz) - r < thr;
 }
 
 // four uniforms of stream `stream` (1 = EPMC reset, 2 = push randomiser, 3 = joystick command), draw `index` (matches the oracle)
@@ -430,6 +442,8 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
   double time = E.time[env];
   const int clip = ENV == 0 ? E.clip[env] : 0;
   int frame_id = 0; double frame_frac = 0.0;
+  int ob_id = 0; bool ob_hit = false;
+  if (ENV == 0 && P.has_ob) ob_id = E.ob_id[env];
   // ---- EPMC bookkeeping (replicated on the 4 lanes): joystick command, push randomiser, per-episode friction
   int counter = 0, cmd_freq = 1, push_count = 0, push_draws = 0, cmd_draws = 0;
   double tgx = 0.0, tgy = 0.0, total_spd = 0.0, max_spd = 0.0, target_angle = 0.0, last_len = 0.0;
@@ -614,6 +628,23 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     Ul[2] = rot<0>(rot<1>(jc[2].Ul, kc23, ks23), kc1, ks1); Ua[2] = rot<0>(rot<1>(jc[2].Ua, kc23, ks23), kc1, ks1) + cross(p3, Ul[2]);
     const float Di[3] = {jc[0].Dinv, jc[1].Dinv, jc[2].Dinv};
 
+    // ---------------- PMC hurdle plate: getContactPoints (PLE:343) reports the manifolds built on the last sub-step's pre-step poses
+    if (ENV == 0 && P.has_ob && sub == P.substeps - 1) {
+      const int o0 = mc.ob_off[clip], n_ob = mc.ob_off[clip + 1] - o0;
+      if (n_ob > 0) {
+        const double* ob = mc.ob_table + (size_t)(o0 + ob_id) * 4;
+        float sy, cy;
+        sincosf((float)ob[3], &sy, &cy);
+        const V3 org = V3{(float)(px - ob[1]), (float)(py - ob[2]), (float)pz};      // base position relative to the plate centre
+        const V3 wh = p2 + rot<0>(rot<1>(ld3(M.wheel_off[k]), kc2, ks2), kc1, ks1);
+        bool hit = plate_hit(org + mul(R, fb), L.foot_r, cy, sy, P.ob_hx, P.ob_hy, P.ob_hz, P.breaking);
+        hit = hit || plate_hit(org + mul(R, wh), M.wheel_r[k], cy, sy, P.ob_hx, P.ob_hy, P.ob_hz, P.breaking);
+        hit = hit || plate_hit(org + mul(R, p1), M.hip_r[k], cy, sy, P.ob_hx, P.ob_hy, P.ob_hz, P.breaking);
+        hit = hit || plate_hit(org + mul(R, ld3(M.corner[2 * k])), 0.f, cy, sy, P.ob_hx, P.ob_hy, P.ob_hz, P.breaking);
+        hit = hit || plate_hit(org + mul(R, ld3(M.corner[2 * k + 1])), 0.f, cy, sy, P.ob_hx, P.ob_hy, P.ob_hz, P.breaking);
+        ob_hit = hit;
+      }
+    }
     // ---------------- collision: foot sphere vs plane z = 0 on the pre-step pose
     const V3 nb = V3{R.a20, R.a21, R.a22};               // world z in base coords
     // The foot clearance feeds Bullet's speculative-contact target (-penetration/dt): a 1e-7 m rounding error becomes
@@ -1018,7 +1049,15 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     bad = bi != 0;
   }
   if (bad || !isfinite(rew)) { rew = 0.f; bad = true; }
-  done = fall || ended || diff || bad;
+  if (P.has_ob) {
+    int oh = ob_hit ? 1 : 0;
+    oh |= __shfl_xor_sync(FULL, oh, 1);
+    oh |= __shfl_xor_sync(FULL, oh, 2);
+    ob_hit = oh != 0;
+    const int o0 = mc.ob_off[clip], n_ob = mc.ob_off[clip + 1] - o0;                 // PLE:262-268 hand-over to the next plate
+    while (ob_id < n_ob - 1 && time > mc.ob_table[(size_t)(o0 + ob_id) * 4] + 0.5) ob_id++;
+  }
+  done = fall || ended || diff || ob_hit || bad;                                     // PLE:347
 
   // ---- write back state (SoA)
   if (valid) {
@@ -1038,6 +1077,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       sw[4 * N + env] = vw.x; sw[5 * N + env] = vw.y; sw[6 * N + env] = vw.z;
       sw[7 * N + env] = ww.x; sw[8 * N + env] = ww.y; sw[9 * N + env] = ww.z;
       E.time[env] = time;
+      if (P.has_ob) E.ob_id[env] = ob_id;
       float rs = E.reward_sum[env] + rew;
       E.reward_sum[env] = rs;
       E.episode_steps[env] += 1;
@@ -1321,6 +1361,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
 #pragma unroll
       for (int i = 0; i < 10; i++) E.kin[(3 + i) * N + env] = b[i];
       E.time[env] = t0; E.clip[env] = clip; E.reward_sum[env] = 0.f; E.episode_steps[env] = 0; E.episode[env] = ep;
+      E.ob_id[env] = 0;                                            // PLE:179
     }
   }
   }

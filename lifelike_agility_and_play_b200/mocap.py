@@ -56,6 +56,63 @@ class MocapTable:
         return rep
 
 
+def find_peaks_height_distance(x, height, distance):
+    """numpy restatement of ``scipy.signal.find_peaks(x, height=height, distance=distance)`` as the reference uses it
+    (utils/obstacle.py:16): strict local maxima (plateaus -> their middle sample), kept if >= height, then thinned so that
+    no two peaks are closer than `distance` samples, highest first."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x)
+    peaks = []
+    i = 1
+    while i < n - 1:
+        if x[i - 1] < x[i]:
+            ahead = i + 1
+            while ahead < n - 1 and x[ahead] == x[i]:
+                ahead += 1
+            if x[ahead] < x[i]:
+                peaks.append((i + ahead - 1) // 2)
+                i = ahead
+        i += 1
+    peaks = np.array([p for p in peaks if x[p] >= height], dtype=np.int64)
+    if len(peaks) == 0:
+        return peaks
+    keep = np.ones(len(peaks), bool)
+    order = np.argsort(x[peaks], kind="stable")           # scipy's _select_by_peak_distance: highest priority last
+    dist = int(np.ceil(distance))
+    for j in order[::-1]:
+        if not keep[j]:
+            continue
+        k = j - 1
+        while k >= 0 and peaks[j] - peaks[k] < dist:
+            keep[k] = False
+            k -= 1
+        k = j + 1
+        while k < len(peaks) and peaks[k] - peaks[j] < dist:
+            keep[k] = False
+            k += 1
+    return peaks[keep]
+
+
+def obstacle_table(table: "MocapTable"):
+    """Per-clip hurdle placements (utils/obstacle.py:6-33, PLE:173-193): one plate per jump apex of the base height.
+    Returns (rows [total, 4] = apex time, x, y, yaw ; offsets [n_clips + 1])."""
+    frame_rate = int(1.0 / table.frame_dt)                                                   # ML:34
+    rows, offs = [], [0]
+    for i in range(table.n_clips):
+        c = table.clip(i)
+        try:                                   # the reference's own library call (utils/obstacle.py:16) when scipy is present
+            from scipy.signal import find_peaks
+            pk = find_peaks(c[:, 2], height=0.5, distance=120)[0]
+        except ImportError:
+            pk = find_peaks_height_distance(c[:, 2], 0.5, 120)
+        for p in pk:
+            x, y, z, w = c[p, 3:7] / np.linalg.norm(c[p, 3:7])
+            yaw = np.arctan2(2 * (x * y + z * w), 1 - 2 * (y * y + z * z))                  # atan2(R[1,0], R[0,0]) (OBS:30-31)
+            rows.append([p / frame_rate, c[p, 0], c[p, 1], yaw])
+        offs.append(len(rows))
+    return np.array(rows, dtype=np.float64).reshape(-1, 4), np.array(offs, dtype=np.int32)
+
+
 def load_mocap(path) -> MocapTable:
     """Restates ML:19-46 (file discovery + JSON parse); ``path`` is a dir of ``*.txt`` or one file."""
     if not os.path.exists(path):

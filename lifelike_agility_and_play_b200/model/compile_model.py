@@ -40,7 +40,8 @@ import numpy as np
 # (mirrored by include/llq_model_layout.h; tests/test_model.py checks the two agree)
 LLQ_MODEL_MAGIC = 0x4C4C5131  # "LLQ1"
 HDR = 16          # header doubles
-H_MAGIC, H_VERSION, H_NLINKS, H_NDOF, H_OFF_GENERIC, H_OFF_SPHERES, H_NSPHERES, H_OFF_SPECIAL, H_TOTAL = range(9)
+H_MAGIC, H_VERSION, H_NLINKS, H_NDOF, H_OFF_GENERIC, H_OFF_SPHERES, H_NSPHERES, H_OFF_SPECIAL, H_TOTAL, H_OFF_PROXIES, H_NPROXIES = range(11)
+PROXY = 8         # proxy stride: link, x, y, z (link frame), radius, kind (0 foot, 1 wheel, 2 hip, 3 body corner), 0, 0
 GL = 64           # generic per-link stride
 G_PARENT, G_JTYPE, G_DOF = 0, 1, 2
 G_JXYZ, G_JROT, G_AXIS = 3, 6, 15
@@ -374,14 +375,36 @@ def pack_model(model):
         for c in ln["collisions"]:
             if c["type"] == "sphere" and ln["name"].endswith("4"):
                 spheres.append([i, *c["xyz"], c["radius"], model["foot_friction"], 0, 0])
+    # detection-only proxy spheres used for "robot touches the PMC hurdle plate" (PLE:341-346): feet, wheels (knees), hips,
+    # body-box corners -- a coarse stand-in for Bullet's exact link shapes
+    proxies = []
+    for i, ln in enumerate(links):
+        nm = ln["name"]
+        for c in ln["collisions"]:
+            if nm.endswith("4") and c["type"] == "sphere":
+                proxies.append([i, *c["xyz"], c["radius"], 0, 0, 0])
+            elif nm.endswith("W") and c["type"] == "cylinder":
+                proxies.append([i, *c["xyz"], c["radius"], 1, 0, 0])
+            elif nm.endswith("1") and c["type"] == "cylinder":
+                proxies.append([i, *c["xyz"], c["radius"], 2, 0, 0])
+            elif nm == "body" and c["type"] == "box":
+                hx, hy, hz = 0.5 * np.array(c["size"])
+                for sx in (1, -1):
+                    for sy in (1, -1):
+                        for sz in (1, -1):
+                            proxies.append([i, c["xyz"][0] + sx * hx, c["xyz"][1] + sy * hy, c["xyz"][2] + sz * hz, 0.0, 3, 0, 0])
     off_generic = HDR
     off_spheres = off_generic + n * GL
     off_special = off_spheres + len(spheres) * SPH
-    total = off_special + S_TOTAL
+    off_proxies = off_special + S_TOTAL
+    total = off_proxies + len(proxies) * PROXY
     blob = np.zeros(total, dtype=np.float64)
     blob[H_MAGIC], blob[H_VERSION], blob[H_NLINKS], blob[H_NDOF] = LLQ_MODEL_MAGIC, 1, n, model["n_dof"]
     blob[H_OFF_GENERIC], blob[H_OFF_SPHERES], blob[H_NSPHERES] = off_generic, off_spheres, len(spheres)
     blob[H_OFF_SPECIAL], blob[H_TOTAL] = off_special, total
+    blob[H_OFF_PROXIES], blob[H_NPROXIES] = off_proxies, len(proxies)
+    for k, pr in enumerate(proxies):
+        blob[off_proxies + k * PROXY: off_proxies + (k + 1) * PROXY] = pr
     for i, ln in enumerate(links):
         g = blob[off_generic + i * GL: off_generic + (i + 1) * GL]
         g[G_PARENT] = ln["parent_index"]
@@ -478,7 +501,7 @@ def load_model_blob(path=DEFAULT_MODEL_JSON, foot_friction=None):
 def write_layout_header(path):
     """Emit include/llq_model_layout.h from the constants above (single source of truth)."""
     names = ["LLQ_MODEL_MAGIC", "HDR", "H_MAGIC", "H_VERSION", "H_NLINKS", "H_NDOF", "H_OFF_GENERIC",
-             "H_OFF_SPHERES", "H_NSPHERES", "H_OFF_SPECIAL", "H_TOTAL", "GL", "G_PARENT", "G_JTYPE", "G_DOF",
+             "H_OFF_SPHERES", "H_NSPHERES", "H_OFF_SPECIAL", "H_TOTAL", "H_OFF_PROXIES", "H_NPROXIES", "PROXY", "GL", "G_PARENT", "G_JTYPE", "G_DOF",
              "G_JXYZ", "G_JROT", "G_AXIS", "G_MASS", "G_COM", "G_RIN", "G_IDIAG", "G_LOWER", "G_UPPER",
              "G_JDAMP", "G_HASLIM", "G_ICLINK", "SPH", "S_QI", "S_BASE_M", "S_BASE_H", "S_BASE_I", "S_BASE_ND",
              "S_BASE_DAMP", "DAMP_ITEM", "S_LEGS", "LJ", "J_R", "J_AXIS_IDX", "J_AXIS_SIGN", "J_M", "J_H", "J_I",

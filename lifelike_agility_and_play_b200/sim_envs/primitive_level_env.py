@@ -47,8 +47,6 @@ class PrimitiveLevelEnv:
         if list(prop_type) != SHIPPED_PROP_TYPE or stack_frame_num != 3:
             raise NotImplementedError("the engine implements the shipped prop_type %r with stack_frame_num=3"
                                       % (SHIPPED_PROP_TYPE,))
-        if set_obstacle:
-            raise NotImplementedError("PMC hurdle obstacle (SURVEY 8 f1) is not built yet; use set_obstacle=False")
         if isinstance(max_tau, (list, tuple)):
             # LR:244 draws one value at construction; the per-episode re-draw of PLE:153 writes a dead attribute
             max_tau = float(np.random.uniform(*max_tau))
@@ -64,6 +62,10 @@ class PrimitiveLevelEnv:
             foot_friction=foot_lateral_friction, prioritized_sample_factor=prioritized_sample_factor, auto_reset=0,
             w_joint_pos=w['joint_pos'], w_joint_vel=w['joint_vel'], w_end_effector=w['end_effector'],
             w_root_pose=w['root_pose'], w_root_vel=w['root_vel'])
+        if set_obstacle:                                                                # PLE:141-142,173-193
+            from ..mocap import obstacle_table
+            tab, offs = obstacle_table(self._mocap)
+            self._engine.load_obstacles(tab, offs, (0.025, 0.5, float(obstacle_height)))  # PLE:184
         prop_size = sum(_FULL_PROP_SIZE[e] for e in prop_type) * stack_frame_num
         self.observation_space = spaces.Dict(OrderedDict({                              # PLE:117-123
             'prop': spaces.Box(0, 0, shape=(prop_size,)),

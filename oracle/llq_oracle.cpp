@@ -233,9 +233,11 @@ struct LinkM {
   double lower, upper, jdamp; bool haslim;
 };
 struct SphereM { int link; V3 c; double r, mu; };
+struct ProxyM { int link; V3 c; double r; int kind; };
 struct Model {
   std::vector<LinkM> links;
   std::vector<SphereM> spheres;
+  std::vector<ProxyM> proxies;   // detection-only spheres for the hurdle plate (llq_load_obstacles)
   int ndof = 0;
   std::vector<int> dof_link;  // dof -> link
 };
@@ -256,6 +258,7 @@ struct Env {
   // EPMC bookkeeping (PGE:146-179, PR:40-54)
   int counter, cmd_freq; double tgt_x, tgt_y, target_spd, target_angle, last_pos_diff_len, total_spd, max_spd;
   int push_count, push_draws, cmd_draws; double push_f[3];
+  int ob_id;      // active hurdle plate (PLE:179,264-265)
   double yaw_accum_deg;   // PGE:181-189 mutates the shared init-state dict: every reset's yaw is applied on top of the previous ones
   float obs[LLQ_OBS_DIM_EPMC];
 };
@@ -270,6 +273,7 @@ struct llq_engine {
   std::vector<double> max_steps, sample_prob, avg_reward;
   std::vector<Env> envs; bool was_reset = false;
   double init_state[LLQ_STATE_DIM]; bool has_init_state = false;
+  std::vector<double> ob_table; std::vector<int32_t> ob_off; double ob_half[3] = {0, 0, 0}; bool has_obstacles = false;
   int obs_dim() const { return cfg.env_kind == LLQ_ENV_EPMC ? LLQ_OBS_DIM_EPMC : LLQ_OBS_DIM; }
   int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
@@ -737,6 +741,7 @@ void reset_env(llq_engine& E, Env& e, int clip, double sampled_time) {
   mocap_state(E, frame_ptr(E, clip, e.frame_id), frame_ptr(E, clip, e.frame_id + 1), e.frame_frac, e.kin);
   unpack_state(e, e.kin);                                                // PLE:162-163
   e.reward_sum = 0; e.episode_steps = 0;
+  e.ob_id = 0;                                                                           // PLE:179
   e.foot_mu = E.cfg.foot_friction;
   for (int s = 0; s < 8; s++) e.warm[s] = 0;
   double prop[LLQ_PROP_DIM];
@@ -766,6 +771,27 @@ void sample_reset(llq_engine& E, Env& e, int64_t gid) {
   reset_env(E, e, clip, u2 * duration);                                  // ML:51
 }
 
+// Robot (detection proxies) vs the active hurdle plate: box [hx, hy, hz] centred at (x, y, 0), yawed (OBS:27-33, PLE:184-193).
+bool obstacle_hit(const llq_engine& E, const Env& e) {
+  if (!E.has_obstacles) return false;
+  int n_ob = E.ob_off[e.clip + 1] - E.ob_off[e.clip];
+  if (n_ob == 0) return false;                                  // MotionLib.obstacle is None for this clip (OBS:17-18)
+  const double* ob = &E.ob_table[(size_t)(E.ob_off[e.clip] + e.ob_id) * 4];
+  Kin k;
+  kinematics(E.model, e.pos, e.quat, e.q, k);
+  double cy = std::cos(ob[3]), sy = std::sin(ob[3]);
+  for (const ProxyM& p : E.model.proxies) {
+    V3 w = k.pl[p.link] + mul(k.Rl[p.link], p.c);
+    double dx = w.x - ob[1], dy = w.y - ob[2], dz = w.z;
+    double bx = cy * dx + sy * dy, by = -sy * dx + cy * dy;    // into the plate frame
+    double qx = bx - clampd(bx, -E.ob_half[0], E.ob_half[0]), qy = by - clampd(by, -E.ob_half[1], E.ob_half[1]),
+           qz = dz - clampd(dz, -E.ob_half[2], E.ob_half[2]);
+    double dist = std::sqrt(qx * qx + qy * qy + qz * qz) - p.r;
+    if (dist < E.cfg.contact_breaking) return true;
+  }
+  return false;
+}
+
 // PLE:195-245 for one env; returns reward, sets *done
 double step_env(llq_engine& E, Env& e, const float* action, bool* done, int64_t* ncr, int64_t* nlr) {
   const llq_config& cf = E.cfg;
@@ -773,16 +799,23 @@ double step_env(llq_engine& E, Env& e, const float* action, bool* done, int64_t*
   e.margin = 1e30;
   double act[12], tgt[12], tau[12];
   for (int j = 0; j < 12; j++) { act[j] = (double)action[j]; tgt[j] = e.q[j] + act[j]; }   // PLE:198-200
-  bool ok = true;
+  bool ok = true, ob_hit = false;
   for (int s = 0; s < cf.substeps; s++) {
     for (int j = 0; j < 12; j++) {                                                          // LR:126-141
       double tg = clampd(tgt[j], -3.0, 3.0);
       double t = cf.kp * (tg - e.q[j]) + cf.kd * (0.0 - e.qd[j]);
       tau[j] = clampd(t, -cf.max_tau, cf.max_tau);
     }
+    // getContactPoints (PLE:343) reports the manifolds of the last stepSimulation, which were built on that sub-step's
+    // pre-step poses, with the plate where _update_obstacle left it at the end of the previous policy step
+    if (s == cf.substeps - 1) ob_hit = obstacle_hit(E, e);
     if (ok) ok = physics_substep(E, e, tau, ncr, nlr);                                       // PLE:206
     motion_set_time(E, e, e.time);                                                           // PLE:208
     e.time += cf.sim_dt;                                                                     // PLE:210
+  }
+  if (E.has_obstacles) {                                                                     // PLE:224-225, 262-268
+    int n_ob = E.ob_off[e.clip + 1] - E.ob_off[e.clip];
+    while (e.ob_id < n_ob - 1 && e.time > E.ob_table[(size_t)(E.ob_off[e.clip] + e.ob_id) * 4] + 0.5) e.ob_id++;
   }
   // PLE:217-222
   mocap_state(E, frame_ptr(E, e.clip, e.frame_id), frame_ptr(E, e.clip, e.frame_id + 1), e.frame_frac, e.kin);
@@ -828,7 +861,7 @@ double step_env(llq_engine& E, Env& e, const float* action, bool* done, int64_t*
   int nf = E.clip_off[e.clip + 1] - E.clip_off[e.clip];
   bool ended = e.frame_id >= nf - E.margin - 1;                                              // ML:168-172
   bool diff = std::fabs(angle) > 1.0 || dp > 1.0;                                            // PLE:319-335
-  *done = fall || ended || diff || !ok;
+  *done = fall || ended || diff || ob_hit || !ok;                                            // PLE:347
   if (!ok || !std::isfinite(r)) { r = 0.0; *done = true; }
   return r;
 }
@@ -1098,6 +1131,11 @@ int llq_load_model(llq_handle h, const double* b, int64_t n) {
   int ns = (int)b[LLQ_H_NSPHERES];
   if (ns > 8) return fail(LLQ_EINVAL, "too many contact spheres");
   for (int i = 0; i < ns; i++, s += LLQ_SPH) md.spheres.push_back({(int)s[0], V3{s[1], s[2], s[3]}, s[4], h->cfg.foot_friction});
+  if ((int64_t)b[LLQ_H_NPROXIES] > 0) {
+    const double* pr = b + (int64_t)b[LLQ_H_OFF_PROXIES];
+    for (int i = 0; i < (int)b[LLQ_H_NPROXIES]; i++, pr += LLQ_PROXY)
+      md.proxies.push_back({(int)pr[0], V3{pr[1], pr[2], pr[3]}, pr[4], (int)pr[5]});
+  }
   h->model = md;
   h->has_model = true;
   return LLQ_OK;
@@ -1120,6 +1158,18 @@ int llq_load_mocap(llq_handle h, const double* frames, const int32_t* off, int32
   h->sample_prob.assign(n_clips, 1.0 / n_clips);                                                   // ML:46
   h->avg_reward.assign(n_clips, 0.0);                                                              // PLE:133
   h->has_mocap = true;
+  return LLQ_OK;
+}
+
+int llq_load_obstacles(llq_handle h, const double* table, const int32_t* offsets, int32_t n_clips, double hx, double hy, double hz) {
+  if (!h || !offsets || n_clips <= 0) return fail(LLQ_EINVAL, "bad obstacle arguments");
+  if (!h->has_mocap || n_clips != h->n_clips) return fail(LLQ_ESTATE, "llq_load_obstacles needs the mocap table first (same clip count)");
+  if (offsets[0] != 0 || (offsets[n_clips] > 0 && !table)) return fail(LLQ_EINVAL, "bad obstacle table");
+  for (int c = 0; c < n_clips; c++) if (offsets[c + 1] < offsets[c]) return fail(LLQ_EINVAL, "obstacle offsets must be non-decreasing");
+  h->ob_off.assign(offsets, offsets + n_clips + 1);
+  h->ob_table.assign(table, table + (size_t)offsets[n_clips] * 4);
+  h->ob_half[0] = hx; h->ob_half[1] = hy; h->ob_half[2] = hz;
+  h->has_obstacles = true;
   return LLQ_OK;
 }
 
@@ -1245,6 +1295,7 @@ int llq_get_field(llq_handle h, int field, void* dst) {
       case LLQ_F_EPISODE_ID: ((int64_t*)dst)[i] = e.episode; break;
       case LLQ_F_FOOT_POS: for (int t = 0; t < 12; t++) ((float*)dst)[(size_t)i * 12 + t] = (float)e.foot_pos[t]; break;
       case LLQ_F_DECISION_MARGIN: ((float*)dst)[i] = (float)e.margin; break;
+      case LLQ_F_OB_ID: ((int32_t*)dst)[i] = e.ob_id; break;
       case LLQ_F_SAMPLE_PROB: case LLQ_F_AVG_REWARD: break;
       default: return fail(LLQ_EINVAL, "unknown field");
     }
@@ -1276,6 +1327,7 @@ int llq_set_field(llq_handle h, int field, const void* src) {
       case LLQ_F_EPISODE_STEPS: e.episode_steps = ((const int32_t*)src)[i]; break;
       case LLQ_F_WARMSTART: for (int t = 0; t < 4; t++) e.warm[t] = ((const float*)src)[(size_t)i * 4 + t]; break;
       case LLQ_F_EPISODE_ID: e.episode = ((const int64_t*)src)[i]; break;
+      case LLQ_F_OB_ID: e.ob_id = ((const int32_t*)src)[i]; break;
       case LLQ_F_AUX: {
         const double* a = (const double*)src + (size_t)i * LLQ_AUX_DIM;
         e.counter = (int)a[0]; e.cmd_freq = (int)a[1]; e.tgt_x = a[2]; e.tgt_y = a[3]; e.target_spd = a[4]; e.target_angle = a[5];
@@ -1348,6 +1400,22 @@ int llq_oracle_substep_push(llq_handle h, int32_t env, const double* tau12, cons
   h->envs[env].margin = 1e30;
   h->envs[env].foot_mu = foot_mu;
   return physics_substep(*h, h->envs[env], tau12, &a, &b, push_local3) ? LLQ_OK : fail(LLQ_ESTATE, "physics sub-step failed");
+}
+int llq_oracle_obstacle_hit(llq_handle h, const double* st37, const double* pose_xy_yaw, const double* half3, int32_t* hit) {
+  if (!h || !st37 || !pose_xy_yaw || !half3 || !hit) return fail(LLQ_EINVAL, "bad arguments");
+  if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
+  Kin k;
+  kinematics(h->model, st37, st37 + 3, st37 + 13, k);
+  double cy = std::cos(pose_xy_yaw[2]), sy = std::sin(pose_xy_yaw[2]);
+  *hit = 0;
+  for (const ProxyM& p : h->model.proxies) {
+    V3 w = k.pl[p.link] + mul(k.Rl[p.link], p.c);
+    double dx = w.x - pose_xy_yaw[0], dy = w.y - pose_xy_yaw[1], dz = w.z;
+    double bx = cy * dx + sy * dy, by = -sy * dx + cy * dy;
+    double qx = bx - clampd(bx, -half3[0], half3[0]), qy = by - clampd(by, -half3[1], half3[1]), qz = dz - clampd(dz, -half3[2], half3[2]);
+    if (std::sqrt(qx * qx + qy * qy + qz * qz) - p.r < h->cfg.contact_breaking) { *hit = 1; break; }
+  }
+  return LLQ_OK;
 }
 int llq_oracle_foot_positions(llq_handle h, const double* st37, double* out12) {
   if (!h || !st37 || !out12) return fail(LLQ_EINVAL, "bad arguments");

@@ -28,7 +28,7 @@ from lifelike_agility_and_play_b200.model.compile_model import load_model_blob  
 from oracle import oracle  # noqa: E402
 
 
-def main():
+def main(obstacle=False):
     assert os.path.isdir(REF_SRC), "reference tree not mounted"
     rng = np.random.default_rng(42)
     lens = [150, 230, 410]
@@ -36,6 +36,10 @@ def main():
     # make clip 1 turn sharply so that slerp / rotvec paths see large angles and w < 0 quaternions
     yaw = np.linspace(0, 3.5, lens[1])
     clips[1][:, 3:7] = np.stack([0 * yaw, 0 * yaw, np.sin(yaw / 2), np.cos(yaw / 2)], 1) * np.where(yaw > 2.0, -1, 1)[:, None]
+    if obstacle:
+        # jumps: the base rises above 0.5 m twice in clip 2 and once in clip 0 => hurdle plates at the apexes (utils/obstacle.py:16)
+        t2 = np.arange(lens[2]); clips[2][:, 2] += 0.25 * np.exp(-((t2 - 60) / 14.0) ** 2) + 0.22 * np.exp(-((t2 - 215) / 14.0) ** 2)
+        t0 = np.arange(lens[0]); clips[0][:, 2] += 0.2 * np.exp(-((t0 - 12) / 6.0) ** 2)
     offsets = np.zeros(4, np.int32); offsets[1:] = np.cumsum(lens)
     table = MocapTable(np.concatenate(clips, 0), offsets, 1.0 / 120.0, ["clip_%d.txt" % i for i in range(3)])
     tmp = tempfile.mkdtemp(prefix="llq_golden_")
@@ -46,7 +50,7 @@ def main():
     env_config = {
         'arena_id': 'LeggedRobotTracking', 'render': False, 'data_path': tmp, 'control_freq': 50.0,
         'prop_type': ['joint_pos', 'joint_vel', 'root_ang_vel_loc', 'root_lin_vel_loc', 'e_g'],
-        'prioritized_sample_factor': 3.0, 'set_obstacle': False, 'kp': 50.0, 'kd': 0.5, 'max_tau': 18,
+        'prioritized_sample_factor': 3.0, 'set_obstacle': bool(obstacle), 'obstacle_height': 0.2, 'kp': 50.0, 'kd': 0.5, 'max_tau': 18,
         'reward_weights': {'joint_pos': 0.3, 'joint_vel': 0.05, 'end_effector': 0.1, 'root_pose': 0.5, 'root_vel': 0.05},
     }
     eng = oracle.make_engine(1, load_model_blob(), table, kp=50.0, kd=0.5, max_tau=18.0)
@@ -60,7 +64,7 @@ def main():
     inner = env.env
     ml = inner._motion_generator
     rec = {k: [] for k in ("episode", "clip", "time0", "action", "prop", "prop_a", "future", "reward", "done", "time",
-                           "state", "kin", "prob", "reset_prop", "reset_future", "reset_state")}
+                           "state", "kin", "prob", "reset_prop", "reset_future", "reset_state", "ob_id", "ob_hit")}
     np.random.seed(7)
     arng = np.random.default_rng(5)
     for ep in range(6):
@@ -79,17 +83,20 @@ def main():
             rec["future"].append(o["future"]); rec["reward"].append(r[0]); rec["done"].append(bool(d)); rec["time"].append(inner.time)
             rec["state"].append(np.concatenate([si["base_pos"], si["base_orn"], si["base_lin_vel"], si["base_ang_vel"], si["joint_pos"], si["joint_vel"]]))
             rec["kin"].append(np.concatenate([ki["base_pos"], ki["base_orn"], ki["base_lin_vel"], ki["base_ang_vel"], ki["joint_pos"], ki["joint_vel"]]))
+            rec["ob_id"].append(getattr(inner, "ob_id", 0) if inner._obstacle is not None else -1)
+            rec["ob_hit"].append(len(inner._bullet_client.getContactPoints(bodyA=0)) > 0)
             if d:
                 rec["prob"].append(np.array(inner._prioritized_sample_probability, dtype=np.float64))
                 break
     out = {k: np.asarray(v) for k, v in rec.items()}
     out.update(frames=table.frames, offsets=table.offsets, frame_dt=table.frame_dt, margin=ml.margin,
                max_steps=np.asarray(ml.max_steps), num_env_steps=inner.num_env_steps)
-    path = os.path.join(ROOT, "tests", "golden", "pmc_reference_golden.npz")
+    out["obstacle"] = bool(obstacle)
+    path = os.path.join(ROOT, "tests", "golden", "pmc_obstacle_reference_golden.npz" if obstacle else "pmc_reference_golden.npz")
     np.savez_compressed(path, **out)
     print("wrote", path, "steps", len(rec["reward"]), "episodes", len(rec["clip"]), "dones", int(np.sum(rec["done"])),
-          "clips", rec["clip"], "size", os.path.getsize(path))
+          "clips", rec["clip"], "obstacle hits", int(np.sum(rec["ob_hit"])), "ob ids", sorted(set(rec["ob_id"])), "size", os.path.getsize(path))
 
 
 if __name__ == "__main__":
-    main()
+    main(obstacle="--obstacle" in sys.argv)

@@ -81,11 +81,30 @@ class FakeBulletClient:
         return None
     setCollisionFilterGroupMask = changeVisualShape = setGravity = _noop
     setPhysicsEngineParameter = setTimeStep = configureDebugVisualizer = resetDebugVisualizerCamera = _noop
-    createVisualShape = createCollisionShape = removeBody = _noop
+    createVisualShape = _noop
 
-    def createMultiBody(self, *a, **k):
-        self.bodies.append(_Body("static"))
+    def createCollisionShape(self, shapeType=None, halfExtents=None, **kw):
+        if not hasattr(self, "shapes"):
+            self.shapes = []
+        self.shapes.append(None if halfExtents is None else np.asarray(halfExtents, dtype=np.float64))
+        return len(self.shapes) - 1
+
+    def createMultiBody(self, baseMass=0, baseCollisionShapeIndex=-1, baseVisualShapeIndex=-1, basePosition=None, baseOrientation=None, **k):
+        b = _Body("static")
+        b.box = self.shapes[baseCollisionShapeIndex] if hasattr(self, "shapes") and baseCollisionShapeIndex >= 0 else None
+        if basePosition is not None:
+            b.state[0:3] = basePosition
+        if baseOrientation is not None:
+            b.state[3:7] = baseOrientation
+        self.bodies.append(b)
         return len(self.bodies) - 1
+
+    def removeBody(self, uid):
+        self.bodies[uid].kind = "removed"
+
+    def getContactPoints(self, bodyA=None, **kw):
+        """Contacts of the last stepSimulation (built on that step's pre-step poses): only robot-vs-box-body pairs are modelled."""
+        return list(getattr(self, "_contacts", []))
 
     def changeDynamics(self, uid, linkIndex=None, lateralFriction=None, **kw):
         if lateralFriction is not None and linkIndex in FOOT_LINKS and self.bodies[uid].kind == "dynamic":
@@ -168,9 +187,6 @@ class FakeBulletClient:
         z3 = (0.0, 0.0, 0.0)
         return [(tuple(out[3 * i:3 * i + 3]), (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, z3) for i in range(4)]
 
-    def getContactPoints(self, **kw):
-        return []
-
     # ---- the physics step
     def stepSimulation(self):
         for b in self.bodies:
@@ -180,6 +196,20 @@ class FakeBulletClient:
                 st = np.ascontiguousarray(b.state, dtype=np.float64)
                 assert self._lib.llq_oracle_set_state64(self._h, 0, st.ctypes.data_as(C.c_void_p)) == 0
                 b.dirty = False
+            # narrow phase on the pre-step pose: robot (oracle detection proxies) vs every static box body
+            self._contacts = []
+            self._lib.llq_oracle_obstacle_hit.restype = C.c_int
+            for uid, o in enumerate(self.bodies):
+                if o.kind == "static" and getattr(o, "box", None) is not None and np.any(o.box > 0):
+                    x, y, z, w = o.state[3:7] / np.linalg.norm(o.state[3:7])
+                    pose = np.array([o.state[0], o.state[1], np.arctan2(2 * (x * y + z * w), 1 - 2 * (y * y + z * z))])
+                    st = np.ascontiguousarray(b.state, dtype=np.float64)
+                    half = np.ascontiguousarray(o.box, dtype=np.float64)
+                    hit = C.c_int32(0)
+                    assert self._lib.llq_oracle_obstacle_hit(self._h, st.ctypes.data_as(C.c_void_p), pose.ctypes.data_as(C.c_void_p),
+                                                             half.ctypes.data_as(C.c_void_p), C.byref(hit)) == 0
+                    if hit.value:
+                        self._contacts.append((0, self.bodies.index(b), uid, -1, -1))
             tau = np.ascontiguousarray(b.tau, dtype=np.float64)
             push = None if b.push is None else np.ascontiguousarray(b.push, dtype=np.float64)
             self._lib.llq_oracle_substep_push.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double]

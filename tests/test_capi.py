@@ -211,3 +211,20 @@ def test_pinned_io_path_matches_plain_step(make_oracle):
         act_p[...] = act
         b.step_pinned(act_p, obs_p, rew_p, done_p)
         assert np.array_equal(o, obs_p) and np.array_equal(r, rew_p) and np.array_equal(d, done_p)
+
+
+def test_shipped_pmc_train_config_with_obstacle(monkeypatch, oracle_lib):
+    """train_scripts/example_pmc_train.sh:67-79 verbatim (set_obstacle True, obstacle_height left to the factory default 0.0)."""
+    from lifelike_agility_and_play_b200.sim_envs import create_envs, primitive_level_env as ple
+    from lifelike_agility_and_play_b200.mocap import synthetic_mocap, obstacle_table
+    monkeypatch.setattr(ple, "engine_factory", lambda n, blob, mocap, **cfg: capi.VecEngine(oracle_lib, n, blob, mocap, **{k: v for k, v in cfg.items() if k != "device"}))
+    mc = synthetic_mocap(3, seed=5, min_frames=400, max_frames=500)
+    mc.frames[:, 2] += 0.25 * np.exp(-((np.arange(len(mc.frames)) % 400 - 200) / 20.0) ** 2)      # periodic jumps
+    assert obstacle_table(mc)[1][-1] >= 3
+    cfg = {'arena_id': 'LeggedRobotTracking', 'render': False, 'data_path': '', 'mocap': mc, 'control_freq': 50.0,
+           'prop_type': ['joint_pos', 'joint_vel', 'root_ang_vel_loc', 'root_lin_vel_loc', 'e_g'],
+           'prioritized_sample_factor': 3.0, 'set_obstacle': True, 'kp': 50.0, 'kd': 0.5, 'max_tau': 18,
+           'reward_weights': {'joint_pos': 0.3, 'joint_vel': 0.05, 'end_effector': 0.1, 'root_pose': 0.5, 'root_vel': 0.05}}
+    env = create_envs.create_tracking_game(**cfg)
+    _drive(env)
+    env.close()

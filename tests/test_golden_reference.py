@@ -21,7 +21,7 @@ def _table(g):
     return MocapTable(g["frames"], g["offsets"].astype(np.int32), float(g["frame_dt"]), ["c%d" % i for i in range(len(g["offsets"]) - 1)])
 
 
-def _replay(eng, g, check):
+def _replay(eng, g, check, with_ob=False):
     ep_of_step = g["episode"]
     step = 0
     n_ep = len(g["clip"])
@@ -42,6 +42,8 @@ def _replay(eng, g, check):
             check("kin", eng.get(capi.F_KIN_STATE)[0], g["kin"][step])
             assert abs(eng.get(capi.F_TIME)[0] - g["time"][step]) < 1e-12
             assert bool(d[0]) == bool(g["done"][step]), "done mismatch at step %d" % step
+            if with_ob and g["ob_id"][step] >= 0:
+                assert int(eng.get(capi.F_OB_ID)[0]) == int(g["ob_id"][step]), "active plate (PLE:262-268) at step %d" % step
             if d[0]:
                 p = eng.get(capi.F_SAMPLE_PROB)
                 assert np.allclose(p, g["prob"][prob_i], rtol=1e-6, atol=1e-9), "prioritized sampling probabilities (PLE:239-240)"
@@ -72,6 +74,61 @@ def test_oracle_replays_reference_golden(gold, make_oracle):
     # the C-ABI returns float32: ~6e-8 relative quantisation; the arithmetic itself agrees to ~1e-12
     for k, v in worst.items():
         assert v < 5e-7, (k, v, worst)
+
+
+GOLD_OB = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "pmc_obstacle_reference_golden.npz")
+
+
+def _with_obstacles(eng, g):
+    from lifelike_agility_and_play_b200.mocap import obstacle_table
+    tab, offs = obstacle_table(_table(g))
+    assert list(np.diff(offs)) == [1, 0, 2]                       # clip 0: one jump apex, clip 1: none, clip 2: two
+    eng.load_obstacles(tab, offs, (0.025, 0.5, 0.2))             # PLE:184 with obstacle_height = 0.2 (test_primitive_level_env.py:34)
+    return eng
+
+
+def test_oracle_replays_reference_obstacle_golden(make_oracle):
+    """set_obstacle=True (example_pmc_train.sh:74): plate placement at the jump apexes, the 0.5 s hand-over rule, and
+    'touching the plate ends the episode' -- replayed against the unmodified reference env."""
+    g = np.load(GOLD_OB)
+    assert bool(g["obstacle"]) and g["ob_hit"].sum() >= 2 and set(g["ob_id"]) >= {0, 1}
+    eng = _with_obstacles(make_oracle(1, mocap=_table(g), kp=50.0, kd=0.5, max_tau=18.0, prioritized_sample_factor=3.0), g)
+    worst = {}
+
+    def check(name, got, want):
+        got, want = np.asarray(got, np.float64), np.asarray(want, np.float64)
+        if name in ("state", "kin", "reset_state") and np.dot(got[3:7], want[3:7]) < 0:
+            got = got.copy(); got[3:7] *= -1
+        worst[name] = max(worst.get(name, 0.0), float(np.max(np.abs(got - want) / (1.0 + np.abs(want)))))
+    _replay(eng, g, check, with_ob=True)
+    assert max(worst.values()) < 5e-7, worst
+    # every obstacle contact of the reference run ended its episode
+    assert np.all(g["done"][g["ob_hit"]])
+
+
+@pytest.mark.gpu
+def test_cuda_obstacle_matches_oracle(make_cuda, make_oracle):
+    g = np.load(GOLD_OB)
+    n = 256
+    gpu = _with_obstacles(make_cuda(n, mocap=_table(g), seed=8), g)
+    cpu = _with_obstacles(make_oracle(n, mocap=_table(g), seed=8), g)
+    gpu.reset(); cpu.reset()
+    rng = np.random.default_rng(0)
+    hits = 0
+    for t in range(40):
+        a = (0.15 * rng.standard_normal((n, 12))).astype(np.float32)
+        for f in (capi.F_STATE, capi.F_WARMSTART, capi.F_OBS, capi.F_TIME, capi.F_CLIP, capi.F_REWARD_SUM, capi.F_OB_ID):
+            gpu.set(f, cpu.get(f))
+        og, rg, dg = gpu.step(a); oc, rc, dc = cpu.step(a)
+        margin = cpu.get(capi.F_DECISION_MARGIN)
+        assert np.array_equal(gpu.get(capi.F_OB_ID), cpu.get(capi.F_OB_ID))
+        assert (dg == dc)[margin > 2.5e-4].mean() > 0.995
+        hits += int(dc.sum())
+        m = dc.astype(np.uint8)
+        if m.any():
+            cpu.reset(m); gpu.reset(m)
+            assert np.all(gpu.get(capi.F_OB_ID)[m == 1] == 0)
+    assert hits > 0
 
 
 @pytest.mark.gpu
