@@ -1,0 +1,31 @@
+"""Small PMC + EPMC + obstacle run for compute-sanitizer (memcheck / racecheck / initcheck)."""
+import os, sys
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import numpy as np
+from lifelike_agility_and_play_b200 import _capi as capi
+from lifelike_agility_and_play_b200.model.compile_model import load_model_blob
+from lifelike_agility_and_play_b200.mocap import synthetic_mocap, obstacle_table
+from lifelike_agility_and_play_b200.sim_envs.playground_env import INIT_STATE_RUN_0, epmc_engine_config
+
+blob = load_model_blob()
+mc = synthetic_mocap(4, seed=2, min_frames=400, max_frames=520)
+mc.frames[:, 2] += 0.25 * np.exp(-((np.arange(len(mc.frames)) % 300 - 150) / 15.0) ** 2)
+lib = capi.load_cuda_library()
+rng = np.random.default_rng(0)
+for n in (5, 70):
+    e = capi.VecEngine(lib, n, blob, mc, seed=1, auto_reset=1)
+    e.load_obstacles(*obstacle_table(mc), (0.025, 0.5, 0.2))
+    e.reset()
+    for t in range(12):
+        e.step((0.4 * rng.standard_normal((n, 12))).astype(np.float32))
+    e.reset(np.arange(n) % 2 == 0)
+    e.close()
+    erc = {'element_id': 0, 'friction_range': [0.4, 3.0], 'cmd_vary_freq_range': [3, 9], 'target_spd_range': [0.5, 3.0],
+           'disturb_force_config': {'start_time': 0.02, 'interval_time': 0.1, 'duration_time': 0.05, 'horizontal_force': [0, 50], 'vertical_force': [0, 10]}}
+    e = capi.VecEngine(lib, n, blob, None, seed=1, auto_reset=1, **epmc_engine_config(50.0, 50.0, 0.5, 16, 20, erc))
+    e.set_init_state(INIT_STATE_RUN_0)
+    e.reset()
+    for t in range(25):
+        e.step((0.4 * rng.standard_normal((n, 12))).astype(np.float32))
+    e.close()
+print("sanitize run done")
