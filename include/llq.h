@@ -42,6 +42,15 @@ extern "C" {
 #define LLQ_ENV_PMC  0       /* PrimitiveLevelEnv  (primitive_level_env.py) */
 #define LLQ_ENV_EPMC 1       /* PlayGroundEnv, element_id 0 = flat-ground joystick task, the shipped script default
                                 (max_game_elements/playground_env.py, train_scripts/example_epmc_train.sh:100) */
+#define LLQ_OBS_DIM_SEPMC 965 /* per agent: prop 99 | prop_a 36 | percept_2d 325 | percept_1d 128 | percept_front 325 | percept_vec 5 |
+                                 oppo_info 15 | oppo_info_cheat 15 | flag_info 7 | flag_info_cheat 7 | with_flag 2 | control_spd 1
+                                 (max_game/chase_tag_game_env.py:111-124) */
+#define LLQ_ENV_SEPMC 2      /* ChaseTagGameEnv in the empty arena of the shipped config (max_game/chase_tag_game_env.py,
+                                train_scripts/example_sepmc_train.sh:113-116).  n_envs counts ROBOTS and must be even: robots 2p and
+                                2p+1 form env-pair p; actions / obs / reward / done are per robot (done is the pair's, on both rows).
+                                LLQ_F_AUX rows for SEPMC: counter, with_flag, flag_x, flag_y, control_spd, oppo_visible, switch_flag,
+                                total_spd, max_spd, push_count, push_fx..z (last applied), foot_friction, push_draws (pair), flag_draws,
+                                yaw_accum_deg, reserved */
 #define LLQ_AUX_DIM  18      /* LLQ_F_AUX: counter, cmd_vary_freq, target_x, target_y, target_spd, target_angle, last_pos_diff_len,
                                 total_spd, max_spd, push_count, push_fx, push_fy, push_fz, foot_friction, push_draws, cmd_draws,
                                 yaw_accum_deg (the reference mutates its module-level init-state dict, so reset yaws accumulate: PGE:181-189), reserved */

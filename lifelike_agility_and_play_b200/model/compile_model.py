@@ -41,7 +41,7 @@ import numpy as np
 LLQ_MODEL_MAGIC = 0x4C4C5131  # "LLQ1"
 HDR = 16          # header doubles
 H_MAGIC, H_VERSION, H_NLINKS, H_NDOF, H_OFF_GENERIC, H_OFF_SPHERES, H_NSPHERES, H_OFF_SPECIAL, H_TOTAL, H_OFF_PROXIES, H_NPROXIES = range(11)
-PROXY = 8         # proxy stride: link, x, y, z (link frame), radius, kind (0 foot, 1 wheel, 2 hip, 3 body corner), 0, 0
+PROXY = 8         # proxy stride: link, x, y, z (link frame), radius, kind (0 foot, 1 wheel, 2 hip, 3 body corner, 4 handle), 0, 0
 GL = 64           # generic per-link stride
 G_PARENT, G_JTYPE, G_DOF = 0, 1, 2
 G_JXYZ, G_JROT, G_AXIS = 3, 6, 15
@@ -387,6 +387,8 @@ def pack_model(model):
                 proxies.append([i, *c["xyz"], c["radius"], 1, 0, 0])
             elif nm.endswith("1") and c["type"] == "cylinder":
                 proxies.append([i, *c["xyz"], c["radius"], 2, 0, 0])
+            elif "handle" in nm and c["type"] == "sphere":
+                proxies.append([i, *c["xyz"], c["radius"], 4, 0, 0])
             elif nm == "body" and c["type"] == "box":
                 hx, hy, hz = 0.5 * np.array(c["size"])
                 for sx in (1, -1):

@@ -259,8 +259,10 @@ struct Env {
   int counter, cmd_freq; double tgt_x, tgt_y, target_spd, target_angle, last_pos_diff_len, total_spd, max_spd;
   int push_count, push_draws, cmd_draws; double push_f[3];
   int ob_id;      // active hurdle plate (PLE:179,264-265)
+  // SEPMC (CTG): per-robot copies of the pair's game state
+  int with_flag, switch_flag, visible, flag_draws; double flag_x, flag_y, fix_spd;
   double yaw_accum_deg;   // PGE:181-189 mutates the shared init-state dict: every reset's yaw is applied on top of the previous ones
-  float obs[LLQ_OBS_DIM_EPMC];
+  float obs[LLQ_OBS_DIM_SEPMC];
 };
 
 }  // namespace
@@ -274,7 +276,7 @@ struct llq_engine {
   std::vector<Env> envs; bool was_reset = false;
   double init_state[LLQ_STATE_DIM]; bool has_init_state = false;
   std::vector<double> ob_table; std::vector<int32_t> ob_off; double ob_half[3] = {0, 0, 0}; bool has_obstacles = false;
-  int obs_dim() const { return cfg.env_kind == LLQ_ENV_EPMC ? LLQ_OBS_DIM_EPMC : LLQ_OBS_DIM; }
+  int obs_dim() const { return cfg.env_kind == LLQ_ENV_EPMC ? LLQ_OBS_DIM_EPMC : (cfg.env_kind == LLQ_ENV_SEPMC ? LLQ_OBS_DIM_SEPMC : LLQ_OBS_DIM); }
   int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
 };
 
@@ -497,15 +499,24 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
   kinematics(md, e.pos, e.quat, e.q, k);
 
   // (a) collision detection on pre-step poses: foot spheres vs plane z = 0
-  struct Contact { int link, sphere; V3 P; double dist, mu; };
+  struct Contact { int link, sphere; V3 P, n; double dist, mu; };
   Contact contacts[8]; int nc = 0;
+  // static half-spaces the feet can touch: the ground, plus (SEPMC) the inner faces of the four arena walls (BSG:863-902:
+  // 5 x 0.01 x 2 boxes centred at +-2.5).  One contact per foot: the deepest half-space.
+  const int n_planes = cf.env_kind == LLQ_ENV_SEPMC ? 5 : 1;
+  const V3 pn[5] = {{0, 0, 1}, {-1, 0, 0}, {1, 0, 0}, {0, -1, 0}, {0, 1, 0}};
+  const double pd[5] = {0.0, -2.495, -2.495, -2.495, -2.495};
   for (size_t s = 0; s < md.spheres.size(); s++) {
     const SphereM& sp = md.spheres[s];
     V3 cw = k.pl[sp.link] + mul(k.Rl[sp.link], sp.c);
-    double dist = cw.z - sp.r;
+    double dist = 1e30; V3 nrm = pn[0];
+    for (int pi = 0; pi < n_planes; pi++) {
+      double dpi = dot(pn[pi], cw) - pd[pi] - sp.r;
+      if (dpi < dist) { dist = dpi; nrm = pn[pi]; }
+    }
     e.margin = std::min(e.margin, std::fabs(dist - cf.contact_breaking));
     if (dist < cf.contact_breaking) {
-      contacts[nc++] = {sp.link, (int)s, V3{cw.x, cw.y, cw.z - sp.r}, dist, cf.ground_friction * e.foot_mu};
+      contacts[nc++] = {sp.link, (int)s, cw - sp.r * nrm, nrm, dist, cf.ground_friction * e.foot_mu};
     } else {
       e.warm[s] = 0.0;  // manifold point removed
     }
@@ -554,7 +565,7 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
   }
   for (int ci = 0; ci < nc; ci++) {
     const Contact& ct = contacts[ci];
-    V3 nrml = {0, 0, 1}, t1, t2;
+    V3 nrml = ct.n, t1, t2;
     plane_space(nrml, t1, t2);
     V3 dirs[3] = {nrml, t1, t2};
     for (int d = 0; d < 3; d++) {
@@ -781,6 +792,7 @@ bool obstacle_hit(const llq_engine& E, const Env& e) {
   kinematics(E.model, e.pos, e.quat, e.q, k);
   double cy = std::cos(ob[3]), sy = std::sin(ob[3]);
   for (const ProxyM& p : E.model.proxies) {
+    if (p.kind > 3) continue;   // handles (kind 4) only serve SEPMC visibility
     V3 w = k.pl[p.link] + mul(k.Rl[p.link], p.c);
     double dx = w.x - ob[1], dy = w.y - ob[2], dz = w.z;
     double bx = cy * dx + sy * dy, by = -sy * dx + cy * dy;    // into the plate frame
@@ -1025,6 +1037,320 @@ double epmc_step(llq_engine& E, Env& e, int64_t gid, const float* action, bool* 
   return r;
 }
 
+
+// ================================================================== SEPMC (ChaseTagGameEnv, empty arena)
+// CTG = max_game/chase_tag_game_env.py, BSG = max_game/bullet_static_entities.py, PR = randomizer/push_randomizer.py
+struct Box { V3 lo, hi; };
+// closest hit of the segment a->b with a set of axis-aligned boxes (rayTest / rayTestBatch, mask 6 => statics only).
+// Returns the hit fraction or -1.  A ray that starts inside a box does not hit that box (Bullet's convex cast).
+double ray_boxes(const Box* bs, int nb, V3 a, V3 b) {
+  double best = -1.0;
+  V3 d = b - a;
+  for (int i = 0; i < nb; i++) {
+    const double lo[3] = {bs[i].lo.x, bs[i].lo.y, bs[i].lo.z}, hi[3] = {bs[i].hi.x, bs[i].hi.y, bs[i].hi.z};
+    const double o[3] = {a.x, a.y, a.z}, dd[3] = {d.x, d.y, d.z};
+    if (o[0] > lo[0] && o[0] < hi[0] && o[1] > lo[1] && o[1] < hi[1] && o[2] > lo[2] && o[2] < hi[2]) continue;
+    double t0 = 0.0, t1 = 1.0; bool hit = true; int ax_in = -1;
+    for (int ax = 0; ax < 3 && hit; ax++) {
+      if (dd[ax] == 0.0) { if (o[ax] < lo[ax] || o[ax] > hi[ax]) hit = false; continue; }
+      double ta = (lo[ax] - o[ax]) / dd[ax], tb = (hi[ax] - o[ax]) / dd[ax];
+      if (ta > tb) std::swap(ta, tb);
+      if (ta > t0) { t0 = ta; ax_in = ax; }
+      t1 = std::min(t1, tb);
+      if (t0 > t1) hit = false;
+    }
+    if (hit && ax_in >= 0 && (best < 0 || t0 < best)) best = t0;
+  }
+  return best;
+}
+void sepmc_boxes(double fx, double fy, Box* b /* 6 */) {
+  b[0] = {{-100, -100, -10}, {100, 100, 0}};                       // ground slab (max_game/data/urdf/small_v3/plane.urdf)
+  b[1] = {{-2.5, 2.495, 0}, {2.5, 2.505, 2}};                      // walls (BSG:895-902)
+  b[2] = {{-2.5, -2.505, 0}, {2.5, -2.495, 2}};
+  b[3] = {{2.495, -2.5, 0}, {2.505, 2.5, 2}};
+  b[4] = {{-2.505, -2.5, 0}, {-2.495, 2.5, 2}};
+  b[5] = {{fx - 0.05, fy - 0.05, 0}, {fx + 0.05, fy + 0.05, 0.5}};  // flag (CTG:163-190, 218-221)
+}
+double sphere_box_dist(V3 c, const Box& b) {
+  double qx = c.x - clampd(c.x, b.lo.x, b.hi.x), qy = c.y - clampd(c.y, b.lo.y, b.hi.y), qz = c.z - clampd(c.z, b.lo.z, b.hi.z);
+  return std::sqrt(qx * qx + qy * qy + qz * qz);
+}
+void proxy_positions(const llq_engine& E, const double* st, V3* out) {   // world positions of the model's proxies
+  Kin k;
+  kinematics(E.model, st, st + 3, st + 13, k);
+  for (size_t i = 0; i < E.model.proxies.size(); i++) out[i] = k.pl[E.model.proxies[i].link] + mul(k.Rl[E.model.proxies[i].link], E.model.proxies[i].c);
+}
+
+struct PairContacts { bool tag; bool flag_touch[2]; };
+// getContactPoints() of the last stepSimulation (CTG:426-456), with detection proxies: a robot's "body" links (legs + wheels,
+// CTG:427) are represented by its hip and wheel spheres; any proxy of the other robot (or the flag box) counts as the other side.
+PairContacts sepmc_contacts(const llq_engine& E, const Env& e0, const Env& e1) {
+  const int np = (int)E.model.proxies.size();
+  V3 p0[32], p1[32];
+  double s0[LLQ_STATE_DIM], s1[LLQ_STATE_DIM];
+  pack_state(e0, s0); pack_state(e1, s1);
+  proxy_positions(E, s0, p0); proxy_positions(E, s1, p1);
+  Box bx[6];
+  sepmc_boxes(e0.flag_x, e0.flag_y, bx);
+  PairContacts pc = {false, {false, false}};
+  const double thr = E.cfg.contact_breaking;
+  for (int r = 0; r < 2; r++) {
+    const V3* mine = r == 0 ? p0 : p1; const V3* other = r == 0 ? p1 : p0;
+    for (int i = 0; i < np; i++) {
+      const ProxyM& pi = E.model.proxies[i];
+      if (pi.kind != 1 && pi.kind != 2) continue;                                 // body_indices = leg + wheel links
+      if (sphere_box_dist(mine[i], bx[5]) - pi.r < thr) pc.flag_touch[r] = true;
+      if (r == 0)
+        for (int j = 0; j < np; j++)
+          if (norm(mine[i] - other[j]) - pi.r - E.model.proxies[j].r < thr) pc.tag = true;
+    }
+  }
+  return pc;
+}
+
+void sepmc_randomize_push(llq_engine& E, Env& a, Env& b, int64_t gid, double* out3) {   // PR:89-99, one draw counter per pair
+  double u[4];
+  stream_uniforms(E.cfg.seed, gid, a.episode - 1, 2, (uint32_t)a.push_draws, u);
+  a.push_draws += 1; b.push_draws = a.push_draws;
+  double theta = 2.0 * M_PI * u[0];
+  double h = E.cfg.push_h_lo + u[1] * (E.cfg.push_h_hi - E.cfg.push_h_lo);
+  out3[0] = h * std::cos(theta); out3[1] = h * std::sin(theta); out3[2] = E.cfg.push_v_lo + u[2] * (E.cfg.push_v_hi - E.cfg.push_v_lo);
+}
+
+// CTG:495-596 for robot i of the pair
+void sepmc_write_obs(const llq_engine&, Env* ev[2], const double st[2][LLQ_STATE_DIM], int i, const V3 prox[2][32], int with_flag_now[2]) {
+  Env& e = *ev[i];
+  const int j = 1 - i;
+  float* o = e.obs;
+  int k = 0;
+  for (int h = 0; h < 3; h++) for (int t = 0; t < LLQ_PROP_DIM; t++) o[k++] = (float)e.prop_hist[h][t];
+  for (int h = 0; h < 3; h++) for (int t = 0; t < LLQ_ACTION_DIM; t++) o[k++] = (float)e.act_hist[h][t];
+  Box bx[6];
+  sepmc_boxes(e.flag_x, e.flag_y, bx);                                   // flag where it stood during this step
+  M3 R = qmat(qnormalize({st[i][3], st[i][4], st[i][5], st[i][6]}));
+  V3 pos = {st[i][0], st[i][1], st[i][2]};
+  double yaw = std::atan2(R.m[1][0], R.m[0][0]);
+  // percept_2d (CTG:621-638): down rays over the 25 x 13 grid, value = hit z (0 on a miss)
+  for (int a = 0; a < 25; a++) {
+    double gx = a == 24 ? 1.2 : -1.2 + a * (2.4 / 24.0);
+    for (int b = 0; b < 13; b++) {
+      double gy = b == 12 ? 0.6 : -0.6 + b * (1.2 / 12.0);
+      V3 t = mul(R, V3{gx, gy, 0.0}) + pos;
+      double f = ray_boxes(bx, 6, V3{t.x, t.y, 10.0}, V3{t.x, t.y, -10.0});
+      o[k++] = f < 0 ? 0.0f : (float)(10.0 + f * (-20.0));
+    }
+  }
+  // percept_1d (CTG:529-537): 128 horizontal rays, 20 m; miss => hit_pos = (0,0,0)
+  for (int r = 0; r < 128; r++) {
+    double ang = yaw + 2.0 * M_PI * (double)r / 128.0;
+    V3 to = {pos.x + 20.0 * std::cos(ang), pos.y + 20.0 * std::sin(ang), pos.z};
+    double f = ray_boxes(bx, 6, pos, to);
+    V3 hit = f < 0 ? V3{0, 0, 0} : pos + f * (to - pos);
+    o[k++] = (float)norm(hit - pos);
+  }
+  // percept_front (CTG:598-619)
+  for (int a = 0; a < 25; a++) {
+    double y = a == 24 ? 0.25 : -0.25 + a * (0.5 / 24.0);
+    for (int b = 0; b < 13; b++) {
+      double z = b == 12 ? 0.1 : -0.3 + b * (0.4 / 12.0);
+      V3 from = mul(R, V3{0.0, y, z}) + pos, to = mul(R, V3{3.0, y, z}) + pos;
+      double f = ray_boxes(bx, 6, from, to);
+      V3 hit = f < 0 ? to : from + f * (to - from);
+      o[k++] = (float)norm(hit - from);
+    }
+  }
+  // percept_vec: position(3), cos yaw, sin yaw
+  o[k++] = (float)pos.x; o[k++] = (float)pos.y; o[k++] = (float)pos.z; o[k++] = (float)std::cos(yaw); o[k++] = (float)std::sin(yaw);
+  // opponent (CTG:540-567)
+  M3 Rj = qmat(qnormalize({st[j][3], st[j][4], st[j][5], st[j][6]}));
+  double yawj = std::atan2(Rj.m[1][0], Rj.m[0][0]);
+  V3 posj = {st[j][0], st[j][1], st[j][2]};
+  V3 dpw = posj - pos;
+  V3 dpl = tmul(R, dpw), vl = tmul(R, V3{st[j][7], st[j][8], st[j][9]}), wl = tmul(R, V3{st[j][10], st[j][11], st[j][12]});
+  double oppo[15] = {(double)e.visible, posj.x, posj.y, posj.z, dpl.x, dpl.y, dpl.z, std::cos(yawj - yaw), std::sin(yawj - yaw),
+                     vl.x, vl.y, vl.z, wl.x, wl.y, wl.z};
+  for (int t = 0; t < 15; t++) o[k++] = e.visible ? (float)oppo[t] : 0.0f;
+  for (int t = 0; t < 15; t++) o[k++] = (float)oppo[t];
+  // flag (CTG:569-583): flag_visible is always true; position = where the flag stood during this step
+  V3 fp = {e.flag_x, e.flag_y, 0.25};
+  V3 fl = tmul(R, fp - pos);
+  double flag[7] = {1.0, fp.x, fp.y, fp.z, fl.x, fl.y, fl.z};
+  for (int rep = 0; rep < 2; rep++) for (int t = 0; t < 7; t++) o[k++] = (float)flag[t];
+  // with_flag (CTG:596): [with_flag, with_flag[::-1]][i]  (after a possible switch in this step)
+  o[k++] = (float)with_flag_now[i]; o[k++] = (float)with_flag_now[j];
+  o[k++] = (float)e.fix_spd;                                                                // control_spd (CTG:364-365)
+  (void)prox;
+}
+
+// visibility (CTG:472-493): clear root-to-root segment, else any clear head-handle -> {feet, wheels, handles} segment; and the
+// bearing test against visible_angle = pi
+void sepmc_visibility(const llq_engine& E, Env* ev[2], const double st[2][LLQ_STATE_DIM], const V3 prox[2][32]) {
+  Box bx[6];
+  sepmc_boxes(ev[0]->flag_x, ev[0]->flag_y, bx);
+  V3 p[2] = {{st[0][0], st[0][1], st[0][2]}, {st[1][0], st[1][1], st[1][2]}};
+  bool root_clear = ray_boxes(bx, 6, p[0], p[1]) < 0;
+  const int np = (int)E.model.proxies.size();
+  for (int i = 0; i < 2; i++) {
+    bool vis = root_clear;
+    if (!vis) {
+      for (int h = 0; h < np && !vis; h++) {
+        if (E.model.proxies[h].kind != 4) continue;
+        // head point = the first handle (front handle, LR:154-156)
+        for (int c = 0; c < np && !vis; c++) {
+          int kd = E.model.proxies[c].kind;
+          if (kd != 0 && kd != 1 && kd != 4) continue;                            // feet + wheels + handles (LR:150-152)
+          if (ray_boxes(bx, 6, prox[i][h], prox[1 - i][c]) < 0) vis = true;
+        }
+        break;                                                                    // only the front handle
+      }
+    }
+    M3 R = qmat(qnormalize({st[i][3], st[i][4], st[i][5], st[i][6]}));
+    double yaw = std::atan2(R.m[1][0], R.m[0][0]);
+    V3 d = p[1 - i] - p[i];
+    double cv = (std::cos(yaw) * d.x + std::sin(yaw) * d.y) / std::sqrt(d.x * d.x + d.y * d.y);
+    ev[i]->visible = (cv >= std::cos(M_PI) && vis) ? 1 : 0;
+  }
+}
+
+void sepmc_finish_obs(llq_engine& E, Env* ev[2], int64_t gid, const PairContacts& pc, bool is_reset) {
+  double st[2][LLQ_STATE_DIM];
+  V3 prox[2][32];
+  for (int i = 0; i < 2; i++) { pack_state(*ev[i], st[i]); proxy_positions(E, st[i], prox[i]); foot_positions(E, st[i], ev[i]->foot_pos); }
+  sepmc_visibility(E, ev, st, prox);
+  // flag switch (CTG:573-581): the robot that does NOT hold the flag touches it
+  int wf[2] = {ev[0]->with_flag, ev[1]->with_flag};
+  double nfx = ev[0]->flag_x, nfy = ev[0]->flag_y;
+  int sw = 0;
+  if (!is_reset && ((wf[0] && pc.flag_touch[1]) || (wf[1] && pc.flag_touch[0]))) {
+    std::swap(wf[0], wf[1]);
+    sw = 1;
+    double u[4];
+    stream_uniforms(E.cfg.seed, gid, ev[0]->episode - 1, 4, (uint32_t)ev[0]->flag_draws, u);
+    ev[0]->flag_draws += 1; ev[1]->flag_draws = ev[0]->flag_draws;
+    nfx = -2.0 + 4.0 * u[0]; nfy = -2.0 + 4.0 * u[1];                              // CTG:218-221
+  }
+  for (int i = 0; i < 2; i++) sepmc_write_obs(E, ev, st, i, prox, wf);
+  for (int i = 0; i < 2; i++) { ev[i]->with_flag = wf[i]; ev[i]->switch_flag = sw; ev[i]->flag_x = nfx; ev[i]->flag_y = nfy; }
+}
+
+void sepmc_reset(llq_engine& E, Env& a, Env& b, int64_t gid) {   // CTG:261-304, 204-230
+  const llq_config& cf = E.cfg;
+  Env* ev[2] = {&a, &b};
+  a.episode++; b.episode = a.episode;
+  double u0[4], u1[4], u2[4];
+  stream_uniforms(cf.seed, gid, a.episode - 1, 1, 0, u0);
+  stream_uniforms(cf.seed, gid, a.episode - 1, 1, 1, u1);
+  stream_uniforms(cf.seed, gid, a.episode - 1, 1, 2, u2);
+  const double fix_spd = 0.5 + 2.5 * u0[0];                                               // CTG:262
+  const int wflag = (int)std::floor(2.0 * u0[1]);                                         // np.random.randint(0, 2)  (CTG:266)
+  const double mu = cf.friction_lo + u0[2] * (cf.friction_hi - cf.friction_lo);           // CTG:277
+  const double px[2] = {-2.0 + 4.0 * u0[3], -2.0 + 4.0 * u1[1]}, py[2] = {-2.0 + 4.0 * u1[0], -2.0 + 4.0 * u1[2]};   // CTG:205-206
+  const double yaws[2] = {360.0 * u1[3], 360.0 * u2[0]};
+  double yaw_acc = a.yaw_accum_deg;      // get_init_states_info() hands both robots the same dict => one running yaw (CTG:209-215)
+  for (int i = 0; i < 2; i++) {
+    Env& e = *ev[i];
+    e.fix_spd = fix_spd; e.with_flag = i == 0 ? wflag : 1 - wflag; e.switch_flag = 0; e.foot_mu = mu; e.flag_draws = 0;
+    e.counter = 0; e.total_spd = 0; e.max_spd = 0; e.time = 0; e.reward_sum = 0; e.episode_steps = 0;
+    e.push_count = cf.push_start_count; e.push_draws = 0;
+    double st[LLQ_STATE_DIM];
+    std::memcpy(st, E.init_state, sizeof(st));
+    yaw_acc = std::fmod(yaw_acc + yaws[i], 360.0);
+    double ang = yaw_acc * M_PI / 180.0;
+    Q4 qn = qmul(qnormalize({st[3], st[4], st[5], st[6]}), Q4{0, 0, std::sin(ang / 2), std::cos(ang / 2)});
+    st[3] = qn.x; st[4] = qn.y; st[5] = qn.z; st[6] = qn.w;
+    st[0] = px[i]; st[1] = py[i]; st[2] = 0.5;
+    unpack_state(e, st);
+    e.yaw_accum_deg = yaw_acc;
+    for (int s = 0; s < 8; s++) e.warm[s] = 0;
+    e.flag_x = -2.0 + 4.0 * u2[1]; e.flag_y = -2.0 + 4.0 * u2[2];                          // CTG:218-221
+    double prop[LLQ_PROP_DIM];
+    make_prop(st, prop);
+    for (int h = 0; h < 3; h++) { std::memcpy(e.prop_hist[h], prop, sizeof(prop)); for (int t = 0; t < 12; t++) e.act_hist[h][t] = 0; }
+  }
+  a.yaw_accum_deg = b.yaw_accum_deg;     // the accumulator is the pair's
+  a.push_f[0] = a.push_f[1] = a.push_f[2] = 0; b.push_f[0] = b.push_f[1] = b.push_f[2] = 0;
+  if (cf.push_enabled) { double f[3]; sepmc_randomize_push(E, a, b, gid, f); }             // PR:54: draw #0 = _randomized_force
+  PairContacts none = {false, {false, false}};
+  sepmc_finish_obs(E, ev, gid, none, true);
+}
+
+void sepmc_step(llq_engine& E, Env& a, Env& b, int64_t gid, const float* act_a, const float* act_b, double* rew2, bool* done,
+                int64_t* ncr, int64_t* nlr) {   // CTG:378-424
+  const llq_config& cf = E.cfg;
+  Env* ev[2] = {&a, &b};
+  const float* acts[2] = {act_a, act_b};
+  double act[2][12], tgt[2][12];
+  for (int i = 0; i < 2; i++) {
+    ev[i]->episode_steps += 1; ev[i]->margin = 1e30;
+    for (int j = 0; j < 12; j++) { act[i][j] = (double)acts[i][j]; tgt[i][j] = ev[i]->q[j] + act[i][j]; }   // CTG:379-380
+  }
+  bool ok = true;
+  PairContacts pc = {false, {false, false}};
+  for (int s = 0; s < cf.substeps; s++) {
+    double tau[2][12];
+    for (int i = 0; i < 2; i++)
+      for (int j = 0; j < 12; j++) {
+        double tg = clampd(tgt[i][j], -3.0, 3.0);
+        tau[i][j] = clampd(cf.kp * (tg - ev[i]->q[j]) + cf.kd * (0.0 - ev[i]->qd[j]), -cf.max_tau, cf.max_tau);
+      }
+    // push randomiser with two robots (PR:56-87): inside the window every robot gets a freshly randomised force every sub-step
+    const double* push[2] = {nullptr, nullptr};
+    double pf[2][3];
+    if (cf.push_enabled) {
+      a.push_count += 1; b.push_count = a.push_count;
+      if (a.push_count > 0) {
+        double f[3];
+        if (a.push_count % cf.push_interval_steps == 0) { sepmc_randomize_push(E, a, b, gid, f); a.push_count = b.push_count = 0; }
+        if (a.push_count < cf.push_duration_steps) {
+          // robot 0 gets the current _randomized_force = draw #(push_draws - 1); robot 1 the next draw; then one more draw
+          double u[4];
+          for (int i = 0; i < 2; i++) {
+            stream_uniforms(cf.seed, gid, a.episode - 1, 2, (uint32_t)(a.push_draws - 1 + i), u);
+            double theta = 2.0 * M_PI * u[0], h = cf.push_h_lo + u[1] * (cf.push_h_hi - cf.push_h_lo);
+            pf[i][0] = h * std::cos(theta); pf[i][1] = h * std::sin(theta); pf[i][2] = cf.push_v_lo + u[2] * (cf.push_v_hi - cf.push_v_lo);
+            push[i] = pf[i];
+            for (int t = 0; t < 3; t++) ev[i]->push_f[t] = pf[i][t];
+          }
+          a.push_draws += 2; b.push_draws = a.push_draws;
+        }
+      }
+    }
+    if (s == cf.substeps - 1) pc = sepmc_contacts(E, a, b);            // manifolds of the last stepSimulation: its pre-step poses
+    for (int i = 0; i < 2; i++) {
+      if (ok) ok = physics_substep(E, *ev[i], tau[i], ncr, nlr, push[i]);
+      ev[i]->time += cf.sim_dt;
+    }
+  }
+  for (int i = 0; i < 2; i++) {
+    double st[LLQ_STATE_DIM], prop[LLQ_PROP_DIM];
+    pack_state(*ev[i], st);
+    make_prop(st, prop);
+    std::memmove(ev[i]->prop_hist[0], ev[i]->prop_hist[1], 2 * sizeof(ev[i]->prop_hist[0]));
+    std::memcpy(ev[i]->prop_hist[2], prop, sizeof(prop));
+    std::memmove(ev[i]->act_hist[0], ev[i]->act_hist[1], 2 * sizeof(ev[i]->act_hist[0]));
+    std::memcpy(ev[i]->act_hist[2], act[i], sizeof(act[i]));
+  }
+  sepmc_finish_obs(E, ev, gid, pc, false);
+  for (int i = 0; i < 2; i++) {                                         // stat_spd (CTG:368-373)
+    double spd = std::sqrt(ev[i]->linv[0] * ev[i]->linv[0] + ev[i]->linv[1] * ev[i]->linv[1]);
+    ev[i]->total_spd += spd;
+    if (spd > ev[i]->max_spd) ev[i]->max_spd = spd;
+    ev[i]->counter += 1;
+  }
+  // termination (CTG:458-470): robot 0's fall only, time, robot-0-body contact with robot 1
+  M3 R = qmat(qnormalize({a.quat[0], a.quat[1], a.quat[2], a.quat[3]}));
+  double left_z = R.m[0][2] * R.m[1][0] - R.m[1][2] * R.m[0][0];
+  bool fall0 = left_z > std::sin(45.0 * M_PI / 180.0) || left_z < std::sin(-45.0 * M_PI / 180.0) || R.m[2][2] < std::cos(60.0 * M_PI / 180.0);
+  *done = fall0 || a.counter >= cf.max_steps || pc.tag || !ok;
+  // rewards (CTG:640-652, 412-419)
+  double sw = (double)a.switch_flag;
+  if (a.with_flag) { rew2[0] = sw; rew2[1] = -sw; } else { rew2[0] = -sw; rew2[1] = sw; }
+  if (*done && pc.tag) {
+    if (a.with_flag) { rew2[0] += 1.0; rew2[1] -= 1.0; } else { rew2[0] -= 1.0; rew2[1] += 1.0; }
+  }
+  a.reward_sum += rew2[0]; b.reward_sum += rew2[1];
+}
+
 void update_sampling(llq_engine& E) {  // PLE:239-240
   double tot = 0;
   for (int c = 0; c < E.n_clips; c++) {
@@ -1038,7 +1364,7 @@ int check_ready(llq_handle h, bool need_reset) {
   if (!h) return fail(LLQ_EINVAL, "null handle");
   if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
   if (h->cfg.env_kind == LLQ_ENV_PMC && !h->has_mocap) return fail(LLQ_ESTATE, "llq_load_mocap has not been called");
-  if (h->cfg.env_kind == LLQ_ENV_EPMC && !h->has_init_state) return fail(LLQ_ESTATE, "llq_set_init_state has not been called");
+  if (h->cfg.env_kind != LLQ_ENV_PMC && !h->has_init_state) return fail(LLQ_ESTATE, "llq_set_init_state has not been called");
   if (need_reset && !h->was_reset) return fail(LLQ_ESTATE, "llq_reset has not been called");
   return LLQ_OK;
 }
@@ -1080,7 +1406,9 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   if (cfg->struct_size != (int32_t)sizeof(llq_config)) return fail(LLQ_EINVAL, "llq_config size mismatch (ABI)");
   if (cfg->n_envs <= 0) return fail(LLQ_EINVAL, "n_envs must be positive");
   if (cfg->substeps <= 0 || cfg->solver_iters < 0 || !(cfg->sim_dt > 0)) return fail(LLQ_EINVAL, "bad step configuration");
-  if (cfg->env_kind != LLQ_ENV_PMC && cfg->env_kind != LLQ_ENV_EPMC) return fail(LLQ_EINVAL, "unknown env_kind");
+  if (cfg->env_kind != LLQ_ENV_PMC && cfg->env_kind != LLQ_ENV_EPMC && cfg->env_kind != LLQ_ENV_SEPMC) return fail(LLQ_EINVAL, "unknown env_kind");
+  if (cfg->env_kind == LLQ_ENV_SEPMC && (cfg->n_envs % 2 != 0 || cfg->max_steps <= 0 || cfg->push_interval_steps <= 0))
+    return fail(LLQ_EINVAL, "SEPMC: n_envs counts robots and must be even");
   if (cfg->env_kind == LLQ_ENV_EPMC && (cfg->max_steps <= 0 || cfg->cmd_freq_hi <= cfg->cmd_freq_lo || cfg->cmd_freq_lo <= 0 ||
                                         cfg->push_interval_steps <= 0))
     return fail(LLQ_EINVAL, "bad EPMC configuration");
@@ -1178,6 +1506,12 @@ int llq_reset(llq_handle h, const uint8_t* mask, float* obs) {
   if (rc) return rc;
   const int od = h->obs_dim();
   for (int i = 0; i < h->cfg.n_envs; i++) {
+    if (h->cfg.env_kind == LLQ_ENV_SEPMC) {            // a pair is reset as a whole (mask of either robot)
+      if (i % 2) continue;
+      if (mask && !mask[i] && !mask[i + 1]) continue;
+      sepmc_reset(*h, h->envs[i], h->envs[i + 1], h->cfg.global_env_offset + i);
+      continue;
+    }
     if (mask && !mask[i]) continue;
     if (h->cfg.env_kind == LLQ_ENV_EPMC) epmc_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
     else sample_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
@@ -1216,7 +1550,8 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
   const int od = h->obs_dim();
   if (obs && obs_ld < od) return fail(LLQ_EINVAL, "obs_ld smaller than the observation width");
   const int n = h->cfg.n_envs;
-  const bool epmc = h->cfg.env_kind == LLQ_ENV_EPMC;
+  const bool epmc = h->cfg.env_kind != LLQ_ENV_PMC;   // no mocap table / sampling bookkeeping
+  const bool sepmc = h->cfg.env_kind == LLQ_ENV_SEPMC;
   std::vector<double> rew(n); std::vector<uint8_t> dn(n);
   int64_t ncr = 0, nlr = 0;
 #ifdef _OPENMP
@@ -1225,6 +1560,14 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
 #endif
   for (int i = 0; i < n; i++) {
     bool d = false;
+    if (sepmc) {
+      if (i % 2) continue;
+      double r2[2];
+      sepmc_step(*h, h->envs[i], h->envs[i + 1], h->cfg.global_env_offset + i, actions + (size_t)i * LLQ_ACTION_DIM,
+                 actions + (size_t)(i + 1) * LLQ_ACTION_DIM, r2, &d, &ncr, &nlr);
+      rew[i] = r2[0]; rew[i + 1] = r2[1]; dn[i] = dn[i + 1] = d ? 1 : 0;
+      continue;
+    }
     if (epmc) rew[i] = epmc_step(*h, h->envs[i], h->cfg.global_env_offset + i, actions + (size_t)i * LLQ_ACTION_DIM, &d, &ncr, &nlr);
     else rew[i] = step_env(*h, h->envs[i], actions + (size_t)i * LLQ_ACTION_DIM, &d, &ncr, &nlr);
     dn[i] = d ? 1 : 0;
@@ -1247,7 +1590,8 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
   if (h->cfg.auto_reset)
     for (int i = 0; i < n; i++)
       if (dn[i]) {
-        if (epmc) epmc_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
+        if (sepmc) { if (i % 2 == 0) sepmc_reset(*h, h->envs[i], h->envs[i + 1], h->cfg.global_env_offset + i); }
+        else if (epmc) epmc_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
         else sample_reset(*h, h->envs[i], h->cfg.global_env_offset + i);
       }
   if (obs)
@@ -1286,6 +1630,12 @@ int llq_get_field(llq_handle h, int field, void* dst) {
       case LLQ_F_OBS: std::memcpy((float*)dst + (size_t)i * h->obs_dim(), e.obs, sizeof(float) * h->obs_dim()); break;
       case LLQ_F_AUX: {
         double* a = (double*)dst + (size_t)i * LLQ_AUX_DIM;
+        if (h->cfg.env_kind == LLQ_ENV_SEPMC) {
+          a[0] = e.counter; a[1] = e.with_flag; a[2] = e.flag_x; a[3] = e.flag_y; a[4] = e.fix_spd; a[5] = e.visible; a[6] = e.switch_flag;
+          a[7] = e.total_spd; a[8] = e.max_spd; a[9] = e.push_count; a[10] = e.push_f[0]; a[11] = e.push_f[1]; a[12] = e.push_f[2];
+          a[13] = e.foot_mu; a[14] = e.push_draws; a[15] = e.flag_draws; a[16] = e.yaw_accum_deg; a[17] = 0;
+          break;
+        }
         a[0] = e.counter; a[1] = e.cmd_freq; a[2] = e.tgt_x; a[3] = e.tgt_y; a[4] = e.target_spd; a[5] = e.target_angle;
         a[6] = e.last_pos_diff_len; a[7] = e.total_spd; a[8] = e.max_spd; a[9] = e.push_count; a[10] = e.push_f[0];
         a[11] = e.push_f[1]; a[12] = e.push_f[2]; a[13] = e.foot_mu; a[14] = e.push_draws; a[15] = e.cmd_draws;
@@ -1330,6 +1680,12 @@ int llq_set_field(llq_handle h, int field, const void* src) {
       case LLQ_F_OB_ID: e.ob_id = ((const int32_t*)src)[i]; break;
       case LLQ_F_AUX: {
         const double* a = (const double*)src + (size_t)i * LLQ_AUX_DIM;
+        if (h->cfg.env_kind == LLQ_ENV_SEPMC) {
+          e.counter = (int)a[0]; e.with_flag = (int)a[1]; e.flag_x = a[2]; e.flag_y = a[3]; e.fix_spd = a[4]; e.visible = (int)a[5];
+          e.switch_flag = (int)a[6]; e.total_spd = a[7]; e.max_spd = a[8]; e.push_count = (int)a[9]; e.push_f[0] = a[10]; e.push_f[1] = a[11];
+          e.push_f[2] = a[12]; e.foot_mu = a[13]; e.push_draws = (int)a[14]; e.flag_draws = (int)a[15]; e.yaw_accum_deg = a[16];
+          break;
+        }
         e.counter = (int)a[0]; e.cmd_freq = (int)a[1]; e.tgt_x = a[2]; e.tgt_y = a[3]; e.target_spd = a[4]; e.target_angle = a[5];
         e.last_pos_diff_len = a[6]; e.total_spd = a[7]; e.max_spd = a[8]; e.push_count = (int)a[9]; e.push_f[0] = a[10];
         e.push_f[1] = a[11]; e.push_f[2] = a[12]; e.foot_mu = a[13]; e.push_draws = (int)a[14]; e.cmd_draws = (int)a[15];
@@ -1409,6 +1765,7 @@ int llq_oracle_obstacle_hit(llq_handle h, const double* st37, const double* pose
   double cy = std::cos(pose_xy_yaw[2]), sy = std::sin(pose_xy_yaw[2]);
   *hit = 0;
   for (const ProxyM& p : h->model.proxies) {
+    if (p.kind > 3) continue;
     V3 w = k.pl[p.link] + mul(k.Rl[p.link], p.c);
     double dx = w.x - pose_xy_yaw[0], dy = w.y - pose_xy_yaw[1], dz = w.z;
     double bx = cy * dx + sy * dy, by = -sy * dx + cy * dy;
