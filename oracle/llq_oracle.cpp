@@ -260,7 +260,7 @@ struct Env {
   int push_count, push_draws, cmd_draws; double push_f[3];
   int ob_id;      // active hurdle plate (PLE:179,264-265)
   // SEPMC (CTG): per-robot copies of the pair's game state
-  int with_flag, switch_flag, visible, flag_draws; double flag_x, flag_y, fix_spd;
+  int with_flag, switch_flag, visible, flag_draws, touch; double flag_x, flag_y, fix_spd;
   double yaw_accum_deg;   // PGE:181-189 mutates the shared init-state dict: every reset's yaw is applied on top of the previous ones
   float obs[LLQ_OBS_DIM_SEPMC];
 };
@@ -1270,8 +1270,10 @@ void sepmc_reset(llq_engine& E, Env& a, Env& b, int64_t gid) {   // CTG:261-304,
   a.yaw_accum_deg = b.yaw_accum_deg;     // the accumulator is the pair's
   a.push_f[0] = a.push_f[1] = a.push_f[2] = 0; b.push_f[0] = b.push_f[1] = b.push_f[2] = 0;
   if (cf.push_enabled) { double f[3]; sepmc_randomize_push(E, a, b, gid, f); }             // PR:54: draw #0 = _randomized_force
-  PairContacts none = {false, {false, false}};
-  sepmc_finish_obs(E, ev, gid, none, true);
+  // reset() runs _prepare_drill too (CTG:302), whose flag-switch test reads getContactPoints(): still the manifolds of the last
+  // stepSimulation of the previous episode (nothing has been stepped since)
+  PairContacts stale = {false, {a.touch != 0, b.touch != 0}};
+  sepmc_finish_obs(E, ev, gid, stale, false);
 }
 
 void sepmc_step(llq_engine& E, Env& a, Env& b, int64_t gid, const float* act_a, const float* act_b, double* rew2, bool* done,
@@ -1315,7 +1317,10 @@ void sepmc_step(llq_engine& E, Env& a, Env& b, int64_t gid, const float* act_a, 
         }
       }
     }
-    if (s == cf.substeps - 1) pc = sepmc_contacts(E, a, b);            // manifolds of the last stepSimulation: its pre-step poses
+    if (s == cf.substeps - 1) {                                        // manifolds of the last stepSimulation: its pre-step poses
+      pc = sepmc_contacts(E, a, b);
+      a.touch = pc.flag_touch[0]; b.touch = pc.flag_touch[1];
+    }
     for (int i = 0; i < 2; i++) {
       if (ok) ok = physics_substep(E, *ev[i], tau[i], ncr, nlr, push[i]);
       ev[i]->time += cf.sim_dt;
@@ -1633,7 +1638,7 @@ int llq_get_field(llq_handle h, int field, void* dst) {
         if (h->cfg.env_kind == LLQ_ENV_SEPMC) {
           a[0] = e.counter; a[1] = e.with_flag; a[2] = e.flag_x; a[3] = e.flag_y; a[4] = e.fix_spd; a[5] = e.visible; a[6] = e.switch_flag;
           a[7] = e.total_spd; a[8] = e.max_spd; a[9] = e.push_count; a[10] = e.push_f[0]; a[11] = e.push_f[1]; a[12] = e.push_f[2];
-          a[13] = e.foot_mu; a[14] = e.push_draws; a[15] = e.flag_draws; a[16] = e.yaw_accum_deg; a[17] = 0;
+          a[13] = e.foot_mu; a[14] = e.push_draws; a[15] = e.flag_draws; a[16] = e.yaw_accum_deg; a[17] = e.touch;
           break;
         }
         a[0] = e.counter; a[1] = e.cmd_freq; a[2] = e.tgt_x; a[3] = e.tgt_y; a[4] = e.target_spd; a[5] = e.target_angle;
@@ -1684,6 +1689,7 @@ int llq_set_field(llq_handle h, int field, const void* src) {
           e.counter = (int)a[0]; e.with_flag = (int)a[1]; e.flag_x = a[2]; e.flag_y = a[3]; e.fix_spd = a[4]; e.visible = (int)a[5];
           e.switch_flag = (int)a[6]; e.total_spd = a[7]; e.max_spd = a[8]; e.push_count = (int)a[9]; e.push_f[0] = a[10]; e.push_f[1] = a[11];
           e.push_f[2] = a[12]; e.foot_mu = a[13]; e.push_draws = (int)a[14]; e.flag_draws = (int)a[15]; e.yaw_accum_deg = a[16];
+          e.touch = (int)a[17];
           break;
         }
         e.counter = (int)a[0]; e.cmd_freq = (int)a[1]; e.tgt_x = a[2]; e.tgt_y = a[3]; e.target_spd = a[4]; e.target_angle = a[5];
@@ -1774,6 +1780,19 @@ int llq_oracle_obstacle_hit(llq_handle h, const double* st37, const double* pose
   }
   return LLQ_OK;
 }
+// oracle-only hook: world positions of the model's detection proxies ([n][3]) for a 37-double state; returns n through *count
+int llq_oracle_proxy_positions(llq_handle h, const double* st37, double* out, int32_t max_n, int32_t* count) {
+  if (!h || !st37 || !out || !count) return fail(LLQ_EINVAL, "bad arguments");
+  if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
+  const int n = (int)h->model.proxies.size();
+  if (n > max_n || n > 32) return fail(LLQ_EINVAL, "proxy buffer too small");
+  V3 p[32];
+  proxy_positions(*h, st37, p);
+  for (int i = 0; i < n; i++) { out[3 * i] = p[i].x; out[3 * i + 1] = p[i].y; out[3 * i + 2] = p[i].z; }
+  *count = n;
+  return LLQ_OK;
+}
+
 int llq_oracle_foot_positions(llq_handle h, const double* st37, double* out12) {
   if (!h || !st37 || !out12) return fail(LLQ_EINVAL, "bad arguments");
   if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");

@@ -23,6 +23,17 @@ for leg in ("FR", "FL", "HR", "HL"):
 JOINT_NAMES += ["joint_front_handle", "joint_hind_handle"]
 
 
+def _proxy_table():
+    from lifelike_agility_and_play_b200.model.compile_model import load_model_blob, H_OFF_PROXIES, H_NPROXIES, PROXY
+    b = load_model_blob()
+    o, n = int(b[H_OFF_PROXIES]), int(b[H_NPROXIES])
+    t = np.asarray(b[o:o + n * PROXY], dtype=np.float64).reshape(n, PROXY)
+    return t[:, 0].astype(int), t[:, 4].copy(), t[:, 5].astype(int)
+
+
+PROXY_LINKS, PROXY_RADII, PROXY_KINDS = _proxy_table()      # model link (pybullet link index + 1), radius, kind
+
+
 class _Body:
     def __init__(self, kind):
         self.kind = kind
@@ -45,7 +56,10 @@ class FakeBulletClient:
     GEOM_BOX, STATE_LOGGING_VIDEO_MP4, GEOM_CYLINDER = 3, 4, 5
     LINK_FRAME, WORLD_FRAME = 1, 2
 
-    oracle_engine = None      # VecEngine over libllq_cpu.so with n_envs = 1, set by the generator
+    oracle_engine = None      # VecEngine over libllq_cpu.so with n_envs = 1 (2 for the chase-tag pair), set by the generator
+    contact_breaking = 0.0005
+    boxes_block_rays = False  # chase-tag generator: createMultiBody boxes (walls, flag) are seen by rays
+    pair_contacts = False     # chase-tag generator: robot-robot / robot-flag contact points from detection proxies
     call_log = None
 
     def __init__(self, connection_mode=None):
@@ -92,6 +106,7 @@ class FakeBulletClient:
     def createMultiBody(self, baseMass=0, baseCollisionShapeIndex=-1, baseVisualShapeIndex=-1, basePosition=None, baseOrientation=None, **k):
         b = _Body("static")
         b.box = self.shapes[baseCollisionShapeIndex] if hasattr(self, "shapes") and baseCollisionShapeIndex >= 0 else None
+        b.ray_target = FakeBulletClient.boxes_block_rays
         if basePosition is not None:
             b.state[0:3] = basePosition
         if baseOrientation is not None:
@@ -114,38 +129,55 @@ class FakeBulletClient:
         assert linkIndex == 0 and flags == self.LINK_FRAME and not np.any(np.asarray(posObj))        # PR:73-77
         self.bodies[objectUniqueId].push = np.asarray(forceObj, dtype=np.float64).copy()
 
+    def _static_boxes(self):
+        """(uid, lo, hi) of everything a mask-6 ray can hit: the ground slab of plane.urdf (box 200 x 200 x 10 centred at
+        z = -5) and every live createMultiBody box (walls, flag).  Boxes are axis aligned in all shipped arenas."""
+        out = [(-2, np.array([-100.0, -100.0, -10.0]), np.array([100.0, 100.0, 0.0]))]
+        for uid, o in enumerate(self.bodies):
+            if o.kind == "static" and getattr(o, "box", None) is not None and np.any(o.box > 0) and getattr(o, "ray_target", False):
+                c = np.asarray(o.state[0:3], dtype=np.float64)
+                out.append((uid, c - o.box, c + o.box))
+        return out
+
     def rayTestBatch(self, rayFromPositions, rayToPositions, collisionFilterMask=-1, **kw):
-        """Closest hit against the static world of EPMC element 0: the ground slab of max_game_elements/data/urdf/plane.urdf
-        (box 200 x 200 x 10 centred at z = -5).  Independent slab test (not the oracle's code).  Mask 6 => robots are invisible."""
-        lo, hi = np.array([-100.0, -100.0, -10.0]), np.array([100.0, 100.0, 0.0])
+        """Closest hit against the static world.  Independent slab test (not the oracle's code).  Mask 6 => robots are invisible."""
+        boxes = self._static_boxes()
         out = []
         for a, b in zip(np.asarray(rayFromPositions, dtype=np.float64), np.asarray(rayToPositions, dtype=np.float64)):
             d = b - a
-            t0, t1, axis_in = 0.0, 1.0, -1
-            inside = bool(np.all(a > lo) and np.all(a < hi))
-            hit = not inside
-            if hit:
-                for ax in range(3):
-                    if d[ax] == 0.0:
-                        if a[ax] < lo[ax] or a[ax] > hi[ax]:
+            best = None
+            for uid, lo, hi in boxes:
+                t0, t1, axis_in = 0.0, 1.0, -1
+                inside = bool(np.all(a > lo) and np.all(a < hi))
+                hit = not inside
+                if hit:
+                    for ax in range(3):
+                        if d[ax] == 0.0:
+                            if a[ax] < lo[ax] or a[ax] > hi[ax]:
+                                hit = False
+                                break
+                            continue
+                        ta, tb = (lo[ax] - a[ax]) / d[ax], (hi[ax] - a[ax]) / d[ax]
+                        if ta > tb:
+                            ta, tb = tb, ta
+                        if ta > t0:
+                            t0, axis_in = ta, ax
+                        t1 = min(t1, tb)
+                        if t0 > t1:
                             hit = False
                             break
-                        continue
-                    ta, tb = (lo[ax] - a[ax]) / d[ax], (hi[ax] - a[ax]) / d[ax]
-                    if ta > tb:
-                        ta, tb = tb, ta
-                    if ta > t0:
-                        t0, axis_in = ta, ax
-                    t1 = min(t1, tb)
-                    if t0 > t1:
-                        hit = False
-                        break
-            if hit and axis_in >= 0:
+                if hit and axis_in >= 0 and (best is None or t0 < best[0]):
+                    best = (t0, axis_in, uid)
+            if best is not None:
+                t0, axis_in, uid = best
                 n = np.zeros(3); n[axis_in] = -np.sign(d[axis_in])
-                out.append((len(self.bodies) - 1, -1, t0, tuple(a + t0 * d), tuple(n)))
+                out.append((uid if uid >= 0 else len(self.bodies), -1, t0, tuple(a + t0 * d), tuple(n)))
             else:
                 out.append((-1, -1, 1.0, (0.0, 0.0, 0.0), (0.0, 0.0, 0.0)))
         return out
+
+    def rayTest(self, rayFromPosition, rayToPosition, collisionFilterMask=-1, **kw):
+        return self.rayTestBatch([rayFromPosition], [rayToPosition], collisionFilterMask)
 
     def setJointMotorControlArray(self, bodyUniqueId, jointIndices, controlMode, forces=None, **kw):
         if controlMode == self.TORQUE_CONTROL:
@@ -178,27 +210,55 @@ class FakeBulletClient:
         s = self.bodies[uid].state
         return [(s[13 + LEG_LINKS.index(j)], s[25 + LEG_LINKS.index(j)], (0.0,) * 6, 0.0) for j in indices]
 
+    def _proxy_positions(self, b):
+        st = np.ascontiguousarray(b.state, dtype=np.float64)
+        out = np.zeros((32, 3))
+        n = C.c_int32(0)
+        self._lib.llq_oracle_proxy_positions.restype = C.c_int
+        assert self._lib.llq_oracle_proxy_positions(self._h, st.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p), 32, C.byref(n)) == 0
+        return out[:n.value]
+
     def getLinkStates(self, uid, indices, computeForwardKinematics=False, computeLinkVelocity=False):
-        assert list(indices) == FOOT_LINKS
-        st = np.ascontiguousarray(self.bodies[uid].state, dtype=np.float64)
-        out = np.zeros(12)
-        rc = self._lib.llq_oracle_foot_positions(self._h, st.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
-        assert rc == 0
         z3 = (0.0, 0.0, 0.0)
-        return [(tuple(out[3 * i:3 * i + 3]), (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, z3) for i in range(4)]
+        b = self.bodies[uid]
+        if list(indices) == FOOT_LINKS:
+            st = np.ascontiguousarray(b.state, dtype=np.float64)
+            out = np.zeros(12)
+            rc = self._lib.llq_oracle_foot_positions(self._h, st.ctypes.data_as(C.c_void_p), out.ctypes.data_as(C.c_void_p))
+            assert rc == 0
+            return [(tuple(out[3 * i:3 * i + 3]), (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, z3) for i in range(4)]
+        # feet / wheels / handles (LR:150-156): link COM == link origin == the proxy sphere centre for these links
+        pp = self._proxy_positions(b)
+        by_link = {int(l) - 1: k for k, l in enumerate(PROXY_LINKS) if PROXY_KINDS[k] != 3}
+        return [(tuple(pp[by_link[j]]), (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, z3) for j in indices]
 
     # ---- the physics step
-    def stepSimulation(self):
-        for b in self.bodies:
-            if b.kind != "dynamic":
-                continue
-            if b.dirty:
-                st = np.ascontiguousarray(b.state, dtype=np.float64)
-                assert self._lib.llq_oracle_set_state64(self._h, 0, st.ctypes.data_as(C.c_void_p)) == 0
-                b.dirty = False
-            # narrow phase on the pre-step pose: robot (oracle detection proxies) vs every static box body
-            self._contacts = []
-            self._lib.llq_oracle_obstacle_hit.restype = C.c_int
+    def _narrow_phase(self):
+        """Contact points for getContactPoints(), built on the pre-step poses.  PMC: robot detection proxies vs static boxes
+        through the oracle's hurdle test.  Chase tag: independent numpy sphere-sphere / sphere-box tests over the model's
+        proxies (link index = model link - 1), in body order."""
+        self._contacts = []
+        dyn = [b for b in self.bodies if b.kind == "dynamic"]
+        if FakeBulletClient.pair_contacts:
+            thr = FakeBulletClient.contact_breaking
+            pps = [self._proxy_positions(b) for b in dyn]
+            ids = [self.bodies.index(b) for b in dyn]
+            for ia in range(len(dyn)):
+                for ib in range(ia + 1, len(dyn)):
+                    for ka in range(len(PROXY_LINKS)):
+                        for kb in range(len(PROXY_LINKS)):
+                            if np.linalg.norm(pps[ia][ka] - pps[ib][kb]) - PROXY_RADII[ka] - PROXY_RADII[kb] < thr:
+                                self._contacts.append((0, ids[ia], ids[ib], int(PROXY_LINKS[ka]) - 1, int(PROXY_LINKS[kb]) - 1))
+                for uid, o in enumerate(self.bodies):
+                    if o.kind == "static" and getattr(o, "box", None) is not None and getattr(o, "is_flag", False):
+                        c = np.asarray(o.state[0:3])
+                        for ka in range(len(PROXY_LINKS)):
+                            q = pps[ia][ka] - np.clip(pps[ia][ka], c - o.box, c + o.box)
+                            if np.linalg.norm(q) - PROXY_RADII[ka] < thr:
+                                self._contacts.append((0, ids[ia], uid, int(PROXY_LINKS[ka]) - 1, -1))
+            return
+        self._lib.llq_oracle_obstacle_hit.restype = C.c_int
+        for b in dyn:
             for uid, o in enumerate(self.bodies):
                 if o.kind == "static" and getattr(o, "box", None) is not None and np.any(o.box > 0):
                     x, y, z, w = o.state[3:7] / np.linalg.norm(o.state[3:7])
@@ -210,14 +270,24 @@ class FakeBulletClient:
                                                              half.ctypes.data_as(C.c_void_p), C.byref(hit)) == 0
                     if hit.value:
                         self._contacts.append((0, self.bodies.index(b), uid, -1, -1))
+
+    def stepSimulation(self):
+        dyn = [b for b in self.bodies if b.kind == "dynamic"]
+        for k, b in enumerate(dyn):
+            if b.dirty:
+                st = np.ascontiguousarray(b.state, dtype=np.float64)
+                assert self._lib.llq_oracle_set_state64(self._h, k, st.ctypes.data_as(C.c_void_p)) == 0
+                b.dirty = False
+        self._narrow_phase()
+        for k, b in enumerate(dyn):
             tau = np.ascontiguousarray(b.tau, dtype=np.float64)
             push = None if b.push is None else np.ascontiguousarray(b.push, dtype=np.float64)
             self._lib.llq_oracle_substep_push.argtypes = [C.c_void_p, C.c_int32, C.c_void_p, C.c_void_p, C.c_double]
-            assert self._lib.llq_oracle_substep_push(self._h, 0, tau.ctypes.data_as(C.c_void_p),
+            assert self._lib.llq_oracle_substep_push(self._h, k, tau.ctypes.data_as(C.c_void_p),
                                                       None if push is None else push.ctypes.data_as(C.c_void_p), C.c_double(b.foot_mu)) == 0
             b.push = None                 # external forces last one step
             out = np.zeros(37)
-            assert self._lib.llq_oracle_get_state64(self._h, 0, out.ctypes.data_as(C.c_void_p)) == 0
+            assert self._lib.llq_oracle_get_state64(self._h, k, out.ctypes.data_as(C.c_void_p)) == 0
             b.state = out
             b.tau = np.zeros(12)          # Bullet clears applied torques after every step
 
