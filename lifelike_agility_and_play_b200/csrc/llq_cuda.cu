@@ -127,6 +127,15 @@ void launch_reset_t(llq_handle h, const llq::EnvArrays& E, const llq::ResetParam
 }
 void launch_step(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
   const bool epmc = h->cfg.env_kind == LLQ_ENV_EPMC;
+  if (h->cfg.env_kind == LLQ_ENV_SEPMC) {
+    switch (h->block) {
+      case 32: launch_step_t<32, 2>(h, E, a, obs2, ld, s); break;
+      case 64: launch_step_t<64, 2>(h, E, a, obs2, ld, s); break;
+      default: launch_step_t<128, 2>(h, E, a, obs2, ld, s); break;
+    }
+    h->counters[4]++;
+    return;
+  }
   switch (h->block) {
     case 32: if (epmc) launch_step_t<32, 1>(h, E, a, obs2, ld, s); else launch_step_t<32, 0>(h, E, a, obs2, ld, s); break;
     case 64: if (epmc) launch_step_t<64, 1>(h, E, a, obs2, ld, s); else launch_step_t<64, 0>(h, E, a, obs2, ld, s); break;
@@ -136,6 +145,7 @@ void launch_step(llq_handle h, const llq::EnvArrays& E, const float* a, float* o
 }
 void launch_reset(llq_handle h, const llq::EnvArrays& E, const llq::ResetParams& RP, float* obs2, long long ld, cudaStream_t s) {
   if (h->cfg.env_kind == LLQ_ENV_EPMC) launch_reset_t<128, 1>(h, E, RP, obs2, ld, s);
+  else if (h->cfg.env_kind == LLQ_ENV_SEPMC) launch_reset_t<128, 2>(h, E, RP, obs2, ld, s);
   else launch_reset_t<128, 0>(h, E, RP, obs2, ld, s);
   h->counters[4]++;
 }
@@ -155,7 +165,7 @@ int check_ready(llq_handle h, bool need_reset) {
   if (!h) return fail(LLQ_EINVAL, "null handle");
   if (!h->has_model) return fail(LLQ_ESTATE, "llq_load_model has not been called");
   if (h->cfg.env_kind == LLQ_ENV_PMC && !h->has_mocap) return fail(LLQ_ESTATE, "llq_load_mocap has not been called");
-  if (h->cfg.env_kind == LLQ_ENV_EPMC && !h->has_init_state) return fail(LLQ_ESTATE, "llq_set_init_state has not been called");
+  if (h->cfg.env_kind != LLQ_ENV_PMC && !h->has_init_state) return fail(LLQ_ESTATE, "llq_set_init_state has not been called");
   if (need_reset && !h->was_reset) return fail(LLQ_ESTATE, "llq_reset has not been called");
   return set_device(h);
 }
@@ -215,7 +225,9 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   if (cfg->struct_size != (int32_t)sizeof(llq_config)) return fail(LLQ_EINVAL, "llq_config size mismatch (ABI)");
   if (cfg->n_envs <= 0) return fail(LLQ_EINVAL, "n_envs must be positive");
   if (cfg->substeps <= 0 || cfg->solver_iters < 0 || !(cfg->sim_dt > 0)) return fail(LLQ_EINVAL, "bad step configuration");
-  if (cfg->env_kind != LLQ_ENV_PMC && cfg->env_kind != LLQ_ENV_EPMC) return fail(LLQ_EINVAL, "unknown env_kind");
+  if (cfg->env_kind != LLQ_ENV_PMC && cfg->env_kind != LLQ_ENV_EPMC && cfg->env_kind != LLQ_ENV_SEPMC) return fail(LLQ_EINVAL, "unknown env_kind");
+  if (cfg->env_kind == LLQ_ENV_SEPMC && (cfg->n_envs % 2 != 0 || cfg->max_steps <= 0 || cfg->push_interval_steps <= 0))
+    return fail(LLQ_EINVAL, "SEPMC: n_envs counts robots and must be even");
   if (cfg->env_kind == LLQ_ENV_EPMC && (cfg->max_steps <= 0 || cfg->cmd_freq_hi <= cfg->cmd_freq_lo || cfg->cmd_freq_lo <= 0 ||
                                         cfg->push_interval_steps <= 0))
     return fail(LLQ_EINVAL, "bad EPMC configuration");
@@ -226,7 +238,7 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   llq_engine* h = new (std::nothrow) llq_engine();
   if (!h) return fail(LLQ_ENOMEM, "out of memory");
   h->cfg = *cfg;
-  h->obs_dim = cfg->env_kind == LLQ_ENV_EPMC ? LLQ_OBS_DIM_EPMC : LLQ_OBS_DIM;
+  h->obs_dim = cfg->env_kind == LLQ_ENV_EPMC ? LLQ_OBS_DIM_EPMC : (cfg->env_kind == LLQ_ENV_SEPMC ? LLQ_OBS_DIM_SEPMC : LLQ_OBS_DIM);
   if (const char* b = std::getenv("LLQ_BLOCK")) {
     int v = std::atoi(b);
     if (v == 32 || v == 64 || v == 128) h->block = v;
@@ -253,7 +265,7 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   if (ce == cudaSuccess) ce = cudaMallocHost((void**)&h->h_done, n);
   if (ce != cudaSuccess) { llq_destroy(h); return fail(LLQ_ECUDA, cudaGetErrorString(ce)); }
 #undef TRY
-  if (cfg->env_kind == LLQ_ENV_EPMC) {   // no mocap table: the winner/avg buffers are still passed to the kernels (unused)
+  if (cfg->env_kind != LLQ_ENV_PMC) {   // no mocap table: the winner/avg buffers are still passed to the kernels (unused)
     h->frame_dt = 1.0 / 120.0; h->margin = 0;
     fill_params(h);
   }
@@ -323,9 +335,14 @@ int llq_load_model(llq_handle h, const double* b, int64_t n) {
   {   // detection proxies for the hurdle plate
     const double* pr = b + (int64_t)b[LLQ_H_OFF_PROXIES];
     const double* gen = b + (int64_t)b[LLQ_H_OFF_GENERIC];
-    int nw = 0, nh = 0, nc = 0;
+    int nw = 0, nh = 0, nc = 0, nhd = 0;
     for (int i = 0; i < (int)b[LLQ_H_NPROXIES]; i++, pr += LLQ_PROXY) {
       const int link = (int)pr[0], kind = (int)pr[5];
+      if (kind == 4 && nhd < 2) {         // handle (fixed to the body): joint origin + shape offset, relative to the base reference point
+        const double* g = gen + (size_t)link * LLQ_GL;
+        for (int t = 0; t < 3; t++) M.handle[nhd][t] = (float)(g[LLQ_G_JXYZ + t] + pr[1 + t] - gen[LLQ_G_COM + t]);
+        M.handle[nhd++][3] = (float)pr[4];
+      }
       if (kind == 1 && nw < 4) {          // wheel: its (fixed) joint origin in the thigh frame + the shape offset (joint rpy only spins the symmetric cylinder)
         const double* g = gen + (size_t)link * LLQ_GL;
         for (int t = 0; t < 3; t++) M.wheel_off[nw][t] = (float)(g[LLQ_G_JXYZ + t] + pr[1 + t]);

@@ -23,8 +23,8 @@
 
 namespace llq {
 
-constexpr int kObsDim = 207, kObsDimEpmc = 916, kPropDim = 33, kActDim = 12, kStateDim = 37, kAuxDim = 18;
-template <int ENV> struct ObsW { static constexpr int value = ENV == 1 ? kObsDimEpmc : kObsDim; };
+constexpr int kObsDim = 207, kObsDimEpmc = 916, kObsDimSepmc = 965, kPropDim = 33, kActDim = 12, kStateDim = 37, kAuxDim = 18;
+template <int ENV> struct ObsW { static constexpr int value = ENV == 1 ? kObsDimEpmc : (ENV == 2 ? kObsDimSepmc : kObsDim); };
 constexpr int kNewObs = 120;
 constexpr int kRowFloats = 153;  // per-lane floats of the constraint-row workspace in shared memory (Yc 18 | Yl 18 | Ul 9 | Acl 36 | Alc 36 | All 36)  // floats staged per env: prop 33 | action 12 | future 72 (+3 pad)
 
@@ -43,6 +43,7 @@ struct alignas(16) ModelConst {
   float init_state[37]; float pad_[3]; // EPMC episode start state (LR:115-117, utils/constants.py:103-116)
   // detection proxies for the PMC hurdle plate: wheel (knee) centre in the thigh frame + radius, hip radius, body-box corners (base coords)
   float wheel_off[4][3]; float wheel_r[4]; float hip_r[4]; float corner[8][3];
+  float handle[2][4];                  // SEPMC: front / hind handle centre (base coords) + radius (LR:150-156)
 };
 
 struct MocapFrame { double x, y, z, pad; float quat[4]; float q[12]; };  // 96 B, 16-byte aligned
@@ -271,6 +272,164 @@ LLQ_DI void epmc_randomize_push(const StepParams& P, unsigned long long seed, lo
   pf[0] = (float)(h * cs); pf[1] = (float)(h * sn); pf[2] = (float)((double)P.pv_lo + u[2] * ((double)P.pv_hi - (double)P.pv_lo));
 }
 
+
+LLQ_DI void push_force_of_draw(const StepParams& P, unsigned long long seed, long long gid, long long ep, int index, float (&pf)[3]) {
+  int d = index;
+  epmc_randomize_push(P, seed, gid, ep, d, pf);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
+// SEPMC (ChaseTagGameEnv, max_game/chase_tag_game_env.py = CTG; arena = max_game/bullet_static_entities.py:863-902):
+// robots 2p and 2p+1 are the two agents of pair p (adjacent 4-lane groups of one warp).
+constexpr float kWallIn = 2.495f;    // inner faces of the four 0.01 m walls centred at +-2.5
+// closest hit fraction of the segment o -> o + d against the arena's static boxes (ground slab, 4 walls, flag), or -1
+LLQ_DI float ray_box1(V3 o, V3 d, V3 lo, V3 hi, float best) {
+  if (o.x > lo.x && o.x < hi.x && o.y > lo.y && o.y < hi.y && o.z > lo.z && o.z < hi.z) return best;   // starts inside: no hit
+  float t0 = 0.f, t1 = 1.f;
+  bool hit = true, entered = false;
+  const float oo[3] = {o.x, o.y, o.z}, dd[3] = {d.x, d.y, d.z}, l[3] = {lo.x, lo.y, lo.z}, h[3] = {hi.x, hi.y, hi.z};
+#pragma unroll
+  for (int ax = 0; ax < 3; ax++) {
+    if (dd[ax] == 0.f) { if (oo[ax] < l[ax] || oo[ax] > h[ax]) hit = false; continue; }
+    const float inv = 1.0f / dd[ax];
+    float ta = (l[ax] - oo[ax]) * inv, tb = (h[ax] - oo[ax]) * inv;
+    if (ta > tb) { const float t = ta; ta = tb; tb = t; }
+    if (ta > t0) { t0 = ta; entered = true; }
+    t1 = fminf(t1, tb);
+    if (t0 > t1) hit = false;
+  }
+  if (hit && entered && (best < 0.f || t0 < best)) best = t0;
+  return best;
+}
+LLQ_DI float ray_arena(V3 o, V3 d, float fx, float fy) {
+  float b = -1.f;
+  b = ray_box1(o, d, V3{-100.f, -100.f, -10.f}, V3{100.f, 100.f, 0.f}, b);
+  b = ray_box1(o, d, V3{-2.5f, 2.495f, 0.f}, V3{2.5f, 2.505f, 2.f}, b);
+  b = ray_box1(o, d, V3{-2.5f, -2.505f, 0.f}, V3{2.5f, -2.495f, 2.f}, b);
+  b = ray_box1(o, d, V3{2.495f, -2.5f, 0.f}, V3{2.505f, 2.5f, 2.f}, b);
+  b = ray_box1(o, d, V3{-2.505f, -2.5f, 0.f}, V3{-2.495f, 2.5f, 2.f}, b);
+  b = ray_box1(o, d, V3{fx - 0.05f, fy - 0.05f, 0.f}, V3{fx + 0.05f, fy + 0.05f, 0.5f}, b);
+  return b;
+}
+LLQ_DI float flag_dist(V3 c, float fx, float fy) {    // distance of a point to the flag box (CTG:163-190)
+  const float qx = c.x - clampf(c.x, fx - 0.05f, fx + 0.05f), qy = c.y - clampf(c.y, fy - 0.05f, fy + 0.05f), qz = c.z - clampf(c.z, 0.f, 0.5f);
+  return sqrtf(qx * qx + qy * qy + qz * qz);
+}
+// points of this lane's leg in base coordinates (B' axes about the base reference point)
+LLQ_DI void leg_points(const ModelConst& M, const LegConst& L, int k, const float (&q)[3], V3& hip, V3& wheel, V3& foot) {
+  float c1, s1, c2, s2, c3, s3;
+  sincosf(q[0], &s1, &c1); sincosf(-q[1], &s2, &c2); sincosf(-q[2], &s3, &c3);
+  hip = ld3(L.j[0].r);
+  const V3 p2 = hip + rot<0>(ld3(L.j[1].r), c1, s1);
+  wheel = p2 + rot<0>(rot<1>(ld3(M.wheel_off[k]), c2, s2), c1, s1);
+  V3 f = rot<1>(ld3(L.foot), c3, s3) + ld3(L.j[2].r);
+  f = rot<1>(f, c2, s2) + ld3(L.j[1].r);
+  foot = rot<0>(f, c1, s1) + hip;
+}
+// force of push-randomiser draw `index` (PR:89-99)
+
+// staging row of SEPMC (kNewObs floats per robot): prop 33 | action 12 | R 9 (45) | pos 3 (54) | flag xy 2 (57) | yaw 1 (59) | pad 2 |
+// small vectors 52 (62): percept_vec 5, oppo_info 15, oppo_info_cheat 15, flag_info 7, flag_info_cheat 7, with_flag 2, control_spd 1
+struct PairState { int with_flag, flag_draws, visible, sw; double flag_x, flag_y; };
+
+// End-of-step pair logic shared by the step and the reset kernels (CTG:495-596, 472-493): visibility, flag switch, the small
+// observation vectors.  Every lane of both robots runs it; `snew` is the robot's staging row, `spart` the partner's.
+LLQ_DI void sepmc_pair_tail(const ModelConst& M, const LegConst& L, int k, int robot, float* snew, const float* spart, double px, double py,
+                            double pz, Q4 qp, Q4 qb, V3 vw, V3 ww, const float (&q)[3], bool touch_own, float fix_spd, unsigned long long seed,
+                            long long pair_gid, long long epi, PairState& S) {
+  const M3 Rp = qmat(qp);
+  const V3 pos = V3{(float)px, (float)py, (float)pz};
+  // own convex points (LR:150-156) in world coordinates -> staging row, read by the partner
+  {
+    V3 hip, wheel, foot;
+    leg_points(M, L, k, q, hip, wheel, foot);
+    const V3 fw = pos + mul(Rp, foot), ww_ = pos + mul(Rp, wheel);
+    snew[3 * k] = fw.x; snew[3 * k + 1] = fw.y; snew[3 * k + 2] = fw.z;
+    snew[12 + 3 * k] = ww_.x; snew[13 + 3 * k] = ww_.y; snew[14 + 3 * k] = ww_.z;
+    if (k < 2) {
+      const V3 hw = pos + mul(Rp, V3{M.handle[k][0], M.handle[k][1], M.handle[k][2]});
+      snew[24 + 3 * k] = hw.x; snew[25 + 3 * k] = hw.y; snew[26 + 3 * k] = hw.z;
+    }
+  }
+  __syncwarp();
+  // partner's root state
+  const double ox = __shfl_xor_sync(FULL, px, 4), oy = __shfl_xor_sync(FULL, py, 4), oz = __shfl_xor_sync(FULL, pz, 4);
+  const Q4 oq = Q4{__shfl_xor_sync(FULL, qb.x, 4), __shfl_xor_sync(FULL, qb.y, 4), __shfl_xor_sync(FULL, qb.z, 4), __shfl_xor_sync(FULL, qb.w, 4)};
+  const V3 ov = V3{__shfl_xor_sync(FULL, vw.x, 4), __shfl_xor_sync(FULL, vw.y, 4), __shfl_xor_sync(FULL, vw.z, 4)};
+  const V3 oww = V3{__shfl_xor_sync(FULL, ww.x, 4), __shfl_xor_sync(FULL, ww.y, 4), __shfl_xor_sync(FULL, ww.z, 4)};
+  const bool touch_other = __shfl_xor_sync(FULL, touch_own ? 1 : 0, 4) != 0;
+  const V3 opos = V3{(float)ox, (float)oy, (float)oz};
+  const float fx = (float)S.flag_x, fy = (float)S.flag_y;
+  // visibility (CTG:472-493): the root segment is cast from robot 0 to robot 1 for both agents
+  const V3 ra = robot == 0 ? pos : opos, rb = robot == 0 ? opos : pos;
+  bool vis = ray_arena(ra, rb - ra, fx, fy) < 0.f;
+  {
+    const V3 head = V3{snew[24], snew[25], snew[26]};
+    const V3 tf = V3{spart[3 * k], spart[3 * k + 1], spart[3 * k + 2]}, tw = V3{spart[12 + 3 * k], spart[13 + 3 * k], spart[14 + 3 * k]};
+    bool any = ray_arena(head, tf - head, fx, fy) < 0.f || ray_arena(head, tw - head, fx, fy) < 0.f;
+    if (k < 2) {
+      const V3 th = V3{spart[24 + 3 * k], spart[25 + 3 * k], spart[26 + 3 * k]};
+      any = any || ray_arena(head, th - head, fx, fy) < 0.f;
+    }
+    int a = any ? 1 : 0;
+    a |= __shfl_xor_sync(FULL, a, 1);
+    a |= __shfl_xor_sync(FULL, a, 2);
+    vis = vis || a != 0;
+  }
+  const Q4 q1 = qnormalize(qb);
+  const M3 Rq = qmat(q1);
+  {
+    // cos of the bearing of the opponent against visible_angle = pi; in fp64 so that |cos| <= 1 holds unless fp64 itself rounds over
+    const double c = (double)Rq.a00, s_ = (double)Rq.a10, n = sqrt(c * c + s_ * s_);
+    const double dx = ox - px, dy = oy - py;
+    const double cv = ((c / n) * dx + (s_ / n) * dy) / sqrt(dx * dx + dy * dy);
+    vis = vis && cv >= -1.0;
+  }
+  __syncwarp();   // convex points consumed; the row is free for the observation staging
+  S.visible = vis ? 1 : 0;
+  // flag switch (CTG:573-581): the robot without the flag touches it
+  const int wf_old = S.with_flag;
+  const double ffx = S.flag_x, ffy = S.flag_y;
+  S.sw = 0;
+  if ((wf_old && touch_other) || (!wf_old && touch_own)) {
+    S.with_flag = 1 - wf_old;
+    S.sw = 1;
+    double u[4];
+    stream_uniforms(seed, pair_gid, epi, 4, (unsigned)S.flag_draws, u);
+    S.flag_draws += 1;
+    S.flag_x = -2.0 + 4.0 * u[0]; S.flag_y = -2.0 + 4.0 * u[1];
+  }
+  if (k == 0) {
+    const V3 wl = tmul(Rq, ww), vl = tmul(Rq, vw);
+    snew[24] = wl.x; snew[25] = wl.y; snew[26] = wl.z; snew[27] = vl.x; snew[28] = vl.y; snew[29] = vl.z;
+    snew[30] = Rq.a20; snew[31] = Rq.a21; snew[32] = Rq.a22;
+    snew[45] = Rq.a00; snew[46] = Rq.a01; snew[47] = Rq.a02; snew[48] = Rq.a10; snew[49] = Rq.a11; snew[50] = Rq.a12;
+    snew[51] = Rq.a20; snew[52] = Rq.a21; snew[53] = Rq.a22;
+    snew[54] = pos.x; snew[55] = pos.y; snew[56] = pos.z;
+    snew[57] = (float)ffx; snew[58] = (float)ffy;                       // the flag where it stood during this step
+    const float yaw = atan2f(Rq.a10, Rq.a00);
+    snew[59] = yaw;
+    float sy, cy;
+    sincosf(yaw, &sy, &cy);
+    float* v = snew + 62;
+    v[0] = pos.x; v[1] = pos.y; v[2] = pos.z; v[3] = cy; v[4] = sy;                          // percept_vec
+    const M3 Ro = qmat(qnormalize(oq));
+    const float yawo = atan2f(Ro.a10, Ro.a00);
+    float sd, cd;
+    sincosf(yawo - yaw, &sd, &cd);
+    const V3 dl = tmul(Rq, V3{(float)(ox - px), (float)(oy - py), (float)(oz - pz)}), ovl = tmul(Rq, ov), owl = tmul(Rq, oww);
+    const float oppo[15] = {vis ? 1.f : 0.f, opos.x, opos.y, opos.z, dl.x, dl.y, dl.z, cd, sd, ovl.x, ovl.y, ovl.z, owl.x, owl.y, owl.z};
+#pragma unroll
+    for (int t = 0; t < 15; t++) { v[5 + t] = vis ? oppo[t] : 0.f; v[20 + t] = oppo[t]; }
+    const V3 fl = tmul(Rq, V3{(float)(ffx - px), (float)(ffy - py), (float)(0.25 - pz)});
+    const float fi[7] = {1.f, (float)ffx, (float)ffy, 0.25f, fl.x, fl.y, fl.z};
+#pragma unroll
+    for (int t = 0; t < 7; t++) { v[35 + t] = fi[t]; v[42 + t] = fi[t]; }
+    v[49] = (float)S.with_flag; v[50] = (float)(1 - S.with_flag);                              // CTG:584, after a possible switch
+    v[51] = fix_spd;
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Shared tail: given the dynamic robot state (pybullet convention) and the mocap cursor, build the new prop / future
 // into the staging row `snew` (120 floats per env) and return the pieces the reward needs.
@@ -356,6 +515,34 @@ LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const floa
         else v = a < 24 ? hs[66 + a] : sn[kPropDim + a - 24];
       } else if (ENV == 0) {
         v = sn[45 + (j - 135)];
+      } else if (ENV == 2) {
+        // SEPMC perception against ground slab, walls and flag (CTG:598-638, PGE:22-54)
+        const V3 pos = V3{sn[54], sn[55], sn[56]};
+        const float fx = sn[57], fy = sn[58];
+        if (j < 460) {                             // percept_2d: down rays over the 25 x 13 grid in the full base frame, value = hit z
+          const int t = j - 135, a = t / 13, b = t - a * 13;
+          const float gx = a == 24 ? 1.2f : -1.2f + (float)a * (2.4f / 24.0f), gy = b == 12 ? 0.6f : -0.6f + (float)b * (1.2f / 12.0f);
+          const float x = fmaf(sn[45], gx, fmaf(sn[46], gy, pos.x)), y = fmaf(sn[48], gx, fmaf(sn[49], gy, pos.y));
+          const float f = ray_arena(V3{x, y, 10.f}, V3{0.f, 0.f, -20.f}, fx, fy);
+          v = f < 0.f ? 0.f : fmaf(f, -20.f, 10.f);
+          if (f >= 0.f && fabsf(v) < 2e-6f) v = 0.f;                     // the slab top is exactly z = 0
+        } else if (j < 588) {                      // percept_1d: 128 horizontal rays of 20 m; a miss reports |ray_from|
+          const float ang = sn[59] + 6.283185307179586f * (float)(j - 460) * (1.0f / 128.0f);
+          float sa, ca;
+          sincosf(ang, &sa, &ca);
+          const V3 d = V3{20.f * ca, 20.f * sa, 0.f};
+          const float f = ray_arena(pos, d, fx, fy);
+          v = f < 0.f ? norm3(pos) : f * 20.f * sqrtf(ca * ca + sa * sa);
+        } else if (j < 913) {                      // percept_front: 25 x 13 rays of 3 m along body +x; a miss reports 3
+          const int t = j - 588, a = t / 13, b = t - a * 13;
+          const float y = a == 24 ? 0.25f : -0.25f + (float)a * (0.5f / 24.0f), z = b == 12 ? 0.1f : -0.3f + (float)b * (0.4f / 12.0f);
+          const V3 from = V3{fmaf(sn[46], y, fmaf(sn[47], z, pos.x)), fmaf(sn[49], y, fmaf(sn[50], z, pos.y)), fmaf(sn[52], y, fmaf(sn[53], z, pos.z))};
+          const V3 d = V3{3.f * sn[45], 3.f * sn[48], 3.f * sn[51]};
+          const float f = ray_arena(from, d, fx, fy);
+          v = (f < 0.f ? 1.f : f) * norm3(d);
+        } else {
+          v = sn[62 + (j - 913)];
+        }
       } else if (j < 460) {
         v = 0.f;                                   // percep_2d: every down-ray hits the slab top, hit z = 0 (PGE:431-447)
       } else if (j < 588) {
@@ -449,6 +636,20 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
   double tgx = 0.0, tgy = 0.0, total_spd = 0.0, max_spd = 0.0, target_angle = 0.0, last_len = 0.0;
   float target_spd = 0.f, pf[3] = {0.f, 0.f, 0.f}, mu_env = P.mu;
   long long epi = 0;
+  // ---- SEPMC bookkeeping (pair state replicated on both robots): CTG / PR
+  PairState PS = {0, 0, 1, 0, 0.0, 0.0};
+  float fix_spd = 0.f;
+  bool touch_own = false, tag = false;
+  const int robot = env & 1;
+  const long long pair_gid = gid0 + (env & ~1);
+  if (ENV == 2) {
+    const double* A = E.aux;
+    counter = (int)A[env]; PS.with_flag = (int)A[N + env]; PS.flag_x = A[2 * N + env]; PS.flag_y = A[3 * N + env];
+    fix_spd = (float)A[4 * N + env]; total_spd = A[7 * N + env]; max_spd = A[8 * N + env]; push_count = (int)A[9 * N + env];
+    pf[0] = (float)A[10 * N + env]; pf[1] = (float)A[11 * N + env]; pf[2] = (float)A[12 * N + env];
+    mu_env = P.mu_ground * (float)A[13 * N + env]; push_draws = (int)A[14 * N + env]; PS.flag_draws = (int)A[15 * N + env];
+    epi = E.episode[env] - 1;
+  }
   if (ENV == 1) {
     const double* A = E.aux;
     counter = (int)A[env]; cmd_freq = (int)A[N + env]; tgx = A[2 * N + env]; tgy = A[3 * N + env];
@@ -490,6 +691,19 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     }
     // ---------------- EPMC push randomiser (PR:56-87): counters in sub-steps, force lasts one sub-step
     bool push_on = false;
+    if (ENV == 2 && P.push_enabled) {
+      // two robots (PR:79-87): inside the window each robot gets a freshly randomised force every sub-step: robot 0 the current
+      // draw, robot 1 the next one, and one more draw is consumed
+      push_count += 1;
+      if (push_count > 0) {
+        if (push_count % P.push_interval == 0) { push_draws += 1; push_count = 0; }
+        if (push_count < P.push_duration) {
+          push_force_of_draw(P, seed, pair_gid, epi, push_draws - 1 + robot, pf);
+          push_draws += 2;
+          push_on = true;
+        }
+      }
+    }
     if (ENV == 1 && P.push_enabled) {
       push_count += 1;
       if (push_count > 0) {
@@ -533,7 +747,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     {
       ABI I1 = rigid_abi(L.j[0].m, ld3(L.j[0].h), ldsym(L.j[0].I));
       SV p1 = bias_force<2>(L.j[0].m, ld3(L.j[0].h), ldsym(L.j[0].I), L.j[0].nd, L.j[0].d, v1.a, v1.l, P.kl, P.ka);
-      if (ENV == 1 && push_on && k == 0) {
+      if (ENV != 0 && push_on && k == 0) {
         // applyExternalForce(link 0 = FR hip, LINK_FRAME): force given in the hip's inertial frame, applied at its CoM
         const V3 fl = V3{M.push_R[0] * pf[0] + M.push_R[1] * pf[1] + M.push_R[2] * pf[2], M.push_R[3] * pf[0] + M.push_R[4] * pf[1] + M.push_R[5] * pf[2],
                          M.push_R[6] * pf[0] + M.push_R[7] * pf[1] + M.push_R[8] * pf[2]};
@@ -645,8 +859,45 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
         ob_hit = hit;
       }
     }
+    // ---------------- SEPMC: getContactPoints() (CTG:426-456) = manifolds of the last sub-step, built on its pre-step poses
+    if (ENV == 2 && sub == P.substeps - 1) {
+      float* srow = &s_new[threadIdx.x >> 2][0];
+      const float* prow = &s_new[(threadIdx.x >> 2) ^ 1][0];
+      const V3 pw = V3{(float)px, (float)py, (float)pz};
+      const V3 wh = pw + mul(R, p2 + rot<0>(rot<1>(ld3(M.wheel_off[k]), kc2, ks2), kc1, ks1));
+      const V3 hp = pw + mul(R, p1), ft = pw + mul(R, fb);
+      const V3 c0 = pw + mul(R, ld3(M.corner[2 * k])), c1_ = pw + mul(R, ld3(M.corner[2 * k + 1]));
+      float* o = srow + 18 * k;
+      o[0] = ft.x; o[1] = ft.y; o[2] = ft.z; o[3] = wh.x; o[4] = wh.y; o[5] = wh.z; o[6] = hp.x; o[7] = hp.y; o[8] = hp.z;
+      o[9] = c0.x; o[10] = c0.y; o[11] = c0.z; o[12] = c1_.x; o[13] = c1_.y; o[14] = c1_.z;
+      if (k < 2) { const V3 hd = pw + mul(R, V3{M.handle[k][0], M.handle[k][1], M.handle[k][2]}); o[15] = hd.x; o[16] = hd.y; o[17] = hd.z; }
+      __syncwarp();
+      const float fx = (float)PS.flag_x, fy = (float)PS.flag_y;
+      // the robot's "body" links (legs + wheels, CTG:427) are represented by its hip and wheel spheres
+      bool tch = flag_dist(hp, fx, fy) - M.hip_r[k] < P.breaking || flag_dist(wh, fx, fy) - M.wheel_r[k] < P.breaking;
+      bool tg = false;
+#pragma unroll 1
+      for (int j = 0; j < 4; j++) {
+        const float* pj = prow + 18 * j;
+        const float rj[6] = {M.leg[j].foot_r, M.wheel_r[j], M.hip_r[j], 0.f, 0.f, M.handle[j & 1][3]};
+#pragma unroll
+        for (int t = 0; t < 6; t++) {
+          if (t == 5 && j >= 2) continue;
+          const V3 c = V3{pj[3 * t], pj[3 * t + 1], pj[3 * t + 2]};
+          tg = tg || norm3(hp - c) - M.hip_r[k] - rj[t] < P.breaking || norm3(wh - c) - M.wheel_r[k] - rj[t] < P.breaking;
+        }
+      }
+      int bits = (tch ? 1 : 0) | (tg ? 2 : 0);
+      bits |= __shfl_xor_sync(FULL, bits, 1);
+      bits |= __shfl_xor_sync(FULL, bits, 2);
+      const int other = __shfl_xor_sync(FULL, bits, 4);
+      touch_own = (bits & 1) != 0;
+      tag = ((robot == 0 ? bits : other) & 2) != 0;               // only robot 0's body counts (CTG:464)
+      __syncwarp();
+    }
     // ---------------- collision: foot sphere vs plane z = 0 on the pre-step pose
-    const V3 nb = V3{R.a20, R.a21, R.a22};               // world z in base coords
+    V3 nb = V3{R.a20, R.a21, R.a22};                     // world z in base coords
+    int plane = 0;                                       // SEPMC: 0 ground, 1..4 walls with normals -x, +x, -y, +y
     // The foot clearance feeds Bullet's speculative-contact target (-penetration/dt): a 1e-7 m rounding error becomes
     // 5e-5 m/s.  Evaluate just this scalar (height of the foot centre) in fp64 from the fp32 joint sines/cosines.
     float dist;
@@ -663,6 +914,17 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       t = dc1 * y - ds1 * z; z = ds1 * y + dc1 * z; y = t;             // Rx(q1)
       x += (double)r[0].x; y += (double)r[0].y; z += (double)r[0].z;
       dist = (float)(pz + nx * x + ny * y + nz * z - (double)L.foot_r);
+      if (ENV == 2) {
+        // the arena walls (BSG:863-902) as four more half-spaces; one contact per foot, the deepest
+        const double wx = px + (1.0 - 2.0 * (qy * qy + qz * qz)) * x + 2.0 * (qx * qy - qz * qw) * y + 2.0 * (qx * qz + qy * qw) * z;
+        const double wy = py + 2.0 * (qx * qy + qz * qw) * x + (1.0 - 2.0 * (qx * qx + qz * qz)) * y + 2.0 * (qy * qz - qx * qw) * z;
+        const double lim = (double)kWallIn - (double)L.foot_r;
+        const float d1 = (float)(lim - wx), d2 = (float)(lim + wx), d3 = (float)(lim - wy), d4 = (float)(lim + wy);
+        if (d1 < dist) { dist = d1; plane = 1; }
+        if (d2 < dist) { dist = d2; plane = 2; }
+        if (d3 < dist) { dist = d3; plane = 3; }
+        if (d4 < dist) { dist = d4; plane = 4; }
+      }
     }
     const bool contact = dist < P.breaking;
     if (!contact) warm = 0.f;
@@ -700,8 +962,16 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       const int g0 = tid & ~3;
       if (any_con_warp) {
         // directions (world): n = +z, t1 = -y, t2 = +x   (btPlaneSpace1 of the plane normal), in base coords
-        const V3 dirs[3] = {nb, neg(V3{R.a10, R.a11, R.a12}), V3{R.a00, R.a01, R.a02}};
-        const V3 Pc = fb - L.foot_r * nb;                 // contact point on the sphere surface
+        V3 dirs[3] = {nb, neg(V3{R.a10, R.a11, R.a12}), V3{R.a00, R.a01, R.a02}};
+        if (ENV == 2 && plane != 0) {                     // btPlaneSpace1 of the wall normals
+          const V3 r0 = V3{R.a00, R.a01, R.a02}, r1 = V3{R.a10, R.a11, R.a12};
+          dirs[2] = nb;                                   // t2 = +z for every wall
+          if (plane == 1) { dirs[0] = neg(r0); dirs[1] = neg(r1); }
+          else if (plane == 2) { dirs[0] = r0; dirs[1] = r1; }
+          else if (plane == 3) { dirs[0] = neg(r1); dirs[1] = r0; }
+          else { dirs[0] = r1; dirs[1] = neg(r0); }
+        }
+        const V3 Pc = fb - L.foot_r * dirs[0];            // contact point on the sphere surface
 #pragma unroll
         for (int d = 0; d < 3; d++) {
           const V3 db = dirs[d];
@@ -862,7 +1132,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           }
         }
       }
-      const float mu = ENV == 1 ? mu_env : P.mu;
+      const float mu = ENV != 0 ? mu_env : P.mu;
 #pragma unroll 1
       for (int it = 0; it < P.solver_iters; it++) {
         if (any_lim_warp) {
@@ -1093,6 +1363,64 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       }
     }
   }
+  } else if (ENV == 2) {
+    // ---------------- SEPMC tail (CTG:378-424, 458-470, 495-596, 640-652)
+    qb = qmul(qp, qI);
+    float* snew = &s_new[threadIdx.x >> 2][0];
+    const float* spart = &s_new[(threadIdx.x >> 2) ^ 1][0];
+    sepmc_pair_tail(M, L, k, robot, snew, spart, px, py, pz, qp, qb, vw, ww, q, touch_own, fix_spd, seed, pair_gid, epi, PS);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { snew[3 * k + i] = q[i]; snew[12 + 3 * k + i] = qd[i]; snew[kPropDim + 3 * k + i] = act[i]; }
+    const float spd = sqrtf(vw.x * vw.x + vw.y * vw.y);              // stat_spd (CTG:368-373)
+    total_spd += (double)spd;
+    if ((double)spd > max_spd) max_spd = (double)spd;
+    counter += 1;
+    const M3 Rq = qmat(qnormalize(qb));
+    const float left_z = Rq.a02 * Rq.a10 - Rq.a12 * Rq.a00;
+    int fall = (left_z > 0.70710678118654752f || left_z < -0.70710678118654752f || Rq.a22 < 0.5f) ? 1 : 0;
+    const int fall_other = __shfl_xor_sync(FULL, fall, 4);
+    if (robot == 1) fall = fall_other;                                  // only robot 0's fall ends the episode (CTG:462)
+    {
+      int bi = bad ? 1 : 0;
+      bi |= __shfl_xor_sync(FULL, bi, 1);
+      bi |= __shfl_xor_sync(FULL, bi, 2);
+      bi |= __shfl_xor_sync(FULL, bi, 4);
+      bad = bi != 0;
+    }
+    done = fall != 0 || counter >= P.max_steps || tag || bad;
+    // rewards (CTG:640-652, 412-419): +-1 on a flag switch, +-1 on a tag; with_flag after the switch
+    const int wf0 = robot == 0 ? PS.with_flag : 1 - PS.with_flag;       // does robot 0 hold the flag
+    float rew = (float)PS.sw * ((wf0 != 0) == (robot == 0) ? 1.f : -1.f);
+    if (done && tag) rew += (wf0 != 0) == (robot == 0) ? 1.f : -1.f;
+    if (bad) rew = 0.f;
+    V3 fd;
+    {
+      V3 f = mul(qmat(qp), foot_in_base(L, q[0], q[1], q[2]));
+      fd = V3{(float)px + f.x, (float)py + f.y, (float)pz + f.z};
+    }
+    if (valid) {
+      float* sw = E.st;
+#pragma unroll
+      for (int i = 0; i < 3; i++) { sw[(10 + 3 * k + i) * N + env] = q[i]; sw[(22 + 3 * k + i) * N + env] = qd[i]; }
+      E.warm[k * N + env] = warm;
+      E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
+      if (k == 0) {
+        E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
+        sw[env] = qb.x; sw[N + env] = qb.y; sw[2 * N + env] = qb.z; sw[3 * N + env] = qb.w;
+        sw[4 * N + env] = vw.x; sw[5 * N + env] = vw.y; sw[6 * N + env] = vw.z;
+        sw[7 * N + env] = ww.x; sw[8 * N + env] = ww.y; sw[9 * N + env] = ww.z;
+        E.time[env] = time;
+        E.reward_sum[env] += rew;
+        E.episode_steps[env] += 1;
+        E.reward[env] = rew;
+        E.done[env] = done ? 1 : 0;
+        double* A = E.aux;
+        A[env] = counter; A[N + env] = PS.with_flag; A[2 * N + env] = PS.flag_x; A[3 * N + env] = PS.flag_y; A[5 * N + env] = PS.visible;
+        A[6 * N + env] = PS.sw; A[7 * N + env] = total_spd; A[8 * N + env] = max_spd; A[9 * N + env] = push_count;
+        A[10 * N + env] = pf[0]; A[11 * N + env] = pf[1]; A[12 * N + env] = pf[2]; A[14 * N + env] = push_draws; A[15 * N + env] = PS.flag_draws;
+        A[17 * N + env] = touch_own ? 1.0 : 0.0;
+      }
+    }
   } else {
     // ---------------- EPMC tail (PGE:334-358, 360-372, 479-502)
     qb = qmul(qp, qI);
@@ -1249,12 +1577,71 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
   bool doit = valid;
   if (RP.mode == 3) doit = false;
   else if (RP.mode == 0) doit = doit && E.done[env] != 0;
-  else if (RP.mask) doit = doit && RP.mask[env] != 0;
+  else if (RP.mask) doit = doit && (RP.mask[env] != 0 || (ENV == 2 && RP.mask[env ^ 1] != 0));   // SEPMC: a pair resets as a whole
   const unsigned wm = __ballot_sync(FULL, doit);
   if (wm == 0) return;                                   // warp-uniform: nothing to reset in these 8 envs
   const LegConst& L = M.leg[k];
 
-  if (ENV == 1) {
+  if (ENV == 2) {
+    // ---------------- SEPMC reset (CTG:261-304, 204-230); draws keyed by the pair: stream 1 = [fix_spd, with_flag, friction, x0 |
+    // y0, x1, y1, yaw0 | yaw1, flag x, flag y]
+    const int robot = env & 1;
+    const long long ep = E.episode[env];
+    const long long gid = RP.gid0 + (env & ~1);
+    double u0[4], u1[4], u2[4];
+    stream_uniforms(RP.seed, gid, ep, 1, 0, u0);
+    stream_uniforms(RP.seed, gid, ep, 1, 1, u1);
+    stream_uniforms(RP.seed, gid, ep, 1, 2, u2);
+    const float fix_spd = (float)(0.5 + 2.5 * u0[0]);
+    const int wflag = (int)floor(2.0 * u0[1]);
+    const double foot_mu = (double)P.fr_lo + u0[2] * ((double)P.fr_hi - (double)P.fr_lo);
+    const double px = robot == 0 ? -2.0 + 4.0 * u0[3] : -2.0 + 4.0 * u1[1], py = robot == 0 ? -2.0 + 4.0 * u1[0] : -2.0 + 4.0 * u1[2];
+    // both robots are handed the same mutable init dict => one running yaw for the pair (CTG:209-215)
+    const double acc0 = E.aux[16 * N + (env & ~1)];
+    const double yaw_a = fmod(acc0 + 360.0 * u1[3], 360.0), yaw_b = fmod(yaw_a + 360.0 * u2[0], 360.0);
+    const double yaw_deg = robot == 0 ? yaw_a : yaw_b;
+    double sn, cs;
+    sincos(0.5 * yaw_deg * (3.14159265358979323846 / 180.0), &sn, &cs);
+    const float* I0 = M.init_state;
+    const Q4 qn = qmul(qnormalize(Q4{I0[3], I0[4], I0[5], I0[6]}), Q4{0.f, 0.f, (float)sn, (float)cs});
+    float q[3], qd[3];
+#pragma unroll
+    for (int i = 0; i < 3; i++) { q[i] = I0[13 + 3 * k + i]; qd[i] = I0[25 + 3 * k + i]; }
+    const V3 lin = V3{I0[7], I0[8], I0[9]}, ang = V3{I0[10], I0[11], I0[12]};
+    const Q4 qI = Q4{M.base.qI[0], M.base.qI[1], M.base.qI[2], M.base.qI[3]};
+    const Q4 qp = qmul(qnormalize(qn), qconj(qI));
+    PairState PS = {robot == 0 ? wflag : 1 - wflag, 0, 1, 0, -2.0 + 4.0 * u2[1], -2.0 + 4.0 * u2[2]};
+    // reset() runs _prepare_drill too (CTG:302): its flag-switch test reads the stale manifolds of the previous episode's last step
+    const bool touch_own = E.aux[17 * N + env] != 0.0;
+    float* snew = &s_new[threadIdx.x >> 2][0];
+    const float* spart = &s_new[(threadIdx.x >> 2) ^ 1][0];
+    sepmc_pair_tail(M, L, k, robot, snew, spart, px, py, 0.5, qp, qn, lin, ang, q, touch_own, fix_spd, RP.seed, gid, ep, PS);
+#pragma unroll
+    for (int i = 0; i < 3; i++) { snew[3 * k + i] = q[i]; snew[12 + 3 * k + i] = qd[i]; }
+    int push_draws = 0;
+    float pf[3] = {0.f, 0.f, 0.f};
+    if (P.push_enabled) push_draws = 1;                              // PR:52-54: draw #0 becomes the current _randomized_force
+    if (doit) {
+      float* sw = E.st;
+      V3 f = mul(qmat(qp), foot_in_base(L, q[0], q[1], q[2]));
+#pragma unroll
+      for (int i = 0; i < 3; i++) { sw[(10 + 3 * k + i) * N + env] = q[i]; sw[(22 + 3 * k + i) * N + env] = qd[i]; }
+      E.warm[k * N + env] = 0.f;
+      E.foot_pos[(3 * k) * N + env] = (float)px + f.x; E.foot_pos[(3 * k + 1) * N + env] = (float)py + f.y; E.foot_pos[(3 * k + 2) * N + env] = 0.5f + f.z;
+      if (k == 0) {
+        E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = 0.5;
+        float b[10] = {qn.x, qn.y, qn.z, qn.w, lin.x, lin.y, lin.z, ang.x, ang.y, ang.z};
+#pragma unroll
+        for (int i = 0; i < 10; i++) sw[i * N + env] = b[i];
+        E.time[env] = 0.0; E.reward_sum[env] = 0.f; E.episode_steps[env] = 0; E.episode[env] = ep + 1;
+        double* A = E.aux;
+        A[env] = 0; A[N + env] = PS.with_flag; A[2 * N + env] = PS.flag_x; A[3 * N + env] = PS.flag_y; A[4 * N + env] = fix_spd;
+        A[5 * N + env] = PS.visible; A[6 * N + env] = PS.sw; A[7 * N + env] = 0.0; A[8 * N + env] = 0.0; A[9 * N + env] = P.push_start_count;
+        A[10 * N + env] = pf[0]; A[11 * N + env] = pf[1]; A[12 * N + env] = pf[2]; A[13 * N + env] = foot_mu; A[14 * N + env] = push_draws;
+        A[15 * N + env] = PS.flag_draws; A[16 * N + env] = yaw_b; A[17 * N + env] = touch_own ? 1.0 : 0.0;
+      }
+    }
+  } else if (ENV == 1) {
     // ---------------- EPMC reset (PGE:196-249)
     long long ep = E.episode[env];
     const long long gid = RP.gid0 + env;

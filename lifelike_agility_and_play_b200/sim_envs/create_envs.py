@@ -68,16 +68,6 @@ def create_tracking_env(**env_config):
     return env
 
 
-def _not_built(name, row):
-    def _f(**env_config):
-        raise NotImplementedError("%s: SURVEY.md 8 row %s is a 'next' row of the hot-path scope and is not built yet"
-                                  % (name, row))
-    _f.__name__ = name
-    return _f
-
-
-# SEPMC factories exist under their reference names so that a mis-pointed --outer_env fails with a clear
-# message instead of an AttributeError (CPE:67-140,150-161).
 def create_playground_game(**env_config):
     """CPE:67-101 -- element_id 0 (flat joystick arena, the shipped script default) runs on the CUDA engine."""
     arena_id = env_config["arena_id"]
@@ -107,5 +97,31 @@ def create_playground_env(**env_config):
     return env
 
 
-create_chase_tag_game = _not_built("create_chase_tag_game", "a23-a26 (SEPMC)")
-create_chase_tag_env = _not_built("create_chase_tag_env", "a23-a26 (SEPMC)")
+def create_chase_tag_game(**env_config):
+    """CPE:104-140 -- the shipped empty arena runs on the CUDA engine (two robots = one pair)."""
+    arena_id = env_config["arena_id"]
+    assert arena_id in [
+        "CTG",
+    ]
+    from .chase_tag_game_env import ChaseTagGameEnv
+    env0 = ChaseTagGameEnv(
+        enable_render=env_config["render"] if "render" in env_config else False,
+        control_freq=env_config["control_freq"] if "control_freq" in env_config else 25.0,
+        kp=env_config["kp"] if "kp" in env_config else 50.0,
+        kd=env_config["kd"] if "kd" in env_config else 1.0,
+        max_tau=env_config["max_tau"] if "max_tau" in env_config else 18.0,
+        prop_type=env_config["prop_type"] if "prop_type" in env_config else None,
+        max_steps=env_config["max_steps"] if "max_steps" in env_config else 1000,
+        obs_randomization=env_config["obs_randomization"] if "obs_randomization" in env_config else None,
+        element_config=env_config.get('element_config', {}),
+        env_randomize_config=env_config.get('env_randomize_config', {}),
+        seed=env_config.get("seed", 0), device=env_config.get("device", 0),
+    )
+    return env0
+
+
+def create_chase_tag_env(**env_config):
+    env = create_chase_tag_game(**env_config)
+    env.observation_space = env.observation_space.spaces[0]
+    env.action_space = env.action_space.spaces[0]
+    return env

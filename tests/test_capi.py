@@ -117,8 +117,8 @@ def test_gym_surface_on_oracle(monkeypatch, oracle_lib, small_mocap):
         create_envs.create_tracking_game(**dict(_tracking_cfg(small_mocap), arena_id="nope"))          # CPE:22-25
     with pytest.raises(TypeError):
         create_envs.create_tracking_game(**dict(_tracking_cfg(small_mocap), prop_type=""))             # PLE:112-113
-    with pytest.raises(NotImplementedError):
-        create_envs.create_chase_tag_game(arena_id="CTG")
+    with pytest.raises(TypeError):
+        create_envs.create_chase_tag_game(arena_id="CTG")                                               # CTG:98-99: prop_type must be a list
 
 
 EPMC_ENV_CONFIG = {
@@ -164,6 +164,66 @@ def test_epmc_gym_surface_on_oracle(monkeypatch, oracle_lib):
     bad = dict(EPMC_ENV_CONFIG, env_randomize_config=dict(EPMC_ENV_CONFIG['env_randomize_config'], element_id=1))
     with pytest.raises(NotImplementedError):
         create_envs.create_playground_game(**bad)
+
+
+SEPMC_ENV_CONFIG = {          # train_scripts/example_sepmc_train.sh:94-117 with a short episode
+    'arena_id': 'CTG', 'render': False, 'control_freq': 50.0,
+    'prop_type': ['joint_pos', 'joint_vel', 'root_ang_vel_loc', 'root_lin_vel_loc', 'e_g'],
+    'kp': 50.0, 'kd': 0.5, 'max_tau': 16, 'max_steps': 25, 'obs_randomization': {},
+    'env_randomize_config': {'friction_range': [0.4, 3.0],
+                             'disturb_force_config': {'start_time': 0.5, 'interval_time': 1.0, 'duration_time': 0.2,
+                                                      'horizontal_force': [0, 50], 'vertical_force': [0, 10]}},
+    'element_config': {'rand_cube': False, 'hurdle': False, 'hole': False},
+}
+
+
+def _drive_sepmc(env):
+    """The loop of test_scripts/strategic_level/test_strategic_level_env.py, head-less, random policies for both agents."""
+    obs = env.reset()
+    keys = ['prop', 'prop_a', 'percept_2d', 'percept_1d', 'percept_front', 'percept_vec', 'oppo_info', 'oppo_info_cheat', 'flag_info',
+            'flag_info_cheat', 'with_flag', 'control_spd']
+    assert len(obs) == 2 and all(list(o.keys()) == keys for o in obs)
+    assert [obs[0][k].shape for k in keys] == [(99,), (36,), (25, 13), (128,), (25, 13), (5,), (15,), (15,), (7,), (7,), (2,), (1,)]
+    assert obs[0]['with_flag'][0] + obs[1]['with_flag'][0] == 1 and obs[0]['with_flag'][0] == obs[1]['with_flag'][1]
+    assert 0.5 <= obs[0]['control_spd'][0] <= 3.0 and obs[0]['control_spd'][0] == obs[1]['control_spd'][0]
+    assert np.allclose(obs[0]['oppo_info_cheat'][1:4], obs[1]['percept_vec'][:3])              # the opponent's position
+    assert 0.0 < obs[0]['percept_1d'].min() and obs[0]['percept_1d'].max() < 7.2                # every horizontal ray ends on a wall / the flag
+    rng = np.random.default_rng(0)
+    dones = 0
+    for t in range(60):
+        acts = [{'A_HLC': np.zeros(1), 'A_Z': 0, 'A_LLC': (0.1 * rng.standard_normal(12)).astype(np.float32)} for _ in range(2)]
+        obs, rwd, done, info = env.step(acts)
+        assert isinstance(done, bool) and len(rwd) == 2 and rwd[0] == -rwd[1] and rwd[0] in (-2.0, -1.0, 0.0, 1.0, 2.0)
+        assert set(info) == {'avg_spd0', 'avg_spd1', 'max_spd0', 'max_spd1'}
+        if done:
+            dones += 1
+            obs = env.reset()
+    assert dones >= 2          # max_steps = 25
+    assert len(env.with_flag) == 2 and len(env.target_pos) == 3
+
+
+def test_sepmc_gym_surface_on_oracle(monkeypatch, oracle_lib):
+    from lifelike_agility_and_play_b200.sim_envs import create_envs, chase_tag_game_env as ctg
+    monkeypatch.setattr(ctg, "engine_factory", lambda n, blob, **cfg: capi.VecEngine(oracle_lib, n, blob, None, **{k: v for k, v in cfg.items() if k != "device"}))
+    env = create_envs.create_chase_tag_game(**SEPMC_ENV_CONFIG)
+    assert len(env.observation_space.spaces) == 2 and list(env.action_space.spaces[0].spaces.keys()) == ['A_HLC', 'A_Z', 'A_LLC']
+    _drive_sepmc(env)
+    env.close()
+    cfg = ctg.sepmc_engine_config(50.0, 50.0, 0.5, 16, 1000, SEPMC_ENV_CONFIG['env_randomize_config'])
+    assert (cfg['push_start_count'], cfg['push_interval_steps'], cfg['push_duration_steps'], cfg['substeps']) == (-250, 499, 100, 10)
+    with pytest.raises(NotImplementedError):
+        create_envs.create_chase_tag_game(**dict(SEPMC_ENV_CONFIG, element_config={'rand_cube': True}))
+    env2 = create_envs.create_chase_tag_env(**SEPMC_ENV_CONFIG)                                   # CPE:157-161
+    assert list(env2.observation_space.spaces.keys())[0] == 'prop' and env2.action_space.spaces['A_LLC'].shape == (12,)
+    env2.close()
+
+
+@pytest.mark.gpu
+def test_sepmc_gym_surface_on_cuda():
+    from lifelike_agility_and_play_b200.sim_envs import create_envs
+    env = create_envs.create_chase_tag_game(**SEPMC_ENV_CONFIG)
+    _drive_sepmc(env)
+    env.close()
 
 
 @pytest.mark.gpu
