@@ -644,7 +644,7 @@ int llq_set_field(llq_handle h, int field, const void* src) {
       const double* a = (const double*)src;
       std::vector<double> tmp((size_t)LLQ_AUX_DIM * n);
       for (size_t i = 0; i < n; i++) {
-        if (!(a[i * LLQ_AUX_DIM + 1] >= 1)) return fail(LLQ_EINVAL, "cmd_vary_freq must be positive");
+        if (h->cfg.env_kind == LLQ_ENV_EPMC && !(a[i * LLQ_AUX_DIM + 1] >= 1)) return fail(LLQ_EINVAL, "cmd_vary_freq must be positive");
         for (int t = 0; t < LLQ_AUX_DIM; t++) tmp[(size_t)t * n + i] = a[i * LLQ_AUX_DIM + t];
       }
       CK(cudaMemcpy(h->E.aux, tmp.data(), sizeof(double) * LLQ_AUX_DIM * n, cudaMemcpyHostToDevice));
