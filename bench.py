@@ -27,13 +27,17 @@ MU_A = np.array([.0124, -.011, -.0793, -.0125, -.0108, -.0806, .0402, -.0505, -.
 SIGMA_A = np.array([.0853, .1525, .1747, .0847, .1503, .1766, .1025, .2023, .3701, .1021, .2035, .426], np.float32)
 TRAJ_WIDTH = 223                        # obs 207 | action 12 | reward | done | neglogp | value  
 UNROLL = 128                            # example_pmc_train.sh:145
-METRIC = {"pmc": "env-steps/sec PMC mocap-tracking", "epmc": "env-steps/sec EPMC playground (element 0, flat joystick arena)"}
+METRIC = {"pmc": "env-steps/sec PMC mocap-tracking", "epmc": "env-steps/sec EPMC playground (element 0, flat joystick arena)",
+          "sepmc": "env-steps/sec SEPMC chase-tag game (one env = one pair of robots, shipped empty arena)"}
 WORKLOAD = {"pmc": "4096-env batched PMC mocap-tracking, flat ground, per GPU (BASELINE configs[1])",
             "epmc": "8192-env batched EPMC playground, element_id 0 = flat joystick arena of example_epmc_train.sh (BASELINE configs[2] "
-                    "asks for box/heightfield terrain, which is not built yet), per GPU"}
+                    "asks for box/heightfield terrain, which is not built yet), per GPU",
+            "sepmc": "2-agent SEPMC chase-tag game, 4096 env-pairs (8192 robots) per GPU, arena of example_sepmc_train.sh (BASELINE configs[4])"}
 # algorithmic bytes per env-step: PMC 157 words read + 262 written; EPMC without a terrain box list: 177 read + 991 written
-ALGO_BYTES = {"pmc": 1676, "epmc": 4672}
-OBS_W = {"pmc": 207, "epmc": 916}
+# SEPMC per pair-step: 2 robots x (182 words read + 1052 written: state, history, aux, the 965-wide observation)
+ALGO_BYTES = {"pmc": 1676, "epmc": 4672, "sepmc": 9872}
+OBS_W = {"pmc": 207, "epmc": 916, "sepmc": 965}
+ROBOTS_PER_ENV = {"pmc": 1, "epmc": 1, "sepmc": 2}
 
 
 def parse():
@@ -46,10 +50,11 @@ def parse():
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL trajectory gather to rank 0")
     ap.add_argument("--block", type=int, default=0, help="CUDA block size override (32/64/128)")
     ap.add_argument("--cpu-envs", type=int, default=256, help="CPU arm: environments per step (bounded sample)")
-    ap.add_argument("--env", default="pmc", choices=["pmc", "epmc"],
-                    help="pmc = BASELINE configs[1] (headline); epmc = configs[2] on the flat element-0 arena (8192 envs)")
+    ap.add_argument("--env", default="pmc", choices=["pmc", "epmc", "sepmc"],
+                    help="pmc = BASELINE configs[1] (headline); epmc = configs[2] on the flat element-0 arena (8192 envs); "
+                         "sepmc = configs[4] (4096 pairs; --envs counts robots)")
     a = ap.parse_args()
-    if a.env == "epmc" and a.envs == 4096:
+    if a.env in ("epmc", "sepmc") and a.envs == 4096:
         a.envs = 8192
     return a
 
@@ -120,6 +125,16 @@ def make_engine(lib_or_none, n, env, **over):
         eng = capi.VecEngine(lib, n, blob, None, **cfg)
         eng.set_init_state(INIT_STATE_RUN_0)
         return eng
+    if env == "sepmc":
+        from lifelike_agility_and_play_b200.sim_envs.chase_tag_game_env import sepmc_engine_config
+        from lifelike_agility_and_play_b200.sim_envs.playground_env import INIT_STATE_RUN_0
+        erc = {'friction_range': [0.4, 3.0],
+               'disturb_force_config': {'start_time': 0.5, 'interval_time': 1.0, 'duration_time': 0.2, 'horizontal_force': [0, 50], 'vertical_force': [0, 10]}}
+        cfg = sepmc_engine_config(50.0, 50.0, 0.5, 16, 1000, erc)      # train_scripts/example_sepmc_train.sh:94-117
+        cfg.update(over)
+        eng = capi.VecEngine(lib, n, blob, None, **cfg)
+        eng.set_init_state(INIT_STATE_RUN_0)
+        return eng
     return capi.VecEngine(lib, n, blob, mocap, **over)
 
 
@@ -137,7 +152,7 @@ def time_cpu_arm(n_envs, steps, warmup, threads=0, env="pmc"):
         eng.step(pool[i % 8])
     dt = time.perf_counter() - t0
     cores = threads if threads > 0 else (os.cpu_count() or 1)
-    return n_envs * steps / dt, dt, cores
+    return (n_envs // ROBOTS_PER_ENV[env]) * steps / dt, dt, cores
 
 
 def run_reference(args, rank):
@@ -174,7 +189,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    n = args.envs
+    n = args.envs                           # robots
+    nu = n // ROBOTS_PER_ENV[args.env]      # env-steps per engine step (SEPMC: pairs)
     ow = OBS_W[args.env]
     traj_w = ow + 16                        # obs | action 12 | reward | done | neglogp | value
     eng = make_engine(None, n, args.env, device=local_rank, seed=1234, auto_reset=1, global_env_offset=rank * n)
@@ -274,7 +290,7 @@ def main():
         dist.all_reduce(tot, op=dist.ReduceOp.MAX)
     step_ms, gather_ms, hot_ms, kern_ms = [float(x) for x in tot.tolist()]
     total_ms = step_ms + gather_ms
-    total_env_steps = n * world * args.steps
+    total_env_steps = nu * world * args.steps
     value = total_env_steps / (total_ms * 1e-3)
 
     # end-to-end through the public host API (numpy in, numpy out; H2D + D2H inside the timed region)
@@ -300,11 +316,11 @@ def main():
     t1 = time.perf_counter()
     for i in range(32):
         eng.step(host_pool[i % 4], out=out)
-    e2e_pageable = n * 32 / (time.perf_counter() - t1)
+    e2e_pageable = nu * 32 / (time.perf_counter() - t1)
     e2e_t = torch.tensor([e2e_s], device=dev, dtype=torch.float64)
     if world > 1:
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
-    e2e_val = n * world * e2e_steps / float(e2e_t.item())
+    e2e_val = nu * world * e2e_steps / float(e2e_t.item())
 
     if rank != 0:
         if world > 1:
@@ -318,7 +334,7 @@ def main():
         pass
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if "hbm_gbs" in peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
-    achieved = ALGO_BYTES[args.env] * n / (kern_ms * 1e-3) / 1e9
+    achieved = ALGO_BYTES[args.env] * nu / (kern_ms * 1e-3) / 1e9
     traffic = None
     try:
         traffic = json.load(open(os.path.join(ROOT, "profiles", "traffic.json"))).get("pmc_step_kernel_dram_bytes_per_launch")
@@ -329,21 +345,21 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD[args.env] + ("; sharded as in configs[3]" if world > 1 else ""),
-                   "envs_per_gpu": n, "global_envs": n * world, "substeps": 10, "solver_iters": 10,
+                   "envs_per_gpu": nu, "global_envs": nu * world, "robots_per_gpu": n, "substeps": 10, "solver_iters": 10,
                    "mocap": "66 synthetic clips, 229k frames" if args.env == "pmc" else None,
                    "auto_reset": True, "prioritized_sample_factor": 3.0 if args.env == "pmc" else None,
                    "actions": "N(mu_a, sigma_a) clipped +-1, device resident",
                    "l2": "flushed (256 MiB write) between timed steps; per-step CUDA events summed",
                    "parallelism": "env shards x%d%s" % (world, ", NCCL gather of [128,N,obs+16] slabs to rank 0 every 128 steps" if do_gather else "")},
-        "value_hot_l2": n * world * args.steps / (hot_ms * 1e-3),
-        "value_no_gather": n * world * args.steps / (step_ms * 1e-3),
+        "value_hot_l2": nu * world * args.steps / (hot_ms * 1e-3),
+        "value_no_gather": nu * world * args.steps / (step_ms * 1e-3),
         "gather_ms_total": gather_ms, "wall_s_timed_region": wall,
         "e2e": {"value": e2e_val, "unit": "env-steps/s", "h2d_bytes_per_step": n * 12 * 4, "d2h_bytes_per_step": n * (ow * 4 + 4 + 1),
                 "steps": e2e_steps, "api": "VecEngine.step_pinned(numpy over page-locked memory) -> llq_step_ex(LLQ_IO_PINNED)",
                 "value_pageable_numpy_api": e2e_pageable * world},
         "gpu_launches": int(c1[4] - c0[4]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "pmc_step_kernel<128,%d>" % (1 if args.env == "epmc" else 0), "kernel_ms": kern_ms,
+                     "kernel": "pmc_step_kernel<128,%d>" % {"pmc": 0, "epmc": 1, "sepmc": 2}[args.env], "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_env_step": ALGO_BYTES[args.env],
                      "peak_source": peak_src,
                      "note": "latency/issue bound by design (SURVEY 7): ~2e5 flop per 1.7 kB; see profiles/"},

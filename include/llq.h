@@ -50,7 +50,8 @@ extern "C" {
                                 2p+1 form env-pair p; actions / obs / reward / done are per robot (done is the pair's, on both rows).
                                 LLQ_F_AUX rows for SEPMC: counter, with_flag, flag_x, flag_y, control_spd, oppo_visible, switch_flag,
                                 total_spd, max_spd, push_count, push_fx..z (last applied), foot_friction, push_draws (pair), flag_draws,
-                                yaw_accum_deg, reserved */
+                                yaw_accum_deg (pair), flag_touch (this robot's body touched the flag in the last sub-step: the stale manifold
+                                reset() sees, CTG:302,573) */
 #define LLQ_AUX_DIM  18      /* LLQ_F_AUX: counter, cmd_vary_freq, target_x, target_y, target_spd, target_angle, last_pos_diff_len,
                                 total_spd, max_spd, push_count, push_fx, push_fy, push_fz, foot_friction, push_draws, cmd_draws,
                                 yaw_accum_deg (the reference mutates its module-level init-state dict, so reset yaws accumulate: PGE:181-189), reserved */
