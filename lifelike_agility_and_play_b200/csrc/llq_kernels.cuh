@@ -1127,8 +1127,8 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
 #pragma unroll
         for (int j = 0; j < 4; j++) {
           if ((warpmask >> (6 * j)) & 1u) {
-            const float l0 = __shfl_sync(FULL, lam[0], j, 4);
-            if ((envmask >> (6 * j)) & 1u) LLQ_APPLY_C(j, 0, l0)
+            const float l0 = __shfl_sync(FULL, lam[0], j, 4);      // 0 for feet without contact
+            LLQ_APPLY_C(j, 0, l0)
           }
         }
       }
@@ -1165,42 +1165,39 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           }
         }
         if (any_con_warp) {
+          // branch-free row updates: only lane j of an env owns foot j's rows, everybody else contributes dl = 0 (the A
+          // columns of feet without contact are finite, so applying a zero impulse is exact)
 #pragma unroll
           for (int j = 0; j < 4; j++) {   // normal rows, feet in order FR FL HR HL
             if ((warpmask >> (6 * j)) & 1u) {
-              float dl = 0.f;
-              if (j == k && contact) {
-                dl = rhs[0] - bq[0] * invd[0];
-                const float sum = lam[0] + dl;
-                if (sum < 0.f) { dl = -lam[0]; lam[0] = 0.f; }
-                else if (sum > 1e10f) { dl = 1e10f - lam[0]; lam[0] = 1e10f; }
-                else lam[0] = sum;
-              }
+              const bool mine = (j == k) && contact;
+              const float dlc = rhs[0] - bq[0] * invd[0];
+              const float sum = lam[0] + dlc;
+              const bool lo = sum < 0.f, hi = sum > 1e10f;
+              float dl = lo ? -lam[0] : (hi ? 1e10f - lam[0] : dlc);
+              const float ln = lo ? 0.f : (hi ? 1e10f : sum);
+              dl = mine ? dl : 0.f;
+              lam[0] = mine ? ln : lam[0];
               dl = __shfl_sync(FULL, dl, j, 4);
-              if ((envmask >> (6 * j)) & 1u) LLQ_APPLY_C(j, 0, dl)
+              LLQ_APPLY_C(j, 0, dl)
             }
           }
 #pragma unroll
           for (int j = 0; j < 4; j++) {   // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
             if ((warpmask >> (6 * j)) & 1u) {
-              float da = 0.f, db = 0.f;
-              if (j == k && contact) {
-                float sa = lam[1] + (rhs[1] - bq[1] * invd[1]), sb = lam[2] + (rhs[2] - bq[2] * invd[2]);
-                const float limit = mu * lam[0];
-                const float r2 = sa * sa + sb * sb;
-                if (r2 >= limit * limit && r2 > 0.f) {
-                  const float sc = limit * rsqrtf(r2);
-                  sa *= sc; sb *= sc;
-                }
-                da = sa - lam[1]; db = sb - lam[2];
-                lam[1] = sa; lam[2] = sb;
-              }
+              const bool mine = (j == k) && contact;
+              float sa = lam[1] + (rhs[1] - bq[1] * invd[1]), sb = lam[2] + (rhs[2] - bq[2] * invd[2]);
+              const float limit = mu * lam[0];
+              const float r2 = sa * sa + sb * sb;
+              const bool clip = r2 >= limit * limit && r2 > 0.f;
+              const float sc = clip ? limit * rsqrtf(r2) : 1.0f;
+              sa = clip ? sa * sc : sa; sb = clip ? sb * sc : sb;
+              float da = mine ? sa - lam[1] : 0.f, db = mine ? sb - lam[2] : 0.f;
+              lam[1] = mine ? sa : lam[1]; lam[2] = mine ? sb : lam[2];
               da = __shfl_sync(FULL, da, j, 4);
               db = __shfl_sync(FULL, db, j, 4);
-              if ((envmask >> (6 * j)) & 1u) {
-                LLQ_APPLY_C(j, 1, da)
-                LLQ_APPLY_C(j, 2, db)
-              }
+              LLQ_APPLY_C(j, 1, da)
+              LLQ_APPLY_C(j, 2, db)
             }
           }
         }
