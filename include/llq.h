@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LLQ_ABI_VERSION 1
+#define LLQ_ABI_VERSION 2
 
 /* per-env sizes (PMC env, reference PLE:102-124 with the shipped prop_type) */
 #define LLQ_STATE_DIM   37   /* base_pos3 base_orn4(xyzw) base_lin_vel3 base_ang_vel3 joint_pos12 joint_vel12 (LR:86-106) */
@@ -54,7 +54,8 @@ extern "C" {
                                 reset() sees, CTG:302,573) */
 #define LLQ_AUX_DIM  18      /* LLQ_F_AUX: counter, cmd_vary_freq, target_x, target_y, target_spd, target_angle, last_pos_diff_len,
                                 total_spd, max_spd, push_count, push_fx, push_fy, push_fz, foot_friction, push_draws, cmd_draws,
-                                yaw_accum_deg (the reference mutates its module-level init-state dict, so reset yaws accumulate: PGE:181-189), reserved */
+                                yaw_accum_deg (the reference mutates its module-level init-state dict, so reset yaws accumulate: PGE:181-189),
+                                init_pos_diff_len (elements 1-3, PGE:192-195) */
 #define LLQ_NUM_FEET    4
 
 /* error codes */
@@ -86,6 +87,9 @@ extern "C" {
 #define LLQ_F_FOOT_POS    11 /* float   [N,12]  world positions of the 4 foot links after the last step (LR:199-205) -- get only */
 #define LLQ_F_AUX         13 /* double  [N,18]  EPMC bookkeeping (LLQ_AUX_DIM): counters, joystick target, push randomiser, friction */
 #define LLQ_F_OB_ID       14 /* int32   [N]     PMC hurdle: index of the active plate within the clip's plate list (PLE:179,264-265) */
+#define LLQ_MAX_BOXES     36 /* static boxes of one EPMC corridor: 2 walls + up to 32 cubes / 18 hurdles / 18 bars (BSE:205-243) */
+#define LLQ_F_BOXES       15 /* float   [N,36,6] centre xyz, half extents xyz of the env's static boxes (walls first) -- get only */
+#define LLQ_F_NBOX        16 /* int32   [N]      number of valid boxes */
 #define LLQ_F_DECISION_MARGIN 12 /* float [N]   CPU oracle only, get only: smallest distance to a discontinuous branch taken during
                                    the last step: min(|q-limit|) over joints [rad], min(|dist-contact_breaking|) over feet [m].
                                    Parity tests use it to tell rounding noise from a flipped joint-limit / contact decision. */
@@ -98,7 +102,7 @@ typedef struct llq_config {
   int32_t solver_iters;       /* PGS iterations, numSolverIterations=10 (LR:261) */
   int32_t auto_reset;         /* 1: envs that finish are re-sampled inside llq_step (vector-env convention) */
   int32_t num_threads;        /* CPU oracle: OpenMP threads over envs (0 = all cores); ignored by CUDA */
-  int32_t reserved0;
+  int32_t element_id;         /* EPMC (PGE:199-206): 0 flat joystick arena, 1 hurdles, 2 'holes' (bars to pass under), 3 cubes (easy) */
   int64_t global_env_offset;  /* global id of env 0 (RNG streams are keyed by global id => result independent of sharding) */
   uint64_t seed;
   double sim_dt;              /* 1/sim_freq = 0.002 (PLE:49) */
@@ -129,6 +133,10 @@ typedef struct llq_config {
   double friction_lo, friction_hi;    /* per-episode foot lateral friction ~ U (PGE:209) */
   double push_h_lo, push_h_hi, push_v_lo, push_v_hi;   /* horizontal / vertical push force ranges (PR:89-99) */
   double target_spd_lo, target_spd_hi;                 /* target_spd_range (PGE:317) */
+  /* EPMC elements 1-3: corridor of max_game_elements/bullet_static_entities.py (BSE) */
+  double wall_width_lo, wall_width_hi;                 /* PGE:160: [0.02, 0.5]  (BSE:171) */
+  double wall_gap_lo, wall_gap_hi;                     /* PGE:161: [1.0, 20.0]  (BSE:174) */
+  double hole_gap_lo, hole_gap_hi;                     /* hole_config min/max_gap_height (BSE:372-373; shipped 0.25, 0.25) */
 } llq_config;
 
 typedef struct llq_engine* llq_handle;

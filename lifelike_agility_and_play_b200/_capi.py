@@ -16,7 +16,8 @@ STATE_DIM, ACTION_DIM, PROP_DIM, OBS_DIM, MOCAP_FRAME = 37, 12, 33, 207, 19
 
 LLQ_IO_HOST, LLQ_IO_DEVICE, LLQ_IO_PINNED = 0, 1, 2
 (F_STATE, F_CLIP, F_TIME, F_REWARD_SUM, F_EPISODE_STEPS, F_WARMSTART, F_OBS, F_KIN_STATE, F_SAMPLE_PROB,
- F_AVG_REWARD, F_EPISODE_ID, F_FOOT_POS, F_DECISION_MARGIN, F_AUX, F_OB_ID) = range(15)
+ F_AVG_REWARD, F_EPISODE_ID, F_FOOT_POS, F_DECISION_MARGIN, F_AUX, F_OB_ID, F_BOXES, F_NBOX) = range(17)
+MAX_BOXES = 36
 ENV_PMC, ENV_EPMC, ENV_SEPMC, OBS_DIM_EPMC, OBS_DIM_SEPMC, AUX_DIM = 0, 1, 2, 916, 965, 18
 
 # field id -> (dtype, per-env width or None for per-clip tables)
@@ -26,6 +27,7 @@ _FIELDS = {
     F_OBS: (np.float32, OBS_DIM), F_KIN_STATE: (np.float32, STATE_DIM), F_SAMPLE_PROB: (np.float64, None),
     F_AVG_REWARD: (np.float64, None), F_EPISODE_ID: (np.int64, 1), F_FOOT_POS: (np.float32, 12),
     F_DECISION_MARGIN: (np.float32, 1), F_AUX: (np.float64, AUX_DIM), F_OB_ID: (np.int32, 1),
+    F_BOXES: (np.float32, 36 * 6), F_NBOX: (np.int32, 1),
 }
 
 
@@ -33,7 +35,7 @@ class LlqConfig(C.Structure):
     """Mirror of ``struct llq_config`` (include/llq.h) -- field order and types must match."""
     _fields_ = [
         ("struct_size", C.c_int32), ("n_envs", C.c_int32), ("device", C.c_int32), ("substeps", C.c_int32),
-        ("solver_iters", C.c_int32), ("auto_reset", C.c_int32), ("num_threads", C.c_int32), ("reserved0", C.c_int32),
+        ("solver_iters", C.c_int32), ("auto_reset", C.c_int32), ("num_threads", C.c_int32), ("element_id", C.c_int32),
         ("global_env_offset", C.c_int64), ("seed", C.c_uint64),
         ("sim_dt", C.c_double), ("kp", C.c_double), ("kd", C.c_double), ("max_tau", C.c_double),
         ("gravity_z", C.c_double), ("ground_friction", C.c_double), ("foot_friction", C.c_double),
@@ -48,6 +50,8 @@ class LlqConfig(C.Structure):
         ("push_enabled", C.c_int32),
         ("friction_lo", C.c_double), ("friction_hi", C.c_double), ("push_h_lo", C.c_double), ("push_h_hi", C.c_double),
         ("push_v_lo", C.c_double), ("push_v_hi", C.c_double), ("target_spd_lo", C.c_double), ("target_spd_hi", C.c_double),
+        ("wall_width_lo", C.c_double), ("wall_width_hi", C.c_double), ("wall_gap_lo", C.c_double), ("wall_gap_hi", C.c_double),
+        ("hole_gap_lo", C.c_double), ("hole_gap_hi", C.c_double),
     ]
 
 

@@ -259,6 +259,8 @@ struct Env {
   int counter, cmd_freq; double tgt_x, tgt_y, target_spd, target_angle, last_pos_diff_len, total_spd, max_spd;
   int push_count, push_draws, cmd_draws; double push_f[3];
   int ob_id;      // active hurdle plate (PLE:179,264-265)
+  // EPMC elements 1-3: static boxes of the corridor (walls first), centre + half extents; PGE:192-195
+  int n_boxes; double boxes[LLQ_MAX_BOXES][6]; double init_pos_diff_len;
   // SEPMC (CTG): per-robot copies of the pair's game state
   int with_flag, switch_flag, visible, flag_draws, touch; double flag_x, flag_y, fix_spd;
   double yaw_accum_deg;   // PGE:181-189 mutates the shared init-state dict: every reset's yaw is applied on top of the previous ones
@@ -513,6 +515,29 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
     for (int pi = 0; pi < n_planes; pi++) {
       double dpi = dot(pn[pi], cw) - pd[pi] - sp.r;
       if (dpi < dist) { dist = dpi; nrm = pn[pi]; }
+    }
+    // EPMC corridor: sphere vs every static box (walls, hurdles, bars, cubes); still one contact per foot, the deepest.
+    // The auxiliary edge cylinders (BSE:43-100) and every non-foot link are not collided.
+    for (int b = 0; b < e.n_boxes; b++) {
+      const double* bx = e.boxes[b];
+      const double p[3] = {cw.x - bx[0], cw.y - bx[1], cw.z - bx[2]};
+      double c[3]; bool inside = true;
+      for (int a = 0; a < 3; a++) { c[a] = clampd(p[a], -bx[3 + a], bx[3 + a]); if (c[a] != p[a]) inside = false; }
+      double db; V3 nb;
+      if (!inside) {
+        const V3 v = {p[0] - c[0], p[1] - c[1], p[2] - c[2]};
+        const double len = norm(v);
+        db = len - sp.r; nb = (1.0 / len) * v;
+      } else {                                  // centre inside the box: leave through the nearest face
+        int ax = 0; double best = 1e30, sg = 1.0;
+        for (int a = 0; a < 3; a++) {
+          const double dp = bx[3 + a] - p[a], dm = bx[3 + a] + p[a];
+          if (dp < best) { best = dp; ax = a; sg = 1.0; }
+          if (dm < best) { best = dm; ax = a; sg = -1.0; }
+        }
+        db = -best - sp.r; nb = V3{ax == 0 ? sg : 0.0, ax == 1 ? sg : 0.0, ax == 2 ? sg : 0.0};
+      }
+      if (db < dist) { dist = db; nrm = nb; }
     }
     e.margin = std::min(e.margin, std::fabs(dist - cf.contact_breaking));
     if (dist < cf.contact_breaking) {
@@ -892,7 +917,112 @@ void epmc_randomize_push(llq_engine& E, Env& e, int64_t gid) {   // PR:89-99
 
 // PGE:374-447 on the flat 200 x 200 ground slab (top face z = 0) -- the only static body of element 0 besides the
 // degenerate target marker (BSE:106-131 gives its collision box zero extents).
-void epmc_drill(const llq_engine& /*E*/, const Env& e, const double* st, float* percep /* 325 + 128 + 325 + 3 */) {
+struct Box { V3 lo, hi; };
+double ray_boxes(const Box* bs, int nb, V3 a, V3 b);
+
+// EPMC corridor (elements 1-3), BSE = max_game_elements/bullet_static_entities.py: reset() -> _generate_random_width_walls
+// (BSE:170-210) then _create_hurdles / _create_holes / _create_cubes(easy=True) (BSE:212-263, 308-470).  Draws come from
+// Philox stream 5 in the order the reference consumes them.
+struct TerrainRng {
+  const llq_config& cf; int64_t gid, ep; int k = 0; double u[4] = {0, 0, 0, 0};
+  double next() {
+    if (k % 4 == 0) stream_uniforms(cf.seed, gid, ep, 5, (uint32_t)(k / 4), u);
+    return u[k++ % 4];
+  }
+  double uniform(double lo, double hi) { return lo + next() * (hi - lo); }
+  int randint(int lo, int hi) { return lo + (int)std::floor(next() * (hi - lo)); }
+};
+void add_box(Env& e, double cx, double cy, double cz, double lx, double ly, double lz) {
+  if (e.n_boxes >= LLQ_MAX_BOXES) return;
+  double* b = e.boxes[e.n_boxes++];
+  b[0] = cx; b[1] = cy; b[2] = cz; b[3] = lx / 2; b[4] = ly / 2; b[5] = lz / 2;
+}
+void epmc_generate_terrain(const llq_engine& E, Env& e, int64_t gid) {
+  const llq_config& cf = E.cfg;
+  TerrainRng R{cf, gid, e.episode - 1, 0, {0, 0, 0, 0}};
+  e.n_boxes = 0;
+  const double width = R.uniform(cf.wall_width_lo, cf.wall_width_hi), gap = R.uniform(cf.wall_gap_lo, cf.wall_gap_hi);   // BSE:171-174
+  add_box(e, 5.0, gap / 2.0 + width / 2.0, 1.0, 200.0, width, 2.0);                                // BSE:207-210
+  add_box(e, 5.0, -(gap / 2.0 + width / 2.0), 1.0, 200.0, width, 2.0);
+  double cur = 0.0;
+  if (cf.element_id == 1 || cf.element_id == 2) {                                                   // BSE:226-248
+    const int n = R.randint(1, 10);
+    for (int pass = 0; pass < 2; pass++) {
+      for (int i = 0; i < n; i++) {
+        if (cf.element_id == 1) {                                                                   // _generate_one_hurdle (BSE:308-363)
+          const double h = R.uniform(0.05, 0.15), d = R.uniform(1.0, 3.0);
+          add_box(e, cur + d / 2, 0.0, h / 2, 0.1, gap, h);
+          cur += d + 0.1;
+        } else {                                                                                    // _generate_one_hole (BSE:365-423)
+          const double d = R.uniform(1.0, 3.0), g = R.uniform(cf.hole_gap_lo, cf.hole_gap_hi);
+          add_box(e, cur + d / 2, 0.0, 0.3 / 2 + g, 0.1, gap, 0.3);
+          cur += d + 0.1;
+        }
+      }
+      if (pass == 0) { e.tgt_x = cur + R.uniform(-1.0, 1.0); e.tgt_y = 0.0; }
+    }
+  } else {                                                                                          // _create_cubes(easy=True) (BSE:212-224, 425-500)
+    const int ns = R.randint(1, 5);
+    for (int pass = 0; pass < 2; pass++) {
+      for (int i = 0; i < ns; i++) {
+        cur += R.uniform(0.0, 1.0);
+        add_box(e, 1.75 + cur, 0.0, 0.25 / 2, 0.5, gap, 0.25);
+        add_box(e, 1.0 + cur, 0.0, 0.1 / 2, 0.5, gap, 0.1);
+        cur += 1.75 + 0.25;
+        add_box(e, cur + 0.5, 0.0, 0.25 / 2, 0.5, gap, 0.25);
+        add_box(e, cur + 1.25, 0.0, 0.1 / 2, 0.5, gap, 0.1);
+        cur += 3.0;
+      }
+      if (pass == 0) { e.tgt_x = cur + R.uniform(-3.0, 3.0); e.tgt_y = 0.0; }
+    }
+  }
+}
+// perception against the ground slab + the corridor's boxes (PGE:374-447)
+void epmc_drill_terrain(const Env& e, const double* st, float* percep) {
+  Box bx[LLQ_MAX_BOXES + 1];
+  bx[0] = {{-100, -100, -10}, {100, 100, 0}};
+  for (int b = 0; b < e.n_boxes; b++) {
+    const double* q = e.boxes[b];
+    bx[1 + b] = {{q[0] - q[3], q[1] - q[4], q[2] - q[5]}, {q[0] + q[3], q[1] + q[4], q[2] + q[5]}};
+  }
+  const int nb = 1 + e.n_boxes;
+  M3 R = qmat(qnormalize({st[3], st[4], st[5], st[6]}));
+  V3 pos = {st[0], st[1], st[2]};
+  const double yaw = std::atan2(R.m[1][0], R.m[0][0]);
+  int k = 0;
+  for (int a = 0; a < 25; a++) {
+    const double gx = a == 24 ? 1.2 : -1.2 + a * (2.4 / 24.0);
+    for (int b = 0; b < 13; b++) {
+      const double gy = b == 12 ? 0.6 : -0.6 + b * (1.2 / 12.0);
+      V3 t = mul(R, V3{gx, gy, 0.0}) + pos;
+      const double f = ray_boxes(bx, nb, V3{t.x, t.y, 10.0}, V3{t.x, t.y, -10.0});
+      percep[k++] = f < 0 ? 0.0f : (float)(10.0 + f * (-20.0));
+    }
+  }
+  for (int r = 0; r < 128; r++) {
+    const double ang = yaw + 2.0 * M_PI * (double)r / 128.0;
+    V3 to = {pos.x + 20.0 * std::cos(ang), pos.y + 20.0 * std::sin(ang), pos.z};
+    const double f = ray_boxes(bx, nb, pos, to);
+    V3 hit = f < 0 ? V3{0, 0, 0} : pos + f * (to - pos);
+    percep[k++] = (float)norm(hit - pos);
+  }
+  for (int a = 0; a < 25; a++) {
+    const double y = a == 24 ? 0.25 : -0.25 + a * (0.5 / 24.0);
+    for (int b = 0; b < 13; b++) {
+      const double z = b == 12 ? 0.1 : -0.3 + b * (0.4 / 12.0);
+      V3 from = mul(R, V3{0.0, y, z}) + pos, to = mul(R, V3{3.0, y, z}) + pos;
+      const double f = ray_boxes(bx, nb, from, to);
+      V3 hit = f < 0 ? to : from + f * (to - from);
+      percep[k++] = (float)norm(hit - from);
+    }
+  }
+  V3 d = tmul(R, V3{e.tgt_x - pos.x, e.tgt_y - pos.y, 0.0 - pos.z});
+  const double n2 = std::sqrt(d.x * d.x + d.y * d.y);
+  percep[778] = (float)(d.x / n2); percep[779] = (float)(d.y / n2); percep[780] = (float)e.target_spd;
+}
+
+void epmc_drill(const llq_engine& E, const Env& e, const double* st, float* percep /* 325 + 128 + 325 + 3 */) {
+  if (E.cfg.element_id != 0) { epmc_drill_terrain(e, st, percep); return; }
   Q4 qb = qnormalize({st[3], st[4], st[5], st[6]});
   M3 R = qmat(qb);
   V3 pos = {st[0], st[1], st[2]};
@@ -957,8 +1087,10 @@ void epmc_reset(llq_engine& E, Env& e, int64_t gid) {   // PGE:196-249
   st[0] = 0.0; st[1] = 0.0; st[2] = 0.5;
   unpack_state(e, st);
   for (int s = 0; s < 8; s++) e.warm[s] = 0;
-  e.tgt_x = 8.0; e.tgt_y = 0.0;                                                          // BSE:247-248, PGE:219
+  e.tgt_x = 8.0; e.tgt_y = 0.0; e.n_boxes = 0;                                           // BSE:247-248, PGE:219
+  if (cf.element_id != 0) epmc_generate_terrain(E, e, gid);                               // PGE:216-219
   e.last_pos_diff_len = std::sqrt((st[0] - e.tgt_x) * (st[0] - e.tgt_x) + (st[1] - e.tgt_y) * (st[1] - e.tgt_y));
+  e.init_pos_diff_len = e.last_pos_diff_len;                                              // PGE:192-195
   double prop[LLQ_PROP_DIM];
   make_prop(st, prop);
   for (int h = 0; h < 3; h++) {
@@ -973,15 +1105,18 @@ double epmc_step(llq_engine& E, Env& e, int64_t gid, const float* action, bool* 
   const llq_config& cf = E.cfg;
   e.episode_steps += 1;
   e.margin = 1e30;
-  if (e.counter % e.cmd_freq == 0) {                                                     // PGE:302-317 (element_id == 0)
+  if (e.counter % e.cmd_freq == 0) {                                                     // PGE:302-317
     double u[4];
     stream_uniforms(cf.seed, gid, e.episode - 1, 3, (uint32_t)e.cmd_draws++, u);
-    e.target_angle = 2.0 * M_PI * u[0];
-    e.tgt_x = e.pos[0] + std::cos(e.target_angle) * 100.0;
-    e.tgt_y = e.pos[1] + std::sin(e.target_angle) * 100.0;
-    e.last_pos_diff_len = std::sqrt((e.pos[0] - e.tgt_x) * (e.pos[0] - e.tgt_x) + (e.pos[1] - e.tgt_y) * (e.pos[1] - e.tgt_y));
+    if (cf.element_id == 0) {
+      e.target_angle = 2.0 * M_PI * u[0];
+      e.tgt_x = e.pos[0] + std::cos(e.target_angle) * 100.0;
+      e.tgt_y = e.pos[1] + std::sin(e.target_angle) * 100.0;
+      e.last_pos_diff_len = std::sqrt((e.pos[0] - e.tgt_x) * (e.pos[0] - e.tgt_x) + (e.pos[1] - e.tgt_y) * (e.pos[1] - e.tgt_y));
+    }
     e.target_spd = cf.target_spd_lo + u[1] * (cf.target_spd_hi - cf.target_spd_lo);
   }
+  if (cf.element_id != 0) e.target_angle = std::atan2(e.tgt_y - e.pos[1], e.tgt_x - e.pos[0]);   // PGE:318-323 (plotting only)
   double act[12], tgt[12], tau[12];
   for (int j = 0; j < 12; j++) { act[j] = (double)action[j]; tgt[j] = e.q[j] + act[j]; }   // PGE:323-324
   bool ok = true;
@@ -1032,6 +1167,12 @@ double epmc_step(llq_engine& E, Env& e, int64_t gid, const float* action, bool* 
   double yaw = std::atan2(R.m[1][0], R.m[0][0]);
   double reward_rot = std::exp((std::cos(yaw) * ux + std::sin(yaw) * uy - 1.0) * 5.0);
   double r = reward_vel * reward_rot / (double)cf.max_steps;
+  if (cf.element_id != 0) {                                                              // _compute_avg_spd_reward (PGE:504-539)
+    const double reward_dist = (plen - e.last_pos_diff_len) / e.init_pos_diff_len;
+    e.last_pos_diff_len = plen;
+    r = reward_rot / (double)cf.max_steps * 0.1 * 2.0 + (-reward_dist * 0.1);
+    if (reach) r += std::exp(-std::fabs(e.total_spd / e.counter - e.target_spd));
+  }
   if (!ok || !std::isfinite(r)) { r = 0.0; *done = true; }
   e.reward_sum += r;
   return r;
@@ -1040,7 +1181,6 @@ double epmc_step(llq_engine& E, Env& e, int64_t gid, const float* action, bool* 
 
 // ================================================================== SEPMC (ChaseTagGameEnv, empty arena)
 // CTG = max_game/chase_tag_game_env.py, BSG = max_game/bullet_static_entities.py, PR = randomizer/push_randomizer.py
-struct Box { V3 lo, hi; };
 // closest hit of the segment a->b with a set of axis-aligned boxes (rayTest / rayTestBatch, mask 6 => statics only).
 // Returns the hit fraction or -1.  A ray that starts inside a box does not hit that box (Bullet's convex cast).
 double ray_boxes(const Box* bs, int nb, V3 a, V3 b) {
@@ -1403,6 +1543,8 @@ int llq_default_config(llq_config* c) {
   c->push_start_count = -250; c->push_interval_steps = 499; c->push_duration_steps = 100; c->push_enabled = 1;
   c->friction_lo = 0.4; c->friction_hi = 3.0; c->push_h_lo = 0.0; c->push_h_hi = 50.0; c->push_v_lo = 0.0; c->push_v_hi = 10.0;
   c->target_spd_lo = 0.5; c->target_spd_hi = 3.0;
+  c->element_id = 0; c->wall_width_lo = 0.02; c->wall_width_hi = 0.5; c->wall_gap_lo = 1.0; c->wall_gap_hi = 20.0;
+  c->hole_gap_lo = 0.25; c->hole_gap_hi = 0.3;
   return LLQ_OK;
 }
 
@@ -1417,6 +1559,7 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   if (cfg->env_kind == LLQ_ENV_EPMC && (cfg->max_steps <= 0 || cfg->cmd_freq_hi <= cfg->cmd_freq_lo || cfg->cmd_freq_lo <= 0 ||
                                         cfg->push_interval_steps <= 0))
     return fail(LLQ_EINVAL, "bad EPMC configuration");
+  if (cfg->env_kind == LLQ_ENV_EPMC && (cfg->element_id < 0 || cfg->element_id > 3)) return fail(LLQ_EINVAL, "EPMC element_id must be 0..3");
   llq_engine* e = new (std::nothrow) llq_engine();
   if (!e) return fail(LLQ_ENOMEM, "out of memory");
   e->cfg = *cfg;
@@ -1644,13 +1787,18 @@ int llq_get_field(llq_handle h, int field, void* dst) {
         a[0] = e.counter; a[1] = e.cmd_freq; a[2] = e.tgt_x; a[3] = e.tgt_y; a[4] = e.target_spd; a[5] = e.target_angle;
         a[6] = e.last_pos_diff_len; a[7] = e.total_spd; a[8] = e.max_spd; a[9] = e.push_count; a[10] = e.push_f[0];
         a[11] = e.push_f[1]; a[12] = e.push_f[2]; a[13] = e.foot_mu; a[14] = e.push_draws; a[15] = e.cmd_draws;
-        a[16] = e.yaw_accum_deg; a[17] = 0;
+        a[16] = e.yaw_accum_deg; a[17] = e.init_pos_diff_len;
         break;
       }
       case LLQ_F_EPISODE_ID: ((int64_t*)dst)[i] = e.episode; break;
       case LLQ_F_FOOT_POS: for (int t = 0; t < 12; t++) ((float*)dst)[(size_t)i * 12 + t] = (float)e.foot_pos[t]; break;
       case LLQ_F_DECISION_MARGIN: ((float*)dst)[i] = (float)e.margin; break;
       case LLQ_F_OB_ID: ((int32_t*)dst)[i] = e.ob_id; break;
+      case LLQ_F_NBOX: ((int32_t*)dst)[i] = e.n_boxes; break;
+      case LLQ_F_BOXES:
+        for (int b = 0; b < LLQ_MAX_BOXES; b++) for (int t = 0; t < 6; t++)
+          ((float*)dst)[((size_t)i * LLQ_MAX_BOXES + b) * 6 + t] = b < e.n_boxes ? (float)e.boxes[b][t] : 0.0f;
+        break;
       case LLQ_F_SAMPLE_PROB: case LLQ_F_AVG_REWARD: break;
       default: return fail(LLQ_EINVAL, "unknown field");
     }
@@ -1695,7 +1843,7 @@ int llq_set_field(llq_handle h, int field, const void* src) {
         e.counter = (int)a[0]; e.cmd_freq = (int)a[1]; e.tgt_x = a[2]; e.tgt_y = a[3]; e.target_spd = a[4]; e.target_angle = a[5];
         e.last_pos_diff_len = a[6]; e.total_spd = a[7]; e.max_spd = a[8]; e.push_count = (int)a[9]; e.push_f[0] = a[10];
         e.push_f[1] = a[11]; e.push_f[2] = a[12]; e.foot_mu = a[13]; e.push_draws = (int)a[14]; e.cmd_draws = (int)a[15];
-        e.yaw_accum_deg = a[16];
+        e.yaw_accum_deg = a[16]; e.init_pos_diff_len = a[17];
         if (e.cmd_freq <= 0) return fail(LLQ_EINVAL, "cmd_vary_freq must be positive");
         break;
       }
@@ -1790,6 +1938,15 @@ int llq_oracle_proxy_positions(llq_handle h, const double* st37, double* out, in
   proxy_positions(*h, st37, p);
   for (int i = 0; i < n; i++) { out[3 * i] = p[i].x; out[3 * i + 1] = p[i].y; out[3 * i + 2] = p[i].z; }
   *count = n;
+  return LLQ_OK;
+}
+
+// oracle-only hook: replace the static boxes env `env` collides with / is seen through (the pybullet shim mirrors its body list here)
+int llq_oracle_set_boxes(llq_handle h, int32_t env, const double* boxes6, int32_t n) {
+  if (!h || env < 0 || env >= h->cfg.n_envs || n < 0 || n > LLQ_MAX_BOXES || (n > 0 && !boxes6)) return fail(LLQ_EINVAL, "bad arguments");
+  Env& e = h->envs[env];
+  e.n_boxes = n;
+  for (int b = 0; b < n; b++) for (int t = 0; t < 6; t++) e.boxes[b][t] = boxes6[b * 6 + t];
   return LLQ_OK;
 }
 

@@ -59,6 +59,7 @@ class FakeBulletClient:
     oracle_engine = None      # VecEngine over libllq_cpu.so with n_envs = 1 (2 for the chase-tag pair), set by the generator
     contact_breaking = 0.0005
     boxes_block_rays = False  # chase-tag generator: createMultiBody boxes (walls, flag) are seen by rays
+    terrain_boxes = False     # EPMC corridor generator: static boxes are mirrored into the oracle (foot contacts) before every step
     pair_contacts = False     # chase-tag generator: robot-robot / robot-flag contact points from detection proxies
     call_log = None
 
@@ -233,6 +234,16 @@ class FakeBulletClient:
         return [(tuple(pp[by_link[j]]), (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, (0, 0, 0, 1), z3, z3) for j in indices]
 
     # ---- the physics step
+    def _mirror_boxes(self, dyn):
+        """EPMC corridor: hand the live static boxes (walls, hurdles, bars, cubes; not the degenerate target marker, not the
+        auxiliary cylinders) to the oracle, whose foot narrow phase then collides with them."""
+        bx = [np.r_[o.state[0:3], o.box] for o in self.bodies
+              if o.kind == "static" and getattr(o, "box", None) is not None and np.any(o.box > 0)]
+        arr = np.ascontiguousarray(np.array(bx, dtype=np.float64).reshape(-1, 6))
+        self._lib.llq_oracle_set_boxes.restype = C.c_int
+        for k in range(len(dyn)):
+            assert self._lib.llq_oracle_set_boxes(self._h, k, arr.ctypes.data_as(C.c_void_p), len(bx)) == 0
+
     def _narrow_phase(self):
         """Contact points for getContactPoints(), built on the pre-step poses.  PMC: robot detection proxies vs static boxes
         through the oracle's hurdle test.  Chase tag: independent numpy sphere-sphere / sphere-box tests over the model's
@@ -278,7 +289,10 @@ class FakeBulletClient:
                 st = np.ascontiguousarray(b.state, dtype=np.float64)
                 assert self._lib.llq_oracle_set_state64(self._h, k, st.ctypes.data_as(C.c_void_p)) == 0
                 b.dirty = False
-        self._narrow_phase()
+        if FakeBulletClient.terrain_boxes:
+            self._mirror_boxes(dyn)
+        else:
+            self._narrow_phase()
         for k, b in enumerate(dyn):
             tau = np.ascontiguousarray(b.tau, dtype=np.float64)
             push = None if b.push is None else np.ascontiguousarray(b.push, dtype=np.float64)

@@ -111,3 +111,66 @@ def test_cuda_replays_reference_epmc_golden(gold, built, blob):
             assert np.allclose(aux[[0, 1, 9, 14, 15]], g["aux"][step][[0, 1, 9, 14, 15]])
             assert np.allclose(aux[[2, 3, 4, 5, 10, 11, 12, 13]], g["aux"][step][[2, 3, 4, 5, 10, 11, 12, 13]], rtol=1e-4, atol=1e-4)
     eng.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# elements 1-3 (hurdles, bars, cubes): tests/golden/gen_golden_epmc_terrain_from_reference.py
+def terrain_gold(element):
+    return np.load(os.path.join(os.path.dirname(GOLD), "epmc_e%d_reference_golden.npz" % element))
+
+
+def terrain_cfg(g):
+    cfg = dict(EPMC_CFG)
+    cfg.update(element_id=int(g["element_id"]), max_steps=int(g["max_steps"]), hole_gap_lo=0.25, hole_gap_hi=0.25,
+               wall_width_lo=0.02, wall_width_hi=0.5, wall_gap_lo=1.0, wall_gap_hi=20.0)
+    return cfg
+
+
+T_EXACT = [0, 1, 9, 14, 15]                 # counter, cmd_vary_freq, push count, push draws, command draws
+T_CONT = [2, 3, 4, 6, 7, 8, 13, 17]         # target xy, target speed, last / init distance, speed stats, friction
+
+
+@pytest.mark.parametrize("element", [1, 2, 3])
+def test_oracle_replays_reference_epmc_terrain_golden(element, oracle_lib, blob):
+    """Terrain generation (Philox stream 5), target placement, perception against the box list, foot contacts with boxes,
+    the average-speed reward with the reach bonus and termination -- through the oracle's own reset()/step() path."""
+    import ctypes as C
+    g = terrain_gold(element)
+    eng = capi.VecEngine(oracle_lib, 1, blob, None, seed=int(g["seed"]), **terrain_cfg(g))
+    eng.set_init_state(g["init_state"])
+    lib = oracle_lib.lib
+    lib.llq_oracle_set_state64.restype = C.c_int
+    tp = {int(s): st for s, st in zip(g["tp_step"], g["tp_state"])}
+    step = 0
+    for ep in range(len(g["reset_obs"])):
+        obs = eng.reset()
+        nb = int(eng.get(capi.F_NBOX)[0])
+        assert nb == int(g["nbox"][ep])
+        bx = eng.get(capi.F_BOXES)[0].reshape(36, 6)
+        assert np.allclose(bx[:nb], g["boxes"][ep][:nb], rtol=1e-6, atol=1e-6), ("boxes", ep)
+        err = np.max(np.abs(obs[0] - g["reset_obs"][ep]) / (1 + np.abs(g["reset_obs"][ep])))
+        assert err < 5e-7, ("reset obs", ep, err, np.argwhere(np.abs(obs[0] - g["reset_obs"][ep]) > 1e-6)[:5])
+        aux = eng.get(capi.F_AUX)[0]
+        assert np.array_equal(aux[T_EXACT], g["reset_aux"][ep][T_EXACT])
+        assert np.allclose(aux[T_CONT], g["reset_aux"][ep][T_CONT], rtol=1e-6, atol=1e-9)
+        while step < len(g["episode"]) and g["episode"][step] == ep:
+            if step in tp:
+                st = np.ascontiguousarray(tp[step], dtype=np.float64)
+                assert lib.llq_oracle_set_state64(eng._h, 0, st.ctypes.data_as(C.c_void_p)) == 0
+            o, r, d = eng.step(g["action"][step][None])
+            tol = 5e-7 if g["aux"][step][9] <= 0 else 1e-4          # inside a push window 1-ulp torque differences get amplified
+            err = np.max(np.abs(o[0] - g["obs"][step]) / (1 + np.abs(g["obs"][step])))
+            assert err < tol, ("obs", step, err, np.argwhere(np.abs(o[0] - g["obs"][step]) > 1e-6)[:5])
+            assert abs(r[0] - g["reward"][step]) < 2 * tol, ("reward", step, r[0], g["reward"][step])
+            assert bool(d[0]) == bool(g["done"][step]), ("done", step)
+            aux = eng.get(capi.F_AUX)[0]
+            assert np.array_equal(aux[T_EXACT], g["aux"][step][T_EXACT]), ("counters", step)
+            assert np.allclose(aux[T_CONT], g["aux"][step][T_CONT], rtol=2 * tol, atol=1e-7), ("aux", step, aux[T_CONT], g["aux"][step][T_CONT])
+            st = eng.get(capi.F_STATE)[0].astype(np.float64); ws = g["state"][step].copy()
+            if np.dot(st[3:7], ws[3:7]) < 0:
+                ws[3:7] *= -1
+            assert np.max(np.abs(st - ws) / (1 + np.abs(ws))) < tol, ("state", step)
+            step += 1
+    assert step == len(g["episode"])
+    assert (g["reward"] > 0.2).any()                 # the reach bonus occurs in the file
+    eng.close()
