@@ -85,6 +85,8 @@ void fill_params(llq_handle h) {
   P.mu_ground = (float)c.ground_friction; P.fr_lo = (float)c.friction_lo; P.fr_hi = (float)c.friction_hi;
   P.ph_lo = (float)c.push_h_lo; P.ph_hi = (float)c.push_h_hi; P.pv_lo = (float)c.push_v_lo; P.pv_hi = (float)c.push_v_hi;
   P.ts_lo = (float)c.target_spd_lo; P.ts_hi = (float)c.target_spd_hi;
+  P.element_id = c.element_id; P.ww_lo = (float)c.wall_width_lo; P.ww_hi = (float)c.wall_width_hi; P.wg_lo = (float)c.wall_gap_lo;
+  P.wg_hi = (float)c.wall_gap_hi; P.hg_lo = (float)c.hole_gap_lo; P.hg_hi = (float)c.hole_gap_hi;
   if (!h->has_obstacles) { P.has_ob = 0; P.ob_hx = P.ob_hy = P.ob_hz = 0.f; }
 }
 
@@ -127,6 +129,15 @@ void launch_reset_t(llq_handle h, const llq::EnvArrays& E, const llq::ResetParam
 }
 void launch_step(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
   const bool epmc = h->cfg.env_kind == LLQ_ENV_EPMC;
+  if (epmc && h->cfg.element_id != 0) {        // corridor arenas: the box-aware instance
+    switch (h->block) {
+      case 32: launch_step_t<32, 3>(h, E, a, obs2, ld, s); break;
+      case 64: launch_step_t<64, 3>(h, E, a, obs2, ld, s); break;
+      default: launch_step_t<128, 3>(h, E, a, obs2, ld, s); break;
+    }
+    h->counters[4]++;
+    return;
+  }
   if (h->cfg.env_kind == LLQ_ENV_SEPMC) {
     switch (h->block) {
       case 32: launch_step_t<32, 2>(h, E, a, obs2, ld, s); break;
@@ -144,7 +155,8 @@ void launch_step(llq_handle h, const llq::EnvArrays& E, const float* a, float* o
   h->counters[4]++;
 }
 void launch_reset(llq_handle h, const llq::EnvArrays& E, const llq::ResetParams& RP, float* obs2, long long ld, cudaStream_t s) {
-  if (h->cfg.env_kind == LLQ_ENV_EPMC) launch_reset_t<128, 1>(h, E, RP, obs2, ld, s);
+  if (h->cfg.env_kind == LLQ_ENV_EPMC && h->cfg.element_id != 0) launch_reset_t<128, 3>(h, E, RP, obs2, ld, s);
+  else if (h->cfg.env_kind == LLQ_ENV_EPMC) launch_reset_t<128, 1>(h, E, RP, obs2, ld, s);
   else if (h->cfg.env_kind == LLQ_ENV_SEPMC) launch_reset_t<128, 2>(h, E, RP, obs2, ld, s);
   else launch_reset_t<128, 0>(h, E, RP, obs2, ld, s);
   h->counters[4]++;
@@ -217,6 +229,8 @@ int llq_default_config(llq_config* c) {
   c->push_start_count = -250; c->push_interval_steps = 499; c->push_duration_steps = 100; c->push_enabled = 1;
   c->friction_lo = 0.4; c->friction_hi = 3.0; c->push_h_lo = 0.0; c->push_h_hi = 50.0; c->push_v_lo = 0.0; c->push_v_hi = 10.0;
   c->target_spd_lo = 0.5; c->target_spd_hi = 3.0;
+  c->element_id = 0; c->wall_width_lo = 0.02; c->wall_width_hi = 0.5; c->wall_gap_lo = 1.0; c->wall_gap_hi = 20.0;
+  c->hole_gap_lo = 0.25; c->hole_gap_hi = 0.3;
   return LLQ_OK;
 }
 
@@ -231,6 +245,7 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   if (cfg->env_kind == LLQ_ENV_EPMC && (cfg->max_steps <= 0 || cfg->cmd_freq_hi <= cfg->cmd_freq_lo || cfg->cmd_freq_lo <= 0 ||
                                         cfg->push_interval_steps <= 0))
     return fail(LLQ_EINVAL, "bad EPMC configuration");
+  if (cfg->env_kind == LLQ_ENV_EPMC && (cfg->element_id < 0 || cfg->element_id > 3)) return fail(LLQ_EINVAL, "EPMC element_id must be 0..3");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(LLQ_ECUDA, "no CUDA device visible (the CUDA engine has no CPU fallback)");
@@ -257,6 +272,7 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   TRY(dalloc(&h->E.counters, 8));
   TRY(dalloc(&h->E.aux, (size_t)LLQ_AUX_DIM * n));
   TRY(dalloc(&h->E.ob_id, n));
+  TRY(dalloc(&h->E.boxes, (size_t)6 * LLQ_MAX_BOXES * n)); TRY(dalloc(&h->E.nbox, n));
   TRY(dalloc(&h->d_actions, (size_t)LLQ_ACTION_DIM * n));
   TRY(dalloc(&h->d_mask, n)); TRY(dalloc(&h->d_clip_in, n)); TRY(dalloc(&h->d_time_in, n));
   ce = cudaMallocHost((void**)&h->h_actions, sizeof(float) * LLQ_ACTION_DIM * n);
@@ -278,7 +294,7 @@ int llq_destroy(llq_handle h) {
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
   void* dptrs[] = {h->d_model, h->d_frames, h->d_clip_off, h->E.pos, h->E.st, h->E.time, h->E.clip, h->E.reward_sum, h->E.episode_steps,
-                   h->E.episode, h->E.warm, h->E.obs, h->E.kin, h->E.foot_pos, h->E.done_reward, h->E.done, h->E.reward, h->E.counters, h->E.aux, h->E.ob_id, h->d_ob_table, h->d_ob_off,
+                   h->E.episode, h->E.warm, h->E.obs, h->E.kin, h->E.foot_pos, h->E.done_reward, h->E.done, h->E.reward, h->E.counters, h->E.aux, h->E.ob_id, h->E.boxes, h->E.nbox, h->d_ob_table, h->d_ob_off,
                    h->d_actions, h->d_winner[0], h->d_winner[1], h->d_avg[0], h->d_avg[1], h->d_prob, h->d_max_steps, h->d_mask,
                    h->d_clip_in, h->d_time_in, h->d_scratch};
   for (void* p : dptrs) if (p) cudaFree(p);
@@ -584,6 +600,8 @@ int llq_get_field(llq_handle h, int field, void* dst) {
     case LLQ_F_EPISODE_ID: CK(cudaMemcpy(dst, h->E.episode, sizeof(long long) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_OB_ID: CK(cudaMemcpy(dst, h->E.ob_id, sizeof(int) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_OBS: CK(cudaMemcpy(dst, h->E.obs, sizeof(float) * h->obs_dim * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
+    case LLQ_F_BOXES: CK(cudaMemcpy(dst, h->E.boxes, sizeof(float) * 6 * LLQ_MAX_BOXES * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
+    case LLQ_F_NBOX: CK(cudaMemcpy(dst, h->E.nbox, sizeof(int) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_AUX: {
       std::vector<double> tmp((size_t)LLQ_AUX_DIM * n);
       CK(cudaMemcpy(tmp.data(), h->E.aux, sizeof(double) * LLQ_AUX_DIM * n, cudaMemcpyDeviceToHost));

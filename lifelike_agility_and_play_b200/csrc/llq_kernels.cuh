@@ -24,7 +24,8 @@
 namespace llq {
 
 constexpr int kObsDim = 207, kObsDimEpmc = 916, kObsDimSepmc = 965, kPropDim = 33, kActDim = 12, kStateDim = 37, kAuxDim = 18;
-template <int ENV> struct ObsW { static constexpr int value = ENV == 1 ? kObsDimEpmc : (ENV == 2 ? kObsDimSepmc : kObsDim); };
+template <int ENV> struct ObsW { static constexpr int value = (ENV == 1 || ENV == 3) ? kObsDimEpmc : (ENV == 2 ? kObsDimSepmc : kObsDim); };
+constexpr int kMaxBoxes = 36, kMaxCand = 8;   // ENV 3 = EPMC corridor (elements 1-3): static boxes per env, contact candidates per step
 constexpr int kNewObs = 120;
 constexpr int kRowFloats = 153;  // per-lane floats of the constraint-row workspace in shared memory (Yc 18 | Yl 18 | Ul 9 | Acl 36 | Alc 36 | All 36)  // floats staged per env: prop 33 | action 12 | future 72 (+3 pad)
 
@@ -59,6 +60,8 @@ struct StepParams {
   float mu_ground, fr_lo, fr_hi, ph_lo, ph_hi, pv_lo, pv_hi, ts_lo, ts_hi;
   // PMC hurdle plates (PLE:173-193)
   int has_ob; float ob_hx, ob_hy, ob_hz;
+  // EPMC corridor (BSE)
+  int element_id; float ww_lo, ww_hi, wg_lo, wg_hi, hg_lo, hg_hi;
 };
 
 struct EnvArrays {      // SoA device arrays, N envs
@@ -79,6 +82,8 @@ struct EnvArrays {      // SoA device arrays, N envs
   unsigned long long* counters;  // [8]
   double* aux;          // [18][N] EPMC bookkeeping (include/llq.h LLQ_F_AUX)
   int* ob_id;           // [N] active hurdle plate
+  float* boxes;         // [N][36][6] EPMC corridor: centre xyz, half extents xyz (walls first)
+  int* nbox;            // [N]
 };
 
 struct MocapDev { const MocapFrame* frames; const int* clip_off; int n_clips; const double* ob_table; const int* ob_off; };
@@ -430,6 +435,108 @@ LLQ_DI void sepmc_pair_tail(const ModelConst& M, const LegConst& L, int k, int r
   }
 }
 
+
+// ---------------------------------------------------------------------------------------------------------------
+// EPMC corridor (elements 1-3; BSE = max_game_elements/bullet_static_entities.py).
+// 64-bit mask of the env's boxes whose xy footprint comes within `margin` of (px, py) (zsel: whose z range contains pz);
+// the 4 lanes of an env scan interleaved quarters and combine.
+LLQ_DI unsigned long long box_mask(const float* boxes, int nb, int k, float px, float py, float pz, float margin, bool zsel) {
+  unsigned long long m = 0ull;
+  for (int j = k; j < nb; j += 4) {
+    const float* b = boxes + 6 * j;
+    const bool hit = zsel ? fabsf(b[2] - pz) <= b[5] : (fabsf(b[0] - px) <= b[3] + margin && fabsf(b[1] - py) <= b[4] + margin);
+    if (hit) m |= 1ull << j;
+  }
+  unsigned lo = (unsigned)m, hi = (unsigned)(m >> 32);
+  lo |= __shfl_xor_sync(FULL, lo, 1); hi |= __shfl_xor_sync(FULL, hi, 1);
+  lo |= __shfl_xor_sync(FULL, lo, 2); hi |= __shfl_xor_sync(FULL, hi, 2);
+  return ((unsigned long long)hi << 32) | lo;
+}
+// closest hit fraction against the ground slab and the boxes selected by `mask`
+LLQ_DI float ray_boxlist(V3 o, V3 d, const float* boxes, unsigned long long mask) {
+  float best = ray_box1(o, d, V3{-100.f, -100.f, -10.f}, V3{100.f, 100.f, 0.f}, -1.f);
+  while (mask) {
+    const int j = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    const float* b = boxes + 6 * j;
+    best = ray_box1(o, d, V3{b[0] - b[3], b[1] - b[4], b[2] - b[5]}, V3{b[0] + b[3], b[1] + b[4], b[2] + b[5]}, best);
+  }
+  return best;
+}
+struct TerrainRng {
+  unsigned long long seed; long long gid, ep; int k; double u[4];
+  LLQ_DI double next() {
+    if ((k & 3) == 0) stream_uniforms(seed, gid, ep, 5, (unsigned)(k >> 2), u);
+    const double v = (k & 3) == 0 ? u[0] : ((k & 3) == 1 ? u[1] : ((k & 3) == 2 ? u[2] : u[3]));
+    k++;
+    return v;
+  }
+  LLQ_DI double uniform(double lo, double hi) { return lo + next() * (hi - lo); }
+  LLQ_DI int randint(int lo, int hi) { return lo + (int)floor(next() * (double)(hi - lo)); }
+};
+LLQ_DI void put_box(float* boxes, int& nb, bool wr, double cx, double cy, double cz, double lx, double ly, double lz) {
+  if (nb < kMaxBoxes && wr) {
+    float* b = boxes + 6 * nb;
+    b[0] = (float)cx; b[1] = (float)cy; b[2] = (float)cz; b[3] = (float)(lx / 2); b[4] = (float)(ly / 2); b[5] = (float)(lz / 2);
+  }
+  if (nb < kMaxBoxes) nb++;
+}
+// reset(): _generate_random_width_walls + _create_hurdles / _create_holes / _create_cubes(easy) (BSE:170-263, 308-500); returns the
+// number of boxes, writes them when `wr`, and the target x (target y = 0)
+LLQ_DI int generate_corridor(const StepParams& P, unsigned long long seed, long long gid, long long ep, float* boxes, bool wr, double& tgx) {
+  TerrainRng R{seed, gid, ep, 0, {0.0, 0.0, 0.0, 0.0}};
+  int nb = 0;
+  const double width = R.uniform((double)P.ww_lo, (double)P.ww_hi), gap = R.uniform((double)P.wg_lo, (double)P.wg_hi);
+  put_box(boxes, nb, wr, 5.0, gap / 2.0 + width / 2.0, 1.0, 200.0, width, 2.0);
+  put_box(boxes, nb, wr, 5.0, -(gap / 2.0 + width / 2.0), 1.0, 200.0, width, 2.0);
+  double cur = 0.0;
+  tgx = 8.0;
+  if (P.element_id == 1 || P.element_id == 2) {
+    const int n = R.randint(1, 10);
+    for (int pass = 0; pass < 2; pass++) {
+      for (int i = 0; i < n; i++) {
+        if (P.element_id == 1) {
+          const double h = R.uniform(0.05, 0.15), d = R.uniform(1.0, 3.0);
+          put_box(boxes, nb, wr, cur + d / 2, 0.0, h / 2, 0.1, gap, h);
+          cur += d + 0.1;
+        } else {
+          const double d = R.uniform(1.0, 3.0), g = R.uniform((double)P.hg_lo, (double)P.hg_hi);
+          put_box(boxes, nb, wr, cur + d / 2, 0.0, 0.3 / 2 + g, 0.1, gap, 0.3);
+          cur += d + 0.1;
+        }
+      }
+      if (pass == 0) tgx = cur + R.uniform(-1.0, 1.0);
+    }
+  } else {
+    const int ns = R.randint(1, 5);
+    for (int pass = 0; pass < 2; pass++) {
+      for (int i = 0; i < ns; i++) {
+        cur += R.uniform(0.0, 1.0);
+        put_box(boxes, nb, wr, 1.75 + cur, 0.0, 0.25 / 2, 0.5, gap, 0.25);
+        put_box(boxes, nb, wr, 1.0 + cur, 0.0, 0.1 / 2, 0.5, gap, 0.1);
+        cur += 1.75 + 0.25;
+        put_box(boxes, nb, wr, cur + 0.5, 0.0, 0.25 / 2, 0.5, gap, 0.25);
+        put_box(boxes, nb, wr, cur + 1.25, 0.0, 0.1 / 2, 0.5, gap, 0.1);
+        cur += 3.0;
+      }
+      if (pass == 0) tgx = cur + R.uniform(-3.0, 3.0);
+    }
+  }
+  return nb;
+}
+// stage the perception context of an EPMC-corridor row: yaw and the three candidate masks (as raw bits)
+LLQ_DI void stage_corridor_masks(float* snew, const float* boxes, int nb, int k, float px, float py, float pz, float yaw) {
+  const unsigned long long m2 = box_mask(boxes, nb, k, px, py, pz, 1.36f, false);   // 2.4 x 1.2 footprint, any yaw
+  const unsigned long long mf = box_mask(boxes, nb, k, px, py, pz, 3.35f, false);   // 3 m rays starting up to 0.27 m off the base
+  const unsigned long long m1 = box_mask(boxes, nb, k, px, py, pz, 0.f, true);      // horizontal rays at the base height
+  if (k == 0) {
+    snew[61] = yaw;
+    snew[62] = __uint_as_float((unsigned)m2); snew[63] = __uint_as_float((unsigned)(m2 >> 32));
+    snew[64] = __uint_as_float((unsigned)mf); snew[65] = __uint_as_float((unsigned)(mf >> 32));
+    snew[66] = __uint_as_float((unsigned)m1); snew[67] = __uint_as_float((unsigned)(m1 >> 32));
+  }
+}
+
 // ---------------------------------------------------------------------------------------------------------------
 // Shared tail: given the dynamic robot state (pybullet convention) and the mocap cursor, build the new prop / future
 // into the staging row `snew` (120 floats per env) and return the pieces the reward needs.
@@ -494,7 +601,7 @@ constexpr int kHist = 90;   // per-env history carry: prop[33:99] (66) | prop_a[
 // EPMC: prop 33 | action 12 | R (world<-base inertial, row major) 9 | pos 3 | target 3 | |base_pos| 1   (perception is evaluated while the row is written)
 template <int ENV>
 LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const float* snew_warp, const float* hist_warp, int env0, int n_envs,
-                          int mode, unsigned row_mask) {
+                          int mode, unsigned row_mask, const float* boxes_all = nullptr) {
   constexpr int OW = ObsW<ENV>::value;
   const int lane = threadIdx.x & 31;
 #pragma unroll 4
@@ -515,6 +622,36 @@ LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const floa
         else v = a < 24 ? hs[66 + a] : sn[kPropDim + a - 24];
       } else if (ENV == 0) {
         v = sn[45 + (j - 135)];
+      } else if (ENV == 3) {
+        // EPMC corridor perception against the ground slab and the env's candidate boxes (PGE:374-447)
+        const V3 pos = V3{sn[54], sn[55], sn[56]};
+        const float* bxs = boxes_all + (size_t)(env0 + e) * (6 * kMaxBoxes);
+        if (j < 460) {
+          const unsigned long long m = ((unsigned long long)__float_as_uint(sn[63]) << 32) | __float_as_uint(sn[62]);
+          const int t = j - 135, a = t / 13, b = t - a * 13;
+          const float gx = a == 24 ? 1.2f : -1.2f + (float)a * (2.4f / 24.0f), gy = b == 12 ? 0.6f : -0.6f + (float)b * (1.2f / 12.0f);
+          const float x = fmaf(sn[45], gx, fmaf(sn[46], gy, pos.x)), y = fmaf(sn[48], gx, fmaf(sn[49], gy, pos.y));
+          const float f = ray_boxlist(V3{x, y, 10.f}, V3{0.f, 0.f, -20.f}, bxs, m);
+          v = f < 0.f ? 0.f : fmaf(f, -20.f, 10.f);
+          if (f >= 0.f && fabsf(v) < 2e-6f) v = 0.f;
+        } else if (j < 588) {
+          const unsigned long long m = ((unsigned long long)__float_as_uint(sn[67]) << 32) | __float_as_uint(sn[66]);
+          const float ang = sn[61] + 6.283185307179586f * (float)(j - 460) * (1.0f / 128.0f);
+          float sa, ca;
+          sincosf(ang, &sa, &ca);
+          const float f = ray_boxlist(pos, V3{20.f * ca, 20.f * sa, 0.f}, bxs, m);
+          v = f < 0.f ? sn[60] : f * 20.f * sqrtf(ca * ca + sa * sa);
+        } else if (j < 913) {
+          const unsigned long long m = ((unsigned long long)__float_as_uint(sn[65]) << 32) | __float_as_uint(sn[64]);
+          const int t = j - 588, a = t / 13, b = t - a * 13;
+          const float y = a == 24 ? 0.25f : -0.25f + (float)a * (0.5f / 24.0f), z = b == 12 ? 0.1f : -0.3f + (float)b * (0.4f / 12.0f);
+          const V3 from = V3{fmaf(sn[46], y, fmaf(sn[47], z, pos.x)), fmaf(sn[49], y, fmaf(sn[50], z, pos.y)), fmaf(sn[52], y, fmaf(sn[53], z, pos.z))};
+          const V3 d = V3{3.f * sn[45], 3.f * sn[48], 3.f * sn[51]};
+          const float f = ray_boxlist(from, d, bxs, m);
+          v = (f < 0.f ? 1.f : f) * norm3(d);
+        } else {
+          v = sn[57 + (j - 913)];
+        }
       } else if (ENV == 2) {
         // SEPMC perception against ground slab, walls and flag (CTG:598-638, PGE:22-54)
         const V3 pos = V3{sn[54], sn[55], sn[56]};
@@ -650,8 +787,10 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     mu_env = P.mu_ground * (float)A[13 * N + env]; push_draws = (int)A[14 * N + env]; PS.flag_draws = (int)A[15 * N + env];
     epi = E.episode[env] - 1;
   }
-  if (ENV == 1) {
+  double init_len = 1.0;
+  if (ENV == 1 || ENV == 3) {
     const double* A = E.aux;
+    if (ENV == 3) init_len = A[17 * N + env];
     counter = (int)A[env]; cmd_freq = (int)A[N + env]; tgx = A[2 * N + env]; tgy = A[3 * N + env];
     target_spd = (float)A[4 * N + env]; target_angle = A[5 * N + env]; last_len = A[6 * N + env]; total_spd = A[7 * N + env];
     max_spd = A[8 * N + env]; push_count = (int)A[9 * N + env]; pf[0] = (float)A[10 * N + env]; pf[1] = (float)A[11 * N + env];
@@ -661,13 +800,36 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     if (counter % cmd_freq == 0) {                        // PGE:302-317, element_id 0
       double u[4];
       stream_uniforms(seed, gid0 + env, epi, 3, (unsigned)cmd_draws++, u);
-      target_angle = 2.0 * 3.14159265358979323846 * u[0];
-      double sn, cs;
-      sincos(target_angle, &sn, &cs);
-      tgx = px + cs * 100.0; tgy = py + sn * 100.0;
-      last_len = sqrt((px - tgx) * (px - tgx) + (py - tgy) * (py - tgy));
+      if (ENV == 1) {
+        target_angle = 2.0 * 3.14159265358979323846 * u[0];
+        double sn, cs;
+        sincos(target_angle, &sn, &cs);
+        tgx = px + cs * 100.0; tgy = py + sn * 100.0;
+        last_len = sqrt((px - tgx) * (px - tgx) + (py - tgy) * (py - tgy));
+      }
       target_spd = (float)((double)P.ts_lo + u[1] * ((double)P.ts_hi - (double)P.ts_lo));
     }
+    if (ENV == 3) target_angle = atan2(tgy - py, tgx - px);            // PGE:318-323 (plotting only)
+  }
+  // ---- EPMC corridor: the boxes the feet can reach during this step -> shared memory (<= kMaxCand per env)
+  int n_cand = 0;
+  float* s_cand = nullptr;
+  if (ENV == 3) {
+    s_cand = &s_new[threadIdx.x >> 2][0];              // the staging row is free until the tail: 8 x 6 floats
+    const float* bxs = E.boxes + (size_t)env * (6 * kMaxBoxes);
+    unsigned long long m = box_mask(bxs, E.nbox[env], k, (float)px, (float)py, (float)pz, 0.6f, false);
+    int c = 0;
+    while (m && c < kMaxCand) {
+      const int j = __ffsll((long long)m) - 1;
+      m &= m - 1;
+      if ((c & 3) == k) {
+#pragma unroll
+        for (int t = 0; t < 6; t++) s_cand[6 * c + t] = bxs[6 * j + t];
+      }
+      c++;
+    }
+    n_cand = c;
+    __syncwarp();
   }
   // base orientation: pybullet speaks in the base inertial frame; dynamics run in URDF body axes B' = inertial * qI^-1
   const Q4 qI = Q4{M.base.qI[0], M.base.qI[1], M.base.qI[2], M.base.qI[3]};
@@ -704,7 +866,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
         }
       }
     }
-    if (ENV == 1 && P.push_enabled) {
+    if ((ENV == 1 || ENV == 3) && P.push_enabled) {
       push_count += 1;
       if (push_count > 0) {
         if (push_count % P.push_interval == 0) { epmc_randomize_push(P, seed, gid0 + env, epi, push_draws, pf); push_count = 0; }
@@ -897,7 +1059,8 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     }
     // ---------------- collision: foot sphere vs plane z = 0 on the pre-step pose
     V3 nb = V3{R.a20, R.a21, R.a22};                     // world z in base coords
-    int plane = 0;                                       // SEPMC: 0 ground, 1..4 walls with normals -x, +x, -y, +y
+    int plane = 0;                                       // SEPMC: 0 ground, 1..4 walls with normals -x, +x, -y, +y; EPMC corridor: 5 = a box
+    V3 nworld = V3{0.f, 0.f, 1.f};                       // plane 5: contact normal in world coordinates
     // The foot clearance feeds Bullet's speculative-contact target (-penetration/dt): a 1e-7 m rounding error becomes
     // 5e-5 m/s.  Evaluate just this scalar (height of the foot centre) in fp64 from the fp32 joint sines/cosines.
     float dist;
@@ -914,6 +1077,34 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       t = dc1 * y - ds1 * z; z = ds1 * y + dc1 * z; y = t;             // Rx(q1)
       x += (double)r[0].x; y += (double)r[0].y; z += (double)r[0].z;
       dist = (float)(pz + nx * x + ny * y + nz * z - (double)L.foot_r);
+      if (ENV == 3) {
+        // EPMC corridor: sphere vs the candidate boxes, in fp64 like the ground clearance; one contact per foot, the deepest
+        const double wx = px + (1.0 - 2.0 * (qy * qy + qz * qz)) * x + 2.0 * (qx * qy - qz * qw) * y + 2.0 * (qx * qz + qy * qw) * z;
+        const double wy = py + 2.0 * (qx * qy + qz * qw) * x + (1.0 - 2.0 * (qx * qx + qz * qz)) * y + 2.0 * (qy * qz - qx * qw) * z;
+        const double wz = pz + nx * x + ny * y + nz * z;
+        for (int c = 0; c < n_cand; c++) {
+          const float* b = s_cand + 6 * c;
+          const double p0 = wx - (double)b[0], p1 = wy - (double)b[1], p2 = wz - (double)b[2];
+          const double h0 = b[3], h1 = b[4], h2 = b[5];
+          const double c0 = fmin(fmax(p0, -h0), h0), c1 = fmin(fmax(p1, -h1), h1), c2 = fmin(fmax(p2, -h2), h2);
+          double db; V3 nn;
+          if (c0 != p0 || c1 != p1 || c2 != p2) {
+            const double v0 = p0 - c0, v1 = p1 - c1, v2 = p2 - c2;
+            const double len = sqrt(v0 * v0 + v1 * v1 + v2 * v2);
+            db = len - (double)L.foot_r;
+            nn = V3{(float)(v0 / len), (float)(v1 / len), (float)(v2 / len)};
+          } else {                                 // centre inside the box: leave through the nearest face
+            double best = h0 - p0; nn = V3{1.f, 0.f, 0.f};
+            if (h0 + p0 < best) { best = h0 + p0; nn = V3{-1.f, 0.f, 0.f}; }
+            if (h1 - p1 < best) { best = h1 - p1; nn = V3{0.f, 1.f, 0.f}; }
+            if (h1 + p1 < best) { best = h1 + p1; nn = V3{0.f, -1.f, 0.f}; }
+            if (h2 - p2 < best) { best = h2 - p2; nn = V3{0.f, 0.f, 1.f}; }
+            if (h2 + p2 < best) { best = h2 + p2; nn = V3{0.f, 0.f, -1.f}; }
+            db = -best - (double)L.foot_r;
+          }
+          if ((float)db < dist) { dist = (float)db; plane = 5; nworld = nn; }
+        }
+      }
       if (ENV == 2) {
         // the arena walls (BSG:863-902) as four more half-spaces; one contact per foot, the deepest
         const double wx = px + (1.0 - 2.0 * (qy * qy + qz * qz)) * x + 2.0 * (qx * qy - qz * qw) * y + 2.0 * (qx * qz + qy * qw) * z;
@@ -970,6 +1161,20 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           else if (plane == 2) { dirs[0] = r0; dirs[1] = r1; }
           else if (plane == 3) { dirs[0] = neg(r1); dirs[1] = r0; }
           else { dirs[0] = r1; dirs[1] = neg(r0); }
+        }
+        if (ENV == 3 && plane == 5) {                     // general normal: btPlaneSpace1 in world axes, then into base coordinates
+          const V3 n = nworld;
+          V3 t1, t2;
+          if (fabsf(n.z) > 0.70710678118654752f) {
+            const float a = n.y * n.y + n.z * n.z, kk = rsqrtf(a);
+            t1 = V3{0.f, -n.z * kk, n.y * kk};
+            t2 = V3{a * kk, -n.x * t1.z, n.x * t1.y};
+          } else {
+            const float a = n.x * n.x + n.y * n.y, kk = rsqrtf(a);
+            t1 = V3{-n.y * kk, n.x * kk, 0.f};
+            t2 = V3{-n.z * t1.y, n.z * t1.x, a * kk};
+          }
+          dirs[0] = tmul(R, n); dirs[1] = tmul(R, t1); dirs[2] = tmul(R, t2);
         }
         const V3 Pc = fb - L.foot_r * dirs[0];            // contact point on the sphere surface
 #pragma unroll
@@ -1452,6 +1657,14 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     float sy, cy;
     sincosf(yaw, &sy, &cy);
     float rew = expf(-fabsf(spd - target_spd)) * expf((cy * ux + sy * uy - 1.0f) * 5.0f) / (float)P.max_steps;
+    if (ENV == 3) {                                                    // _compute_avg_spd_reward (PGE:504-539)
+      const float reward_rot = expf((cy * ux + sy * uy - 1.0f) * 5.0f);
+      const float reward_dist = (float)((plen - last_len) / init_len);
+      last_len = plen;
+      rew = reward_rot / (float)P.max_steps * 0.1f * 2.0f - reward_dist * 0.1f;
+      if (reach) rew += expf(-fabsf((float)(total_spd / (double)counter) - target_spd));
+      stage_corridor_masks(snew, E.boxes + (size_t)env * (6 * kMaxBoxes), E.nbox[env], k, (float)px, (float)py, (float)pz, yaw);
+    }
     {
       int bi = bad ? 1 : 0;
       bi |= __shfl_xor_sync(FULL, bi, 1);
@@ -1506,7 +1719,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
   __pipeline_wait_prior(0);
   __syncwarp();
   const int warp_env0 = (blockIdx.x * BLOCK + (threadIdx.x & ~31)) >> 2;
-  emit_obs_rows<ENV>(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], &s_hist[(threadIdx.x & ~31) >> 2][0], warp_env0, N, 0, 0xFFu);
+  emit_obs_rows<ENV>(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], &s_hist[(threadIdx.x & ~31) >> 2][0], warp_env0, N, 0, 0xFFu, E.boxes);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1638,7 +1851,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
         A[15 * N + env] = PS.flag_draws; A[16 * N + env] = yaw_b; A[17 * N + env] = touch_own ? 1.0 : 0.0;
       }
     }
-  } else if (ENV == 1) {
+  } else if (ENV == 1 || ENV == 3) {
     // ---------------- EPMC reset (PGE:196-249)
     long long ep = E.episode[env];
     const long long gid = RP.gid0 + env;
@@ -1661,6 +1874,9 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
     float* snew = &s_new[threadIdx.x >> 2][0];
     const M3 Rq = qmat(qnormalize(qn));
     const float target_spd = (float)E.aux[4 * N + env];            // persists across episodes (PGE:170-172)
+    double tgx0 = 8.0;
+    int nb0 = 0;
+    if (ENV == 3) nb0 = generate_corridor(P, RP.seed, gid, ep, E.boxes + (size_t)env * (6 * kMaxBoxes), doit && k == 0, tgx0);   // PGE:216-219
 #pragma unroll
     for (int i = 0; i < 3; i++) { snew[3 * k + i] = q[i]; snew[12 + 3 * k + i] = qd[i]; }
     if (k == 0) {
@@ -1670,10 +1886,14 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
       snew[45] = Rq.a00; snew[46] = Rq.a01; snew[47] = Rq.a02; snew[48] = Rq.a10; snew[49] = Rq.a11; snew[50] = Rq.a12;
       snew[51] = Rq.a20; snew[52] = Rq.a21; snew[53] = Rq.a22;
       snew[54] = 0.f; snew[55] = 0.f; snew[56] = 0.5f;
-      V3 d = tmul(Rq, V3{8.0f, 0.f, -0.5f});                        // target (8,0,0) - pos (0,0,0.5)  (BSE:247-248)
+      V3 d = tmul(Rq, V3{(float)tgx0, 0.f, -0.5f});                 // target - pos (0,0,0.5); element 0: (8,0,0) (BSE:247-248)
       float n2 = sqrtf(d.x * d.x + d.y * d.y);
       snew[57] = d.x / n2; snew[58] = d.y / n2; snew[59] = target_spd;
       snew[60] = 0.5f;
+    }
+    if (ENV == 3) {
+      __syncwarp();                                                 // lane 0's boxes are visible to the env's other lanes
+      stage_corridor_masks(snew, E.boxes + (size_t)env * (6 * kMaxBoxes), doit ? nb0 : E.nbox[env], k, 0.f, 0.f, 0.5f, atan2f(Rq.a10, Rq.a00));
     }
     if (doit) {
       float* sw = E.st;
@@ -1690,7 +1910,8 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
         for (int i = 0; i < 10; i++) sw[i * N + env] = b[i];
         E.time[env] = 0.0; E.reward_sum[env] = 0.f; E.episode_steps[env] = 0; E.episode[env] = ep + 1;
         double* A = E.aux;
-        A[env] = 0; A[N + env] = cmd_freq; A[2 * N + env] = 8.0; A[3 * N + env] = 0.0; A[6 * N + env] = 8.0; A[7 * N + env] = 0.0;
+        A[env] = 0; A[N + env] = cmd_freq; A[2 * N + env] = tgx0; A[3 * N + env] = 0.0; A[6 * N + env] = fabs(tgx0); A[7 * N + env] = 0.0;
+        if (ENV == 3) { A[17 * N + env] = fabs(tgx0); E.nbox[env] = nb0; }
         A[8 * N + env] = 0.0; A[9 * N + env] = P.push_start_count; A[10 * N + env] = pf[0]; A[11 * N + env] = pf[1]; A[12 * N + env] = pf[2];
         A[13 * N + env] = foot_mu; A[14 * N + env] = push_draws; A[15 * N + env] = 0; A[16 * N + env] = yaw_deg;
       }
@@ -1754,7 +1975,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
 #pragma unroll
   for (int e = 0; e < 8; e++) if ((wm >> (4 * e)) & 1u) rows |= 1u << e;
   const int warp_env0 = (blockIdx.x * BLOCK + (threadIdx.x & ~31)) >> 2;
-  emit_obs_rows<ENV>(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], &s_new[0][0], warp_env0, N, 1, rows);
+  emit_obs_rows<ENV>(E.obs, obs2, obs2_ld, &s_new[(threadIdx.x & ~31) >> 2][0], &s_new[0][0], warp_env0, N, 1, rows, E.boxes);
 }
 
 }  // namespace llq

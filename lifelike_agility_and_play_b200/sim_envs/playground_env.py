@@ -1,10 +1,11 @@
 """Gym-style single-environment adaptor for the environmental-level (EPMC) playground env.
 
-Mirrors ``PlayGroundEnv`` (reference max_game_elements/playground_env.py:57-539) for ``element_id == 0`` -- the flat
-"joystick" arena that the shipped training script selects (train_scripts/example_epmc_train.sh:100): same constructor
-keywords, observation / action spaces (PGE:129-150), ``reset(**kwargs)``, ``step(rl_action)`` (dict with ``A_LLC`` or a
-bare 12-vector, PGE:323), ``info`` keys on termination (PGE:345-357).  Elements 1-3 (hurdles / holes / cubes: box terrain,
-BulletStatics) are SURVEY rows a19/a21 still to be built and raise ``NotImplementedError``.
+Mirrors ``PlayGroundEnv`` (reference max_game_elements/playground_env.py:57-539) : ``element_id`` 0 is the flat
+"joystick" arena that the shipped training script selects (train_scripts/example_epmc_train.sh:100), 1-3 the corridor
+arenas of ``BulletStatics`` (hurdles / "holes" = bars to pass under / cubes, bullet_static_entities.py:170-500).  Same
+constructor keywords, observation / action spaces (PGE:129-150), ``reset(**kwargs)``, ``step(rl_action)`` (dict with
+``A_LLC`` or a bare 12-vector, PGE:323), ``info`` keys on termination (PGE:345-357).  Only the feet collide with the
+corridor's boxes: a bar does not stop the trunk, a hurdle does not stop a shank.
 """
 from collections import OrderedDict
 
@@ -43,6 +44,9 @@ def epmc_engine_config(control_freq=50, kp=50.0, kd=1.0, max_tau=16, max_steps=1
                kp=kp, kd=kd, max_tau=float(max_tau), ground_friction=1.0,                   # max_game_elements plane.urdf:5
                max_steps=int(max_steps), friction_lo=float(erc['friction_range'][0]), friction_hi=float(erc['friction_range'][1]),
                target_spd_lo=float(erc['target_spd_range'][0]), target_spd_hi=float(erc['target_spd_range'][1]))
+    cfg.update(element_id=int(erc['element_id']), wall_width_lo=0.02, wall_width_hi=0.5, wall_gap_lo=1.0, wall_gap_hi=20.0)   # PGE:160-161,199
+    hc = erc.get('hole_config') or {}
+    cfg.update(hole_gap_lo=float(hc.get('min_gap_height', 0.25)), hole_gap_hi=float(hc.get('max_gap_height', 0.3)))    # BSE:372-373
     lo, hi = erc.get('cmd_vary_freq_range', [25, 200])                                        # PGE:170
     cfg.update(cmd_freq_lo=int(lo), cmd_freq_hi=int(hi))
     dfc = erc.get('disturb_force_config')
@@ -72,9 +76,10 @@ class PlayGroundEnv:
                 raise KeyError(e)
         if list(prop_type) != SHIPPED_PROP_TYPE or stack_frame_num != 3:
             raise NotImplementedError("the engine implements the shipped prop_type with stack_frame_num=3")
-        if env_randomize_config['element_id'] != 0:
-            raise NotImplementedError("EPMC element_id %r (box terrain, SURVEY rows a19/a21) is not built yet; element_id 0 is"
-                                      % (env_randomize_config['element_id'],))
+        if env_randomize_config['element_id'] not in (0, 1, 2, 3):
+            raise ValueError('Unknown element id.')                                           # BSE:263
+        if any(k in (env_randomize_config.get('hole_config') or {}) for k in ('length', 'height', 'max_distance', 'min_distance')):
+            raise NotImplementedError("only min/max_gap_height of hole_config are wired through")
         if obs_randomization:
             raise NotImplementedError("obs_randomization (episodic observation noise, PGE:174-179) is not built yet")
         if isinstance(max_tau, (list, tuple)):
@@ -89,7 +94,7 @@ class PlayGroundEnv:
             'percep_front': spaces.Box(0, 0, shape=(25, 13)), 'target': spaces.Box(0, 0, shape=(3,)),
         }))
         self.action_space = spaces.Dict(OrderedDict({'A_Z': spaces.Discrete(256), 'A_LLC': spaces.Box(0, 0, shape=(12,))}))   # PGE:141-144
-        self.reward_type = 'joystick'
+        self.reward_type = 'joystick' if env_randomize_config['element_id'] == 0 else 'average_speed'                      # PGE:201-204
         self.episodic_reward = OrderedDict({'reward_vel': 0.0, 'reward_rotation': 0.0, 'reward_dist': 0.0, 'reward_avg_spd': 0.0})
 
     @staticmethod

@@ -30,7 +30,7 @@ def test_config_struct_matches_header(built, oracle_lib):
     assert cfg.struct_size == ctypes.sizeof(capi.LlqConfig)
     cuda = capi.LlqLibrary(capi.CUDA_LIB_PATH)
     c2 = cuda.default_config()
-    assert cuda.is_cuda and not oracle_lib.is_cuda and cuda.abi == oracle_lib.abi == 1
+    assert cuda.is_cuda and not oracle_lib.is_cuda and cuda.abi == oracle_lib.abi == 2
     for f, _ in capi.LlqConfig._fields_:
         assert getattr(cfg, f) == getattr(c2, f), f
     assert (cfg.substeps, cfg.solver_iters, cfg.kp, cfg.kd, cfg.max_tau) == (10, 10, 50.0, 0.5, 18.0)
@@ -161,9 +161,23 @@ def test_epmc_gym_surface_on_oracle(monkeypatch, oracle_lib):
     env.close()
     cfg = pge.epmc_engine_config(50.0, 50.0, 0.5, 16, 1000, EPMC_ENV_CONFIG['env_randomize_config'])
     assert (cfg['push_start_count'], cfg['push_interval_steps'], cfg['push_duration_steps'], cfg['substeps']) == (-250, 499, 100, 10)   # K7
-    bad = dict(EPMC_ENV_CONFIG, env_randomize_config=dict(EPMC_ENV_CONFIG['env_randomize_config'], element_id=1))
-    with pytest.raises(NotImplementedError):
-        create_envs.create_playground_game(**bad)
+    bad = dict(EPMC_ENV_CONFIG, env_randomize_config=dict(EPMC_ENV_CONFIG['env_randomize_config'], element_id=4))
+    with pytest.raises(ValueError):
+        create_envs.create_playground_game(**bad)                                                   # BSE:263
+    for element in (1, 2, 3):           # corridor arenas: walls, hurdles / bars / cubes
+        cfg = dict(EPMC_ENV_CONFIG, env_randomize_config=dict(EPMC_ENV_CONFIG['env_randomize_config'], element_id=element))
+        env = create_envs.create_playground_game(**cfg)
+        assert env.reward_type == 'average_speed'
+        obs = env.reset(inter_kwargs={})
+        nb = int(env.env._engine.get(capi.F_NBOX)[0])
+        bx = env.env._engine.get(capi.F_BOXES)[0].reshape(36, 6)
+        assert 4 <= nb <= 36 and np.all(bx[:2, 3] == 100.0) and bx[0, 1] == -bx[1, 1] > 0          # two 200 m walls, symmetric
+        assert np.all(bx[2:nb, 4] == bx[0, 1] - bx[0, 4])                                           # obstacles span the corridor
+        assert obs[0]['percep_1d'].max() < 20.0 + 1e-3 and abs(np.linalg.norm(obs[0]['target'][:2]) - 1.0) < 1e-5
+        for t in range(5):
+            obs, rwd, done, info = env.step([{'A_LLC': np.zeros(12, np.float32)}])
+        assert np.isfinite(rwd[0])
+        env.close()
 
 
 SEPMC_ENV_CONFIG = {          # train_scripts/example_sepmc_train.sh:94-117 with a short episode

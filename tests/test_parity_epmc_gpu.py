@@ -95,3 +95,125 @@ def test_epmc_policy_step_parity_moderate_friction(built, blob, oracle_lib):
         e.size, np.percentile(e, 50), np.percentile(e, 99), np.percentile(e, 99.9), e.max(), int(bad.sum()), ["%.1e" % x for x in m[bad][:8]]))
     assert bad.mean() <= 2e-3
     gpu.close(); cpu.close()
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# elements 1-3: corridor arenas (walls, hurdles / bars / cubes)
+from test_golden_epmc import T_CONT, T_EXACT, terrain_cfg, terrain_gold  # noqa: E402
+
+
+def _terrain_pair(element, n, blob, oracle_lib, seed, **over):
+    g = terrain_gold(element)
+    cfg = terrain_cfg(g); cfg.update(over)
+    gpu = capi.VecEngine(capi.load_cuda_library(), n, blob, None, seed=seed, **cfg)
+    cpu = capi.VecEngine(oracle_lib, n, blob, None, seed=seed, **cfg)
+    for e in (gpu, cpu):
+        e.set_init_state(g["init_state"])
+    return gpu, cpu
+
+
+@pytest.mark.parametrize("element", [1, 2, 3])
+def test_epmc_terrain_reset_parity(element, built, blob, oracle_lib):
+    n = 512
+    gpu, cpu = _terrain_pair(element, n, blob, oracle_lib, 41)
+    for rep in range(2):
+        og, oc = gpu.reset(), cpu.reset()
+        assert np.array_equal(gpu.get(capi.F_NBOX), cpu.get(capi.F_NBOX))
+        assert np.allclose(gpu.get(capi.F_BOXES), cpu.get(capi.F_BOXES), rtol=1e-6, atol=1e-6)
+        ag, ac = gpu.get(capi.F_AUX), cpu.get(capi.F_AUX)
+        assert np.array_equal(ag[:, T_EXACT], ac[:, T_EXACT])
+        assert np.allclose(ag[:, T_CONT], ac[:, T_CONT], rtol=1e-6, atol=1e-6)
+        assert np.maximum(blockrel(og[:, :135], oc[:, :135]), blockrel(og[:, 135:], oc[:, 135:])).max() < TOL
+    gpu.close(); cpu.close()
+
+
+def _crowd_terrain(cpu, rng, n):
+    """drop a share of the robots onto / next to their obstacles, the walls and the target"""
+    st = cpu.get(capi.F_STATE); aux = cpu.get(capi.F_AUX)
+    bx = cpu.get(capi.F_BOXES).reshape(n, 36, 6); nb = cpu.get(capi.F_NBOX)
+    for i in rng.choice(n, size=n // 4, replace=False):
+        kind = rng.integers(0, 4)
+        j = rng.integers(2, nb[i])
+        b = bx[i, j]
+        if kind == 0:       # on top of / inside the footprint of an obstacle
+            st[i, 0] = b[0] + rng.uniform(-0.3, 0.3); st[i, 1] = rng.uniform(-0.2, 0.2); st[i, 2] = 0.31 + (b[2] + b[5] if b[2] - b[5] < 0.05 else 0.0)
+        elif kind == 1:     # at the near wall
+            st[i, 1] = (bx[i, 0, 1] - bx[i, 0, 4]) - rng.uniform(0.05, 0.3)
+        elif kind == 2:     # feet at an obstacle's front edge
+            st[i, 0] = b[0] - b[3] - rng.uniform(0.15, 0.3); st[i, 1] = rng.uniform(-0.2, 0.2)
+        else:               # next to the target
+            st[i, 0] = aux[i, 2] - rng.uniform(0.2, 0.8); st[i, 1] = rng.uniform(-0.2, 0.2); st[i, 2] = 0.35
+    cpu.set(capi.F_STATE, st)
+
+
+@pytest.mark.parametrize("element", [1, 2, 3])
+def test_epmc_terrain_policy_step_parity(element, built, blob, oracle_lib):
+    """Teacher-forced policy steps in the corridor arenas, friction capped at 1 (see the flat-arena test above for why)."""
+    n, steps = 1024, int(os.environ.get("LLQ_PARITY_STEPS", 12))
+    gpu, cpu = _terrain_pair(element, n, blob, oracle_lib, 7, max_steps=40, friction_hi=1.0, cmd_freq_lo=3, cmd_freq_hi=9)
+    gpu.reset(); cpu.reset()
+    rng = np.random.default_rng(3)
+    E, DD, reach = [], [], 0
+    for t in range(steps):
+        if t % 3 == 1:
+            _crowd_terrain(cpu, rng, n)
+        a = np.clip(MU_A + SIGMA_A * rng.standard_normal((n, 12)).astype(np.float32), -1, 1).astype(np.float32)
+        for f in (capi.F_STATE, capi.F_WARMSTART, capi.F_OBS, capi.F_TIME, capi.F_AUX, capi.F_EPISODE_ID, capi.F_REWARD_SUM):
+            gpu.set(f, cpu.get(f))
+        og, rg, dg = gpu.step(a); oc, rc, dc = cpu.step(a)
+        ag, ac = gpu.get(capi.F_AUX), cpu.get(capi.F_AUX)
+        assert np.array_equal(ag[:, T_EXACT], ac[:, T_EXACT])
+        e = np.maximum.reduce([blockrel(og[:, :135], oc[:, :135]), blockrel(og[:, 135:460], oc[:, 135:460]), blockrel(og[:, 460:588], oc[:, 460:588]),
+                               blockrel(og[:, 588:913], oc[:, 588:913]), blockrel(og[:, 913:], oc[:, 913:]),
+                               blockrel(gpu.get(capi.F_STATE), cpu.get(capi.F_STATE)), np.abs(rg - rc) / (1 + np.abs(rc))])
+        E.append(e); DD.append(dg != dc); reach += int((rc > 0.2).sum())
+        m = dc.astype(np.uint8)
+        if m.any():
+            cpu.reset(m); gpu.reset(m)
+    e, dd = np.concatenate(E), np.concatenate(DD)
+    bad = (e >= TOL) | dd
+    print("EPMC element %d teacher-forced: %d env-steps; rel err 50/99/99.9/max = %.1e %.1e %.1e %.1e; %d above 1e-4; %d done mismatches; %d reaches" % (
+        element, e.size, np.percentile(e, 50), np.percentile(e, 99), np.percentile(e, 99.9), e.max(), int((e >= TOL).sum()), int(dd.sum()), reach))
+    assert reach > 0 and bad.mean() <= 5e-3
+    gpu.close(); cpu.close()
+
+
+@pytest.mark.parametrize("element", [1, 2, 3])
+def test_cuda_replays_reference_epmc_terrain_golden(element, built, blob):
+    """The reference-generated corridor files through the CUDA engine's own reset()/step() path, robot state teacher-forced."""
+    g = terrain_gold(element)
+    eng = capi.VecEngine(capi.load_cuda_library(), 1, blob, None, seed=int(g["seed"]), **terrain_cfg(g))
+    eng.set_init_state(g["init_state"])
+    tp = {int(s): st for s, st in zip(g["tp_step"], g["tp_state"])}
+    step, worst = 0, 0.0
+    new = np.r_[66:99, 123:916]
+    for ep in range(len(g["reset_obs"])):
+        obs = eng.reset()
+        nb = int(eng.get(capi.F_NBOX)[0])
+        assert nb == int(g["nbox"][ep])
+        assert np.allclose(eng.get(capi.F_BOXES)[0].reshape(36, 6)[:nb], g["boxes"][ep][:nb], rtol=1e-6, atol=1e-6)
+        assert blockrel(obs, g["reset_obs"][ep][None]).max() < 1e-5
+        t = 0
+        while step < len(g["episode"]) and g["episode"][step] == ep:
+            if t > 0 or step in tp:
+                st = eng.get(capi.F_STATE); wm = eng.get(capi.F_WARMSTART)
+                if t > 0:
+                    st[0] = g["state"][step - 1]
+                if step in tp:
+                    st[0] = tp[step]; wm[0] = 0.0
+                eng.set(capi.F_STATE, st); eng.set(capi.F_WARMSTART, wm)
+            o, r, d = eng.step(g["action"][step][None])
+            e_new = max(blockrel(o[:, 66:99], g["obs"][step][None, 66:99]).max(), blockrel(o[:, 135:460], g["obs"][step][None, 135:460]).max(),
+                        blockrel(o[:, 460:588], g["obs"][step][None, 460:588]).max(), blockrel(o[:, 588:913], g["obs"][step][None, 588:913]).max(),
+                        blockrel(o[:, 913:], g["obs"][step][None, 913:]).max())
+            worst = max(worst, e_new)
+            assert e_new < 5e-3, ("obs", step, e_new)
+            assert abs(r[0] - g["reward"][step]) < 2e-4, ("reward", step, r[0], g["reward"][step])
+            assert bool(d[0]) == bool(g["done"][step]), ("done", step)
+            aux = eng.get(capi.F_AUX)[0]
+            assert np.array_equal(aux[T_EXACT], g["aux"][step][T_EXACT]), ("counters", step)
+            assert np.allclose(aux[[2, 3, 4, 13, 17]], g["aux"][step][[2, 3, 4, 13, 17]], rtol=1e-5, atol=1e-6)
+            step += 1; t += 1
+    assert step == len(g["episode"])
+    print("CUDA vs reference EPMC element %d golden (state teacher-forced): worst block-rel err %.1e" % (element, worst))
+    eng.close()
