@@ -30,14 +30,15 @@ UNROLL = 128                            # example_pmc_train.sh:145
 METRIC = {"pmc": "env-steps/sec PMC mocap-tracking", "epmc": "env-steps/sec EPMC playground (element 0, flat joystick arena)",
           "sepmc": "env-steps/sec SEPMC chase-tag game (one env = one pair of robots, shipped empty arena)"}
 WORKLOAD = {"pmc": "4096-env batched PMC mocap-tracking, flat ground, per GPU (BASELINE configs[1])",
-            "epmc": "8192-env batched EPMC playground, element_id 0 = flat joystick arena of example_epmc_train.sh (BASELINE configs[2] "
-                    "asks for box/heightfield terrain, which is not built yet), per GPU",
+            "epmc": "8192-env batched EPMC playground (BASELINE configs[2]), per GPU; --element 3 (default) = corridor with cube steps, 1 = hurdles, "
+                    "2 = bars, 0 = the flat joystick arena example_epmc_train.sh ships; the reference has box terrain, no heightfield",
             "sepmc": "2-agent SEPMC chase-tag game, 4096 env-pairs (8192 robots) per GPU, arena of example_sepmc_train.sh (BASELINE configs[4])"}
 # algorithmic bytes per env-step: PMC 157 words read + 262 written; EPMC without a terrain box list: 177 read + 991 written
 # SEPMC per pair-step: 2 robots x (182 words read + 1052 written: state, history, aux, the 965-wide observation)
 ALGO_BYTES = {"pmc": 1676, "epmc": 4672, "sepmc": 9872}
 OBS_W = {"pmc": 207, "epmc": 916, "sepmc": 965}
 ROBOTS_PER_ENV = {"pmc": 1, "epmc": 1, "sepmc": 2}
+ELEMENT = [3]
 
 
 def parse():
@@ -50,10 +51,12 @@ def parse():
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL trajectory gather to rank 0")
     ap.add_argument("--block", type=int, default=0, help="CUDA block size override (32/64/128)")
     ap.add_argument("--cpu-envs", type=int, default=256, help="CPU arm: environments per step (bounded sample)")
+    ap.add_argument("--element", type=int, default=3, help="EPMC element_id (0 flat joystick arena, 1 hurdles, 2 bars, 3 cubes)")
     ap.add_argument("--env", default="pmc", choices=["pmc", "epmc", "sepmc"],
                     help="pmc = BASELINE configs[1] (headline); epmc = configs[2] on the flat element-0 arena (8192 envs); "
                          "sepmc = configs[4] (4096 pairs; --envs counts robots)")
     a = ap.parse_args()
+    ELEMENT[0] = a.element
     if a.env in ("epmc", "sepmc") and a.envs == 4096:
         a.envs = 8192
     return a
@@ -118,7 +121,8 @@ def make_engine(lib_or_none, n, env, **over):
     blob, mocap = synthetic_inputs()
     if env == "epmc":
         from lifelike_agility_and_play_b200.sim_envs.playground_env import INIT_STATE_RUN_0, epmc_engine_config
-        erc = {'element_id': 0, 'friction_range': [0.4, 3.0], 'cmd_vary_freq_range': [9999, 10000], 'target_spd_range': [0.5, 3.0],
+        erc = {'element_id': ELEMENT[0], 'friction_range': [0.4, 3.0], 'cmd_vary_freq_range': [9999, 10000], 'target_spd_range': [0.5, 3.0],
+               'hole_config': {'min_gap_height': 0.25, 'max_gap_height': 0.25},
                'disturb_force_config': {'start_time': 0.5, 'interval_time': 1.0, 'duration_time': 0.2, 'horizontal_force': [0, 50], 'vertical_force': [0, 10]}}
         cfg = epmc_engine_config(50.0, 50.0, 0.5, 16, 1000, erc)       # train_scripts/example_epmc_train.sh:88-117
         cfg.update(over)
@@ -345,7 +349,7 @@ def main():
         "warmup": args.warmup, "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": WORKLOAD[args.env] + ("; sharded as in configs[3]" if world > 1 else ""),
-                   "envs_per_gpu": nu, "global_envs": nu * world, "robots_per_gpu": n, "substeps": 10, "solver_iters": 10,
+                   "element_id": args.element if args.env == "epmc" else None, "envs_per_gpu": nu, "global_envs": nu * world, "robots_per_gpu": n, "substeps": 10, "solver_iters": 10,
                    "mocap": "66 synthetic clips, 229k frames" if args.env == "pmc" else None,
                    "auto_reset": True, "prioritized_sample_factor": 3.0 if args.env == "pmc" else None,
                    "actions": "N(mu_a, sigma_a) clipped +-1, device resident",
@@ -359,7 +363,7 @@ def main():
                 "value_pageable_numpy_api": e2e_pageable * world},
         "gpu_launches": int(c1[4] - c0[4]),
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
-                     "kernel": "pmc_step_kernel<128,%d>" % {"pmc": 0, "epmc": 1, "sepmc": 2}[args.env], "kernel_ms": kern_ms,
+                     "kernel": "pmc_step_kernel<128,%d>" % {"pmc": 0, "epmc": 1 if args.element == 0 else 3, "sepmc": 2}[args.env], "kernel_ms": kern_ms,
                      "algorithmic_bytes_per_env_step": ALGO_BYTES[args.env],
                      "peak_source": peak_src,
                      "note": "latency/issue bound by design (SURVEY 7): ~2e5 flop per 1.7 kB; see profiles/"},

@@ -600,7 +600,14 @@ int llq_get_field(llq_handle h, int field, void* dst) {
     case LLQ_F_EPISODE_ID: CK(cudaMemcpy(dst, h->E.episode, sizeof(long long) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_OB_ID: CK(cudaMemcpy(dst, h->E.ob_id, sizeof(int) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_OBS: CK(cudaMemcpy(dst, h->E.obs, sizeof(float) * h->obs_dim * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
-    case LLQ_F_BOXES: CK(cudaMemcpy(dst, h->E.boxes, sizeof(float) * 6 * LLQ_MAX_BOXES * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
+    case LLQ_F_BOXES: {
+      std::vector<int> nb(n);
+      CK(cudaMemcpy(dst, h->E.boxes, sizeof(float) * 6 * LLQ_MAX_BOXES * n, cudaMemcpyDeviceToHost));
+      CK(cudaMemcpy(nb.data(), h->E.nbox, sizeof(int) * n, cudaMemcpyDeviceToHost));
+      for (size_t i = 0; i < n; i++)                      // rows past the env's box count hold stale boxes of earlier episodes
+        for (int b = nb[i]; b < LLQ_MAX_BOXES; b++) std::memset((float*)dst + (i * LLQ_MAX_BOXES + b) * 6, 0, 6 * sizeof(float));
+      return LLQ_OK;
+    }
     case LLQ_F_NBOX: CK(cudaMemcpy(dst, h->E.nbox, sizeof(int) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_AUX: {
       std::vector<double> tmp((size_t)LLQ_AUX_DIM * n);

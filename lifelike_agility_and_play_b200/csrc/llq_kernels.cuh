@@ -1911,7 +1911,8 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
         E.time[env] = 0.0; E.reward_sum[env] = 0.f; E.episode_steps[env] = 0; E.episode[env] = ep + 1;
         double* A = E.aux;
         A[env] = 0; A[N + env] = cmd_freq; A[2 * N + env] = tgx0; A[3 * N + env] = 0.0; A[6 * N + env] = fabs(tgx0); A[7 * N + env] = 0.0;
-        if (ENV == 3) { A[17 * N + env] = fabs(tgx0); E.nbox[env] = nb0; }
+        A[17 * N + env] = fabs(tgx0);                                  // init_pos_diff_len (PGE:192-195)
+        if (ENV == 3) E.nbox[env] = nb0;
         A[8 * N + env] = 0.0; A[9 * N + env] = P.push_start_count; A[10 * N + env] = pf[0]; A[11 * N + env] = pf[1]; A[12 * N + env] = pf[2];
         A[13 * N + env] = foot_mu; A[14 * N + env] = push_draws; A[15 * N + env] = 0; A[16 * N + env] = yaw_deg;
       }
