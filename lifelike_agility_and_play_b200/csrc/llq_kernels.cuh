@@ -62,6 +62,8 @@ struct StepParams {
   int has_ob; float ob_hx, ob_hy, ob_hz;
   // EPMC corridor (BSE)
   int element_id; float ww_lo, ww_hi, wg_lo, wg_hi, hg_lo, hg_hi;
+  // knee-wheel ground contact (llq_config.knee_contacts / link_friction)
+  int knee; float mu_wheel;
 };
 
 struct EnvArrays {      // SoA device arrays, N envs
@@ -762,7 +764,9 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     act[i] = actions[(size_t)env * kActDim + 3 * k + i];
     tgt[i] = clampf(q[i] + act[i], -3.0f, 3.0f);           // PLE:200, LR:126-127
   }
-  float warm = E.warm[k * N + env];
+  float warm = E.warm[k * N + env];               // remembered normal impulse of this leg's contact; negative: it is the knee wheel's
+  bool warm_wheel = warm < 0.f;
+  warm = fabsf(warm);
   double time = E.time[env];
   const int clip = ENV == 0 ? E.clip[env] : 0;
   int frame_id = 0; double frame_frac = 0.0;
@@ -1117,8 +1121,29 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
         if (d4 < dist) { dist = d4; plane = 4; }
       }
     }
+    // knee wheel vs ground (fp64 clearance like the foot); one contact per leg: the deeper of {foot, knee wheel}
+    bool onwheel = false;
+    V3 cb = fb;                                           // centre of the contact sphere, base coordinates
+    float crad = L.foot_r;
+    if (P.knee) {
+      const double qx = qp.x, qy = qp.y, qz = qp.z, qw = qp.w;
+      const double nx = 2.0 * (qx * qz - qy * qw), ny = 2.0 * (qy * qz + qx * qw), nz = 1.0 - 2.0 * (qx * qx + qy * qy);
+      const double dc1 = kc1, ds1 = ks1, dc2 = kc2, ds2 = ks2;
+      double x = M.wheel_off[k][0], y = M.wheel_off[k][1], z = M.wheel_off[k][2], t;
+      t = dc2 * x + ds2 * z; z = -ds2 * x + dc2 * z; x = t;            // Ry(theta2)
+      x += (double)r[1].x; y += (double)r[1].y; z += (double)r[1].z;
+      t = dc1 * y - ds1 * z; z = ds1 * y + dc1 * z; y = t;             // Rx(q1)
+      x += (double)r[0].x; y += (double)r[0].y; z += (double)r[0].z;
+      const float dw = (float)(pz + nx * x + ny * y + nz * z - (double)M.wheel_r[k]);
+      if (dw < dist) {
+        dist = dw; onwheel = true; plane = 0;
+        cb = p2 + rot<0>(rot<1>(ld3(M.wheel_off[k]), kc2, ks2), kc1, ks1);
+        crad = M.wheel_r[k];
+      }
+    }
     const bool contact = dist < P.breaking;
-    if (!contact) warm = 0.f;
+    if (!contact || warm_wheel != onwheel) warm = 0.f;   // another manifold point: no warm start
+    warm_wheel = contact && onwheel;
     // joint-limit rows (btMultiBodyJointLimitConstraint: a row exists only while the limit is violated)
     float limdir[3];
     unsigned mymask = contact ? 7u : 0u;   // bits 0-2: contact rows n,t1,t2 ; bits 3-5: limit rows of joints 0-2
@@ -1176,13 +1201,13 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           }
           dirs[0] = tmul(R, n); dirs[1] = tmul(R, t1); dirs[2] = tmul(R, t2);
         }
-        const V3 Pc = fb - L.foot_r * dirs[0];            // contact point on the sphere surface
+        const V3 Pc = cb - crad * dirs[0];                // contact point on the sphere surface
 #pragma unroll
         for (int d = 0; d < 3; d++) {
           const V3 db = dirs[d];
           V3 Ga = cross(Pc, db), Gl = db;                 // spatial force of a unit impulse, about the base origin
           const float rel0 = dot(Ga, wbs) + dot(Gl, vbs);
-          uc[d][2] = dot(Sa[2], Ga) + dot(Sl[2], Gl);
+          uc[d][2] = onwheel ? 0.f : dot(Sa[2], Ga) + dot(Sl[2], Gl);   // the wheel sits on the thigh: the shank joint does not move it
           const float j2 = dot(Sa[1], Ga) + dot(Sl[1], Gl), j1 = dot(Sa[0], Ga) + dot(Sl[0], Gl);
           const float rel = rel0 + j1 * qd[0] + j2 * qd[1] + uc[d][2] * qd[2];
           float g = uc[d][2] * Di[2];
@@ -1392,7 +1417,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
             if ((warpmask >> (6 * j)) & 1u) {
               const bool mine = (j == k) && contact;
               float sa = lam[1] + (rhs[1] - bq[1] * invd[1]), sb = lam[2] + (rhs[2] - bq[2] * invd[2]);
-              const float limit = mu * lam[0];
+              const float limit = (onwheel ? P.mu_wheel : mu) * lam[0];
               const float r2 = sa * sa + sb * sb;
               const bool clip = r2 >= limit * limit && r2 > 0.f;
               const float sc = clip ? limit * rsqrtf(r2) : 1.0f;
@@ -1541,7 +1566,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       E.kin[(13 + 3 * k + i) * N + env] = oc.kq[i];
       E.kin[(25 + 3 * k + i) * N + env] = oc.kqd[i];
     }
-    E.warm[k * N + env] = warm;
+    E.warm[k * N + env] = warm_wheel ? -warm : warm;
     E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
     if (k == 0) {
       E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
@@ -1604,7 +1629,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       float* sw = E.st;
 #pragma unroll
       for (int i = 0; i < 3; i++) { sw[(10 + 3 * k + i) * N + env] = q[i]; sw[(22 + 3 * k + i) * N + env] = qd[i]; }
-      E.warm[k * N + env] = warm;
+      E.warm[k * N + env] = warm_wheel ? -warm : warm;
       E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
       if (k == 0) {
         E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
@@ -1682,7 +1707,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       float* sw = E.st;
 #pragma unroll
       for (int i = 0; i < 3; i++) { sw[(10 + 3 * k + i) * N + env] = q[i]; sw[(22 + 3 * k + i) * N + env] = qd[i]; }
-      E.warm[k * N + env] = warm;
+      E.warm[k * N + env] = warm_wheel ? -warm : warm;
       E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
       if (k == 0) {
         E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;

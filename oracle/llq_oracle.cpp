@@ -250,7 +250,7 @@ struct Env {
   double kin[LLQ_STATE_DIM];
   double time; int clip; double reward_sum; int episode_steps; int64_t episode;
   int frame_id; double frame_frac;
-  double warm[8];
+  double warm[24];
   double prop_hist[3][LLQ_PROP_DIM]; double act_hist[3][LLQ_ACTION_DIM];
   double foot_pos[12];
   double margin;   // LLQ_F_DECISION_MARGIN
@@ -502,7 +502,7 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
 
   // (a) collision detection on pre-step poses: foot spheres vs plane z = 0
   struct Contact { int link, sphere; V3 P, n; double dist, mu; };
-  Contact contacts[8]; int nc = 0;
+  Contact contacts[24]; int nc = 0;
   // static half-spaces the feet can touch: the ground, plus (SEPMC) the inner faces of the four arena walls (BSG:863-902:
   // 5 x 0.01 x 2 boxes centred at +-2.5).  One contact per foot: the deepest half-space.
   const int n_planes = cf.env_kind == LLQ_ENV_SEPMC ? 5 : 1;
@@ -512,13 +512,13 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
     const SphereM& sp = md.spheres[s];
     V3 cw = k.pl[sp.link] + mul(k.Rl[sp.link], sp.c);
     double dist = 1e30; V3 nrm = pn[0];
-    for (int pi = 0; pi < n_planes; pi++) {
+    for (int pi = 0; pi < (s < 4 ? n_planes : 1); pi++) {       // knee wheels: ground only
       double dpi = dot(pn[pi], cw) - pd[pi] - sp.r;
       if (dpi < dist) { dist = dpi; nrm = pn[pi]; }
     }
     // EPMC corridor: sphere vs every static box (walls, hurdles, bars, cubes); still one contact per foot, the deepest.
     // The auxiliary edge cylinders (BSE:43-100) and every non-foot link are not collided.
-    for (int b = 0; b < e.n_boxes; b++) {
+    for (int b = 0; b < (s < 4 ? e.n_boxes : 0); b++) {
       const double* bx = e.boxes[b];
       const double p[3] = {cw.x - bx[0], cw.y - bx[1], cw.z - bx[2]};
       double c[3]; bool inside = true;
@@ -541,12 +541,27 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
     }
     e.margin = std::min(e.margin, std::fabs(dist - cf.contact_breaking));
     if (dist < cf.contact_breaking) {
-      contacts[nc++] = {sp.link, (int)s, cw - sp.r * nrm, nrm, dist, cf.ground_friction * e.foot_mu};
+      contacts[nc++] = {sp.link, (int)s, cw - sp.r * nrm, nrm, dist, cf.ground_friction * (s < 4 ? e.foot_mu : sp.mu)};
     } else {
       e.warm[s] = 0.0;  // manifold point removed
     }
   }
 
+  if (md.spheres.size() == 8) {
+    // one contact per leg: the deeper of {foot, knee wheel} (llq_config.knee_contacts)
+    Contact kept[24]; int nk = 0;
+    for (int leg = 0; leg < 4; leg++) {
+      int best = -1;
+      for (int ci = 0; ci < nc; ci++)
+        if (contacts[ci].sphere == leg || contacts[ci].sphere == 4 + leg)
+          if (best < 0 || contacts[ci].dist < contacts[best].dist) best = ci;
+      for (int ci = 0; ci < nc; ci++)
+        if ((contacts[ci].sphere == leg || contacts[ci].sphere == 4 + leg) && ci != best) e.warm[contacts[ci].sphere] = 0.0;
+      if (best >= 0) kept[nk++] = contacts[best];
+    }
+    nc = nk;
+    for (int ci = 0; ci < nc; ci++) contacts[ci] = kept[ci];
+  }
   // (b) joint damping (pybullet applyJointDamping) + motor torque, forward dynamics, velocity prediction
   double gv[MAXD], tt[16], acc[MAXD];
   for (int t = 0; t < 3; t++) { gv[t] = e.angv[t]; gv[3 + t] = e.linv[t]; }
@@ -779,7 +794,7 @@ void reset_env(llq_engine& E, Env& e, int clip, double sampled_time) {
   e.reward_sum = 0; e.episode_steps = 0;
   e.ob_id = 0;                                                                           // PLE:179
   e.foot_mu = E.cfg.foot_friction;
-  for (int s = 0; s < 8; s++) e.warm[s] = 0;
+  for (int s = 0; s < 24; s++) e.warm[s] = 0;
   double prop[LLQ_PROP_DIM];
   make_prop(e.kin, prop);
   for (int h = 0; h < 3; h++) {                                          // PLE:282-290
@@ -1086,7 +1101,7 @@ void epmc_reset(llq_engine& E, Env& e, int64_t gid) {   // PGE:196-249
   st[3] = qn.x; st[4] = qn.y; st[5] = qn.z; st[6] = qn.w;
   st[0] = 0.0; st[1] = 0.0; st[2] = 0.5;
   unpack_state(e, st);
-  for (int s = 0; s < 8; s++) e.warm[s] = 0;
+  for (int s = 0; s < 24; s++) e.warm[s] = 0;
   e.tgt_x = 8.0; e.tgt_y = 0.0; e.n_boxes = 0;                                           // BSE:247-248, PGE:219
   if (cf.element_id != 0) epmc_generate_terrain(E, e, gid);                               // PGE:216-219
   e.last_pos_diff_len = std::sqrt((st[0] - e.tgt_x) * (st[0] - e.tgt_x) + (st[1] - e.tgt_y) * (st[1] - e.tgt_y));
@@ -1401,7 +1416,7 @@ void sepmc_reset(llq_engine& E, Env& a, Env& b, int64_t gid) {   // CTG:261-304,
     st[0] = px[i]; st[1] = py[i]; st[2] = 0.5;
     unpack_state(e, st);
     e.yaw_accum_deg = yaw_acc;
-    for (int s = 0; s < 8; s++) e.warm[s] = 0;
+    for (int s = 0; s < 24; s++) e.warm[s] = 0;
     e.flag_x = -2.0 + 4.0 * u2[1]; e.flag_y = -2.0 + 4.0 * u2[2];                          // CTG:218-221
     double prop[LLQ_PROP_DIM];
     make_prop(st, prop);
@@ -1545,6 +1560,7 @@ int llq_default_config(llq_config* c) {
   c->target_spd_lo = 0.5; c->target_spd_hi = 3.0;
   c->element_id = 0; c->wall_width_lo = 0.02; c->wall_width_hi = 0.5; c->wall_gap_lo = 1.0; c->wall_gap_hi = 20.0;
   c->hole_gap_lo = 0.25; c->hole_gap_hi = 0.3;
+  c->knee_contacts = 1; c->reserved1 = 0; c->link_friction = 0.5;
   return LLQ_OK;
 }
 
@@ -1612,6 +1628,9 @@ int llq_load_model(llq_handle h, const double* b, int64_t n) {
     for (int i = 0; i < (int)b[LLQ_H_NPROXIES]; i++, pr += LLQ_PROXY)
       md.proxies.push_back({(int)pr[0], V3{pr[1], pr[2], pr[3]}, pr[4], (int)pr[5]});
   }
+  if (h->cfg.knee_contacts)     // knee wheels (proxy kind 1) collide with the ground too: spheres 4-7, in leg order
+    for (const ProxyM& p : md.proxies)
+      if (p.kind == 1 && md.spheres.size() < 8) md.spheres.push_back({p.link, p.c, p.r, h->cfg.link_friction});
   h->model = md;
   h->has_model = true;
   return LLQ_OK;
@@ -1774,7 +1793,9 @@ int llq_get_field(llq_handle h, int field, void* dst) {
       case LLQ_F_TIME: ((double*)dst)[i] = e.time; break;
       case LLQ_F_REWARD_SUM: ((float*)dst)[i] = (float)e.reward_sum; break;
       case LLQ_F_EPISODE_STEPS: ((int32_t*)dst)[i] = e.episode_steps; break;
-      case LLQ_F_WARMSTART: for (int t = 0; t < 4; t++) ((float*)dst)[(size_t)i * 4 + t] = (float)e.warm[t]; break;
+      case LLQ_F_WARMSTART:   // per leg: the remembered normal impulse, negative when it belongs to the knee-wheel contact
+        for (int t = 0; t < 4; t++) ((float*)dst)[(size_t)i * 4 + t] = e.warm[4 + t] > 0 ? -(float)e.warm[4 + t] : (float)e.warm[t];
+        break;
       case LLQ_F_OBS: std::memcpy((float*)dst + (size_t)i * h->obs_dim(), e.obs, sizeof(float) * h->obs_dim()); break;
       case LLQ_F_AUX: {
         double* a = (double*)dst + (size_t)i * LLQ_AUX_DIM;
@@ -1828,7 +1849,12 @@ int llq_set_field(llq_handle h, int field, const void* src) {
       case LLQ_F_TIME: e.time = ((const double*)src)[i]; if (h->has_mocap) motion_set_time(*h, e, e.time); break;
       case LLQ_F_REWARD_SUM: e.reward_sum = ((const float*)src)[i]; break;
       case LLQ_F_EPISODE_STEPS: e.episode_steps = ((const int32_t*)src)[i]; break;
-      case LLQ_F_WARMSTART: for (int t = 0; t < 4; t++) e.warm[t] = ((const float*)src)[(size_t)i * 4 + t]; break;
+      case LLQ_F_WARMSTART:
+        for (int t = 0; t < 4; t++) {
+          const float v = ((const float*)src)[(size_t)i * 4 + t];
+          e.warm[t] = v > 0 ? v : 0.0; e.warm[4 + t] = v < 0 ? -v : 0.0;
+        }
+        break;
       case LLQ_F_EPISODE_ID: e.episode = ((const int64_t*)src)[i]; break;
       case LLQ_F_OB_ID: e.ob_id = ((const int32_t*)src)[i]; break;
       case LLQ_F_AUX: {
@@ -1892,7 +1918,7 @@ int llq_oracle_get_state64(llq_handle h, int32_t env, double* st37) {
 int llq_oracle_set_state64(llq_handle h, int32_t env, const double* st37) {
   if (!h || !st37 || env < 0 || env >= h->cfg.n_envs) return fail(LLQ_EINVAL, "bad arguments");
   unpack_state(h->envs[env], st37);
-  for (int s = 0; s < 8; s++) h->envs[env].warm[s] = 0;   // resetBasePositionAndOrientation drops the contact cache
+  for (int s = 0; s < 24; s++) h->envs[env].warm[s] = 0;   // resetBasePositionAndOrientation drops the contact cache
   return LLQ_OK;
 }
 int llq_oracle_substep(llq_handle h, int32_t env, const double* tau12) {
