@@ -1,0 +1,34 @@
+"""Host reference of the PMC policy forward (lifelike_agility_and_play_b200/policy.py; pmc_net.py:33-58,99-178)."""
+import numpy as np
+
+from lifelike_agility_and_play_b200.policy import PmcPolicy
+
+SHAPES = [(1, 135), (1, 135), (1, 72), (1, 72), (207, 256), (256,), (256, 256), (256,), (256, 1), (1,), (207, 256), (256,), (256, 256), (256,),
+          (256, 32), (32,), (32, 256), (135, 64), (64,), (32, 32), (32,), (96, 256), (256,), (256, 256), (256,), (256, 12), (12,), (1, 12)]
+
+
+def random_weights(seed=0):
+    rng = np.random.default_rng(seed)
+    w = [(rng.standard_normal(s) / np.sqrt(s[0] if len(s) == 2 and s[0] > 1 else 1.0)).astype(np.float32) for s in SHAPES]
+    w[1] = np.abs(w[1]) + 0.1; w[3] = np.abs(w[3]) + 0.1        # running std > 0
+    return w
+
+
+def test_policy_forward_structure():
+    pol = PmcPolicy(random_weights())
+    rng = np.random.default_rng(1)
+    obs = rng.standard_normal((50, 207)).astype(np.float32) * 3
+    a, idx = pol.act(obs, return_code=True)
+    assert a.shape == (50, 12) and idx.shape == (50,) and idx.min() >= 0 and idx.max() < 256
+    p, f = pol.normalise(obs)
+    assert np.abs(p).max() <= 5.0 and np.abs(f).max() <= 5.0                         # pmc_net.py:133,136
+    z, idx2 = pol.encode(p, f)
+    d = ((z[:, :, None] - pol.codebook[None]) ** 2).sum(1)                            # brute-force nearest code
+    assert np.array_equal(idx2, d.argmin(1))
+    # the action only depends on the observation through (normalised prop, code): same prop + same code -> same action
+    obs2 = obs.copy(); obs2[:, 135:] += 1e-4
+    a2, idx3 = pol.act(obs2, return_code=True)
+    same = idx3 == idx
+    assert same.mean() > 0.8 and np.allclose(a2[same], a[same], atol=1e-5)
+    # batch independence
+    assert np.allclose(pol.act(obs[7:8]), a[7:8], atol=1e-5)
