@@ -1125,7 +1125,9 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     bool onwheel = false;
     V3 cb = fb;                                           // centre of the contact sphere, base coordinates
     float crad = L.foot_r;
-    if (P.knee) {
+    const V3 wheel_b = p2 + rot<0>(rot<1>(ld3(M.wheel_off[k]), kc2, ks2), kc1, ks1);
+    // cheap fp32 screen first: the fp64 clearance is only needed when the wheel is within 1 cm of becoming the leg's contact
+    if (P.knee && (float)pz + dot(nb, wheel_b) - M.wheel_r[k] < fmaxf(dist, P.breaking) + 0.01f) {
       const double qx = qp.x, qy = qp.y, qz = qp.z, qw = qp.w;
       const double nx = 2.0 * (qx * qz - qy * qw), ny = 2.0 * (qy * qz + qx * qw), nz = 1.0 - 2.0 * (qx * qx + qy * qy);
       const double dc1 = kc1, ds1 = ks1, dc2 = kc2, ds2 = ks2;
@@ -1137,7 +1139,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       const float dw = (float)(pz + nx * x + ny * y + nz * z - (double)M.wheel_r[k]);
       if (dw < dist) {
         dist = dw; onwheel = true; plane = 0;
-        cb = p2 + rot<0>(rot<1>(ld3(M.wheel_off[k]), kc2, ks2), kc1, ks1);
+        cb = wheel_b;
         crad = M.wheel_r[k];
       }
     }
