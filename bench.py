@@ -326,6 +326,46 @@ def main():
         dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_val = nu * world * e2e_steps / float(e2e_t.item())
 
+    # row f2: the whole actor loop on the device -- policy forward (csrc/llq_policy.cu, random weights of the shipped architecture)
+    # reads the observation rows in place, writes the actions the next fused step consumes; no host round trip
+    actor = None
+    if args.env == "pmc" and world == 1:
+        from lifelike_agility_and_play_b200.policy import DevicePolicy
+        prng = np.random.default_rng(42)
+        shapes = [(1, 135), (1, 135), (1, 72), (1, 72), (207, 256), (256,), (256, 256), (256,), (256, 1), (1,), (207, 256), (256,), (256, 256), (256,),
+                  (256, 32), (32,), (32, 256), (135, 64), (64,), (32, 32), (32,), (96, 256), (256,), (256, 256), (256,), (256, 12), (12,), (1, 12)]
+        wts = [(prng.standard_normal(sh) / np.sqrt(sh[0] if len(sh) == 2 and sh[0] > 1 else 1.0)).astype(np.float32) for sh in shapes]
+        wts[1] = np.abs(wts[1]) + 0.5; wts[3] = np.abs(wts[3]) + 0.5
+        wts[25] *= 0.05                                        # small actions, like a trained policy's
+        pol = DevicePolicy(wts, device=local_rank)
+        obs_t = torch.zeros((n, ow), device=dev, dtype=torch.float32)
+        act_t = torch.zeros((n, 12), device=dev, dtype=torch.float32)
+        eng.step_device(pool[0].data_ptr(), obs_t.data_ptr(), reward.data_ptr(), done.data_ptr(), obs_ld=ow, stream=stream)
+
+        def actor_step():
+            pol.forward(obs_t.data_ptr(), ow, n, act_t.data_ptr(), None, stream)
+            eng.step_device(act_t.data_ptr(), obs_t.data_ptr(), reward.data_ptr(), done.data_ptr(), obs_ld=ow, stream=stream)
+        for i in range(8):
+            actor_step()
+        torch.cuda.synchronize()
+        a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a0.record()
+        for i in range(args.steps):
+            actor_step()
+        a1.record()
+        torch.cuda.synchronize()
+        actor_ms = a0.elapsed_time(a1)
+        p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        p0.record()
+        for i in range(64):
+            pol.forward(obs_t.data_ptr(), ow, n, act_t.data_ptr(), None, stream)
+        p1.record()
+        torch.cuda.synchronize()
+        actor = {"value": nu * args.steps / (actor_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": actor_ms / args.steps,
+                 "policy_kernel_ms": p0.elapsed_time(p1) / 64, "policy": "PMC net 207-256-256-32 VQ(256) + 135/32-96-256-256-12, fp32, random weights",
+                 "note": "policy forward + fused env step, observations and actions stay in HBM (hot L2, no flush)"}
+        pol.close()
+
     if rank != 0:
         if world > 1:
             dist.destroy_process_group()
@@ -369,6 +409,8 @@ def main():
                      "note": "latency/issue bound by design (SURVEY 7): ~2e5 flop per 1.7 kB; see profiles/"},
         "clocks": sampler.summary(),
     }
+    if actor is not None:
+        line["on_device_actor_loop"] = actor
     if world == 1:
         cval, cdt, cores = time_cpu_arm(args.cpu_envs, 24, 2, env=args.env)
         line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": cores, "kind": "port",

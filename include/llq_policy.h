@@ -1,0 +1,40 @@
+/* llq_policy.h -- C ABI of the on-device PMC policy forward.
+ *
+ * Replaces, for the batched actor loop, the TensorFlow graph of the reference's primitive-level policy evaluated once per
+ * env step in `PGAgent.step(obs, argmax=True)` (test_scripts/primitive_level/test_primitive_level_env.py:75-88):
+ *   networks/legged_robot/pmc_net/pmc_net.py:33-58   vq_encoder / decoder (fully connected, ReLU)
+ *   networks/legged_robot/pmc_net/pmc_net.py:99-114  llc: prop 135 -> 64, z 32 -> 32, concat -> 256 -> 256 -> 12 (mean)
+ *   networks/legged_robot/pmc_net/pmc_net.py:130-137 running-mean normalisation, clip to +-5 (networks/layers.py:55)
+ *   networks/legged_robot/pmc_net/pmc_net.py:155-171 nearest code of the 32 x 256 codebook
+ * The observation rows are read in place from the engine's device buffer (or a trajectory slab: `obs_ld` floats per row) and
+ * the 12 actions per env are written to device memory that llq_step_ex(LLQ_IO_DEVICE) consumes: no host round trip.
+ *
+ * `weights`: the 24 arrays the policy path uses, fp32, concatenated in this order (numbers = index in a shipped *.model):
+ *   prop_mean[135] (0) prop_std[135] (1) future_mean[72] (2) future_std[72] (3)
+ *   enc W1[207x256] b1[256] W2[256x256] b2[256] W3[256x32] b3[32] (10-15)   codebook[32x256] (16)
+ *   prop_embed W[135x64] b[64] (17-18)   z_embed W[32x32] b[32] (19-20)
+ *   dec W1[96x256] b1[256] W2[256x256] b2[256] W3[256x12] b3[12] (21-26)
+ * All matrices row major [in][out] as TensorFlow stores them. */
+#ifndef LLQ_POLICY_H
+#define LLQ_POLICY_H
+#include <stdint.h>
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LLQ_POLICY_N_WEIGHTS 239338   /* total floats of the list above */
+
+typedef struct llq_policy* llq_policy_handle;
+
+/* Uploads the weights to `device`.  Returns 0 or a negative LLQ_E* code (llq.h); message via llq_policy_last_error(). */
+int llq_policy_create(const float* weights, int64_t n_weights, int32_t device, llq_policy_handle* out);
+int llq_policy_destroy(llq_policy_handle h);
+/* actions[n,12] = mean action for obs[n, >=207] (device pointers; obs_ld = row stride in floats); `codes` (int32[n], device,
+ * nullable) receives the selected codebook index.  Asynchronous on `stream` (a cudaStream_t, 0 = the default stream). */
+int llq_policy_forward(llq_policy_handle h, const float* d_obs, int64_t obs_ld, int32_t n, float* d_actions, int32_t* d_codes, void* stream);
+const char* llq_policy_last_error(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

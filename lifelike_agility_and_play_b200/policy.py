@@ -47,3 +47,56 @@ class PmcPolicy:
         x = np.maximum(x @ self.dec[1][0] + self.dec[1][1], 0.0)
         a = x @ self.dec[2][0] + self.dec[2][1]
         return (a, idx) if return_code else a
+
+
+# ------------------------------------------------------------------------------------------------------------------------
+# device side (include/llq_policy.h, csrc/llq_policy.cu)
+import ctypes as _C
+import os as _os
+
+POLICY_LIB_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "csrc", "libllq_policy.so")
+POLICY_EXPORTS = ["llq_policy_create", "llq_policy_destroy", "llq_policy_forward", "llq_policy_last_error"]
+_ORDER = [0, 1, 2, 3, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26]     # arrays of a *.model file the actor path uses
+
+
+def pack_weights(weights):
+    """The blob llq_policy_create() expects (order documented in include/llq_policy.h) from the 28 arrays of a model file."""
+    blob = np.concatenate([np.asarray(weights[i], dtype=np.float32).reshape(-1) for i in _ORDER])
+    assert blob.size == 239338
+    return np.ascontiguousarray(blob)
+
+
+class DevicePolicy:
+    """ctypes binding of the CUDA policy forward.  No CPU fallback: construction fails without the library or a GPU."""
+
+    def __init__(self, weights, device=0):
+        if not _os.path.exists(POLICY_LIB_PATH):
+            raise OSError("%s is missing: run `python __graft_entry__.py` (nvcc) first" % POLICY_LIB_PATH)
+        self._lib = _C.CDLL(POLICY_LIB_PATH)
+        L = self._lib
+        L.llq_policy_create.argtypes = [_C.c_void_p, _C.c_int64, _C.c_int32, _C.POINTER(_C.c_void_p)]
+        L.llq_policy_forward.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_int64, _C.c_int32, _C.c_void_p, _C.c_void_p, _C.c_void_p]
+        L.llq_policy_destroy.argtypes = [_C.c_void_p]
+        L.llq_policy_last_error.restype = _C.c_char_p
+        blob = pack_weights(weights)
+        self._h = _C.c_void_p()
+        rc = L.llq_policy_create(blob.ctypes.data_as(_C.c_void_p), blob.size, device, _C.byref(self._h))
+        if rc != 0:
+            raise RuntimeError("llq_policy_create failed (%d): %s" % (rc, (L.llq_policy_last_error() or b"").decode()))
+
+    def forward(self, obs_ptr, obs_ld, n, actions_ptr, codes_ptr=None, stream=None):
+        """Device pointers (ints); asynchronous on `stream`."""
+        rc = self._lib.llq_policy_forward(self._h, obs_ptr, obs_ld, n, actions_ptr, codes_ptr, stream)
+        if rc != 0:
+            raise RuntimeError("llq_policy_forward failed (%d): %s" % (rc, (self._lib.llq_policy_last_error() or b"").decode()))
+
+    def close(self):
+        if getattr(self, "_h", None):
+            self._lib.llq_policy_destroy(self._h)
+            self._h = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass

@@ -32,3 +32,48 @@ def test_policy_forward_structure():
     assert same.mean() > 0.8 and np.allclose(a2[same], a[same], atol=1e-5)
     # batch independence
     assert np.allclose(pol.act(obs[7:8]), a[7:8], atol=1e-5)
+
+
+def test_policy_library_exports():
+    import ctypes
+    import os
+    from lifelike_agility_and_play_b200 import policy
+    import __graft_entry__
+    __graft_entry__.build()
+    assert os.path.exists(policy.POLICY_LIB_PATH)
+    lib = ctypes.CDLL(policy.POLICY_LIB_PATH)
+    for name in policy.POLICY_EXPORTS:
+        assert hasattr(lib, name), name
+    assert policy.pack_weights(random_weights()).size == 239338
+    hdr = open(os.path.join(os.path.dirname(policy.POLICY_LIB_PATH), "..", "..", "include", "llq_policy.h")).read()
+    for name in policy.POLICY_EXPORTS:
+        assert name + "(" in hdr
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+def test_device_policy_matches_host_forward():
+    """CUDA forward vs the numpy restatement on random weights and observations: same code for (almost) every row, actions
+    within 1e-4 relative where the code agrees (a different nearest code is only possible at fp32 ties of the distance)."""
+    import torch
+    from lifelike_agility_and_play_b200.policy import DevicePolicy
+    w = random_weights(3)
+    host = PmcPolicy(w)
+    dev = DevicePolicy(w, device=0)
+    rng = np.random.default_rng(5)
+    for n, ld in ((4096, 223), (77, 207), (1, 207)):
+        obs = (2.0 * rng.standard_normal((n, ld))).astype(np.float32)
+        t_obs = torch.from_numpy(obs).cuda()
+        t_act = torch.zeros((n, 12), device="cuda", dtype=torch.float32)
+        t_code = torch.zeros((n,), device="cuda", dtype=torch.int32)
+        dev.forward(t_obs.data_ptr(), ld, n, t_act.data_ptr(), t_code.data_ptr(), None)
+        torch.cuda.synchronize()
+        a_ref, c_ref = host.act(obs[:, :207], return_code=True)
+        code = t_code.cpu().numpy(); act = t_act.cpu().numpy()
+        same = code == c_ref
+        assert same.mean() > 0.99, same.mean()
+        err = np.abs(act[same] - a_ref[same]).max() / (1.0 + np.abs(a_ref).max())
+        assert err < 1e-4, err
+    dev.close()

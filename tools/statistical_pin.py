@@ -37,6 +37,7 @@ def main():
     ap.add_argument("--data", default="/root/reference/data/mocap_data")
     ap.add_argument("--obstacle", type=int, default=0)
     ap.add_argument("--out", default="")
+    ap.add_argument("--cfg", default="{}", help="python dict of llq_config overrides, e.g. \"{'contact_erp': 0.2}\"")
     a = ap.parse_args()
     pol = PmcPolicy(load(a.model).model)
     mocap = load_mocap(a.data)
@@ -46,7 +47,7 @@ def main():
     else:
         lib = capi.load_cuda_library()
     eng = capi.VecEngine(lib, a.envs, load_model_blob(), mocap, seed=2024, auto_reset=0, kp=50.0, kd=0.5, max_tau=18.0,
-                         prioritized_sample_factor=0.0)
+                         prioritized_sample_factor=0.0, **eval(a.cfg))
     if a.obstacle:
         eng.load_obstacles(mocap, 0.2)
     obs = eng.reset()
