@@ -35,9 +35,27 @@ __device__ __forceinline__ void dense(const float* in, int K, const float* __res
     const float bj = b[j];
 #pragma unroll
     for (int m = 0; m < M; m++) acc[m] = bj;
-#pragma unroll 4
-    for (int k = 0; k < K; k++) {
-      const float w = W[(size_t)k * nout + j];
+    // the weights come from L2 (~300 cycles): keep PF of them in flight per thread
+    constexpr int PF = 16;
+    int k0 = 0;
+    for (; k0 + PF <= K; k0 += PF) {
+      float wv[PF];
+#pragma unroll
+      for (int t = 0; t < PF; t++) wv[t] = __ldg(W + (size_t)(k0 + t) * nout + j);
+#pragma unroll
+      for (int t = 0; t < PF; t++) {
+        const float w = wv[t];
+        const float4* a4 = reinterpret_cast<const float4*>(in + (k0 + t) * M);
+#pragma unroll
+        for (int m4 = 0; m4 < M / 4; m4++) {
+          const float4 a = a4[m4];
+          acc[4 * m4] = fmaf(a.x, w, acc[4 * m4]); acc[4 * m4 + 1] = fmaf(a.y, w, acc[4 * m4 + 1]);
+          acc[4 * m4 + 2] = fmaf(a.z, w, acc[4 * m4 + 2]); acc[4 * m4 + 3] = fmaf(a.w, w, acc[4 * m4 + 3]);
+        }
+      }
+    }
+    for (int k = k0; k < K; k++) {
+      const float w = __ldg(W + (size_t)k * nout + j);
       const float4* a4 = reinterpret_cast<const float4*>(in + k * M);
 #pragma unroll
       for (int m4 = 0; m4 < M / 4; m4++) {
