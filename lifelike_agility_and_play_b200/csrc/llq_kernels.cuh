@@ -308,6 +308,23 @@ LLQ_DI float ray_box1(V3 o, V3 d, V3 lo, V3 hi, float best) {
   if (hit && entered && (best < 0.f || t0 < best)) best = t0;
   return best;
 }
+// Fast paths of ray_arena for origins inside the arena (|x|, |y| < 2.49): the four walls are then hit on their inner faces, the
+// first one crossed is always a valid hit of that face in xy, so only its z range needs checking; same slab arithmetic.
+LLQ_DI float ray_arena_inside(V3 o, V3 d, float fx, float fy) {
+  float best = -1.f;
+  if (d.z < 0.f && o.z > 0.f) {                                    // ground slab top
+    const float t = (0.f - o.z) * (1.0f / d.z);
+    if (t <= 1.f) best = t;
+  }
+  float tw = 2.f; 
+  if (d.x != 0.f) { const float t = ((d.x > 0.f ? kWallIn : -kWallIn) - o.x) * (1.0f / d.x); tw = t; }
+  if (d.y != 0.f) { const float t = ((d.y > 0.f ? kWallIn : -kWallIn) - o.y) * (1.0f / d.y); tw = fminf(tw, t); }
+  if (tw <= 1.f) {
+    const float z = fmaf(tw, d.z, o.z);
+    if (z >= 0.f && z <= 2.f && (best < 0.f || tw < best)) best = tw;
+  }
+  return ray_box1(o, d, V3{fx - 0.05f, fy - 0.05f, 0.f}, V3{fx + 0.05f, fy + 0.05f, 0.5f}, best);
+}
 LLQ_DI float ray_arena(V3 o, V3 d, float fx, float fy) {
   float b = -1.f;
   b = ray_box1(o, d, V3{-100.f, -100.f, -10.f}, V3{100.f, 100.f, 0.f}, b);
@@ -662,22 +679,30 @@ LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const floa
           const int t = j - 135, a = t / 13, b = t - a * 13;
           const float gx = a == 24 ? 1.2f : -1.2f + (float)a * (2.4f / 24.0f), gy = b == 12 ? 0.6f : -0.6f + (float)b * (1.2f / 12.0f);
           const float x = fmaf(sn[45], gx, fmaf(sn[46], gy, pos.x)), y = fmaf(sn[48], gx, fmaf(sn[49], gy, pos.y));
-          const float f = ray_arena(V3{x, y, 10.f}, V3{0.f, 0.f, -20.f}, fx, fy);
-          v = f < 0.f ? 0.f : fmaf(f, -20.f, 10.f);
-          if (f >= 0.f && fabsf(v) < 2e-6f) v = 0.f;                     // the slab top is exactly z = 0
+          // a vertical ray sees the highest top among the boxes whose footprint holds (x, y): flag 0.5, walls 2, ground 0
+          const bool in_x = fabsf(x) <= 2.5f, in_y = fabsf(y) <= 2.5f;
+          const bool wall = (in_x && fabsf(fabsf(y) - 2.5f) <= 0.005f) || (in_y && fabsf(fabsf(x) - 2.5f) <= 0.005f);
+          const bool flag = fabsf(x - fx) <= 0.05f && fabsf(y - fy) <= 0.05f;
+          v = wall ? 2.0f : (flag ? 0.5f : 0.0f);
+          if (!(fabsf(x) < 99.f && fabsf(y) < 99.f)) {                    // off the slab: the general test decides
+            const float f = ray_arena(V3{x, y, 10.f}, V3{0.f, 0.f, -20.f}, fx, fy);
+            v = f < 0.f ? 0.f : fmaf(f, -20.f, 10.f);
+          }
         } else if (j < 588) {                      // percept_1d: 128 horizontal rays of 20 m; a miss reports |ray_from|
           const float ang = sn[59] + 6.283185307179586f * (float)(j - 460) * (1.0f / 128.0f);
           float sa, ca;
           sincosf(ang, &sa, &ca);
           const V3 d = V3{20.f * ca, 20.f * sa, 0.f};
-          const float f = ray_arena(pos, d, fx, fy);
+          const bool inside = fabsf(pos.x) < 2.49f && fabsf(pos.y) < 2.49f;
+          const float f = inside ? ray_arena_inside(pos, d, fx, fy) : ray_arena(pos, d, fx, fy);
           v = f < 0.f ? norm3(pos) : f * 20.f * sqrtf(ca * ca + sa * sa);
         } else if (j < 913) {                      // percept_front: 25 x 13 rays of 3 m along body +x; a miss reports 3
           const int t = j - 588, a = t / 13, b = t - a * 13;
           const float y = a == 24 ? 0.25f : -0.25f + (float)a * (0.5f / 24.0f), z = b == 12 ? 0.1f : -0.3f + (float)b * (0.4f / 12.0f);
           const V3 from = V3{fmaf(sn[46], y, fmaf(sn[47], z, pos.x)), fmaf(sn[49], y, fmaf(sn[50], z, pos.y)), fmaf(sn[52], y, fmaf(sn[53], z, pos.z))};
           const V3 d = V3{3.f * sn[45], 3.f * sn[48], 3.f * sn[51]};
-          const float f = ray_arena(from, d, fx, fy);
+          const bool inside = fabsf(from.x) < 2.49f && fabsf(from.y) < 2.49f && from.z > 0.f;
+          const float f = inside ? ray_arena_inside(from, d, fx, fy) : ray_arena(from, d, fx, fy);
           v = (f < 0.f ? 1.f : f) * norm3(d);
         } else {
           v = sn[62 + (j - 913)];

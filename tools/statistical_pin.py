@@ -48,8 +48,10 @@ def main():
         lib = capi.load_cuda_library()
     eng = capi.VecEngine(lib, a.envs, load_model_blob(), mocap, seed=2024, auto_reset=0, kp=50.0, kd=0.5, max_tau=18.0,
                          prioritized_sample_factor=0.0, **eval(a.cfg))
-    if a.obstacle:
-        eng.load_obstacles(mocap, 0.2)
+    if a.obstacle:            # set_obstacle=True, obstacle_height=0.2 of test_primitive_level_env.py:32-33 (plate half extents PLE:184)
+        from lifelike_agility_and_play_b200.mocap import obstacle_table
+        tab, offs = obstacle_table(mocap)
+        eng.load_obstacles(tab, offs, (0.025, 0.5, 0.2))
     obs = eng.reset()
     n = a.envs
     rew_sum, steps_alive = np.zeros(n), np.zeros(n, int)
