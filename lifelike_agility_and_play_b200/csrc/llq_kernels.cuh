@@ -323,6 +323,9 @@ LLQ_DI float ray_arena_inside(V3 o, V3 d, float fx, float fy) {
     const float z = fmaf(tw, d.z, o.z);
     if (z >= 0.f && z <= 2.f && (best < 0.f || tw < best)) best = tw;
   }
+  // the flag is a 0.1 m column: only rays whose line passes within its circumscribed radius (in xy) need the slab test
+  const float cx = fx - o.x, cy = fy - o.y, cr = d.x * cy - d.y * cx;
+  if (cr * cr > 0.00501f * (d.x * d.x + d.y * d.y)) return best;
   return ray_box1(o, d, V3{fx - 0.05f, fy - 0.05f, 0.f}, V3{fx + 0.05f, fy + 0.05f, 0.5f}, best);
 }
 LLQ_DI float ray_arena(V3 o, V3 d, float fx, float fy) {
