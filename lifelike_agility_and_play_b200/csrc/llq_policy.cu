@@ -3,7 +3,9 @@
 // One CTA (256 threads) owns a tile of M = 32 observation rows.  Activations live in shared memory, transposed
 // ([feature][row], so one float4 load hands a thread four rows of the same feature); the weights (0.96 MB fp32 in total)
 // stream through L2, coalesced: in a layer with `nout` outputs thread j < nout owns output neuron j for all 32 rows
-// (32 fp32 accumulators), i.e. per input feature one weight load, eight LDS.128 and 32 FFMA.  At 4096 envs that is one
+// (32 fp32 accumulators), i.e. per input feature one weight load, eight LDS.128 and 32 FFMA.  Two register-tiled variants
+// (4 rows x 8 outputs per thread; two neurons x 32 rows on 128 threads) measured slower on B200 (0.21 / 0.25 ms against
+// 0.137 ms at 4096 rows): with one 92 KB CTA per SM the kernel lives on latency hiding across its 8 warps, not on LSU economy.  At 4096 envs that is one
 // wave of 128 CTAs, 2.1 GFLOP per launch in fp32 -- the actions feed the physics, so the layers stay in fp32 rather than
 // TF32 tensor-core arithmetic (next step: 3xTF32 on tcgen05).
 #include <cuda_runtime.h>
@@ -183,12 +185,23 @@ int llq_policy_create(const float* weights, int64_t n_weights, int32_t device, l
   if (!h) return fail(LLQ_ENOMEM, "out of memory");
   h->device = device;
   cudaSetDevice(device);
-  if (cudaMalloc(&h->d_w, sizeof(float) * n_weights) != cudaSuccess) { delete h; return fail(LLQ_ECUDA, "cudaMalloc failed"); }
-  if (cudaMemcpy(h->d_w, weights, sizeof(float) * n_weights, cudaMemcpyHostToDevice) != cudaSuccess) {
-    cudaFree(h->d_w); delete h; return fail(LLQ_ECUDA, "weight upload failed");
+  // device copy with every array padded to a 16-byte boundary (the tiled layers read the weights as float4)
+  const size_t sizes[21] = {N_PROP, N_PROP, N_FUT, N_FUT, (size_t)N_OBS * H, H, (size_t)H * H, H, (size_t)H * Z, Z, (size_t)Z * NCODE,
+                            (size_t)N_PROP * PE, PE, (size_t)Z * ZE, ZE, (size_t)(PE + ZE) * H, H, (size_t)H * H, H, (size_t)H * NACT, NACT};
+  size_t off[22]; off[0] = 0;
+  for (int i = 0; i < 21; i++) off[i + 1] = off[i] + ((sizes[i] + 3) & ~(size_t)3);
+  if (cudaMalloc(&h->d_w, sizeof(float) * off[21]) != cudaSuccess) { delete h; return fail(LLQ_ECUDA, "cudaMalloc failed"); }
+  {
+    const float* src = weights;
+    for (int i = 0; i < 21; i++) {
+      if (cudaMemcpy(h->d_w + off[i], src, sizeof(float) * sizes[i], cudaMemcpyHostToDevice) != cudaSuccess) {
+        cudaFree(h->d_w); delete h; return fail(LLQ_ECUDA, "weight upload failed");
+      }
+      src += sizes[i];
+    }
   }
-  const float* p = h->d_w;
-  auto take = [&p](size_t n) { const float* q = p; p += n; return q; };
+  int ai = 0;
+  auto take = [&](size_t) { return (const float*)(h->d_w + off[ai++]); };
   Weights& w = h->w;
   w.prop_mean = take(N_PROP); w.prop_std = take(N_PROP); w.fut_mean = take(N_FUT); w.fut_std = take(N_FUT);
   w.e1w = take(N_OBS * H); w.e1b = take(H); w.e2w = take(H * H); w.e2b = take(H); w.e3w = take(H * Z); w.e3b = take(Z);
