@@ -1,0 +1,60 @@
+"""On-device actor loop producing learner-ready unrolls (rows f2 + f3 joined to the hot path).
+
+Replaces, for one GPU's block of environments, the reference actor's per-env loop `obs -> agent.step -> env.step -> queue`
+(learning/actors/distill_actor.py:205-270) and its unroll assembly (`:120-167`): the policy kernel (csrc/llq_policy.cu) reads
+observation row t of the trajectory slab in place, the fused env step (llq_step_ex, LLQ_IO_DEVICE) consumes its actions and
+writes the *next* observation straight into row t+1 of the slab, so record t = (obs_t, a_t, r_t, done_t) is aligned the way
+`PMCInputs` wants it (X = the observation the action was computed from) without any staging copy.  Nothing synchronises with
+the host inside an unroll.  Two slabs ping-pong: `finish_unroll()` hands back the `[T, N, 223]` view of the finished one (it stays
+valid for the whole next unroll, so the NCCL gather / unroll conversion overlaps the stepping) and carries observation T over
+to row 0 of the other.
+"""
+import torch
+
+from .trajectory import ACT_DIM, COL_ACTION, COL_DONE, COL_REWARD, OBS_DIM, TRAJ_WIDTH
+
+
+class RolloutWorker:
+    def __init__(self, engine, policy, unroll, device):
+        """`engine`: a `_capi.VecEngine` on the CUDA library with auto_reset=1 (PMC, 207-wide observations);
+        `policy`: a `policy.DevicePolicy` on the same device; `unroll`: T (128 in example_pmc_train.sh:145)."""
+        if engine.obs_dim != OBS_DIM:
+            raise ValueError("RolloutWorker drives the PMC env (207-wide observations)")
+        self.eng, self.pol, self.T, self.n = engine, policy, int(unroll), engine.n
+        self.dev = torch.device(device)
+        self.bufs = [torch.zeros((self.T + 1, self.n, TRAJ_WIDTH), dtype=torch.float32, device=self.dev) for _ in range(2)]
+        self.buf = self.bufs[0]
+        self.act = torch.zeros((self.n, ACT_DIM), dtype=torch.float32, device=self.dev)
+        self.rew = torch.zeros((self.n,), dtype=torch.float32, device=self.dev)
+        self.done = torch.zeros((self.n,), dtype=torch.uint8, device=self.dev)
+        self.t = 0
+        self.launches = 0
+
+    def start(self, first_obs):
+        """`first_obs` [N, 207] (host or device): the observation `engine.reset()` returned."""
+        self.buf[0, :, :OBS_DIM] = torch.as_tensor(first_obs, dtype=torch.float32).to(self.dev)
+        self.t = 0
+
+    def step(self):
+        """One policy forward + one fused env step; fills record t.  Asynchronous on torch's current stream (the kernels
+        are launched on it so that they order with the column copies below)."""
+        assert self.t < self.T, "unroll is full: call finish_unroll()"
+        s = torch.cuda.current_stream(self.dev).cuda_stream
+        row, nxt = self.buf[self.t], self.buf[self.t + 1]
+        self.pol.forward(row.data_ptr(), TRAJ_WIDTH, self.n, self.act.data_ptr(), None, s)
+        self.eng.step_device(self.act.data_ptr(), nxt.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(), obs_ld=TRAJ_WIDTH, stream=s)
+        row[:, COL_ACTION:COL_ACTION + ACT_DIM] = self.act
+        row[:, COL_REWARD] = self.rew
+        row[:, COL_DONE] = self.done
+        self.t += 1
+        self.launches += 3            # policy, step, reset kernels (the three column copies are torch's)
+
+    def finish_unroll(self):
+        """Copy-free `[T, N, 223]` view of the finished records, valid until the end of the NEXT unroll; stepping continues
+        in the other slab, whose row 0 receives observation T."""
+        assert self.t == self.T
+        done_buf = self.buf
+        self.buf = self.bufs[1] if done_buf is self.bufs[0] else self.bufs[0]
+        self.buf[0, :, :OBS_DIM] = done_buf[self.T, :, :OBS_DIM]
+        self.t = 0
+        return done_buf[:self.T]
