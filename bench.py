@@ -50,7 +50,7 @@ def parse():
     ap.add_argument("--envs", type=int, default=4096, help="environments per GPU (BASELINE configs[1]: 4096)")
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the NCCL trajectory gather to rank 0")
     ap.add_argument("--block", type=int, default=0, help="CUDA block size override (32/64/128)")
-    ap.add_argument("--cpu-envs", type=int, default=256, help="CPU arm: environments per step (bounded sample)")
+    ap.add_argument("--cpu-envs", type=int, default=4096, help="CPU arm: environments per step (default: the same 4096-env batch as the GPU arm)")
     ap.add_argument("--element", type=int, default=3, help="EPMC element_id (0 flat joystick arena, 1 hurdles, 2 bars, 3 cubes)")
     ap.add_argument("--env", default="pmc", choices=["pmc", "epmc", "sepmc"],
                     help="pmc = BASELINE configs[1] (headline); epmc = configs[2] on the flat element-0 arena (8192 envs); "
@@ -144,16 +144,25 @@ def make_engine(lib_or_none, n, env, **over):
 
 def time_cpu_arm(n_envs, steps, warmup, threads=0, env="pmc"):
     """Oracle port of the reference step on the host cores (kind 'port': the reference itself is Python over the
-    pybullet wheel, which is not installable here -- DESIGN.md 6)."""
+    pybullet wheel, which is not installable here -- DESIGN.md 6).  The warm-up runs at least `warmup` steps AND until the
+    OpenMP team is up to speed (>= 1 s elapsed and the last three step times within 25 % of the fastest so far): a cold
+    team / idle cores cost the first second up to 15x per step, which would understate the CPU arm."""
     from oracle import oracle
     eng = make_engine(oracle.load(), n_envs, env, seed=1234, auto_reset=1, num_threads=threads)
     eng.reset()
     pool = action_pool_np(n_envs, 8, 5678)
-    for i in range(warmup):
+    hist, t_start, i = [], time.perf_counter(), 0
+    while True:
+        t0 = time.perf_counter()
         eng.step(pool[i % 8])
+        hist.append(time.perf_counter() - t0)
+        i += 1
+        el = time.perf_counter() - t_start
+        if i >= warmup and ((el >= 1.0 and max(hist[-3:]) <= 1.25 * min(hist)) or el >= 20.0):
+            break
     t0 = time.perf_counter()
-    for i in range(steps):
-        eng.step(pool[i % 8])
+    for k in range(steps):
+        eng.step(pool[(i + k) % 8])
     dt = time.perf_counter() - t0
     cores = threads if threads > 0 else (os.cpu_count() or 1)
     return (n_envs // ROBOTS_PER_ENV[env]) * steps / dt, dt, cores
@@ -164,7 +173,7 @@ def run_reference(args, rank):
         return
     n = args.cpu_envs
     val, dt, cores = time_cpu_arm(n, args.steps, args.warmup, env=args.env)
-    sample = "%d envs x %d steps of the 4096-env workload, oracle/libllq_cpu.so, OpenMP over envs" % (n, args.steps)
+    sample = "%d envs x %d steps of the same workload after a >= 1 s warm-up, oracle/libllq_cpu.so, OpenMP over envs" % (n, args.steps)
     line = {
         "impl": "reference", "metric": METRIC[args.env], "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -412,9 +421,9 @@ def main():
     if actor is not None:
         line["on_device_actor_loop"] = actor
     if world == 1:
-        cval, cdt, cores = time_cpu_arm(args.cpu_envs, 24, 2, env=args.env)
+        cval, cdt, cores = time_cpu_arm(args.cpu_envs, 64, 3, env=args.env)
         line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                "sample": "%d envs x 24 steps of the same workload on the host cores (oracle/libllq_cpu.so, OpenMP)" % args.cpu_envs}
+                                "sample": "%d envs x 64 steps of the same workload on the host cores after a >= 1 s warm-up (oracle/libllq_cpu.so, OpenMP over envs)" % args.cpu_envs}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
