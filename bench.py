@@ -142,38 +142,63 @@ def make_engine(lib_or_none, n, env, **over):
     return capi.VecEngine(lib, n, blob, mocap, **over)
 
 
-def time_cpu_arm(n_envs, steps, warmup, threads=0, env="pmc"):
-    """Oracle port of the reference step on the host cores (kind 'port': the reference itself is Python over the
-    pybullet wheel, which is not installable here -- DESIGN.md 6).  The warm-up runs at least `warmup` steps AND until the
-    OpenMP team is up to speed (>= 1 s elapsed and the last three step times within 25 % of the fastest so far): a cold
-    team / idle cores cost the first second up to 15x per step, which would understate the CPU arm."""
+def _cpu_engine(n_envs, env, threads):
     from oracle import oracle
     eng = make_engine(oracle.load(), n_envs, env, seed=1234, auto_reset=1, num_threads=threads)
     eng.reset()
-    pool = action_pool_np(n_envs, 8, 5678)
+    return eng
+
+
+def _cpu_warm(eng, pool, min_steps, min_s=1.0, max_s=20.0):
+    """Steps until the OpenMP team is up to speed: >= min_steps, >= min_s elapsed and the last three step times within 25 %
+    of the fastest so far (a cold team / idle cores cost the first second up to 15x per step).  Returns the best step time."""
     hist, t_start, i = [], time.perf_counter(), 0
     while True:
         t0 = time.perf_counter()
-        eng.step(pool[i % 8])
+        eng.step(pool[i % len(pool)])
         hist.append(time.perf_counter() - t0)
         i += 1
         el = time.perf_counter() - t_start
-        if i >= warmup and ((el >= 1.0 and max(hist[-3:]) <= 1.25 * min(hist)) or el >= 20.0):
-            break
+        if i >= min_steps and ((el >= min_s and max(hist[-3:]) <= 1.25 * min(hist)) or el >= max_s):
+            return min(hist)
+
+
+def time_cpu_arm(n_envs, steps, warmup, threads=0, env="pmc"):
+    """Oracle port of the reference step on the host cores (kind 'port': the reference itself is Python over the
+    pybullet wheel, which is not installable here -- DESIGN.md 6).  The CPU arm gets its best configuration: a short
+    auto-tune over (envs per call, OpenMP threads) -- the whole batch or cache-sized blocks of 256 envs, all hardware
+    threads or half of them (SMT siblings) -- picks the fastest, then `steps` calls of it are timed after a warm-up.
+    Returns (env-steps/s, seconds, threads used, envs per call)."""
+    ncpu = os.cpu_count() or 1
+    rpe = ROBOTS_PER_ENV[env]
+    cands = [(n_envs, threads)] if threads > 0 else sorted({(n_envs, ncpu), (n_envs, max(1, ncpu // 2)),
+                                                            (min(256, n_envs), ncpu), (min(256, n_envs), max(1, ncpu // 2))})
+    best = None
+    for ne, th in cands:
+        eng = _cpu_engine(ne, env, th)
+        pool = action_pool_np(ne, 8, 5678)
+        rate = (ne // rpe) / _cpu_warm(eng, pool, 3, min_s=0.7, max_s=6.0)
+        if best is None or rate > best[0]:
+            best = (rate, ne, th)
+        eng.close()
+    _, ne, th = best
+    eng = _cpu_engine(ne, env, th)
+    pool = action_pool_np(ne, 8, 5678)
+    _cpu_warm(eng, pool, max(3, warmup))
     t0 = time.perf_counter()
     for k in range(steps):
-        eng.step(pool[(i + k) % 8])
+        eng.step(pool[k % 8])
     dt = time.perf_counter() - t0
-    cores = threads if threads > 0 else (os.cpu_count() or 1)
-    return (n_envs // ROBOTS_PER_ENV[env]) * steps / dt, dt, cores
+    eng.close()
+    return (ne // rpe) * steps / dt, dt, th, ne
 
 
 def run_reference(args, rank):
     if rank != 0:
         return
-    n = args.cpu_envs
-    val, dt, cores = time_cpu_arm(n, args.steps, args.warmup, env=args.env)
-    sample = "%d envs x %d steps of the same workload after a >= 1 s warm-up, oracle/libllq_cpu.so, OpenMP over envs" % (n, args.steps)
+    val, dt, cores, n = time_cpu_arm(args.cpu_envs, args.steps, args.warmup, env=args.env)
+    sample = ("%d envs x %d steps of the same workload after a >= 1 s warm-up, oracle/libllq_cpu.so, OpenMP over envs; "
+              "(envs per call, threads) = (%d, %d) picked by a short auto-tune" % (n, args.steps, n, cores))
     line = {
         "impl": "reference", "metric": METRIC[args.env], "value": val, "unit": "env-steps/s", "n_gpus": args.gpus,
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -370,8 +395,16 @@ def main():
             pol.forward(obs_t.data_ptr(), ow, n, act_t.data_ptr(), None, stream)
         p1.record()
         torch.cuda.synchronize()
+        val_t = torch.zeros((n,), device=dev, dtype=torch.float32)
+        nlp_t = torch.zeros((n,), device=dev, dtype=torch.float32)
+        q0, q1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        q0.record()
+        for i in range(64):
+            pol.forward_ex(obs_t.data_ptr(), ow, n, act_t.data_ptr(), None, val_t.data_ptr(), nlp_t.data_ptr(), 1, i, stream)
+        q1.record()
+        torch.cuda.synchronize()
         actor = {"value": nu * args.steps / (actor_ms * 1e-3), "unit": "env-steps/s", "ms_per_step": actor_ms / args.steps,
-                 "policy_kernel_ms": p0.elapsed_time(p1) / 64, "policy": "PMC net 207-256-256-32 VQ(256) + 135/32-96-256-256-12, fp32, random weights",
+                 "policy_kernel_ms": p0.elapsed_time(p1) / 64, "policy_kernel_ms_with_value_head_and_sampling": q0.elapsed_time(q1) / 64, "policy": "PMC net 207-256-256-32 VQ(256) + 135/32-96-256-256-12, 3xTF32 mma.sync (fp32-level accuracy), random weights",
                  "note": "policy forward + fused env step, observations and actions stay in HBM (hot L2, no flush)"}
         pol.close()
 
@@ -421,9 +454,9 @@ def main():
     if actor is not None:
         line["on_device_actor_loop"] = actor
     if world == 1:
-        cval, cdt, cores = time_cpu_arm(args.cpu_envs, 64, 3, env=args.env)
+        cval, cdt, cores, cne = time_cpu_arm(args.cpu_envs, 64, 3, env=args.env)
         line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": cores, "kind": "port",
-                                "sample": "%d envs x 64 steps of the same workload on the host cores after a >= 1 s warm-up (oracle/libllq_cpu.so, OpenMP over envs)" % args.cpu_envs}
+                                "sample": "%d envs x 64 steps of the same workload on the host cores after a >= 1 s warm-up (oracle/libllq_cpu.so, OpenMP over envs; envs per call and threads auto-tuned)" % cne}
     print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()

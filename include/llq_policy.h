@@ -9,11 +9,12 @@
  * The observation rows are read in place from the engine's device buffer (or a trajectory slab: `obs_ld` floats per row) and
  * the 12 actions per env are written to device memory that llq_step_ex(LLQ_IO_DEVICE) consumes: no host round trip.
  *
- * `weights`: the 24 arrays the policy path uses, fp32, concatenated in this order (numbers = index in a shipped *.model):
- *   prop_mean[135] (0) prop_std[135] (1) future_mean[72] (2) future_std[72] (3)
- *   enc W1[207x256] b1[256] W2[256x256] b2[256] W3[256x32] b3[32] (10-15)   codebook[32x256] (16)
- *   prop_embed W[135x64] b[64] (17-18)   z_embed W[32x32] b[32] (19-20)
- *   dec W1[96x256] b1[256] W2[256x256] b2[256] W3[256x12] b3[12] (21-26)
+ * `weights`: the 28 arrays of a shipped *.model file, fp32, concatenated in their stored order:
+ *   0-3   prop_mean[135] prop_std[135] future_mean[72] future_std[72]
+ *   4-9   value head W1[207x256] b1[256] W2[256x256] b2[256] W3[256x1] b3[1]   (tanh; pmc_net.py:139-144)
+ *   10-15 enc W1[207x256] b1[256] W2[256x256] b2[256] W3[256x32] b3[32]          16 codebook[32x256]
+ *   17-20 prop_embed W[135x64] b[64], z_embed W[32x32] b[32]
+ *   21-26 dec W1[96x256] b1[256] W2[256x256] b2[256] W3[256x12] b3[12]           27 logstd[12]
  * All matrices row major [in][out] as TensorFlow stores them. */
 #ifndef LLQ_POLICY_H
 #define LLQ_POLICY_H
@@ -22,7 +23,7 @@
 extern "C" {
 #endif
 
-#define LLQ_POLICY_N_WEIGHTS 239338   /* total floats of the list above */
+#define LLQ_POLICY_N_WEIGHTS 358647   /* total floats of the list above */
 
 typedef struct llq_policy* llq_policy_handle;
 
@@ -32,6 +33,14 @@ int llq_policy_destroy(llq_policy_handle h);
 /* actions[n,12] = mean action for obs[n, >=207] (device pointers; obs_ld = row stride in floats); `codes` (int32[n], device,
  * nullable) receives the selected codebook index.  Asynchronous on `stream` (a cudaStream_t, 0 = the default stream). */
 int llq_policy_forward(llq_policy_handle h, const float* d_obs, int64_t obs_ld, int32_t n, float* d_actions, int32_t* d_codes, void* stream);
+/* Full actor step for rollouts: as llq_policy_forward, plus
+ *   d_values  (float[n], device, nullable): the value head's V(obs)  -> PMCInputs.V (pmc_net_data.py:7-16);
+ *   d_neglogp (float[n], device, nullable): when given, d_actions receives a SAMPLE a = mean + exp(logstd) * eps of the diagonal
+ *     Gaussian head (agent.step(argmax=False); pmc_net.py:107-113) and d_neglogp its -log p(a) = 0.5 sum eps^2 + sum logstd +
+ *     6 log(2 pi) -> PMCInputs.neglogp; eps ~ N(0,1) from Philox4x32-10 keyed by `seed`, counter (row, draw, `counter`): pass a
+ *     different `counter` every step.  NULL: d_actions is the mean (argmax=True). */
+int llq_policy_forward_ex(llq_policy_handle h, const float* d_obs, int64_t obs_ld, int32_t n, float* d_actions, int32_t* d_codes,
+                          float* d_values, float* d_neglogp, uint64_t seed, uint64_t counter, void* stream);
 const char* llq_policy_last_error(void);
 
 #ifdef __cplusplus

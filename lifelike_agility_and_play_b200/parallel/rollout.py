@@ -11,13 +11,14 @@ to row 0 of the other.
 """
 import torch
 
-from .trajectory import ACT_DIM, COL_ACTION, COL_DONE, COL_REWARD, OBS_DIM, TRAJ_WIDTH
+from .trajectory import ACT_DIM, COL_ACTION, COL_DONE, COL_NEGLOGP, COL_REWARD, COL_VALUE, OBS_DIM, TRAJ_WIDTH
 
 
 class RolloutWorker:
-    def __init__(self, engine, policy, unroll, device):
+    def __init__(self, engine, policy, unroll, device, sample=True, seed=0):
         """`engine`: a `_capi.VecEngine` on the CUDA library with auto_reset=1 (PMC, 207-wide observations);
-        `policy`: a `policy.DevicePolicy` on the same device; `unroll`: T (128 in example_pmc_train.sh:145)."""
+        `policy`: a `policy.DevicePolicy` on the same device; `unroll`: T (128 in example_pmc_train.sh:145);
+        `sample`: draw the actions from the Gaussian head and record -log p (training rollouts) instead of the mean (evaluation)."""
         if engine.obs_dim != OBS_DIM:
             raise ValueError("RolloutWorker drives the PMC env (207-wide observations)")
         self.eng, self.pol, self.T, self.n = engine, policy, int(unroll), engine.n
@@ -27,27 +28,41 @@ class RolloutWorker:
         self.act = torch.zeros((self.n, ACT_DIM), dtype=torch.float32, device=self.dev)
         self.rew = torch.zeros((self.n,), dtype=torch.float32, device=self.dev)
         self.done = torch.zeros((self.n,), dtype=torch.uint8, device=self.dev)
+        self.val = torch.zeros((self.n,), dtype=torch.float32, device=self.dev)
+        self.nlp = torch.zeros((self.n,), dtype=torch.float32, device=self.dev)
+        self.sample, self.seed, self.calls = bool(sample), int(seed), 0
+        # everything this worker launches (kernels through the C-ABI and torch's column copies) is ordered on ONE side stream: a
+        # NULL stream would mean "the engine's own non-blocking stream" to llq_step_ex and would not order with torch's work
+        self.stream = torch.cuda.Stream(self.dev)
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
         self.t = 0
         self.launches = 0
 
     def start(self, first_obs):
         """`first_obs` [N, 207] (host or device): the observation `engine.reset()` returned."""
-        self.buf[0, :, :OBS_DIM] = torch.as_tensor(first_obs, dtype=torch.float32).to(self.dev)
+        first = torch.as_tensor(first_obs, dtype=torch.float32).to(self.dev)
+        self.stream.wait_stream(torch.cuda.current_stream(self.dev))
+        with torch.cuda.stream(self.stream):
+            self.buf[0, :, :OBS_DIM] = first
         self.t = 0
 
     def step(self):
-        """One policy forward + one fused env step; fills record t.  Asynchronous on torch's current stream (the kernels
-        are launched on it so that they order with the column copies below)."""
+        """One policy forward + one fused env step; fills record t.  Asynchronous on the worker's stream."""
         assert self.t < self.T, "unroll is full: call finish_unroll()"
-        s = torch.cuda.current_stream(self.dev).cuda_stream
+        s = self.stream.cuda_stream
         row, nxt = self.buf[self.t], self.buf[self.t + 1]
-        self.pol.forward(row.data_ptr(), TRAJ_WIDTH, self.n, self.act.data_ptr(), None, s)
-        self.eng.step_device(self.act.data_ptr(), nxt.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(), obs_ld=TRAJ_WIDTH, stream=s)
-        row[:, COL_ACTION:COL_ACTION + ACT_DIM] = self.act
-        row[:, COL_REWARD] = self.rew
-        row[:, COL_DONE] = self.done
+        with torch.cuda.stream(self.stream):
+            self.pol.forward_ex(row.data_ptr(), TRAJ_WIDTH, self.n, self.act.data_ptr(), None, self.val.data_ptr(),
+                                self.nlp.data_ptr() if self.sample else None, self.seed, self.calls, s)
+            self.eng.step_device(self.act.data_ptr(), nxt.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(), obs_ld=TRAJ_WIDTH, stream=s)
+            row[:, COL_ACTION:COL_ACTION + ACT_DIM] = self.act
+            row[:, COL_REWARD] = self.rew
+            row[:, COL_DONE] = self.done
+            row[:, COL_VALUE] = self.val
+            row[:, COL_NEGLOGP] = self.nlp
+        self.calls += 1
         self.t += 1
-        self.launches += 3            # policy, step, reset kernels (the three column copies are torch's)
+        self.launches += 3            # policy, step, reset kernels (the column copies are torch's)
 
     def finish_unroll(self):
         """Copy-free `[T, N, 223]` view of the finished records, valid until the end of the NEXT unroll; stepping continues
@@ -55,6 +70,11 @@ class RolloutWorker:
         assert self.t == self.T
         done_buf = self.buf
         self.buf = self.bufs[1] if done_buf is self.bufs[0] else self.bufs[0]
-        self.buf[0, :, :OBS_DIM] = done_buf[self.T, :, :OBS_DIM]
+        with torch.cuda.stream(self.stream):
+            self.buf[0, :, :OBS_DIM] = done_buf[self.T, :, :OBS_DIM]
         self.t = 0
         return done_buf[:self.T]
+
+    def wait(self):
+        """Make torch's current stream wait for everything queued so far (call before reading a finished slab there)."""
+        torch.cuda.current_stream(self.dev).wait_stream(self.stream)

@@ -20,6 +20,7 @@ class PmcPolicy:
         self.prop_embed, self.z_embed = (w[17], w[18]), (w[19], w[20])
         self.dec = [(w[21], w[22]), (w[23], w[24]), (w[25], w[26])]
         self.logstd = w[27]
+        self.vf = [(w[4], w[5]), (w[6], w[7]), (w[8], w[9])]
 
     def normalise(self, obs):
         p = np.clip((obs[:, :135] - self.prop_mean) / (self.prop_std + 1e-8), -5.0, 5.0)
@@ -48,6 +49,20 @@ class PmcPolicy:
         a = x @ self.dec[2][0] + self.dec[2][1]
         return (a, idx) if return_code else a
 
+    def value(self, obs):
+        """V(obs): 207 -> 256 -> 256 -> 1 with tanh on the normalised observation (pmc_net.py:139-144)."""
+        p, f = self.normalise(np.asarray(obs, dtype=np.float32))
+        x = np.concatenate([p, f], axis=1)
+        x = np.tanh(x @ self.vf[0][0] + self.vf[0][1])
+        x = np.tanh(x @ self.vf[1][0] + self.vf[1][1])
+        return (x @ self.vf[2][0] + self.vf[2][1])[:, 0]
+
+    def neglogp(self, action, mean):
+        """-log p(action) under the diagonal Gaussian head (mean, exp(logstd)) (pmc_net.py:107-113)."""
+        ls = self.logstd.reshape(-1)
+        e = (action - mean) / np.exp(ls)
+        return 0.5 * (e * e).sum(1) + ls.sum() + 0.5 * e.shape[1] * np.log(2.0 * np.pi)
+
 
 # ------------------------------------------------------------------------------------------------------------------------
 # device side (include/llq_policy.h, csrc/llq_policy.cu)
@@ -55,14 +70,14 @@ import ctypes as _C
 import os as _os
 
 POLICY_LIB_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "csrc", "libllq_policy.so")
-POLICY_EXPORTS = ["llq_policy_create", "llq_policy_destroy", "llq_policy_forward", "llq_policy_last_error"]
-_ORDER = [0, 1, 2, 3, 10, 11, 12, 13, 14, 15, 16, 17, 18, 19, 20, 21, 22, 23, 24, 25, 26]     # arrays of a *.model file the actor path uses
+POLICY_EXPORTS = ["llq_policy_create", "llq_policy_destroy", "llq_policy_forward", "llq_policy_forward_ex", "llq_policy_last_error"]
+N_WEIGHTS = 358647
 
 
 def pack_weights(weights):
-    """The blob llq_policy_create() expects (order documented in include/llq_policy.h) from the 28 arrays of a model file."""
-    blob = np.concatenate([np.asarray(weights[i], dtype=np.float32).reshape(-1) for i in _ORDER])
-    assert blob.size == 239338
+    """The blob llq_policy_create() expects: the 28 arrays of a model file in their stored order (include/llq_policy.h)."""
+    blob = np.concatenate([np.asarray(w, dtype=np.float32).reshape(-1) for w in weights])
+    assert len(weights) == 28 and blob.size == N_WEIGHTS
     return np.ascontiguousarray(blob)
 
 
@@ -76,6 +91,8 @@ class DevicePolicy:
         L = self._lib
         L.llq_policy_create.argtypes = [_C.c_void_p, _C.c_int64, _C.c_int32, _C.POINTER(_C.c_void_p)]
         L.llq_policy_forward.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_int64, _C.c_int32, _C.c_void_p, _C.c_void_p, _C.c_void_p]
+        L.llq_policy_forward_ex.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_int64, _C.c_int32, _C.c_void_p, _C.c_void_p, _C.c_void_p,
+                                            _C.c_void_p, _C.c_uint64, _C.c_uint64, _C.c_void_p]
         L.llq_policy_destroy.argtypes = [_C.c_void_p]
         L.llq_policy_last_error.restype = _C.c_char_p
         blob = pack_weights(weights)
@@ -89,6 +106,14 @@ class DevicePolicy:
         rc = self._lib.llq_policy_forward(self._h, obs_ptr, obs_ld, n, actions_ptr, codes_ptr, stream)
         if rc != 0:
             raise RuntimeError("llq_policy_forward failed (%d): %s" % (rc, (self._lib.llq_policy_last_error() or b"").decode()))
+
+    def forward_ex(self, obs_ptr, obs_ld, n, actions_ptr, codes_ptr=None, values_ptr=None, neglogp_ptr=None, seed=0, counter=0,
+                   stream=None):
+        """Rollout step: optional V(obs) and, when `neglogp_ptr` is given, sampled actions with their -log p."""
+        rc = self._lib.llq_policy_forward_ex(self._h, obs_ptr, obs_ld, n, actions_ptr, codes_ptr, values_ptr, neglogp_ptr,
+                                             seed, counter, stream)
+        if rc != 0:
+            raise RuntimeError("llq_policy_forward_ex failed (%d): %s" % (rc, (self._lib.llq_policy_last_error() or b"").decode()))
 
     def close(self):
         if getattr(self, "_h", None):

@@ -44,7 +44,7 @@ def test_policy_library_exports():
     lib = ctypes.CDLL(policy.POLICY_LIB_PATH)
     for name in policy.POLICY_EXPORTS:
         assert hasattr(lib, name), name
-    assert policy.pack_weights(random_weights()).size == 239338
+    assert policy.pack_weights(random_weights()).size == policy.N_WEIGHTS == 358647
     hdr = open(os.path.join(os.path.dirname(policy.POLICY_LIB_PATH), "..", "..", "include", "llq_policy.h")).read()
     for name in policy.POLICY_EXPORTS:
         assert name + "(" in hdr
@@ -76,4 +76,24 @@ def test_device_policy_matches_host_forward():
         assert same.mean() > 0.99, same.mean()
         err = np.abs(act[same] - a_ref[same]).max() / (1.0 + np.abs(a_ref).max())
         assert err < 1e-4, err
+        # rollout entry: value head + sampled actions with their -log p
+        t_val = torch.zeros((n,), device="cuda", dtype=torch.float32)
+        t_nlp = torch.zeros((n,), device="cuda", dtype=torch.float32)
+        t_smp = torch.zeros((n, 12), device="cuda", dtype=torch.float32)
+        dev.forward_ex(t_obs.data_ptr(), ld, n, t_smp.data_ptr(), None, t_val.data_ptr(), t_nlp.data_ptr(), seed=7, counter=3)
+        torch.cuda.synchronize()
+        v_ref = host.value(obs[:, :207])
+        assert np.abs(t_val.cpu().numpy() - v_ref).max() < 1e-4 * (1.0 + np.abs(v_ref).max())
+        smp, nlp = t_smp.cpu().numpy(), t_nlp.cpu().numpy()
+        assert np.abs(nlp[same] - host.neglogp(smp, act)[same]).max() < 1e-3          # consistent with (sample, mean, logstd)
+        eps = ((smp - act) / np.exp(host.logstd.reshape(-1)))[same]
+        if n >= 4096:
+            assert abs(eps.mean()) < 0.02 and abs(eps.std() - 1.0) < 0.02 and np.abs(eps).max() < 6.5
+            assert abs(np.corrcoef(eps[:, 0], eps[:, 1])[0, 1]) < 0.05
+        t_smp2 = torch.zeros_like(t_smp)
+        dev.forward_ex(t_obs.data_ptr(), ld, n, t_smp2.data_ptr(), None, None, t_nlp.data_ptr(), seed=7, counter=3)
+        t_smp3 = torch.zeros_like(t_smp)
+        dev.forward_ex(t_obs.data_ptr(), ld, n, t_smp3.data_ptr(), None, None, t_nlp.data_ptr(), seed=7, counter=4)
+        torch.cuda.synchronize()
+        assert torch.equal(t_smp2, t_smp) and not torch.equal(t_smp3, t_smp)           # keyed by (seed, counter), reproducible
     dev.close()
