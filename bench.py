@@ -12,6 +12,8 @@ of every environment of the batch.  Contract: see the task statement / DESIGN.md
 import argparse
 import json
 import os
+
+os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # CPU arm: idle OpenMP threads must not spin away the container's CPU quota
 import subprocess
 import sys
 import threading
@@ -149,42 +151,58 @@ def _cpu_engine(n_envs, env, threads):
     return eng
 
 
-def _cpu_warm(eng, pool, min_steps, min_s=1.0, max_s=20.0):
-    """Steps until the OpenMP team is up to speed: >= min_steps, >= min_s elapsed and the last three step times within 25 %
-    of the fastest so far (a cold team / idle cores cost the first second up to 15x per step).  Returns the best step time."""
-    hist, t_start, i = [], time.perf_counter(), 0
-    while True:
+def _cpu_quota():
+    """CPUs this container may use: min(hardware threads, cgroup CPU quota).  The GPU boxes expose 128 hardware threads under
+    a 16-CPU quota; an OpenMP team wider than the quota burns it in spin-waits and gets throttled (measured: 128 threads ->
+    3 k env-steps/s, 16-32 threads -> 150-200 k; tools/cpu_arm_sweep.py)."""
+    ncpu = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+    try:
+        q, per = open("/sys/fs/cgroup/cpu.max").read().split()[:2]
+        if q != "max":
+            return max(1, min(ncpu, int(np.ceil(float(q) / float(per))))), ncpu
+    except Exception:
+        pass
+    try:
+        q = float(open("/sys/fs/cgroup/cpu/cpu.cfs_quota_us").read()); per = float(open("/sys/fs/cgroup/cpu/cpu.cfs_period_us").read())
+        if q > 0:
+            return max(1, min(ncpu, int(np.ceil(q / per)))), ncpu
+    except Exception:
+        pass
+    return ncpu, ncpu
+
+
+def _cpu_sustained(eng, pool, seconds, min_steps=3):
+    """Steps for `seconds`; returns the median step time of the second half of the window (sustained, after the OpenMP team
+    and the cores are up to speed and any CPU-quota burst is spent)."""
+    hist, t_start = [], time.perf_counter()
+    while len(hist) < min_steps or time.perf_counter() - t_start < seconds:
         t0 = time.perf_counter()
-        eng.step(pool[i % len(pool)])
+        eng.step(pool[len(hist) % len(pool)])
         hist.append(time.perf_counter() - t0)
-        i += 1
-        el = time.perf_counter() - t_start
-        if i >= min_steps and ((el >= min_s and max(hist[-3:]) <= 1.25 * min(hist)) or el >= max_s):
-            return min(hist)
+    return float(np.median(hist[len(hist) // 2:]))
 
 
 def time_cpu_arm(n_envs, steps, warmup, threads=0, env="pmc"):
     """Oracle port of the reference step on the host cores (kind 'port': the reference itself is Python over the
-    pybullet wheel, which is not installable here -- DESIGN.md 6).  The CPU arm gets its best configuration: a short
-    auto-tune over (envs per call, OpenMP threads) -- the whole batch or cache-sized blocks of 256 envs, all hardware
-    threads or half of them (SMT siblings) -- picks the fastest, then `steps` calls of it are timed after a warm-up.
+    pybullet wheel, which is not installable here -- DESIGN.md 6).  The CPU arm gets its best sustained configuration: a
+    short auto-tune over (envs per call: whole batch or cache-sized blocks of 256; OpenMP threads: the container's CPU quota,
+    twice that, or every hardware thread) picks the fastest, then `steps` calls of it are timed after a >= 1 s warm-up.
     Returns (env-steps/s, seconds, threads used, envs per call)."""
-    ncpu = os.cpu_count() or 1
+    quota, ncpu = _cpu_quota()
     rpe = ROBOTS_PER_ENV[env]
-    cands = [(n_envs, threads)] if threads > 0 else sorted({(n_envs, ncpu), (n_envs, max(1, ncpu // 2)),
-                                                            (min(256, n_envs), ncpu), (min(256, n_envs), max(1, ncpu // 2))})
+    ths = [threads] if threads > 0 else sorted({quota, min(ncpu, 2 * quota), ncpu})
+    cands = [(ne, th) for ne in sorted({n_envs, min(256, n_envs)}) for th in ths]
     best = None
     for ne, th in cands:
         eng = _cpu_engine(ne, env, th)
-        pool = action_pool_np(ne, 8, 5678)
-        rate = (ne // rpe) / _cpu_warm(eng, pool, 3, min_s=0.7, max_s=6.0)
+        rate = (ne // rpe) / _cpu_sustained(eng, action_pool_np(ne, 8, 5678), 1.5)
         if best is None or rate > best[0]:
             best = (rate, ne, th)
         eng.close()
     _, ne, th = best
     eng = _cpu_engine(ne, env, th)
     pool = action_pool_np(ne, 8, 5678)
-    _cpu_warm(eng, pool, max(3, warmup))
+    _cpu_sustained(eng, pool, 1.0, min_steps=max(3, warmup))
     t0 = time.perf_counter()
     for k in range(steps):
         eng.step(pool[k % 8])
@@ -204,7 +222,8 @@ def run_reference(args, rank):
         "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * dt / args.steps, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD[args.env] + "; CPU arm steps a %d-env sample" % n, "envs_per_step": n},
-        "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline": {"value": val, "unit": "env-steps/s", "cores": cores, "kind": "port", "sample": sample,
+                         "cpu_quota": _cpu_quota()[0], "hw_threads": _cpu_quota()[1]},
         "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -455,7 +474,7 @@ def main():
         line["on_device_actor_loop"] = actor
     if world == 1:
         cval, cdt, cores, cne = time_cpu_arm(args.cpu_envs, 64, 3, env=args.env)
-        line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": cores, "kind": "port",
+        line["cpu_baseline"] = {"value": cval, "unit": "env-steps/s", "cores": cores, "kind": "port", "cpu_quota": _cpu_quota()[0], "hw_threads": _cpu_quota()[1],
                                 "sample": "%d envs x 64 steps of the same workload on the host cores after a >= 1 s warm-up (oracle/libllq_cpu.so, OpenMP over envs; envs per call and threads auto-tuned)" % cne}
     print(json.dumps(line), flush=True)
     if world > 1:

@@ -3,7 +3,7 @@
 // One CTA (256 threads = 8 warps) owns a tile of M = 32 observation rows and walks the whole net with the activations in
 // shared memory ([row][feature], padded so that the MMA A-fragment loads are conflict free).  The fully connected layers run
 // on the tensor cores as 3xTF32 (`mma.sync.m16n8k8.tf32`, fp32 accumulate): every operand is split into a TF32 head and a
-// TF32 remainder and the three significant products a_lo*b_hi + a_hi*b_lo + a_hi*b_hi are accumulated, which restores fp32-level
+// remainder (truncation split) and the three significant products a_lo*b_hi + a_hi*b_lo + a_hi*b_hi are accumulated, which restores fp32-level
 // accuracy (the 12 outputs are joint targets for the physics and the parity bar is 1e-4, so plain TF32 -- a 1e-3 perturbation that
 // can also flip the discrete code -- is not an option).  The weights are re-ordered once, at llq_policy_create, into MMA
 // B-fragment order, so a warp fetches the fragments of a k-step with one coalesced 8-byte load per lane and n-tile; they stream
@@ -36,14 +36,17 @@ struct Weights {
   const float* logstd;
 };
 
+// x = hi + lo with hi = x truncated to TF32 (one LOP3) and lo = x - hi (exact in fp32, <= 13 significant bits).  The tensor
+// core reads only the TF32 bits of an operand register, i.e. it truncates lo to 11 significant bits itself: the dropped part
+// is <= 2^-21 |x|, the same order as the a_lo * b_lo product 3xTF32 leaves out.  (cvt.rna.tf32.f32 is emulated with ~5
+// integer instructions per value on sm_100a: with it the splits, not the MMAs, filled the issue slots.)
 __device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hi) : "f"(x));
-  const float r = x - __uint_as_float(hi);
-  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(lo) : "f"(r));
+  hi = __float_as_uint(x) & 0xffffe000u;
+  lo = __float_as_uint(x - __uint_as_float(hi));
 }
 
 __device__ __forceinline__ void mma_tf32(float (&d)[4], const uint32_t (&a)[4], uint32_t b0, uint32_t b1) {
-  asm volatile("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+  asm("mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                : "+f"(d[0]), "+f"(d[1]), "+f"(d[2]), "+f"(d[3])
                : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b0), "r"(b1));
 }
@@ -96,18 +99,25 @@ __device__ __forceinline__ void mma_layer(const float* A, int lda, Layer L, floa
           split_tf32(ap[(mi * 16) * lda + 4], ah[mi][2], al[mi][2]);
           split_tf32(ap[(mi * 16 + 8) * lda + 4], ah[mi][3], al[mi][3]);
         }
+        uint32_t bh[NT][2], bl[NT][2];
 #pragma unroll
         for (int i = 0; i < NT; i++) {
-          uint32_t bh0, bl0, bh1, bl1;
-          split_tf32(bc[u][i].x, bh0, bl0);
-          split_tf32(bc[u][i].y, bh1, bl1);
-#pragma unroll
-          for (int mi = 0; mi < MT; mi++) {
-            mma_tf32(acc[mi][i], al[mi], bh0, bh1);      // small terms first
-            mma_tf32(acc[mi][i], ah[mi], bl0, bl1);
-            mma_tf32(acc[mi][i], ah[mi], bh0, bh1);
-          }
+          split_tf32(bc[u][i].x, bh[i][0], bl[i][0]);
+          split_tf32(bc[u][i].y, bh[i][1], bl[i][1]);
         }
+        // the three products of one accumulator are MT*NT instructions apart (small terms first), so no MMA waits on its predecessor
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+#pragma unroll
+          for (int mi = 0; mi < MT; mi++) mma_tf32(acc[mi][i], al[mi], bh[i][0], bh[i][1]);
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+#pragma unroll
+          for (int mi = 0; mi < MT; mi++) mma_tf32(acc[mi][i], ah[mi], bl[i][0], bl[i][1]);
+#pragma unroll
+        for (int i = 0; i < NT; i++)
+#pragma unroll
+          for (int mi = 0; mi < MT; mi++) mma_tf32(acc[mi][i], ah[mi], bh[i][0], bh[i][1]);
       }
     }
 #pragma unroll
@@ -210,7 +220,7 @@ __global__ void __launch_bounds__(THREADS) pmc_policy_kernel(const float* __rest
       }
     }
 #pragma unroll
-    for (int m = 0; m < M; m++) Q[tid * M + m] = d[m];   // Q as dist[c][m] (256 x 32 floats fit the 32 x 260 buffer)
+    for (int m = 0; m < M; m++) Q[m * LDH + tid] = d[m];   // dist[m][c]: consecutive codes in consecutive banks
   }
   __syncthreads();
   {
@@ -218,7 +228,7 @@ __global__ void __launch_bounds__(THREADS) pmc_policy_kernel(const float* __rest
     for (int m = warp; m < M; m += THREADS / 32) {
       float best = 3.4e38f; int bi = 0;
       for (int c = lane; c < NCODE; c += 32) {
-        const float v = Q[c * M + m];
+        const float v = Q[m * LDH + c];
         if (v < best) { best = v; bi = c; }
       }
 #pragma unroll
