@@ -189,3 +189,28 @@ def test_full_size_properties(make_cuda):
     assert np.abs(st[:, 7:]).max() <= 100.0 + 1e-3
     c = eng.counters()
     assert c[0] == 60 * n and c[1] == dones and c[4] >= 120
+
+
+@pytest.mark.parametrize("n", [1, 3, 9, 37])
+def test_ragged_batch_sizes(n, make_cuda, make_oracle):
+    """Edge sizes: fewer envs than a warp holds (8), than a CTA holds (32), odd counts -- the padded lanes of the last warp must
+    neither write nor disturb the live ones (reset, masked reset of the last env, teacher-forced steps, auto-reset bookkeeping)."""
+    gpu, cpu = make_cuda(n, seed=31, auto_reset=1), make_oracle(n, seed=31, auto_reset=1)
+    og, oc = gpu.reset(), cpu.reset()
+    assert og.shape == (n, 207) and np.array_equal(gpu.get(capi.F_CLIP), cpu.get(capi.F_CLIP))
+    assert blockrel(og[:, :99], oc[:, :99]).max() < TOL and blockrel(og[:, 135:], oc[:, 135:]).max() < TOL
+    mask = np.zeros(n, np.uint8); mask[-1] = 1
+    gpu.reset(mask); cpu.reset(mask)
+    assert np.array_equal(gpu.get(capi.F_TIME), cpu.get(capi.F_TIME))
+    rng = np.random.default_rng(n)
+    for t in range(4):
+        a = np.clip(MU_A + SIGMA_A * rng.standard_normal((n, 12)).astype(np.float32), -1, 1).astype(np.float32)
+        teacher_force(gpu, cpu)
+        og, rg, dg = gpu.step(a)
+        oc, rc, dc = cpu.step(a)
+        near = cpu.get(capi.F_DECISION_MARGIN) < 2.5e-4
+        assert np.array_equal(dg[~near], dc[~near])
+        ok = (dc == 0) & (dg == 0) & ~near                      # finished envs were re-seeded by each side's own table
+        e = np.maximum(blockrel(og[:, :99], oc[:, :99]), blockrel(og[:, 135:], oc[:, 135:]))
+        assert np.all(e[ok] < TOL) and np.all(np.abs(rg - rc)[ok] < TOL)
+    assert gpu.counters()[0] == 4 * n
