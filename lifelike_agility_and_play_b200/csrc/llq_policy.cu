@@ -7,7 +7,8 @@
 // accuracy (the 12 outputs are joint targets for the physics and the parity bar is 1e-4, so plain TF32 -- a 1e-3 perturbation that
 // can also flip the discrete code -- is not an option).  The weights are re-ordered once, at llq_policy_create, into MMA
 // B-fragment order, so a warp fetches the fragments of a k-step with one coalesced 8-byte load per lane and n-tile; they stream
-// through L2 (1.4 MB per CTA) double-buffered in registers four k-steps ahead.  The previous version of this kernel did the same
+// through L2 (1.4 MB per CTA) double-buffered in registers four k-steps ahead (A/B on the B200: eight or two k-steps per buffer and
+// `prefetch.global.L1` of the following group / of the next layer's head were all 3-10 % slower; profiles/r01_policy_ab.txt).  The previous version of this kernel did the same
 // layers with fp32 FFMA (one output neuron per thread, 32 accumulators): 0.137 ms per 4096 rows.
 // The tile is 32 rows, not 128, on purpose: 4096 envs -> 128 CTAs = one wave over the 148 SMs; a tcgen05 tile (M = 128) would
 // leave 116 SMs idle at this batch.  The 32-code search, the 256 -> 1 value output and the Gaussian sampling stay on the CUDA cores.
@@ -19,6 +20,10 @@
 #include <vector>
 #include "../../include/llq.h"
 #include "../../include/llq_policy.h"
+
+#ifndef LLQ_POLICY_KU
+#define LLQ_POLICY_KU 4      // k-steps of weight fragments per register buffer (two buffers)
+#endif
 
 namespace {
 
@@ -58,28 +63,11 @@ __device__ __forceinline__ float activate(float v) {
   return v;
 }
 
-__device__ __forceinline__ void prefetch_l1(const void* p) { asm volatile("prefetch.global.L1 [%0];" ::"l"(p)); }
-
-// Pull the first two k-groups of a layer's B fragments (this warp's slice) into L1 ahead of time: the weights are L2 hits, but a
-// layer's first loads have nothing to hide behind (~1 us each, ten layers) unless they were requested one layer earlier.
-template <int KT, int NTILES, int MT, int NT>
-__device__ __forceinline__ void prefetch_head(Layer L) {
-  constexpr int MG = 2 / MT, NG = NTILES / NT, KU = 4;
-  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  if (warp >= MG * NG) return;
-  const float2* wp = L.w + (size_t)((warp / MG) * NT) * 32 + lane;
-#pragma unroll
-  for (int u = 0; u < 2 * KU; u++)
-#pragma unroll
-    for (int i = 0; i < NT; i++)
-      if (u < KT) prefetch_l1(wp + ((size_t)u * NTILES + i) * 32);
-}
-
 // out[m][n] = act(b[n] + sum_k A[m][k] W[k][n]) for the CTA's 32 rows; KT k-tiles of 8, NTILES n-tiles of 8.
 // A warp owns MT m-tiles (of 16 rows) x NT n-tiles; warps beyond (2/MT) * (NTILES/NT) idle.  TRANSPOSE: out[n * M + m].
 template <int KT, int NTILES, int MT, int NT, int ACT, bool TRANSPOSE>
 __device__ __forceinline__ void mma_layer(const float* A, int lda, Layer L, float* out, int ldo) {
-  constexpr int MG = 2 / MT, NG = NTILES / NT, KU = 4;
+  constexpr int MG = 2 / MT, NG = NTILES / NT, KU = LLQ_POLICY_KU;
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31, g = lane >> 2, t = lane & 3;
   if (warp >= MG * NG) return;
   const int m0 = (warp % MG) * MT * 16, nt0 = (warp / MG) * NT;
@@ -103,11 +91,6 @@ __device__ __forceinline__ void mma_layer(const float* A, int lda, Layer L, floa
 #pragma unroll
       for (int i = 0; i < NT; i++)
         bn[u][i] = (kg + KU + u < KT) ? __ldg(wp + ((size_t)(kg + KU + u) * NTILES + i) * 32) : make_float2(0.f, 0.f);
-#pragma unroll
-    for (int u = 0; u < KU; u++)        // and the group after that goes from L2 into L1
-#pragma unroll
-      for (int i = 0; i < NT; i++)
-        if (kg + 2 * KU + u < KT) prefetch_l1(wp + ((size_t)(kg + 2 * KU + u) * NTILES + i) * 32);
 #pragma unroll
     for (int u = 0; u < KU; u++) {
       const int kt = kg + u;
@@ -187,7 +170,6 @@ __global__ void __launch_bounds__(THREADS) pmc_policy_kernel(const float* __rest
   __shared__ int s_code[M];
   const int row0 = blockIdx.x * M;
   const int tid = threadIdx.x;
-  if (values != nullptr) prefetch_head<26, 32, 2, 4>(w.v1); else prefetch_head<26, 32, 2, 4>(w.e1);
   // ---- normalise + clip (pmc_net.py:130-137), coalesced along the observation row
   for (int idx = tid; idx < M * (N_OBS + 1); idx += THREADS) {
     const int m = idx / (N_OBS + 1), k = idx - m * (N_OBS + 1);
@@ -203,10 +185,8 @@ __global__ void __launch_bounds__(THREADS) pmc_policy_kernel(const float* __rest
   __syncthreads();
   // ---- value head 207 -> 256 -> 256 -> 1, tanh (pmc_net.py:139-144); only when the caller wants it
   if (values != nullptr) {
-    prefetch_head<32, 32, 2, 4>(w.v2);
     mma_layer<26, 32, 2, 4, ACT_TANH, false>(X, LDX, w.v1, P, LDH);
     __syncthreads();
-    prefetch_head<26, 32, 2, 4>(w.e1);
     mma_layer<32, 32, 2, 4, ACT_TANH, false>(P, LDH, w.v2, Q, LDH);
     __syncthreads();
     const int warp = tid >> 5, lane = tid & 31;
@@ -220,14 +200,10 @@ __global__ void __launch_bounds__(THREADS) pmc_policy_kernel(const float* __rest
     __syncthreads();
   }
   // ---- VQ encoder 207 -> 256 -> 256 -> 32 (pmc_net.py:33-45)
-  prefetch_head<32, 32, 2, 4>(w.e2);
   mma_layer<26, 32, 2, 4, ACT_RELU, false>(X, LDX, w.e1, P, LDH);
   __syncthreads();
-  prefetch_head<32, 4, 1, 1>(w.e3);
   mma_layer<32, 32, 2, 4, ACT_RELU, false>(P, LDH, w.e2, Q, LDH);
   __syncthreads();
-  prefetch_head<17, 8, 2, 1>(w.pe);
-  prefetch_head<4, 4, 1, 1>(w.ze);
   mma_layer<32, 4, 1, 1, ACT_NONE, true>(Q, LDH, w.e3, P, 0);           // z transposed: P[k * M + m]
   __syncthreads();
   // ---- nearest code: thread c owns code c, squared distance to all M rows; then per-row argmin (first index wins ties)
@@ -276,15 +252,12 @@ __global__ void __launch_bounds__(THREADS) pmc_policy_kernel(const float* __rest
     Q[m * LDH + k] = w.code[k * NCODE + s_code[m]];
   }
   __syncthreads();
-  prefetch_head<12, 32, 2, 4>(w.d1);
   mma_layer<17, 8, 2, 1, ACT_RELU, false>(X, LDX, w.pe, P, LDH);          // weight rows >= 135 are zero: X[:, 135] (future[0]) drops out
   mma_layer<4, 4, 1, 1, ACT_RELU, false>(Q, LDH, w.ze, P + PE, LDH);
   __syncthreads();
   // ---- decoder 96 -> 256 -> 256 -> 12 (pmc_net.py:47-58)
-  prefetch_head<32, 32, 2, 4>(w.d2);
   mma_layer<12, 32, 2, 4, ACT_RELU, false>(P, LDH, w.d1, Q, LDH);
   __syncthreads();
-  prefetch_head<32, 2, 1, 1>(w.d3);
   mma_layer<32, 32, 2, 4, ACT_RELU, false>(Q, LDH, w.d2, P, LDH);
   __syncthreads();
   mma_layer<32, 2, 1, 1, ACT_NONE, false>(P, LDH, w.d3, Q, LDH);          // mean in Q[m][0..11]

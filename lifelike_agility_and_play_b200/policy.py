@@ -87,7 +87,7 @@ class DevicePolicy:
     def __init__(self, weights, device=0):
         if not _os.path.exists(POLICY_LIB_PATH):
             raise OSError("%s is missing: run `python __graft_entry__.py` (nvcc) first" % POLICY_LIB_PATH)
-        self._lib = _C.CDLL(POLICY_LIB_PATH)
+        self._lib = _C.CDLL(_os.environ.get("LLQ_POLICY_LIB", POLICY_LIB_PATH))     # the override is for tools/policy_bench.py variants
         L = self._lib
         L.llq_policy_create.argtypes = [_C.c_void_p, _C.c_int64, _C.c_int32, _C.POINTER(_C.c_void_p)]
         L.llq_policy_forward.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_int64, _C.c_int32, _C.c_void_p, _C.c_void_p, _C.c_void_p]

@@ -8,7 +8,7 @@ from bench import synthetic_inputs, action_pool_np
 blob, mocap = synthetic_inputs()
 dev = torch.device("cuda", 0)
 stream = torch.cuda.Stream(device=dev); torch.cuda.set_stream(stream)
-libs = [("default", capi.CUDA_LIB_PATH)] + [(os.path.basename(p), p) for p in sorted(glob.glob(os.path.join(os.path.dirname(capi.CUDA_LIB_PATH), "variants", "*.so")))]
+libs = [("default", capi.CUDA_LIB_PATH)] + [(os.path.basename(p), p) for p in sorted(glob.glob(os.path.join(os.path.dirname(capi.CUDA_LIB_PATH), "variants", "libllq_cuda*.so")))]
 envs = [int(x) for x in os.environ.get("ENVS", "1024,4096,16384,65536").split(",")]
 blocks = [int(x) for x in os.environ.get("BLOCKS", "32").split(",")]
 out = []
