@@ -237,7 +237,7 @@ LLQ_DI KinBase mocap_base(const MocapFrame* fc, const MocapFrame* fn, double fra
 // R_bp = world <- B' (URDF body axes), p = base CoM.  q = this leg's joint angles.
 LLQ_DI V3 foot_in_base(const LegConst& L, float q1, float q2, float q3) {
   float c1, s1, c2, s2, c3, s3;
-  sincosf(q1, &s1, &c1); sincosf(-q2, &s2, &c2); sincosf(-q3, &s3, &c3);
+  llq_sincosf(q1, &s1, &c1); llq_sincosf(-q2, &s2, &c2); llq_sincosf(-q3, &s3, &c3);
   V3 p = rot<1>(ld3(L.foot), c3, s3) + ld3(L.j[2].r);
   p = rot<1>(p, c2, s2) + ld3(L.j[1].r);
   p = rot<0>(p, c1, s1) + ld3(L.j[0].r);
@@ -345,7 +345,7 @@ LLQ_DI float flag_dist(V3 c, float fx, float fy) {    // distance of a point to 
 // points of this lane's leg in base coordinates (B' axes about the base reference point)
 LLQ_DI void leg_points(const ModelConst& M, const LegConst& L, int k, const float (&q)[3], V3& hip, V3& wheel, V3& foot) {
   float c1, s1, c2, s2, c3, s3;
-  sincosf(q[0], &s1, &c1); sincosf(-q[1], &s2, &c2); sincosf(-q[2], &s3, &c3);
+  llq_sincosf(q[0], &s1, &c1); llq_sincosf(-q[1], &s2, &c2); llq_sincosf(-q[2], &s3, &c3);
   hip = ld3(L.j[0].r);
   const V3 p2 = hip + rot<0>(ld3(L.j[1].r), c1, s1);
   wheel = p2 + rot<0>(rot<1>(ld3(M.wheel_off[k]), c2, s2), c1, s1);
@@ -437,13 +437,13 @@ LLQ_DI void sepmc_pair_tail(const ModelConst& M, const LegConst& L, int k, int r
     const float yaw = atan2f(Rq.a10, Rq.a00);
     snew[59] = yaw;
     float sy, cy;
-    sincosf(yaw, &sy, &cy);
+    llq_sincosf(yaw, &sy, &cy);
     float* v = snew + 62;
     v[0] = pos.x; v[1] = pos.y; v[2] = pos.z; v[3] = cy; v[4] = sy;                          // percept_vec
     const M3 Ro = qmat(qnormalize(oq));
     const float yawo = atan2f(Ro.a10, Ro.a00);
     float sd, cd;
-    sincosf(yawo - yaw, &sd, &cd);
+    llq_sincosf(yawo - yaw, &sd, &cd);
     const V3 dl = tmul(Rq, V3{(float)(ox - px), (float)(oy - py), (float)(oz - pz)}), ovl = tmul(Rq, ov), owl = tmul(Rq, oww);
     const float oppo[15] = {vis ? 1.f : 0.f, opos.x, opos.y, opos.z, dl.x, dl.y, dl.z, cd, sd, ovl.x, ovl.y, ovl.z, owl.x, owl.y, owl.z};
 #pragma unroll
@@ -660,7 +660,7 @@ LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const floa
           const unsigned long long m = ((unsigned long long)__float_as_uint(sn[67]) << 32) | __float_as_uint(sn[66]);
           const float ang = sn[61] + 6.283185307179586f * (float)(j - 460) * (1.0f / 128.0f);
           float sa, ca;
-          sincosf(ang, &sa, &ca);
+          llq_sincosf(ang, &sa, &ca);
           const float f = ray_boxlist(pos, V3{20.f * ca, 20.f * sa, 0.f}, bxs, m);
           v = f < 0.f ? sn[60] : f * 20.f * sqrtf(ca * ca + sa * sa);
         } else if (j < 913) {
@@ -694,7 +694,7 @@ LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const floa
         } else if (j < 588) {                      // percept_1d: 128 horizontal rays of 20 m; a miss reports |ray_from|
           const float ang = sn[59] + 6.283185307179586f * (float)(j - 460) * (1.0f / 128.0f);
           float sa, ca;
-          sincosf(ang, &sa, &ca);
+          llq_sincosf(ang, &sa, &ca);
           const V3 d = V3{20.f * ca, 20.f * sa, 0.f};
           const bool inside = fabsf(pos.x) < 2.49f && fabsf(pos.y) < 2.49f;
           const float f = inside ? ray_arena_inside(pos, d, fx, fy) : ray_arena(pos, d, fx, fy);
@@ -908,9 +908,9 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     // ---------------- kinematics
     const M3 R = qmat(qp);                       // world <- B'
     JC jc[3];
-    sincosf(q[0], &jc[0].s, &jc[0].c);
-    sincosf(-q[1], &jc[1].s, &jc[1].c);
-    sincosf(-q[2], &jc[2].s, &jc[2].c);
+    llq_sincosf(q[0], &jc[0].s, &jc[0].c);
+    llq_sincosf(-q[1], &jc[1].s, &jc[1].c);
+    llq_sincosf(-q[2], &jc[2].s, &jc[2].c);
     // ---------------- ABA pass 1: velocities, velocity products, bias forces (link coords, link origins)
     SV v0; v0.a = tmul(R, ww); v0.l = tmul(R, vw);
     SV v1 = xmotion<0>(v0, r[0], jc[0].c, jc[0].s);
@@ -1042,7 +1042,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       if (n_ob > 0) {
         const double* ob = mc.ob_table + (size_t)(o0 + ob_id) * 4;
         float sy, cy;
-        sincosf((float)ob[3], &sy, &cy);
+        llq_sincosf((float)ob[3], &sy, &cy);
         const V3 org = V3{(float)(px - ob[1]), (float)(py - ob[2]), (float)pz};      // base position relative to the plate centre
         const V3 wh = p2 + rot<0>(rot<1>(ld3(M.wheel_off[k]), kc2, ks2), kc1, ks1);
         bool hit = plate_hit(org + mul(R, fb), L.foot_r, cy, sy, P.ob_hx, P.ob_hy, P.ob_hz, P.breaking);
@@ -1516,9 +1516,11 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       px += (double)vw.x * P.sim_dt; py += (double)vw.y * P.sim_dt; pz += (double)vw.z * P.sim_dt;
       float fa = norm3(ww);
       float sc;
-      if (fa < 0.001f) sc = 0.5f * dt - dt * dt * dt * 0.020833333333f * fa * fa;
-      else sc = sinf(0.5f * fa * dt) / fa;
-      Q4 dq = Q4{sc * ww.x, sc * ww.y, sc * ww.z, cosf(0.5f * fa * dt)};
+      sc = 0.5f * dt - dt * dt * dt * 0.020833333333f * fa * fa;      // used below 1e-3 rad/s (btMultiBody's series)
+      float sh, ch;
+      llq_sincosf(0.5f * fa * dt, &sh, &ch);
+      if (!(fa < 0.001f)) sc = sh / fa;
+      Q4 dq = Q4{sc * ww.x, sc * ww.y, sc * ww.z, ch};
       qp = qnormalize(qmul(dq, qp));
     }
     bad = bad || !(fabsf(qd[0]) <= P.vmax) || !(fabsf(ww.x) <= P.vmax) || !(fabsf(vw.x) <= P.vmax);
@@ -1710,7 +1712,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     if ((double)spd > max_spd) max_spd = (double)spd;
     const float yaw = atan2f(Rq.a10, Rq.a00);
     float sy, cy;
-    sincosf(yaw, &sy, &cy);
+    llq_sincosf(yaw, &sy, &cy);
     float rew = expf(-fabsf(spd - target_spd)) * expf((cy * ux + sy * uy - 1.0f) * 5.0f) / (float)P.max_steps;
     if (ENV == 3) {                                                    // _compute_avg_spd_reward (PGE:504-539)
       const float reward_rot = expf((cy * ux + sy * uy - 1.0f) * 5.0f);
