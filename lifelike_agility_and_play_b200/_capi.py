@@ -119,7 +119,7 @@ class LlqLibrary:
 
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-CUDA_LIB_PATH = os.path.join(_HERE, "csrc", "libllq_cuda.so")
+CUDA_LIB_PATH = os.environ.get("LLQ_CUDA_LIB", os.path.join(_HERE, "csrc", "libllq_cuda.so"))   # override: profiling variants only
 _cuda_lib = None
 
 

@@ -1285,13 +1285,14 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           for (int t = 0; t < 6; t++) { dg = fmaf(y[t], y[t], dg); ws[(W_YL + i * 6 + t) * BLOCK] = y[t]; }
 #pragma unroll
           for (int m = 0; m < 3; m++) ws[(W_UL + i * 3 + m) * BLOCK] = u[m];
-          if (dir != 0.f) {
+          {   // branch-free: an absent row keeps invdl = rhsl = 0
+            const bool act = dir != 0.f;
             const float rel = dir * qd[i];
             const float pen = dir > 0.f ? q[i] - L.j[i].lower : L.j[i].upper - q[i];
-            invdl[i] = 1.0f / dg;
+            invdl[i] = act ? 1.0f / dg : 0.f;
             const float poserr = pen > -0.04f ? -pen * P.jerp / dt : 0.f;   // split-impulse threshold quirk
-            rhsl[i] = (poserr - rel) * invdl[i];
-            n_limit_rows += 1;
+            rhsl[i] = act ? (poserr - rel) * invdl[i] : 0.f;
+            n_limit_rows += act ? 1 : 0;
           }
         }
       }
@@ -1337,7 +1338,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
 #pragma unroll
             for (int t = 0; t < 6; t++) ys[t] = rows_sm[(W_YL + il * 6 + t) * BLOCK + g0 + jl];
 #pragma unroll
-            for (int m = 0; m < 3; m++) us[m] = own ? rows_sm[(W_UL + il * 3 + m) * BLOCK + g0 + jl] * Di[m] : 0.f;
+            for (int m = 0; m < 3; m++) us[m] = rows_sm[(W_UL + il * 3 + m) * BLOCK + g0 + jl] * (own ? Di[m] : 0.f);
 #pragma unroll
             for (int rr = 0; rr < 3; rr++) {                              // targets: own contact rows, own limit rows
               float a1 = uc[rr][0] * us[0] + uc[rr][1] * us[1] + uc[rr][2] * us[2];
@@ -1348,6 +1349,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
               ws[(W_ALL + rr * 12 + 3 * jl + il) * BLOCK] = a2;
             }
           }
+#ifndef LLQ_SYM_LC
           if (any_con_warp && ((warpmask >> (6 * jl)) & 1u)) {            // sources: contact rows of leg jl, targets: own limit rows
 #pragma unroll 1
             for (int sr = 0; sr < 3; sr++) {
@@ -1360,15 +1362,35 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
               const float u2 = sr == 0 ? uc[0][2] : (sr == 1 ? uc[1][2] : uc[2][2]);
 #pragma unroll
               for (int rr = 0; rr < 3; rr++) {
-                float a2 = own ? (ws[(W_UL + rr * 3 + 0) * BLOCK] * u0 * Di[0] + ws[(W_UL + rr * 3 + 1) * BLOCK] * u1 * Di[1] +
-                                  ws[(W_UL + rr * 3 + 2) * BLOCK] * u2 * Di[2]) : 0.f;
+                float a2 = (ws[(W_UL + rr * 3 + 0) * BLOCK] * u0 * Di[0] + ws[(W_UL + rr * 3 + 1) * BLOCK] * u1 * Di[1] +
+                            ws[(W_UL + rr * 3 + 2) * BLOCK] * u2 * Di[2]) * (own ? 1.f : 0.f);
 #pragma unroll
                 for (int t = 0; t < 6; t++) a2 = fmaf(ws[(W_YL + rr * 6 + t) * BLOCK], ys[t], a2);
                 ws[(W_ALC + rr * 12 + 3 * jl + sr) * BLOCK] = a2;
               }
             }
           }
+#endif
         }
+#ifdef LLQ_SYM_LC
+        // (own limit row rr) x (contact row sr of leg jl) is the transpose of the entry lane jl just wrote for (its contact row sr) x
+        // (limit slot (k, rr)): fetch it from that lane's workspace instead of recomputing 36 nine-term dot products
+        if (any_con_warp) {
+          __syncwarp();
+          const float* other = rows_sm + g0 + (W_ACL + 3 * k) * BLOCK;
+#pragma unroll 1
+          for (int jl = 0; jl < 4; jl++) {
+            if (!((warpmask >> (6 * jl)) & 1u)) continue;
+#pragma unroll
+            for (int sr = 0; sr < 3; sr++)
+#pragma unroll
+              for (int rr = 0; rr < 3; rr++) {
+                const float v = other[(sr * 12 + rr) * BLOCK + jl];
+                ws[(W_ALC + rr * 12 + 3 * jl + sr) * BLOCK] = ((warpmask >> (6 * k + 3 + rr)) & 1u) ? v : 0.f;
+              }
+          }
+        }
+#endif
       }
       // ---- projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration order: limits, normals, friction)
       // an impulse dl_ on contact column (j_, d_) of the env: own contact rows from registers, own limit rows from smem
@@ -1401,16 +1423,19 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
 #pragma unroll
             for (int i = 0; i < 3; i++) {
               if (!((warpmask >> (6 * j + 3 + i)) & 1u)) continue;
-              float dl = 0.f;
-              if (j == k && limdir[i] != 0.f) {
-                dl = rhsl[i] - bl[i] * invdl[i];
-                const float sum = laml[i] + dl;
-                if (sum < 0.f) { dl = -laml[i]; laml[i] = 0.f; }
-                else if (sum > P.max_imp) { dl = P.max_imp - laml[i]; laml[i] = P.max_imp; }
-                else laml[i] = sum;
-              }
+              // branch-free: every lane evaluates its own row i, only the owner of an existing row keeps the result; the
+              // coefficients of a warp-active slot are finite in every env (images of absent rows are zero), so applying
+              // dl = 0 there is exact
+              const bool mine = (j == k) && limdir[i] != 0.f;
+              const float dlc = rhsl[i] - bl[i] * invdl[i];
+              const float sum = laml[i] + dlc;
+              const bool lo = sum < 0.f, hi = sum > P.max_imp;
+              float dl = lo ? -laml[i] : (hi ? P.max_imp - laml[i] : dlc);
+              const float ln = lo ? 0.f : (hi ? P.max_imp : sum);
+              dl = mine ? dl : 0.f;
+              laml[i] = mine ? ln : laml[i];
               dl = __shfl_sync(FULL, dl, j, 4);
-              if ((envmask >> (6 * j + 3 + i)) & 1u) {
+              {
                 const int col = 3 * j + i;
                 bl[0] = fmaf(ws[(W_ALL + 0 * 12 + col) * BLOCK], dl, bl[0]);
                 bl[1] = fmaf(ws[(W_ALL + 1 * 12 + col) * BLOCK], dl, bl[1]);
@@ -1466,7 +1491,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       if (contact) warm = lam[0];
       // ---- total impulse -> velocity change: one back substitution and one down pass (base coordinates)
       float Yt[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, wt[3] = {0.f, 0.f, 0.f};
-      if (contact) {
+      if (any_con_warp) {      // lam = 0 on feet without contact: no per-lane branch needed
 #pragma unroll
         for (int rr = 0; rr < 3; rr++) {
 #pragma unroll
@@ -1478,7 +1503,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       if (any_lim_warp) {
 #pragma unroll
         for (int rr = 0; rr < 3; rr++) {
-          if (limdir[rr] != 0.f) {
+          {                    // laml = 0 on absent rows
 #pragma unroll
             for (int t = 0; t < 6; t++) Yt[t] = fmaf(laml[rr], ws[(W_YL + rr * 6 + t) * BLOCK], Yt[t]);
 #pragma unroll

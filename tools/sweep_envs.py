@@ -21,8 +21,8 @@ for name, path in libs:
             eng.reset()
             pool = torch.from_numpy(action_pool_np(n, 4, 5678)).to(dev)
             obs = torch.empty((n, 207), device=dev); rew = torch.empty((n,), device=dev); done = torch.empty((n,), device=dev, dtype=torch.uint8)
-            K = 100
-            for i in range(20):
+            K = int(os.environ.get("K", 100))
+            for i in range(int(os.environ.get("WARM", 20))):      # joint-limit activity takes ~100 steps to reach its steady state
                 eng.step_device(pool[i % 4].data_ptr(), obs.data_ptr(), rew.data_ptr(), done.data_ptr(), stream=stream.cuda_stream)
             torch.cuda.synchronize()
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
