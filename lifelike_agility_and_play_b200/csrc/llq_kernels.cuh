@@ -1307,7 +1307,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
             ut[rr][sr] = uc[rr][0] * uc[sr][0] * Di[0] + uc[rr][1] * uc[sr][1] * Di[1] + uc[rr][2] * uc[sr][2] * Di[2];
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          if ((warpmask >> (6 * j)) & 1u) {
+          {   // all four legs, always: a warp whose 8 envs all have leg j in the air is a 2 % case, and the uniform skip cost more than it saved
             const float* Yj = rows_sm + g0 + j;
             const bool own = (j == k);
 #pragma unroll
@@ -1349,30 +1349,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
               ws[(W_ALL + rr * 12 + 3 * jl + il) * BLOCK] = a2;
             }
           }
-#ifndef LLQ_SYM_LC
-          if (any_con_warp && ((warpmask >> (6 * jl)) & 1u)) {            // sources: contact rows of leg jl, targets: own limit rows
-#pragma unroll 1
-            for (int sr = 0; sr < 3; sr++) {
-              float ys[6];
-#pragma unroll
-              for (int t = 0; t < 6; t++) ys[t] = rows_sm[(W_YC + sr * 6 + t) * BLOCK + g0 + jl];
-              // u of the source contact row is only needed on its own leg, where it is uc[sr] (sr rolled -> select)
-              const float u0 = sr == 0 ? uc[0][0] : (sr == 1 ? uc[1][0] : uc[2][0]);
-              const float u1 = sr == 0 ? uc[0][1] : (sr == 1 ? uc[1][1] : uc[2][1]);
-              const float u2 = sr == 0 ? uc[0][2] : (sr == 1 ? uc[1][2] : uc[2][2]);
-#pragma unroll
-              for (int rr = 0; rr < 3; rr++) {
-                float a2 = (ws[(W_UL + rr * 3 + 0) * BLOCK] * u0 * Di[0] + ws[(W_UL + rr * 3 + 1) * BLOCK] * u1 * Di[1] +
-                            ws[(W_UL + rr * 3 + 2) * BLOCK] * u2 * Di[2]) * (own ? 1.f : 0.f);
-#pragma unroll
-                for (int t = 0; t < 6; t++) a2 = fmaf(ws[(W_YL + rr * 6 + t) * BLOCK], ys[t], a2);
-                ws[(W_ALC + rr * 12 + 3 * jl + sr) * BLOCK] = a2;
-              }
-            }
-          }
-#endif
         }
-#ifdef LLQ_SYM_LC
         // (own limit row rr) x (contact row sr of leg jl) is the transpose of the entry lane jl just wrote for (its contact row sr) x
         // (limit slot (k, rr)): fetch it from that lane's workspace instead of recomputing 36 nine-term dot products
         if (any_con_warp) {
@@ -1380,7 +1357,6 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           const float* other = rows_sm + g0 + (W_ACL + 3 * k) * BLOCK;
 #pragma unroll 1
           for (int jl = 0; jl < 4; jl++) {
-            if (!((warpmask >> (6 * jl)) & 1u)) continue;
 #pragma unroll
             for (int sr = 0; sr < 3; sr++)
 #pragma unroll
@@ -1390,7 +1366,6 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
               }
           }
         }
-#endif
       }
       // ---- projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration order: limits, normals, friction)
       // an impulse dl_ on contact column (j_, d_) of the env: own contact rows from registers, own limit rows from smem
@@ -1408,7 +1383,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       if (any_con_warp) {   // warm start of the normal rows
 #pragma unroll
         for (int j = 0; j < 4; j++) {
-          if ((warpmask >> (6 * j)) & 1u) {
+          {
             const float l0 = __shfl_sync(FULL, lam[0], j, 4);      // 0 for feet without contact
             LLQ_APPLY_C(j, 0, l0)
           }
@@ -1454,7 +1429,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           // columns of feet without contact are finite, so applying a zero impulse is exact)
 #pragma unroll
           for (int j = 0; j < 4; j++) {   // normal rows, feet in order FR FL HR HL
-            if ((warpmask >> (6 * j)) & 1u) {
+            {
               const bool mine = (j == k) && contact;
               const float dlc = rhs[0] - bq[0] * invd[0];
               const float sum = lam[0] + dlc;
@@ -1469,7 +1444,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
           }
 #pragma unroll
           for (int j = 0; j < 4; j++) {   // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
-            if ((warpmask >> (6 * j)) & 1u) {
+            {
               const bool mine = (j == k) && contact;
               float sa = lam[1] + (rhs[1] - bq[1] * invd[1]), sb = lam[2] + (rhs[2] - bq[2] * invd[2]);
               const float limit = (onwheel ? P.mu_wheel : mu) * lam[0];
