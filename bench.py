@@ -13,6 +13,8 @@ import argparse
 import json
 import os
 
+if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
+    os.environ["NCCL_DEBUG"] = "WARN"                  # NCCL's version banner goes to stdout: keep that to the one JSON line
 os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # CPU arm: idle OpenMP threads must not spin away the container's CPU quota
 import subprocess
 import sys
