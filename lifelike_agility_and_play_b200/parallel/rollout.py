@@ -30,6 +30,9 @@ class RolloutWorker:
         self.done = torch.zeros((self.n,), dtype=torch.uint8, device=self.dev)
         self.val = torch.zeros((self.n,), dtype=torch.float32, device=self.dev)
         self.nlp = torch.zeros((self.n,), dtype=torch.float32, device=self.dev)
+        self.boots = [torch.zeros((self.n,), dtype=torch.float32, device=self.dev) for _ in range(2)]   # V(obs_T) per slab
+        self._scratch = torch.zeros((self.n, ACT_DIM), dtype=torch.float32, device=self.dev)
+        self.bootstrap_value = self.boots[0]
         self.sample, self.seed, self.calls = bool(sample), int(seed), 0
         # everything this worker launches (kernels through the C-ABI and torch's column copies) is ordered on ONE side stream: a
         # NULL stream would mean "the engine's own non-blocking stream" to llq_step_ex and would not order with torch's work
@@ -66,12 +69,18 @@ class RolloutWorker:
 
     def finish_unroll(self):
         """Copy-free `[T, N, 223]` view of the finished records, valid until the end of the NEXT unroll; stepping continues
-        in the other slab, whose row 0 receives observation T."""
+        in the other slab, whose row 0 receives observation T.  `self.bootstrap_value` [N] = V(observation T) for this slab."""
         assert self.t == self.T
         done_buf = self.buf
-        self.buf = self.bufs[1] if done_buf is self.bufs[0] else self.bufs[0]
+        idx = 0 if done_buf is self.bufs[0] else 1
+        self.buf = self.bufs[1 - idx]
         with torch.cuda.stream(self.stream):
+            # V of the observation that follows the last record: the bootstrap of the lambda-return (unroll.slab_records)
+            self.pol.forward_ex(done_buf[self.T].data_ptr(), TRAJ_WIDTH, self.n, self._scratch.data_ptr(), None,
+                                self.boots[idx].data_ptr(), None, 0, 0, self.stream.cuda_stream)
             self.buf[0, :, :OBS_DIM] = done_buf[self.T, :, :OBS_DIM]
+        self.bootstrap_value = self.boots[idx]
+        self.launches += 1
         self.t = 0
         return done_buf[:self.T]
 

@@ -86,13 +86,14 @@ def test_rollout_worker_records_are_aligned(built):
     o0 = eng.reset()
     assert np.array_equal(o0, chk.reset())
     worker.start(o0)
-    views = []
+    views, boots = [], []
     for u in range(2):
         for _ in range(T):
             worker.step()
         v = worker.finish_unroll()
         worker.wait()
         views.append(v.clone())                                        # the view itself is recycled after the next unroll
+        boots.append(worker.bootstrap_value.clone())
     torch.cuda.synchronize()
     slab = torch.cat(views, 0).cpu().numpy()                       # [2T, N, 223]
     obs = o0
@@ -106,6 +107,10 @@ def test_rollout_worker_records_are_aligned(built):
         assert np.abs(slab[t, :, COL_VALUE] - host_pol.value(obs)).max() < 1e-4 * (1 + np.abs(host_pol.value(obs)).max())
         obs, rew, done = chk.step(a)
         assert np.array_equal(rew, slab[t, :, COL_REWARD]) and np.array_equal(done.astype(np.float32), slab[t, :, COL_DONE])
+    # bootstrap of slab 0 = V(obs_T) = the value recorded with the first step of slab 1; `obs` now holds the observation after the
+    # last step = what slab 1's bootstrap was computed from
+    assert np.abs(boots[0].cpu().numpy() - slab[T, :, COL_VALUE]).max() < 1e-5
+    assert np.abs(boots[1].cpu().numpy() - host_pol.value(obs)).max() < 1e-4 * (1 + np.abs(host_pol.value(obs)).max())
     unrolls = slab_to_unrolls(torch.from_numpy(slab), "m", gamma=0.95, lam=0.95)
     assert len(unrolls) == n and unrolls[0][1].size == 2 * T * RECORD_WIDTH
     pol.close(); eng.close(); chk.close()
