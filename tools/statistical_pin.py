@@ -7,9 +7,11 @@ engine and compare (a) how well it tracks -- per-step reward, episode length rel
 env (first four arrays of the model file).  A policy trained on Bullet only tracks, and only reproduces its own training
 distribution, if the dynamics it meets here behave like Bullet's.
 
-    python tools/statistical_pin.py [--engine oracle|cuda] [--envs 64] [--steps 600] [--out profiles/r01_statistical_pin.json]
+    python tools/statistical_pin.py [--engine oracle|cuda] [--policy host|device] [--envs 64] [--steps 600] [--out profiles/...json]
+    python tools/statistical_pin.py --stage DIR      # pack model weights + mocap table into DIR (git-ignored scratch that travels
+                                                     # with gpurun), then on the GPU box: --staged DIR --engine cuda --policy device
 
-Needs /root/reference (model + mocap data); nothing under tests/ depends on it."""
+Needs /root/reference (model + mocap data) or a staged copy of the two; nothing under tests/ depends on it."""
 import argparse
 import json
 import os
@@ -22,7 +24,7 @@ sys.path.insert(0, ROOT)
 sys.path.insert(0, os.path.join(ROOT, "tools"))
 
 from lifelike_agility_and_play_b200 import _capi as capi  # noqa: E402
-from lifelike_agility_and_play_b200.mocap import load_mocap  # noqa: E402
+from lifelike_agility_and_play_b200.mocap import load_mocap, load_packed, save_packed  # noqa: E402
 from lifelike_agility_and_play_b200.model.compile_model import load_model_blob  # noqa: E402
 from lifelike_agility_and_play_b200.policy import PmcPolicy  # noqa: E402
 from load_reference_model import load  # noqa: E402
@@ -38,9 +40,30 @@ def main():
     ap.add_argument("--obstacle", type=int, default=0)
     ap.add_argument("--out", default="")
     ap.add_argument("--cfg", default="{}", help="python dict of llq_config overrides, e.g. \"{'contact_erp': 0.2}\"")
+    ap.add_argument("--policy", default="host", choices=["host", "device"], help="numpy forward or the CUDA policy kernel (llq_policy.cu)")
+    ap.add_argument("--stage", default="", help="write weights.npz + mocap.npz to this directory and exit")
+    ap.add_argument("--staged", default="", help="read weights.npz + mocap.npz from this directory instead of /root/reference")
     a = ap.parse_args()
-    pol = PmcPolicy(load(a.model).model)
-    mocap = load_mocap(a.data)
+    if a.staged:
+        wz = np.load(os.path.join(a.staged, "weights.npz"))
+        weights = [wz["w%d" % i] for i in range(28)]
+        mocap = load_packed(os.path.join(a.staged, "mocap.npz"))
+    else:
+        weights = load(a.model).model
+        mocap = load_mocap(a.data)
+    if a.stage:
+        os.makedirs(a.stage, exist_ok=True)
+        np.savez(os.path.join(a.stage, "weights.npz"), **{"w%d" % i: np.asarray(w, np.float32) for i, w in enumerate(weights)})
+        save_packed(mocap, os.path.join(a.stage, "mocap.npz"))
+        print("staged", a.stage)
+        return
+    pol = PmcPolicy(weights)
+    dev_pol = None
+    if a.policy == "device":
+        import torch
+        from lifelike_agility_and_play_b200.policy import DevicePolicy
+        dev_pol = DevicePolicy(weights, device=0)
+        t_act = torch.zeros((a.envs, 12), device="cuda", dtype=torch.float32)
     if a.engine == "oracle":
         from oracle import oracle
         lib = oracle.load()
@@ -60,7 +83,13 @@ def main():
     frames = np.diff(mocap.offsets)
     X = []
     for t in range(a.steps):
-        act = pol.act(obs)
+        if dev_pol is not None:
+            t_obs = torch.from_numpy(np.ascontiguousarray(obs, np.float32)).cuda()
+            dev_pol.forward(t_obs.data_ptr(), obs.shape[1], a.envs, t_act.data_ptr(), None, None)
+            torch.cuda.synchronize()
+            act = t_act.cpu().numpy()
+        else:
+            act = pol.act(obs)
         X.append(obs[:, :135].copy())
         prev_clip, prev_t0 = clip0.copy(), t0.copy()
         obs, r, d = eng.step(act.astype(np.float32))
@@ -92,7 +121,7 @@ def main():
     m_ref, s_ref = pol.prop_mean[newest], pol.prop_std[newest]
     z = (mean[newest] - m_ref) / s_ref
     rep = {
-        "engine": a.engine, "envs": n, "steps": a.steps, "env_steps": int(n * a.steps), "episodes_finished": len(ep_len),
+        "engine": a.engine, "policy": a.policy, "envs": n, "steps": a.steps, "env_steps": int(n * a.steps), "episodes_finished": len(ep_len),
         "mean_reward_per_step": float(np.mean(ep_rew)) if ep_rew else None,
         "median_episode_steps": float(np.median(ep_len)) if ep_len else None,
         "fraction_of_remaining_clip_survived_mean": float(np.mean(ep_frac)) if ep_frac else None,
