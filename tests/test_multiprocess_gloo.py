@@ -66,3 +66,9 @@ def test_two_rank_shards_gather_equals_single_process(built):
     _rollout(0, 1, N_PER * WORLD, ref)
     assert gathered.shape == (T, N_PER * WORLD, TRAJ_WIDTH)
     assert np.array_equal(gathered, ref.buf.numpy()), "sharded rollout differs from the single-process rollout"
+    # learner side: the gathered slab turns into one TLeague-format unroll per global env (parallel/unroll.py), identical to the
+    # single-process ones
+    from lifelike_agility_and_play_b200.parallel import RECORD_WIDTH, slab_to_unrolls
+    ua, ub = slab_to_unrolls(torch.from_numpy(gathered), "k"), slab_to_unrolls(ref.buf, "k")
+    assert len(ua) == N_PER * WORLD and ua[0][1].shape == (T * RECORD_WIDTH,)
+    assert all(np.array_equal(x[1], y[1]) and x[3] == y[3] for x, y in zip(ua, ub))
