@@ -28,4 +28,17 @@ for n in (5, 70):
     for t in range(25):
         e.step((0.4 * rng.standard_normal((n, 12))).astype(np.float32))
     e.close()
+# policy kernel (3xTF32 MMA layers, value head, sampling) on a ragged row count, rows read in place with a slab stride
+import torch
+from lifelike_agility_and_play_b200.policy import DevicePolicy
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tests"))
+from test_policy import random_weights
+pol = DevicePolicy(random_weights(2), device=0)
+for n in (1, 77):
+    o = torch.randn((n, 223), device="cuda"); a = torch.zeros((n, 12), device="cuda"); v = torch.zeros((n,), device="cuda")
+    p = torch.zeros((n,), device="cuda"); c = torch.zeros((n,), device="cuda", dtype=torch.int32)
+    pol.forward(o.data_ptr(), 223, n, a.data_ptr(), c.data_ptr(), None)
+    pol.forward_ex(o.data_ptr(), 223, n, a.data_ptr(), c.data_ptr(), v.data_ptr(), p.data_ptr(), 5, 9, None)
+    torch.cuda.synchronize()
+pol.close()
 print("sanitize run done")
