@@ -91,3 +91,28 @@ def test_contact_needs_proximity(make_oracle):
     eng.step(np.zeros((1, 12), np.float32))
     assert eng.counters()[2] == c0
     assert np.all(eng.get(capi.F_WARMSTART) == 0)
+
+
+def test_translation_invariance_of_the_tracking_env(oracle_lib, blob, small_mocap):
+    """Domain property (flat infinite ground): shifting every mocap clip by (dx, dy) shifts the rollout and nothing else -- the
+    body-frame observation, the reward and the termination of every step are unchanged.  World positions are carried in fp64
+    on both engines precisely so that this holds tens of metres away from the origin."""
+    from lifelike_agility_and_play_b200._capi import VecEngine, F_STATE
+    from lifelike_agility_and_play_b200.mocap import MocapTable
+    shifted = MocapTable(small_mocap.frames.copy(), small_mocap.offsets, small_mocap.frame_dt, small_mocap.names)
+    shifted.frames[:, 0] += 37.25; shifted.frames[:, 1] -= 12.5
+    n = 24
+    a = VecEngine(oracle_lib, n, blob, small_mocap, seed=8, auto_reset=1)
+    b = VecEngine(oracle_lib, n, blob, shifted, seed=8, auto_reset=1)
+    oa, ob = a.reset(), b.reset()
+    assert np.abs(oa - ob).max() < 1e-6
+    rng = np.random.default_rng(3)
+    for t in range(40):
+        act = (0.15 * rng.standard_normal((n, 12))).astype(np.float32)
+        (oa, ra, da), (ob, rb, db) = a.step(act), b.step(act)
+        assert np.array_equal(da, db)
+        assert np.abs(oa - ob).max() < 2e-5 and np.abs(ra - rb).max() < 2e-6, (t, np.abs(oa - ob).max())
+    sa, sb = a.get(F_STATE), b.get(F_STATE)
+    assert np.abs(sb[:, 0] - sa[:, 0] - 37.25).max() < 1e-4 and np.abs(sb[:, 1] - sa[:, 1] + 12.5).max() < 1e-4
+    assert np.abs(sa[:, 2:] - sb[:, 2:]).max() < 2e-5
+    a.close(); b.close()
