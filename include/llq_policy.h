@@ -41,6 +41,12 @@ int llq_policy_forward(llq_policy_handle h, const float* d_obs, int64_t obs_ld, 
  *     different `counter` every step.  NULL: d_actions is the mean (argmax=True). */
 int llq_policy_forward_ex(llq_policy_handle h, const float* d_obs, int64_t obs_ld, int32_t n, float* d_actions, int32_t* d_codes,
                           float* d_values, float* d_neglogp, uint64_t seed, uint64_t counter, void* stream);
+/* Record variant for the rollout worker (the kernels write the whole trajectory record): as llq_policy_forward_ex, but
+ * value and -log p of row i go to d_values[i * out_ld] / d_neglogp[i * out_ld] (out_ld = the slab's row stride puts them straight into
+ * the value / neglogp columns of a [N, 223] record row), and the Gaussian noise is keyed by the GLOBAL row row_gid0 + i so that
+ * shards with equal seeds draw different noise (one actor process per shard in the reference draws from its own np.random). */
+int llq_policy_forward_rec(llq_policy_handle h, const float* d_obs, int64_t obs_ld, int32_t n, float* d_actions, int32_t* d_codes,
+                           float* d_values, float* d_neglogp, int64_t out_ld, uint64_t seed, uint64_t counter, int64_t row_gid0, void* stream);
 const char* llq_policy_last_error(void);
 
 #ifdef __cplusplus

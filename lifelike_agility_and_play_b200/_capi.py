@@ -141,6 +141,30 @@ def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
 
 
+class _PinnedBlock:
+    """Page-locked host block (llq_host_alloc).  numpy views made with ``np.asarray(block)`` keep the block alive through
+    their ``base``; the memory is returned to the driver only when the last view is gone, not when the engine closes."""
+
+    def __init__(self, lib, shape, dtype):
+        self._lib, self.shape, self.dtype = lib, tuple(int(x) for x in shape), np.dtype(dtype)
+        self.nbytes = int(np.prod(self.shape)) * self.dtype.itemsize
+        p = C.c_void_p()
+        lib.check(lib.lib.llq_host_alloc(C.byref(p), self.nbytes))
+        self._p = p
+
+    @property
+    def __array_interface__(self):
+        return {"shape": self.shape, "typestr": self.dtype.str, "data": (self._p.value, False), "version": 3}
+
+    def __del__(self):
+        try:
+            if self._p:
+                self._lib.lib.llq_host_free(self._p)
+                self._p = None
+        except Exception:
+            pass
+
+
 class VecEngine:
     """N lock-step environments behind one ``llq_handle``.
 
@@ -189,9 +213,6 @@ class VecEngine:
         if self._h:
             self.lib.lib.llq_destroy(self._h)
             self._h = C.c_void_p()
-            for p in getattr(self, "_pinned", []):
-                self.lib.lib.llq_host_free(p)
-            self._pinned = []
 
     def __del__(self):
         try:
@@ -227,21 +248,17 @@ class VecEngine:
             done = np.empty((self.n,), np.uint8)
         else:
             obs, rew, done = out
+            for arr, shape, dt in ((obs, (self.n, self.obs_dim), np.float32), (rew, (self.n,), np.float32), (done, (self.n,), np.uint8)):
+                if not (isinstance(arr, np.ndarray) and arr.shape == shape and arr.dtype == dt and arr.flags.c_contiguous and arr.flags.writeable):
+                    raise ValueError("out arrays must be writeable C-contiguous %s arrays of shape %s" % (np.dtype(dt).name, shape))
         self.lib.check(self.lib.lib.llq_step(self._h, _ptr(a), _ptr(obs), _ptr(rew), _ptr(done)))
         return obs, rew, done
 
     # -- page-locked I/O (LLQ_IO_PINNED): no staging memcpy on either side
     def pinned_array(self, shape, dtype):
-        """numpy array over page-locked host memory owned by this engine (freed on close)."""
-        dtype = np.dtype(dtype)
-        nbytes = int(np.prod(shape)) * dtype.itemsize
-        p = C.c_void_p()
-        self.lib.check(self.lib.lib.llq_host_alloc(C.byref(p), nbytes))
-        if not hasattr(self, "_pinned"):
-            self._pinned = []
-        self._pinned.append(p)
-        buf = (C.c_char * nbytes).from_address(p.value)
-        return np.frombuffer(buf, dtype=dtype).reshape(shape)
+        """numpy array over page-locked host memory; the block is freed when the last view of it is released (it may outlive
+        the engine -- TLeague queues observation objects for another thread, distill_actor.py:267-270)."""
+        return np.asarray(_PinnedBlock(self.lib, shape, dtype))
 
     def pinned_io(self):
         """(actions, obs, reward, done) page-locked buffers for step_pinned."""
@@ -249,7 +266,9 @@ class VecEngine:
                 self.pinned_array((self.n,), np.float32), self.pinned_array((self.n,), np.uint8))
 
     def step_pinned(self, actions, obs, reward, done):
-        """Like step(), but all four arrays must be page-locked (pinned_io()); results land in obs / reward / done."""
+        """Like step(), but the arrays must be page-locked (pinned_io()); results land in obs / reward / done.  obs may be None:
+        the observation then stays on the device (llq_get_field / an on-device policy reads it there) and only reward / done
+        travel back."""
         self.lib.check(self.lib.lib.llq_step_ex(self._h, _ptr(actions), _ptr(obs), self.obs_dim, _ptr(reward), _ptr(done),
                                                  LLQ_IO_PINNED, None))
         return obs, reward, done

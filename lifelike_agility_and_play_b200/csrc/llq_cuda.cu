@@ -58,6 +58,8 @@ struct llq_engine {
   int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   llq::StepParams P{};
   bool profile = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool ev_valid = false;
+  int record = 0;              // "record" option: the step kernel also writes action | reward | done behind the observation of a slab row
+  unsigned smem_attr_set = 0;  // bit (ENV * 3 + block index): cudaFuncAttributeMaxDynamicSharedMemorySize raised on this handle's device
 };
 
 namespace {
@@ -112,14 +114,19 @@ int ensure_scratch(llq_handle h, size_t bytes) {
 llq::MocapDev mocap_dev(llq_handle h) { return llq::MocapDev{h->d_frames, h->d_clip_off, h->n_clips, h->d_ob_table, h->d_ob_off}; }
 
 template <int BLOCK, int ENV>
-void launch_step_t(llq_handle h, const llq::EnvArrays& E, const float* d_actions, float* obs2, long long ld, cudaStream_t s) {
+int launch_step_t(llq_handle h, const llq::EnvArrays& E, const float* d_actions, float* obs2, long long ld, cudaStream_t s) {
   int threads = 4 * h->cfg.n_envs;
   int grid = (threads + BLOCK - 1) / BLOCK;
   const size_t smem = sizeof(float) * llq::kRowFloats * BLOCK;
-  static bool attr_set = false;   // per template instance
-  if (!attr_set) { cudaFuncSetAttribute(llq::pmc_step_kernel<BLOCK, ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem); attr_set = true; }
+  // the opt-in above 48 kB is a per-device function attribute: raise it once per handle (= per device), not once per process
+  const unsigned bit = 1u << (ENV * 3 + (BLOCK == 32 ? 0 : (BLOCK == 64 ? 1 : 2)));
+  if (!(h->smem_attr_set & bit)) {
+    CK(cudaFuncSetAttribute(llq::pmc_step_kernel<BLOCK, ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->smem_attr_set |= bit;
+  }
   llq::pmc_step_kernel<BLOCK, ENV><<<grid, BLOCK, smem, s>>>(E, mocap_dev(h), h->P, h->d_model, d_actions, obs2, ld, h->d_winner[h->parity],
-                                                             (unsigned long long)h->cfg.seed, (long long)h->cfg.global_env_offset);
+                                                             (unsigned long long)h->cfg.seed, (long long)h->cfg.global_env_offset, h->record);
+  return LLQ_OK;
 }
 template <int BLOCK, int ENV>
 void launch_reset_t(llq_handle h, const llq::EnvArrays& E, const llq::ResetParams& RP, float* obs2, long long ld, cudaStream_t s) {
@@ -128,32 +135,20 @@ void launch_reset_t(llq_handle h, const llq::EnvArrays& E, const llq::ResetParam
   size_t smem = sizeof(double) * (size_t)(h->n_clips > 0 ? h->n_clips : 1);
   llq::pmc_reset_kernel<BLOCK, ENV><<<grid, BLOCK, smem, s>>>(E, mocap_dev(h), h->P, h->d_model, RP, obs2, ld);
 }
-void launch_step(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
-  const bool epmc = h->cfg.env_kind == LLQ_ENV_EPMC;
-  if (epmc && h->cfg.element_id != 0) {        // corridor arenas: the box-aware instance
-    switch (h->block) {
-      case 32: launch_step_t<32, 3>(h, E, a, obs2, ld, s); break;
-      case 64: launch_step_t<64, 3>(h, E, a, obs2, ld, s); break;
-      default: launch_step_t<128, 3>(h, E, a, obs2, ld, s); break;
-    }
-    h->counters[4]++;
-    return;
-  }
-  if (h->cfg.env_kind == LLQ_ENV_SEPMC) {
-    switch (h->block) {
-      case 32: launch_step_t<32, 2>(h, E, a, obs2, ld, s); break;
-      case 64: launch_step_t<64, 2>(h, E, a, obs2, ld, s); break;
-      default: launch_step_t<128, 2>(h, E, a, obs2, ld, s); break;
-    }
-    h->counters[4]++;
-    return;
-  }
+template <int ENV>
+int launch_step_b(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
   switch (h->block) {
-    case 32: if (epmc) launch_step_t<32, 1>(h, E, a, obs2, ld, s); else launch_step_t<32, 0>(h, E, a, obs2, ld, s); break;
-    case 64: if (epmc) launch_step_t<64, 1>(h, E, a, obs2, ld, s); else launch_step_t<64, 0>(h, E, a, obs2, ld, s); break;
-    default: if (epmc) launch_step_t<128, 1>(h, E, a, obs2, ld, s); else launch_step_t<128, 0>(h, E, a, obs2, ld, s); break;
+    case 32: return launch_step_t<32, ENV>(h, E, a, obs2, ld, s);
+    case 64: return launch_step_t<64, ENV>(h, E, a, obs2, ld, s);
+    default: return launch_step_t<128, ENV>(h, E, a, obs2, ld, s);
   }
+}
+int launch_step(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
+  const bool epmc = h->cfg.env_kind == LLQ_ENV_EPMC;
   h->counters[4]++;
+  if (epmc && h->cfg.element_id != 0) return launch_step_b<3>(h, E, a, obs2, ld, s);        // corridor arenas: the box-aware instance
+  if (h->cfg.env_kind == LLQ_ENV_SEPMC) return launch_step_b<2>(h, E, a, obs2, ld, s);
+  return epmc ? launch_step_b<1>(h, E, a, obs2, ld, s) : launch_step_b<0>(h, E, a, obs2, ld, s);
 }
 void launch_reset(llq_handle h, const llq::EnvArrays& E, const llq::ResetParams& RP, float* obs2, long long ld, cudaStream_t s) {
   if (h->cfg.env_kind == LLQ_ENV_EPMC && h->cfg.element_id != 0) launch_reset_t<128, 3>(h, E, RP, obs2, ld, s);
@@ -513,6 +508,8 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
   if (!actions) return fail(LLQ_EINVAL, "null actions");
   const size_t od = (size_t)h->obs_dim;
   if (obs && obs_ld < (int64_t)od) return fail(LLQ_EINVAL, "obs_ld smaller than the observation width");
+  if (h->record && io_mode == LLQ_IO_DEVICE && obs && obs_ld < (int64_t)od + 14)
+    return fail(LLQ_EINVAL, "record mode needs obs_ld >= observation width + 14 (action 12 | reward | done)");
   const size_t n = (size_t)h->cfg.n_envs;
   llq::EnvArrays E = h->E;
   const float* d_act;
@@ -535,7 +532,8 @@ int llq_step_ex(llq_handle h, const float* actions, float* obs, int64_t obs_ld, 
     return fail(LLQ_EINVAL, "bad io_mode");
   }
   if (h->profile) CK(cudaEventRecord(h->ev[0], s));
-  launch_step(h, E, d_act, obs2, (long long)obs_ld, s);
+  rc = launch_step(h, E, d_act, obs2, (long long)obs_ld, s);
+  if (rc) return rc;
   if (h->profile) CK(cudaEventRecord(h->ev[1], s));
   // prioritized-sampling table update (PLE:235-240) + auto reset of finished envs
   llq::ResetParams RP = reset_params(h, h->cfg.auto_reset ? 0 : 3, true);
@@ -661,7 +659,11 @@ int llq_set_field(llq_handle h, int field, const void* src) {
       for (size_t i = 0; i < n; i++) if (c[i] < 0 || c[i] >= h->n_clips) return fail(LLQ_EINVAL, "clip id out of range");
       CK(cudaMemcpy(h->E.clip, src, sizeof(int) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
     }
-    case LLQ_F_TIME: CK(cudaMemcpy(h->E.time, src, sizeof(double) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
+    case LLQ_F_TIME: {
+      const double* t = (const double*)src;      // the clock indexes the mocap table (ML:65-67): reject what the reference would raise on
+      for (size_t i = 0; i < n; i++) if (!(t[i] >= 0.0) || !std::isfinite(t[i])) return fail(LLQ_EINVAL, "env clock must be finite and >= 0");
+      CK(cudaMemcpy(h->E.time, src, sizeof(double) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
+    }
     case LLQ_F_REWARD_SUM: CK(cudaMemcpy(h->E.reward_sum, src, sizeof(float) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
     case LLQ_F_EPISODE_STEPS: CK(cudaMemcpy(h->E.episode_steps, src, sizeof(int) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
     case LLQ_F_EPISODE_ID: CK(cudaMemcpy(h->E.episode, src, sizeof(long long) * n, cudaMemcpyHostToDevice)); return LLQ_OK;
@@ -707,6 +709,12 @@ int llq_set_option(llq_handle h, const char* name, double value) {
   if (!std::strcmp(name, "profile")) {
     h->profile = value != 0;
     if (h->profile && !h->ev[0]) for (int i = 0; i < 3; i++) CK(cudaEventCreate(&h->ev[i]));
+    return LLQ_OK;
+  }
+  if (!std::strcmp(name, "record")) {
+    const int v = (int)value;
+    if (v < 0 || v > 2) return fail(LLQ_EINVAL, "record must be 0 (off), 1 (same slab row as the observation) or 2 (the row before)");
+    h->record = v;
     return LLQ_OK;
   }
   if (!std::strcmp(name, "block")) {

@@ -756,7 +756,7 @@ LLQ_DI void prefetch_model(const ModelConst* gmodel, ModelConst* smodel, int nth
 template <int BLOCK, int ENV>
 __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev mc, StepParams P, const ModelConst* __restrict__ gmodel,
                                                          const float* __restrict__ actions, float* obs2, long long obs2_ld,
-                                                         int* __restrict__ winner, unsigned long long seed, long long gid0) {
+                                                         int* __restrict__ winner, unsigned long long seed, long long gid0, int record) {
   __shared__ __align__(16) ModelConst M;
   __shared__ __align__(16) float s_new[BLOCK / 4][kNewObs];
   __shared__ __align__(16) float s_hist[BLOCK / 4][kHist];
@@ -1528,12 +1528,18 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
     if (ENV == 0) {
       frame_id = (int)floor(time / P.frame_dt);
       frame_frac = (time - frame_id * P.frame_dt) / P.frame_dt;
+      // a cursor past the clip's playable range (auto_reset off and a finished env stepped on, or a clock set through
+      // llq_set_field) stays on the clip's last playable frame instead of walking into the next clip; the reference raises there
+      const int last = mc.clip_off[clip + 1] - mc.clip_off[clip] - P.margin - 1;
+      if (frame_id > last) { frame_id = last; frame_frac = 0.0; }
+      if (frame_id < 0) { frame_id = 0; frame_frac = 0.0; }
     }
     time += P.sim_dt;
   }
 
   // ================= end of the policy step: observation, reward, termination =================
   bool done = false;
+  float rew_out = 0.f;
   if (ENV == 0) {
   qb = qmul(qp, qI);                                 // back to the pybullet (inertial-frame) convention
   float* snew = &s_new[threadIdx.x >> 2][0];
@@ -1610,7 +1616,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       float rs = E.reward_sum[env] + rew;
       E.reward_sum[env] = rs;
       E.episode_steps[env] += 1;
-      E.reward[env] = rew;
+      E.reward[env] = rew; rew_out = rew;
       E.done[env] = done ? 1 : 0;
       E.kin[env] = (float)oc.kb.px; E.kin[N + env] = (float)oc.kb.py; E.kin[2 * N + env] = (float)oc.kb.pz;
       E.kin[3 * N + env] = oc.kb.q.x; E.kin[4 * N + env] = oc.kb.q.y; E.kin[5 * N + env] = oc.kb.q.z; E.kin[6 * N + env] = oc.kb.q.w;
@@ -1671,7 +1677,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
         E.time[env] = time;
         E.reward_sum[env] += rew;
         E.episode_steps[env] += 1;
-        E.reward[env] = rew;
+        E.reward[env] = rew; rew_out = rew;
         E.done[env] = done ? 1 : 0;
         double* A = E.aux;
         A[env] = counter; A[N + env] = PS.with_flag; A[2 * N + env] = PS.flag_x; A[3 * N + env] = PS.flag_y; A[5 * N + env] = PS.visible;
@@ -1749,7 +1755,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
         E.time[env] = time;
         E.reward_sum[env] += rew;
         E.episode_steps[env] += 1;
-        E.reward[env] = rew;
+        E.reward[env] = rew; rew_out = rew;
         E.done[env] = done ? 1 : 0;
         double* A = E.aux;
         A[env] = counter; A[N + env] = cmd_freq; A[2 * N + env] = tgx; A[3 * N + env] = tgy; A[4 * N + env] = target_spd;
@@ -1758,6 +1764,16 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
         A[14 * N + env] = push_draws; A[15 * N + env] = cmd_draws;
       }
     }
+  }
+  // record mode (llq_set_option "record"): the trajectory columns action 12 | reward | done behind the observation of the slab row
+  // (the kernel writes the whole record, no column copies afterwards); neglogp / value belong to the policy kernel
+  // record == 2: into the slab row before the one that receives the observation (the [T+1, N, ld] layout of parallel/rollout.py, where
+  // row t holds obs_t and this step's a_t | r_t | done_t while obs_{t+1} goes to row t+1)
+  if (record && obs2 && valid) {
+    float* row = obs2 + (size_t)env * obs2_ld + ObsW<ENV>::value - (record == 2 ? (long long)N * obs2_ld : 0ll);
+#pragma unroll
+    for (int i = 0; i < 3; i++) row[3 * k + i] = act[i];
+    if (k == 0) { row[12] = rew_out; row[13] = done ? 1.f : 0.f; }
   }
   // counters: one atomic per warp
   {
@@ -1989,8 +2005,10 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
   } else {
   int clip; double t0;
   long long ep = E.episode[env];
-  if (RP.mode == 2) { clip = RP.clip_in[env]; t0 = RP.time_in[env]; }
-  else {
+  if (RP.mode == 2) {
+    clip = RP.clip_in[env]; t0 = RP.time_in[env];
+    if (!doit) { clip = 0; t0 = 0.0; }     // entries of masked-out envs are not validated by the host: never index the table with them
+  } else {
     long long gid = RP.gid0 + env;
     unsigned c4[4] = {(unsigned)gid, (unsigned)((unsigned long long)gid >> 32), (unsigned)ep, (unsigned)((unsigned long long)ep >> 32)};
     philox4x32_10(c4, (unsigned)RP.seed, (unsigned)(RP.seed >> 32));
@@ -2003,6 +2021,11 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
   }
   int frame_id = (int)floor(t0 / P.frame_dt);
   double frac = (t0 - frame_id * P.frame_dt) / P.frame_dt;
+  {
+    const int last = mc.clip_off[clip + 1] - mc.clip_off[clip] - P.margin - 1;
+    if (frame_id > last) { frame_id = last; frac = 0.0; }
+    if (frame_id < 0) { frame_id = 0; frac = 0.0; }
+  }
   const MocapFrame* f0 = mc.frames + mc.clip_off[clip] + frame_id;
   KinBase kb = mocap_base(f0, f0 + 1, frac, P.frame_dt);
   float inv = (float)(1.0 / P.frame_dt), fr = (float)frac;

@@ -162,7 +162,7 @@ __device__ __forceinline__ uint4 philox4x32(uint4 c, uint2 k) {
 __global__ void __launch_bounds__(THREADS) pmc_policy_kernel(const float* __restrict__ obs, long long ld, int n, Weights w,
                                                              float* __restrict__ act, int* __restrict__ codes,
                                                              float* __restrict__ values, float* __restrict__ neglogp,
-                                                             unsigned long long seed, unsigned long long counter) {
+                                                             unsigned long long seed, unsigned long long counter, long long out_ld, long long row_gid0) {
   extern __shared__ __align__(16) float sm[];
   float* X = sm;                       // [M][LDX]  normalised observation, column 207 = 0
   float* P = X + M * LDX;              // [M][LDH]
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(THREADS) pmc_policy_kernel(const float* __rest
       for (int k = lane; k < H; k += 32) s = fmaf(Q[m * LDH + k], w.v3w[k], s);
 #pragma unroll
       for (int o = 16; o > 0; o >>= 1) s += __shfl_xor_sync(0xffffffffu, s, o);
-      if (lane == 0 && row0 + m < n) values[row0 + m] = s + w.v3b[0];
+      if (lane == 0 && row0 + m < n) values[(size_t)(row0 + m) * out_ld] = s + w.v3b[0];
     }
     __syncthreads();
   }
@@ -274,7 +274,7 @@ __global__ void __launch_bounds__(THREADS) pmc_policy_kernel(const float* __rest
       float eps[NACT];
 #pragma unroll
       for (int q4 = 0; q4 < NACT / 4; q4++) {
-        const uint4 r = philox4x32(make_uint4((uint32_t)row, (uint32_t)q4, (uint32_t)counter, (uint32_t)(counter >> 32)),
+        const uint4 r = philox4x32(make_uint4((uint32_t)(row_gid0 + row), (uint32_t)q4, (uint32_t)counter, (uint32_t)(counter >> 32)),
                                    make_uint2((uint32_t)seed, (uint32_t)(seed >> 32)));
         const float u0 = ((float)r.x + 0.5f) * 2.3283064365386963e-10f, u1 = (float)r.y * 2.3283064365386963e-10f;
         const float u2 = ((float)r.z + 0.5f) * 2.3283064365386963e-10f, u3 = (float)r.w * 2.3283064365386963e-10f;
@@ -291,7 +291,7 @@ __global__ void __launch_bounds__(THREADS) pmc_policy_kernel(const float* __rest
         a[j] = fmaf(expf(ls), eps[j], mean[j]);
         nl += 0.5f * eps[j] * eps[j] + ls;
       }
-      neglogp[row] = nl;
+      neglogp[(size_t)row * out_ld] = nl;
     }
   }
 }
@@ -381,15 +381,20 @@ int llq_policy_destroy(llq_policy_handle h) {
   return LLQ_OK;
 }
 
-int llq_policy_forward_ex(llq_policy_handle h, const float* d_obs, int64_t obs_ld, int32_t n, float* d_actions, int32_t* d_codes,
-                          float* d_values, float* d_neglogp, uint64_t seed, uint64_t counter, void* stream) {
-  if (!h || !d_obs || !d_actions || n <= 0 || obs_ld < N_OBS) return fail(LLQ_EINVAL, "bad arguments");
+int llq_policy_forward_rec(llq_policy_handle h, const float* d_obs, int64_t obs_ld, int32_t n, float* d_actions, int32_t* d_codes,
+                           float* d_values, float* d_neglogp, int64_t out_ld, uint64_t seed, uint64_t counter, int64_t row_gid0, void* stream) {
+  if (!h || !d_obs || !d_actions || n <= 0 || obs_ld < N_OBS || out_ld < 1) return fail(LLQ_EINVAL, "bad arguments");
   cudaSetDevice(h->device);
   pmc_policy_kernel<<<(n + M - 1) / M, THREADS, SMEM_BYTES, (cudaStream_t)stream>>>(d_obs, (long long)obs_ld, n, h->w, d_actions, d_codes,
-                                                                                      d_values, d_neglogp, seed, counter);
+                                                                                      d_values, d_neglogp, seed, counter, (long long)out_ld, (long long)row_gid0);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(LLQ_ECUDA, cudaGetErrorString(e));
   return LLQ_OK;
+}
+
+int llq_policy_forward_ex(llq_policy_handle h, const float* d_obs, int64_t obs_ld, int32_t n, float* d_actions, int32_t* d_codes,
+                          float* d_values, float* d_neglogp, uint64_t seed, uint64_t counter, void* stream) {
+  return llq_policy_forward_rec(h, d_obs, obs_ld, n, d_actions, d_codes, d_values, d_neglogp, 1, seed, counter, 0, stream);
 }
 
 int llq_policy_forward(llq_policy_handle h, const float* d_obs, int64_t obs_ld, int32_t n, float* d_actions, int32_t* d_codes, void* stream) {

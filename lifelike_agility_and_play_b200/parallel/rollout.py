@@ -34,6 +34,8 @@ class RolloutWorker:
         self._scratch = torch.zeros((self.n, ACT_DIM), dtype=torch.float32, device=self.dev)
         self.bootstrap_value = self.boots[0]
         self.sample, self.seed, self.calls = bool(sample), int(seed), 0
+        self.row_gid0 = int(engine.cfg.global_env_offset)      # noise keyed by the global env id: equal seeds on two shards still differ
+        engine.set_option("record", 2)                          # a_t | r_t | done_t go to the slab row BEFORE the one receiving obs_{t+1}
         # everything this worker launches (kernels through the C-ABI and torch's column copies) is ordered on ONE side stream: a
         # NULL stream would mean "the engine's own non-blocking stream" to llq_step_ex and would not order with torch's work
         self.stream = torch.cuda.Stream(self.dev)
@@ -54,18 +56,17 @@ class RolloutWorker:
         assert self.t < self.T, "unroll is full: call finish_unroll()"
         s = self.stream.cuda_stream
         row, nxt = self.buf[self.t], self.buf[self.t + 1]
-        with torch.cuda.stream(self.stream):
-            self.pol.forward_ex(row.data_ptr(), TRAJ_WIDTH, self.n, self.act.data_ptr(), None, self.val.data_ptr(),
-                                self.nlp.data_ptr() if self.sample else None, self.seed, self.calls, s)
-            self.eng.step_device(self.act.data_ptr(), nxt.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(), obs_ld=TRAJ_WIDTH, stream=s)
-            row[:, COL_ACTION:COL_ACTION + ACT_DIM] = self.act
-            row[:, COL_REWARD] = self.rew
-            row[:, COL_DONE] = self.done
-            row[:, COL_VALUE] = self.val
-            row[:, COL_NEGLOGP] = self.nlp
+        # Every column of record t is written by the two kernels themselves, no copies: the policy kernel reads observation t in
+        # place and writes V / -log p into the value / neglogp columns of row t (row stride 223); the fused step (record option 2)
+        # writes a_t | r_t | done_t into row t and observation t+1 into row t+1.
+        fsz = 4
+        self.pol.forward_rec(row.data_ptr(), TRAJ_WIDTH, self.n, self.act.data_ptr(), row.data_ptr() + COL_VALUE * fsz,
+                             (row.data_ptr() + COL_NEGLOGP * fsz) if self.sample else None, TRAJ_WIDTH, self.seed, self.calls,
+                             self.row_gid0, s)
+        self.eng.step_device(self.act.data_ptr(), nxt.data_ptr(), self.rew.data_ptr(), self.done.data_ptr(), obs_ld=TRAJ_WIDTH, stream=s)
         self.calls += 1
         self.t += 1
-        self.launches += 3            # policy, step, reset kernels (the column copies are torch's)
+        self.launches += 3            # policy, step, reset kernels; nothing else runs inside an unroll
 
     def finish_unroll(self):
         """Copy-free `[T, N, 223]` view of the finished records, valid until the end of the NEXT unroll; stepping continues

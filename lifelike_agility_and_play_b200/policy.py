@@ -70,7 +70,8 @@ import ctypes as _C
 import os as _os
 
 POLICY_LIB_PATH = _os.path.join(_os.path.dirname(_os.path.abspath(__file__)), "csrc", "libllq_policy.so")
-POLICY_EXPORTS = ["llq_policy_create", "llq_policy_destroy", "llq_policy_forward", "llq_policy_forward_ex", "llq_policy_last_error"]
+POLICY_EXPORTS = ["llq_policy_create", "llq_policy_destroy", "llq_policy_forward", "llq_policy_forward_ex", "llq_policy_forward_rec",
+                  "llq_policy_last_error"]
 N_WEIGHTS = 358647
 
 
@@ -93,6 +94,8 @@ class DevicePolicy:
         L.llq_policy_forward.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_int64, _C.c_int32, _C.c_void_p, _C.c_void_p, _C.c_void_p]
         L.llq_policy_forward_ex.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_int64, _C.c_int32, _C.c_void_p, _C.c_void_p, _C.c_void_p,
                                             _C.c_void_p, _C.c_uint64, _C.c_uint64, _C.c_void_p]
+        L.llq_policy_forward_rec.argtypes = [_C.c_void_p, _C.c_void_p, _C.c_int64, _C.c_int32, _C.c_void_p, _C.c_void_p, _C.c_void_p,
+                                             _C.c_void_p, _C.c_int64, _C.c_uint64, _C.c_uint64, _C.c_int64, _C.c_void_p]
         L.llq_policy_destroy.argtypes = [_C.c_void_p]
         L.llq_policy_last_error.restype = _C.c_char_p
         blob = pack_weights(weights)
@@ -114,6 +117,14 @@ class DevicePolicy:
                                              seed, counter, stream)
         if rc != 0:
             raise RuntimeError("llq_policy_forward_ex failed (%d): %s" % (rc, (self._lib.llq_policy_last_error() or b"").decode()))
+
+    def forward_rec(self, obs_ptr, obs_ld, n, actions_ptr, values_ptr, neglogp_ptr, out_ld, seed=0, counter=0, row_gid0=0, stream=None):
+        """Rollout step writing V(obs) / -log p with row stride `out_ld` (straight into the columns of a trajectory slab row);
+        the sampling noise is keyed by the global row `row_gid0 + i`."""
+        rc = self._lib.llq_policy_forward_rec(self._h, obs_ptr, obs_ld, n, actions_ptr, None, values_ptr, neglogp_ptr, out_ld,
+                                              seed, counter, row_gid0, stream)
+        if rc != 0:
+            raise RuntimeError("llq_policy_forward_rec failed (%d): %s" % (rc, (self._lib.llq_policy_last_error() or b"").decode()))
 
     def close(self):
         if getattr(self, "_h", None):

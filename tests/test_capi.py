@@ -302,3 +302,67 @@ def test_shipped_pmc_train_config_with_obstacle(monkeypatch, oracle_lib):
     env = create_envs.create_tracking_game(**cfg)
     _drive(env)
     env.close()
+
+
+@pytest.mark.gpu
+def test_record_mode_writes_the_whole_trajectory_row(make_cuda):
+    """llq_set_option("record", 1): the step kernel writes action | reward | done behind the observation of the slab row it is
+    handed (no column copies after the step); auto-reset rewrites only the observation part."""
+    import torch
+    n, ld = 96, 207 + 16
+    eng = make_cuda(n, seed=4, auto_reset=1)
+    eng.reset()
+    eng.set_option("record", 1)
+    dev = torch.device("cuda", 0)
+    slab = torch.full((3, n, ld), -7.0, device=dev)
+    rew = torch.zeros(n, device=dev); done = torch.zeros(n, dtype=torch.uint8, device=dev)
+    rng = np.random.default_rng(0)
+    for t in range(3):
+        a = torch.from_numpy((0.4 * rng.standard_normal((n, 12))).astype(np.float32)).to(dev)
+        eng.step_device(a.data_ptr(), slab[t].data_ptr(), rew.data_ptr(), done.data_ptr(), obs_ld=ld)
+        eng.sync()
+        row = slab[t].cpu().numpy()
+        assert np.array_equal(row[:, 207:219], a.cpu().numpy())
+        assert np.array_equal(row[:, 219], rew.cpu().numpy())
+        assert np.array_equal(row[:, 220], done.cpu().numpy().astype(np.float32))
+        assert np.all(row[:, 221:] == -7.0)                                  # neglogp | value belong to the policy kernel
+        assert np.array_equal(row[:, :207], eng.get(capi.F_OBS))
+    with pytest.raises(capi.LlqError):
+        eng.step_device(a.data_ptr(), slab[0].data_ptr(), rew.data_ptr(), done.data_ptr(), obs_ld=207 + 8)
+
+
+@pytest.mark.gpu
+def test_two_handles_on_two_devices_in_one_process(built, blob, small_mocap):
+    """llq.h: several handles (one per GPU) may coexist in one process -- the > 48 kB dynamic shared memory opt-in of the step
+    kernel is a per-device function attribute and must be raised on each handle's device."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs")
+    engs = [capi.VecEngine(capi.load_cuda_library(), 64, blob, small_mocap, seed=8, device=d) for d in (0, 1)]
+    a = (0.1 * np.random.default_rng(0).standard_normal((64, 12))).astype(np.float32)
+    outs = []
+    for e in engs:
+        e.reset()
+        outs.append(e.step(a))
+    assert np.array_equal(outs[0][0], outs[1][0]) and np.array_equal(outs[0][1], outs[1][1])
+    for e in engs:
+        e.close()
+
+
+@pytest.mark.gpu
+def test_reset_to_ignores_unvalidated_entries_of_masked_out_envs(make_cuda):
+    """clip / time of envs whose mask is 0 are never used to index the mocap table; a stale clock past the clip end stays on the
+    clip's last playable frame (the reference raises IndexError there)."""
+    n = 40
+    eng = make_cuda(n, seed=2)
+    eng.reset()
+    mask = np.zeros(n, np.uint8); mask[::2] = 1
+    clip = np.where(mask == 1, 1, -12345).astype(np.int32)
+    t = np.where(mask == 1, 0.25, 1e9)
+    eng.reset_to(clip, t, mask=mask)
+    assert np.all(eng.get(capi.F_CLIP)[mask == 1] == 1)
+    with pytest.raises(capi.LlqError):
+        eng.set(capi.F_TIME, np.full(n, -1.0))
+    eng.set(capi.F_TIME, np.full(n, 1e4))                                    # far past every clip
+    obs, rew, done = eng.step(np.zeros((n, 12), np.float32))
+    assert np.all(done == 1) and np.all(np.isfinite(obs)) and np.all(np.isfinite(rew))

@@ -72,3 +72,44 @@ def test_two_rank_shards_gather_equals_single_process(built):
     ua, ub = slab_to_unrolls(torch.from_numpy(gathered), "k"), slab_to_unrolls(ref.buf, "k")
     assert len(ua) == N_PER * WORLD and ua[0][1].shape == (T * RECORD_WIDTH,)
     assert all(np.array_equal(x[1], y[1]) and x[3] == y[3] for x, y in zip(ua, ub))
+
+
+def _xch_worker(rank, port, q):
+    sys.path.insert(0, ROOT)
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(WORLD))
+    dist.init_process_group("gloo", rank=rank, world_size=WORLD)
+    from lifelike_agility_and_play_b200.parallel import TrajectoryExchange
+    x = TrajectoryExchange(T, N_PER, 7, "cpu")
+    got = []
+    for u in range(3):                                # three unrolls: both slabs are reused
+        x.slab()[...] = torch.arange(T * N_PER * 7, dtype=torch.float32).reshape(T, N_PER, 7) + 1000 * u + 100000 * rank
+        b = x.hand_over()
+        g = x.gathered(b)
+        if rank == 0:
+            got.append(g.clone().numpy())
+        else:
+            assert g is None
+    if rank == 0:
+        q.put(np.stack(got))
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_trajectory_exchange_hands_every_unroll_to_the_learner(built):
+    """The designed hand-over (parallel/trajectory.py: ping-pong slabs, grouped send / recv) on two gloo ranks."""
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = 31500 + (os.getpid() % 2000)
+    procs = [ctx.Process(target=_xch_worker, args=(r, port, q)) for r in range(WORLD)]
+    for p in procs:
+        p.start()
+    got = q.get(timeout=240)
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    assert got.shape == (3, WORLD, T, N_PER, 7)
+    base = np.arange(T * N_PER * 7, dtype=np.float32).reshape(T, N_PER, 7)
+    for u in range(3):
+        for r in range(WORLD):
+            assert np.array_equal(got[u, r], base + 1000 * u + 100000 * r)
