@@ -1530,7 +1530,9 @@ __global__ void __launch_bounds__(BLOCK) pmc_step_kernel(EnvArrays E, MocapDev m
       frame_frac = (time - frame_id * P.frame_dt) / P.frame_dt;
       // a cursor past the clip's playable range (auto_reset off and a finished env stepped on, or a clock set through
       // llq_set_field) stays on the clip's last playable frame instead of walking into the next clip; the reference raises there
-      const int last = mc.clip_off[clip + 1] - mc.clip_off[clip] - P.margin - 1;
+      // (the last policy step of an episode legitimately runs up to 2.4 frames past the "ended" threshold nf - margin - 1; the bound
+      // is the last cursor whose 1 s future window (122 frames) still lies inside the clip)
+      const int last = mc.clip_off[clip + 1] - mc.clip_off[clip] - P.margin + 2;
       if (frame_id > last) { frame_id = last; frame_frac = 0.0; }
       if (frame_id < 0) { frame_id = 0; frame_frac = 0.0; }
     }
@@ -2022,7 +2024,7 @@ __global__ void __launch_bounds__(BLOCK) pmc_reset_kernel(EnvArrays E, MocapDev 
   int frame_id = (int)floor(t0 / P.frame_dt);
   double frac = (t0 - frame_id * P.frame_dt) / P.frame_dt;
   {
-    const int last = mc.clip_off[clip + 1] - mc.clip_off[clip] - P.margin - 1;
+    const int last = mc.clip_off[clip + 1] - mc.clip_off[clip] - P.margin + 2;
     if (frame_id > last) { frame_id = last; frac = 0.0; }
     if (frame_id < 0) { frame_id = 0; frac = 0.0; }
   }
