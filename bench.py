@@ -49,7 +49,7 @@ ALGO_BYTES = {"pmc": 1676, "epmc": 6208, "epmc_flat": 4672, "sepmc": 9576}
 OBS_W = {"pmc": 207, "epmc": 916, "sepmc": 965}
 ROBOTS_PER_ENV = {"pmc": 1, "epmc": 1, "sepmc": 2}
 ELEMENT = [3]
-KERNEL_SOURCES = ["lifelike_agility_and_play_b200/csrc/llq_kernels.cuh", "lifelike_agility_and_play_b200/csrc/llq_cuda.cu",
+KERNEL_SOURCES = ["lifelike_agility_and_play_b200/csrc/llq_step16.cuh", "lifelike_agility_and_play_b200/csrc/llq_kernels.cuh", "lifelike_agility_and_play_b200/csrc/llq_cuda.cu",
                   "lifelike_agility_and_play_b200/csrc/llq_math.cuh"]
 
 
@@ -526,7 +526,7 @@ def actor_loop(args, eng, n, ow, ctx, pool, reward, done):
 
 def kernel_name(env):
     inst = {"pmc": 0, "epmc": 1 if ELEMENT[0] == 0 else 3, "sepmc": 2}[env]
-    return "pmc_step_kernel<128,%d>" % inst
+    return "llq_step16_kernel<%d>" % inst
 
 
 def assemble(args, r, world, peak, peak_src, reduce_max):

@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define LLQ_ABI_VERSION 3
+#define LLQ_ABI_VERSION 4
 
 /* per-env sizes (PMC env, reference PLE:102-124 with the shipped prop_type) */
 #define LLQ_STATE_DIM   37   /* base_pos3 base_orn4(xyzw) base_lin_vel3 base_ang_vel3 joint_pos12 joint_vel12 (LR:86-106) */
@@ -78,7 +78,10 @@ extern "C" {
 #define LLQ_F_TIME        2  /* double  [N]     env clock PLE.time (PLE:208-210,271) */
 #define LLQ_F_REWARD_SUM  3  /* float   [N]     PLE.reward_sum (PLE:231) */
 #define LLQ_F_EPISODE_STEPS 4 /* int32  [N]     PLE._episode_steps (PLE:197) */
-#define LLQ_F_WARMSTART   5  /* float   [N,4]   previous sub-step's normal impulse per foot (contact warm start) */
+#define LLQ_MAX_SPHERES   32 /* collision spheres of the robot: 4 feet, 4 knee wheels, 4 hips, 4 thighs, 8 shank, 8 trunk corners */
+#define LLQ_MAX_CONTACTS  8  /* manifold points kept per robot and sub-step (sphere order); counter [5] counts what was dropped */
+#define LLQ_MAX_LIMIT_ROWS 8 /* joint-limit rows kept per robot and sub-step (joint order) */
+#define LLQ_F_WARMSTART   5  /* float   [N,32]  previous sub-step's normal impulse per collision sphere (contact warm start) */
 #define LLQ_F_OBS         6  /* float   [N,207] last observation (carries the 3-frame prop / action history) */
 #define LLQ_F_KIN_STATE   7  /* float   [N,37]  kinematic (mocap) robot state (PLE:217-218) -- get only */
 #define LLQ_F_SAMPLE_PROB 8  /* double  [n_clips] prioritized sampling probabilities (PLE:239-240) */
@@ -137,10 +140,14 @@ typedef struct llq_config {
   double wall_width_lo, wall_width_hi;                 /* PGE:160: [0.02, 0.5]  (BSE:171) */
   double wall_gap_lo, wall_gap_hi;                     /* PGE:161: [1.0, 20.0]  (BSE:174) */
   double hole_gap_lo, hole_gap_hi;                     /* hole_config min/max_gap_height (BSE:372-373; shipped 0.25, 0.25) */
-  /* ---- ground contact of the knee wheels (link_*W, cylinders r = 0.028 / 0.036 on the thigh links, max.urdf): as spheres, one
-     contact per leg = the deeper of {foot, knee wheel}.  Without them the shipped Bullet-trained policy falls in 57 % of its
-     episodes, with them in 5 % (tools/statistical_pin.py). */
-  int32_t knee_contacts;      /* 1 (default) / 0 = feet only */
+  /* ---- which collision shapes of the robot touch the statics (the reference loads every link with its geometry, LR:212-217):
+     0 = the four foot spheres only;
+     1 = + the knee wheels (link_*W, cylinders r = 0.028 / 0.036 on the thigh links, as spheres), ONE contact per leg = the deeper
+         of {foot, knee wheel} -- the round-1 model, kept selectable;
+     2 = (default) every collision sphere of the model blob, each with its own manifold point: feet, knee wheels, hips, thighs,
+         shanks, trunk-box corners, against ground, arena walls and corridor boxes (at most LLQ_MAX_CONTACTS per robot).
+     Without the knee wheels the shipped Bullet-trained policy falls in 57 % of its episodes (tools/statistical_pin.py). */
+  int32_t knee_contacts;
   int32_t reserved1;
   double link_friction;       /* lateral friction of links without a changeDynamics() call: Bullet's default 0.5 */
 } llq_config;
@@ -211,7 +218,8 @@ int llq_get_field(llq_handle h, int field, void* dst);
 int llq_set_field(llq_handle h, int field, const void* src);
 
 /* counters: [0] env steps, [1] episodes finished, [2] contact rows solved, [3] joint-limit rows solved,
- * [4] kernel launches issued by the engine (CUDA) / 0 (CPU). n <= 8. */
+ * [4] kernel launches issued by the engine (CUDA) / 0 (CPU), [5] manifold points / limit rows dropped by the LLQ_MAX_CONTACTS /
+ * LLQ_MAX_LIMIT_ROWS caps. n <= 8. */
 int llq_get_counters(llq_handle h, int64_t* out, int32_t n);
 
 /* Per-kernel device timing of the most recent llq_step*: out[0] = fused step kernel ms, out[1] = reset/table kernel ms

@@ -23,7 +23,7 @@ ENV_PMC, ENV_EPMC, ENV_SEPMC, OBS_DIM_EPMC, OBS_DIM_SEPMC, AUX_DIM = 0, 1, 2, 91
 # field id -> (dtype, per-env width or None for per-clip tables)
 _FIELDS = {
     F_STATE: (np.float32, STATE_DIM), F_CLIP: (np.int32, 1), F_TIME: (np.float64, 1),
-    F_REWARD_SUM: (np.float32, 1), F_EPISODE_STEPS: (np.int32, 1), F_WARMSTART: (np.float32, 4),
+    F_REWARD_SUM: (np.float32, 1), F_EPISODE_STEPS: (np.int32, 1), F_WARMSTART: (np.float32, 32),
     F_OBS: (np.float32, OBS_DIM), F_KIN_STATE: (np.float32, STATE_DIM), F_SAMPLE_PROB: (np.float64, None),
     F_AVG_REWARD: (np.float64, None), F_EPISODE_ID: (np.int64, 1), F_FOOT_POS: (np.float32, 12),
     F_DECISION_MARGIN: (np.float32, 1), F_AUX: (np.float64, AUX_DIM), F_OB_ID: (np.int32, 1),

@@ -10,6 +10,7 @@
 #include "../../include/llq.h"
 #include "../../include/llq_model_layout.h"
 #include "llq_kernels.cuh"
+#include "llq_step16.cuh"
 
 #include <cmath>
 #include <cstdio>
@@ -58,6 +59,8 @@ struct llq_engine {
   int64_t counters[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   llq::StepParams P{};
   bool profile = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool ev_valid = false;
+  llq::SphTable* d_sph = nullptr; llq::SphTable h_sph{};   // collision spheres of the robot (llq_step16.cuh)
+  int lanes = 16;              // "lanes" option: 16 = llq_step16_kernel (default), 4 = the round-1 kernel (one lane per leg; A/B timing only)
   int record = 0;              // "record" option: the step kernel also writes action | reward | done behind the observation of a slab row
   unsigned smem_attr_set = 0;  // bit (ENV * 3 + block index): cudaFuncAttributeMaxDynamicSharedMemorySize raised on this handle's device
 };
@@ -143,9 +146,21 @@ int launch_step_b(llq_handle h, const llq::EnvArrays& E, const float* a, float* 
     default: return launch_step_t<128, ENV>(h, E, a, obs2, ld, s);
   }
 }
+template <int ENV>
+int launch_step16(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
+  const int grid = (h->cfg.n_envs + 7) / 8;       // 8 envs (16 lanes each) per CTA of 128 threads
+  llq::llq_step16_kernel<ENV><<<grid, 128, 0, s>>>(E, mocap_dev(h), h->P, h->d_model, h->d_sph, a, obs2, ld, h->d_winner[h->parity],
+                                                   (unsigned long long)h->cfg.seed, (long long)h->cfg.global_env_offset, h->record);
+  return LLQ_OK;
+}
 int launch_step(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
   const bool epmc = h->cfg.env_kind == LLQ_ENV_EPMC;
   h->counters[4]++;
+  if (h->lanes == 16) {
+    if (epmc && h->cfg.element_id != 0) return launch_step16<3>(h, E, a, obs2, ld, s);
+    if (h->cfg.env_kind == LLQ_ENV_SEPMC) return launch_step16<2>(h, E, a, obs2, ld, s);
+    return epmc ? launch_step16<1>(h, E, a, obs2, ld, s) : launch_step16<0>(h, E, a, obs2, ld, s);
+  }
   if (epmc && h->cfg.element_id != 0) return launch_step_b<3>(h, E, a, obs2, ld, s);        // corridor arenas: the box-aware instance
   if (h->cfg.env_kind == LLQ_ENV_SEPMC) return launch_step_b<2>(h, E, a, obs2, ld, s);
   return epmc ? launch_step_b<1>(h, E, a, obs2, ld, s) : launch_step_b<0>(h, E, a, obs2, ld, s);
@@ -243,6 +258,7 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
                                         cfg->push_interval_steps <= 0))
     return fail(LLQ_EINVAL, "bad EPMC configuration");
   if (cfg->env_kind == LLQ_ENV_EPMC && (cfg->element_id < 0 || cfg->element_id > 3)) return fail(LLQ_EINVAL, "EPMC element_id must be 0..3");
+  if (cfg->knee_contacts < 0 || cfg->knee_contacts > 2) return fail(LLQ_EINVAL, "knee_contacts must be 0, 1 or 2");
   int ndev = 0;
   if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
     return fail(LLQ_ECUDA, "no CUDA device visible (the CUDA engine has no CPU fallback)");
@@ -261,10 +277,10 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
 #define TRY(x) do { rc = (x); if (rc) { llq_destroy(h); return rc; } } while (0)
   cudaError_t ce = cudaStreamCreateWithFlags(&h->stream, cudaStreamNonBlocking);
   if (ce != cudaSuccess) { delete h; return fail(LLQ_ECUDA, cudaGetErrorString(ce)); }
-  TRY(dalloc(&h->d_model, 1));
+  TRY(dalloc(&h->d_model, 1)); TRY(dalloc(&h->d_sph, 1));
   TRY(dalloc(&h->E.pos, 3 * n)); TRY(dalloc(&h->E.st, 34 * n)); TRY(dalloc(&h->E.time, n)); TRY(dalloc(&h->E.clip, n));
   TRY(dalloc(&h->E.reward_sum, n)); TRY(dalloc(&h->E.episode_steps, n)); TRY(dalloc(&h->E.episode, n));
-  TRY(dalloc(&h->E.warm, 4 * n)); TRY(dalloc(&h->E.obs, (size_t)h->obs_dim * n)); TRY(dalloc(&h->E.kin, 37 * n));
+  TRY(dalloc(&h->E.warm, LLQ_MAX_SPHERES * n)); TRY(dalloc(&h->E.obs, (size_t)h->obs_dim * n)); TRY(dalloc(&h->E.kin, 37 * n));
   TRY(dalloc(&h->E.foot_pos, 12 * n)); TRY(dalloc(&h->E.done_reward, n)); TRY(dalloc(&h->E.done, n)); TRY(dalloc(&h->E.reward, n));
   TRY(dalloc(&h->E.counters, 8));
   TRY(dalloc(&h->E.aux, (size_t)LLQ_AUX_DIM * n));
@@ -290,7 +306,7 @@ int llq_destroy(llq_handle h) {
   if (!h) return LLQ_OK;
   cudaSetDevice(h->cfg.device);
   if (h->stream) cudaStreamSynchronize(h->stream);
-  void* dptrs[] = {h->d_model, h->d_frames, h->d_clip_off, h->E.pos, h->E.st, h->E.time, h->E.clip, h->E.reward_sum, h->E.episode_steps,
+  void* dptrs[] = {h->d_sph, h->d_model, h->d_frames, h->d_clip_off, h->E.pos, h->E.st, h->E.time, h->E.clip, h->E.reward_sum, h->E.episode_steps,
                    h->E.episode, h->E.warm, h->E.obs, h->E.kin, h->E.foot_pos, h->E.done_reward, h->E.done, h->E.reward, h->E.counters, h->E.aux, h->E.ob_id, h->E.boxes, h->E.nbox, h->d_ob_table, h->d_ob_off,
                    h->d_actions, h->d_winner[0], h->d_winner[1], h->d_avg[0], h->d_avg[1], h->d_prob, h->d_max_steps, h->d_mask,
                    h->d_clip_in, h->d_time_in, h->d_scratch};
@@ -369,6 +385,42 @@ int llq_load_model(llq_handle h, const double* b, int64_t n) {
       }
     }
     if ((int)b[LLQ_H_NPROXIES] > 0 && (nw != 4 || nh != 4 || nc != 8)) return fail(LLQ_EINVAL, "unexpected proxy table");
+  }
+  {   // collision spheres (llq_step16.cuh): centre in the frame of the articulated link they ride on
+    llq::SphTable& T = h->h_sph;
+    std::memset(&T, 0, sizeof(T));
+    T.rule = h->cfg.knee_contacts;
+    const double* sps = b + (int64_t)b[LLQ_H_OFF_SPHERES];
+    const double* gen = b + (int64_t)b[LLQ_H_OFF_GENERIC];
+    const int ns = (int)b[LLQ_H_NSPHERES];
+    int nfoot = 0;
+    for (int i = 0; i < ns; i++, sps += LLQ_SPH) {
+      const int kind = (int)sps[6];
+      if (kind != 0 && !(T.rule == 2 || (T.rule == 1 && kind == 1))) continue;
+      if (T.n >= llq::kMaxSph) return fail(LLQ_EINVAL, "too many collision spheres");
+      llq::SphConst& S = T.s[T.n++];
+      if (kind == 0) {            // foot k: its centre in the shank frame comes from the special section
+        if (nfoot >= 4) return fail(LLQ_EINVAL, "more than four foot spheres");
+        for (int t = 0; t < 3; t++) S.c[t] = M.leg[nfoot].foot[t];
+        S.r = M.leg[nfoot].foot_r; S.leg = nfoot; S.depth = 3; S.foot = 1; S.mu_link = 0.f;
+        nfoot++;
+        continue;
+      }
+      const int link = (int)sps[0];
+      const double* g = gen + (size_t)link * LLQ_GL;
+      S.r = (float)sps[4]; S.foot = 0; S.mu_link = (float)(h->cfg.ground_friction * h->cfg.link_friction);
+      if (link == 0) {            // trunk: relative to the base reference point (body CoM), body axes
+        S.leg = 0; S.depth = 0;
+        for (int t = 0; t < 3; t++) S.c[t] = (float)(sps[1 + t] - gen[LLQ_G_COM + t]);
+      } else {
+        if ((int)g[LLQ_G_JTYPE] != 1) return fail(LLQ_EINVAL, "collision spheres must ride on the base or on an actuated link");
+        const int dof = (int)g[LLQ_G_DOF];
+        S.leg = dof / 3; S.depth = dof % 3 + 1;
+        for (int t = 0; t < 3; t++) S.c[t] = (float)sps[1 + t];
+      }
+    }
+    if (nfoot != 4) return fail(LLQ_EINVAL, "model blob must list the four foot spheres first");
+    CK(cudaMemcpy(h->d_sph, &T, sizeof(T), cudaMemcpyHostToDevice));
   }
   for (int i = 0; i < 37; i++) M.init_state[i] = h->h_model.init_state[i];
   h->h_model = M;
@@ -591,7 +643,7 @@ int llq_get_field(llq_handle h, int field, void* dst) {
       return LLQ_OK;
     }
     case LLQ_F_KIN_STATE: return get_soa_f(h, h->E.kin, 37, (float*)dst);
-    case LLQ_F_WARMSTART: return get_soa_f(h, h->E.warm, 4, (float*)dst);
+    case LLQ_F_WARMSTART: return get_soa_f(h, h->E.warm, LLQ_MAX_SPHERES, (float*)dst);
     case LLQ_F_FOOT_POS: return get_soa_f(h, h->E.foot_pos, 12, (float*)dst);
     case LLQ_F_CLIP: CK(cudaMemcpy(dst, h->E.clip, sizeof(int) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
     case LLQ_F_TIME: CK(cudaMemcpy(dst, h->E.time, sizeof(double) * n, cudaMemcpyDeviceToHost)); return LLQ_OK;
@@ -649,9 +701,9 @@ int llq_set_field(llq_handle h, int field, const void* src) {
     }
     case LLQ_F_WARMSTART: {
       const float* s = (const float*)src;
-      std::vector<float> w(4 * n);
-      for (size_t i = 0; i < n; i++) for (int t = 0; t < 4; t++) w[t * n + i] = s[i * 4 + t];
-      CK(cudaMemcpy(h->E.warm, w.data(), sizeof(float) * 4 * n, cudaMemcpyHostToDevice));
+      std::vector<float> w(LLQ_MAX_SPHERES * n);
+      for (size_t i = 0; i < n; i++) for (int t = 0; t < LLQ_MAX_SPHERES; t++) w[t * n + i] = s[i * LLQ_MAX_SPHERES + t];
+      CK(cudaMemcpy(h->E.warm, w.data(), sizeof(float) * LLQ_MAX_SPHERES * n, cudaMemcpyHostToDevice));
       return LLQ_OK;
     }
     case LLQ_F_CLIP: {
@@ -697,7 +749,7 @@ int llq_get_counters(llq_handle h, int64_t* out, int32_t n) {
   CK(cudaMemcpy(dc, h->E.counters, sizeof(dc), cudaMemcpyDeviceToHost));
   int64_t c[8];
   for (int i = 0; i < 8; i++) c[i] = h->counters[i];
-  c[1] = (int64_t)dc[1]; c[2] = (int64_t)dc[2]; c[3] = (int64_t)dc[3];
+  c[1] = (int64_t)dc[1]; c[2] = (int64_t)dc[2]; c[3] = (int64_t)dc[3]; c[5] = (int64_t)dc[5];
   for (int i = 0; i < n; i++) out[i] = c[i];
   return LLQ_OK;
 }
@@ -715,6 +767,12 @@ int llq_set_option(llq_handle h, const char* name, double value) {
     const int v = (int)value;
     if (v < 0 || v > 2) return fail(LLQ_EINVAL, "record must be 0 (off), 1 (same slab row as the observation) or 2 (the row before)");
     h->record = v;
+    return LLQ_OK;
+  }
+  if (!std::strcmp(name, "lanes")) {
+    const int v = (int)value;
+    if (v != 4 && v != 16) return fail(LLQ_EINVAL, "lanes must be 16 (default kernel) or 4 (round-1 kernel)");
+    h->lanes = v;
     return LLQ_OK;
   }
   if (!std::strcmp(name, "block")) {

@@ -361,6 +361,7 @@ struct PairState { int with_flag, flag_draws, visible, sw; double flag_x, flag_y
 
 // End-of-step pair logic shared by the step and the reset kernels (CTG:495-596, 472-493): visibility, flag switch, the small
 // observation vectors.  Every lane of both robots runs it; `snew` is the robot's staging row, `spart` the partner's.
+template <int PX = 4>   // lane distance of the partner robot: 4 (one robot = 4 lanes) or 16 (one robot = a half-warp)
 LLQ_DI void sepmc_pair_tail(const ModelConst& M, const LegConst& L, int k, int robot, float* snew, const float* spart, double px, double py,
                             double pz, Q4 qp, Q4 qb, V3 vw, V3 ww, const float (&q)[3], bool touch_own, float fix_spd, unsigned long long seed,
                             long long pair_gid, long long epi, PairState& S) {
@@ -380,11 +381,11 @@ LLQ_DI void sepmc_pair_tail(const ModelConst& M, const LegConst& L, int k, int r
   }
   __syncwarp();
   // partner's root state
-  const double ox = __shfl_xor_sync(FULL, px, 4), oy = __shfl_xor_sync(FULL, py, 4), oz = __shfl_xor_sync(FULL, pz, 4);
-  const Q4 oq = Q4{__shfl_xor_sync(FULL, qb.x, 4), __shfl_xor_sync(FULL, qb.y, 4), __shfl_xor_sync(FULL, qb.z, 4), __shfl_xor_sync(FULL, qb.w, 4)};
-  const V3 ov = V3{__shfl_xor_sync(FULL, vw.x, 4), __shfl_xor_sync(FULL, vw.y, 4), __shfl_xor_sync(FULL, vw.z, 4)};
-  const V3 oww = V3{__shfl_xor_sync(FULL, ww.x, 4), __shfl_xor_sync(FULL, ww.y, 4), __shfl_xor_sync(FULL, ww.z, 4)};
-  const bool touch_other = __shfl_xor_sync(FULL, touch_own ? 1 : 0, 4) != 0;
+  const double ox = __shfl_xor_sync(FULL, px, PX), oy = __shfl_xor_sync(FULL, py, PX), oz = __shfl_xor_sync(FULL, pz, PX);
+  const Q4 oq = Q4{__shfl_xor_sync(FULL, qb.x, PX), __shfl_xor_sync(FULL, qb.y, PX), __shfl_xor_sync(FULL, qb.z, PX), __shfl_xor_sync(FULL, qb.w, PX)};
+  const V3 ov = V3{__shfl_xor_sync(FULL, vw.x, PX), __shfl_xor_sync(FULL, vw.y, PX), __shfl_xor_sync(FULL, vw.z, PX)};
+  const V3 oww = V3{__shfl_xor_sync(FULL, ww.x, PX), __shfl_xor_sync(FULL, ww.y, PX), __shfl_xor_sync(FULL, ww.z, PX)};
+  const bool touch_other = __shfl_xor_sync(FULL, touch_own ? 1 : 0, PX) != 0;
   const V3 opos = V3{(float)ox, (float)oy, (float)oz};
   const float fx = (float)S.flag_x, fy = (float)S.flag_y;
   // visibility (CTG:472-493): the root segment is cast from robot 0 to robot 1 for both agents
@@ -621,16 +622,16 @@ constexpr int kHist = 90;   // per-env history carry: prop[33:99] (66) | prop_a[
 
 // staging row (kNewObs floats per env).  PMC: prop 33 | action 12 | future 72.
 // EPMC: prop 33 | action 12 | R (world<-base inertial, row major) 9 | pos 3 | target 3 | |base_pos| 1   (perception is evaluated while the row is written)
-template <int ENV>
+template <int ENV, int EPW = 8>   // EPW = envs per warp (8 with 4 lanes per env, 2 with 16)
 LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const float* snew_warp, const float* hist_warp, int env0, int n_envs,
                           int mode, unsigned row_mask, const float* boxes_all = nullptr) {
   constexpr int OW = ObsW<ENV>::value;
   const int lane = threadIdx.x & 31;
 #pragma unroll 4
-  for (int base = 0; base < 8 * OW; base += 32) {
+  for (int base = 0; base < EPW * OW; base += 32) {
     int idx = base + lane;
     int e = idx / OW, j = idx - e * OW;
-    bool ok = idx < 8 * OW && (env0 + e) < n_envs && ((row_mask >> e) & 1u);
+    bool ok = idx < EPW * OW && (env0 + e) < n_envs && ((row_mask >> e) & 1u);
     float v = 0.f;
     if (ok) {
       const float* sn = snew_warp + e * kNewObs;
@@ -733,11 +734,11 @@ LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const floa
 }
 
 // Asynchronous (cp.async) prefetch issued at kernel start; consumed after the ten sub-steps, so DRAM latency is hidden.
-template <int ENV>
+template <int ENV, int EPW = 8>
 LLQ_DI void prefetch_history(const float* obs, float* hist_warp, int env0, int n_envs) {
   constexpr int OW = ObsW<ENV>::value;
   const int lane = threadIdx.x & 31;
-  for (int idx = lane; idx < 8 * kHist; idx += 32) {
+  for (int idx = lane; idx < EPW * kHist; idx += 32) {
     int e = idx / kHist, t = idx - e * kHist;
     int env = env0 + e < n_envs ? env0 + e : n_envs - 1;
     int j = t < 66 ? 33 + t : 99 + 12 + (t - 66);

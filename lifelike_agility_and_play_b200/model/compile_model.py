@@ -48,7 +48,7 @@ G_JXYZ, G_JROT, G_AXIS = 3, 6, 15
 G_MASS, G_COM, G_RIN, G_IDIAG = 18, 19, 22, 31
 G_LOWER, G_UPPER, G_JDAMP, G_HASLIM = 34, 35, 36, 37
 G_ICLINK = 38
-SPH = 8           # sphere stride: link, cx, cy, cz, radius, friction, 0, 0
+SPH = 8           # sphere stride: link, cx, cy, cz, radius, friction, kind (0 foot, 1 wheel, 2 hip, 3 trunk corner, 5 thigh, 6 shank), 0
 # special section
 S_QI = 0          # 4  quaternion xyzw of R_I (body link axes <- base inertial axes)
 S_BASE_M = 4      # 1
@@ -366,6 +366,53 @@ def _composite(model, idx, ref_point):
     return m_tot, h, i_o, items
 
 
+SPH_FOOT, SPH_WHEEL, SPH_HIP, SPH_CORNER, SPH_THIGH, SPH_SHANK = 0, 1, 2, 3, 5, 6
+
+
+def contact_proxy_spheres(model):
+    """Collision spheres that stand in for the robot's non-foot shapes (the reference loads every link with its collision geometry,
+    LR:212-217): rows [articulated link, centre xyz in that link's frame, radius, 0, kind, 0] in the order both engines keep --
+    4 knee wheels (cylinders r 0.028 / 0.036, as spheres), 4 hips (cylinder r 0.047), 4 thighs (one sphere on the 0.2 m box, r = half
+    its larger cross-section), 8 shank spheres (two per 0.24 m box, r = half its larger cross-section), 8 trunk-box corners (r 0).
+    llq_config.knee_contacts selects how many are live: 0 none, 1 the wheels, 2 all of them."""
+    links = model["links"]
+
+    def art(idx):                                     # first non-fixed ancestor and the pose of idx in it
+        anc = idx
+        while links[anc]["joint_type"] == "fixed":
+            anc = links[anc]["parent_index"]
+        return anc, _pose_in_ancestor(model, idx, anc)
+
+    out = {k: [] for k in (SPH_WHEEL, SPH_HIP, SPH_THIGH, SPH_SHANK, SPH_CORNER)}
+    for leg in LEG_ORDER:
+        widx = _link_index(model, "link_%sW" % leg)
+        cyl = [c for c in links[widx]["collisions"] if c["type"] == "cylinder"][0]
+        anc, (r_w, t_w) = art(widx)
+        out[SPH_WHEEL].append([anc, *(r_w @ np.array(cyl["xyz"]) + t_w), cyl["radius"], 0, SPH_WHEEL, 0])
+        hidx = _link_index(model, "link_%s1" % leg)
+        cyl = [c for c in links[hidx]["collisions"] if c["type"] == "cylinder"][0]
+        out[SPH_HIP].append([hidx, *cyl["xyz"], cyl["radius"], 0, SPH_HIP, 0])
+        tidx = _link_index(model, "link_%s2" % leg)
+        box = [c for c in links[tidx]["collisions"] if c["type"] == "box"][0]
+        size = sorted(box["size"])                    # the long side runs along the link (rpy turns the box's x onto z)
+        ctr = np.array(box["xyz"], dtype=np.float64)
+        out[SPH_THIGH].append([tidx, *(ctr + [0, 0, -0.05 * size[2]]), 0.5 * size[1], 0, SPH_THIGH, 0])
+        sidx = _link_index(model, "link_%s3" % leg)
+        box = [c for c in links[sidx]["collisions"] if c["type"] == "box"][0]
+        size = sorted(box["size"])
+        ctr = np.array(box["xyz"], dtype=np.float64)
+        for off in (0.125 * size[2], -0.1875 * size[2]):          # z_c + 0.03, z_c - 0.045 for the 0.24 m shank box
+            out[SPH_SHANK].append([sidx, *(ctr + [0, 0, off]), 0.5 * size[1], 0, SPH_SHANK, 0])
+    body = links[0]
+    box = [c for c in body["collisions"] if c["type"] == "box"][0]
+    hx, hy, hz = 0.5 * np.array(box["size"])
+    for sx in (1, -1):
+        for sy in (1, -1):
+            for sz in (1, -1):
+                out[SPH_CORNER].append([0, box["xyz"][0] + sx * hx, box["xyz"][1] + sy * hy, box["xyz"][2] + sz * hz, 0.0, 0, SPH_CORNER, 0])
+    return out[SPH_WHEEL] + out[SPH_HIP] + out[SPH_THIGH] + out[SPH_SHANK] + out[SPH_CORNER]
+
+
 def pack_model(model):
     """Flat float64 blob (layout: include/llq_model_layout.h)."""
     links = model["links"]
@@ -375,6 +422,7 @@ def pack_model(model):
         for c in ln["collisions"]:
             if c["type"] == "sphere" and ln["name"].endswith("4"):
                 spheres.append([i, *c["xyz"], c["radius"], model["foot_friction"], 0, 0])
+    spheres += contact_proxy_spheres(model)
     # detection-only proxy spheres used for "robot touches the PMC hurdle plate" (PLE:341-346): feet, wheels (knees), hips,
     # body-box corners -- a coarse stand-in for Bullet's exact link shapes
     proxies = []

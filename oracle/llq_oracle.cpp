@@ -250,7 +250,7 @@ struct Env {
   double kin[LLQ_STATE_DIM];
   double time; int clip; double reward_sum; int episode_steps; int64_t episode;
   int frame_id; double frame_frac;
-  double warm[24];
+  double warm[LLQ_MAX_SPHERES];
   double prop_hist[3][LLQ_PROP_DIM]; double act_hist[3][LLQ_ACTION_DIM];
   double foot_pos[12];
   double margin;   // LLQ_F_DECISION_MARGIN
@@ -502,7 +502,7 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
 
   // (a) collision detection on pre-step poses: foot spheres vs plane z = 0
   struct Contact { int link, sphere; V3 P, n; double dist, mu; };
-  Contact contacts[24]; int nc = 0;
+  Contact contacts[LLQ_MAX_SPHERES]; int nc = 0;
   // static half-spaces the feet can touch: the ground, plus (SEPMC) the inner faces of the four arena walls (BSG:863-902:
   // 5 x 0.01 x 2 boxes centred at +-2.5).  One contact per foot: the deepest half-space.
   const int n_planes = cf.env_kind == LLQ_ENV_SEPMC ? 5 : 1;
@@ -512,13 +512,14 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
     const SphereM& sp = md.spheres[s];
     V3 cw = k.pl[sp.link] + mul(k.Rl[sp.link], sp.c);
     double dist = 1e30; V3 nrm = pn[0];
-    for (int pi = 0; pi < (s < 4 ? n_planes : 1); pi++) {       // knee wheels: ground only
+    const bool statics = s < 4 || cf.knee_contacts == 2;           // legacy sets: only the feet touch walls and boxes
+    for (int pi = 0; pi < (statics ? n_planes : 1); pi++) {
       double dpi = dot(pn[pi], cw) - pd[pi] - sp.r;
       if (dpi < dist) { dist = dpi; nrm = pn[pi]; }
     }
     // EPMC corridor: sphere vs every static box (walls, hurdles, bars, cubes); still one contact per foot, the deepest.
     // The auxiliary edge cylinders (BSE:43-100) and every non-foot link are not collided.
-    for (int b = 0; b < (s < 4 ? e.n_boxes : 0); b++) {
+    for (int b = 0; b < (statics ? e.n_boxes : 0); b++) {
       const double* bx = e.boxes[b];
       const double p[3] = {cw.x - bx[0], cw.y - bx[1], cw.z - bx[2]};
       double c[3]; bool inside = true;
@@ -547,9 +548,9 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
     }
   }
 
-  if (md.spheres.size() == 8) {
-    // one contact per leg: the deeper of {foot, knee wheel} (llq_config.knee_contacts)
-    Contact kept[24]; int nk = 0;
+  if (cf.knee_contacts == 1 && md.spheres.size() == 8) {
+    // legacy rule (llq_config.knee_contacts = 1): one contact per leg, the deeper of {foot, knee wheel}
+    Contact kept[LLQ_MAX_SPHERES]; int nk = 0;
     for (int leg = 0; leg < 4; leg++) {
       int best = -1;
       for (int ci = 0; ci < nc; ci++)
@@ -561,6 +562,15 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
     }
     nc = nk;
     for (int ci = 0; ci < nc; ci++) contacts[ci] = kept[ci];
+  }
+  // both engines keep at most LLQ_MAX_CONTACTS manifold points per robot (sphere order) and LLQ_MAX_LIMIT_ROWS limit rows (joint order);
+  // anything beyond that is a heap of a robot whose episode ends with this step (counter [5] counts the dropped rows)
+  for (int ci = LLQ_MAX_CONTACTS; ci < nc; ci++) e.warm[contacts[ci].sphere] = 0.0;
+  if (nc > LLQ_MAX_CONTACTS) {
+    const int64_t dropped = nc - LLQ_MAX_CONTACTS;
+#pragma omp atomic
+    E.counters[5] += dropped;
+    nc = LLQ_MAX_CONTACTS;
   }
   // (b) joint damping (pybullet applyJointDamping) + motor torque, forward dynamics, velocity prediction
   double gv[MAXD], tt[16], acc[MAXD];
@@ -600,7 +610,11 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
       double poserr = pen > -0.04 ? -pen * cf.joint_erp / dt : 0.0;
       r.rhs = (poserr - rel) * r.invd;
       r.lo = 0; r.hi = cf.max_applied_impulse; r.lam = 0;
-      lim.push_back(r);
+      if ((int)lim.size() < LLQ_MAX_LIMIT_ROWS) lim.push_back(r);
+      else {
+#pragma omp atomic
+        E.counters[5] += 1;
+      }
     }
   }
   for (int ci = 0; ci < nc; ci++) {
@@ -794,7 +808,7 @@ void reset_env(llq_engine& E, Env& e, int clip, double sampled_time) {
   e.reward_sum = 0; e.episode_steps = 0;
   e.ob_id = 0;                                                                           // PLE:179
   e.foot_mu = E.cfg.foot_friction;
-  for (int s = 0; s < 24; s++) e.warm[s] = 0;
+  for (int s = 0; s < LLQ_MAX_SPHERES; s++) e.warm[s] = 0;
   double prop[LLQ_PROP_DIM];
   make_prop(e.kin, prop);
   for (int h = 0; h < 3; h++) {                                          // PLE:282-290
@@ -1101,7 +1115,7 @@ void epmc_reset(llq_engine& E, Env& e, int64_t gid) {   // PGE:196-249
   st[3] = qn.x; st[4] = qn.y; st[5] = qn.z; st[6] = qn.w;
   st[0] = 0.0; st[1] = 0.0; st[2] = 0.5;
   unpack_state(e, st);
-  for (int s = 0; s < 24; s++) e.warm[s] = 0;
+  for (int s = 0; s < LLQ_MAX_SPHERES; s++) e.warm[s] = 0;
   e.tgt_x = 8.0; e.tgt_y = 0.0; e.n_boxes = 0;                                           // BSE:247-248, PGE:219
   if (cf.element_id != 0) epmc_generate_terrain(E, e, gid);                               // PGE:216-219
   e.last_pos_diff_len = std::sqrt((st[0] - e.tgt_x) * (st[0] - e.tgt_x) + (st[1] - e.tgt_y) * (st[1] - e.tgt_y));
@@ -1416,7 +1430,7 @@ void sepmc_reset(llq_engine& E, Env& a, Env& b, int64_t gid) {   // CTG:261-304,
     st[0] = px[i]; st[1] = py[i]; st[2] = 0.5;
     unpack_state(e, st);
     e.yaw_accum_deg = yaw_acc;
-    for (int s = 0; s < 24; s++) e.warm[s] = 0;
+    for (int s = 0; s < LLQ_MAX_SPHERES; s++) e.warm[s] = 0;
     e.flag_x = -2.0 + 4.0 * u2[1]; e.flag_y = -2.0 + 4.0 * u2[2];                          // CTG:218-221
     double prop[LLQ_PROP_DIM];
     make_prop(st, prop);
@@ -1621,16 +1635,19 @@ int llq_load_model(llq_handle h, const double* b, int64_t n) {
   }
   const double* s = b + (int64_t)b[LLQ_H_OFF_SPHERES];
   int ns = (int)b[LLQ_H_NSPHERES];
-  if (ns > 8) return fail(LLQ_EINVAL, "too many contact spheres");
-  for (int i = 0; i < ns; i++, s += LLQ_SPH) md.spheres.push_back({(int)s[0], V3{s[1], s[2], s[3]}, s[4], h->cfg.foot_friction});
+  if (ns > LLQ_MAX_SPHERES) return fail(LLQ_EINVAL, "too many contact spheres");
+  // llq_config.knee_contacts: 0 = the foot spheres, 1 = + the knee wheels (one contact per leg), 2 = every collision sphere of the blob
+  for (int i = 0; i < ns; i++, s += LLQ_SPH) {
+    const int kind = (int)s[6];
+    if (kind == 0) md.spheres.push_back({(int)s[0], V3{s[1], s[2], s[3]}, s[4], h->cfg.foot_friction});
+    else if (h->cfg.knee_contacts == 2 || (h->cfg.knee_contacts == 1 && kind == 1))
+      md.spheres.push_back({(int)s[0], V3{s[1], s[2], s[3]}, s[4], h->cfg.link_friction});
+  }
   if ((int64_t)b[LLQ_H_NPROXIES] > 0) {
     const double* pr = b + (int64_t)b[LLQ_H_OFF_PROXIES];
     for (int i = 0; i < (int)b[LLQ_H_NPROXIES]; i++, pr += LLQ_PROXY)
       md.proxies.push_back({(int)pr[0], V3{pr[1], pr[2], pr[3]}, pr[4], (int)pr[5]});
   }
-  if (h->cfg.knee_contacts)     // knee wheels (proxy kind 1) collide with the ground too: spheres 4-7, in leg order
-    for (const ProxyM& p : md.proxies)
-      if (p.kind == 1 && md.spheres.size() < 8) md.spheres.push_back({p.link, p.c, p.r, h->cfg.link_friction});
   h->model = md;
   h->has_model = true;
   return LLQ_OK;
@@ -1793,8 +1810,8 @@ int llq_get_field(llq_handle h, int field, void* dst) {
       case LLQ_F_TIME: ((double*)dst)[i] = e.time; break;
       case LLQ_F_REWARD_SUM: ((float*)dst)[i] = (float)e.reward_sum; break;
       case LLQ_F_EPISODE_STEPS: ((int32_t*)dst)[i] = e.episode_steps; break;
-      case LLQ_F_WARMSTART:   // per leg: the remembered normal impulse, negative when it belongs to the knee-wheel contact
-        for (int t = 0; t < 4; t++) ((float*)dst)[(size_t)i * 4 + t] = e.warm[4 + t] > 0 ? -(float)e.warm[4 + t] : (float)e.warm[t];
+      case LLQ_F_WARMSTART:   // per collision sphere: the remembered normal impulse of its manifold point
+        for (int t = 0; t < LLQ_MAX_SPHERES; t++) ((float*)dst)[(size_t)i * LLQ_MAX_SPHERES + t] = (float)e.warm[t];
         break;
       case LLQ_F_OBS: std::memcpy((float*)dst + (size_t)i * h->obs_dim(), e.obs, sizeof(float) * h->obs_dim()); break;
       case LLQ_F_AUX: {
@@ -1850,10 +1867,7 @@ int llq_set_field(llq_handle h, int field, const void* src) {
       case LLQ_F_REWARD_SUM: e.reward_sum = ((const float*)src)[i]; break;
       case LLQ_F_EPISODE_STEPS: e.episode_steps = ((const int32_t*)src)[i]; break;
       case LLQ_F_WARMSTART:
-        for (int t = 0; t < 4; t++) {
-          const float v = ((const float*)src)[(size_t)i * 4 + t];
-          e.warm[t] = v > 0 ? v : 0.0; e.warm[4 + t] = v < 0 ? -v : 0.0;
-        }
+        for (int t = 0; t < LLQ_MAX_SPHERES; t++) e.warm[t] = ((const float*)src)[(size_t)i * LLQ_MAX_SPHERES + t];
         break;
       case LLQ_F_EPISODE_ID: e.episode = ((const int64_t*)src)[i]; break;
       case LLQ_F_OB_ID: e.ob_id = ((const int32_t*)src)[i]; break;
@@ -1918,7 +1932,7 @@ int llq_oracle_get_state64(llq_handle h, int32_t env, double* st37) {
 int llq_oracle_set_state64(llq_handle h, int32_t env, const double* st37) {
   if (!h || !st37 || env < 0 || env >= h->cfg.n_envs) return fail(LLQ_EINVAL, "bad arguments");
   unpack_state(h->envs[env], st37);
-  for (int s = 0; s < 24; s++) h->envs[env].warm[s] = 0;   // resetBasePositionAndOrientation drops the contact cache
+  for (int s = 0; s < LLQ_MAX_SPHERES; s++) h->envs[env].warm[s] = 0;   // resetBasePositionAndOrientation drops the contact cache
   return LLQ_OK;
 }
 int llq_oracle_substep(llq_handle h, int32_t env, const double* tau12) {

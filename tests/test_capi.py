@@ -30,7 +30,7 @@ def test_config_struct_matches_header(built, oracle_lib):
     assert cfg.struct_size == ctypes.sizeof(capi.LlqConfig)
     cuda = capi.LlqLibrary(capi.CUDA_LIB_PATH)
     c2 = cuda.default_config()
-    assert cuda.is_cuda and not oracle_lib.is_cuda and cuda.abi == oracle_lib.abi == 3
+    assert cuda.is_cuda and not oracle_lib.is_cuda and cuda.abi == oracle_lib.abi == 4
     for f, _ in capi.LlqConfig._fields_:
         assert getattr(cfg, f) == getattr(c2, f), f
     assert (cfg.substeps, cfg.solver_iters, cfg.kp, cfg.kd, cfg.max_tau) == (10, 10, 50.0, 0.5, 18.0)

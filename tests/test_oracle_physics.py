@@ -62,7 +62,7 @@ def test_static_stand_supports_weight(model, make_oracle):
         eng.step((nominal - q)[None].astype(np.float32))
     w = eng.get(capi.F_WARMSTART)[0]
     s = eng.get(capi.F_STATE)[0]
-    assert np.all(w > 0), "all four feet should be loaded"
+    assert np.all(w[:4] > 0) and np.all(w[4:] == 0), "all four feet (spheres 0-3) should be loaded, nothing else"
     assert abs(w.sum() - 13.00021 * 9.80665 * 0.002) < 1e-4 * 13.00021 * 9.80665 * 0.002
     assert 0.25 < s[2] < 0.36 and np.abs(s[7:13]).max() < 1e-3 and np.abs(s[25:37]).max() < 1e-3
 
