@@ -148,8 +148,15 @@ int launch_step_b(llq_handle h, const llq::EnvArrays& E, const float* a, float* 
 }
 template <int ENV>
 int launch_step16(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
-  const int grid = (h->cfg.n_envs + 7) / 8;       // 8 envs (16 lanes each) per CTA of 128 threads
-  llq::llq_step16_kernel<ENV><<<grid, 128, 0, s>>>(E, mocap_dev(h), h->P, h->d_model, h->d_sph, a, obs2, ld, h->d_winner[h->parity],
+  constexpr int EPB = LLQ16_BLOCK / 16;           // envs per CTA (16 lanes each)
+  const int grid = (h->cfg.n_envs + EPB - 1) / EPB;
+  const size_t smem = sizeof(float) * EPB * llq::kEnvFloats;
+  const unsigned bit = 1u << (16 + ENV);          // static + dynamic shared memory exceeds 48 kB: per-device opt-in, once per handle
+  if (!(h->smem_attr_set & bit)) {
+    CK(cudaFuncSetAttribute(llq::llq_step16_kernel<ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    h->smem_attr_set |= bit;
+  }
+  llq::llq_step16_kernel<ENV><<<grid, LLQ16_BLOCK, smem, s>>>(E, mocap_dev(h), h->P, h->d_model, h->d_sph, a, obs2, ld, h->d_winner[h->parity],
                                                    (unsigned long long)h->cfg.seed, (long long)h->cfg.global_env_offset, h->record);
   return LLQ_OK;
 }

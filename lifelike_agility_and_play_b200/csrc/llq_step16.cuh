@@ -23,6 +23,16 @@
 
 namespace llq {
 
+#ifndef LLQ16_BLOCK
+#define LLQ16_BLOCK 256   // threads per CTA (16 per env).  Measured at 4096 envs, step + reset per policy step: 32 threads 0.43 ms, 64 0.375,
+                          // 128 0.334, 256 0.302, 512 0.303 -- the bigger the CTA, the more warps march through the 86 kB sub-step body together
+#endif
+#ifndef LLQ16_BAR
+#define LLQ16_BAR 1     // CTA barrier at the top of every sub-step: not needed for correctness, worth 20 % through the instruction cache
+#endif
+#ifndef LLQ16_MINB
+#define LLQ16_MINB 4   // resident CTAs per SM the register budget is sized for (4 x 128 threads x 128 registers = the whole file)
+#endif
 constexpr int kMaxSph = 32, kMaxCon = 8, kMaxLim = 8;
 struct SphConst { float c[3]; float r; float mu_link; int leg; int depth; int foot; };   // centre in the frame of link (leg, depth - 1); depth 0 = base
 struct alignas(16) SphTable { int n; int rule; int pad[2]; SphConst s[kMaxSph]; };         // rule: llq_config.knee_contacts
@@ -33,8 +43,10 @@ constexpr int kLegTab = 4 * 48;       // leg k: dynamics phase F(18) Hrow(9) rhs
 constexpr int kConW = 20, kConTab = kMaxCon * kConW;   // contact: leg depth | Pc(3) n(3) t1(3) t2(3) | dist mu lam0 lam
 constexpr int kLimTab = kMaxLim * 4;  // limit row: leg joint dir pen
 constexpr int kRowW = 12, kRowTab = 32 * kRowW;        // row: y(6) e(3) leg - -   (aliased by the 16 x 20 float scratch of the dynamics phase)
-constexpr int kEnvTab = 16;           // p_base(6) ...
-constexpr int kEnvFloats = kLinkTab + kLegTab + kConTab + kLimTab + kRowTab + kEnvTab;
+constexpr int kEnvTab = 56;           // p_base(6) - - | Cholesky factor of the base block (21) - - - | joint targets (12) | actions (12)
+constexpr int kATab = 16 * 16;         // Delassus rows of the common path: atab[col * 16 + lane]
+constexpr int kEnvFloats = 1200;       // >= the sum of the tables, and = 16 (mod 32): the two envs of a warp hit disjoint banks
+static_assert(kLinkTab + kLegTab + kConTab + kLimTab + kRowTab + kEnvTab + kATab <= kEnvFloats && kEnvFloats % 32 == 16, "per-env table layout");
 
 LLQ_DI float hsum16(float v) {        // sum over the 16 lanes of an env
   v += __shfl_xor_sync(FULL, v, 1); v += __shfl_xor_sync(FULL, v, 2); v += __shfl_xor_sync(FULL, v, 4); v += __shfl_xor_sync(FULL, v, 8);
@@ -80,6 +92,25 @@ LLQ_DI SV bias_wrench(float m, V3 h, Sym3 I, int nd, const DampItem* d, V3 w, V3
   }
   return p;
 }
+// triangular solves with the packed Cholesky factor (llq_math.cuh layout) kept in shared memory
+LLQ_DI void chol6_fwd_p(const float* l, const float (&b)[6], float (&y)[6]) {
+#pragma unroll
+  for (int i = 0; i < 6; i++) {
+    float s = b[i];
+#pragma unroll
+    for (int k = 0; k < i; k++) s = fmaf(-l[tri(i, k)], y[k], s);
+    y[i] = s * l[tri(i, i)];
+  }
+}
+LLQ_DI void chol6_bwd_p(const float* l, const float (&y)[6], float (&x)[6]) {
+#pragma unroll
+  for (int i = 5; i >= 0; i--) {
+    float s = y[i];
+#pragma unroll
+    for (int k = i + 1; k < 6; k++) s = fmaf(-l[tri(k, i)], x[k], s);
+    x[i] = s * l[tri(i, i)];
+  }
+}
 LLQ_DI float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 LLQ_DI void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 
@@ -110,217 +141,268 @@ LLQ_DI void sphere_box(double wx, double wy, double wz, double r, const float* b
 // NS = row slots per lane: slot s holds contacts 4 s .. 4 s + 3 (lanes 0-11) and limit rows 4 s .. 4 s + 3 (lanes 12-15).
 // Returns Yt = sum lam_r y_r (base part) and om = sum over the rows of this lane's leg of lam_r w_r (joint part).
 struct RowsIn {
-  const float* legtab; const float* linktab; float* contab; const float* limtab; float* rowtab;
+  const float* legtab; const float* linktab; float* contab; const float* limtab; float* rowtab; const float* chol;
   int nc, nl, Cmax, Lmax, l16, k;
   V3 wbs, vbs;
   float dt, slop, erp, jerp, max_imp;
   int iters;
 };
-template <int NS>
-LLQ_DI void solve_rows_impl(const RowsIn& in, const Chol6& ch, float (&Yt)[6], float (&om)[3]) {
-  const int l16 = in.l16;
+// one row: its image under the factorised mass matrix and the scalars of the sweep
+struct RowRegs { float y[6], wj[3], b, rhs, invd, lam, hi, mu; int leg; };
+// slot sl of lane l16: contact 4 sl + l16 / 3 in direction l16 % 3 (lanes 0-11) or limit row 4 sl + l16 - 12; also leaves
+// (y, e = D^-1 w, leg) in the row table for the other rows' Delassus entries (zeros for an absent row)
+LLQ_DI void row_image(const RowsIn& in, int sl, int l16, RowRegs& r) {
   const bool is_con = l16 < 12;
   const int d = l16 % 3, cq = l16 / 3;
-  float y[NS][6], wj[NS][3], A[NS][16 * NS], b[NS], rhs[NS], invd[NS], lam[NS], hi[NS], mu[NS];
-  int rleg[NS];
-  // ---- row images
+  float e[3] = {0.f, 0.f, 0.f};
 #pragma unroll
-  for (int sl = 0; sl < NS; sl++) {
-    float e[3] = {0.f, 0.f, 0.f};
-#pragma unroll
-    for (int t = 0; t < 6; t++) y[sl][t] = 0.f;
-    wj[sl][0] = wj[sl][1] = wj[sl][2] = 0.f;
-    b[sl] = 0.f; rhs[sl] = 0.f; invd[sl] = 0.f; lam[sl] = 0.f; hi[sl] = 0.f; mu[sl] = 0.f; rleg[sl] = -2;
-    const int idx = 4 * sl + (is_con ? cq : l16 - 12);
-    const bool act = is_con ? idx < in.nc : idx < in.nl;
-    if (act) {
-      V3 Ga = V3{0.f, 0.f, 0.f}, Gl = V3{0.f, 0.f, 0.f};
-      float j[3] = {0.f, 0.f, 0.f}, rel = 0.f, dist = 0.f, lam0 = 0.f, pen = 0.f, dirl = 0.f;
-      int leg, jj = 0;
-      if (is_con) {
-        const float* cr = in.contab + idx * kConW;
-        leg = __float_as_int(cr[0]);
-        const int depth = __float_as_int(cr[1]);
-        const V3 Pc = ld3(cr + 2), dir = ld3(cr + 5 + 3 * d);
-        dist = cr[14]; mu[sl] = cr[15]; lam0 = cr[16];
-        Ga = cross(Pc, dir); Gl = dir;
-        rel = dot(Ga, in.wbs) + dot(Gl, in.vbs);
-        if (leg >= 0) {
-          const float* lk = in.linktab + leg * 24;
-          const float c1 = lk[0], s1 = lk[1];
-          const V3 p1 = ld3(lk + 4), p2 = ld3(lk + 12), p3 = ld3(lk + 20), n2 = V3{0.f, -c1, -s1};
-          j[0] = Ga.x + dot(cross(p1, V3{1.f, 0.f, 0.f}), Gl);
-          if (depth >= 2) j[1] = dot(n2, Ga) + dot(cross(p2, n2), Gl);
-          if (depth >= 3) j[2] = dot(n2, Ga) + dot(cross(p3, n2), Gl);
-        }
-      } else {
-        const float* lr = in.limtab + idx * 4;
-        leg = __float_as_int(lr[0]); jj = __float_as_int(lr[1]); dirl = lr[2]; pen = lr[3];
-        j[0] = jj == 0 ? dirl : 0.f; j[1] = jj == 1 ? dirl : 0.f; j[2] = jj == 2 ? dirl : 0.f;
-      }
-      rleg[sl] = leg;
-      float g[6] = {Ga.x, Ga.y, Ga.z, Gl.x, Gl.y, Gl.z};
+  for (int t = 0; t < 6; t++) r.y[t] = 0.f;
+  r.wj[0] = r.wj[1] = r.wj[2] = 0.f;
+  r.b = 0.f; r.rhs = 0.f; r.invd = 0.f; r.lam = 0.f; r.hi = 0.f; r.mu = 0.f; r.leg = -2;
+  const int idx = 4 * sl + (is_con ? cq : l16 - 12);
+  const bool act = is_con ? idx < in.nc : idx < in.nl;
+  if (act) {
+    V3 Ga = V3{0.f, 0.f, 0.f}, Gl = V3{0.f, 0.f, 0.f};
+    float j[3] = {0.f, 0.f, 0.f}, rel = 0.f, dist = 0.f, lam0 = 0.f, pen = 0.f, dirl = 0.f;
+    int leg, jj = 0;
+    if (is_con) {
+      const float* cr = in.contab + idx * kConW;
+      leg = __float_as_int(cr[0]);
+      const int depth = __float_as_int(cr[1]);
+      const V3 Pc = ld3(cr + 2), dir = ld3(cr + 5 + 3 * d);
+      dist = cr[14]; r.mu = cr[15]; lam0 = cr[16];
+      Ga = cross(Pc, dir); Gl = dir;
+      rel = dot(Ga, in.wbs) + dot(Gl, in.vbs);
       if (leg >= 0) {
-        const float* lt = in.legtab + leg * 48;
-        const float L10 = lt[18], L20 = lt[19], L21 = lt[20];
-        rel += j[0] * lt[24] + j[1] * lt[25] + j[2] * lt[26];
-        wj[sl][0] = j[0];
-        wj[sl][1] = fmaf(-L10, wj[sl][0], j[1]);
-        wj[sl][2] = fmaf(-L20, wj[sl][0], fmaf(-L21, wj[sl][1], j[2]));
-        e[0] = wj[sl][0] * lt[21]; e[1] = wj[sl][1] * lt[22]; e[2] = wj[sl][2] * lt[23];
-#pragma unroll
-        for (int m = 0; m < 3; m++)
-#pragma unroll
-          for (int t = 0; t < 6; t++) g[t] = fmaf(-e[m], lt[6 * m + t], g[t]);
+        const float* lk = in.linktab + leg * 24;
+        const float c1 = lk[0], s1 = lk[1];
+        const V3 p1 = ld3(lk + 4), p2 = ld3(lk + 12), p3 = ld3(lk + 20), n2 = V3{0.f, -c1, -s1};
+        j[0] = Ga.x + dot(cross(p1, V3{1.f, 0.f, 0.f}), Gl);
+        if (depth >= 2) j[1] = dot(n2, Ga) + dot(cross(p2, n2), Gl);
+        if (depth >= 3) j[2] = dot(n2, Ga) + dot(cross(p3, n2), Gl);
       }
-      chol6_fwd(ch, g, y[sl]);
-      const float dg = dot6(y[sl], y[sl]) + wj[sl][0] * e[0] + wj[sl][1] * e[1] + wj[sl][2] * e[2];
-      invd[sl] = 1.0f / dg;
-      if (is_con) {
-        if (d == 0) {   // btMultiBodyConstraintSolver::setupMultiBodyContactConstraint
-          const float pn = dist + in.slop;
-          float poserr = 0.f, velerr = -rel;
-          if (pn > 0.f) velerr -= pn / in.dt; else poserr = -pn * in.erp / in.dt;
-          rhs[sl] = (poserr + velerr) * invd[sl];
-          lam[sl] = lam0; hi[sl] = 1e10f;
-        } else {
-          rhs[sl] = -rel * invd[sl];
-        }
-      } else {
-        const float poserr = pen > -0.04f ? -pen * in.jerp / in.dt : 0.f;   // split-impulse threshold quirk
-        rhs[sl] = (poserr - rel) * invd[sl];
-        hi[sl] = in.max_imp;
-      }
+    } else {
+      const float* lr = in.limtab + idx * 4;
+      leg = __float_as_int(lr[0]); jj = __float_as_int(lr[1]); dirl = lr[2]; pen = lr[3];
+      j[0] = jj == 0 ? dirl : 0.f; j[1] = jj == 1 ? dirl : 0.f; j[2] = jj == 2 ? dirl : 0.f;
     }
-    float* rw = in.rowtab + (sl * 16 + l16) * kRowW;
-    st4(rw, y[sl][0], y[sl][1], y[sl][2], y[sl][3]);
-    st4(rw + 4, y[sl][4], y[sl][5], e[0], e[1]);
-    st4(rw + 8, e[2], __int_as_float(rleg[sl]), 0.f, 0.f);
+    r.leg = leg;
+    float g[6] = {Ga.x, Ga.y, Ga.z, Gl.x, Gl.y, Gl.z};
+    if (leg >= 0) {
+      const float* lt = in.legtab + leg * 48;
+      const float L10 = lt[18], L20 = lt[19], L21 = lt[20];
+      rel += j[0] * lt[24] + j[1] * lt[25] + j[2] * lt[26];
+      r.wj[0] = j[0];
+      r.wj[1] = fmaf(-L10, r.wj[0], j[1]);
+      r.wj[2] = fmaf(-L20, r.wj[0], fmaf(-L21, r.wj[1], j[2]));
+      e[0] = r.wj[0] * lt[21]; e[1] = r.wj[1] * lt[22]; e[2] = r.wj[2] * lt[23];
+#pragma unroll
+      for (int m = 0; m < 3; m++)
+#pragma unroll
+        for (int t = 0; t < 6; t++) g[t] = fmaf(-e[m], lt[6 * m + t], g[t]);
+    }
+    chol6_fwd_p(in.chol, g, r.y);
+    const float dg = dot6(r.y, r.y) + r.wj[0] * e[0] + r.wj[1] * e[1] + r.wj[2] * e[2];
+    r.invd = 1.0f / dg;
+    if (is_con) {
+      if (d == 0) {   // btMultiBodyConstraintSolver::setupMultiBodyContactConstraint
+        const float pn = dist + in.slop;
+        float poserr = 0.f, velerr = -rel;
+        if (pn > 0.f) velerr -= pn / in.dt; else poserr = -pn * in.erp / in.dt;
+        r.rhs = (poserr + velerr) * r.invd;
+        r.lam = lam0; r.hi = 1e10f;
+      } else {
+        r.rhs = -rel * r.invd;
+      }
+    } else {
+      const float poserr = pen > -0.04f ? -pen * in.jerp / in.dt : 0.f;   // split-impulse threshold quirk
+      r.rhs = (poserr - rel) * r.invd;
+      r.hi = in.max_imp;
+    }
   }
+  float* rw = in.rowtab + (sl * 16 + l16) * kRowW;
+  st4(rw, r.y[0], r.y[1], r.y[2], r.y[3]);
+  st4(rw + 4, r.y[4], r.y[5], e[0], e[1]);
+  st4(rw + 8, e[2], __int_as_float(r.leg), 0.f, 0.f);
+}
+// entry (r, col) of the Delassus matrix from this lane's row r and the table entry of row `col`
+LLQ_DI float delassus_entry(const RowRegs& r, const float* rw) {
+  const float4 a = ld4(rw), bq = ld4(rw + 4), cq4 = ld4(rw + 8);
+  const float ys[6] = {a.x, a.y, a.z, a.w, bq.x, bq.y};
+  const float jt = r.wj[0] * bq.z + r.wj[1] * bq.w + r.wj[2] * cq4.x;
+  return dot6(r.y, ys) + (__float_as_int(cq4.y) == r.leg ? jt : 0.f);
+}
+// total impulse of the env: Yt = sum lam_r y_r and, per leg, sum lam_r w_r -- 18 values, butterfly over the env's 16 lanes
+LLQ_DI void impulse_sums(float (&v18)[18], int k, float (&Yt)[6], float (&om)[3]) {
+#pragma unroll 1
+  for (int o = 1; o < 16; o <<= 1) {
+#pragma unroll
+    for (int t = 0; t < 18; t++) v18[t] += __shfl_xor_sync(FULL, v18[t], o);
+  }
+#pragma unroll
+  for (int t = 0; t < 6; t++) Yt[t] = v18[t];
+#pragma unroll
+  for (int m = 0; m < 3; m++) om[m] = k == 0 ? v18[6 + m] : (k == 1 ? v18[9 + m] : (k == 2 ? v18[12 + m] : v18[15 + m]));
+}
+LLQ_DI void add_row_impulse(const RowRegs& r, float (&v18)[18]) {
+#pragma unroll
+  for (int t = 0; t < 6; t++) v18[t] = fmaf(r.lam, r.y[t], v18[t]);
+#pragma unroll
+  for (int kk = 0; kk < 4; kk++) {
+    const float f = r.leg == kk ? r.lam : 0.f;
+#pragma unroll
+    for (int m = 0; m < 3; m++) v18[6 + 3 * kk + m] = fmaf(f, r.wj[m], v18[6 + 3 * kk + m]);
+  }
+}
+
+// ---- common path: at most 4 contacts and 4 limit rows in both envs of the warp.  One row per lane; the row's 16 Delassus
+// coefficients live in shared memory (atab[col * 16 + lane]: conflict free), so every loop is rolled and indexed by run-time lane ids --
+// the whole solver is ~250 instructions of code, which matters more than the extra LDS per update: the sub-step body has to stay
+// inside the SM's 32 KB instruction cache now that sixteen warps per SM run through it at their own pace.
+LLQ_DI void solve_rows_s(const RowsIn& in, float* atab, float (&Yt)[6], float (&om)[3]) {
+  int l16 = in.l16;
+  asm volatile("" : "+r"(l16));            // opaque: held in a register instead of being re-derived from %tid at every row
+  RowRegs r;
+  row_image(in, 0, l16, r);
   __syncwarp();
-  // ---- Delassus rows: columns of the active contacts / limit rows only (bounds are warp-uniform)
+  float* acol = atab + l16;
+  const int ncc = 3 * in.Cmax, ncols = ncc + in.Lmax;
+#pragma unroll 1
+  for (int t = 0; t < ncols; t++) {          // columns of the active contacts, then of the active limit rows (warp-uniform bounds)
+    const int col = t < ncc ? t : 12 + t - ncc;
+    acol[col * 16] = delassus_entry(r, in.rowtab + col * kRowW);
+  }
+  // warm start of the normal rows
+#pragma unroll 1
+  for (int c = 0; c < in.Cmax; c++) r.b = fmaf(acol[48 * c], __shfl_sync(FULL, r.lam, 3 * c, 16), r.b);
+  // projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration order); an absent row has rhs = invd = A = 0 => dl = 0
+  const int nrow = in.Lmax + in.Cmax;
+#pragma unroll 1
+  for (int it = 0; it < in.iters; it++) {
+#pragma unroll 1
+    for (int t = 0; t < nrow; t++) {          // joint-limit rows in joint order, then the normal rows in contact order
+      const int ln = t < in.Lmax ? 12 + t : 3 * (t - in.Lmax);
+      const float dlc = fmaf(-r.b, r.invd, r.rhs);
+      const float sum = r.lam + dlc;
+      const float cl = fminf(fmaxf(sum, 0.f), r.hi);                  // Bullet: clamp the accumulated impulse to [0, hi]
+      const float dl = cl == sum ? dlc : cl - r.lam;                  // (unclamped: exactly the computed increment)
+      r.lam = l16 == ln ? cl : r.lam;
+      r.b = fmaf(acol[ln * 16], __shfl_sync(FULL, dl, ln, 16), r.b);
+    }
+#pragma unroll 1
+    for (int c = 0; c < in.Cmax; c++) {       // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
+      const int ln = 3 * c;
+      const float sown = r.lam + fmaf(-r.b, r.invd, r.rhs);
+      const float sa = __shfl_sync(FULL, sown, ln + 1, 16), sb = __shfl_sync(FULL, sown, ln + 2, 16);
+      const float limit = r.mu * __shfl_sync(FULL, r.lam, ln, 16);
+      const float r2 = sa * sa + sb * sb;
+      const bool clip = r2 >= limit * limit && r2 > 0.f;
+      const float sc = clip ? limit * rsqrtf(r2) : 1.0f;
+      const float snew = clip ? sown * sc : sown;
+      const float dl = snew - r.lam;
+      r.lam = (l16 == ln + 1 || l16 == ln + 2) ? snew : r.lam;
+      const float da = __shfl_sync(FULL, dl, ln + 1, 16), db = __shfl_sync(FULL, dl, ln + 2, 16);
+      r.b = fmaf(acol[(ln + 1) * 16], da, fmaf(acol[(ln + 2) * 16], db, r.b));
+    }
+  }
+  // the normal impulses go back to the contact records (warm start of the next sub-step)
+  if (l16 < 12 && l16 % 3 == 0 && l16 / 3 < in.nc) in.contab[(l16 / 3) * kConW + 17] = r.lam;
+  float v18[18];
 #pragma unroll
-  for (int sl = 0; sl < NS; sl++)
+  for (int t = 0; t < 18; t++) v18[t] = 0.f;
+  add_row_impulse(r, v18);
+  impulse_sums(v18, in.k, Yt, om);
+}
+
+// ---- rare path: more than 4 contacts or 4 limit rows in one of the warp's envs.  Two row slots per lane (slot s: contacts
+// 4 s .. 4 s + 3 on lanes 0-11, limit rows 4 s .. 4 s + 3 on lanes 12-15), 2 x 32 Delassus coefficients per lane in local
+// memory, out of line so that the common path keeps its register budget and its code footprint.
+__device__ __noinline__ void solve_rows2(const RowsIn& in, float (&Yt)[6], float (&om)[3]) {
+  constexpr int NS = 2;
+  int l16 = in.l16;
+  asm volatile("" : "+r"(l16));
+  RowRegs r[NS];
+  float A[NS][16 * NS];
 #pragma unroll
-    for (int c = 0; c < 16 * NS; c++) A[sl][c] = 0.f;
+  for (int sl = 0; sl < NS; sl++) row_image(in, sl, l16, r[sl]);
+  __syncwarp();
 #pragma unroll
   for (int col = 0; col < 16 * NS; col++) {
     const int cs = col >> 4, cl = col & 15;
     const bool want = cl < 12 ? (4 * cs + cl / 3) < in.Cmax : (4 * cs + cl - 12) < in.Lmax;
-    if (want) {
-      const float* rw = in.rowtab + col * kRowW;
-      const float4 a = ld4(rw), bq = ld4(rw + 4), cq4 = ld4(rw + 8);
-      const float ys[6] = {a.x, a.y, a.z, a.w, bq.x, bq.y};
-      const int legs = __float_as_int(cq4.y);
 #pragma unroll
-      for (int sl = 0; sl < NS; sl++) {
-        const float jt = wj[sl][0] * bq.z + wj[sl][1] * bq.w + wj[sl][2] * cq4.x;
-        A[sl][col] = dot6(y[sl], ys) + (legs == rleg[sl] ? jt : 0.f);
-      }
-    }
+    for (int sl = 0; sl < NS; sl++) A[sl][col] = want ? delassus_entry(r[sl], in.rowtab + col * kRowW) : 0.f;
   }
-  // ---- warm start of the normal rows
 #pragma unroll
   for (int c = 0; c < 4 * NS; c++) {
     if (c < in.Cmax) {
-      const float l0 = __shfl_sync(FULL, lam[c >> 2], 3 * (c & 3), 16);
+      const float l0 = __shfl_sync(FULL, r[c >> 2].lam, 3 * (c & 3), 16);
 #pragma unroll
-      for (int sl = 0; sl < NS; sl++) b[sl] = fmaf(A[sl][(c >> 2) * 16 + 3 * (c & 3)], l0, b[sl]);
+      for (int sl = 0; sl < NS; sl++) r[sl].b = fmaf(A[sl][(c >> 2) * 16 + 3 * (c & 3)], l0, r[sl].b);
     }
   }
-  // ---- projected Gauss-Seidel; an absent row has rhs = invd = A = 0 and therefore dl = 0
 #pragma unroll 1
   for (int it = 0; it < in.iters; it++) {
 #pragma unroll
-    for (int l = 0; l < 4 * NS; l++) {            // joint-limit rows, joint order
-      if (l < in.Lmax) {
-        const int so = l >> 2, ln = 12 + (l & 3);
-        const float dlc = fmaf(-b[so], invd[so], rhs[so]);
-        const float sum = lam[so] + dlc;
-        const bool lo = sum < 0.f, up = sum > hi[so];
-        const float dl = lo ? -lam[so] : (up ? hi[so] - lam[so] : dlc);
-        if (l16 == ln) lam[so] = lo ? 0.f : (up ? hi[so] : sum);
+    for (int t = 0; t < 8 * NS; t++) {            // joint-limit rows, joint order; then the normal rows, contact order
+      const bool lim = t < 4 * NS;
+      const int ix = lim ? t : t - 4 * NS;
+      if (ix < (lim ? in.Lmax : in.Cmax)) {
+        const int so = ix >> 2, ln = lim ? 12 + (ix & 3) : 3 * (ix & 3);
+        RowRegs& q = r[so];
+        const float dlc = fmaf(-q.b, q.invd, q.rhs);
+        const float sum = q.lam + dlc;
+        const float cl = fminf(fmaxf(sum, 0.f), q.hi);
+        const float dl = cl == sum ? dlc : cl - q.lam;
+        q.lam = l16 == ln ? cl : q.lam;
         const float v = __shfl_sync(FULL, dl, ln, 16);
 #pragma unroll
-        for (int sl = 0; sl < NS; sl++) b[sl] = fmaf(A[sl][so * 16 + ln], v, b[sl]);
+        for (int sl = 0; sl < NS; sl++) r[sl].b = fmaf(A[sl][so * 16 + ln], v, r[sl].b);
       }
     }
 #pragma unroll
-    for (int c = 0; c < 4 * NS; c++) {            // normal rows, contact order
+    for (int c = 0; c < 4 * NS; c++) {            // friction pairs with the implicit cone
       if (c < in.Cmax) {
         const int so = c >> 2, ln = 3 * (c & 3);
-        const float dlc = fmaf(-b[so], invd[so], rhs[so]);
-        const float sum = lam[so] + dlc;
-        const bool lo = sum < 0.f, up = sum > hi[so];
-        const float dl = lo ? -lam[so] : (up ? hi[so] - lam[so] : dlc);
-        if (l16 == ln) lam[so] = lo ? 0.f : (up ? hi[so] : sum);
-        const float v = __shfl_sync(FULL, dl, ln, 16);
-#pragma unroll
-        for (int sl = 0; sl < NS; sl++) b[sl] = fmaf(A[sl][so * 16 + ln], v, b[sl]);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 4 * NS; c++) {            // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
-      if (c < in.Cmax) {
-        const int so = c >> 2, ln = 3 * (c & 3);
-        const float sown = lam[so] + fmaf(-b[so], invd[so], rhs[so]);
+        RowRegs& q = r[so];
+        const float sown = q.lam + fmaf(-q.b, q.invd, q.rhs);
         const float sa = __shfl_sync(FULL, sown, ln + 1, 16), sb = __shfl_sync(FULL, sown, ln + 2, 16);
-        const float limit = mu[so] * __shfl_sync(FULL, lam[so], ln, 16);
+        const float limit = q.mu * __shfl_sync(FULL, q.lam, ln, 16);
         const float r2 = sa * sa + sb * sb;
         const bool clip = r2 >= limit * limit && r2 > 0.f;
         const float sc = clip ? limit * rsqrtf(r2) : 1.0f;
         const float snew = clip ? sown * sc : sown;
-        const float dl = snew - lam[so];
-        if (l16 == ln + 1 || l16 == ln + 2) lam[so] = snew;
+        const float dl = snew - q.lam;
+        q.lam = (l16 == ln + 1 || l16 == ln + 2) ? snew : q.lam;
         const float da = __shfl_sync(FULL, dl, ln + 1, 16), db = __shfl_sync(FULL, dl, ln + 2, 16);
 #pragma unroll
-        for (int sl = 0; sl < NS; sl++) b[sl] = fmaf(A[sl][so * 16 + ln + 1], da, fmaf(A[sl][so * 16 + ln + 2], db, b[sl]));
+        for (int sl = 0; sl < NS; sl++) r[sl].b = fmaf(A[sl][so * 16 + ln + 1], da, fmaf(A[sl][so * 16 + ln + 2], db, r[sl].b));
       }
     }
   }
-  // ---- the normal impulses go back to the contact records (warm start of the next sub-step)
 #pragma unroll
   for (int sl = 0; sl < NS; sl++)
-    if (is_con && d == 0 && 4 * sl + cq < in.nc) in.contab[(4 * sl + cq) * kConW + 17] = lam[sl];
-  // ---- total impulse: base part and the joint part of this lane's leg
+    if (l16 < 12 && l16 % 3 == 0 && 4 * sl + l16 / 3 < in.nc) in.contab[(4 * sl + l16 / 3) * kConW + 17] = r[sl].lam;
   float v18[18];
 #pragma unroll
   for (int t = 0; t < 18; t++) v18[t] = 0.f;
 #pragma unroll
-  for (int sl = 0; sl < NS; sl++) {
-#pragma unroll
-    for (int t = 0; t < 6; t++) v18[t] = fmaf(lam[sl], y[sl][t], v18[t]);
-#pragma unroll
-    for (int kk = 0; kk < 4; kk++) {
-      const float f = rleg[sl] == kk ? lam[sl] : 0.f;
-#pragma unroll
-      for (int m = 0; m < 3; m++) v18[6 + 3 * kk + m] = fmaf(f, wj[sl][m], v18[6 + 3 * kk + m]);
-    }
-  }
-#pragma unroll
-  for (int t = 0; t < 18; t++) v18[t] = hsum16(v18[t]);
-#pragma unroll
-  for (int t = 0; t < 6; t++) Yt[t] = v18[t];
-#pragma unroll
-  for (int m = 0; m < 3; m++) om[m] = in.k == 0 ? v18[6 + m] : (in.k == 1 ? v18[9 + m] : (in.k == 2 ? v18[12 + m] : v18[15 + m]));
+  for (int sl = 0; sl < NS; sl++) add_row_impulse(r[sl], v18);
+  impulse_sums(v18, in.k, Yt, om);
 }
-LLQ_DI void solve_rows1(const RowsIn& in, const Chol6& ch, float (&Yt)[6], float (&om)[3]) { solve_rows_impl<1>(in, ch, Yt, om); }
-// the rare path (more than 4 contacts or 4 limit rows in one of the warp's envs): its 2 x 32 Delassus coefficients per lane live in
-// local memory, out of line, so that the common path keeps its register budget
-__device__ __noinline__ void solve_rows2(const RowsIn& in, const Chol6& ch, float (&Yt)[6], float (&om)[3]) { solve_rows_impl<2>(in, ch, Yt, om); }
 
 // ---------------------------------------------------------------------------------------------------------------
 template <int ENV>
-__global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDev mc, StepParams P, const ModelConst* __restrict__ gmodel,
+__global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) llq_step16_kernel(EnvArrays E, MocapDev mc, StepParams P, const ModelConst* __restrict__ gmodel,
                                                             const SphTable* __restrict__ gsph, const float* __restrict__ actions,
                                                             float* obs2, long long obs2_ld, int* __restrict__ winner,
                                                             unsigned long long seed, long long gid0, int record) {
-  constexpr int BLOCK = 128, EPB = BLOCK / 16;        // 8 envs per CTA, 2 per warp
+  constexpr int BLOCK = LLQ16_BLOCK, EPB = BLOCK / 16;        // 2 envs per warp
   __shared__ __align__(16) ModelConst M;
   __shared__ __align__(16) SphTable ST;
   __shared__ __align__(16) float s_new[EPB][kNewObs];
   __shared__ __align__(16) float s_hist[EPB][kHist];
-  __shared__ __align__(16) float s_env[EPB][kEnvFloats];
+  extern __shared__ __align__(16) float s_env_dyn[];   // [EPB][kEnvFloats]: 38.4 kB, beside 10 kB of static shared memory
   const int tid = threadIdx.x;
   const int N = P.n_envs;
   prefetch_model(gmodel, &M, BLOCK);
@@ -342,13 +424,14 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
   const bool valid = env_raw < N;
   const LegConst& L = M.leg[k];
   const V3 r0 = ld3(L.j[0].r), r1 = ld3(L.j[1].r), r2 = ld3(L.j[2].r);
-  float* const linktab = &s_env[el][0];
+  float* const linktab = s_env_dyn + el * kEnvFloats;
   float* const legtab = linktab + kLinkTab;
   float* const contab = legtab + kLegTab;
   float* const limtab = contab + kConTab;
   float* const rowtab = limtab + kLimTab;
   float* const scr = rowtab;                         // dynamics-phase scratch (16 lanes x 20 floats) aliases the row table
   float* const envtab = rowtab + kRowTab;
+  float* const atab = envtab + kEnvTab;
   // joints with a lower dof index than this lane's (k, i): rank of a violated limit in Bullet's row order
   unsigned lowmask = 0;
 #pragma unroll
@@ -360,13 +443,16 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
   Q4 qb = Q4{st[env], st[N + env], st[2 * N + env], st[3 * N + env]};
   V3 vw = V3{st[4 * N + env], st[5 * N + env], st[6 * N + env]};
   V3 ww = V3{st[7 * N + env], st[8 * N + env], st[9 * N + env]};
-  float q[3], qd[3], act[3], tgt[3];
+  float q[3], qd[3];
 #pragma unroll
   for (int t = 0; t < 3; t++) {
     q[t] = st[(10 + 3 * k + t) * N + env];
     qd[t] = st[(22 + 3 * k + t) * N + env];
-    act[t] = actions[(size_t)env * kActDim + 3 * k + t];
-    tgt[t] = clampf(q[t] + act[t], -3.0f, 3.0f);           // PLE:200, LR:126-127
+  }
+  if (i < 3) {                                               // joint (k, i): action and clipped target stay in shared memory
+    const float a = actions[(size_t)env * kActDim + 3 * k + i];
+    envtab[44 + 3 * k + i] = a;
+    envtab[32 + 3 * k + i] = clampf((i == 0 ? q[0] : (i == 1 ? q[1] : q[2])) + a, -3.0f, 3.0f);           // PLE:200, LR:126-127
   }
   const int nsph = ST.n, rule = ST.rule;
   float warm[2];                                             // remembered normal impulses of spheres l16 and l16 + 16
@@ -416,12 +502,16 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
   // base orientation: pybullet speaks in the base inertial frame; dynamics run in URDF body axes B' = inertial * qI^-1
   const Q4 qI = Q4{M.base.qI[0], M.base.qI[1], M.base.qI[2], M.base.qI[3]};
   Q4 qp = qmul(qnormalize(qb), qconj(qI));
-  unsigned long long n_contact_rows = 0, n_limit_rows = 0, n_overflow = 0;
+  unsigned n_contact_rows = 0, n_limit_rows = 0, n_overflow = 0;
   bool bad = false;
   const float mu_foot = ENV != 0 ? mu_env : P.mu;
 
   for (int sub = 0; sub < P.substeps; sub++) {
-    __syncthreads();      // keeps the CTA's warps on the same stretch of code (instruction-cache sharing) and orders the table reuse
+#if LLQ16_BAR >= 1
+    __syncthreads();      // not needed for correctness (the tables are per half-warp): keeps the CTA's warps on one stretch of code
+#else
+    __syncwarp();         // the tables are per env (= per half-warp): no CTA-wide ordering is needed
+#endif
     const float dt = P.dt;
     // ---------------- push randomiser (PR:56-87): counters in sub-steps, force lasts one sub-step
     bool push_on = false;
@@ -443,6 +533,8 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
         push_on = push_count < P.push_duration;
       }
     }
+    V3 wbs, vbs;                                  // predicted base velocity in base coordinates (the rows' generalised velocity)
+    {   // ================ forward dynamics; everything declared here dies at the closing brace (register budget of the solver)
     // ---------------- kinematics: every lane evaluates the sine / cosine of its own joint, the leg's six values go round by shuffle
     const M3 R = qmat(qp);                       // world <- B'
     float c1, s1, c2, s2, c3, s3;
@@ -525,7 +617,7 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
       const float Cb = dot(ax, f.a) + dot(al, f.l);
       const float h0 = Fa.x + dot(l1, Fl), h1 = dot(n2, Fa) + dot(l2, Fl), h2 = dot(n2, Fa) + dot(l3, Fl);
       const float qi = i == 0 ? q[0] : (i == 1 ? q[1] : q[2]), qdi = i == 0 ? qd[0] : (i == 1 ? qd[1] : qd[2]);
-      const float tg = i == 0 ? tgt[0] : (i == 1 ? tgt[1] : tgt[2]);
+      const float tg = envtab[32 + 3 * k + ic];
       const float tau = clampf(fmaf(P.kp, tg - qi, P.kd * (0.f - qdi)), -P.max_tau, P.max_tau) - L.j[ic].jdamp * qdi;
       float* lt = legtab + k * 48;
       if (i < 3) {
@@ -606,13 +698,17 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
 #pragma unroll
       for (int t = 0; t < 6; t++) z0[t] += envtab[t];
     }
-    const Chol6 ch = chol6(m6);
     float a0[6];
     {
+      const Chol6 ch = chol6(m6);
       float bneg[6];
 #pragma unroll
       for (int t = 0; t < 6; t++) bneg[t] = -z0[t];
       chol6_solve(ch, bneg, a0);                // acceleration relative to free fall (gravity as a fictitious base acceleration)
+      if (l16 == 0) {                           // the factor is needed again by the row images and the final back substitution
+#pragma unroll
+        for (int t = 0; t < 21; t++) envtab[8 + t] = ch.l[t];
+      }
     }
     // ---------------- joint accelerations of this lane's leg, velocity prediction v* = clamp(v + a dt)
     {
@@ -630,7 +726,7 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
 #pragma unroll
       for (int t = 0; t < 3; t++) qd[t] = clampf(fmaf(qdd[t], dt, qd[t]), -P.vmax, P.vmax);
     }
-    const V3 wbs = tmul(R, ww), vbs = tmul(R, vw);   // predicted base velocity in base coordinates
+    wbs = tmul(R, ww); vbs = tmul(R, vw);
     __syncwarp();                                     // every lane has read F / H: the leg table becomes the rows' table
     if (i == 0) {
       float* lt = legtab + k * 48;
@@ -642,11 +738,21 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
       lt[24] = qd[0]; lt[25] = qd[1]; lt[26] = qd[2];
       lt[28] = c3; lt[29] = s3;                       // for the fp64 clearance of the shank's spheres
     }
-    const V3 fb = p3 + rot<0>(rot<1>(ld3(L.foot), c23, s23), c1, s1);     // foot centre of this lane's leg
+    }   // ================ end of the forward dynamics
+#if LLQ16_BAR >= 2
+    __syncthreads();
+#else
+    __syncwarp();
+#endif
+    const M3 R = qmat(qp);                            // world <- B' (recomputed: cheaper than keeping nine registers alive)
     // ---------------- PMC hurdle plate: getContactPoints (PLE:343) reports the manifolds built on the last sub-step's pre-step poses
     if (ENV == 0 && P.has_ob && sub == P.substeps - 1) {
       const int o0 = mc.ob_off[clip], n_ob = mc.ob_off[clip + 1] - o0;
       if (n_ob > 0) {
+        const float* lk = linktab + 24 * k;
+        const float c1 = lk[0], s1 = lk[1], c2 = lk[10], s2 = lk[11], c23 = lk[18], s23 = lk[19];
+        const V3 p1 = ld3(lk + 4), p2 = ld3(lk + 12), p3 = ld3(lk + 20);
+        const V3 fb = p3 + rot<0>(rot<1>(ld3(L.foot), c23, s23), c1, s1);     // foot centre of this lane's leg
         const double* ob = mc.ob_table + (size_t)(o0 + ob_id) * 4;
         float sy_, cy_;
         llq_sincosf((float)ob[3], &sy_, &cy_);
@@ -665,6 +771,10 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
       float* srow = &s_new[el][0];
       const float* prow = &s_new[el ^ 1][0];
       const V3 pw = V3{(float)px, (float)py, (float)pz};
+      const float* lk = linktab + 24 * k;
+      const float c1 = lk[0], s1 = lk[1], c2 = lk[10], s2 = lk[11], c23 = lk[18], s23 = lk[19];
+      const V3 p1 = ld3(lk + 4), p2 = ld3(lk + 12), p3 = ld3(lk + 20);
+      const V3 fb = p3 + rot<0>(rot<1>(ld3(L.foot), c23, s23), c1, s1);       // foot centre of this lane's leg
       const V3 wh = pw + mul(R, p2 + rot<0>(rot<1>(ld3(M.wheel_off[k]), c2, s2), c1, s1));
       const V3 hp_ = pw + mul(R, p1), ft = pw + mul(R, fb);
       const V3 c0 = pw + mul(R, ld3(M.corner[2 * k])), c1_ = pw + mul(R, ld3(M.corner[2 * k + 1]));
@@ -833,6 +943,7 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
     int nl = 0;
     {
       float dir = 0.f, pen = 0.f;
+      const int ic = i < 3 ? i : 0;
       if (i < 3 && L.j[ic].haslim) {
         const float qi = i == 0 ? q[0] : (i == 1 ? q[1] : q[2]);
         if (qi - L.j[ic].lower <= 0.f) { dir = 1.f; pen = qi - L.j[ic].lower; }
@@ -850,22 +961,21 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
     __syncwarp();
     float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dvl[3] = {0.f, 0.f, 0.f};
     {
-      int Cmax = nc, Lmax = nl;
-      Cmax = max(Cmax, __shfl_xor_sync(FULL, Cmax, 16));
-      Lmax = max(Lmax, __shfl_xor_sync(FULL, Lmax, 16));
+      // warp-uniform loop bounds (a redux result lives in a uniform register: the guards below compile to uniform branches)
+      const int Cmax = __reduce_max_sync(FULL, nc), Lmax = __reduce_max_sync(FULL, nl);
       if (Cmax | Lmax) {
         RowsIn in;
-        in.legtab = legtab; in.linktab = linktab; in.contab = contab; in.limtab = limtab; in.rowtab = rowtab;
+        in.legtab = legtab; in.linktab = linktab; in.contab = contab; in.limtab = limtab; in.rowtab = rowtab; in.chol = envtab + 8;
         in.nc = nc; in.nl = nl; in.Cmax = Cmax; in.Lmax = Lmax; in.l16 = l16; in.k = k;
         in.wbs = wbs; in.vbs = vbs; in.dt = dt; in.slop = P.slop; in.erp = P.erp; in.jerp = P.jerp; in.max_imp = P.max_imp; in.iters = P.solver_iters;
         float Yt[6], om[3];
-        if (Cmax > 4 || Lmax > 4) solve_rows2(in, ch, Yt, om); else solve_rows1(in, ch, Yt, om);
-        if (l16 == 0) { n_contact_rows += 3ull * (unsigned)nc; n_limit_rows += (unsigned)nl; }
+        if (Cmax > 4 || Lmax > 4) solve_rows2(in, Yt, om); else solve_rows_s(in, atab, Yt, om);
+        if (l16 == 0) { n_contact_rows += 3u * (unsigned)nc; n_limit_rows += (unsigned)nl; }
         __syncwarp();
 #pragma unroll
         for (int rd = 0; rd < 2; rd++) if (mycon[rd] >= 0) warm[rd] = contab[mycon[rd] * kConW + 17];
         // ---- total impulse -> velocity change: one back substitution for the base, one 3x3 solve per leg
-        chol6_bwd(ch, Yt, dvb);
+        chol6_bwd_p(envtab + 8, Yt, dvb);
         const float* lt = legtab + k * 48;            // W, L, D^-1 of this lane's leg come back from the leg table (not kept live across the solve)
         float t3[3];
 #pragma unroll
@@ -898,7 +1008,7 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
     }
     bad = bad || !(fabsf(qd[0]) <= P.vmax) || !(fabsf(ww.x) <= P.vmax) || !(fabsf(vw.x) <= P.vmax);
     // ---------------- mocap clock (PLE:208-210): sampled with the time *before* the increment
-    if (ENV == 0) {
+    if (ENV == 0 && sub == P.substeps - 1) {
       frame_id = (int)floor(time / P.frame_dt);
       frame_frac = (time - frame_id * P.frame_dt) / P.frame_dt;
       const int last = mc.clip_off[clip + 1] - mc.clip_off[clip] - P.margin + 2;     // see llq_kernels.cuh: runaway cursors only
@@ -928,7 +1038,7 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
     float* snew = &s_new[el][0];
     ObsCtx oc = build_obs_new(mc, P, M, k, clip, frame_id, frame_frac, px, py, pz, qb, vw, ww, q, qd, snew);
 #pragma unroll
-    for (int t = 0; t < 3; t++) snew[kPropDim + 3 * k + t] = act[t];
+    for (int t = 0; t < 3; t++) snew[kPropDim + 3 * k + t] = envtab[44 + 3 * k + t];
     // reward (PLE:350-426)
     float djp = 0.f, djv = 0.f;
 #pragma unroll
@@ -1015,7 +1125,7 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
     const float* spart = &s_new[el ^ 1][0];
     sepmc_pair_tail<16>(M, L, k, robot, snew, spart, px, py, pz, qp, qb, vw, ww, q, touch_own, fix_spd, seed, pair_gid, epi, PS);
 #pragma unroll
-    for (int t = 0; t < 3; t++) { snew[3 * k + t] = q[t]; snew[12 + 3 * k + t] = qd[t]; snew[kPropDim + 3 * k + t] = act[t]; }
+    for (int t = 0; t < 3; t++) { snew[3 * k + t] = q[t]; snew[12 + 3 * k + t] = qd[t]; snew[kPropDim + 3 * k + t] = envtab[44 + 3 * k + t]; }
     const float spd = sqrtf(vw.x * vw.x + vw.y * vw.y);              // stat_spd (CTG:368-373)
     total_spd += (double)spd;
     if ((double)spd > max_spd) max_spd = (double)spd;
@@ -1092,7 +1202,7 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
     const Q4 q1 = qnormalize(qb);
     const M3 Rq = qmat(q1);
 #pragma unroll
-    for (int t = 0; t < 3; t++) { snew[3 * k + t] = q[t]; snew[12 + 3 * k + t] = qd[t]; snew[kPropDim + 3 * k + t] = act[t]; }
+    for (int t = 0; t < 3; t++) { snew[3 * k + t] = q[t]; snew[12 + 3 * k + t] = qd[t]; snew[kPropDim + 3 * k + t] = envtab[44 + 3 * k + t]; }
     counter += 1;
     const double dx = tgx - px, dy = tgy - py;
     const double plen = sqrt(dx * dx + dy * dy);
@@ -1163,20 +1273,20 @@ __global__ void __launch_bounds__(128, 4) llq_step16_kernel(EnvArrays E, MocapDe
   if (record && obs2 && wr) {
     float* row = obs2 + (size_t)env * obs2_ld + ObsW<ENV>::value - (record == 2 ? (long long)N * obs2_ld : 0ll);
 #pragma unroll
-    for (int t = 0; t < 3; t++) row[3 * k + t] = act[t];
+    for (int t = 0; t < 3; t++) row[3 * k + t] = envtab[44 + 3 * k + t];
     if (k == 0) { row[12] = rew_out; row[13] = done ? 1.f : 0.f; }
   }
   // counters: one atomic per warp
   {
-    unsigned long long cr = n_contact_rows, lr = n_limit_rows, ov = n_overflow;
+    unsigned cr = n_contact_rows, lr = n_limit_rows, ov = n_overflow;
     if (!valid) { cr = 0; lr = 0; ov = 0; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { cr += __shfl_xor_sync(FULL, cr, o); lr += __shfl_xor_sync(FULL, lr, o); ov += __shfl_xor_sync(FULL, ov, o); }
     unsigned dm = __ballot_sync(FULL, valid && l16 == 0 && done);
     if ((threadIdx.x & 31) == 0) {
-      if (cr) atomicAdd(&E.counters[2], cr);
-      if (lr) atomicAdd(&E.counters[3], lr);
-      if (ov) atomicAdd(&E.counters[5], ov);
+      if (cr) atomicAdd(&E.counters[2], (unsigned long long)cr);
+      if (lr) atomicAdd(&E.counters[3], (unsigned long long)lr);
+      if (ov) atomicAdd(&E.counters[5], (unsigned long long)ov);
       if (dm) atomicAdd(&E.counters[1], (unsigned long long)__popc(dm));
     }
   }

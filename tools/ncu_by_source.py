@@ -1,6 +1,7 @@
 """Dynamic warp-instructions and stall samples of one kernel of an .ncu-rep, aggregated by SOURCE REGION of the calling file
-(llq_kernels.cuh): SASS addresses from the report's source page are mapped to `//## File ... line N` markers of `nvdisasm -g` on
-the same library (inlined llq_math.cuh helpers are attributed to the last llq_kernels.cuh line seen before them).
+(default llq_step16.cuh; LLQ_SRC_FILE overrides): SASS addresses from the report's source page are mapped to `//## File ... line N`
+markers of `nvdisasm -g` on the same library (inlined helpers from other headers are attributed to the last line of the calling file
+seen before them).
 Usage: python tools/ncu_by_source.py REP LIB.so KERNEL_MANGLED_SUBSTR [bucket]"""
 import collections
 import csv
@@ -25,7 +26,7 @@ def main():
     for l in dis[start:end]:
         m = re.match(r'\s*//## File "([^"]+)", line (\d+)', l)
         if m:
-            if m.group(1).endswith("llq_kernels.cuh"):
+            if m.group(1).endswith(os.environ.get("LLQ_SRC_FILE", "llq_step16.cuh")):
                 klast = int(m.group(2))
             continue
         m = re.match(r"\s+/\*([0-9a-f]{4,5})\*/", l)
@@ -48,7 +49,7 @@ def main():
         samp[b] += int(r[col["# Samples"]] or 0)
         inst[b] += int(r[col["Instructions Executed"]] or 0)
     ts, ti = sum(samp.values()) or 1, sum(inst.values()) or 1
-    print("# %s: %d warp-instructions, %d samples; rows = llq_kernels.cuh lines [b, b+%d)" % (os.path.basename(rep), ti, ts, bucket))
+    print("# %s: %d warp-instructions, %d samples; rows = %s lines [b, b+%d)" % (os.path.basename(rep), ti, ts, os.environ.get("LLQ_SRC_FILE", "llq_step16.cuh"), bucket))
     for b in sorted(samp, key=lambda x: (x is None, x)):
         print("%6s  inst %5.1f%%  samples %5.1f%%" % (b, 100.0 * inst[b] / ti, 100.0 * samp[b] / ts))
 
