@@ -249,7 +249,7 @@ int llq_default_config(llq_config* c) {
   c->target_spd_lo = 0.5; c->target_spd_hi = 3.0;
   c->element_id = 0; c->wall_width_lo = 0.02; c->wall_width_hi = 0.5; c->wall_gap_lo = 1.0; c->wall_gap_hi = 20.0;
   c->hole_gap_lo = 0.25; c->hole_gap_hi = 0.3;
-  c->knee_contacts = 1; c->reserved1 = 0; c->link_friction = 0.5;
+  c->knee_contacts = 2; c->reserved1 = 0; c->link_friction = 0.5;
   return LLQ_OK;
 }
 

@@ -485,7 +485,9 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
   if (ENV == 3) {
     s_cand = &s_new[el][0];                            // the staging row is free until the tail: 8 x 6 floats
     const float* bxs = E.boxes + (size_t)env * (6 * kMaxBoxes);
-    unsigned long long m = box_mask(bxs, E.nbox[env], k, (float)px, (float)py, (float)pz, 0.6f, false);
+    // reach of the robot's spheres from the base reference point: hip offset 0.195 + leg 0.48 in x, 0.15 + 0.05 in y, plus the
+    // travel during the step (<= 0.06 m at 3 m/s) -> 0.8 m per axis (0.6 missed hind feet stretched backwards over a hurdle)
+    unsigned long long m = box_mask(bxs, E.nbox[env], k, (float)px, (float)py, (float)pz, 0.8f, false);
     int c = 0;
     while (m && c < kMaxCand) {
       const int j = __ffsll((long long)m) - 1;

@@ -15,6 +15,7 @@ from .. import spaces
 from ..model.compile_model import load_model_blob
 from .playground_env import INIT_STATE_RUN_0
 from .primitive_level_env import SHIPPED_PROP_TYPE, _FULL_PROP_SIZE
+from .primitive_level_env import default_seed
 
 
 def _default_engine_factory(n_envs, model_blob, **cfg):
@@ -56,7 +57,7 @@ class ChaseTagGameEnv:
 
     def __init__(self, enable_render=False, control_freq=25.0, kp=50.0, kd=1.0, max_tau=16, terrain_perception=None, prop_type=None,
                  stack_frame_num=3, n_max=2, max_steps=1000, visible_angle=np.pi, obs_randomization=None, env_randomize_config=None,
-                 element_config=None, seed=0, device=0):
+                 element_config=None, seed=None, device=0):
         if not isinstance(prop_type, list):
             raise TypeError("Expected 'prop_type' to be a list.")                            # CTG:98-99
         for e in prop_type:
@@ -75,7 +76,7 @@ class ChaseTagGameEnv:
             max_tau = float(np.random.uniform(*max_tau))                                     # LR:244
         self.n_max = n_max
         self.max_steps = max_steps
-        self._engine = engine_factory(2, load_model_blob(), device=device, seed=seed, auto_reset=0,
+        self._engine = engine_factory(2, load_model_blob(), device=device, seed=default_seed() if seed is None else seed, auto_reset=0,
                                       **sepmc_engine_config(control_freq, kp, kd, max_tau, max_steps, env_randomize_config))
         self._engine.set_init_state(INIT_STATE_RUN_0)
         dict_obs_space = OrderedDict((k, spaces.Box(0, 0, shape=shp if shp else (n,))) for k, n, shp in OBS_LAYOUT)

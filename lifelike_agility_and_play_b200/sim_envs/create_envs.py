@@ -56,7 +56,7 @@ def create_tracking_game(**env_config):
         obstacle_height=env_config.get("obstacle_height", 0.0),
         reward_weights=env_config.get("reward_weights", None),
         # engine-only extras (ignored by the reference)
-        seed=env_config.get("seed", 0), device=env_config.get("device", 0), mocap=env_config.get("mocap", None),
+        seed=env_config.get("seed", None), device=env_config.get("device", 0), mocap=env_config.get("mocap", None),
     )
     return SingleAgentWrapper(env0)
 
@@ -85,7 +85,7 @@ def create_playground_game(**env_config):
         max_steps=env_config["max_steps"] if "max_steps" in env_config else 1000,
         obs_randomization=env_config["obs_randomization"] if "obs_randomization" in env_config else None,
         env_randomize_config=env_config["env_randomize_config"] if "env_randomize_config" in env_config else None,
-        seed=env_config.get("seed", 0), device=env_config.get("device", 0),
+        seed=env_config.get("seed", None), device=env_config.get("device", 0),
     )
     return SingleAgentWrapper(env0)
 
@@ -115,7 +115,7 @@ def create_chase_tag_game(**env_config):
         obs_randomization=env_config["obs_randomization"] if "obs_randomization" in env_config else None,
         element_config=env_config.get('element_config', {}),
         env_randomize_config=env_config.get('env_randomize_config', {}),
-        seed=env_config.get("seed", 0), device=env_config.get("device", 0),
+        seed=env_config.get("seed", None), device=env_config.get("device", 0),
     )
     return env0
 

@@ -14,7 +14,7 @@ import numpy as np
 from .. import _capi as capi
 from .. import spaces
 from ..model.compile_model import load_model_blob
-from .primitive_level_env import SHIPPED_PROP_TYPE, _FULL_PROP_SIZE
+from .primitive_level_env import SHIPPED_PROP_TYPE, _FULL_PROP_SIZE, default_seed
 
 # LeggedRobot.get_init_states_info() (LR:115-117) -> utils/constants.py:103-116 STATES_INFO_12_RUN_0
 INIT_STATE_RUN_0 = np.array(
@@ -68,7 +68,7 @@ class PlayGroundEnv:
     metadata = {}
 
     def __init__(self, enable_render=False, control_freq=50, kp=50.0, kd=1.0, max_tau=16, prop_type=None, stack_frame_num=3,
-                 max_steps=1000, obs_randomization=None, env_randomize_config=None, seed=0, device=0):
+                 max_steps=1000, obs_randomization=None, env_randomize_config=None, seed=None, device=0):
         if not isinstance(prop_type, list):
             raise TypeError("Expected 'prop_type' to be a list.")                            # PGE:125-126
         for e in prop_type:
@@ -85,6 +85,7 @@ class PlayGroundEnv:
         if isinstance(max_tau, (list, tuple)):
             max_tau = float(np.random.uniform(*max_tau))                                     # LR:244 (PGE:236 writes a dead attribute)
         self._max_steps = max_steps
+        seed = default_seed() if seed is None else seed
         self._engine = engine_factory(1, load_model_blob(), device=device, seed=seed, auto_reset=0,
                                       **epmc_engine_config(control_freq, kp, kd, max_tau, max_steps, env_randomize_config))
         self._engine.set_init_state(INIT_STATE_RUN_0)
@@ -104,16 +105,46 @@ class PlayGroundEnv:
                             'target': row[913:916].copy()})
 
     def reset(self, **kwargs):
-        return self._split(self._engine.reset()[0])                                          # PGE:196-249
+        self.episodic_reward = OrderedDict({'reward_vel': 0.0, 'reward_rotation': 0.0, 'reward_dist': 0.0, 'reward_avg_spd': 0.0})   # PGE:228
+        obs = self._split(self._engine.reset()[0])                                           # PGE:196-249
+        self._last_len = float(self._engine.get(capi.F_AUX)[0][6])
+        return obs
+
+    def _episodic_terms(self, aux, reward, done):
+        """The per-term sums the reference reports in `info` on termination (PGE:354-357, 498-501, 527-538), restated on the host from
+        the step's post-state: the kernel returns the summed reward only."""
+        st = self._engine.get(capi.F_STATE)[0].astype(np.float64)
+        d = np.array([aux[2] - st[0], aux[3] - st[1]])
+        plen = float(np.linalg.norm(d))
+        u = d / plen
+        x, y, z, w = st[3:7] / np.linalg.norm(st[3:7])
+        yaw = np.arctan2(2 * (x * y + z * w), 1 - 2 * (y * y + z * z))
+        reward_rotation = float(np.exp((np.cos(yaw) * u[0] + np.sin(yaw) * u[1] - 1.0) * 5.0))
+        if self.reward_type == 'joystick':
+            spd = abs(st[7] * u[0] + st[8] * u[1])
+            self.episodic_reward['reward_rotation'] += reward_rotation / float(self._max_steps)
+            self.episodic_reward['reward_vel'] += float(np.exp(-abs(spd - aux[4]))) / float(self._max_steps)
+        else:
+            init_len = float(aux[17])
+            scaled_rot = reward_rotation / float(self._max_steps) * 0.1
+            scaled_dist = -((plen - self._last_len) / init_len) * 0.1
+            self._last_len = plen
+            self.episodic_reward['reward_rotation'] += scaled_rot * 2.0
+            self.episodic_reward['reward_dist'] += scaled_dist
+            if done and plen < 0.5:
+                self.episodic_reward['reward_avg_spd'] += float(reward) - (scaled_rot * 2.0 + scaled_dist)
 
     def step(self, rl_action):
         a = rl_action['A_LLC'] if isinstance(rl_action, dict) and 'A_LLC' in rl_action else rl_action    # PGE:323
         obs, reward, done = self._engine.step(np.asarray(a, dtype=np.float32).reshape(1, 12))
         info = {}
+        aux = self._engine.get(capi.F_AUX)[0]
+        self._episodic_terms(aux, reward[0], bool(done[0]))
         if done[0]:                                                                           # PGE:345-357
-            aux = self._engine.get(capi.F_AUX)[0]
             info['ave_spd'] = float(aux[7] / aux[0])
             info['max_spd'] = float(aux[8])
+            for key in ('reward_vel', 'reward_rotation', 'reward_dist', 'reward_avg_spd'):
+                info[key] = self.episodic_reward[key]
         return self._split(obs[0]), float(reward[0]), bool(done[0]), info
 
     def close(self):

@@ -30,13 +30,20 @@ def _default_engine_factory(n_envs, model_blob, mocap, **cfg):
 engine_factory = _default_engine_factory
 
 
+def default_seed():
+    """The reference draws from the unseeded global np.random, so every actor process differs; an engine constructed without a
+    seed does the same (OS entropy), instead of every actor replaying the streams of seed 0."""
+    import os
+    return int.from_bytes(os.urandom(8), 'little') >> 1
+
+
 class PrimitiveLevelEnv:
     metadata = {}
 
     def __init__(self, enable_render=False, control_freq=50.0, sim_freq=500.0, kp=50.0, kd=0.5,
                  foot_lateral_friction=0.5, max_tau=18, enable_gui=True, video_path=None, data_path="",
                  prop_type=None, stack_frame_num=3, prioritized_sample_factor=0.0, set_obstacle=False,
-                 obstacle_height=0.2, reward_weights=None, seed=0, device=0, mocap=None):
+                 obstacle_height=0.2, reward_weights=None, seed=None, device=0, mocap=None):
         if video_path is not None:
             assert isinstance(video_path, str) and video_path.endswith('.mp4')       # PLE:53-55
         if not isinstance(prop_type, list):
@@ -57,7 +64,7 @@ class PrimitiveLevelEnv:
                                'root_vel': 0.1}                                         # PLE:352-363
         self._mocap = mocap if mocap is not None else load_mocap(data_path)             # PLE:129 -> ML:19-46
         self._engine = engine_factory(
-            1, load_model_blob(), self._mocap, device=device, seed=seed, substeps=self.num_env_steps,
+            1, load_model_blob(), self._mocap, device=device, seed=default_seed() if seed is None else seed, substeps=self.num_env_steps,
             sim_dt=self._time_step, policy_dt=self._policy_step, kp=kp, kd=kd, max_tau=float(max_tau),
             foot_friction=foot_lateral_friction, prioritized_sample_factor=prioritized_sample_factor, auto_reset=0,
             w_joint_pos=w['joint_pos'], w_joint_vel=w['joint_vel'], w_end_effector=w['end_effector'],

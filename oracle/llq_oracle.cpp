@@ -796,6 +796,12 @@ void write_obs(const llq_engine& E, Env& e, const double* st) {
 void motion_set_time(const llq_engine& E, Env& e, double t) {  // ML:65-67
   e.frame_id = (int)std::floor(t / E.frame_dt);
   e.frame_frac = (t - e.frame_id * E.frame_dt) / E.frame_dt;
+  // A cursor past the clip's playable range (a finished env stepped on without a reset, a clock set through llq_set_field) stays on
+  // the last cursor whose 1 s future window (122 frames) lies inside the clip -- the reference raises IndexError there; both engines
+  // clamp.  The final step of an episode legitimately runs up to 2.4 frames past the "ended" threshold nf - margin - 1.
+  const int last = E.clip_off[e.clip + 1] - E.clip_off[e.clip] - E.margin + 2;
+  if (e.frame_id > last) { e.frame_id = last; e.frame_frac = 0.0; }
+  if (e.frame_id < 0) { e.frame_id = 0; e.frame_frac = 0.0; }
 }
 
 // PLE:150-171 with (clip, sampled_time) given
@@ -1574,7 +1580,7 @@ int llq_default_config(llq_config* c) {
   c->target_spd_lo = 0.5; c->target_spd_hi = 3.0;
   c->element_id = 0; c->wall_width_lo = 0.02; c->wall_width_hi = 0.5; c->wall_gap_lo = 1.0; c->wall_gap_hi = 20.0;
   c->hole_gap_lo = 0.25; c->hole_gap_hi = 0.3;
-  c->knee_contacts = 1; c->reserved1 = 0; c->link_friction = 0.5;
+  c->knee_contacts = 2; c->reserved1 = 0; c->link_friction = 0.5;
   return LLQ_OK;
 }
 
