@@ -392,12 +392,303 @@ __device__ __noinline__ void solve_rows2(const RowsIn& in, float (&Yt)[6], float
 }
 
 // ---------------------------------------------------------------------------------------------------------------
+// End of the policy step: observation, reward, termination, write-back -- run by FOUR lanes per env (lane k = leg k, 8 envs per
+// warp) on the first EPB / 8 warps of the CTA, from the state the sub-step lanes left in shared memory.  With 16 lanes per env this
+// part (mocap interpolation, four future targets, reward, the cooperative emission of the observation rows) would run once per TWO
+// envs; here one instruction stream serves eight.
+struct TailState {            // per env, written by the env's lane 0 (base part) and its lanes (k, 0) (joint part)
+  double px, py, pz, time, frame_frac;
+  int frame_id, ob_id, flags, push_count, push_draws;      // flags: bad | ob_hit << 1 | touch_own << 2 | tag << 3
+  float pf[3], qp[4], vw[3], ww[3], q[12], qd[12];
+};
+static_assert(sizeof(TailState) <= sizeof(float) * kRowTab, "the hand-over record lives in the row table");
+template <int ENV, int EPB>
+LLQ_DI void step_tail(const EnvArrays& E, const MocapDev& mc, const StepParams& P, const ModelConst& M, float* s_new, const float* s_hist,
+                      const TailState& T, const float* act_src, float* obs2, long long obs2_ld, int* winner, unsigned long long seed, long long gid0,
+                      int record, int el, int k, int env, bool valid) {
+  const int N = P.n_envs;
+  double px = T.px, py = T.py, pz = T.pz, time = T.time, frame_frac = T.frame_frac;
+  int frame_id = T.frame_id, ob_id = T.ob_id, push_count = T.push_count, push_draws = T.push_draws;
+  bool bad = (T.flags & 1) != 0, ob_hit = (T.flags & 2) != 0;
+  const bool touch_own = (T.flags & 4) != 0, tag = (T.flags & 8) != 0;
+  const float pf[3] = {T.pf[0], T.pf[1], T.pf[2]};
+  const Q4 qp = Q4{T.qp[0], T.qp[1], T.qp[2], T.qp[3]};
+  const V3 vw = V3{T.vw[0], T.vw[1], T.vw[2]}, ww = V3{T.ww[0], T.ww[1], T.ww[2]};
+  float q[3], qd[3];
+#pragma unroll
+  for (int t = 0; t < 3; t++) { q[t] = T.q[3 * k + t]; qd[t] = T.qd[3 * k + t]; }
+  const int clip = ENV == 0 ? E.clip[env] : 0;
+  const long long epi = ENV != 0 ? E.episode[env] - 1 : 0;
+  const int robot = env & 1;
+  const long long pair_gid = gid0 + (env & ~1);
+  bool done = false;
+  float rew_out = 0.f;
+  const bool wr = valid;
+  const LegConst& L = M.leg[k];
+  const Q4 qI = Q4{M.base.qI[0], M.base.qI[1], M.base.qI[2], M.base.qI[3]};
+  Q4 qb;
+  PairState PS = {0, 0, 1, 0, 0.0, 0.0};
+  if (ENV == 0) {
+    qb = qmul(qp, qI);                                 // back to the pybullet (inertial-frame) convention
+    float* snew = s_new + el * kNewObs;
+    ObsCtx oc = build_obs_new(mc, P, M, k, clip, frame_id, frame_frac, px, py, pz, qb, vw, ww, q, qd, snew);
+#pragma unroll
+    for (int t = 0; t < 3; t++) snew[kPropDim + 3 * k + t] = act_src[3 * k + t];
+    // reward (PLE:350-426)
+    float djp = 0.f, djv = 0.f;
+#pragma unroll
+    for (int t = 0; t < 3; t++) { float a = q[t] - oc.kq[t], b = qd[t] - oc.kqd[t]; djp = fmaf(a, a, djp); djv = fmaf(b, b, djv); }
+    V3 fd, fk;
+    {
+      M3 Rp = qmat(qp);
+      V3 f = mul(Rp, foot_in_base(L, q[0], q[1], q[2]));
+      fd = V3{(float)px + f.x, (float)py + f.y, (float)pz + f.z};
+      Q4 kqp = qmul(qnormalize(oc.kb.q), qconj(qI));
+      V3 g = mul(qmat(kqp), foot_in_base(L, oc.kq[0], oc.kq[1], oc.kq[2]));
+      // difference of foot positions, formed in double for the base offset
+      fk = V3{(float)(oc.kb.px - px) + g.x - f.x, (float)(oc.kb.py - py) + g.y - f.y, (float)(oc.kb.pz - pz) + g.z - f.z};
+    }
+    float dee = dot(fk, fk);
+    djp = gsum4(djp); djv = gsum4(djv); dee = gsum4(dee);
+    float dpx = (float)(px - oc.kb.px), dpy = (float)(py - oc.kb.py), dpz = (float)(pz - oc.kb.pz);
+    float dp = dpx * dpx + dpy * dpy + dpz * dpz;
+    V3 dvl3 = vw - oc.kb.lin, dva3 = ww - oc.kb.ang;
+    Q4 q1 = qnormalize(qb), q2 = qnormalize(oc.kb.q);
+    float angle = norm3(q_rotvec(qnormalize(qmul(q2, qconj(q1)))));
+    float rew = P.w_jp * expf(-1.0f * djp) + P.w_jv * expf(-0.1f * djv) + P.w_ee * expf(-40.0f * dee) +
+                P.w_pose * expf(-20.0f * dp - 10.0f * angle * angle) + P.w_vel * expf(-2.0f * dot(dvl3, dvl3) - 0.2f * dot(dva3, dva3));
+    // termination (PLE:337-348, LR:158-179, ML:168-172)
+    M3 Rq = qmat(q1);
+    float left_z = Rq.a02 * Rq.a10 - Rq.a12 * Rq.a00;
+    bool fall = left_z > 0.70710678118654752f || left_z < -0.70710678118654752f || Rq.a22 < 0.5f;
+    int nf = mc.clip_off[clip + 1] - mc.clip_off[clip];
+    bool ended = frame_id >= nf - P.margin - 1;
+    bool diff = fabsf(angle) > 1.0f || dp > 1.0f;
+    if (bad || !isfinite(rew)) { rew = 0.f; bad = true; }
+    if (P.has_ob) {
+      int oh = ob_hit ? 1 : 0;
+      oh |= __shfl_xor_sync(FULL, oh, 1);
+      oh |= __shfl_xor_sync(FULL, oh, 2);
+      ob_hit = oh != 0;
+      const int o0 = mc.ob_off[clip], n_ob = mc.ob_off[clip + 1] - o0;                 // PLE:262-268 hand-over to the next plate
+      while (ob_id < n_ob - 1 && time > mc.ob_table[(size_t)(o0 + ob_id) * 4] + 0.5) ob_id++;
+    }
+    done = fall || ended || diff || ob_hit || bad;                                     // PLE:347
+    rew_out = rew;
+    if (wr) {
+      float* sw = E.st;
+#pragma unroll
+      for (int t = 0; t < 3; t++) {
+        sw[(10 + 3 * k + t) * N + env] = q[t];
+        sw[(22 + 3 * k + t) * N + env] = qd[t];
+        E.kin[(13 + 3 * k + t) * N + env] = oc.kq[t];
+        E.kin[(25 + 3 * k + t) * N + env] = oc.kqd[t];
+      }
+      E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
+      if (k == 0) {
+        E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
+        sw[env] = qb.x; sw[N + env] = qb.y; sw[2 * N + env] = qb.z; sw[3 * N + env] = qb.w;
+        sw[4 * N + env] = vw.x; sw[5 * N + env] = vw.y; sw[6 * N + env] = vw.z;
+        sw[7 * N + env] = ww.x; sw[8 * N + env] = ww.y; sw[9 * N + env] = ww.z;
+        E.time[env] = time;
+        if (P.has_ob) E.ob_id[env] = ob_id;
+        float rs = E.reward_sum[env] + rew;
+        E.reward_sum[env] = rs;
+        E.episode_steps[env] += 1;
+        E.reward[env] = rew;
+        E.done[env] = done ? 1 : 0;
+        E.kin[env] = (float)oc.kb.px; E.kin[N + env] = (float)oc.kb.py; E.kin[2 * N + env] = (float)oc.kb.pz;
+        E.kin[3 * N + env] = oc.kb.q.x; E.kin[4 * N + env] = oc.kb.q.y; E.kin[5 * N + env] = oc.kb.q.z; E.kin[6 * N + env] = oc.kb.q.w;
+        E.kin[7 * N + env] = oc.kb.lin.x; E.kin[8 * N + env] = oc.kb.lin.y; E.kin[9 * N + env] = oc.kb.lin.z;
+        E.kin[10 * N + env] = oc.kb.ang.x; E.kin[11 * N + env] = oc.kb.ang.y; E.kin[12 * N + env] = oc.kb.ang.z;
+        if (done) {
+          E.done_reward[env] = rs;
+          atomicMax(&winner[clip], env);       // highest finished env index owns the clip's slot this step (PLE:236)
+        }
+      }
+    }
+  } else if (ENV == 2) {
+    // ---------------- SEPMC tail (CTG:378-424, 458-470, 495-596, 640-652)
+    const double* A = E.aux;
+    int counter = (int)A[env];
+    PS.with_flag = (int)A[N + env]; PS.flag_x = A[2 * N + env]; PS.flag_y = A[3 * N + env];
+    const float fix_spd = (float)A[4 * N + env];
+    double total_spd = A[7 * N + env], max_spd = A[8 * N + env];
+    PS.flag_draws = (int)A[15 * N + env];
+    qb = qmul(qp, qI);
+    float* snew = s_new + el * kNewObs;
+    const float* spart = s_new + (el ^ 1) * kNewObs;
+    sepmc_pair_tail<4>(M, L, k, robot, snew, spart, px, py, pz, qp, qb, vw, ww, q, touch_own, fix_spd, seed, pair_gid, epi, PS);
+#pragma unroll
+    for (int t = 0; t < 3; t++) { snew[3 * k + t] = q[t]; snew[12 + 3 * k + t] = qd[t]; snew[kPropDim + 3 * k + t] = act_src[3 * k + t]; }
+    const float spd = sqrtf(vw.x * vw.x + vw.y * vw.y);              // stat_spd (CTG:368-373)
+    total_spd += (double)spd;
+    if ((double)spd > max_spd) max_spd = (double)spd;
+    counter += 1;
+    const M3 Rq = qmat(qnormalize(qb));
+    const float left_z = Rq.a02 * Rq.a10 - Rq.a12 * Rq.a00;
+    int fall = (left_z > 0.70710678118654752f || left_z < -0.70710678118654752f || Rq.a22 < 0.5f) ? 1 : 0;
+    const int fall_other = __shfl_xor_sync(FULL, fall, 4);
+    if (robot == 1) fall = fall_other;                                  // only robot 0's fall ends the episode (CTG:462)
+    bad = bad || __shfl_xor_sync(FULL, bad ? 1 : 0, 4) != 0;
+    done = fall != 0 || counter >= P.max_steps || tag || bad;
+    // rewards (CTG:640-652, 412-419): +-1 on a flag switch, +-1 on a tag; with_flag after the switch
+    const int wf0 = robot == 0 ? PS.with_flag : 1 - PS.with_flag;       // does robot 0 hold the flag
+    float rew = (float)PS.sw * ((wf0 != 0) == (robot == 0) ? 1.f : -1.f);
+    if (done && tag) rew += (wf0 != 0) == (robot == 0) ? 1.f : -1.f;
+    if (bad) rew = 0.f;
+    rew_out = rew;
+    V3 fd;
+    {
+      V3 f = mul(qmat(qp), foot_in_base(L, q[0], q[1], q[2]));
+      fd = V3{(float)px + f.x, (float)py + f.y, (float)pz + f.z};
+    }
+    if (wr) {
+      float* sw = E.st;
+#pragma unroll
+      for (int t = 0; t < 3; t++) { sw[(10 + 3 * k + t) * N + env] = q[t]; sw[(22 + 3 * k + t) * N + env] = qd[t]; }
+      E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
+      if (k == 0) {
+        E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
+        sw[env] = qb.x; sw[N + env] = qb.y; sw[2 * N + env] = qb.z; sw[3 * N + env] = qb.w;
+        sw[4 * N + env] = vw.x; sw[5 * N + env] = vw.y; sw[6 * N + env] = vw.z;
+        sw[7 * N + env] = ww.x; sw[8 * N + env] = ww.y; sw[9 * N + env] = ww.z;
+        E.time[env] = time;
+        E.reward_sum[env] += rew;
+        E.episode_steps[env] += 1;
+        E.reward[env] = rew;
+        E.done[env] = done ? 1 : 0;
+        double* Aw = E.aux;
+        Aw[env] = counter; Aw[N + env] = PS.with_flag; Aw[2 * N + env] = PS.flag_x; Aw[3 * N + env] = PS.flag_y; Aw[5 * N + env] = PS.visible;
+        Aw[6 * N + env] = PS.sw; Aw[7 * N + env] = total_spd; Aw[8 * N + env] = max_spd; Aw[9 * N + env] = push_count;
+        Aw[10 * N + env] = pf[0]; Aw[11 * N + env] = pf[1]; Aw[12 * N + env] = pf[2]; Aw[14 * N + env] = push_draws; Aw[15 * N + env] = PS.flag_draws;
+        Aw[17 * N + env] = touch_own ? 1.0 : 0.0;
+      }
+    }
+  } else {
+    // ---------------- EPMC tail (PGE:302-321, 334-358, 360-372, 479-539)
+    const double* A = E.aux;
+    int counter = (int)A[env], cmd_draws = (int)A[15 * N + env];
+    const int cmd_freq = (int)A[N + env];
+    double tgx = A[2 * N + env], tgy = A[3 * N + env], target_angle = A[5 * N + env], last_len = A[6 * N + env];
+    double total_spd = A[7 * N + env], max_spd = A[8 * N + env];
+    float target_spd = (float)A[4 * N + env];
+    const double init_len = ENV == 3 ? A[17 * N + env] : 1.0;
+    {
+      // the command of this step was drawn from the pose at the START of the step (PGE:302-317): recover it from the stored state
+      const double sx0 = E.pos[env], sy0 = E.pos[N + env];
+      if (counter % cmd_freq == 0) {
+        double uu[4];
+        stream_uniforms(seed, gid0 + env, epi, 3, (unsigned)cmd_draws++, uu);
+        if (ENV == 1) {
+          target_angle = 2.0 * 3.14159265358979323846 * uu[0];
+          double sn, cs;
+          sincos(target_angle, &sn, &cs);
+          tgx = sx0 + cs * 100.0; tgy = sy0 + sn * 100.0;
+          last_len = sqrt((sx0 - tgx) * (sx0 - tgx) + (sy0 - tgy) * (sy0 - tgy));
+        }
+        target_spd = (float)((double)P.ts_lo + uu[1] * ((double)P.ts_hi - (double)P.ts_lo));
+      }
+      if (ENV == 3) target_angle = atan2(tgy - sy0, tgx - sx0);            // PGE:318-323 (plotting only)
+    }
+    __syncwarp();                                        // the pose above is read before lane 0 overwrites it below
+    qb = qmul(qp, qI);
+    float* snew = s_new + el * kNewObs;
+    const Q4 q1 = qnormalize(qb);
+    const M3 Rq = qmat(q1);
+#pragma unroll
+    for (int t = 0; t < 3; t++) { snew[3 * k + t] = q[t]; snew[12 + 3 * k + t] = qd[t]; snew[kPropDim + 3 * k + t] = act_src[3 * k + t]; }
+    counter += 1;
+    const double dx = tgx - px, dy = tgy - py;
+    const double plen = sqrt(dx * dx + dy * dy);
+    if (k == 0) {
+      V3 wl = tmul(Rq, ww), vl = tmul(Rq, vw);
+      snew[24] = wl.x; snew[25] = wl.y; snew[26] = wl.z; snew[27] = vl.x; snew[28] = vl.y; snew[29] = vl.z;
+      snew[30] = Rq.a20; snew[31] = Rq.a21; snew[32] = Rq.a22;
+      snew[45] = Rq.a00; snew[46] = Rq.a01; snew[47] = Rq.a02; snew[48] = Rq.a10; snew[49] = Rq.a11; snew[50] = Rq.a12;
+      snew[51] = Rq.a20; snew[52] = Rq.a21; snew[53] = Rq.a22;
+      snew[54] = (float)px; snew[55] = (float)py; snew[56] = (float)pz;
+      V3 dd = tmul(Rq, V3{(float)dx, (float)dy, (float)(0.0 - pz)});
+      float n2_ = sqrtf(dd.x * dd.x + dd.y * dd.y);
+      snew[57] = dd.x / n2_; snew[58] = dd.y / n2_; snew[59] = target_spd;
+      snew[60] = (float)sqrt(px * px + py * py + pz * pz);
+    }
+    const float left_z = Rq.a02 * Rq.a10 - Rq.a12 * Rq.a00;
+    const bool fall = left_z > 0.70710678118654752f || left_z < -0.70710678118654752f || Rq.a22 < 0.5f;
+    const bool reach = plen < 0.5, timeup = counter >= P.max_steps;
+    const float ux = (float)(dx / plen), uy = (float)(dy / plen);
+    const float spd = fabsf(vw.x * ux + vw.y * uy);
+    total_spd += (double)spd;
+    if ((double)spd > max_spd) max_spd = (double)spd;
+    const float yaw = atan2f(Rq.a10, Rq.a00);
+    float sy_, cy_;
+    llq_sincosf(yaw, &sy_, &cy_);
+    float rew = expf(-fabsf(spd - target_spd)) * expf((cy_ * ux + sy_ * uy - 1.0f) * 5.0f) / (float)P.max_steps;
+    if (ENV == 3) {                                                    // _compute_avg_spd_reward (PGE:504-539)
+      const float reward_rot = expf((cy_ * ux + sy_ * uy - 1.0f) * 5.0f);
+      const float reward_dist = (float)((plen - last_len) / init_len);
+      last_len = plen;
+      rew = reward_rot / (float)P.max_steps * 0.1f * 2.0f - reward_dist * 0.1f;
+      if (reach) rew += expf(-fabsf((float)(total_spd / (double)counter) - target_spd));
+      stage_corridor_masks(snew, E.boxes + (size_t)env * (6 * kMaxBoxes), E.nbox[env], k, (float)px, (float)py, (float)pz, yaw);
+    }
+    if (bad || !isfinite(rew)) { rew = 0.f; bad = true; }
+    done = fall || timeup || reach || bad;
+    rew_out = rew;
+    V3 fd;
+    {
+      V3 f = mul(qmat(qp), foot_in_base(L, q[0], q[1], q[2]));
+      fd = V3{(float)px + f.x, (float)py + f.y, (float)pz + f.z};
+    }
+    if (wr) {
+      float* sw = E.st;
+#pragma unroll
+      for (int t = 0; t < 3; t++) { sw[(10 + 3 * k + t) * N + env] = q[t]; sw[(22 + 3 * k + t) * N + env] = qd[t]; }
+      E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
+      if (k == 0) {
+        E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
+        sw[env] = qb.x; sw[N + env] = qb.y; sw[2 * N + env] = qb.z; sw[3 * N + env] = qb.w;
+        sw[4 * N + env] = vw.x; sw[5 * N + env] = vw.y; sw[6 * N + env] = vw.z;
+        sw[7 * N + env] = ww.x; sw[8 * N + env] = ww.y; sw[9 * N + env] = ww.z;
+        E.time[env] = time;
+        E.reward_sum[env] += rew;
+        E.episode_steps[env] += 1;
+        E.reward[env] = rew;
+        E.done[env] = done ? 1 : 0;
+        double* Aw = E.aux;
+        Aw[env] = counter; Aw[N + env] = cmd_freq; Aw[2 * N + env] = tgx; Aw[3 * N + env] = tgy; Aw[4 * N + env] = target_spd;
+        Aw[5 * N + env] = target_angle; Aw[6 * N + env] = last_len; Aw[7 * N + env] = total_spd; Aw[8 * N + env] = max_spd;
+        Aw[9 * N + env] = push_count; Aw[10 * N + env] = pf[0]; Aw[11 * N + env] = pf[1]; Aw[12 * N + env] = pf[2];
+        Aw[14 * N + env] = push_draws; Aw[15 * N + env] = cmd_draws;
+      }
+    }
+  }
+  // record mode (llq_set_option "record"): the trajectory columns action 12 | reward | done behind the observation of the slab row;
+  // record == 2: into the slab row before the one that receives the observation (parallel/rollout.py)
+  if (record && obs2 && wr) {
+    float* row = obs2 + (size_t)env * obs2_ld + ObsW<ENV>::value - (record == 2 ? (long long)N * obs2_ld : 0ll);
+#pragma unroll
+    for (int t = 0; t < 3; t++) row[3 * k + t] = act_src[3 * k + t];
+    if (k == 0) { row[12] = rew_out; row[13] = done ? 1.f : 0.f; }
+  }
+  {
+    const unsigned dm = __ballot_sync(FULL, valid && k == 0 && done);       // episodes finished: one atomic per warp
+    if ((threadIdx.x & 31) == 0 && dm) atomicAdd(&E.counters[1], (unsigned long long)__popc(dm));
+  }
+  // ---- observation rows of this warp's 8 envs (history shift + new prop / action / future), coalesced
+  __syncwarp();
+  const int w8 = (threadIdx.x >> 5) * 8;
+  emit_obs_rows<ENV, 8>(E.obs, obs2, obs2_ld, s_new + w8 * kNewObs, s_hist + w8 * kHist, blockIdx.x * EPB + w8, N, 0, 0xFFu, E.boxes);
+}
+
+// ---------------------------------------------------------------------------------------------------------------
 template <int ENV>
 __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) llq_step16_kernel(EnvArrays E, MocapDev mc, StepParams P, const ModelConst* __restrict__ gmodel,
                                                             const SphTable* __restrict__ gsph, const float* __restrict__ actions,
                                                             float* obs2, long long obs2_ld, int* __restrict__ winner,
                                                             unsigned long long seed, long long gid0, int record) {
   constexpr int BLOCK = LLQ16_BLOCK, EPB = BLOCK / 16;        // 2 envs per warp
+  static_assert(EPB % 8 == 0, "the tail runs 8 envs per warp on whole warps");
   __shared__ __align__(16) ModelConst M;
   __shared__ __align__(16) SphTable ST;
   __shared__ __align__(16) float s_new[EPB][kNewObs];
@@ -1021,11 +1312,7 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
   }
   __syncwarp();
 
-  // ================= end of the policy step: observation, reward, termination =================
-  // The tail runs with k = the lane's leg on all four link-index groups (identical values in each); lanes i == 0 write.
-  bool done = false;
-  float rew_out = 0.f;
-  const bool wr = valid && i == 0;
+  // ================= end of the policy step: hand the state over to the tail lanes (4 per env, 8 envs per warp) =================
   {
     int bi = bad ? 1 : 0;
     bi |= __shfl_xor_sync(FULL, bi, 1); bi |= __shfl_xor_sync(FULL, bi, 2); bi |= __shfl_xor_sync(FULL, bi, 4); bi |= __shfl_xor_sync(FULL, bi, 8);
@@ -1035,248 +1322,23 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
     if (l16 < nsph) E.warm[(size_t)l16 * N + env] = warm[0];
     if (16 + l16 < nsph) E.warm[(size_t)(16 + l16) * N + env] = warm[1];
   }
-  if (ENV == 0) {
-    qb = qmul(qp, qI);                                 // back to the pybullet (inertial-frame) convention
-    float* snew = &s_new[el][0];
-    ObsCtx oc = build_obs_new(mc, P, M, k, clip, frame_id, frame_frac, px, py, pz, qb, vw, ww, q, qd, snew);
+  {
+    TailState* T = reinterpret_cast<TailState*>(rowtab);
+    if (l16 == 0) {
+      T->px = px; T->py = py; T->pz = pz; T->time = time; T->frame_frac = frame_frac;
+      T->frame_id = frame_id; T->ob_id = ob_id; T->push_count = push_count; T->push_draws = push_draws;
+      T->pf[0] = pf[0]; T->pf[1] = pf[1]; T->pf[2] = pf[2];
+      T->qp[0] = qp.x; T->qp[1] = qp.y; T->qp[2] = qp.z; T->qp[3] = qp.w;
+      T->vw[0] = vw.x; T->vw[1] = vw.y; T->vw[2] = vw.z; T->ww[0] = ww.x; T->ww[1] = ww.y; T->ww[2] = ww.z;
+    }
+    // ob_hit / touch / tag are per-leg partial results: fold them over the legs here
+    int fl = (bad ? 1 : 0) | (ob_hit ? 2 : 0) | (touch_own ? 4 : 0) | (tag ? 8 : 0);
+    fl |= __shfl_xor_sync(FULL, fl, 1); fl |= __shfl_xor_sync(FULL, fl, 2);
+    if (l16 == 0) T->flags = fl;
+    if (i == 0) {
 #pragma unroll
-    for (int t = 0; t < 3; t++) snew[kPropDim + 3 * k + t] = envtab[44 + 3 * k + t];
-    // reward (PLE:350-426)
-    float djp = 0.f, djv = 0.f;
-#pragma unroll
-    for (int t = 0; t < 3; t++) { float a = q[t] - oc.kq[t], b = qd[t] - oc.kqd[t]; djp = fmaf(a, a, djp); djv = fmaf(b, b, djv); }
-    V3 fd, fk;
-    {
-      M3 Rp = qmat(qp);
-      V3 f = mul(Rp, foot_in_base(L, q[0], q[1], q[2]));
-      fd = V3{(float)px + f.x, (float)py + f.y, (float)pz + f.z};
-      Q4 kqp = qmul(qnormalize(oc.kb.q), qconj(qI));
-      V3 g = mul(qmat(kqp), foot_in_base(L, oc.kq[0], oc.kq[1], oc.kq[2]));
-      // difference of foot positions, formed in double for the base offset
-      fk = V3{(float)(oc.kb.px - px) + g.x - f.x, (float)(oc.kb.py - py) + g.y - f.y, (float)(oc.kb.pz - pz) + g.z - f.z};
+      for (int t = 0; t < 3; t++) { T->q[3 * k + t] = q[t]; T->qd[3 * k + t] = qd[t]; }
     }
-    float dee = dot(fk, fk);
-    djp = gsum4(djp); djv = gsum4(djv); dee = gsum4(dee);
-    float dpx = (float)(px - oc.kb.px), dpy = (float)(py - oc.kb.py), dpz = (float)(pz - oc.kb.pz);
-    float dp = dpx * dpx + dpy * dpy + dpz * dpz;
-    V3 dvl3 = vw - oc.kb.lin, dva3 = ww - oc.kb.ang;
-    Q4 q1 = qnormalize(qb), q2 = qnormalize(oc.kb.q);
-    float angle = norm3(q_rotvec(qnormalize(qmul(q2, qconj(q1)))));
-    float rew = P.w_jp * expf(-1.0f * djp) + P.w_jv * expf(-0.1f * djv) + P.w_ee * expf(-40.0f * dee) +
-                P.w_pose * expf(-20.0f * dp - 10.0f * angle * angle) + P.w_vel * expf(-2.0f * dot(dvl3, dvl3) - 0.2f * dot(dva3, dva3));
-    // termination (PLE:337-348, LR:158-179, ML:168-172)
-    M3 Rq = qmat(q1);
-    float left_z = Rq.a02 * Rq.a10 - Rq.a12 * Rq.a00;
-    bool fall = left_z > 0.70710678118654752f || left_z < -0.70710678118654752f || Rq.a22 < 0.5f;
-    int nf = mc.clip_off[clip + 1] - mc.clip_off[clip];
-    bool ended = frame_id >= nf - P.margin - 1;
-    bool diff = fabsf(angle) > 1.0f || dp > 1.0f;
-    if (bad || !isfinite(rew)) { rew = 0.f; bad = true; }
-    if (P.has_ob) {
-      int oh = ob_hit ? 1 : 0;
-      oh |= __shfl_xor_sync(FULL, oh, 1);
-      oh |= __shfl_xor_sync(FULL, oh, 2);
-      ob_hit = oh != 0;
-      const int o0 = mc.ob_off[clip], n_ob = mc.ob_off[clip + 1] - o0;                 // PLE:262-268 hand-over to the next plate
-      while (ob_id < n_ob - 1 && time > mc.ob_table[(size_t)(o0 + ob_id) * 4] + 0.5) ob_id++;
-    }
-    done = fall || ended || diff || ob_hit || bad;                                     // PLE:347
-    rew_out = rew;
-    if (wr) {
-      float* sw = E.st;
-#pragma unroll
-      for (int t = 0; t < 3; t++) {
-        sw[(10 + 3 * k + t) * N + env] = q[t];
-        sw[(22 + 3 * k + t) * N + env] = qd[t];
-        E.kin[(13 + 3 * k + t) * N + env] = oc.kq[t];
-        E.kin[(25 + 3 * k + t) * N + env] = oc.kqd[t];
-      }
-      E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
-      if (k == 0) {
-        E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
-        sw[env] = qb.x; sw[N + env] = qb.y; sw[2 * N + env] = qb.z; sw[3 * N + env] = qb.w;
-        sw[4 * N + env] = vw.x; sw[5 * N + env] = vw.y; sw[6 * N + env] = vw.z;
-        sw[7 * N + env] = ww.x; sw[8 * N + env] = ww.y; sw[9 * N + env] = ww.z;
-        E.time[env] = time;
-        if (P.has_ob) E.ob_id[env] = ob_id;
-        float rs = E.reward_sum[env] + rew;
-        E.reward_sum[env] = rs;
-        E.episode_steps[env] += 1;
-        E.reward[env] = rew;
-        E.done[env] = done ? 1 : 0;
-        E.kin[env] = (float)oc.kb.px; E.kin[N + env] = (float)oc.kb.py; E.kin[2 * N + env] = (float)oc.kb.pz;
-        E.kin[3 * N + env] = oc.kb.q.x; E.kin[4 * N + env] = oc.kb.q.y; E.kin[5 * N + env] = oc.kb.q.z; E.kin[6 * N + env] = oc.kb.q.w;
-        E.kin[7 * N + env] = oc.kb.lin.x; E.kin[8 * N + env] = oc.kb.lin.y; E.kin[9 * N + env] = oc.kb.lin.z;
-        E.kin[10 * N + env] = oc.kb.ang.x; E.kin[11 * N + env] = oc.kb.ang.y; E.kin[12 * N + env] = oc.kb.ang.z;
-        if (done) {
-          E.done_reward[env] = rs;
-          atomicMax(&winner[clip], env);       // highest finished env index owns the clip's slot this step (PLE:236)
-        }
-      }
-    }
-  } else if (ENV == 2) {
-    // ---------------- SEPMC tail (CTG:378-424, 458-470, 495-596, 640-652)
-    const double* A = E.aux;
-    int counter = (int)A[env];
-    PS.with_flag = (int)A[N + env];
-    const float fix_spd = (float)A[4 * N + env];
-    double total_spd = A[7 * N + env], max_spd = A[8 * N + env];
-    PS.flag_draws = (int)A[15 * N + env];
-    qb = qmul(qp, qI);
-    float* snew = &s_new[el][0];
-    const float* spart = &s_new[el ^ 1][0];
-    sepmc_pair_tail<16>(M, L, k, robot, snew, spart, px, py, pz, qp, qb, vw, ww, q, touch_own, fix_spd, seed, pair_gid, epi, PS);
-#pragma unroll
-    for (int t = 0; t < 3; t++) { snew[3 * k + t] = q[t]; snew[12 + 3 * k + t] = qd[t]; snew[kPropDim + 3 * k + t] = envtab[44 + 3 * k + t]; }
-    const float spd = sqrtf(vw.x * vw.x + vw.y * vw.y);              // stat_spd (CTG:368-373)
-    total_spd += (double)spd;
-    if ((double)spd > max_spd) max_spd = (double)spd;
-    counter += 1;
-    const M3 Rq = qmat(qnormalize(qb));
-    const float left_z = Rq.a02 * Rq.a10 - Rq.a12 * Rq.a00;
-    int fall = (left_z > 0.70710678118654752f || left_z < -0.70710678118654752f || Rq.a22 < 0.5f) ? 1 : 0;
-    const int fall_other = __shfl_xor_sync(FULL, fall, 16);
-    if (robot == 1) fall = fall_other;                                  // only robot 0's fall ends the episode (CTG:462)
-    bad = bad || __shfl_xor_sync(FULL, bad ? 1 : 0, 16) != 0;
-    done = fall != 0 || counter >= P.max_steps || tag || bad;
-    // rewards (CTG:640-652, 412-419): +-1 on a flag switch, +-1 on a tag; with_flag after the switch
-    const int wf0 = robot == 0 ? PS.with_flag : 1 - PS.with_flag;       // does robot 0 hold the flag
-    float rew = (float)PS.sw * ((wf0 != 0) == (robot == 0) ? 1.f : -1.f);
-    if (done && tag) rew += (wf0 != 0) == (robot == 0) ? 1.f : -1.f;
-    if (bad) rew = 0.f;
-    rew_out = rew;
-    V3 fd;
-    {
-      V3 f = mul(qmat(qp), foot_in_base(L, q[0], q[1], q[2]));
-      fd = V3{(float)px + f.x, (float)py + f.y, (float)pz + f.z};
-    }
-    if (wr) {
-      float* sw = E.st;
-#pragma unroll
-      for (int t = 0; t < 3; t++) { sw[(10 + 3 * k + t) * N + env] = q[t]; sw[(22 + 3 * k + t) * N + env] = qd[t]; }
-      E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
-      if (k == 0) {
-        E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
-        sw[env] = qb.x; sw[N + env] = qb.y; sw[2 * N + env] = qb.z; sw[3 * N + env] = qb.w;
-        sw[4 * N + env] = vw.x; sw[5 * N + env] = vw.y; sw[6 * N + env] = vw.z;
-        sw[7 * N + env] = ww.x; sw[8 * N + env] = ww.y; sw[9 * N + env] = ww.z;
-        E.time[env] = time;
-        E.reward_sum[env] += rew;
-        E.episode_steps[env] += 1;
-        E.reward[env] = rew;
-        E.done[env] = done ? 1 : 0;
-        double* Aw = E.aux;
-        Aw[env] = counter; Aw[N + env] = PS.with_flag; Aw[2 * N + env] = PS.flag_x; Aw[3 * N + env] = PS.flag_y; Aw[5 * N + env] = PS.visible;
-        Aw[6 * N + env] = PS.sw; Aw[7 * N + env] = total_spd; Aw[8 * N + env] = max_spd; Aw[9 * N + env] = push_count;
-        Aw[10 * N + env] = pf[0]; Aw[11 * N + env] = pf[1]; Aw[12 * N + env] = pf[2]; Aw[14 * N + env] = push_draws; Aw[15 * N + env] = PS.flag_draws;
-        Aw[17 * N + env] = touch_own ? 1.0 : 0.0;
-      }
-    }
-  } else {
-    // ---------------- EPMC tail (PGE:302-321, 334-358, 360-372, 479-539)
-    const double* A = E.aux;
-    int counter = (int)A[env], cmd_draws = (int)A[15 * N + env];
-    const int cmd_freq = (int)A[N + env];
-    double tgx = A[2 * N + env], tgy = A[3 * N + env], target_angle = A[5 * N + env], last_len = A[6 * N + env];
-    double total_spd = A[7 * N + env], max_spd = A[8 * N + env];
-    float target_spd = (float)A[4 * N + env];
-    const double init_len = ENV == 3 ? A[17 * N + env] : 1.0;
-    {
-      // the command of this step was drawn from the pose at the START of the step (PGE:302-317): recover it from the stored state
-      const double sx0 = E.pos[env], sy0 = E.pos[N + env];
-      if (counter % cmd_freq == 0) {
-        double uu[4];
-        stream_uniforms(seed, gid0 + env, epi, 3, (unsigned)cmd_draws++, uu);
-        if (ENV == 1) {
-          target_angle = 2.0 * 3.14159265358979323846 * uu[0];
-          double sn, cs;
-          sincos(target_angle, &sn, &cs);
-          tgx = sx0 + cs * 100.0; tgy = sy0 + sn * 100.0;
-          last_len = sqrt((sx0 - tgx) * (sx0 - tgx) + (sy0 - tgy) * (sy0 - tgy));
-        }
-        target_spd = (float)((double)P.ts_lo + uu[1] * ((double)P.ts_hi - (double)P.ts_lo));
-      }
-      if (ENV == 3) target_angle = atan2(tgy - sy0, tgx - sx0);            // PGE:318-323 (plotting only)
-    }
-    __syncwarp();                                        // the pose above is read before lane 0 overwrites it below
-    qb = qmul(qp, qI);
-    float* snew = &s_new[el][0];
-    const Q4 q1 = qnormalize(qb);
-    const M3 Rq = qmat(q1);
-#pragma unroll
-    for (int t = 0; t < 3; t++) { snew[3 * k + t] = q[t]; snew[12 + 3 * k + t] = qd[t]; snew[kPropDim + 3 * k + t] = envtab[44 + 3 * k + t]; }
-    counter += 1;
-    const double dx = tgx - px, dy = tgy - py;
-    const double plen = sqrt(dx * dx + dy * dy);
-    if (k == 0) {
-      V3 wl = tmul(Rq, ww), vl = tmul(Rq, vw);
-      snew[24] = wl.x; snew[25] = wl.y; snew[26] = wl.z; snew[27] = vl.x; snew[28] = vl.y; snew[29] = vl.z;
-      snew[30] = Rq.a20; snew[31] = Rq.a21; snew[32] = Rq.a22;
-      snew[45] = Rq.a00; snew[46] = Rq.a01; snew[47] = Rq.a02; snew[48] = Rq.a10; snew[49] = Rq.a11; snew[50] = Rq.a12;
-      snew[51] = Rq.a20; snew[52] = Rq.a21; snew[53] = Rq.a22;
-      snew[54] = (float)px; snew[55] = (float)py; snew[56] = (float)pz;
-      V3 dd = tmul(Rq, V3{(float)dx, (float)dy, (float)(0.0 - pz)});
-      float n2_ = sqrtf(dd.x * dd.x + dd.y * dd.y);
-      snew[57] = dd.x / n2_; snew[58] = dd.y / n2_; snew[59] = target_spd;
-      snew[60] = (float)sqrt(px * px + py * py + pz * pz);
-    }
-    const float left_z = Rq.a02 * Rq.a10 - Rq.a12 * Rq.a00;
-    const bool fall = left_z > 0.70710678118654752f || left_z < -0.70710678118654752f || Rq.a22 < 0.5f;
-    const bool reach = plen < 0.5, timeup = counter >= P.max_steps;
-    const float ux = (float)(dx / plen), uy = (float)(dy / plen);
-    const float spd = fabsf(vw.x * ux + vw.y * uy);
-    total_spd += (double)spd;
-    if ((double)spd > max_spd) max_spd = (double)spd;
-    const float yaw = atan2f(Rq.a10, Rq.a00);
-    float sy_, cy_;
-    llq_sincosf(yaw, &sy_, &cy_);
-    float rew = expf(-fabsf(spd - target_spd)) * expf((cy_ * ux + sy_ * uy - 1.0f) * 5.0f) / (float)P.max_steps;
-    if (ENV == 3) {                                                    // _compute_avg_spd_reward (PGE:504-539)
-      const float reward_rot = expf((cy_ * ux + sy_ * uy - 1.0f) * 5.0f);
-      const float reward_dist = (float)((plen - last_len) / init_len);
-      last_len = plen;
-      rew = reward_rot / (float)P.max_steps * 0.1f * 2.0f - reward_dist * 0.1f;
-      if (reach) rew += expf(-fabsf((float)(total_spd / (double)counter) - target_spd));
-      stage_corridor_masks(snew, E.boxes + (size_t)env * (6 * kMaxBoxes), E.nbox[env], k, (float)px, (float)py, (float)pz, yaw);
-    }
-    if (bad || !isfinite(rew)) { rew = 0.f; bad = true; }
-    done = fall || timeup || reach || bad;
-    rew_out = rew;
-    V3 fd;
-    {
-      V3 f = mul(qmat(qp), foot_in_base(L, q[0], q[1], q[2]));
-      fd = V3{(float)px + f.x, (float)py + f.y, (float)pz + f.z};
-    }
-    if (wr) {
-      float* sw = E.st;
-#pragma unroll
-      for (int t = 0; t < 3; t++) { sw[(10 + 3 * k + t) * N + env] = q[t]; sw[(22 + 3 * k + t) * N + env] = qd[t]; }
-      E.foot_pos[(3 * k) * N + env] = fd.x; E.foot_pos[(3 * k + 1) * N + env] = fd.y; E.foot_pos[(3 * k + 2) * N + env] = fd.z;
-      if (k == 0) {
-        E.pos[env] = px; E.pos[N + env] = py; E.pos[2 * N + env] = pz;
-        sw[env] = qb.x; sw[N + env] = qb.y; sw[2 * N + env] = qb.z; sw[3 * N + env] = qb.w;
-        sw[4 * N + env] = vw.x; sw[5 * N + env] = vw.y; sw[6 * N + env] = vw.z;
-        sw[7 * N + env] = ww.x; sw[8 * N + env] = ww.y; sw[9 * N + env] = ww.z;
-        E.time[env] = time;
-        E.reward_sum[env] += rew;
-        E.episode_steps[env] += 1;
-        E.reward[env] = rew;
-        E.done[env] = done ? 1 : 0;
-        double* Aw = E.aux;
-        Aw[env] = counter; Aw[N + env] = cmd_freq; Aw[2 * N + env] = tgx; Aw[3 * N + env] = tgy; Aw[4 * N + env] = target_spd;
-        Aw[5 * N + env] = target_angle; Aw[6 * N + env] = last_len; Aw[7 * N + env] = total_spd; Aw[8 * N + env] = max_spd;
-        Aw[9 * N + env] = push_count; Aw[10 * N + env] = pf[0]; Aw[11 * N + env] = pf[1]; Aw[12 * N + env] = pf[2];
-        Aw[14 * N + env] = push_draws; Aw[15 * N + env] = cmd_draws;
-      }
-    }
-  }
-  // record mode (llq_set_option "record"): the trajectory columns action 12 | reward | done behind the observation of the slab row;
-  // record == 2: into the slab row before the one that receives the observation (parallel/rollout.py)
-  if (record && obs2 && wr) {
-    float* row = obs2 + (size_t)env * obs2_ld + ObsW<ENV>::value - (record == 2 ? (long long)N * obs2_ld : 0ll);
-#pragma unroll
-    for (int t = 0; t < 3; t++) row[3 * k + t] = envtab[44 + 3 * k + t];
-    if (k == 0) { row[12] = rew_out; row[13] = done ? 1.f : 0.f; }
   }
   // counters: one atomic per warp
   {
@@ -1284,18 +1346,22 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
     if (!valid) { cr = 0; lr = 0; ov = 0; }
 #pragma unroll
     for (int o = 16; o > 0; o >>= 1) { cr += __shfl_xor_sync(FULL, cr, o); lr += __shfl_xor_sync(FULL, lr, o); ov += __shfl_xor_sync(FULL, ov, o); }
-    unsigned dm = __ballot_sync(FULL, valid && l16 == 0 && done);
     if ((threadIdx.x & 31) == 0) {
       if (cr) atomicAdd(&E.counters[2], (unsigned long long)cr);
       if (lr) atomicAdd(&E.counters[3], (unsigned long long)lr);
       if (ov) atomicAdd(&E.counters[5], (unsigned long long)ov);
-      if (dm) atomicAdd(&E.counters[1], (unsigned long long)__popc(dm));
     }
   }
-  // ---- observation rows of this warp (history shift + new prop / action / future), coalesced
-  __pipeline_wait_prior(0);
-  __syncwarp();
-  emit_obs_rows<ENV, 2>(E.obs, obs2, obs2_ld, &s_new[(tid >> 5) << 1][0], &s_hist[(tid >> 5) << 1][0], warp_env0, N, 0, 0x3u, E.boxes);
+  __pipeline_wait_prior(0);                                // this thread's share of the history prefetch has landed
+  __syncthreads();
+  if (tid >= 4 * EPB) return;
+  {
+    const int tel = tid >> 2, tk = tid & 3;
+    const int tenv_raw = blockIdx.x * EPB + tel;
+    const float* tbase = s_env_dyn + tel * kEnvFloats;
+    step_tail<ENV, EPB>(E, mc, P, M, &s_new[0][0], &s_hist[0][0], *reinterpret_cast<const TailState*>(tbase + (rowtab - linktab)),
+                        tbase + (envtab - linktab) + 44, obs2, obs2_ld, winner, seed, gid0, record, tel, tk, tenv_raw < N ? tenv_raw : N - 1, tenv_raw < N);
+  }
 }
 
 }  // namespace llq
