@@ -150,6 +150,10 @@ typedef struct llq_config {
   int32_t knee_contacts;
   int32_t reserved1;
   double link_friction;       /* lateral friction of links without a changeDynamics() call: Bullet's default 0.5 */
+  double auxiliary_radius;    /* EPMC elements 1-3: radius of the two auxiliary cylinders the reference lays along the front / back top
+                                 edges of every hurdle and cube and along the bottom edges of every bar (BSE:43-104, 360-362, 418-420,
+                                 451-453; env_randomize_config['auxiliary_radius'], shipped 0.02).  They collide with the robot and are
+                                 invisible to rays.  0 = none. */
 } llq_config;
 
 typedef struct llq_engine* llq_handle;

@@ -52,7 +52,7 @@ class LlqConfig(C.Structure):
         ("push_v_lo", C.c_double), ("push_v_hi", C.c_double), ("target_spd_lo", C.c_double), ("target_spd_hi", C.c_double),
         ("wall_width_lo", C.c_double), ("wall_width_hi", C.c_double), ("wall_gap_lo", C.c_double), ("wall_gap_hi", C.c_double),
         ("hole_gap_lo", C.c_double), ("hole_gap_hi", C.c_double),
-        ("knee_contacts", C.c_int32), ("reserved1", C.c_int32), ("link_friction", C.c_double),
+        ("knee_contacts", C.c_int32), ("reserved1", C.c_int32), ("link_friction", C.c_double), ("auxiliary_radius", C.c_double),
     ]
 
 

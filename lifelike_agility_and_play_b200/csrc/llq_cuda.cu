@@ -90,7 +90,7 @@ void fill_params(llq_handle h) {
   P.mu_ground = (float)c.ground_friction; P.fr_lo = (float)c.friction_lo; P.fr_hi = (float)c.friction_hi;
   P.ph_lo = (float)c.push_h_lo; P.ph_hi = (float)c.push_h_hi; P.pv_lo = (float)c.push_v_lo; P.pv_hi = (float)c.push_v_hi;
   P.ts_lo = (float)c.target_spd_lo; P.ts_hi = (float)c.target_spd_hi;
-  P.knee = c.knee_contacts; P.mu_wheel = (float)(c.ground_friction * c.link_friction);
+  P.knee = c.knee_contacts; P.mu_wheel = (float)(c.ground_friction * c.link_friction); P.aux_r = (float)c.auxiliary_radius;
   P.element_id = c.element_id; P.ww_lo = (float)c.wall_width_lo; P.ww_hi = (float)c.wall_width_hi; P.wg_lo = (float)c.wall_gap_lo;
   P.wg_hi = (float)c.wall_gap_hi; P.hg_lo = (float)c.hole_gap_lo; P.hg_hi = (float)c.hole_gap_hi;
   if (!h->has_obstacles) { P.has_ob = 0; P.ob_hx = P.ob_hy = P.ob_hz = 0.f; }
@@ -249,7 +249,7 @@ int llq_default_config(llq_config* c) {
   c->target_spd_lo = 0.5; c->target_spd_hi = 3.0;
   c->element_id = 0; c->wall_width_lo = 0.02; c->wall_width_hi = 0.5; c->wall_gap_lo = 1.0; c->wall_gap_hi = 20.0;
   c->hole_gap_lo = 0.25; c->hole_gap_hi = 0.3;
-  c->knee_contacts = 2; c->reserved1 = 0; c->link_friction = 0.5;
+  c->knee_contacts = 2; c->reserved1 = 0; c->link_friction = 0.5; c->auxiliary_radius = 0.0;
   return LLQ_OK;
 }
 

@@ -64,6 +64,7 @@ struct StepParams {
   int element_id; float ww_lo, ww_hi, wg_lo, wg_hi, hg_lo, hg_hi;
   // knee-wheel ground contact (llq_config.knee_contacts / link_friction)
   int knee; float mu_wheel;
+  float aux_r;      // EPMC elements 1-3: radius of the auxiliary edge cylinders (0 = none)
 };
 
 struct EnvArrays {      // SoA device arrays, N envs

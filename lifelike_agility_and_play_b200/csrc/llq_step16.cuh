@@ -1173,8 +1173,20 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
                 const double wz = pz + nx * x + ny * y + nz * z;
                 for (int c = 0; c < n_cand; c++) {
                   double db; V3 nn;
-                  sphere_box(wx, wy, wz, (double)sp.r, s_cand + 6 * c, db, nn);
+                  const float* bx = s_cand + 6 * c;
+                  sphere_box(wx, wy, wz, (double)sp.r, bx, db, nn);
                   if ((float)db < dist) { dist = (float)db; plane = 5; nworld = nn; }
+                  // the element's two auxiliary cylinders (BSE:43-104): along y on the box's x faces, on its top edge (bars: bottom edge);
+                  // the 200 m walls carry none
+                  if (P.aux_r > 0.f && bx[3] < 50.f && fabs(wy - (double)bx[1]) <= (double)bx[4]) {
+                    const double ez = (double)bx[2] + (P.element_id == 2 ? -(double)bx[5] : (double)bx[5]), dz = wz - ez;
+#pragma unroll
+                    for (int side = -1; side <= 1; side += 2) {
+                      const double dx = wx - ((double)bx[0] + (double)side * (double)bx[3]), len = sqrt(dx * dx + dz * dz);
+                      const double dc = len - (double)P.aux_r - (double)sp.r;
+                      if (len > 0.0 && (float)dc < dist) { dist = (float)dc; plane = 5; nworld = V3{(float)(dx / len), 0.f, (float)(dz / len)}; }
+                    }
+                  }
                 }
               }
             }

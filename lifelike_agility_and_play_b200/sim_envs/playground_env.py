@@ -45,6 +45,7 @@ def epmc_engine_config(control_freq=50, kp=50.0, kd=1.0, max_tau=16, max_steps=1
                max_steps=int(max_steps), friction_lo=float(erc['friction_range'][0]), friction_hi=float(erc['friction_range'][1]),
                target_spd_lo=float(erc['target_spd_range'][0]), target_spd_hi=float(erc['target_spd_range'][1]))
     cfg.update(element_id=int(erc['element_id']), wall_width_lo=0.02, wall_width_hi=0.5, wall_gap_lo=1.0, wall_gap_hi=20.0)   # PGE:160-161,199
+    cfg.update(auxiliary_radius=float(erc.get('auxiliary_radius') or 0.0))                  # PGE -> BulletStatics(auxiliary_radius=...), BSE:9-16
     hc = erc.get('hole_config') or {}
     cfg.update(hole_gap_lo=float(hc.get('min_gap_height', 0.25)), hole_gap_hi=float(hc.get('max_gap_height', 0.3)))    # BSE:372-373
     lo, hi = erc.get('cmd_vary_freq_range', [25, 200])                                        # PGE:170

@@ -261,6 +261,7 @@ struct Env {
   int ob_id;      // active hurdle plate (PLE:179,264-265)
   // EPMC elements 1-3: static boxes of the corridor (walls first), centre + half extents; PGE:192-195
   int n_boxes; double boxes[LLQ_MAX_BOXES][6]; double init_pos_diff_len;
+  int n_cyl; double cyl[2 * LLQ_MAX_BOXES][5];   // auxiliary edge cylinders (BSE:43-104): axis point x, y, z | radius | length along y
   // SEPMC (CTG): per-robot copies of the pair's game state
   int with_flag, switch_flag, visible, flag_draws, touch; double flag_x, flag_y, fix_spd;
   double yaw_accum_deg;   // PGE:181-189 mutates the shared init-state dict: every reset's yaw is applied on top of the previous ones
@@ -539,6 +540,15 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
         db = -best - sp.r; nb = V3{ax == 0 ? sg : 0.0, ax == 1 ? sg : 0.0, ax == 2 ? sg : 0.0};
       }
       if (db < dist) { dist = db; nrm = nb; }
+    }
+    // auxiliary edge cylinders (static bodies of their own in the reference; here they compete for the sphere's one manifold point)
+    for (int c = 0; c < (statics ? e.n_cyl : 0); c++) {
+      const double* cy = e.cyl[c];
+      if (std::fabs(cw.y - cy[1]) > 0.5 * cy[4]) continue;          // beside the cylinder's length (its flat ends lie in the walls)
+      const double dx = cw.x - cy[0], dz = cw.z - cy[2], len = std::sqrt(dx * dx + dz * dz);
+      if (!(len > 0)) continue;
+      const double dc = len - cy[3] - sp.r;
+      if (dc < dist) { dist = dc; nrm = V3{dx / len, 0.0, dz / len}; }
     }
     e.margin = std::min(e.margin, std::fabs(dist - cf.contact_breaking));
     if (dist < cf.contact_breaking) {
@@ -972,6 +982,15 @@ void add_box(Env& e, double cx, double cy, double cz, double lx, double ly, doub
   double* b = e.boxes[e.n_boxes++];
   b[0] = cx; b[1] = cy; b[2] = cz; b[3] = lx / 2; b[4] = ly / 2; b[5] = lz / 2;
 }
+// _create_auxiliary_obj (BSE:43-104): one cylinder of radius `ra` along y at each of the box's two x faces, on its top (flag = 1:
+// hurdles BSE:360-362, cubes BSE:451-453) or bottom (flag = -1: bars BSE:418-420) edge
+void add_aux_cylinders(Env& e, const double* b, double ra, double flag) {
+  for (int side = -1; side <= 1; side += 2) {
+    if (e.n_cyl >= 2 * LLQ_MAX_BOXES) return;
+    double* c = e.cyl[e.n_cyl++];
+    c[0] = b[0] + side * b[3]; c[1] = b[1]; c[2] = b[2] + flag * b[5]; c[3] = ra; c[4] = 2.0 * b[4];
+  }
+}
 void epmc_generate_terrain(const llq_engine& E, Env& e, int64_t gid) {
   const llq_config& cf = E.cfg;
   TerrainRng R{cf, gid, e.episode - 1, 0, {0, 0, 0, 0}};
@@ -1011,6 +1030,9 @@ void epmc_generate_terrain(const llq_engine& E, Env& e, int64_t gid) {
       if (pass == 0) { e.tgt_x = cur + R.uniform(-3.0, 3.0); e.tgt_y = 0.0; }
     }
   }
+  e.n_cyl = 0;
+  if (cf.auxiliary_radius > 0)
+    for (int b = 2; b < e.n_boxes; b++) add_aux_cylinders(e, e.boxes[b], cf.auxiliary_radius, cf.element_id == 2 ? -1.0 : 1.0);
 }
 // perception against the ground slab + the corridor's boxes (PGE:374-447)
 void epmc_drill_terrain(const Env& e, const double* st, float* percep) {
@@ -1122,7 +1144,7 @@ void epmc_reset(llq_engine& E, Env& e, int64_t gid) {   // PGE:196-249
   st[0] = 0.0; st[1] = 0.0; st[2] = 0.5;
   unpack_state(e, st);
   for (int s = 0; s < LLQ_MAX_SPHERES; s++) e.warm[s] = 0;
-  e.tgt_x = 8.0; e.tgt_y = 0.0; e.n_boxes = 0;                                           // BSE:247-248, PGE:219
+  e.tgt_x = 8.0; e.tgt_y = 0.0; e.n_boxes = 0; e.n_cyl = 0;                              // BSE:247-248, PGE:219
   if (cf.element_id != 0) epmc_generate_terrain(E, e, gid);                               // PGE:216-219
   e.last_pos_diff_len = std::sqrt((st[0] - e.tgt_x) * (st[0] - e.tgt_x) + (st[1] - e.tgt_y) * (st[1] - e.tgt_y));
   e.init_pos_diff_len = e.last_pos_diff_len;                                              // PGE:192-195
@@ -1580,7 +1602,7 @@ int llq_default_config(llq_config* c) {
   c->target_spd_lo = 0.5; c->target_spd_hi = 3.0;
   c->element_id = 0; c->wall_width_lo = 0.02; c->wall_width_hi = 0.5; c->wall_gap_lo = 1.0; c->wall_gap_hi = 20.0;
   c->hole_gap_lo = 0.25; c->hole_gap_hi = 0.3;
-  c->knee_contacts = 2; c->reserved1 = 0; c->link_friction = 0.5;
+  c->knee_contacts = 2; c->reserved1 = 0; c->link_friction = 0.5; c->auxiliary_radius = 0.0;
   return LLQ_OK;
 }
 
@@ -1993,6 +2015,15 @@ int llq_oracle_set_boxes(llq_handle h, int32_t env, const double* boxes6, int32_
   Env& e = h->envs[env];
   e.n_boxes = n;
   for (int b = 0; b < n; b++) for (int t = 0; t < 6; t++) e.boxes[b][t] = boxes6[b * 6 + t];
+  return LLQ_OK;
+}
+
+// oracle-only hook: replace the auxiliary cylinders of env `env` (the pybullet shim mirrors the ones the reference creates)
+int llq_oracle_set_cylinders(llq_handle h, int32_t env, const double* cyl5, int32_t n) {
+  if (!h || env < 0 || env >= h->cfg.n_envs || n < 0 || n > 2 * LLQ_MAX_BOXES || (n > 0 && !cyl5)) return fail(LLQ_EINVAL, "bad arguments");
+  Env& e = h->envs[env];
+  e.n_cyl = n;
+  for (int c = 0; c < n; c++) for (int t = 0; t < 5; t++) e.cyl[c][t] = cyl5[c * 5 + t];
   return LLQ_OK;
 }
 

@@ -98,15 +98,20 @@ class FakeBulletClient:
     setPhysicsEngineParameter = setTimeStep = configureDebugVisualizer = resetDebugVisualizerCamera = _noop
     createVisualShape = _noop
 
-    def createCollisionShape(self, shapeType=None, halfExtents=None, **kw):
+    def createCollisionShape(self, shapeType=None, halfExtents=None, radius=None, height=None, **kw):
         if not hasattr(self, "shapes"):
             self.shapes = []
-        self.shapes.append(None if halfExtents is None else np.asarray(halfExtents, dtype=np.float64))
+        if shapeType == self.GEOM_CYLINDER:          # auxiliary edge cylinder (BSE:43-104): always laid along y
+            self.shapes.append(("cyl", float(radius), float(height)))
+        else:
+            self.shapes.append(None if halfExtents is None else np.asarray(halfExtents, dtype=np.float64))
         return len(self.shapes) - 1
 
     def createMultiBody(self, baseMass=0, baseCollisionShapeIndex=-1, baseVisualShapeIndex=-1, basePosition=None, baseOrientation=None, **k):
         b = _Body("static")
-        b.box = self.shapes[baseCollisionShapeIndex] if hasattr(self, "shapes") and baseCollisionShapeIndex >= 0 else None
+        shp = self.shapes[baseCollisionShapeIndex] if hasattr(self, "shapes") and baseCollisionShapeIndex >= 0 else None
+        b.cyl = shp[1:] if isinstance(shp, tuple) else None
+        b.box = None if isinstance(shp, tuple) else shp
         b.ray_target = FakeBulletClient.boxes_block_rays
         if basePosition is not None:
             b.state[0:3] = basePosition
@@ -235,14 +240,18 @@ class FakeBulletClient:
 
     # ---- the physics step
     def _mirror_boxes(self, dyn):
-        """EPMC corridor: hand the live static boxes (walls, hurdles, bars, cubes; not the degenerate target marker, not the
-        auxiliary cylinders) to the oracle, whose foot narrow phase then collides with them."""
+        """EPMC corridor: hand the live static boxes (walls, hurdles, bars, cubes; not the degenerate target marker) and the
+        auxiliary edge cylinders to the oracle, whose narrow phase then collides the robot's spheres with them."""
         bx = [np.r_[o.state[0:3], o.box] for o in self.bodies
               if o.kind == "static" and getattr(o, "box", None) is not None and np.any(o.box > 0)]
         arr = np.ascontiguousarray(np.array(bx, dtype=np.float64).reshape(-1, 6))
         self._lib.llq_oracle_set_boxes.restype = C.c_int
+        cy = [np.r_[o.state[0:3], o.cyl] for o in self.bodies if o.kind == "static" and getattr(o, "cyl", None) is not None]
+        carr = np.ascontiguousarray(np.array(cy, dtype=np.float64).reshape(-1, 5))
+        self._lib.llq_oracle_set_cylinders.restype = C.c_int
         for k in range(len(dyn)):
             assert self._lib.llq_oracle_set_boxes(self._h, k, arr.ctypes.data_as(C.c_void_p), len(bx)) == 0
+            assert self._lib.llq_oracle_set_cylinders(self._h, k, carr.ctypes.data_as(C.c_void_p), len(cy)) == 0
 
     def _narrow_phase(self):
         """Contact points for getContactPoints(), built on the pre-step poses.  PMC: robot detection proxies vs static boxes

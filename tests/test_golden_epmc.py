@@ -122,7 +122,8 @@ def terrain_gold(element):
 def terrain_cfg(g):
     cfg = dict(EPMC_CFG)
     cfg.update(element_id=int(g["element_id"]), max_steps=int(g["max_steps"]), hole_gap_lo=0.25, hole_gap_hi=0.25,
-               wall_width_lo=0.02, wall_width_hi=0.5, wall_gap_lo=1.0, wall_gap_hi=20.0)
+               wall_width_lo=0.02, wall_width_hi=0.5, wall_gap_lo=1.0, wall_gap_hi=20.0,
+               auxiliary_radius=0.02)             # env_randomize_config['auxiliary_radius'] of the generator (example_epmc_train.sh:112)
     return cfg
 
 
