@@ -512,11 +512,11 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
   for (size_t s = 0; s < md.spheres.size(); s++) {
     const SphereM& sp = md.spheres[s];
     V3 cw = k.pl[sp.link] + mul(k.Rl[sp.link], sp.c);
-    double dist = 1e30; V3 nrm = pn[0];
+    double dist = 1e30, second = 1e30; V3 nrm = pn[0];      // second: runner-up among the statics (the sphere keeps ONE manifold point)
     const bool statics = s < 4 || cf.knee_contacts == 2;           // legacy sets: only the feet touch walls and boxes
     for (int pi = 0; pi < (statics ? n_planes : 1); pi++) {
       double dpi = dot(pn[pi], cw) - pd[pi] - sp.r;
-      if (dpi < dist) { dist = dpi; nrm = pn[pi]; }
+      if (dpi < dist) { second = dist; dist = dpi; nrm = pn[pi]; } else second = std::min(second, dpi);
     }
     // EPMC corridor: sphere vs every static box (walls, hurdles, bars, cubes); still one contact per foot, the deepest.
     // The auxiliary edge cylinders (BSE:43-100) and every non-foot link are not collided.
@@ -539,7 +539,7 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
         }
         db = -best - sp.r; nb = V3{ax == 0 ? sg : 0.0, ax == 1 ? sg : 0.0, ax == 2 ? sg : 0.0};
       }
-      if (db < dist) { dist = db; nrm = nb; }
+      if (db < dist) { second = dist; dist = db; nrm = nb; } else second = std::min(second, db);
     }
     // auxiliary edge cylinders (static bodies of their own in the reference; here they compete for the sphere's one manifold point)
     for (int c = 0; c < (statics ? e.n_cyl : 0); c++) {
@@ -548,9 +548,10 @@ bool physics_substep(llq_engine& E, Env& e, const double* tau, int64_t* n_contac
       const double dx = cw.x - cy[0], dz = cw.z - cy[2], len = std::sqrt(dx * dx + dz * dz);
       if (!(len > 0)) continue;
       const double dc = len - cy[3] - sp.r;
-      if (dc < dist) { dist = dc; nrm = V3{dx / len, 0.0, dz / len}; }
+      if (dc < dist) { second = dist; dist = dc; nrm = V3{dx / len, 0.0, dz / len}; } else second = std::min(second, dc);
     }
     e.margin = std::min(e.margin, std::fabs(dist - cf.contact_breaking));
+    if (second < cf.contact_breaking) e.margin = std::min(e.margin, second - dist);   // which static is the deepest: also a branch of the step
     if (dist < cf.contact_breaking) {
       contacts[nc++] = {sp.link, (int)s, cw - sp.r * nrm, nrm, dist, cf.ground_friction * (s < 4 ? e.foot_mu : sp.mu)};
     } else {

@@ -156,7 +156,7 @@ def test_epmc_terrain_policy_step_parity(element, built, blob, oracle_lib):
     gpu, cpu = _terrain_pair(element, n, blob, oracle_lib, 7, max_steps=40, friction_hi=1.0, cmd_freq_lo=3, cmd_freq_hi=9)
     gpu.reset(); cpu.reset()
     rng = np.random.default_rng(3)
-    E, DD, reach = [], [], 0
+    E, DD, M, reach = [], [], [], 0
     for t in range(steps):
         if t % 3 == 1:
             _crowd_terrain(cpu, rng, n)
@@ -169,18 +169,20 @@ def test_epmc_terrain_policy_step_parity(element, built, blob, oracle_lib):
         e = np.maximum.reduce([blockrel(og[:, :135], oc[:, :135]), blockrel(og[:, 135:460], oc[:, 135:460]), blockrel(og[:, 460:588], oc[:, 460:588]),
                                blockrel(og[:, 588:913], oc[:, 588:913]), blockrel(og[:, 913:], oc[:, 913:]),
                                blockrel(gpu.get(capi.F_STATE), cpu.get(capi.F_STATE)), np.abs(rg - rc) / (1 + np.abs(rc))])
-        E.append(e); DD.append(dg != dc); reach += int((rc > 0.2).sum())
+        E.append(e); DD.append(dg != dc); M.append(cpu.get(capi.F_DECISION_MARGIN)); reach += int((rc > 0.2).sum())
         m = dc.astype(np.uint8)
         if m.any():
             cpu.reset(m); gpu.reset(m)
-    e, dd = np.concatenate(E), np.concatenate(DD)
+    e, dd, m = np.concatenate(E), np.concatenate(DD), np.concatenate(M)
     bad = (e >= TOL) | dd
-    print("EPMC element %d teacher-forced: %d env-steps; rel err 50/99/99.9/max = %.1e %.1e %.1e %.1e; %d above 1e-4; %d done mismatches; %d reaches" % (
-        element, e.size, np.percentile(e, 50), np.percentile(e, 99), np.percentile(e, 99.9), e.max(), int((e >= TOL).sum()), int(dd.sum()), reach))
-    # robots are repeatedly dropped INTO obstacles (teleports of _crowd_terrain): with every collision sphere live, trunk / hips / shanks
-    # start several centimetres inside boxes, Bullet's penetration recovery throws them out at metres per second and the unconverged
-    # Gauss-Seidel sweep amplifies fp32 rounding (measured 0.4-0.55 % above 1e-4; 0.3 % with the foot-only contact set of round 1)
-    assert reach > 0 and bad.mean() <= 6.5e-3
+    print("EPMC element %d teacher-forced: %d env-steps; rel err 50/99/99.9/max = %.1e %.1e %.1e %.1e; %d above 1e-4, %d of them with a decision margin "
+          "above 5e-4; %d done mismatches; %d reaches" % (element, e.size, np.percentile(e, 50), np.percentile(e, 99), np.percentile(e, 99.9), e.max(),
+                                                       int((e >= TOL).sum()), int((bad & (m > 5e-4)).sum()), int(dd.sum()), reach))
+    # robots are repeatedly dropped INTO obstacles (_crowd_terrain): with every collision sphere and the auxiliary edge cylinders live, trunk /
+    # hips / shanks start centimetres inside boxes, Bullet's penetration recovery throws them out at metres per second, spheres sit between a
+    # box face and its edge cylinder (which of the two owns the manifold point is a branch of the step) and the unconverged Gauss-Seidel sweep
+    # amplifies fp32 rounding.  Bars: 1.5 % of all env-steps may deviate, 0.4 % of those away from every branch.
+    assert reach > 0 and bad.mean() <= 1.5e-2 and (bad & (m > 5e-4)).mean() <= 4e-3 and np.percentile(e, 99) < 3e-4
     gpu.close(); cpu.close()
 
 
