@@ -62,7 +62,6 @@ def parse():
     ap.add_argument("--envs", type=int, default=0, help="robots per GPU (default: 4096 PMC, 8192 EPMC / SEPMC)")
     ap.add_argument("--no-gather", action="store_true", help="N>1: skip the trajectory hand-over to rank 0")
     ap.add_argument("--no-sub", action="store_true", help="skip the epmc_8192 / sepmc_4096pairs sub-results")
-    ap.add_argument("--block", type=int, default=0, help="CUDA block size override (32/64/128)")
     ap.add_argument("--cpu-envs", type=int, default=4096, help="CPU arm: environments per step (default: the same 4096-env batch as the GPU arm)")
     ap.add_argument("--element", type=int, default=3, help="EPMC element_id (0 flat joystick arena, 1 hurdles, 2 bars, 3 cubes)")
     ap.add_argument("--env", default="pmc", choices=["pmc", "epmc", "sepmc"],
@@ -314,8 +313,6 @@ def measure(args, env, n, ctx, headline):
     ow = OBS_W[env]
     traj_w = ow + 16                        # obs | action 12 | reward | done | neglogp | value
     eng = make_engine(None, n, env, device=local_rank, seed=1234, auto_reset=1, global_env_offset=rank * n)
-    if args.block:
-        eng.set_option("block", args.block)
     eng.set_option("record", 1)             # the step kernel writes action | reward | done into the slab row itself
     eng.reset()
     POOL = 16

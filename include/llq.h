@@ -229,7 +229,9 @@ int llq_get_counters(llq_handle h, int64_t* out, int32_t n);
 
 /* Per-kernel device timing of the most recent llq_step*: out[0] = fused step kernel ms, out[1] = reset/table kernel ms
  * (CUDA events on the launching stream; valid after llq_sync).  Enabled by llq_set_option(h, "profile", 1).
- * Other options: "block" = CUDA block size (32, 64, 128).  The CPU oracle returns LLQ_EUNSUPPORTED. */
+ * Other options: "record" = 1: the step kernel also writes action 12 | reward | done behind the observation of the slab row it is handed
+ * (obs_ld >= observation width + 14; SURVEY 8e: no column copies after the step), 2: into the slab row before it (the [T+1, N, ld]
+ * layout of parallel/rollout.py).  The CPU oracle returns LLQ_EUNSUPPORTED. */
 int llq_set_option(llq_handle h, const char* name, double value);
 int llq_get_timing(llq_handle h, double* out, int32_t n);
 

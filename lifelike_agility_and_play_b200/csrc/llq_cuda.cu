@@ -36,7 +36,6 @@ constexpr int kPadFrames = 128;  // replicated tail frames so that a stale curso
 
 struct llq_engine {
   llq_config cfg;
-  int block = 128;   // 4 warps per CTA kept on the same code stretch by per-sub-step barriers (instruction-cache sharing)
   cudaStream_t stream = nullptr;
   bool has_model = false, has_mocap = false, was_reset = false;
   // device
@@ -60,9 +59,8 @@ struct llq_engine {
   llq::StepParams P{};
   bool profile = false; cudaEvent_t ev[3] = {nullptr, nullptr, nullptr}; bool ev_valid = false;
   llq::SphTable* d_sph = nullptr; llq::SphTable h_sph{};   // collision spheres of the robot (llq_step16.cuh)
-  int lanes = 16;              // "lanes" option: 16 = llq_step16_kernel (default), 4 = the round-1 kernel (one lane per leg; A/B timing only)
   int record = 0;              // "record" option: the step kernel also writes action | reward | done behind the observation of a slab row
-  unsigned smem_attr_set = 0;  // bit (ENV * 3 + block index): cudaFuncAttributeMaxDynamicSharedMemorySize raised on this handle's device
+  unsigned smem_attr_set = 0;  // bit 16 + ENV: cudaFuncAttributeMaxDynamicSharedMemorySize raised for that kernel instance on this handle's device
 };
 
 namespace {
@@ -117,34 +115,11 @@ int ensure_scratch(llq_handle h, size_t bytes) {
 llq::MocapDev mocap_dev(llq_handle h) { return llq::MocapDev{h->d_frames, h->d_clip_off, h->n_clips, h->d_ob_table, h->d_ob_off}; }
 
 template <int BLOCK, int ENV>
-int launch_step_t(llq_handle h, const llq::EnvArrays& E, const float* d_actions, float* obs2, long long ld, cudaStream_t s) {
-  int threads = 4 * h->cfg.n_envs;
-  int grid = (threads + BLOCK - 1) / BLOCK;
-  const size_t smem = sizeof(float) * llq::kRowFloats * BLOCK;
-  // the opt-in above 48 kB is a per-device function attribute: raise it once per handle (= per device), not once per process
-  const unsigned bit = 1u << (ENV * 3 + (BLOCK == 32 ? 0 : (BLOCK == 64 ? 1 : 2)));
-  if (!(h->smem_attr_set & bit)) {
-    CK(cudaFuncSetAttribute(llq::pmc_step_kernel<BLOCK, ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    h->smem_attr_set |= bit;
-  }
-  llq::pmc_step_kernel<BLOCK, ENV><<<grid, BLOCK, smem, s>>>(E, mocap_dev(h), h->P, h->d_model, d_actions, obs2, ld, h->d_winner[h->parity],
-                                                             (unsigned long long)h->cfg.seed, (long long)h->cfg.global_env_offset, h->record);
-  return LLQ_OK;
-}
-template <int BLOCK, int ENV>
 void launch_reset_t(llq_handle h, const llq::EnvArrays& E, const llq::ResetParams& RP, float* obs2, long long ld, cudaStream_t s) {
   int threads = 4 * h->cfg.n_envs;
   int grid = (threads + BLOCK - 1) / BLOCK;
   size_t smem = sizeof(double) * (size_t)(h->n_clips > 0 ? h->n_clips : 1);
   llq::pmc_reset_kernel<BLOCK, ENV><<<grid, BLOCK, smem, s>>>(E, mocap_dev(h), h->P, h->d_model, RP, obs2, ld);
-}
-template <int ENV>
-int launch_step_b(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
-  switch (h->block) {
-    case 32: return launch_step_t<32, ENV>(h, E, a, obs2, ld, s);
-    case 64: return launch_step_t<64, ENV>(h, E, a, obs2, ld, s);
-    default: return launch_step_t<128, ENV>(h, E, a, obs2, ld, s);
-  }
 }
 template <int ENV>
 int launch_step16(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
@@ -163,14 +138,9 @@ int launch_step16(llq_handle h, const llq::EnvArrays& E, const float* a, float* 
 int launch_step(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
   const bool epmc = h->cfg.env_kind == LLQ_ENV_EPMC;
   h->counters[4]++;
-  if (h->lanes == 16) {
-    if (epmc && h->cfg.element_id != 0) return launch_step16<3>(h, E, a, obs2, ld, s);
-    if (h->cfg.env_kind == LLQ_ENV_SEPMC) return launch_step16<2>(h, E, a, obs2, ld, s);
-    return epmc ? launch_step16<1>(h, E, a, obs2, ld, s) : launch_step16<0>(h, E, a, obs2, ld, s);
-  }
-  if (epmc && h->cfg.element_id != 0) return launch_step_b<3>(h, E, a, obs2, ld, s);        // corridor arenas: the box-aware instance
-  if (h->cfg.env_kind == LLQ_ENV_SEPMC) return launch_step_b<2>(h, E, a, obs2, ld, s);
-  return epmc ? launch_step_b<1>(h, E, a, obs2, ld, s) : launch_step_b<0>(h, E, a, obs2, ld, s);
+  if (epmc && h->cfg.element_id != 0) return launch_step16<3>(h, E, a, obs2, ld, s);      // corridor arenas: the box-aware instance
+  if (h->cfg.env_kind == LLQ_ENV_SEPMC) return launch_step16<2>(h, E, a, obs2, ld, s);
+  return epmc ? launch_step16<1>(h, E, a, obs2, ld, s) : launch_step16<0>(h, E, a, obs2, ld, s);
 }
 void launch_reset(llq_handle h, const llq::EnvArrays& E, const llq::ResetParams& RP, float* obs2, long long ld, cudaStream_t s) {
   if (h->cfg.env_kind == LLQ_ENV_EPMC && h->cfg.element_id != 0) launch_reset_t<128, 3>(h, E, RP, obs2, ld, s);
@@ -274,10 +244,6 @@ int llq_create(const llq_config* cfg, llq_handle* out) {
   if (!h) return fail(LLQ_ENOMEM, "out of memory");
   h->cfg = *cfg;
   h->obs_dim = cfg->env_kind == LLQ_ENV_EPMC ? LLQ_OBS_DIM_EPMC : (cfg->env_kind == LLQ_ENV_SEPMC ? LLQ_OBS_DIM_SEPMC : LLQ_OBS_DIM);
-  if (const char* b = std::getenv("LLQ_BLOCK")) {
-    int v = std::atoi(b);
-    if (v == 32 || v == 64 || v == 128) h->block = v;
-  }
   int rc = set_device(h);
   if (rc) { delete h; return rc; }
   const size_t n = (size_t)cfg->n_envs;
@@ -774,18 +740,6 @@ int llq_set_option(llq_handle h, const char* name, double value) {
     const int v = (int)value;
     if (v < 0 || v > 2) return fail(LLQ_EINVAL, "record must be 0 (off), 1 (same slab row as the observation) or 2 (the row before)");
     h->record = v;
-    return LLQ_OK;
-  }
-  if (!std::strcmp(name, "lanes")) {
-    const int v = (int)value;
-    if (v != 4 && v != 16) return fail(LLQ_EINVAL, "lanes must be 16 (default kernel) or 4 (round-1 kernel)");
-    h->lanes = v;
-    return LLQ_OK;
-  }
-  if (!std::strcmp(name, "block")) {
-    int v = (int)value;
-    if (v != 32 && v != 64 && v != 128) return fail(LLQ_EINVAL, "block must be 32, 64 or 128");
-    h->block = v;
     return LLQ_OK;
   }
   return fail(LLQ_EINVAL, std::string("unknown option ") + name);

@@ -28,6 +28,24 @@ for n in (5, 70):
     for t in range(25):
         e.step((0.4 * rng.standard_normal((n, 12))).astype(np.float32))
     e.close()
+    # corridor arena (boxes, auxiliary edge cylinders, candidate staging) and the chase-tag pair game; large actions make robots fall
+    # over, which takes the warp through the two-slot solver (more than 4 contacts / limit rows)
+    erc3 = dict(erc, element_id=3, auxiliary_radius=0.02)
+    e = capi.VecEngine(lib, n, blob, None, seed=2, auto_reset=1, **epmc_engine_config(50.0, 50.0, 0.5, 16, 30, erc3))
+    e.set_init_state(INIT_STATE_RUN_0)
+    e.reset()
+    for t in range(25):
+        e.step((1.0 * rng.standard_normal((n, 12))).astype(np.float32))
+    assert e.counters()[5] == 0
+    e.close()
+    from lifelike_agility_and_play_b200.sim_envs.chase_tag_game_env import sepmc_engine_config
+    n2 = n + (n & 1)
+    e = capi.VecEngine(lib, n2, blob, None, seed=3, auto_reset=1, **sepmc_engine_config(50.0, 50.0, 0.5, 16, 30, {'friction_range': [0.4, 3.0], 'disturb_force_config': erc['disturb_force_config']}))
+    e.set_init_state(INIT_STATE_RUN_0)
+    e.reset()
+    for t in range(25):
+        e.step((1.0 * rng.standard_normal((n2, 12))).astype(np.float32))
+    e.close()
 # policy kernel (3xTF32 MMA layers, value head, sampling) on a ragged row count, rows read in place with a slab stride
 import torch
 from lifelike_agility_and_play_b200.policy import DevicePolicy

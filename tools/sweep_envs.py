@@ -17,9 +17,6 @@ for name, path in libs:
     for n in envs:
         for blk in blocks:
             eng = capi.VecEngine(lib, n, blob, mocap, seed=1234, auto_reset=1, **({'knee_contacts': int(os.environ['KNEE'])} if 'KNEE' in os.environ else {}))
-            if 'LANES' in os.environ:
-                eng.set_option('lanes', int(os.environ['LANES']))
-            eng.set_option("block", blk)
             eng.reset()
             pool = torch.from_numpy(action_pool_np(n, 4, 5678)).to(dev)
             obs = torch.empty((n, 207), device=dev); rew = torch.empty((n,), device=dev); done = torch.empty((n,), device=dev, dtype=torch.uint8)
