@@ -402,7 +402,7 @@ struct TailState {            // per env, written by the env's lane 0 (base part
   float pf[3], qp[4], vw[3], ww[3], q[12], qd[12];
 };
 static_assert(sizeof(TailState) <= sizeof(float) * kRowTab, "the hand-over record lives in the row table");
-template <int ENV, int EPB>
+template <int ENV>
 LLQ_DI void step_tail(const EnvArrays& E, const MocapDev& mc, const StepParams& P, const ModelConst& M, float* s_new, const float* s_hist,
                       const TailState& T, const float* act_src, float* obs2, long long obs2_ld, int* winner, unsigned long long seed, long long gid0,
                       int record, int el, int k, int env, bool valid) {
@@ -675,10 +675,7 @@ LLQ_DI void step_tail(const EnvArrays& E, const MocapDev& mc, const StepParams& 
     const unsigned dm = __ballot_sync(FULL, valid && k == 0 && done);       // episodes finished: one atomic per warp
     if ((threadIdx.x & 31) == 0 && dm) atomicAdd(&E.counters[1], (unsigned long long)__popc(dm));
   }
-  // ---- observation rows of this warp's 8 envs (history shift + new prop / action / future), coalesced
-  __syncwarp();
-  const int w8 = (threadIdx.x >> 5) * 8;
-  emit_obs_rows<ENV, 8>(E.obs, obs2, obs2_ld, s_new + w8 * kNewObs, s_hist + w8 * kHist, blockIdx.x * EPB + w8, N, 0, 0xFFu, E.boxes);
+  // (the observation rows are emitted by ALL warps of the CTA after a barrier: kernel epilogue)
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -1132,7 +1129,17 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
           const V3 cw = V3{(float)px, (float)py, (float)pz} + mul(R, cb);
           near_ = near_ || fmaxf(fabsf(cw.x), fabsf(cw.y)) + sp.r > kWallIn - P.breaking - 0.01f;
         }
-        if (ENV == 3 && statics && have && n_cand > 0) near_ = true;
+        unsigned cmask = 0;                              // ENV 3: candidate boxes this sphere can touch (fp32 screen, 3 cm of slack)
+        if (ENV == 3 && statics && have && n_cand > 0) {
+          const V3 cw = V3{(float)px, (float)py, (float)pz} + mul(R, cb);
+          const float reach = sp.r + P.aux_r + P.breaking + 0.03f;
+          for (int c = 0; c < n_cand; c++) {
+            const float* bx = s_cand + 6 * c;
+            const float ex = fabsf(cw.x - bx[0]) - bx[3], ey = fabsf(cw.y - bx[1]) - bx[4], ez = fabsf(cw.z - bx[2]) - bx[5];
+            if (fmaxf(ex, fmaxf(ey, ez)) < reach) cmask |= 1u << c;
+          }
+          near_ = near_ || cmask != 0;
+        }
         int plane = 0;                                   // 0 ground, 1..4 arena walls (normals -x, +x, -y, +y), 5 a corridor box
         V3 nworld = V3{0.f, 0.f, 1.f};
         if (__any_sync(FULL, near_)) {
@@ -1171,7 +1178,8 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
               } else {
                 // EPMC corridor: sphere vs the candidate boxes, in fp64 like the ground clearance; one contact per sphere, the deepest
                 const double wz = pz + nx * x + ny * y + nz * z;
-                for (int c = 0; c < n_cand; c++) {
+                for (unsigned cm = cmask; cm; cm &= cm - 1) {
+                  const int c = __ffs((int)cm) - 1;
                   double db; V3 nn;
                   const float* bx = s_cand + 6 * c;
                   sphere_box(wx, wy, wz, (double)sp.r, bx, db, nn);
@@ -1366,14 +1374,17 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
   }
   __pipeline_wait_prior(0);                                // this thread's share of the history prefetch has landed
   __syncthreads();
-  if (tid >= 4 * EPB) return;
-  {
+  if (tid < 4 * EPB) {
     const int tel = tid >> 2, tk = tid & 3;
     const int tenv_raw = blockIdx.x * EPB + tel;
     const float* tbase = s_env_dyn + tel * kEnvFloats;
-    step_tail<ENV, EPB>(E, mc, P, M, &s_new[0][0], &s_hist[0][0], *reinterpret_cast<const TailState*>(tbase + (rowtab - linktab)),
+    step_tail<ENV>(E, mc, P, M, &s_new[0][0], &s_hist[0][0], *reinterpret_cast<const TailState*>(tbase + (rowtab - linktab)),
                         tbase + (envtab - linktab) + 44, obs2, obs2_ld, winner, seed, gid0, record, tel, tk, tenv_raw < N ? tenv_raw : N - 1, tenv_raw < N);
   }
+  // ---- observation rows (history shift + new prop / action / future; EPMC / SEPMC: the 778 perception rays are cast while the row is
+  // written): every warp of the CTA emits the rows of its own two envs, coalesced
+  __syncthreads();
+  emit_obs_rows<ENV, 2>(E.obs, obs2, obs2_ld, &s_new[(tid >> 5) << 1][0], &s_hist[(tid >> 5) << 1][0], warp_env0, N, 0, 0x3u, E.boxes);
 }
 
 }  // namespace llq
