@@ -143,23 +143,24 @@ LLQ_DI void sphere_box(double wx, double wy, double wz, double r, const float* b
 struct RowsIn {
   const float* legtab; const float* linktab; float* contab; const float* limtab; float* rowtab; const float* chol;
   int nc, nl, Cmax, Lmax, l16, k;
+  int lim0;      // first lane of the limit rows: 3 Cmax on the common path (rows packed: contacts, then limits), 12 in the two-slot layout
   V3 wbs, vbs;
   float dt, slop, erp, jerp, max_imp;
   int iters;
 };
 // one row: its image under the factorised mass matrix and the scalars of the sweep
 struct RowRegs { float y[6], wj[3], b, rhs, invd, lam, hi, mu; int leg; };
-// slot sl of lane l16: contact 4 sl + l16 / 3 in direction l16 % 3 (lanes 0-11) or limit row 4 sl + l16 - 12; also leaves
-// (y, e = D^-1 w, leg) in the row table for the other rows' Delassus entries (zeros for an absent row)
+// slot sl of lane l16: contact 4 sl + l16 / 3 in direction l16 % 3 (lanes below in.lim0) or limit row 4 sl + l16 - in.lim0; also
+// leaves (y, e = D^-1 w, leg) in the row table for the other rows' Delassus entries (zeros for an absent row)
 LLQ_DI void row_image(const RowsIn& in, int sl, int l16, RowRegs& r) {
-  const bool is_con = l16 < 12;
+  const bool is_con = l16 < in.lim0;
   const int d = l16 % 3, cq = l16 / 3;
   float e[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int t = 0; t < 6; t++) r.y[t] = 0.f;
   r.wj[0] = r.wj[1] = r.wj[2] = 0.f;
   r.b = 0.f; r.rhs = 0.f; r.invd = 0.f; r.lam = 0.f; r.hi = 0.f; r.mu = 0.f; r.leg = -2;
-  const int idx = 4 * sl + (is_con ? cq : l16 - 12);
+  const int idx = 4 * sl + (is_con ? cq : l16 - in.lim0);
   const bool act = is_con ? idx < in.nc : idx < in.nl;
   if (act) {
     V3 Ga = V3{0.f, 0.f, 0.f}, Gl = V3{0.f, 0.f, 0.f};
@@ -255,7 +256,8 @@ LLQ_DI void add_row_impulse(const RowRegs& r, float (&v18)[18]) {
   }
 }
 
-// ---- common path: at most 4 contacts and 4 limit rows in both envs of the warp.  One row per lane; the row's 16 Delassus
+// ---- common path: 3 Cmax + Lmax <= 16 rows in both envs of the warp (lanes [0, 3 Cmax): the contacts' rows, then the limit rows).
+// One row per lane; the row's 16 Delassus
 // coefficients live in shared memory (atab[col * 16 + lane]: conflict free), so every loop is rolled and indexed by run-time lane ids --
 // the whole solver is ~250 instructions of code, which matters more than the extra LDS per update: the sub-step body has to stay
 // inside the SM's 32 KB instruction cache now that sixteen warps per SM run through it at their own pace.
@@ -268,10 +270,8 @@ LLQ_DI void solve_rows_s(const RowsIn& in, float* atab, float (&Yt)[6], float (&
   float* acol = atab + l16;
   const int ncc = 3 * in.Cmax, ncols = ncc + in.Lmax;
 #pragma unroll 1
-  for (int t = 0; t < ncols; t++) {          // columns of the active contacts, then of the active limit rows (warp-uniform bounds)
-    const int col = t < ncc ? t : 12 + t - ncc;
+  for (int col = 0; col < ncols; col++)      // columns of the active contacts, then of the active limit rows (warp-uniform bounds)
     acol[col * 16] = delassus_entry(r, in.rowtab + col * kRowW);
-  }
   // warm start of the normal rows
 #pragma unroll 1
   for (int c = 0; c < in.Cmax; c++) r.b = fmaf(acol[48 * c], __shfl_sync(FULL, r.lam, 3 * c, 16), r.b);
@@ -281,7 +281,7 @@ LLQ_DI void solve_rows_s(const RowsIn& in, float* atab, float (&Yt)[6], float (&
   for (int it = 0; it < in.iters; it++) {
 #pragma unroll 1
     for (int t = 0; t < nrow; t++) {          // joint-limit rows in joint order, then the normal rows in contact order
-      const int ln = t < in.Lmax ? 12 + t : 3 * (t - in.Lmax);
+      const int ln = t < in.Lmax ? ncc + t : 3 * (t - in.Lmax);
       const float dlc = fmaf(-r.b, r.invd, r.rhs);
       const float sum = r.lam + dlc;
       const float cl = fminf(fmaxf(sum, 0.f), r.hi);                  // Bullet: clamp the accumulated impulse to [0, hi]
@@ -306,7 +306,7 @@ LLQ_DI void solve_rows_s(const RowsIn& in, float* atab, float (&Yt)[6], float (&
     }
   }
   // the normal impulses go back to the contact records (warm start of the next sub-step)
-  if (l16 < 12 && l16 % 3 == 0 && l16 / 3 < in.nc) in.contab[(l16 / 3) * kConW + 17] = r.lam;
+  if (l16 < ncc && l16 % 3 == 0 && l16 / 3 < in.nc) in.contab[(l16 / 3) * kConW + 17] = r.lam;
   float v18[18];
 #pragma unroll
   for (int t = 0; t < 18; t++) v18[t] = 0.f;
@@ -314,7 +314,7 @@ LLQ_DI void solve_rows_s(const RowsIn& in, float* atab, float (&Yt)[6], float (&
   impulse_sums(v18, in.k, Yt, om);
 }
 
-// ---- rare path: more than 4 contacts or 4 limit rows in one of the warp's envs.  Two row slots per lane (slot s: contacts
+// ---- rare path: more than 16 rows (3 Cmax + Lmax) in one of the warp's envs.  Two row slots per lane (slot s: contacts
 // 4 s .. 4 s + 3 on lanes 0-11, limit rows 4 s .. 4 s + 3 on lanes 12-15), 2 x 32 Delassus coefficients per lane in local
 // memory, out of line so that the common path keeps its register budget and its code footprint.
 __device__ __noinline__ void solve_rows2(const RowsIn& in, float (&Yt)[6], float (&om)[3]) {
@@ -1279,10 +1279,11 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
       if (Cmax | Lmax) {
         RowsIn in;
         in.legtab = legtab; in.linktab = linktab; in.contab = contab; in.limtab = limtab; in.rowtab = rowtab; in.chol = envtab + 8;
-        in.nc = nc; in.nl = nl; in.Cmax = Cmax; in.Lmax = Lmax; in.l16 = l16; in.k = k;
+        const bool two_slots = 3 * Cmax + Lmax > 16;
+        in.nc = nc; in.nl = nl; in.Cmax = Cmax; in.Lmax = Lmax; in.l16 = l16; in.k = k; in.lim0 = two_slots ? 12 : 3 * Cmax;
         in.wbs = wbs; in.vbs = vbs; in.dt = dt; in.slop = P.slop; in.erp = P.erp; in.jerp = P.jerp; in.max_imp = P.max_imp; in.iters = P.solver_iters;
         float Yt[6], om[3];
-        if (Cmax > 4 || Lmax > 4) solve_rows2(in, Yt, om); else solve_rows_s(in, atab, Yt, om);
+        if (two_slots) solve_rows2(in, Yt, om); else solve_rows_s(in, atab, Yt, om);
         if (l16 == 0) { n_contact_rows += 3u * (unsigned)nc; n_limit_rows += (unsigned)nl; }
         __syncwarp();
 #pragma unroll
