@@ -20,7 +20,11 @@ import json
 import os
 
 if os.environ.get("NCCL_DEBUG", "VERSION").upper() == "VERSION":
-    os.environ["NCCL_DEBUG"] = "WARN"                  # NCCL's version banner goes to stdout: keep that to the one JSON line
+    os.environ["NCCL_DEBUG"] = "WARN"
+# stdout carries exactly ONE line, the JSON result: libraries that write to file descriptor 1 on their own (NCCL prints its version
+# banner there when a communicator is created) are sent to stderr for the whole run, the result goes to the saved descriptor
+_RESULT_OUT = os.fdopen(os.dup(1), "w")
+os.dup2(2, 1)
 os.environ.setdefault("OMP_WAIT_POLICY", "passive")   # CPU arm: idle OpenMP threads must not spin away the container's CPU quota
 import subprocess
 import sys
@@ -281,7 +285,7 @@ def run_reference(args, rank):
         "e2e": {"value": val, "unit": "env-steps/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
 
 
 # ------------------------------------------------------------------------------------------------ GPU arm
@@ -664,7 +668,7 @@ def main():
         cn = args.cpu_envs if env == "pmc" else args.envs
         cval, cdt, cores, cne, rates = time_cpu_arm(cn, 32, 3, env=env)
         line["cpu_baseline"] = cpu_baseline_obj(cval, cores, cne, 32, rates)
-    print(json.dumps(line), flush=True)
+    print(json.dumps(line), file=_RESULT_OUT, flush=True)
     if world > 1:
         dist.destroy_process_group()
 
