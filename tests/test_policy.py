@@ -73,7 +73,17 @@ def test_device_policy_matches_host_forward():
         a_ref, c_ref = host.act(obs[:, :207], return_code=True)
         code = t_code.cpu().numpy(); act = t_act.cpu().numpy()
         same = code == c_ref
-        assert same.mean() > 0.99, same.mean()
+        assert same.mean() >= (0.999 if n >= 1000 else 1.0), same.mean()
+        if not same.all():
+            # every mismatch must be a tie at fp32 resolution: in fp64, the code the kernel picked is as near as the host's
+            # pick to within the rounding of a 256-wide fp32 encoder (|z|^2 cancels; the gap is compared with the distance scale)
+            p, f = host.normalise(obs[:, :207])
+            z, _ = host.encode(p, f)
+            z = z.astype(np.float64)[~same]; cb = host.codebook.astype(np.float64)
+            d = ((z[:, :, None] - cb[None]) ** 2).sum(1)
+            rows = np.arange(z.shape[0])
+            gap = np.abs(d[rows, code[~same]] - d[rows, c_ref[~same]]) / (1.0 + d.min(1))
+            assert gap.max() < 2e-5, (gap.max(), int((~same).sum()))
         err = np.abs(act[same] - a_ref[same]).max() / (1.0 + np.abs(a_ref).max())
         assert err < 1e-4, err
         # rollout entry: value head + sampled actions with their -log p

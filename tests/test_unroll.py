@@ -97,16 +97,18 @@ def test_rollout_worker_records_are_aligned(built):
     torch.cuda.synchronize()
     slab = torch.cat(views, 0).cpu().numpy()                       # [2T, N, 223]
     obs = o0
+    n_close = 0
     for t in range(2 * T):
         assert np.array_equal(slab[t, :, :207], obs), "record %d does not hold the observation the action was computed from" % t
         a = slab[t, :, COL_ACTION:COL_ACTION + 12]
         a_ref, c_ref = host_pol.act(obs, return_code=True)
         nlp_ref = host_pol.neglogp(a, a_ref)                          # the recorded -log p belongs to the recorded (sampled) action
         close = np.abs(slab[t, :, COL_NEGLOGP] - nlp_ref) < 1e-2
-        assert close.mean() > 0.98                                    # a different VQ code only at fp32 distance ties
+        n_close += int(close.sum())                                   # a different VQ code only at fp32 distance ties (test_policy.py)
         assert np.abs(slab[t, :, COL_VALUE] - host_pol.value(obs)).max() < 1e-4 * (1 + np.abs(host_pol.value(obs)).max())
         obs, rew, done = chk.step(a)
         assert np.array_equal(rew, slab[t, :, COL_REWARD]) and np.array_equal(done.astype(np.float32), slab[t, :, COL_DONE])
+    assert n_close >= 0.999 * 2 * T * n, (n_close, 2 * T * n)
     # bootstrap of slab 0 = V(obs_T) = the value recorded with the first step of slab 1; `obs` now holds the observation after the
     # last step = what slab 1's bootstrap was computed from
     assert np.abs(boots[0].cpu().numpy() - slab[T, :, COL_VALUE]).max() < 1e-5
