@@ -779,3 +779,10 @@ int llq_sync(llq_handle h) {
 const char* llq_last_error(void) { return g_err.c_str(); }
 
 }  // extern "C"
+
+#ifdef LLQ16_TIMING
+// development aid (tools/warp_timing.py): per-warp phase clocks of the last step launch
+extern "C" int llq_debug_timing(void* out, int n_warps) {
+  return cudaMemcpyFromSymbol(out, llq::g_t16, (size_t)n_warps * 12 * sizeof(unsigned long long)) == cudaSuccess ? 0 : -1;
+}
+#endif

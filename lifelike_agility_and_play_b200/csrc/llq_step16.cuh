@@ -30,6 +30,9 @@ namespace llq {
 #ifndef LLQ16_BAR
 #define LLQ16_BAR 1     // CTA barrier at the top of every sub-step: not needed for correctness, worth 20 % through the instruction cache
 #endif
+#ifndef LLQ16_PGS_V2
+#define LLQ16_PGS_V2 1   // sweep loops with induction-variable addressing (0: the indexed form, kept for A/B builds)
+#endif
 #ifndef LLQ16_MINB
 #define LLQ16_MINB 4   // resident CTAs per SM the register budget is sized for (4 x 128 threads x 128 registers = the whole file)
 #endif
@@ -140,7 +143,24 @@ LLQ_DI void sphere_box(double wx, double wy, double wz, double r, const float* b
 // (btMultiBodyConstraintSolver::solveSingleIteration order: limits, normals, friction pairs with the implicit cone).
 // NS = row slots per lane: slot s holds contacts 4 s .. 4 s + 3 (lanes 0-11) and limit rows 4 s .. 4 s + 3 (lanes 12-15).
 // Returns Yt = sum lam_r y_r (base part) and om = sum over the rows of this lane's leg of lam_r w_r (joint part).
+// ---- development aid (-DLLQ16_TIMING, tools/warp_timing.py): per-warp clock64 totals of the sub-step phases
+#ifdef LLQ16_TIMING
+__device__ unsigned long long g_t16[16384 * 12];
+#define T16_DECL long long t16_[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, t16_c = clock64(), t16_s = t16_c
+#define T16_MARK(slot) { const long long t16_n = clock64(); t16_[slot] += t16_n - t16_c; t16_c = t16_n; }
+#define T16_ADD(slot, v) t16_[slot] += (v)
+#define T16_IN(slot) { const long long t16_n = clock64(); in.t16[slot] += t16_n - *in.t16c; *in.t16c = t16_n; }
+#else
+#define T16_DECL
+#define T16_MARK(slot)
+#define T16_ADD(slot, v)
+#define T16_IN(slot)
+#endif
+
 struct RowsIn {
+#ifdef LLQ16_TIMING
+  long long* t16; long long* t16c;
+#endif
   const float* legtab; const float* linktab; float* contab; const float* limtab; float* rowtab; const float* chol;
   int nc, nl, Cmax, Lmax, l16, k;
   int lim0;      // first lane of the limit rows: 3 Cmax on the common path (rows packed: contacts, then limits), 12 in the two-slot layout
@@ -267,6 +287,7 @@ LLQ_DI void solve_rows_s(const RowsIn& in, float* atab, float (&Yt)[6], float (&
   RowRegs r;
   row_image(in, 0, l16, r);
   __syncwarp();
+  T16_IN(8);
   float* acol = atab + l16;
   const int ncc = 3 * in.Cmax, ncols = ncc + in.Lmax;
 #pragma unroll 1
@@ -275,7 +296,69 @@ LLQ_DI void solve_rows_s(const RowsIn& in, float* atab, float (&Yt)[6], float (&
   // warm start of the normal rows
 #pragma unroll 1
   for (int c = 0; c < in.Cmax; c++) r.b = fmaf(acol[48 * c], __shfl_sync(FULL, r.lam, 3 * c, 16), r.b);
+  T16_IN(9);
   // projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration order); an absent row has rhs = invd = A = 0 => dl = 0
+#if LLQ16_PGS_V2
+  // one row update: candidate on every lane (only the owner's counts), owner commits, broadcast, one LDS + FMA per lane.  The column
+  // pointer and the owner lane are induction variables (no index arithmetic inside the loops).
+#if LLQ16_PGS_V2 >= 2
+  // shortest dependent chain per row: FFMA (candidate from c = lam + rhs, kept up to date off the chain) -> 2 FMNMX -> FADD -> SHFL -> FFMA
+  float rc = r.lam + r.rhs;
+#define LLQ16_ROW_UPDATE(ln, ap)                                                                      \
+  {                                                                                                   \
+    const float cl = fminf(fmaxf(fmaf(-r.b, r.invd, rc), 0.f), r.hi);                                 \
+    const float dl = cl - r.lam;                                                                      \
+    const bool own = l16 == (ln);                                                                     \
+    r.lam = own ? cl : r.lam;                                                                         \
+    rc = own ? cl + r.rhs : rc;                                                                       \
+    r.b = fmaf(*(ap), __shfl_sync(FULL, dl, (ln), 16), r.b);                                          \
+  }
+#define LLQ16_SOWN fmaf(-r.b, r.invd, rc)
+#define LLQ16_SET_FRIC(snew) { const bool own = (unsigned)(l16 - ln - 1) < 2u; r.lam = own ? (snew) : r.lam; rc = own ? (snew) + r.rhs : rc; }
+#else
+#define LLQ16_ROW_UPDATE(ln, ap)                                                                      \
+  {                                                                                                   \
+    const float dlc = fmaf(-r.b, r.invd, r.rhs);                                                      \
+    const float sum = r.lam + dlc;                                                                    \
+    const float cl = fminf(fmaxf(sum, 0.f), r.hi);       /* Bullet: clamp the accumulated impulse */  \
+    const float dl = cl == sum ? dlc : cl - r.lam;       /* (unclamped: exactly the increment) */     \
+    r.lam = l16 == (ln) ? cl : r.lam;                                                                 \
+    r.b = fmaf(*(ap), __shfl_sync(FULL, dl, (ln), 16), r.b);                                          \
+  }
+#define LLQ16_SOWN (r.lam + fmaf(-r.b, r.invd, r.rhs))
+#define LLQ16_SET_FRIC(snew) r.lam = (unsigned)(l16 - ln - 1) < 2u ? (snew) : r.lam;
+#endif
+  const float* const alim = acol + ncc * 16;
+  const float* const alim_end = alim + in.Lmax * 16;
+  const float* const anrm_end = acol + ncc * 16;
+#pragma unroll 1
+  for (int it = 0; it < in.iters; it++) {
+    int ln = ncc;
+#pragma unroll 1
+    for (const float* ap = alim; ap != alim_end; ap += 16, ln++) LLQ16_ROW_UPDATE(ln, ap)      // joint-limit rows in joint order
+    ln = 0;
+#pragma unroll 1
+    for (const float* ap = acol; ap != anrm_end; ap += 48, ln += 3) LLQ16_ROW_UPDATE(ln, ap)   // normal rows in contact order
+    ln = 0;
+#pragma unroll 1
+    for (const float* ap = acol; ap != anrm_end; ap += 48, ln += 3) {   // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
+      const float sown = LLQ16_SOWN;
+      const float sa = __shfl_sync(FULL, sown, ln + 1, 16), sb = __shfl_sync(FULL, sown, ln + 2, 16);
+      const float limit = r.mu * __shfl_sync(FULL, r.lam, ln, 16);
+      const float r2 = sa * sa + sb * sb;
+      const bool clip = r2 >= limit * limit && r2 > 0.f;
+      const float sc = clip ? limit * rsqrtf(r2) : 1.0f;
+      const float snew = clip ? sown * sc : sown;
+      const float dl = snew - r.lam;
+      LLQ16_SET_FRIC(snew)
+      const float da = __shfl_sync(FULL, dl, ln + 1, 16), db = __shfl_sync(FULL, dl, ln + 2, 16);
+      r.b = fmaf(ap[16], da, fmaf(ap[32], db, r.b));
+    }
+  }
+#undef LLQ16_ROW_UPDATE
+#undef LLQ16_SOWN
+#undef LLQ16_SET_FRIC
+#else
   const int nrow = in.Lmax + in.Cmax;
 #pragma unroll 1
   for (int it = 0; it < in.iters; it++) {
@@ -305,6 +388,8 @@ LLQ_DI void solve_rows_s(const RowsIn& in, float* atab, float (&Yt)[6], float (&
       r.b = fmaf(acol[(ln + 1) * 16], da, fmaf(acol[(ln + 2) * 16], db, r.b));
     }
   }
+#endif
+  T16_IN(10);
   // the normal impulses go back to the contact records (warm start of the next sub-step)
   if (l16 < ncc && l16 % 3 == 0 && l16 / 3 < in.nc) in.contab[(l16 / 3) * kConW + 17] = r.lam;
   float v18[18];
@@ -326,6 +411,7 @@ __device__ __noinline__ void solve_rows2(const RowsIn& in, float (&Yt)[6], float
 #pragma unroll
   for (int sl = 0; sl < NS; sl++) row_image(in, sl, l16, r[sl]);
   __syncwarp();
+  T16_IN(8);
 #pragma unroll
   for (int col = 0; col < 16 * NS; col++) {
     const int cs = col >> 4, cl = col & 15;
@@ -341,6 +427,7 @@ __device__ __noinline__ void solve_rows2(const RowsIn& in, float (&Yt)[6], float
       for (int sl = 0; sl < NS; sl++) r[sl].b = fmaf(A[sl][(c >> 2) * 16 + 3 * (c & 3)], l0, r[sl].b);
     }
   }
+  T16_IN(9);
 #pragma unroll 1
   for (int it = 0; it < in.iters; it++) {
 #pragma unroll
@@ -380,6 +467,7 @@ __device__ __noinline__ void solve_rows2(const RowsIn& in, float (&Yt)[6], float
       }
     }
   }
+  T16_IN(10);
 #pragma unroll
   for (int sl = 0; sl < NS; sl++)
     if (l16 < 12 && l16 % 3 == 0 && 4 * sl + l16 / 3 < in.nc) in.contab[(4 * sl + l16 / 3) * kConW + 17] = r[sl].lam;
@@ -685,11 +773,12 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
                                                             float* obs2, long long obs2_ld, int* __restrict__ winner,
                                                             unsigned long long seed, long long gid0, int record) {
   constexpr int BLOCK = LLQ16_BLOCK, EPB = BLOCK / 16;        // 2 envs per warp
-  static_assert(EPB % 8 == 0, "the tail runs 8 envs per warp on whole warps");
+  constexpr int EPT = (EPB + 7) / 8 * 8;                      // the tail runs 8 envs per warp on whole warps: rows EPB.. are dummies
+  static_assert(BLOCK % 32 == 0, "whole warps");
   __shared__ __align__(16) ModelConst M;
   __shared__ __align__(16) SphTable ST;
-  __shared__ __align__(16) float s_new[EPB][kNewObs];
-  __shared__ __align__(16) float s_hist[EPB][kHist];
+  __shared__ __align__(16) float s_new[EPT][kNewObs];
+  __shared__ __align__(16) float s_hist[EPT][kHist];
   extern __shared__ __align__(16) float s_env_dyn[];   // [EPB][kEnvFloats]: 38.4 kB, beside 10 kB of static shared memory
   const int tid = threadIdx.x;
   const int N = P.n_envs;
@@ -796,12 +885,15 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
   bool bad = false;
   const float mu_foot = ENV != 0 ? mu_env : P.mu;
 
+  T16_DECL;
   for (int sub = 0; sub < P.substeps; sub++) {
+    T16_MARK(5);
 #if LLQ16_BAR >= 1
     __syncthreads();      // not needed for correctness (the tables are per half-warp): keeps the CTA's warps on one stretch of code
 #else
     __syncwarp();         // the tables are per env (= per half-warp): no CTA-wide ordering is needed
 #endif
+    T16_MARK(0);
     const float dt = P.dt;
     // ---------------- push randomiser (PR:56-87): counters in sub-steps, force lasts one sub-step
     bool push_on = false;
@@ -1029,6 +1121,7 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
       lt[28] = c3; lt[29] = s3;                       // for the fp64 clearance of the shank's spheres
     }
     }   // ================ end of the forward dynamics
+    T16_MARK(1);
 #if LLQ16_BAR >= 2
     __syncthreads();
 #else
@@ -1272,16 +1365,21 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
       if (nl > kMaxLim) nl = kMaxLim;
     }
     __syncwarp();
+    T16_MARK(2);
     float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dvl[3] = {0.f, 0.f, 0.f};
     {
       // warp-uniform loop bounds (a redux result lives in a uniform register: the guards below compile to uniform branches)
       const int Cmax = __reduce_max_sync(FULL, nc), Lmax = __reduce_max_sync(FULL, nl);
+      T16_ADD(6, Cmax * 256 + Lmax + (3 * Cmax + Lmax > 16 ? 65536 : 0));
       if (Cmax | Lmax) {
         RowsIn in;
         in.legtab = legtab; in.linktab = linktab; in.contab = contab; in.limtab = limtab; in.rowtab = rowtab; in.chol = envtab + 8;
         const bool two_slots = 3 * Cmax + Lmax > 16;
         in.nc = nc; in.nl = nl; in.Cmax = Cmax; in.Lmax = Lmax; in.l16 = l16; in.k = k; in.lim0 = two_slots ? 12 : 3 * Cmax;
         in.wbs = wbs; in.vbs = vbs; in.dt = dt; in.slop = P.slop; in.erp = P.erp; in.jerp = P.jerp; in.max_imp = P.max_imp; in.iters = P.solver_iters;
+#ifdef LLQ16_TIMING
+        in.t16 = t16_; in.t16c = &t16_c;
+#endif
         float Yt[6], om[3];
         if (two_slots) solve_rows2(in, Yt, om); else solve_rows_s(in, atab, Yt, om);
         if (l16 == 0) { n_contact_rows += 3u * (unsigned)nc; n_limit_rows += (unsigned)nl; }
@@ -1300,6 +1398,7 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
         dvl[2] = t3[2]; dvl[1] = fmaf(-lt[20], dvl[2], t3[1]); dvl[0] = fmaf(-lt[18], dvl[1], fmaf(-lt[19], dvl[2], t3[0]));
       }
     }
+    T16_MARK(3);
     // ---------------- apply the impulses, clamp, integrate (btMultiBody::stepPositionsMultiDof)
     {
       V3 dw = mul(R, V3{dvb[0], dvb[1], dvb[2]}), dv = mul(R, V3{dvb[3], dvb[4], dvb[5]});
@@ -1375,17 +1474,27 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
   }
   __pipeline_wait_prior(0);                                // this thread's share of the history prefetch has landed
   __syncthreads();
-  if (tid < 4 * EPB) {
+  if (tid < 4 * EPT) {
     const int tel = tid >> 2, tk = tid & 3;
-    const int tenv_raw = blockIdx.x * EPB + tel;
-    const float* tbase = s_env_dyn + tel * kEnvFloats;
+    const bool tval = tel < EPB && blockIdx.x * EPB + tel < N;          // surplus lanes shadow the CTA's last env into a dummy staging row
+    const int tsrc = tel < EPB ? tel : EPB - 1;
+    const int tenv_raw = blockIdx.x * EPB + tsrc;
+    const float* tbase = s_env_dyn + tsrc * kEnvFloats;
     step_tail<ENV>(E, mc, P, M, &s_new[0][0], &s_hist[0][0], *reinterpret_cast<const TailState*>(tbase + (rowtab - linktab)),
-                        tbase + (envtab - linktab) + 44, obs2, obs2_ld, winner, seed, gid0, record, tel, tk, tenv_raw < N ? tenv_raw : N - 1, tenv_raw < N);
+                        tbase + (envtab - linktab) + 44, obs2, obs2_ld, winner, seed, gid0, record, tel, tk, tenv_raw < N ? tenv_raw : N - 1, tval);
   }
   // ---- observation rows (history shift + new prop / action / future; EPMC / SEPMC: the 778 perception rays are cast while the row is
   // written): every warp of the CTA emits the rows of its own two envs, coalesced
   __syncthreads();
   emit_obs_rows<ENV, 2>(E.obs, obs2, obs2_ld, &s_new[(tid >> 5) << 1][0], &s_hist[(tid >> 5) << 1][0], warp_env0, N, 0, 0x3u, E.boxes);
+#ifdef LLQ16_TIMING
+  T16_MARK(4);
+  t16_[7] = clock64() - t16_s;
+  if ((tid & 31) == 0) {
+    const int gw = blockIdx.x * (BLOCK / 32) + (tid >> 5);
+    if (gw < 16384) for (int t = 0; t < 12; t++) g_t16[gw * 12 + t] = (unsigned long long)t16_[t];
+  }
+#endif
 }
 
 }  // namespace llq
