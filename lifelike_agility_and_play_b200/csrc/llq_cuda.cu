@@ -125,7 +125,7 @@ template <int ENV>
 int launch_step16(llq_handle h, const llq::EnvArrays& E, const float* a, float* obs2, long long ld, cudaStream_t s) {
   constexpr int EPB = LLQ16_BLOCK / 16;           // envs per CTA (16 lanes each)
   const int grid = (h->cfg.n_envs + EPB - 1) / EPB;
-  const size_t smem = sizeof(float) * EPB * llq::kEnvFloats;
+  const size_t smem = sizeof(float) * (EPB * llq::kEnvFloats + (LLQ16_BLOCK / 32) * llq::kATabWarp);
   const unsigned bit = 1u << (16 + ENV);          // static + dynamic shared memory exceeds 48 kB: per-device opt-in, once per handle
   if (!(h->smem_attr_set & bit)) {
     CK(cudaFuncSetAttribute(llq::llq_step16_kernel<ENV>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

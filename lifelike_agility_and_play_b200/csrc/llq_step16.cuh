@@ -28,7 +28,7 @@ namespace llq {
                           // 128 0.334, 256 0.302, 512 0.303 -- the bigger the CTA, the more warps march through the 86 kB sub-step body together
 #endif
 #ifndef LLQ16_BAR
-#define LLQ16_BAR 1     // CTA barrier at the top of every sub-step: not needed for correctness, worth 20 % through the instruction cache
+#define LLQ16_BAR 1     // (>= 2: one more CTA barrier after the dynamics phase; the two around the solver are always there)
 #endif
 #ifndef LLQ16_PGS_V2
 #define LLQ16_PGS_V2 1   // sweep loops with induction-variable addressing (0: the indexed form, kept for A/B builds)
@@ -47,9 +47,9 @@ constexpr int kConW = 20, kConTab = kMaxCon * kConW;   // contact: leg depth | P
 constexpr int kLimTab = kMaxLim * 4;  // limit row: leg joint dir pen
 constexpr int kRowW = 12, kRowTab = 32 * kRowW;        // row: y(6) e(3) leg - -   (aliased by the 16 x 20 float scratch of the dynamics phase)
 constexpr int kEnvTab = 56;           // p_base(6) - - | Cholesky factor of the base block (21) - - - | joint targets (12) | actions (12)
-constexpr int kATab = 16 * 16;         // Delassus rows of the common path: atab[col * 16 + lane]
-constexpr int kEnvFloats = 1200;       // >= the sum of the tables, and = 16 (mod 32): the two envs of a warp hit disjoint banks
-static_assert(kLinkTab + kLegTab + kConTab + kLimTab + kRowTab + kEnvTab + kATab <= kEnvFloats && kEnvFloats % 32 == 16, "per-env table layout");
+constexpr int kATabWarp = 32 * 32;     // Delassus coefficients of one WARP (its two envs' rows packed into 32 lanes): atab[col * 32 + lane]
+constexpr int kEnvFloats = 944;        // >= the sum of the tables, and = 16 (mod 32): the two envs of a warp hit disjoint banks
+static_assert(kLinkTab + kLegTab + kConTab + kLimTab + kRowTab + kEnvTab <= kEnvFloats && kEnvFloats % 32 == 16, "per-env table layout");
 
 LLQ_DI float hsum16(float v) {        // sum over the 16 lanes of an env
   v += __shfl_xor_sync(FULL, v, 1); v += __shfl_xor_sync(FULL, v, 2); v += __shfl_xor_sync(FULL, v, 4); v += __shfl_xor_sync(FULL, v, 8);
@@ -141,8 +141,16 @@ LLQ_DI void sphere_box(double wx, double wy, double wz, double r, const float* b
 // ---------------------------------------------------------------------------------------------------------------
 // Constraint rows of one sub-step for the warp's two envs: row images, Delassus rows, Bullet's sequential-impulse sweep
 // (btMultiBodyConstraintSolver::solveSingleIteration order: limits, normals, friction pairs with the implicit cone).
-// NS = row slots per lane: slot s holds contacts 4 s .. 4 s + 3 (lanes 0-11) and limit rows 4 s .. 4 s + 3 (lanes 12-15).
-// Returns Yt = sum lam_r y_r (base part) and om = sum over the rows of this lane's leg of lam_r w_r (joint part).
+//
+// One row per lane, the rows of the two envs PACKED into the warp's 32 lanes: env A (the lower half-warp's) owns lanes [0, split),
+// env B lanes [split, 32); an env's rows are its contacts' (3 per contact: normal, two tangents), then its limit rows.  split = 16
+// whenever both envs have <= 16 rows; an env with more borrows lanes of its partner (3 c + l <= 32 rows per env by the caps); a pair
+// with more than 32 rows between them is solved in two passes, each env on all 32 lanes.  A lane therefore reads the tables of the env
+// its ROW belongs to (RowsIn::tb), which need not be the env its link / sphere roles belong to.  The Delassus coefficients of a row
+// live in shared memory (atab[col * 32 + lane], col = position of the other row in its env's row list: conflict free); all loops are
+// rolled, with warp-uniform bounds, and indexed by per-lane owners -- the whole solver is ~300 instructions of code.
+// The warp's two envs are ANY two envs of the CTA (the kernel pairs heavy with light ones after a CTA barrier); the totals
+// sum lam_r y_r (base part, 6) and, per leg, sum lam_r w_r (joint part, 4 x 3) go back through the env's row table.
 // ---- development aid (-DLLQ16_TIMING, tools/warp_timing.py): per-warp clock64 totals of the sub-step phases
 #ifdef LLQ16_TIMING
 __device__ unsigned long long g_t16[16384 * 12];
@@ -156,46 +164,57 @@ __device__ unsigned long long g_t16[16384 * 12];
 #define T16_ADD(slot, v)
 #define T16_IN(slot)
 #endif
-
 struct RowsIn {
 #ifdef LLQ16_TIMING
   long long* t16; long long* t16c;
 #endif
-  const float* legtab; const float* linktab; float* contab; const float* limtab; float* rowtab; const float* chol;
-  int nc, nl, Cmax, Lmax, l16, k;
-  int lim0;      // first lane of the limit rows: 3 Cmax on the common path (rows packed: contacts, then limits), 12 in the two-slot layout
-  V3 wbs, vbs;
+  float* tb;            // table block (s_env_dyn + e * kEnvFloats) of the env this lane's ROW belongs to
+  float* acol;          // this lane's column of the warp's coefficient table: acol[col * 32]
+  int nc, nl;           // contacts / limit rows of that env
+  int rr;               // index of this lane's row in the env's row list (>= 3 nc + nl: no row)
+  int lane0;            // first lane of that env's rows
+  int lane;             // 0..31
+  int split;            // warp-uniform: 16 = every row on its own env's half-warp
+  int Cmax, Lmax, ncols;   // warp-uniform maxima over the envs of this pass: contacts, limit rows, rows
+  float* res;           // where the totals of the env behind this lane's HALF-warp go (18 floats at the head of its row table), or
+                        // nullptr when that env is not solved in this pass
   float dt, slop, erp, jerp, max_imp;
   int iters;
 };
 // one row: its image under the factorised mass matrix and the scalars of the sweep
 struct RowRegs { float y[6], wj[3], b, rhs, invd, lam, hi, mu; int leg; };
-// slot sl of lane l16: contact 4 sl + l16 / 3 in direction l16 % 3 (lanes below in.lim0) or limit row 4 sl + l16 - in.lim0; also
-// leaves (y, e = D^-1 w, leg) in the row table for the other rows' Delassus entries (zeros for an absent row)
-LLQ_DI void row_image(const RowsIn& in, int sl, int l16, RowRegs& r) {
-  const bool is_con = l16 < in.lim0;
-  const int d = l16 % 3, cq = l16 / 3;
+// row rr of the env behind in.tb: contact rr / 3 in direction rr % 3, or limit row rr - 3 nc; also leaves (y, e = D^-1 w, leg) in the
+// env's row table for the other rows' Delassus entries.  Returns true for a normal row (its impulse is the contact's warm start).
+LLQ_DI bool row_image(const RowsIn& in, RowRegs& r) {
+  const float* linktab = in.tb;
+  const float* legtab = in.tb + kLinkTab;
+  const float* contab = legtab + kLegTab;
+  const float* limtab = contab + kConTab;
+  float* rowtab = in.tb + kLinkTab + kLegTab + kConTab + kLimTab;
+  const float* envtab = rowtab + kRowTab;
+  const int rr = in.rr;
+  const bool is_con = rr < 3 * in.nc;
+  const int d = rr % 3, cq = rr / 3;
   float e[3] = {0.f, 0.f, 0.f};
 #pragma unroll
   for (int t = 0; t < 6; t++) r.y[t] = 0.f;
   r.wj[0] = r.wj[1] = r.wj[2] = 0.f;
   r.b = 0.f; r.rhs = 0.f; r.invd = 0.f; r.lam = 0.f; r.hi = 0.f; r.mu = 0.f; r.leg = -2;
-  const int idx = 4 * sl + (is_con ? cq : l16 - in.lim0);
-  const bool act = is_con ? idx < in.nc : idx < in.nl;
+  const bool act = rr < 3 * in.nc + in.nl;
   if (act) {
     V3 Ga = V3{0.f, 0.f, 0.f}, Gl = V3{0.f, 0.f, 0.f};
     float j[3] = {0.f, 0.f, 0.f}, rel = 0.f, dist = 0.f, lam0 = 0.f, pen = 0.f, dirl = 0.f;
     int leg, jj = 0;
     if (is_con) {
-      const float* cr = in.contab + idx * kConW;
+      const float* cr = contab + cq * kConW;
       leg = __float_as_int(cr[0]);
       const int depth = __float_as_int(cr[1]);
       const V3 Pc = ld3(cr + 2), dir = ld3(cr + 5 + 3 * d);
       dist = cr[14]; r.mu = cr[15]; lam0 = cr[16];
       Ga = cross(Pc, dir); Gl = dir;
-      rel = dot(Ga, in.wbs) + dot(Gl, in.vbs);
+      rel = dot(Ga, ld3(envtab)) + dot(Gl, ld3(envtab + 3));     // predicted base velocity (base coordinates), parked by the env's lane 0
       if (leg >= 0) {
-        const float* lk = in.linktab + leg * 24;
+        const float* lk = linktab + leg * 24;
         const float c1 = lk[0], s1 = lk[1];
         const V3 p1 = ld3(lk + 4), p2 = ld3(lk + 12), p3 = ld3(lk + 20), n2 = V3{0.f, -c1, -s1};
         j[0] = Ga.x + dot(cross(p1, V3{1.f, 0.f, 0.f}), Gl);
@@ -203,14 +222,14 @@ LLQ_DI void row_image(const RowsIn& in, int sl, int l16, RowRegs& r) {
         if (depth >= 3) j[2] = dot(n2, Ga) + dot(cross(p3, n2), Gl);
       }
     } else {
-      const float* lr = in.limtab + idx * 4;
+      const float* lr = limtab + (rr - 3 * in.nc) * 4;
       leg = __float_as_int(lr[0]); jj = __float_as_int(lr[1]); dirl = lr[2]; pen = lr[3];
       j[0] = jj == 0 ? dirl : 0.f; j[1] = jj == 1 ? dirl : 0.f; j[2] = jj == 2 ? dirl : 0.f;
     }
     r.leg = leg;
     float g[6] = {Ga.x, Ga.y, Ga.z, Gl.x, Gl.y, Gl.z};
     if (leg >= 0) {
-      const float* lt = in.legtab + leg * 48;
+      const float* lt = legtab + leg * 48;
       const float L10 = lt[18], L20 = lt[19], L21 = lt[20];
       rel += j[0] * lt[24] + j[1] * lt[25] + j[2] * lt[26];
       r.wj[0] = j[0];
@@ -222,7 +241,7 @@ LLQ_DI void row_image(const RowsIn& in, int sl, int l16, RowRegs& r) {
 #pragma unroll
         for (int t = 0; t < 6; t++) g[t] = fmaf(-e[m], lt[6 * m + t], g[t]);
     }
-    chol6_fwd_p(in.chol, g, r.y);
+    chol6_fwd_p(envtab + 8, g, r.y);
     const float dg = dot6(r.y, r.y) + r.wj[0] * e[0] + r.wj[1] * e[1] + r.wj[2] * e[2];
     r.invd = 1.0f / dg;
     if (is_con) {
@@ -240,11 +259,12 @@ LLQ_DI void row_image(const RowsIn& in, int sl, int l16, RowRegs& r) {
       r.rhs = (poserr - rel) * r.invd;
       r.hi = in.max_imp;
     }
+    float* rw = rowtab + rr * kRowW;
+    st4(rw, r.y[0], r.y[1], r.y[2], r.y[3]);
+    st4(rw + 4, r.y[4], r.y[5], e[0], e[1]);
+    st4(rw + 8, e[2], __int_as_float(r.leg), 0.f, 0.f);
   }
-  float* rw = in.rowtab + (sl * 16 + l16) * kRowW;
-  st4(rw, r.y[0], r.y[1], r.y[2], r.y[3]);
-  st4(rw + 4, r.y[4], r.y[5], e[0], e[1]);
-  st4(rw + 8, e[2], __int_as_float(r.leg), 0.f, 0.f);
+  return act && is_con && d == 0;
 }
 // entry (r, col) of the Delassus matrix from this lane's row r and the table entry of row `col`
 LLQ_DI float delassus_entry(const RowRegs& r, const float* rw) {
@@ -253,230 +273,119 @@ LLQ_DI float delassus_entry(const RowRegs& r, const float* rw) {
   const float jt = r.wj[0] * bq.z + r.wj[1] * bq.w + r.wj[2] * cq4.x;
   return dot6(r.y, ys) + (__float_as_int(cq4.y) == r.leg ? jt : 0.f);
 }
-// total impulse of the env: Yt = sum lam_r y_r and, per leg, sum lam_r w_r -- 18 values, butterfly over the env's 16 lanes
-LLQ_DI void impulse_sums(float (&v18)[18], int k, float (&Yt)[6], float (&om)[3]) {
+// total impulse of an env: Yt += sum lam_r y_r and, per leg, sum lam_r w_r -- 18 values.  Rows that sit on the partner's half-warp are
+// handed across first (xor 16), then a butterfly over each half-warp.
+LLQ_DI void impulse_sums(const RowsIn& in, const RowRegs& r) {
+  float v18[18];
+#pragma unroll
+  for (int t = 0; t < 6; t++) v18[t] = r.lam * r.y[t];
+#pragma unroll
+  for (int kk = 0; kk < 4; kk++) {
+    const float f = r.leg == kk ? r.lam : 0.f;
+#pragma unroll
+    for (int m = 0; m < 3; m++) v18[6 + 3 * kk + m] = f * r.wj[m];
+  }
+  if (in.split != 16) {                                     // warp-uniform
+    const bool foreign = (in.lane >= 16) != (in.lane >= in.split);      // the row belongs to the other half-warp's env
+#pragma unroll 1
+    for (int t = 0; t < 18; t++) {
+      const float mine = foreign ? 0.f : v18[t], give = foreign ? v18[t] : 0.f;
+      v18[t] = mine + __shfl_xor_sync(FULL, give, 16);
+    }
+  }
 #pragma unroll 1
   for (int o = 1; o < 16; o <<= 1) {
 #pragma unroll
     for (int t = 0; t < 18; t++) v18[t] += __shfl_xor_sync(FULL, v18[t], o);
   }
-#pragma unroll
-  for (int t = 0; t < 6; t++) Yt[t] = v18[t];
-#pragma unroll
-  for (int m = 0; m < 3; m++) om[m] = k == 0 ? v18[6 + m] : (k == 1 ? v18[9 + m] : (k == 2 ? v18[12 + m] : v18[15 + m]));
-}
-LLQ_DI void add_row_impulse(const RowRegs& r, float (&v18)[18]) {
-#pragma unroll
-  for (int t = 0; t < 6; t++) v18[t] = fmaf(r.lam, r.y[t], v18[t]);
-#pragma unroll
-  for (int kk = 0; kk < 4; kk++) {
-    const float f = r.leg == kk ? r.lam : 0.f;
-#pragma unroll
-    for (int m = 0; m < 3; m++) v18[6 + 3 * kk + m] = fmaf(f, r.wj[m], v18[6 + 3 * kk + m]);
+  if (in.res && (in.lane & 15) == 0) {                    // the lower half-warp holds env A's totals, the upper one env B's
+    st4(in.res, v18[0], v18[1], v18[2], v18[3]); st4(in.res + 4, v18[4], v18[5], v18[6], v18[7]);
+    st4(in.res + 8, v18[8], v18[9], v18[10], v18[11]); st4(in.res + 12, v18[12], v18[13], v18[14], v18[15]);
+    in.res[16] = v18[16]; in.res[17] = v18[17];
   }
 }
 
-// ---- common path: 3 Cmax + Lmax <= 16 rows in both envs of the warp (lanes [0, 3 Cmax): the contacts' rows, then the limit rows).
-// One row per lane; the row's 16 Delassus
-// coefficients live in shared memory (atab[col * 16 + lane]: conflict free), so every loop is rolled and indexed by run-time lane ids --
-// the whole solver is ~250 instructions of code, which matters more than the extra LDS per update: the sub-step body has to stay
-// inside the SM's 32 KB instruction cache now that sixteen warps per SM run through it at their own pace.
-LLQ_DI void solve_rows_s(const RowsIn& in, float* atab, float (&Yt)[6], float (&om)[3]) {
-  int l16 = in.l16;
-  asm volatile("" : "+r"(l16));            // opaque: held in a register instead of being re-derived from %tid at every row
+LLQ_DI void solve_rows(const RowsIn& in) {
+  int lane = in.lane;
+  asm volatile("" : "+r"(lane));            // opaque: held in a register instead of being re-derived from %tid at every row
   RowRegs r;
-  row_image(in, 0, l16, r);
+  const bool is_normal = row_image(in, r);
   __syncwarp();
   T16_IN(8);
-  float* acol = atab + l16;
-  const int ncc = 3 * in.Cmax, ncols = ncc + in.Lmax;
+  float* acol = in.acol;
+  const int nrows = 3 * in.nc + in.nl;
+  {
+    const float* rowtab = in.tb + kLinkTab + kLegTab + kConTab + kLimTab;
 #pragma unroll 1
-  for (int col = 0; col < ncols; col++)      // columns of the active contacts, then of the active limit rows (warp-uniform bounds)
-    acol[col * 16] = delassus_entry(r, in.rowtab + col * kRowW);
+    for (int col = 0; col < in.ncols; col++) {     // columns = the env's rows, in its row order (warp-uniform bound: the longer list)
+      const float a = delassus_entry(r, rowtab + col * kRowW);
+      acol[col * 32] = col < nrows ? a : 0.f;       // (beyond the env's list the table holds old rows: finite, never used)
+    }
+  }
+  const int lane0 = in.lane0, nc = in.nc, nl = in.nl;
   // warm start of the normal rows
 #pragma unroll 1
-  for (int c = 0; c < in.Cmax; c++) r.b = fmaf(acol[48 * c], __shfl_sync(FULL, r.lam, 3 * c, 16), r.b);
+  for (int c = 0; c < in.Cmax; c++) {
+    const float v = __shfl_sync(FULL, r.lam, lane0 + 3 * c);
+    r.b = fmaf(acol[96 * c], c < nc ? v : 0.f, r.b);
+  }
   T16_IN(9);
-  // projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration order); an absent row has rhs = invd = A = 0 => dl = 0
-#if LLQ16_PGS_V2
-  // one row update: candidate on every lane (only the owner's counts), owner commits, broadcast, one LDS + FMA per lane.  The column
-  // pointer and the owner lane are induction variables (no index arithmetic inside the loops).
-#if LLQ16_PGS_V2 >= 2
-  // shortest dependent chain per row: FFMA (candidate from c = lam + rhs, kept up to date off the chain) -> 2 FMNMX -> FADD -> SHFL -> FFMA
-  float rc = r.lam + r.rhs;
-#define LLQ16_ROW_UPDATE(ln, ap)                                                                      \
+  // projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration order).  One row update: candidate on every lane (only
+  // the owner's counts), owner commits, broadcast, one LDS + FMA per lane; the column pointer and the owner lane are induction
+  // variables.  A step beyond the env's own list (the partner's is longer) is masked.
+  float rc = r.lam + r.rhs;                  // lam + rhs, kept up to date off the dependent chain
+#define LLQ16_ROW_UPDATE(src, ap, valid)                                                              \
   {                                                                                                   \
-    const float cl = fminf(fmaxf(fmaf(-r.b, r.invd, rc), 0.f), r.hi);                                 \
+    const float cl = fminf(fmaxf(fmaf(-r.b, r.invd, rc), 0.f), r.hi);   /* clamp the accumulated impulse */ \
     const float dl = cl - r.lam;                                                                      \
-    const bool own = l16 == (ln);                                                                     \
+    const bool own = lane == (src) && (valid);                                                        \
     r.lam = own ? cl : r.lam;                                                                         \
     rc = own ? cl + r.rhs : rc;                                                                       \
-    r.b = fmaf(*(ap), __shfl_sync(FULL, dl, (ln), 16), r.b);                                          \
+    const float v = __shfl_sync(FULL, dl, (src));                                                     \
+    r.b = fmaf(*(ap), (valid) ? v : 0.f, r.b);                                                        \
   }
-#define LLQ16_SOWN fmaf(-r.b, r.invd, rc)
-#define LLQ16_SET_FRIC(snew) { const bool own = (unsigned)(l16 - ln - 1) < 2u; r.lam = own ? (snew) : r.lam; rc = own ? (snew) + r.rhs : rc; }
-#else
-#define LLQ16_ROW_UPDATE(ln, ap)                                                                      \
-  {                                                                                                   \
-    const float dlc = fmaf(-r.b, r.invd, r.rhs);                                                      \
-    const float sum = r.lam + dlc;                                                                    \
-    const float cl = fminf(fmaxf(sum, 0.f), r.hi);       /* Bullet: clamp the accumulated impulse */  \
-    const float dl = cl == sum ? dlc : cl - r.lam;       /* (unclamped: exactly the increment) */     \
-    r.lam = l16 == (ln) ? cl : r.lam;                                                                 \
-    r.b = fmaf(*(ap), __shfl_sync(FULL, dl, (ln), 16), r.b);                                          \
-  }
-#define LLQ16_SOWN (r.lam + fmaf(-r.b, r.invd, r.rhs))
-#define LLQ16_SET_FRIC(snew) r.lam = (unsigned)(l16 - ln - 1) < 2u ? (snew) : r.lam;
-#endif
-  const float* const alim = acol + ncc * 16;
-  const float* const alim_end = alim + in.Lmax * 16;
-  const float* const anrm_end = acol + ncc * 16;
 #pragma unroll 1
   for (int it = 0; it < in.iters; it++) {
-    int ln = ncc;
+    {
+      int src = lane0 + 3 * nc;
+      const float* ap = acol + 96 * nc;
 #pragma unroll 1
-    for (const float* ap = alim; ap != alim_end; ap += 16, ln++) LLQ16_ROW_UPDATE(ln, ap)      // joint-limit rows in joint order
-    ln = 0;
-#pragma unroll 1
-    for (const float* ap = acol; ap != anrm_end; ap += 48, ln += 3) LLQ16_ROW_UPDATE(ln, ap)   // normal rows in contact order
-    ln = 0;
-#pragma unroll 1
-    for (const float* ap = acol; ap != anrm_end; ap += 48, ln += 3) {   // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
-      const float sown = LLQ16_SOWN;
-      const float sa = __shfl_sync(FULL, sown, ln + 1, 16), sb = __shfl_sync(FULL, sown, ln + 2, 16);
-      const float limit = r.mu * __shfl_sync(FULL, r.lam, ln, 16);
-      const float r2 = sa * sa + sb * sb;
-      const bool clip = r2 >= limit * limit && r2 > 0.f;
-      const float sc = clip ? limit * rsqrtf(r2) : 1.0f;
-      const float snew = clip ? sown * sc : sown;
-      const float dl = snew - r.lam;
-      LLQ16_SET_FRIC(snew)
-      const float da = __shfl_sync(FULL, dl, ln + 1, 16), db = __shfl_sync(FULL, dl, ln + 2, 16);
-      r.b = fmaf(ap[16], da, fmaf(ap[32], db, r.b));
+      for (int t = 0; t < in.Lmax; t++, src++, ap += 32) LLQ16_ROW_UPDATE(src, ap, t < nl)       // joint-limit rows in joint order
     }
-  }
-#undef LLQ16_ROW_UPDATE
-#undef LLQ16_SOWN
-#undef LLQ16_SET_FRIC
-#else
-  const int nrow = in.Lmax + in.Cmax;
+    {
+      int src = lane0;
+      const float* ap = acol;
 #pragma unroll 1
-  for (int it = 0; it < in.iters; it++) {
+      for (int t = 0; t < in.Cmax; t++, src += 3, ap += 96) LLQ16_ROW_UPDATE(src, ap, t < nc)    // normal rows in contact order
+    }
+    {
+      int src = lane0;
+      const float* ap = acol;
 #pragma unroll 1
-    for (int t = 0; t < nrow; t++) {          // joint-limit rows in joint order, then the normal rows in contact order
-      const int ln = t < in.Lmax ? ncc + t : 3 * (t - in.Lmax);
-      const float dlc = fmaf(-r.b, r.invd, r.rhs);
-      const float sum = r.lam + dlc;
-      const float cl = fminf(fmaxf(sum, 0.f), r.hi);                  // Bullet: clamp the accumulated impulse to [0, hi]
-      const float dl = cl == sum ? dlc : cl - r.lam;                  // (unclamped: exactly the computed increment)
-      r.lam = l16 == ln ? cl : r.lam;
-      r.b = fmaf(acol[ln * 16], __shfl_sync(FULL, dl, ln, 16), r.b);
-    }
-#pragma unroll 1
-    for (int c = 0; c < in.Cmax; c++) {       // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
-      const int ln = 3 * c;
-      const float sown = r.lam + fmaf(-r.b, r.invd, r.rhs);
-      const float sa = __shfl_sync(FULL, sown, ln + 1, 16), sb = __shfl_sync(FULL, sown, ln + 2, 16);
-      const float limit = r.mu * __shfl_sync(FULL, r.lam, ln, 16);
-      const float r2 = sa * sa + sb * sb;
-      const bool clip = r2 >= limit * limit && r2 > 0.f;
-      const float sc = clip ? limit * rsqrtf(r2) : 1.0f;
-      const float snew = clip ? sown * sc : sown;
-      const float dl = snew - r.lam;
-      r.lam = (l16 == ln + 1 || l16 == ln + 2) ? snew : r.lam;
-      const float da = __shfl_sync(FULL, dl, ln + 1, 16), db = __shfl_sync(FULL, dl, ln + 2, 16);
-      r.b = fmaf(acol[(ln + 1) * 16], da, fmaf(acol[(ln + 2) * 16], db, r.b));
-    }
-  }
-#endif
-  T16_IN(10);
-  // the normal impulses go back to the contact records (warm start of the next sub-step)
-  if (l16 < ncc && l16 % 3 == 0 && l16 / 3 < in.nc) in.contab[(l16 / 3) * kConW + 17] = r.lam;
-  float v18[18];
-#pragma unroll
-  for (int t = 0; t < 18; t++) v18[t] = 0.f;
-  add_row_impulse(r, v18);
-  impulse_sums(v18, in.k, Yt, om);
-}
-
-// ---- rare path: more than 16 rows (3 Cmax + Lmax) in one of the warp's envs.  Two row slots per lane (slot s: contacts
-// 4 s .. 4 s + 3 on lanes 0-11, limit rows 4 s .. 4 s + 3 on lanes 12-15), 2 x 32 Delassus coefficients per lane in local
-// memory, out of line so that the common path keeps its register budget and its code footprint.
-__device__ __noinline__ void solve_rows2(const RowsIn& in, float (&Yt)[6], float (&om)[3]) {
-  constexpr int NS = 2;
-  int l16 = in.l16;
-  asm volatile("" : "+r"(l16));
-  RowRegs r[NS];
-  float A[NS][16 * NS];
-#pragma unroll
-  for (int sl = 0; sl < NS; sl++) row_image(in, sl, l16, r[sl]);
-  __syncwarp();
-  T16_IN(8);
-#pragma unroll
-  for (int col = 0; col < 16 * NS; col++) {
-    const int cs = col >> 4, cl = col & 15;
-    const bool want = cl < 12 ? (4 * cs + cl / 3) < in.Cmax : (4 * cs + cl - 12) < in.Lmax;
-#pragma unroll
-    for (int sl = 0; sl < NS; sl++) A[sl][col] = want ? delassus_entry(r[sl], in.rowtab + col * kRowW) : 0.f;
-  }
-#pragma unroll
-  for (int c = 0; c < 4 * NS; c++) {
-    if (c < in.Cmax) {
-      const float l0 = __shfl_sync(FULL, r[c >> 2].lam, 3 * (c & 3), 16);
-#pragma unroll
-      for (int sl = 0; sl < NS; sl++) r[sl].b = fmaf(A[sl][(c >> 2) * 16 + 3 * (c & 3)], l0, r[sl].b);
-    }
-  }
-  T16_IN(9);
-#pragma unroll 1
-  for (int it = 0; it < in.iters; it++) {
-#pragma unroll
-    for (int t = 0; t < 8 * NS; t++) {            // joint-limit rows, joint order; then the normal rows, contact order
-      const bool lim = t < 4 * NS;
-      const int ix = lim ? t : t - 4 * NS;
-      if (ix < (lim ? in.Lmax : in.Cmax)) {
-        const int so = ix >> 2, ln = lim ? 12 + (ix & 3) : 3 * (ix & 3);
-        RowRegs& q = r[so];
-        const float dlc = fmaf(-q.b, q.invd, q.rhs);
-        const float sum = q.lam + dlc;
-        const float cl = fminf(fmaxf(sum, 0.f), q.hi);
-        const float dl = cl == sum ? dlc : cl - q.lam;
-        q.lam = l16 == ln ? cl : q.lam;
-        const float v = __shfl_sync(FULL, dl, ln, 16);
-#pragma unroll
-        for (int sl = 0; sl < NS; sl++) r[sl].b = fmaf(A[sl][so * 16 + ln], v, r[sl].b);
-      }
-    }
-#pragma unroll
-    for (int c = 0; c < 4 * NS; c++) {            // friction pairs with the implicit cone
-      if (c < in.Cmax) {
-        const int so = c >> 2, ln = 3 * (c & 3);
-        RowRegs& q = r[so];
-        const float sown = q.lam + fmaf(-q.b, q.invd, q.rhs);
-        const float sa = __shfl_sync(FULL, sown, ln + 1, 16), sb = __shfl_sync(FULL, sown, ln + 2, 16);
-        const float limit = q.mu * __shfl_sync(FULL, q.lam, ln, 16);
+      for (int t = 0; t < in.Cmax; t++, src += 3, ap += 96) {   // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
+        const bool valid = t < nc;
+        const float sown = fmaf(-r.b, r.invd, rc);
+        const float sa = __shfl_sync(FULL, sown, src + 1), sb = __shfl_sync(FULL, sown, src + 2);
+        const float limit = r.mu * __shfl_sync(FULL, r.lam, src);
         const float r2 = sa * sa + sb * sb;
         const bool clip = r2 >= limit * limit && r2 > 0.f;
         const float sc = clip ? limit * rsqrtf(r2) : 1.0f;
         const float snew = clip ? sown * sc : sown;
-        const float dl = snew - q.lam;
-        q.lam = (l16 == ln + 1 || l16 == ln + 2) ? snew : q.lam;
-        const float da = __shfl_sync(FULL, dl, ln + 1, 16), db = __shfl_sync(FULL, dl, ln + 2, 16);
-#pragma unroll
-        for (int sl = 0; sl < NS; sl++) r[sl].b = fmaf(A[sl][so * 16 + ln + 1], da, fmaf(A[sl][so * 16 + ln + 2], db, r[sl].b));
+        const float dl = snew - r.lam;
+        const bool own = (unsigned)(lane - src - 1) < 2u && valid;
+        r.lam = own ? snew : r.lam;
+        rc = own ? snew + r.rhs : rc;
+        const float da = __shfl_sync(FULL, dl, src + 1), db = __shfl_sync(FULL, dl, src + 2);
+        r.b = fmaf(ap[32], valid ? da : 0.f, fmaf(ap[64], valid ? db : 0.f, r.b));
       }
     }
   }
+#undef LLQ16_ROW_UPDATE
   T16_IN(10);
-#pragma unroll
-  for (int sl = 0; sl < NS; sl++)
-    if (l16 < 12 && l16 % 3 == 0 && 4 * sl + l16 / 3 < in.nc) in.contab[(4 * sl + l16 / 3) * kConW + 17] = r[sl].lam;
-  float v18[18];
-#pragma unroll
-  for (int t = 0; t < 18; t++) v18[t] = 0.f;
-#pragma unroll
-  for (int sl = 0; sl < NS; sl++) add_row_impulse(r[sl], v18);
-  impulse_sums(v18, in.k, Yt, om);
+  // the normal impulses go back to the contact records (warm start of the next sub-step)
+  if (is_normal) in.tb[kLinkTab + kLegTab + (in.rr / 3) * kConW + 17] = r.lam;
+  __syncwarp();                     // every lane is done with the row table: its head becomes the result area
+  impulse_sums(in, r);
 }
 
 // ---------------------------------------------------------------------------------------------------------------
@@ -774,11 +683,12 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
                                                             unsigned long long seed, long long gid0, int record) {
   constexpr int BLOCK = LLQ16_BLOCK, EPB = BLOCK / 16;        // 2 envs per warp
   constexpr int EPT = (EPB + 7) / 8 * 8;                      // the tail runs 8 envs per warp on whole warps: rows EPB.. are dummies
-  static_assert(BLOCK % 32 == 0, "whole warps");
+  static_assert(BLOCK % 32 == 0 && EPB <= 32, "whole warps; one lane per env in the pairing");
   __shared__ __align__(16) ModelConst M;
   __shared__ __align__(16) SphTable ST;
   __shared__ __align__(16) float s_new[EPT][kNewObs];
   __shared__ __align__(16) float s_hist[EPT][kHist];
+  __shared__ int s_cnt[32];                                   // contacts | limit rows << 8 of the CTA's envs, this sub-step
   extern __shared__ __align__(16) float s_env_dyn[];   // [EPB][kEnvFloats]: 38.4 kB, beside 10 kB of static shared memory
   const int tid = threadIdx.x;
   const int N = P.n_envs;
@@ -808,7 +718,8 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
   float* const rowtab = limtab + kLimTab;
   float* const scr = rowtab;                         // dynamics-phase scratch (16 lanes x 20 floats) aliases the row table
   float* const envtab = rowtab + kRowTab;
-  float* const atab = envtab + kEnvTab;
+  float* const s_atab = s_env_dyn + EPB * kEnvFloats;   // [BLOCK / 32][32 cols][32 lanes] Delassus coefficients, one table per warp
+  for (int col = 0; col < 32; col++) s_atab[(tid >> 5) * kATabWarp + col * 32 + (tid & 31)] = 0.f;      // finite from the start (masked steps multiply them by 0)
   // joints with a lower dof index than this lane's (k, i): rank of a violated limit in Bullet's row order
   unsigned lowmask = 0;
 #pragma unroll
@@ -888,12 +799,6 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
   T16_DECL;
   for (int sub = 0; sub < P.substeps; sub++) {
     T16_MARK(5);
-#if LLQ16_BAR >= 1
-    __syncthreads();      // not needed for correctness (the tables are per half-warp): keeps the CTA's warps on one stretch of code
-#else
-    __syncwarp();         // the tables are per env (= per half-warp): no CTA-wide ordering is needed
-#endif
-    T16_MARK(0);
     const float dt = P.dt;
     // ---------------- push randomiser (PR:56-87): counters in sub-steps, force lasts one sub-step
     bool push_on = false;
@@ -1110,6 +1015,9 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
     }
     wbs = tmul(R, ww); vbs = tmul(R, vw);
     __syncwarp();                                     // every lane has read F / H: the leg table becomes the rows' table
+    if (l16 == 0) {                                   // predicted base velocity for the rows' right-hand sides (any lane of the warp may build them)
+      envtab[0] = wbs.x; envtab[1] = wbs.y; envtab[2] = wbs.z; envtab[3] = vbs.x; envtab[4] = vbs.y; envtab[5] = vbs.z;
+    }
     if (i == 0) {
       float* lt = legtab + k * 48;
 #pragma unroll
@@ -1367,37 +1275,81 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
     __syncwarp();
     T16_MARK(2);
     float dvb[6] = {0.f, 0.f, 0.f, 0.f, 0.f, 0.f}, dvl[3] = {0.f, 0.f, 0.f};
+    // ---------------- the rows of the CTA's envs: publish the counts, pair the envs by load, solve, hand the totals back
+    if (l16 == 0) s_cnt[el] = nc | (nl << 8);
+    __syncthreads();           // every env's tables (links, legs, contacts, limits, Cholesky factor, predicted velocity) are complete
+    T16_MARK(0);
     {
-      // warp-uniform loop bounds (a redux result lives in a uniform register: the guards below compile to uniform branches)
-      const int Cmax = __reduce_max_sync(FULL, nc), Lmax = __reduce_max_sync(FULL, nl);
-      T16_ADD(6, Cmax * 256 + Lmax + (3 * Cmax + Lmax > 16 ? 65536 : 0));
-      if (Cmax | Lmax) {
+      // Pairing: the critical path of the sub-step is the longest row list of the CTA (the sweep is sequential within an env), and a
+      // warp whose two envs have more than 32 rows between them needs two passes -- so warp w takes the env of rank w (by row count,
+      // descending) together with the env of rank EPB - 1 - w.  The result does not depend on the pairing (an env's rows only meet
+      // its own tables).
+      const int lane = tid & 31, wq = tid >> 5;
+      const int cnt = lane < EPB ? s_cnt[lane] : 0;
+      const int nrow = 3 * (cnt & 255) + (cnt >> 8);
+      int rank = 0;
+#pragma unroll 1
+      for (int j = 0; j < EPB; j++) {
+        const int nj = __shfl_sync(FULL, nrow, j);
+        rank += (nj > nrow || (nj == nrow && j < lane)) ? 1 : 0;
+      }
+      const int ea = __ffs(__ballot_sync(FULL, lane < EPB && rank == wq)) - 1;
+      const int eb = __ffs(__ballot_sync(FULL, lane < EPB && rank == EPB - 1 - wq)) - 1;
+      const int ca_ = __shfl_sync(FULL, cnt, ea), cb_ = __shfl_sync(FULL, cnt, eb);
+      // (redux results live in uniform registers: the guards below compile to uniform branches)
+      const int cA = __reduce_max_sync(FULL, ca_ & 255), lA = __reduce_max_sync(FULL, ca_ >> 8);
+      const int cB = __reduce_max_sync(FULL, cb_ & 255), lB = __reduce_max_sync(FULL, cb_ >> 8);
+      const int eA = __reduce_max_sync(FULL, ea), eB = __reduce_max_sync(FULL, eb);
+      const int nA = 3 * cA + lA, nB = 3 * cB + lB;
+      T16_ADD(6, max(cA, cB) * 256 + max(lA, lB) + (nA > 16 || nB > 16 ? 65536 : 0) + (nA + nB > 32 ? (1 << 24) : 0));
+      if (nA | nB) {
         RowsIn in;
-        in.legtab = legtab; in.linktab = linktab; in.contab = contab; in.limtab = limtab; in.rowtab = rowtab; in.chol = envtab + 8;
-        const bool two_slots = 3 * Cmax + Lmax > 16;
-        in.nc = nc; in.nl = nl; in.Cmax = Cmax; in.Lmax = Lmax; in.l16 = l16; in.k = k; in.lim0 = two_slots ? 12 : 3 * Cmax;
-        in.wbs = wbs; in.vbs = vbs; in.dt = dt; in.slop = P.slop; in.erp = P.erp; in.jerp = P.jerp; in.max_imp = P.max_imp; in.iters = P.solver_iters;
 #ifdef LLQ16_TIMING
         in.t16 = t16_; in.t16c = &t16_c;
 #endif
-        float Yt[6], om[3];
-        if (two_slots) solve_rows2(in, Yt, om); else solve_rows_s(in, atab, Yt, om);
-        if (l16 == 0) { n_contact_rows += 3u * (unsigned)nc; n_limit_rows += (unsigned)nl; }
-        __syncwarp();
-#pragma unroll
-        for (int rd = 0; rd < 2; rd++) if (mycon[rd] >= 0) warm[rd] = contab[mycon[rd] * kConW + 17];
-        // ---- total impulse -> velocity change: one back substitution for the base, one 3x3 solve per leg
-        chol6_bwd_p(envtab + 8, Yt, dvb);
-        const float* lt = legtab + k * 48;            // W, L, D^-1 of this lane's leg come back from the leg table (not kept live across the solve)
-        float t3[3];
-#pragma unroll
-        for (int m = 0; m < 3; m++) {
-          const float wm[6] = {lt[6 * m], lt[6 * m + 1], lt[6 * m + 2], lt[6 * m + 3], lt[6 * m + 4], lt[6 * m + 5]};
-          t3[m] = (om[m] - dot6(wm, dvb)) * lt[21 + m];
+        in.lane = lane; in.acol = s_atab + wq * kATabWarp + lane;
+        in.dt = dt; in.slop = P.slop; in.erp = P.erp; in.jerp = P.jerp; in.max_imp = P.max_imp; in.iters = P.solver_iters;
+        float* const tbA = s_env_dyn + eA * kEnvFloats;
+        float* const tbB = s_env_dyn + eB * kEnvFloats;
+        const bool two_pass = nA + nB > 32;            // more rows than lanes: env A on all 32 lanes, then env B
+#pragma unroll 1
+        for (int pass = 0; pass < (two_pass ? 2 : 1); pass++) {
+          const int split = two_pass ? (pass == 0 ? 32 : 0) : ((nA <= 16 && nB <= 16) ? 16 : (nA > 16 ? nA : 32 - nB));
+          const bool X = lane >= split;
+          in.tb = X ? tbB : tbA;
+          in.nc = X ? cB : cA; in.nl = X ? lB : lA;
+          in.lane0 = X ? split : 0; in.rr = lane - in.lane0; in.split = split;
+          in.Cmax = two_pass ? (pass == 0 ? cA : cB) : max(cA, cB);
+          in.Lmax = two_pass ? (pass == 0 ? lA : lB) : max(lA, lB);
+          in.ncols = two_pass ? (pass == 0 ? nA : nB) : max(nA, nB);
+          const bool upper = lane >= 16;
+          in.res = (two_pass && upper != (pass == 1)) ? nullptr : (upper ? tbB : tbA) + (kLinkTab + kLegTab + kConTab + kLimTab);
+          solve_rows(in);
+          __syncwarp();
         }
-        dvl[2] = t3[2]; dvl[1] = fmaf(-lt[20], dvl[2], t3[1]); dvl[0] = fmaf(-lt[18], dvl[1], fmaf(-lt[19], dvl[2], t3[0]));
       }
     }
+    __syncthreads();           // the totals of every env of the CTA are in its row table
+    T16_MARK(3);
+    if (nc | nl) {
+      if (l16 == 0) { n_contact_rows += 3u * (unsigned)nc; n_limit_rows += (unsigned)nl; }
+#pragma unroll
+      for (int rd = 0; rd < 2; rd++) if (mycon[rd] >= 0) warm[rd] = contab[mycon[rd] * kConW + 17];
+      // ---- total impulse -> velocity change: one back substitution for the base, one 3x3 solve per leg
+      const float4 y0 = ld4(rowtab), y1 = ld4(rowtab + 4);
+      const float Yt[6] = {y0.x, y0.y, y0.z, y0.w, y1.x, y1.y};
+      const float om[3] = {rowtab[6 + 3 * k], rowtab[7 + 3 * k], rowtab[8 + 3 * k]};
+      chol6_bwd_p(envtab + 8, Yt, dvb);
+      const float* lt = legtab + k * 48;            // W, L, D^-1 of this lane's leg come back from the leg table (not kept live across the solve)
+      float t3[3];
+#pragma unroll
+      for (int m = 0; m < 3; m++) {
+        const float wm[6] = {lt[6 * m], lt[6 * m + 1], lt[6 * m + 2], lt[6 * m + 3], lt[6 * m + 4], lt[6 * m + 5]};
+        t3[m] = (om[m] - dot6(wm, dvb)) * lt[21 + m];
+      }
+      dvl[2] = t3[2]; dvl[1] = fmaf(-lt[20], dvl[2], t3[1]); dvl[0] = fmaf(-lt[18], dvl[1], fmaf(-lt[19], dvl[2], t3[0]));
+    }
+    __syncwarp();              // the row table is the next sub-step's scratch
     T16_MARK(3);
     // ---------------- apply the impulses, clamp, integrate (btMultiBody::stepPositionsMultiDof)
     {

@@ -32,9 +32,10 @@ for label, warm in (("fresh", 3), ("steady", int(os.environ.get("WARM", 200)))):
     for j in (0, 1, 2, 3, 4, 5):
         r[names[j]] = {"mean": t[:, j].mean(), "max": t[:, j].max(), "share_of_total": t[:, j].sum() / tot.sum()}
     rows = buf[:, 6]
-    two = (rows >> np.uint64(16)).astype(np.float64); cm = ((rows >> np.uint64(8)) & np.uint64(0xFF)).astype(np.float64); lm = (rows & np.uint64(0xFF)).astype(np.float64)
+    two = ((rows >> np.uint64(16)) & np.uint64(0xFF)).astype(np.float64); twop = (rows >> np.uint64(24)).astype(np.float64); cm = ((rows >> np.uint64(8)) & np.uint64(0xFF)).astype(np.float64); lm = (rows & np.uint64(0xFF)).astype(np.float64)
     r["Cmax_sum_per_step"] = {"mean": cm.mean(), "max": cm.max()}; r["Lmax_sum_per_step"] = {"mean": lm.mean(), "max": lm.max()}
-    r["two_slot_substeps"] = {"mean": two.mean(), "max": two.max(), "warps_with_any": float((two > 0).mean())}
+    r["substeps_with_an_env_over_16_rows"] = {"mean": two.mean(), "max": two.max(), "warps_with_any": float((two > 0).mean())}
+    r["two_pass_substeps"] = {"mean": twop.mean(), "max": twop.max(), "warps_with_any": float((twop > 0).mean())}
     work = t[:, 1] + t[:, 2] + t[:, 3] + t[:, 5]
     r["work_without_barrier"] = {"mean": work.mean(), "max": work.max(), "p99": float(np.percentile(work, 99))}
     r["corr_solver_vs_rows"] = float(np.corrcoef(t[:, 3], cm + lm)[0, 1])
