@@ -24,7 +24,7 @@
 namespace llq {
 
 #ifndef LLQ16_BLOCK
-#define LLQ16_BLOCK 256   // threads per CTA (16 per env).  Measured at 4096 envs, step + reset per policy step: 32 threads 0.43 ms, 64 0.375,
+#define LLQ16_BLOCK 224   // 14 envs per CTA: 4096 envs = 293 CTAs = one wave of 2 CTAs (14 warps) per SM; 256 would put 16 warps on 108 of the 148 SMs
                           // 128 0.334, 256 0.302, 512 0.303 -- the bigger the CTA, the more warps march through the 86 kB sub-step body together
 #endif
 #ifndef LLQ16_BAR
