@@ -313,57 +313,68 @@ LLQ_DI void solve_rows(const RowsIn& in) {
   __syncwarp();
   T16_IN(8);
   float* acol = in.acol;
-  const int nrows = 3 * in.nc + in.nl;
+  const int lane0 = in.lane0, nc = in.nc, nl = in.nl;
+  // Coefficient columns: contact c, direction d -> column 3 c + d (0..23); limit row t -> column 24 + t.  Columns the sweep visits
+  // for the partner's sake (its lists are longer) hold zeros, so that those steps change nothing; the loop bounds are rounded up to
+  // even (the sweeps are unrolled by two; the caps are even).
+  const int Ce = (in.Cmax + 1) & ~1, Le = (in.Lmax + 1) & ~1;
   {
     const float* rowtab = in.tb + kLinkTab + kLegTab + kConTab + kLimTab;
+    const int ncon = 3 * nc;
 #pragma unroll 1
-    for (int col = 0; col < in.ncols; col++) {     // columns = the env's rows, in its row order (warp-uniform bound: the longer list)
+    for (int col = 0; col < 3 * Ce; col++) {
       const float a = delassus_entry(r, rowtab + col * kRowW);
-      acol[col * 32] = col < nrows ? a : 0.f;       // (beyond the env's list the table holds old rows: finite, never used)
+      acol[col * 32] = col < ncon ? a : 0.f;        // (beyond the env's list the table holds old rows: finite, masked)
+    }
+    const float* rl = rowtab + ncon * kRowW;
+#pragma unroll 1
+    for (int t = 0; t < Le; t++) {
+      const float a = delassus_entry(r, rl + t * kRowW);
+      acol[(24 + t) * 32] = t < nl ? a : 0.f;
     }
   }
-  const int lane0 = in.lane0, nc = in.nc, nl = in.nl;
   // warm start of the normal rows
 #pragma unroll 1
-  for (int c = 0; c < in.Cmax; c++) {
-    const float v = __shfl_sync(FULL, r.lam, lane0 + 3 * c);
-    r.b = fmaf(acol[96 * c], c < nc ? v : 0.f, r.b);
-  }
+  for (int c = 0; c < in.Cmax; c++) r.b = fmaf(acol[96 * c], __shfl_sync(FULL, r.lam, lane0 + 3 * c), r.b);
   T16_IN(9);
   // projected Gauss-Seidel (btMultiBodyConstraintSolver::solveSingleIteration order).  One row update: candidate on every lane (only
-  // the owner's counts), owner commits, broadcast, one LDS + FMA per lane; the column pointer and the owner lane are induction
-  // variables.  A step beyond the env's own list (the partner's is longer) is masked.
-  float rc = r.lam + r.rhs;                  // lam + rhs, kept up to date off the dependent chain
-#define LLQ16_ROW_UPDATE(src, ap, valid)                                                              \
+  // the owner's counts), owner commits, broadcast, one LDS + FMA per lane.  Dependent chain per row: FFMA (candidate from
+  // c = lam + rhs, kept up to date off the chain) -> 2 FMNMX -> FADD -> SHFL -> FFMA.
+  float rc = r.lam + r.rhs;
+#define LLQ16_ROW_UPDATE(src, a, valid)                                                               \
   {                                                                                                   \
     const float cl = fminf(fmaxf(fmaf(-r.b, r.invd, rc), 0.f), r.hi);   /* clamp the accumulated impulse */ \
     const float dl = cl - r.lam;                                                                      \
     const bool own = lane == (src) && (valid);                                                        \
     r.lam = own ? cl : r.lam;                                                                         \
     rc = own ? cl + r.rhs : rc;                                                                       \
-    const float v = __shfl_sync(FULL, dl, (src));                                                     \
-    r.b = fmaf(*(ap), (valid) ? v : 0.f, r.b);                                                        \
+    r.b = fmaf((a), __shfl_sync(FULL, dl, (src)), r.b);                                               \
   }
 #pragma unroll 1
   for (int it = 0; it < in.iters; it++) {
     {
       int src = lane0 + 3 * nc;
-      const float* ap = acol + 96 * nc;
+      const float* ap = acol + 24 * 32;
 #pragma unroll 1
-      for (int t = 0; t < in.Lmax; t++, src++, ap += 32) LLQ16_ROW_UPDATE(src, ap, t < nl)       // joint-limit rows in joint order
+      for (int t = 0; t < Le; t += 2, src += 2, ap += 64) {     // joint-limit rows in joint order
+        LLQ16_ROW_UPDATE(src, ap[0], t < nl)
+        LLQ16_ROW_UPDATE(src + 1, ap[32], t + 1 < nl)
+      }
     }
     {
       int src = lane0;
       const float* ap = acol;
 #pragma unroll 1
-      for (int t = 0; t < in.Cmax; t++, src += 3, ap += 96) LLQ16_ROW_UPDATE(src, ap, t < nc)    // normal rows in contact order
+      for (int t = 0; t < Ce; t += 2, src += 6, ap += 192) {    // normal rows in contact order
+        LLQ16_ROW_UPDATE(src, ap[0], t < nc)
+        LLQ16_ROW_UPDATE(src + 3, ap[96], t + 1 < nc)
+      }
     }
     {
       int src = lane0;
       const float* ap = acol;
 #pragma unroll 1
       for (int t = 0; t < in.Cmax; t++, src += 3, ap += 96) {   // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
-        const bool valid = t < nc;
         const float sown = fmaf(-r.b, r.invd, rc);
         const float sa = __shfl_sync(FULL, sown, src + 1), sb = __shfl_sync(FULL, sown, src + 2);
         const float limit = r.mu * __shfl_sync(FULL, r.lam, src);
@@ -372,11 +383,10 @@ LLQ_DI void solve_rows(const RowsIn& in) {
         const float sc = clip ? limit * rsqrtf(r2) : 1.0f;
         const float snew = clip ? sown * sc : sown;
         const float dl = snew - r.lam;
-        const bool own = (unsigned)(lane - src - 1) < 2u && valid;
+        const bool own = (unsigned)(lane - src - 1) < 2u && t < nc;
         r.lam = own ? snew : r.lam;
         rc = own ? snew + r.rhs : rc;
-        const float da = __shfl_sync(FULL, dl, src + 1), db = __shfl_sync(FULL, dl, src + 2);
-        r.b = fmaf(ap[32], valid ? da : 0.f, fmaf(ap[64], valid ? db : 0.f, r.b));
+        r.b = fmaf(ap[32], __shfl_sync(FULL, dl, src + 1), fmaf(ap[64], __shfl_sync(FULL, dl, src + 2), r.b));
       }
     }
   }
