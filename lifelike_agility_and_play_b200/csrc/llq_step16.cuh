@@ -341,9 +341,11 @@ LLQ_DI void solve_rows(const RowsIn& in) {
   // the owner's counts), owner commits, broadcast, one LDS + FMA per lane.  Dependent chain per row: FFMA (candidate from
   // c = lam + rhs, kept up to date off the chain) -> 2 FMNMX -> FADD -> SHFL -> FFMA.
   float rc = r.lam + r.rhs;
-#define LLQ16_ROW_UPDATE(src, a, valid)                                                               \
+#define LLQ16_CLAMP_LIMIT(x) fminf(fmaxf((x), 0.f), r.hi)      /* joint-limit rows: [0, max impulse] */
+#define LLQ16_CLAMP_NORMAL(x) fmaxf((x), 0.f)                  /* normal rows: [0, 1e10] -- the upper bound never binds a finite state */
+#define LLQ16_ROW_UPDATE(src, a, valid, CLAMP)                                                        \
   {                                                                                                   \
-    const float cl = fminf(fmaxf(fmaf(-r.b, r.invd, rc), 0.f), r.hi);   /* clamp the accumulated impulse */ \
+    const float cl = CLAMP(fmaf(-r.b, r.invd, rc));      /* clamp the accumulated impulse */           \
     const float dl = cl - r.lam;                                                                      \
     const bool own = lane == (src) && (valid);                                                        \
     r.lam = own ? cl : r.lam;                                                                         \
@@ -357,8 +359,8 @@ LLQ_DI void solve_rows(const RowsIn& in) {
       const float* ap = acol + 24 * 32;
 #pragma unroll 1
       for (int t = 0; t < Le; t += 2, src += 2, ap += 64) {     // joint-limit rows in joint order
-        LLQ16_ROW_UPDATE(src, ap[0], t < nl)
-        LLQ16_ROW_UPDATE(src + 1, ap[32], t + 1 < nl)
+        LLQ16_ROW_UPDATE(src, ap[0], t < nl, LLQ16_CLAMP_LIMIT)
+        LLQ16_ROW_UPDATE(src + 1, ap[32], t + 1 < nl, LLQ16_CLAMP_LIMIT)
       }
     }
     {
@@ -366,8 +368,8 @@ LLQ_DI void solve_rows(const RowsIn& in) {
       const float* ap = acol;
 #pragma unroll 1
       for (int t = 0; t < Ce; t += 2, src += 6, ap += 192) {    // normal rows in contact order
-        LLQ16_ROW_UPDATE(src, ap[0], t < nc)
-        LLQ16_ROW_UPDATE(src + 3, ap[96], t + 1 < nc)
+        LLQ16_ROW_UPDATE(src, ap[0], t < nc, LLQ16_CLAMP_NORMAL)
+        LLQ16_ROW_UPDATE(src + 3, ap[96], t + 1 < nc, LLQ16_CLAMP_NORMAL)
       }
     }
     {
@@ -379,9 +381,9 @@ LLQ_DI void solve_rows(const RowsIn& in) {
         const float sa = __shfl_sync(FULL, sown, src + 1), sb = __shfl_sync(FULL, sown, src + 2);
         const float limit = r.mu * __shfl_sync(FULL, r.lam, src);
         const float r2 = sa * sa + sb * sb;
+        const float rs = rsqrtf(r2);                           // issued before the comparison resolves (inf for r2 = 0: not selected)
         const bool clip = r2 >= limit * limit && r2 > 0.f;
-        const float sc = clip ? limit * rsqrtf(r2) : 1.0f;
-        const float snew = clip ? sown * sc : sown;
+        const float snew = clip ? sown * (limit * rs) : sown;
         const float dl = snew - r.lam;
         const bool own = (unsigned)(lane - src - 1) < 2u && t < nc;
         r.lam = own ? snew : r.lam;
@@ -391,6 +393,8 @@ LLQ_DI void solve_rows(const RowsIn& in) {
     }
   }
 #undef LLQ16_ROW_UPDATE
+#undef LLQ16_CLAMP_LIMIT
+#undef LLQ16_CLAMP_NORMAL
   T16_IN(10);
   // the normal impulses go back to the contact records (warm start of the next sub-step)
   if (is_normal) in.tb[kLinkTab + kLegTab + (in.rr / 3) * kConW + 17] = r.lam;
