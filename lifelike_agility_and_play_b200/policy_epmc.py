@@ -15,7 +15,9 @@ llc_light, discrete_z, expert_lstm, lstm_layer_norm, append_hist_a, rms on the p
 
 The LSTM comes from `tpolicies` (TLeague's policy library, absent from the reference tree): restated from its published form --
 `z = ln(x wx) + ln(h wh) + b`, gates `i, f, o, u`, `f = sigmoid(f + forget_bias)`, `h = o tanh(ln(c))`, state `[c, h]`, both zeroed
-where the mask (episode start) is set -- with the variable order of the shipped files (wx, wh, b, gx, bx, gh, bh, gc, bc).  Nothing pins
+where the mask (episode start) is set -- with the variable order of the shipped files: wx, wh, b, then (beta, gamma) of the three layer
+norms (x, h, c), as `tf.contrib.layers.layer_norm` creates them; the three additive vectors carry identical values in the shipped
+files (same initialiser, same gradient), the two 128-vectors and the 32-vector with means 2.2 / 1.1 / 3.6 are the gains.  Nothing pins
 this restatement bit for bit (no TensorFlow here); it is pinned behaviourally: the shipped Bullet-trained weights have to traverse the
 corridors on the engine.
 
@@ -64,7 +66,7 @@ def _conv1d_strided(x, w, b, stride):
     return np.maximum(out + b, 0.0)
 
 
-def _ln(x, g, b, eps=1e-5):
+def _ln(x, g, b, eps=1e-12):        # tf.contrib.layers.layer_norm: last axis, variance_epsilon 1e-12
     m = x.mean(1, keepdims=True)
     v = ((x - m) ** 2).mean(1, keepdims=True)
     return (x - m) / np.sqrt(v + eps) * g + b
@@ -76,7 +78,7 @@ def _sigmoid(x):
 
 class LnLstm:
     def __init__(self, w, forget_bias=1.0):
-        self.wx, self.wh, self.b, self.gx, self.bx, self.gh, self.bh, self.gc, self.bc = w
+        self.wx, self.wh, self.b, self.bx, self.gx, self.bh, self.gh, self.bc, self.gc = w
         self.nh = self.wh.shape[0]
         self.forget_bias = forget_bias
 

@@ -39,8 +39,22 @@ class _U(pickle.Unpickler):
 
 
 def load(path):
-    with open(path, "rb") as f:
-        return _U(f).load()
+    try:
+        with open(path, "rb") as f:
+            return _U(f).load()
+    except pickle.UnpicklingError:
+        # joblib.dump with numpy arrays stored raw after the pickle opcodes (environmental_level_hole.model)
+        import inspect
+        from joblib import numpy_pickle
+
+        class _J(numpy_pickle.NumpyUnpickler):
+            def find_class(self, module, name):
+                if module.startswith("numpy") or module.startswith("joblib") or module in ("builtins", "collections", "_codecs", "copyreg"):
+                    return super().find_class(module, name)
+                return _U.find_class(self, module, name)
+        with open(path, "rb") as f:
+            kw = {"ensure_native_byte_order": False} if "ensure_native_byte_order" in inspect.signature(numpy_pickle.NumpyUnpickler.__init__).parameters else {}
+            return _J(path, f, **kw).load()
 
 
 def walk(o, depth=0, name="root", out=None):
