@@ -1,0 +1,69 @@
+"""Host restatement of the environmental-level policy (lifelike_agility_and_play_b200/policy_epmc.py; epmc_net.py:86-177): layer shapes of
+the shipped files, TF 'SAME' convolutions against a brute-force evaluation, LSTM state handling.  The behavioural pin with the shipped
+weights is tools/statistical_pin_epmc.py."""
+import numpy as np
+
+from lifelike_agility_and_play_b200.policy_epmc import EpmcPolicy, _same_pad, conv1d_same_relu, conv2d_same_relu
+
+ENC = [(1, 1, 1, 4), (4,), (4, 4, 4, 4), (4,), (2, 2, 4, 4), (4,), (2, 2, 4, 1), (1,), (4, 1, 4), (4,), (4, 4, 4), (4,), (4, 4, 4), (4,), (4, 4, 1), (1,),
+       (1, 1, 1, 4), (4,), (4, 4, 4, 4), (4,), (2, 2, 4, 4), (4,), (2, 2, 4, 1), (1,), (3, 32), (32,), (120, 64), (64,)]
+LSTM = [(256, 128), (32, 128), (128,), (128,), (128,), (128,), (128,), (32,), (32,)]
+SHAPES = ([(1, 135), (1, 135), (135, 128), (128,)] + ENC + [(64, 128), (128,), (256, 256), (256,)] + LSTM + [(32, 1), (1,)] +
+          [(135, 64), (64,)] + ENC + [(128, 256), (256,)] + LSTM + [(32, 256), (256,), (32, 256)] +
+          [(135, 64), (64,), (32, 32), (32,), (96, 256), (256,), (256, 256), (256,), (256, 12), (12,), (1, 12)])
+
+
+def random_weights(seed=0):
+    rng = np.random.default_rng(seed)
+    w = [(rng.standard_normal(s) / np.sqrt(max(1, int(np.prod(s[:-1]))))).astype(np.float32) for s in SHAPES]
+    w[1] = np.abs(w[1]) + 0.2
+    return w
+
+
+def test_shipped_layout_has_102_arrays():
+    assert len(SHAPES) == 102
+
+
+def test_same_convolutions_match_brute_force():
+    rng = np.random.default_rng(3)
+    for (H, W, k, s) in ((25, 13, 4, 2), (13, 7, 2, 2), (7, 4, 2, 1), (25, 13, 1, 1)):
+        x = rng.standard_normal((2, H, W, 3)).astype(np.float32)
+        w = rng.standard_normal((k, k, 3, 2)).astype(np.float32); b = rng.standard_normal(2).astype(np.float32)
+        got = conv2d_same_relu(x, w, b, s)
+        oh, pt, _ = _same_pad(H, k, s); ow, pl, _ = _same_pad(W, k, s)
+        assert got.shape == (2, oh, ow, 2)
+        ref = np.zeros_like(got)
+        for n in range(2):
+            for i in range(oh):
+                for j in range(ow):
+                    acc = b.copy()
+                    for di in range(k):
+                        for dj in range(k):
+                            y, xx = i * s + di - pt, j * s + dj - pl
+                            if 0 <= y < H and 0 <= xx < W:
+                                acc = acc + x[n, y, xx] @ w[di, dj]
+                    ref[n, i, j] = np.maximum(acc, 0)
+        assert np.abs(got - ref).max() < 1e-4
+    x = rng.standard_normal((2, 136, 1)).astype(np.float32)
+    w = rng.standard_normal((4, 1, 4)).astype(np.float32)
+    assert conv1d_same_relu(x, w, np.zeros(4, np.float32), 1).shape == (2, 136, 4)
+    assert conv1d_same_relu(x[:, :128].repeat(4, 2), rng.standard_normal((4, 4, 4)).astype(np.float32), np.zeros(4, np.float32), 2).shape == (2, 64, 4)
+
+
+def test_policy_structure_and_state():
+    pol = EpmcPolicy(random_weights())
+    rng = np.random.default_rng(1)
+    obs = rng.standard_normal((6, 916)).astype(np.float32)
+    s0 = pol.initial_state(6)
+    a, s1, code = pol.act(obs, s0, np.ones(6, np.float32), return_code=True)
+    assert a.shape == (6, 12) and s1.shape == (6, 64) and code.min() >= 0 and code.max() < 256 and np.isfinite(a).all()
+    # the state matters, and the episode-start mask wipes it
+    a2, s2 = pol.act(obs, s1, np.zeros(6, np.float32))
+    a3, s3 = pol.act(obs, s1, np.ones(6, np.float32))
+    assert not np.allclose(s2, s1) and np.allclose(s3, s1, atol=1e-6) and np.allclose(a3, a, atol=1e-6)
+    # batch independence
+    a4, s4 = pol.act(obs[2:3], s0[2:3], np.ones(1, np.float32))
+    assert np.allclose(a4, a[2:3], atol=1e-5) and np.allclose(s4, s1[2:3], atol=1e-5)
+    # only the proprioception is normalised and clipped
+    big = obs.copy(); big[:, :135] = 1e6
+    assert np.isfinite(pol.act(big, s0, np.ones(6, np.float32))[0]).all()
