@@ -29,7 +29,7 @@ for n in (5, 70):
         e.step((0.4 * rng.standard_normal((n, 12))).astype(np.float32))
     e.close()
     # corridor arena (boxes, auxiliary edge cylinders, candidate staging) and the chase-tag pair game; large actions make robots fall
-    # over, which takes the warp through the two-slot solver (more than 4 contacts / limit rows)
+    # over: envs with more than 16 rows borrow their partner's lanes, CTAs full of them run the solver in two passes
     erc3 = dict(erc, element_id=3, auxiliary_radius=0.02)
     e = capi.VecEngine(lib, n, blob, None, seed=2, auto_reset=1, **epmc_engine_config(50.0, 50.0, 0.5, 16, 30, erc3))
     e.set_init_state(INIT_STATE_RUN_0)
