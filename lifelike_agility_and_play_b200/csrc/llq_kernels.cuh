@@ -361,16 +361,35 @@ LLQ_DI unsigned long long box_mask(const float* boxes, int nb, int k, float px, 
   lo |= __shfl_xor_sync(FULL, lo, 2); hi |= __shfl_xor_sync(FULL, hi, 2);
   return ((unsigned long long)hi << 32) | lo;
 }
-// closest hit fraction against the ground slab and the boxes selected by `mask`
+// closest hit fraction against the ground slab and the boxes selected by `mask`.  A box whose bounds lie clear (by more than 0.1 mm:
+// grazing cases stay with the slab test) of the segment's own bounds cannot be hit and is skipped before the slab test.
 LLQ_DI float ray_boxlist(V3 o, V3 d, const float* boxes, unsigned long long mask) {
   float best = ray_box1(o, d, V3{-100.f, -100.f, -10.f}, V3{100.f, 100.f, 0.f}, -1.f);
+  const float ex = o.x + d.x, ey = o.y + d.y, ez = o.z + d.z;
+  const float x0 = fminf(o.x, ex) - 1e-4f, x1 = fmaxf(o.x, ex) + 1e-4f, y0 = fminf(o.y, ey) - 1e-4f, y1 = fmaxf(o.y, ey) + 1e-4f;
+  const float z0 = fminf(o.z, ez) - 1e-4f, z1 = fmaxf(o.z, ez) + 1e-4f;
   while (mask) {
     const int j = __ffsll((long long)mask) - 1;
     mask &= mask - 1;
     const float* b = boxes + 6 * j;
-    best = ray_box1(o, d, V3{b[0] - b[3], b[1] - b[4], b[2] - b[5]}, V3{b[0] + b[3], b[1] + b[4], b[2] + b[5]}, best);
+    const V3 lo = V3{b[0] - b[3], b[1] - b[4], b[2] - b[5]}, hi = V3{b[0] + b[3], b[1] + b[4], b[2] + b[5]};
+    if (lo.x > x1 || hi.x < x0 || lo.y > y1 || hi.y < y0 || lo.z > z1 || hi.z < z0) continue;
+    best = ray_box1(o, d, lo, hi, best);
   }
   return best;
+}
+// a vertical ray from z = 10 down to z = -10 at (x, y): the z of what it hits first = the highest top among the ground slab and the
+// selected boxes whose footprint holds (x, y) (same inclusive bounds as the slab test); < 0: nothing (off the slab)
+LLQ_DI float down_ray_top(float x, float y, const float* boxes, unsigned long long mask) {
+  float top = (x < -100.f || x > 100.f || y < -100.f || y > 100.f) ? -1.f : 0.f;
+  while (mask) {
+    const int j = __ffsll((long long)mask) - 1;
+    mask &= mask - 1;
+    const float* b = boxes + 6 * j;
+    const bool out = x < b[0] - b[3] || x > b[0] + b[3] || y < b[1] - b[4] || y > b[1] + b[4];
+    if (!out) top = fmaxf(top, b[2] + b[5]);
+  }
+  return top;
 }
 struct TerrainRng {
   unsigned long long seed; long long gid, ep; int k; double u[4];
@@ -540,9 +559,7 @@ LLQ_DI void emit_obs_rows(float* obs, float* obs2, long long obs2_ld, const floa
           const int t = j - 135, a = t / 13, b = t - a * 13;
           const float gx = a == 24 ? 1.2f : -1.2f + (float)a * (2.4f / 24.0f), gy = b == 12 ? 0.6f : -0.6f + (float)b * (1.2f / 12.0f);
           const float x = fmaf(sn[45], gx, fmaf(sn[46], gy, pos.x)), y = fmaf(sn[48], gx, fmaf(sn[49], gy, pos.y));
-          const float f = ray_boxlist(V3{x, y, 10.f}, V3{0.f, 0.f, -20.f}, bxs, m);
-          v = f < 0.f ? 0.f : fmaf(f, -20.f, 10.f);
-          if (f >= 0.f && fabsf(v) < 2e-6f) v = 0.f;
+          v = fmaxf(down_ray_top(x, y, bxs, m), 0.f);          // hit z of the down ray (0 when it misses everything)
         } else if (j < 588) {
           const unsigned long long m = ((unsigned long long)__float_as_uint(sn[67]) << 32) | __float_as_uint(sn[66]);
           const float ang = sn[61] + 6.283185307179586f * (float)(j - 460) * (1.0f / 128.0f);
