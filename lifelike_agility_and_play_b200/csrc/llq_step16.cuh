@@ -377,18 +377,21 @@ LLQ_DI void solve_rows(const RowsIn& in) {
       const float* ap = acol;
 #pragma unroll 1
       for (int t = 0; t < in.Cmax; t++, src += 3, ap += 96) {   // friction pairs with the implicit cone (resolveConeFrictionConstraintRows)
+        // One shuffle round trip on the dependent chain: the two tangent rows' candidates go to every lane together with their current
+        // impulses and the cone's radius (those three do not depend on this step's b), and every lane forms both increments itself.
         const float sown = fmaf(-r.b, r.invd, rc);
         const float sa = __shfl_sync(FULL, sown, src + 1), sb = __shfl_sync(FULL, sown, src + 2);
-        const float limit = r.mu * __shfl_sync(FULL, r.lam, src);
+        const float la = __shfl_sync(FULL, r.lam, src + 1), lb = __shfl_sync(FULL, r.lam, src + 2);
+        const float limit = __shfl_sync(FULL, r.mu * r.lam, src);
         const float r2 = sa * sa + sb * sb;
         const float rs = rsqrtf(r2);                           // issued before the comparison resolves (inf for r2 = 0: not selected)
         const bool clip = r2 >= limit * limit && r2 > 0.f;
-        const float snew = clip ? sown * (limit * rs) : sown;
-        const float dl = snew - r.lam;
-        const bool own = (unsigned)(lane - src - 1) < 2u && t < nc;
-        r.lam = own ? snew : r.lam;
-        rc = own ? snew + r.rhs : rc;
-        r.b = fmaf(ap[32], __shfl_sync(FULL, dl, src + 1), fmaf(ap[64], __shfl_sync(FULL, dl, src + 2), r.b));
+        const float sc = limit * rs;
+        const float na = clip ? sa * sc : sa, nb = clip ? sb * sc : sb;
+        const bool valid = t < nc;
+        if (lane == src + 1 && valid) { r.lam = na; rc = na + r.rhs; }
+        if (lane == src + 2 && valid) { r.lam = nb; rc = nb + r.rhs; }
+        r.b = fmaf(ap[32], na - la, fmaf(ap[64], nb - lb, r.b));
       }
     }
   }
