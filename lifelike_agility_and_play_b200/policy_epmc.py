@@ -95,9 +95,14 @@ class LnLstm:
 
 class CommandEncoder:
     def __init__(self, w):
-        """w = the 28 arrays of one `usr_cmd_encoder` in creation order: percep_2d (8), percep_1d (8), percep_front (8), target (2), fc (2)."""
+        """w = the arrays of one `usr_cmd_encoder` in creation order: percep_2d (8), percep_1d (8), percep_front (8), [vector feature
+        (2),] fc (2) -- 28 with the vector feature (the target direction), 26 without (sepmc_net.py:149-173 before `target_info` exists)."""
         self.c2d, self.c1d, self.cfr = w[0:8], w[8:16], w[16:24]
-        self.wt, self.bt, self.wf, self.bf = w[24], w[25], w[26], w[27]
+        if len(w) == 28:
+            self.wt, self.bt, self.wf, self.bf = w[24], w[25], w[26], w[27]
+        else:
+            assert len(w) == 26
+            self.wt, self.bt, self.wf, self.bf = None, None, w[24], w[25]
 
     @staticmethod
     def _enc2d(x, w):
@@ -117,9 +122,11 @@ class CommandEncoder:
         e = conv1d_same_relu(e, w[6], w[7], 1)
         return e.reshape(e.shape[0], -1)
 
-    def __call__(self, percep_2d, percep_1d, percep_front, target):
-        t = np.maximum(target @ self.wt + self.bt, 0.0)
-        e = np.concatenate([t, self._enc2d(percep_2d, self.c2d), self._enc1d(percep_1d, self.c1d), self._enc2d(percep_front, self.cfr)], axis=1)
+    def __call__(self, percep_2d, percep_1d, percep_front, target=None):
+        parts = [self._enc2d(percep_2d, self.c2d), self._enc1d(percep_1d, self.c1d), self._enc2d(percep_front, self.cfr)]
+        if self.wt is not None:
+            parts = [np.maximum(target @ self.wt + self.bt, 0.0)] + parts
+        e = np.concatenate(parts, axis=1)
         return np.maximum(e @ self.wf + self.bf, 0.0)
 
 
@@ -172,3 +179,53 @@ class EpmcPolicy:
         x = np.maximum(x @ self.dec[1][0] + self.dec[1][1], 0.0)
         act = (x @ self.dec[2][0] + self.dec[2][1]).astype(np.float32)
         return (act, state, code) if return_code else (act, state)
+
+
+class SepmcPolicy:
+    """Deterministic inference of the shipped strategic-level policy (networks/legged_robot/sepmc_net/sepmc_net.py, actor configuration
+    of test_scripts/strategic_level/test_strategic_level_env.py:44-75) on [N, 965] engine observations: `hlc_encoder` (sepmc_net.py:122-146:
+    prop 135 -> 64 | perception 88 -> 64 | game vector 29 -> 64 -> 64, concat 192 -> 256 -> LSTM(32) -> heading angle, clipped to +-pi),
+    whose (cos, sin) joins the commanded speed as the `target_info` of the environmental-level encoder (`mlc_encoder`, :176-203) -> 256-way
+    code -> the frozen primitive-level decoder.  `weights` = the 152 arrays of ``strategic_level.model``:
+    0-1 rms | 2-50 value tower | 51-96 heading controller | 97-139 code controller | 140 codebook | 141-150 decoder | 151 logstd."""
+
+    def __init__(self, weights):
+        w = [np.asarray(a, np.float32) for a in weights]
+        assert len(w) == 152 and w[83].shape == (192, 256) and w[140].shape == (32, 256), "not a strategic-level model"
+        self.mean, self.std = w[0], w[1]
+        self.h_prop, self.h_percept = (w[51], w[52]), CommandEncoder(w[53:79])
+        self.h_vec = [(w[79], w[80]), (w[81], w[82])]
+        self.h_embed, self.h_lstm, self.h_mu = (w[83], w[84]), LnLstm(w[85:94]), (w[94], w[95])
+        self.m_prop, self.m_cmd, self.m_embed = (w[97], w[98]), CommandEncoder(w[99:127]), (w[127], w[128])
+        self.m_lstm, self.logits = LnLstm(w[129:138]), (w[138], w[139])
+        self.codebook = w[140]
+        self.llc_prop, self.llc_z = (w[141], w[142]), (w[143], w[144])
+        self.dec = [(w[145], w[146]), (w[147], w[148]), (w[149], w[150])]
+        self.nh = 32
+
+    def initial_state(self, n):
+        return np.zeros((n, 4 * self.nh), np.float32)          # [c, h] of the heading LSTM, then of the code LSTM
+
+    def act(self, obs, state, mask, return_aux=False):
+        o = np.asarray(obs, np.float32)
+        prop, p2d, p1d, pfr = o[:, 0:135], o[:, 135:460].reshape(-1, 25, 13), o[:, 460:588], o[:, 588:913].reshape(-1, 25, 13)
+        game = np.concatenate([o[:, 913:918], o[:, 918:933], o[:, 948:955], o[:, 962:964]], axis=1)      # percept_vec | oppo_info | flag_info | with_flag
+        spd = o[:, 964:965]
+        mask = np.asarray(mask, np.float32)
+        p = np.clip((prop - self.mean) / (self.std + 1e-8), -5.0, 5.0)
+        relu = lambda x: np.maximum(x, 0.0)
+        ge = relu(relu(game @ self.h_vec[0][0] + self.h_vec[0][1]) @ self.h_vec[1][0] + self.h_vec[1][1])
+        e = relu(np.concatenate([relu(p @ self.h_prop[0] + self.h_prop[1]), self.h_percept(p2d, p1d, pfr), ge], axis=1) @ self.h_embed[0] + self.h_embed[1])
+        hh, s_h = self.h_lstm.step(e, state[:, :2 * self.nh], mask)
+        ang = np.clip(hh @ self.h_mu[0] + self.h_mu[1], -np.pi, np.pi)
+        tgt = np.concatenate([np.cos(ang), np.sin(ang), spd], axis=1).astype(np.float32)
+        e2 = relu(np.concatenate([relu(p @ self.m_prop[0] + self.m_prop[1]), self.m_cmd(p2d, p1d, pfr, tgt)], axis=1) @ self.m_embed[0] + self.m_embed[1])
+        hm, s_m = self.m_lstm.step(e2, state[:, 2 * self.nh:], mask)
+        code = (hm @ self.logits[0] + self.logits[1]).argmax(1)
+        z = self.codebook.T[code]
+        x = np.concatenate([relu(p @ self.llc_prop[0] + self.llc_prop[1]), relu(z @ self.llc_z[0] + self.llc_z[1])], axis=1)
+        x = relu(x @ self.dec[0][0] + self.dec[0][1])
+        x = relu(x @ self.dec[1][0] + self.dec[1][1])
+        act = (x @ self.dec[2][0] + self.dec[2][1]).astype(np.float32)
+        new_state = np.concatenate([s_h, s_m], axis=1)
+        return (act, new_state, ang[:, 0], code) if return_aux else (act, new_state)

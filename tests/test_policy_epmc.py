@@ -67,3 +67,30 @@ def test_policy_structure_and_state():
     # only the proprioception is normalised and clipped
     big = obs.copy(); big[:, :135] = 1e6
     assert np.isfinite(pol.act(big, s0, np.ones(6, np.float32))[0]).all()
+
+
+ENC26 = ENC[:24] + [(88, 64), (64,)]
+SEPMC_SHAPES = ([(1, 135), (1, 135), (135, 128), (128,)] + ENC26 + [(64, 128), (128,), (29, 64), (64,), (64, 64), (64,), (64, 128), (128,), (384, 256), (256,)] +
+                LSTM + [(32, 1), (1,)] +
+                [(135, 64), (64,)] + ENC26 + [(29, 64), (64,), (64, 64), (64,), (192, 256), (256,)] + LSTM + [(32, 1), (1,), (1, 1)] +
+                [(135, 64), (64,)] + ENC + [(128, 256), (256,)] + LSTM + [(32, 256), (256,), (32, 256)] +
+                [(135, 64), (64,), (32, 32), (32,), (96, 256), (256,), (256, 256), (256,), (256, 12), (12,), (1, 12)])
+
+
+def test_strategic_policy_structure_and_state():
+    from lifelike_agility_and_play_b200.policy_epmc import SepmcPolicy
+    assert len(SEPMC_SHAPES) == 152
+    rng = np.random.default_rng(5)
+    w = [(rng.standard_normal(s) / np.sqrt(max(1, int(np.prod(s[:-1]))))).astype(np.float32) for s in SEPMC_SHAPES]
+    w[1] = np.abs(w[1]) + 0.2
+    pol = SepmcPolicy(w)
+    obs = rng.standard_normal((4, 965)).astype(np.float32)
+    s0 = pol.initial_state(4)
+    a, s1, ang, code = pol.act(obs, s0, np.ones(4, np.float32), return_aux=True)
+    assert a.shape == (4, 12) and s1.shape == (4, 128) and np.all(np.abs(ang) <= np.pi) and code.max() < 256 and np.isfinite(a).all()
+    a2, s2 = pol.act(obs, s1, np.zeros(4, np.float32))
+    a3, s3 = pol.act(obs, s1, np.ones(4, np.float32))
+    assert not np.allclose(s2, s1) and np.allclose(s3, s1, atol=1e-6) and np.allclose(a3, a, atol=1e-6)
+    # the game vector (opponent / flag) reaches the action only through the heading: the cheat copies of it (value tower inputs) do not
+    o2 = obs.copy(); o2[:, 933:948] += 5.0; o2[:, 955:962] -= 3.0
+    assert np.allclose(pol.act(o2, s0, np.ones(4, np.float32))[0], a, atol=1e-6)
