@@ -49,6 +49,31 @@ int llq_policy_forward_rec(llq_policy_handle h, const float* d_obs, int64_t obs_
                            float* d_values, float* d_neglogp, int64_t out_ld, uint64_t seed, uint64_t counter, int64_t row_gid0, void* stream);
 const char* llq_policy_last_error(void);
 
+/* ---- environmental- and strategic-level policies (csrc/llq_policy_hier.cu): conv encoders + layer-norm LSTMs + the frozen
+ * primitive-level decoder, one CTA per observation row, fp32 on the CUDA cores.  Replaces `PGAgent.step(obs, argmax=True)` of
+ * test_scripts/environmental_level/test_environmental_level_env.py:95-100 and test_scripts/strategic_level/test_strategic_level_env.py:96
+ * (mean heading, argmax code, mean action) for a whole batch of envs; nets: networks/legged_robot/epmc_net/epmc_net.py:86-177,
+ * networks/legged_robot/sepmc_net/sepmc_net.py:122-203, networks/legged_robot/pmc_net/pmc_net.py:99-112.
+ * `weights`: all arrays of the shipped *.model file, fp32, concatenated; `offsets[role]`: start of the array that plays `role`
+ * (the host-side table is lifelike_agility_and_play_b200/policy_epmc.py::hier_role_arrays):
+ *   0 prop mean, 1 prop std | code controller: 2-3 prop embed W b, 4-31 usr_cmd_encoder (2-D map 8, lidar 8, front map 8, target fc 2,
+ *   fusion fc 2), 32-33 embed, 34-42 LSTM (wx wh b beta_x gamma_x beta_h gamma_h beta_c gamma_c), 43-44 logits, 45 codebook,
+ *   46-55 low-level controller | heading controller (strategic level only): 56-57 prop embed, 58-83 perception encoder (24 + fusion fc 2),
+ *   84-87 game-vector fc x 2, 88-89 embed, 90-98 LSTM, 99-100 heading fc. */
+#define LLQ_HIER_ROLES_MLC 56
+#define LLQ_HIER_ROLES_ALL 101
+typedef struct llq_hier_policy* llq_hier_policy_handle;
+int llq_hier_policy_create(const float* weights, int64_t n_weights, const int32_t* offsets, int32_t n_roles, int32_t strategic, int32_t device,
+                           llq_hier_policy_handle* out);
+int llq_hier_policy_destroy(llq_hier_policy_handle h);
+/* d_actions[n,12] = mean action for d_obs[n, >= 916 (environmental) / 965 (strategic)] (device pointers, obs_ld = row stride in floats).
+ * d_state [n, 64 / 128] floats: the LSTM states ([c, h] of the heading LSTM first at the strategic level), updated in place; rows whose
+ * d_done[i] != 0 (uint8, nullable: the done flags of the step that produced these observations) start from a zero state.
+ * d_codes (int32[n]) / d_heading (float[n], strategic level) are optional outputs.  Asynchronous on `stream`. */
+int llq_hier_policy_forward(llq_hier_policy_handle h, const float* d_obs, int64_t obs_ld, int32_t n, const uint8_t* d_done, float* d_state,
+                            float* d_actions, int32_t* d_codes, float* d_heading, void* stream);
+const char* llq_hier_policy_last_error(void);
+
 #ifdef __cplusplus
 }
 #endif

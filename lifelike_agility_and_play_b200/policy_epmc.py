@@ -229,3 +229,53 @@ class SepmcPolicy:
         act = (x @ self.dec[2][0] + self.dec[2][1]).astype(np.float32)
         new_state = np.concatenate([s_h, s_m], axis=1)
         return (act, new_state, ang[:, 0], code) if return_aux else (act, new_state)
+
+
+# ---------------------------------------------------------------------------------------------------------------- device side
+def hier_role_arrays(strategic):
+    """Index (in the shipped file's array list) of the array that plays each role of include/llq_policy.h."""
+    if not strategic:
+        return [0, 1, 47, 48] + list(range(49, 77)) + [77, 78] + list(range(79, 88)) + [88, 89, 90] + list(range(91, 101))
+    mlc = [0, 1, 97, 98] + list(range(99, 127)) + [127, 128] + list(range(129, 138)) + [138, 139, 140] + list(range(141, 151))
+    hlc = [51, 52] + list(range(53, 79)) + [79, 80, 81, 82] + [83, 84] + list(range(85, 94)) + [94, 95]
+    return mlc + hlc
+
+
+class DeviceHierPolicy:
+    """The environmental- / strategic-level policy on the GPU (csrc/llq_policy_hier.cu through include/llq_policy.h): reads the engine's
+    observation rows in place, keeps the LSTM states on the device, writes the actions the fused env step consumes."""
+
+    def __init__(self, weights, device=0):
+        import ctypes as C
+        from .policy import POLICY_LIB_PATH
+        import os
+        if not os.path.exists(POLICY_LIB_PATH):
+            raise RuntimeError("%s is not built (python -c 'import __graft_entry__ as g; g.build()'); there is no CPU fallback" % POLICY_LIB_PATH)
+        self._C, self.lib = C, C.CDLL(POLICY_LIB_PATH)
+        w = [np.ascontiguousarray(a, np.float32).reshape(-1) for a in weights]
+        self.strategic = len(w) == 152
+        assert len(w) in (102, 152), "expected an environmental-level (102 arrays) or a strategic-level (152 arrays) model"
+        starts = np.concatenate([[0], np.cumsum([a.size for a in w])]).astype(np.int64)
+        blob = np.concatenate(w)
+        off = np.array([starts[i] for i in hier_role_arrays(self.strategic)], np.int32)
+        self.lib.llq_hier_policy_last_error.restype = C.c_char_p
+        h = C.c_void_p()
+        rc = self.lib.llq_hier_policy_create(blob.ctypes.data_as(C.c_void_p), C.c_int64(blob.size), off.ctypes.data_as(C.c_void_p), C.c_int32(off.size),
+                                             C.c_int32(int(self.strategic)), C.c_int32(device), C.byref(h))
+        if rc:
+            raise RuntimeError("llq_hier_policy_create: %s" % self.lib.llq_hier_policy_last_error().decode())
+        self._h = h
+        self.state_dim = 128 if self.strategic else 64
+        self.obs_dim = 965 if self.strategic else 916
+
+    def forward(self, obs_ptr, obs_ld, n, done_ptr, state_ptr, act_ptr, codes_ptr=None, heading_ptr=None, stream=None):
+        C = self._C
+        rc = self.lib.llq_hier_policy_forward(self._h, C.c_void_p(obs_ptr), C.c_int64(obs_ld), C.c_int32(n), C.c_void_p(done_ptr or 0), C.c_void_p(state_ptr),
+                                              C.c_void_p(act_ptr), C.c_void_p(codes_ptr or 0), C.c_void_p(heading_ptr or 0), C.c_void_p(stream or 0))
+        if rc:
+            raise RuntimeError("llq_hier_policy_forward: %s" % self.lib.llq_hier_policy_last_error().decode())
+
+    def close(self):
+        if self._h:
+            self.lib.llq_hier_policy_destroy(self._h)
+            self._h = None

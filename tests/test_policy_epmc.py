@@ -94,3 +94,49 @@ def test_strategic_policy_structure_and_state():
     # the game vector (opponent / flag) reaches the action only through the heading: the cheat copies of it (value tower inputs) do not
     o2 = obs.copy(); o2[:, 933:948] += 5.0; o2[:, 955:962] -= 3.0
     assert np.allclose(pol.act(o2, s0, np.ones(4, np.float32))[0], a, atol=1e-6)
+
+
+import pytest  # noqa: E402
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("strategic", [False, True])
+def test_device_hierarchical_policy_matches_host(strategic):
+    """csrc/llq_policy_hier.cu against the numpy statement of the same nets, random weights, three recurrent steps with episode starts in
+    between: LSTM states to 1e-4, the same code for (almost) every row, actions to 1e-4 where the code agrees."""
+    import torch
+    from lifelike_agility_and_play_b200.policy_epmc import DeviceHierPolicy, SepmcPolicy
+    rng = np.random.default_rng(11)
+    shapes = SEPMC_SHAPES if strategic else SHAPES
+    w = [(rng.standard_normal(s) / np.sqrt(max(1, int(np.prod(s[:-1]))))).astype(np.float32) for s in shapes]
+    w[1] = np.abs(w[1]) + 0.2
+    host = SepmcPolicy(w) if strategic else EpmcPolicy(w)
+    dev = DeviceHierPolicy(w, device=0)
+    n, ow, ld = 300, dev.obs_dim, dev.obs_dim + 7
+    t_state = torch.zeros((n, dev.state_dim), device="cuda")
+    t_act = torch.zeros((n, 12), device="cuda"); t_code = torch.zeros((n,), device="cuda", dtype=torch.int32)
+    t_head = torch.zeros((n,), device="cuda")
+    s_host = host.initial_state(n)
+    same_total, rows = 0, 0
+    for step in range(3):
+        obs = np.zeros((n, ld), np.float32)
+        obs[:, :ow] = rng.standard_normal((n, ow)).astype(np.float32)
+        obs[:, 135:913] = np.abs(obs[:, 135:913]) * 0.7                 # distances / heights are non-negative in the env
+        mask = (rng.uniform(size=n) < (1.0 if step == 0 else 0.3)).astype(np.float32)
+        t_obs = torch.from_numpy(obs).cuda(); t_done = torch.from_numpy(mask.astype(np.uint8)).cuda()
+        dev.forward(t_obs.data_ptr(), ld, n, t_done.data_ptr(), t_state.data_ptr(), t_act.data_ptr(), t_code.data_ptr(), t_head.data_ptr() if strategic else None)
+        torch.cuda.synchronize()
+        if strategic:
+            a_ref, s_host, ang, c_ref = host.act(obs[:, :ow], s_host, mask, return_aux=True)
+            assert np.abs(t_head.cpu().numpy() - ang).max() < 1e-4
+        else:
+            a_ref, s_host, c_ref = host.act(obs[:, :ow], s_host, mask, return_code=True)
+        code = t_code.cpu().numpy(); same = code == c_ref
+        same_total += int(same.sum()); rows += n
+        st = t_state.cpu().numpy()
+        assert np.abs(st - s_host).max() < 2e-4, np.abs(st - s_host).max()
+        err = np.abs(t_act.cpu().numpy()[same] - a_ref[same]).max() / (1.0 + np.abs(a_ref).max())
+        assert err < 1e-4, err
+        s_host = st.copy()                                              # keep both sides on the same trajectory
+    assert same_total >= 0.99 * rows, (same_total, rows)
+    dev.close()

@@ -42,6 +42,7 @@ def main():
     ap.add_argument("--aux", type=float, default=0.0, help="auxiliary_radius (the test script passes None, the train script 0.02)")
     ap.add_argument("--cfg", default="{}")
     ap.add_argument("--out", default="")
+    ap.add_argument("--policy", default="host", choices=["host", "device"], help="numpy statement or csrc/llq_policy_hier.cu")
     a = ap.parse_args()
     if a.stage:
         from load_reference_model import load
@@ -75,6 +76,13 @@ def main():
     eng.set_init_state(INIT_STATE_RUN_0)
     obs = eng.reset()
     state, mask = pol.initial_state(n), np.ones(n, np.float32)
+    dev = None
+    if a.policy == "device":
+        import torch
+        from lifelike_agility_and_play_b200.policy_epmc import DeviceHierPolicy
+        dev = DeviceHierPolicy(weights, device=0)
+        t_state = torch.zeros((n, dev.state_dim), device="cuda"); t_act = torch.zeros((n, 12), device="cuda")
+        t_code = torch.zeros((n,), device="cuda", dtype=torch.int32)
     rng = np.random.default_rng(7) if a.sample else None
     steps_alive, rew_sum = np.zeros(n, int), np.zeros(n)
     start_dist = None
@@ -82,7 +90,13 @@ def main():
     ep_len, ep_rew, ep_progress, ep_speed = [], [], [], []
     codes = np.zeros(256, int)
     for t in range(a.steps):
-        act, state, code = pol.act(obs, state, mask, rng=rng, return_code=True)
+        if dev is not None:
+            t_obs = torch.from_numpy(np.ascontiguousarray(obs, np.float32)).cuda(); t_done = torch.from_numpy(mask.astype(np.uint8)).cuda()
+            dev.forward(t_obs.data_ptr(), obs.shape[1], n, t_done.data_ptr(), t_state.data_ptr(), t_act.data_ptr(), t_code.data_ptr())
+            torch.cuda.synchronize()
+            act, code = t_act.cpu().numpy(), t_code.cpu().numpy()
+        else:
+            act, state, code = pol.act(obs, state, mask, rng=rng, return_code=True)
         codes += np.bincount(code, minlength=256)
         mask[:] = 0
         if start_dist is None:
@@ -118,7 +132,7 @@ def main():
            "mean_episode_reward_sum": float(np.mean(ep_rew)) if ep_rew else None,
            "distinct_codes_used": int((codes > 0).sum()), "top_codes": [int(c) for c in np.argsort(-codes)[:8]],
            "config": {"friction_range": [0.4, 1.0], "target_spd": 3.0, "push": bool(a.push), "auxiliary_radius": a.aux or None,
-                      "code": "sample" if a.sample else "argmax", "overrides": a.cfg}}
+                      "code": "sample" if a.sample else "argmax", "overrides": a.cfg, "policy": a.policy}}
     print(json.dumps(rep, indent=1))
     if a.out:
         json.dump(rep, open(a.out, "w"), indent=1)

@@ -34,6 +34,7 @@ def main():
     ap.add_argument("--staged", default="")
     ap.add_argument("--push", type=int, default=1)
     ap.add_argument("--out", default="")
+    ap.add_argument("--policy", default="host", choices=["host", "device"], help="numpy statement or csrc/llq_policy_hier.cu")
     a = ap.parse_args()
     if a.stage:
         from load_reference_model import load
@@ -65,12 +66,25 @@ def main():
     eng.set_init_state(INIT_STATE_RUN_0)
     obs = eng.reset()
     state, mask = pol.initial_state(n), np.ones(n, np.float32)
+    dev = None
+    if a.policy == "device":
+        import torch
+        from lifelike_agility_and_play_b200.policy_epmc import DeviceHierPolicy
+        dev = DeviceHierPolicy(weights, device=0)
+        t_state = torch.zeros((n, dev.state_dim), device="cuda"); t_act = torch.zeros((n, 12), device="cuda")
+        t_code = torch.zeros((n,), device="cuda", dtype=torch.int32)
     alive = np.zeros(a.pairs, int)
     ends = {"tag": 0, "fall": 0, "timeup": 0}
     ep_len, tag_rew, speeds, gaps = [], [], [], []
     codes = np.zeros(256, int)
     for t in range(a.steps):
-        act, state, ang, code = pol.act(obs, state, mask, return_aux=True)
+        if dev is not None:
+            t_obs = torch.from_numpy(np.ascontiguousarray(obs, np.float32)).cuda(); t_done = torch.from_numpy(mask.astype(np.uint8)).cuda()
+            dev.forward(t_obs.data_ptr(), obs.shape[1], n, t_done.data_ptr(), t_state.data_ptr(), t_act.data_ptr(), t_code.data_ptr())
+            torch.cuda.synchronize()
+            act, code = t_act.cpu().numpy(), t_code.cpu().numpy()
+        else:
+            act, state, ang, code = pol.act(obs, state, mask, return_aux=True)
         codes += np.bincount(code, minlength=256)
         mask[:] = 0
         obs, r, d = eng.step(act)
@@ -102,7 +116,7 @@ def main():
            "mean_robot_speed_mps": float(np.mean(speeds)), "mean_distance_between_the_two_robots_m": float(np.mean(gaps)),
            "robot0_reward_at_tag_mean": float(np.mean(tag_rew)) if tag_rew else None,
            "distinct_codes_used": int((codes > 0).sum()),
-           "config": {"friction_range": [0.4, 1.0], "push": bool(a.push), "control_spd": "engine default", "policy": "mean heading, argmax code, mean action"}}
+           "config": {"friction_range": [0.4, 1.0], "push": bool(a.push), "control_spd": "engine default", "policy": "mean heading, argmax code, mean action", "policy_on": a.policy}}
     print(json.dumps(rep, indent=1))
     if a.out:
         json.dump(rep, open(a.out, "w"), indent=1)
