@@ -468,6 +468,8 @@ def measure(args, env, n, ctx, headline):
            "contact_rows_per_env_substep": float(c1[2] - c0[2]) / max(1, nu * ROBOTS_PER_ENV[env] * args.steps * 10)}
     if headline:
         res["actor"] = actor_loop(args, eng, n, ow, ctx, pool, reward, done) if (env == "pmc" and world == 1) else None
+    if env != "pmc" and world == 1:
+        res["actor"] = hier_actor_loop(args, eng, n, ow, ctx, pool, reward, done, strategic=(env == "sepmc"))
     eng.close()
     return res
 
@@ -521,6 +523,52 @@ def actor_loop(args, eng, n, ow, ctx, pool, reward, done):
            "policy_kernel_ms": p0.elapsed_time(p1) / 64, "policy_kernel_ms_with_value_head_and_sampling": q0.elapsed_time(q1) / 64,
            "policy": "PMC net 207-256-256-32 VQ(256) + 135/32-96-256-256-12, 3xTF32 mma.sync (fp32-level accuracy), random weights",
            "note": "policy forward + fused env step, observations and actions stay in HBM (hot L2, no flush)"}
+    pol.close()
+    return out
+
+
+def hier_actor_loop(args, eng, n, ow, ctx, pool, reward, done, strategic):
+    """Row f2 for the environmental / strategic level: csrc/llq_policy_hier.cu (random weights of the shipped architecture) reads the
+    observation rows in place, keeps its LSTM states on the device, resets them from the engine's own done flags."""
+    import torch
+    from lifelike_agility_and_play_b200.policy_epmc import DeviceHierPolicy, random_weights
+    dev, stream = ctx["dev"], ctx["stream"].cuda_stream
+    wts = random_weights(strategic, seed=42)
+    li = 150 if strategic else 100                           # last decoder layer: small actions, like a trained policy's
+    wts[li - 1] = wts[li - 1] * 0.05
+    pol = DeviceHierPolicy(wts, device=ctx["local_rank"])
+    eng.set_option("record", 0)
+    obs_t = torch.zeros((n, ow), device=dev, dtype=torch.float32)
+    act_t = torch.zeros((n, 12), device=dev, dtype=torch.float32)
+    st_t = torch.zeros((n, pol.state_dim), device=dev, dtype=torch.float32)
+    eng.step_device(pool[0].data_ptr(), obs_t.data_ptr(), reward.data_ptr(), done.data_ptr(), obs_ld=ow, stream=stream)
+
+    def actor_step():
+        pol.forward(obs_t.data_ptr(), ow, n, done.data_ptr(), st_t.data_ptr(), act_t.data_ptr(), None, None, stream)
+        eng.step_device(act_t.data_ptr(), obs_t.data_ptr(), reward.data_ptr(), done.data_ptr(), obs_ld=ow, stream=stream)
+    for i in range(8):
+        actor_step()
+    torch.cuda.synchronize()
+    a0, a1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    a0.record()
+    for i in range(args.steps):
+        actor_step()
+    a1.record()
+    torch.cuda.synchronize()
+    actor_ms = a0.elapsed_time(a1)
+    p0, p1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    p0.record()
+    for i in range(32):
+        pol.forward(obs_t.data_ptr(), ow, n, done.data_ptr(), st_t.data_ptr(), act_t.data_ptr(), None, None, stream)
+    p1.record()
+    torch.cuda.synchronize()
+    units = n // 2 if strategic else n
+    out = {"value": units * args.steps / (actor_ms * 1e-3), "unit": "pair-steps/s" if strategic else "env-steps/s", "ms_per_step": actor_ms / args.steps,
+           "policy_kernel_ms": p0.elapsed_time(p1) / 32, "policy_rows": n,
+           "policy": ("strategic-level net (heading controller + code controller + frozen decoder)" if strategic else
+                      "environmental-level net (conv encoders, layer-norm LSTM, 256-way code, frozen decoder)") +
+                     ", fp32 CUDA cores, one CTA per row, random weights (csrc/llq_policy_hier.cu)",
+           "note": "policy forward + fused env step; observations, LSTM states and actions stay in HBM (hot L2, no flush)"}
     pol.close()
     return out
 
@@ -660,6 +708,8 @@ def main():
     if head.get("actor"):
         line["on_device_actor_loop"] = head["actor"]
     for k, v in sub_out.items():
+        if subs[k].get("actor"):
+            v["on_device_actor_loop"] = subs[k]["actor"]
         v["config"] = {"workload": WORKLOAD["epmc" if k.startswith("epmc") else "sepmc"], "envs_per_gpu": subs[k]["nu"], "robots_per_gpu": subs[k]["n"],
                        "scaling": "weak" if k.startswith("epmc") else "strong (4096 pairs in total over %d GPU%s)" % (world, "s" if world > 1 else ""),
                        "element_id": ELEMENT[0] if k.startswith("epmc") else None, "preroll_steps": max(PREROLL, args.warmup)}

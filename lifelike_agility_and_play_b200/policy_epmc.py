@@ -231,6 +231,29 @@ class SepmcPolicy:
         return (act, new_state, ang[:, 0], code) if return_aux else (act, new_state)
 
 
+_ENC = [(1, 1, 1, 4), (4,), (4, 4, 4, 4), (4,), (2, 2, 4, 4), (4,), (2, 2, 4, 1), (1,), (4, 1, 4), (4,), (4, 4, 4), (4,), (4, 4, 4), (4,), (4, 4, 1), (1,),
+        (1, 1, 1, 4), (4,), (4, 4, 4, 4), (4,), (2, 2, 4, 4), (4,), (2, 2, 4, 1), (1,)]
+_ENC28, _ENC26 = _ENC + [(3, 32), (32,), (120, 64), (64,)], _ENC + [(88, 64), (64,)]
+_LSTM = [(256, 128), (32, 128), (128,), (128,), (128,), (128,), (128,), (32,), (32,)]
+_LLC = [(135, 64), (64,), (32, 32), (32,), (96, 256), (256,), (256, 256), (256,), (256, 12), (12,), (1, 12)]
+# array shapes of the shipped files, in their stored order (environmental_level_*.model: 102 arrays, strategic_level.model: 152)
+EPMC_SHAPES = ([(1, 135), (1, 135), (135, 128), (128,)] + _ENC28 + [(64, 128), (128,), (256, 256), (256,)] + _LSTM + [(32, 1), (1,)] +
+               [(135, 64), (64,)] + _ENC28 + [(128, 256), (256,)] + _LSTM + [(32, 256), (256,), (32, 256)] + _LLC)
+SEPMC_SHAPES = ([(1, 135), (1, 135), (135, 128), (128,)] + _ENC26 + [(64, 128), (128,), (29, 64), (64,), (64, 64), (64,), (64, 128), (128,), (384, 256), (256,)] +
+                _LSTM + [(32, 1), (1,)] +
+                [(135, 64), (64,)] + _ENC26 + [(29, 64), (64,), (64, 64), (64,), (192, 256), (256,)] + _LSTM + [(32, 1), (1,), (1, 1)] +
+                [(135, 64), (64,)] + _ENC28 + [(128, 256), (256,)] + _LSTM + [(32, 256), (256,), (32, 256)] + _LLC)
+
+
+def random_weights(strategic=False, seed=0):
+    """Random weights of the shipped architecture (benchmarks, tests): fan-in scaled normals, positive running std."""
+    rng = np.random.default_rng(seed)
+    shapes = SEPMC_SHAPES if strategic else EPMC_SHAPES
+    w = [(rng.standard_normal(s) / np.sqrt(max(1, int(np.prod(s[:-1]))))).astype(np.float32) for s in shapes]
+    w[1] = np.abs(w[1]) + 0.2
+    return w
+
+
 # ---------------------------------------------------------------------------------------------------------------- device side
 def hier_role_arrays(strategic):
     """Index (in the shipped file's array list) of the array that plays each role of include/llq_policy.h."""

@@ -5,12 +5,7 @@ import numpy as np
 
 from lifelike_agility_and_play_b200.policy_epmc import EpmcPolicy, _same_pad, conv1d_same_relu, conv2d_same_relu
 
-ENC = [(1, 1, 1, 4), (4,), (4, 4, 4, 4), (4,), (2, 2, 4, 4), (4,), (2, 2, 4, 1), (1,), (4, 1, 4), (4,), (4, 4, 4), (4,), (4, 4, 4), (4,), (4, 4, 1), (1,),
-       (1, 1, 1, 4), (4,), (4, 4, 4, 4), (4,), (2, 2, 4, 4), (4,), (2, 2, 4, 1), (1,), (3, 32), (32,), (120, 64), (64,)]
-LSTM = [(256, 128), (32, 128), (128,), (128,), (128,), (128,), (128,), (32,), (32,)]
-SHAPES = ([(1, 135), (1, 135), (135, 128), (128,)] + ENC + [(64, 128), (128,), (256, 256), (256,)] + LSTM + [(32, 1), (1,)] +
-          [(135, 64), (64,)] + ENC + [(128, 256), (256,)] + LSTM + [(32, 256), (256,), (32, 256)] +
-          [(135, 64), (64,), (32, 32), (32,), (96, 256), (256,), (256, 256), (256,), (256, 12), (12,), (1, 12)])
+from lifelike_agility_and_play_b200.policy_epmc import EPMC_SHAPES as SHAPES, SEPMC_SHAPES  # noqa: E402
 
 
 def random_weights(seed=0):
@@ -67,14 +62,6 @@ def test_policy_structure_and_state():
     # only the proprioception is normalised and clipped
     big = obs.copy(); big[:, :135] = 1e6
     assert np.isfinite(pol.act(big, s0, np.ones(6, np.float32))[0]).all()
-
-
-ENC26 = ENC[:24] + [(88, 64), (64,)]
-SEPMC_SHAPES = ([(1, 135), (1, 135), (135, 128), (128,)] + ENC26 + [(64, 128), (128,), (29, 64), (64,), (64, 64), (64,), (64, 128), (128,), (384, 256), (256,)] +
-                LSTM + [(32, 1), (1,)] +
-                [(135, 64), (64,)] + ENC26 + [(29, 64), (64,), (64, 64), (64,), (192, 256), (256,)] + LSTM + [(32, 1), (1,), (1, 1)] +
-                [(135, 64), (64,)] + ENC + [(128, 256), (256,)] + LSTM + [(32, 256), (256,), (32, 256)] +
-                [(135, 64), (64,), (32, 32), (32,), (96, 256), (256,), (256, 256), (256,), (256, 12), (12,), (1, 12)])
 
 
 def test_strategic_policy_structure_and_state():

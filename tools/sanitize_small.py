@@ -59,4 +59,16 @@ for n in (1, 77):
     pol.forward_ex(o.data_ptr(), 223, n, a.data_ptr(), c.data_ptr(), v.data_ptr(), p.data_ptr(), 5, 9, None)
     torch.cuda.synchronize()
 pol.close()
+# environmental- / strategic-level policy kernel (convolutions, LSTM state in place, ragged row count, slab stride)
+from lifelike_agility_and_play_b200.policy_epmc import DeviceHierPolicy, random_weights as hier_weights
+for strategic in (False, True):
+    hp = DeviceHierPolicy(hier_weights(strategic, 3), device=0)
+    for n in (1, 37):
+        ld = hp.obs_dim + 3
+        o = torch.rand((n, ld), device="cuda"); a = torch.zeros((n, 12), device="cuda"); st = torch.zeros((n, hp.state_dim), device="cuda")
+        d = (torch.rand((n,), device="cuda") < 0.5).to(torch.uint8); c = torch.zeros((n,), device="cuda", dtype=torch.int32); hd = torch.zeros((n,), device="cuda")
+        hp.forward(o.data_ptr(), ld, n, d.data_ptr(), st.data_ptr(), a.data_ptr(), c.data_ptr(), hd.data_ptr() if strategic else None)
+        hp.forward(o.data_ptr(), ld, n, None, st.data_ptr(), a.data_ptr(), None, None)
+        torch.cuda.synchronize()
+    hp.close()
 print("sanitize run done")
