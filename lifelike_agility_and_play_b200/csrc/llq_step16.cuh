@@ -6,11 +6,11 @@
 //                 base/joint coupling block and its row of the leg's 3x3 joint-space inertia H_k (composite-rigid-body form);
 //   * sphere lane collision spheres l and l + 16 of the robot (feet, knee wheels, hips, thighs, shanks, trunk corners) against
 //                 the ground / arena walls / corridor boxes, compacted into the env's contact list with one ballot;
-//   * row lane    ONE constraint row of the sub-step's LCP (lanes 0-11: direction d = l % 3 of contact l / 3; lanes 12-15: a
-//                 violated joint limit): its image (y, w) under the block factorisation of the mass matrix, its row of the
-//                 Delassus matrix in registers, and its impulse in Bullet's sequential-impulse sweep, where every row update is
-//                 one __shfl_sync broadcast + one FMA per lane.  More than 4 contacts or 4 limit rows in an env switch the warp
-//                 to a second slot per lane (8 + 8 rows per env).
+//   * row lane    ONE constraint row of the sub-step's LCP: its image (y, w) under the block factorisation of the mass matrix, its row
+//                 of Delassus coefficients (shared memory) and its impulse in Bullet's sequential-impulse sweep, where every row
+//                 update is one __shfl_sync broadcast + one FMA per lane.  For this role the CTA's envs are re-paired by row count
+//                 every sub-step (heaviest with lightest) and the rows of a pair are packed into the warp's 32 lanes -- a lane's row
+//                 may belong to either env of the pair, or (after the re-pairing) to an env another warp owns (see solve_rows).
 // The dynamics are the same equations Bullet's articulated-body algorithm solves, factorised block-wise instead of link by link:
 //   [ Ic  F ] [a0]   [-p0   ]        H_k = L D L^T per leg,  S = Ic - sum_k F_k H_k^-1 F_k^T = L0 L0^T  (6x6, replicated),
 //   [ F^T H ] [qdd] = [tau - C]       J M^-1 J'^T = y.y' + [same leg] w.(D^-1 w'),  y = L0^-1 (G - F_k H_k^-1 j),  w = L^-1 j.
@@ -24,14 +24,8 @@
 namespace llq {
 
 #ifndef LLQ16_BLOCK
-#define LLQ16_BLOCK 224   // 14 envs per CTA: 4096 envs = 293 CTAs = one wave of 2 CTAs (14 warps) per SM; 256 would put 16 warps on 108 of the 148 SMs
-                          // 128 0.334, 256 0.302, 512 0.303 -- the bigger the CTA, the more warps march through the 86 kB sub-step body together
-#endif
-#ifndef LLQ16_BAR
-#define LLQ16_BAR 1     // (>= 2: one more CTA barrier after the dynamics phase; the two around the solver are always there)
-#endif
-#ifndef LLQ16_PGS_V2
-#define LLQ16_PGS_V2 1   // sweep loops with induction-variable addressing (0: the indexed form, kept for A/B builds)
+#define LLQ16_BLOCK 224   // 14 envs per CTA: 4096 envs = 293 CTAs = one wave of 2 CTAs (14 warps) per SM; 256 would put 16 warps on 108 of the
+                          // 148 SMs (0.263 -> 0.247 ms); 128 / 160 threads: 0.256 / 0.249 ms
 #endif
 #ifndef LLQ16_MINB
 #define LLQ16_MINB 4   // resident CTAs per SM the register budget is sized for (4 x 128 threads x 128 registers = the whole file)
@@ -48,13 +42,9 @@ constexpr int kLimTab = kMaxLim * 4;  // limit row: leg joint dir pen
 constexpr int kRowW = 12, kRowTab = 32 * kRowW;        // row: y(6) e(3) leg - -   (aliased by the 16 x 20 float scratch of the dynamics phase)
 constexpr int kEnvTab = 56;           // p_base(6) - - | Cholesky factor of the base block (21) - - - | joint targets (12) | actions (12)
 constexpr int kATabWarp = 32 * 32;     // Delassus coefficients of one WARP (its two envs' rows packed into 32 lanes): atab[col * 32 + lane]
-constexpr int kEnvFloats = 944;        // >= the sum of the tables, and = 16 (mod 32): the two envs of a warp hit disjoint banks
+constexpr int kEnvFloats = 944;        // >= the sum of the tables, and = 16 (mod 32): envs an odd number of slots apart hit disjoint banks
 static_assert(kLinkTab + kLegTab + kConTab + kLimTab + kRowTab + kEnvTab <= kEnvFloats && kEnvFloats % 32 == 16, "per-env table layout");
 
-LLQ_DI float hsum16(float v) {        // sum over the 16 lanes of an env
-  v += __shfl_xor_sync(FULL, v, 1); v += __shfl_xor_sync(FULL, v, 2); v += __shfl_xor_sync(FULL, v, 4); v += __shfl_xor_sync(FULL, v, 8);
-  return v;
-}
 LLQ_DI V3 rotxy(V3 v, float cy, float sy, float cx, float sx) { return rot<0>(rot<1>(v, cy, sy), cx, sx); }     // Rx Ry v
 LLQ_DI V3 rotxyT(V3 v, float cy, float sy, float cx, float sx) { return rotT<1>(rotT<0>(v, cx, sx), cy, sy); }  // (Rx Ry)^T v
 LLQ_DI float dot6(const float (&a)[6], const float (&b)[6]) {
@@ -117,7 +107,7 @@ LLQ_DI void chol6_bwd_p(const float* l, const float (&y)[6], float (&x)[6]) {
 LLQ_DI float4 ld4(const float* p) { return *reinterpret_cast<const float4*>(p); }
 LLQ_DI void st4(float* p, float a, float b, float c, float d) { *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d); }
 
-// fp64 distance of a sphere centre (world) to an axis-aligned box (centre + half extents), with the contact normal (old kernel, ENV 3)
+// fp64 distance of a sphere centre (world) to an axis-aligned box (centre + half extents), with the contact normal (EPMC corridor)
 LLQ_DI void sphere_box(double wx, double wy, double wz, double r, const float* b, double& db, V3& nn) {
   const double p0 = wx - (double)b[0], p1 = wy - (double)b[1], p2 = wz - (double)b[2];
   const double h0 = b[3], h1 = b[4], h2 = b[5];
@@ -175,7 +165,7 @@ struct RowsIn {
   int lane0;            // first lane of that env's rows
   int lane;             // 0..31
   int split;            // warp-uniform: 16 = every row on its own env's half-warp
-  int Cmax, Lmax, ncols;   // warp-uniform maxima over the envs of this pass: contacts, limit rows, rows
+  int Cmax, Lmax;       // warp-uniform maxima over the envs of this pass: contacts, limit rows
   float* res;           // where the totals of the env behind this lane's HALF-warp go (18 floats at the head of its row table), or
                         // nullptr when that env is not solved in this pass
   float dt, slop, erp, jerp, max_imp;
@@ -287,8 +277,8 @@ LLQ_DI void impulse_sums(const RowsIn& in, const RowRegs& r) {
   }
   if (in.split != 16) {                                     // warp-uniform
     const bool foreign = (in.lane >= 16) != (in.lane >= in.split);      // the row belongs to the other half-warp's env
-#pragma unroll 1
-    for (int t = 0; t < 18; t++) {
+#pragma unroll
+    for (int t = 0; t < 18; t++) {                          // (unrolled: a rolled loop would index v18 in local memory)
       const float mine = foreign ? 0.f : v18[t], give = foreign ? v18[t] : 0.f;
       v18[t] = mine + __shfl_xor_sync(FULL, give, 16);
     }
@@ -706,7 +696,7 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
   __shared__ __align__(16) float s_new[EPT][kNewObs];
   __shared__ __align__(16) float s_hist[EPT][kHist];
   __shared__ int s_cnt[32];                                   // contacts | limit rows << 8 of the CTA's envs, this sub-step
-  extern __shared__ __align__(16) float s_env_dyn[];   // [EPB][kEnvFloats]: 38.4 kB, beside 10 kB of static shared memory
+  extern __shared__ __align__(16) float s_env_dyn[];   // [EPB][kEnvFloats] per-env tables, then one kATabWarp coefficient table per warp
   const int tid = threadIdx.x;
   const int N = P.n_envs;
   prefetch_model(gmodel, &M, BLOCK);
@@ -1047,11 +1037,7 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
     }
     }   // ================ end of the forward dynamics
     T16_MARK(1);
-#if LLQ16_BAR >= 2
-    __syncthreads();
-#else
     __syncwarp();
-#endif
     const M3 R = qmat(qp);                            // world <- B' (recomputed: cheaper than keeping nine registers alive)
     // ---------------- PMC hurdle plate: getContactPoints (PLE:343) reports the manifolds built on the last sub-step's pre-step poses
     if (ENV == 0 && P.has_ob && sub == P.substeps - 1) {
@@ -1338,7 +1324,6 @@ __global__ void __launch_bounds__(LLQ16_BLOCK, LLQ16_MINB * 128 / LLQ16_BLOCK) l
           in.lane0 = X ? split : 0; in.rr = lane - in.lane0; in.split = split;
           in.Cmax = two_pass ? (pass == 0 ? cA : cB) : max(cA, cB);
           in.Lmax = two_pass ? (pass == 0 ? lA : lB) : max(lA, lB);
-          in.ncols = two_pass ? (pass == 0 ? nA : nB) : max(nA, nB);
           const bool upper = lane >= 16;
           in.res = (two_pass && upper != (pass == 1)) ? nullptr : (upper ? tbB : tbA) + (kLinkTab + kLegTab + kConTab + kLimTab);
           solve_rows(in);
