@@ -42,45 +42,47 @@ static_assert(R_N_MLC == LLQ_HIER_ROLES_MLC && R_N_ALL == LLQ_HIER_ROLES_ALL, "r
 struct Net { const float* w; const int* off; };
 __device__ __forceinline__ const float* arr(const Net& n, int role) { return n.w + n.off[role]; }
 
-// out[r][j] = act(b[j] + sum_k in[r][k] W[k][j]) for the CTA's kRows rows; W row major [K][N]; the 256 threads split K into 256 / N
-// parts (N <= 256); a weight is loaded once and used for all rows (the inputs are shared-memory broadcasts)
+// out[r][j] = act(b[j] + sum_k in[r][k] W[k][j]) for the CTA's kRows rows; W row major [K][N], N a multiple of 4, every array 16-byte
+// aligned in the blob.  A thread owns FOUR consecutive columns of all rows (one 16-byte weight load and kRows shared-memory broadcasts
+// per 4 x kRows FMAs); the input dimension is split into `parts` interleaved slices over the thread groups, partial sums meet in `scratch`
+// (parts * kRows * N <= 4096 floats).
 __device__ void dense(const float* in, int in_ld, int K, const float* W, const float* b, int N, float* out, int out_ld, float* scratch, bool relu) {
   const int t = threadIdx.x;
-  int parts = kThreads / N; if (parts < 1) parts = 1; if (parts > 8) parts = 8;
-  const int j = t % N, p = t / N;
-  float acc[kRows];
-#pragma unroll
-  for (int r = 0; r < kRows; r++) acc[r] = 0.f;
+  const int quads = N >> 2;
+  int parts = kThreads / quads; if (parts > 8) parts = 8; if (parts > 512 / N) parts = 512 / N; if (parts < 1) parts = 1;
+  const int jq = t % quads, p = t / quads;
   if (p < parts) {
+    float acc[kRows][4];
+#pragma unroll
+    for (int r = 0; r < kRows; r++) { acc[r][0] = 0.f; acc[r][1] = 0.f; acc[r][2] = 0.f; acc[r][3] = 0.f; }
+    const float4* Wq = reinterpret_cast<const float4*>(W) + jq;
     int k = p;
-    for (; k + 7 * parts < K; k += 8 * parts) {             // eight weight loads in flight (the layer is bound by L2 latency, not bandwidth)
-      float w[8];
+    for (; k + 3 * parts < K; k += 4 * parts) {             // four 16-byte weight loads in flight
+      float4 w[4];
 #pragma unroll
-      for (int u = 0; u < 8; u++) w[u] = W[(size_t)(k + u * parts) * N + j];
+      for (int u = 0; u < 4; u++) w[u] = Wq[(size_t)(k + u * parts) * quads];
 #pragma unroll
-      for (int u = 0; u < 8; u++) {
+      for (int u = 0; u < 4; u++) {
 #pragma unroll
-        for (int r = 0; r < kRows; r++) acc[r] = fmaf(in[r * in_ld + k + u * parts], w[u], acc[r]);
+        for (int r = 0; r < kRows; r++) {
+          const float x = in[r * in_ld + k + u * parts];
+          acc[r][0] = fmaf(x, w[u].x, acc[r][0]); acc[r][1] = fmaf(x, w[u].y, acc[r][1]);
+          acc[r][2] = fmaf(x, w[u].z, acc[r][2]); acc[r][3] = fmaf(x, w[u].w, acc[r][3]);
+        }
       }
     }
     for (; k < K; k += parts) {
-      const float w = W[(size_t)k * N + j];
+      const float4 w = Wq[(size_t)k * quads];
 #pragma unroll
-      for (int r = 0; r < kRows; r++) acc[r] = fmaf(in[r * in_ld + k], w, acc[r]);
+      for (int r = 0; r < kRows; r++) {
+        const float x = in[r * in_ld + k];
+        acc[r][0] = fmaf(x, w.x, acc[r][0]); acc[r][1] = fmaf(x, w.y, acc[r][1]);
+        acc[r][2] = fmaf(x, w.z, acc[r][2]); acc[r][3] = fmaf(x, w.w, acc[r][3]);
+      }
     }
-  }
-  if (parts == 1) {
-    if (t < N) {
-      const float bj = b ? b[t] : 0.f;
 #pragma unroll
-      for (int r = 0; r < kRows; r++) { const float v = acc[r] + bj; out[r * out_ld + t] = relu ? fmaxf(v, 0.f) : v; }
-    }
-    __syncthreads();
-    return;
-  }
-  if (p < parts) {
-#pragma unroll
-    for (int r = 0; r < kRows; r++) scratch[(p * kRows + r) * N + j] = acc[r];
+    for (int r = 0; r < kRows; r++)
+      *reinterpret_cast<float4*>(scratch + (p * kRows + r) * N + 4 * jq) = make_float4(acc[r][0], acc[r][1], acc[r][2], acc[r][3]);
   }
   __syncthreads();
   for (int idx = t; idx < kRows * N; idx += kThreads) {
@@ -235,13 +237,13 @@ __device__ void lstm_step(const Net& n, int lstm, const float* x, float* state, 
 }
 
 constexpr int kObsLd = 968;      // shared-memory row stride of the observation block
-struct Smem {
+struct alignas(16) Smem {
+  float scr[4096];                 // partial sums of the split layers (parts * rows * N <= 4096); first member: 16-byte aligned
   float obs[kRows][kObsLd];
   float p[kRows][136];
   float cat[kRows][256], x[kRows][256], y[kRows][256];
   float zx[kRows][128], zh[kRows][128], c[kRows][64], h[kRows][32];
   float a[kRows * 364], b[kRows * 128];   // convolution buffers: [13][7][4] / [64][4] and [7][4][4] / [32][4] per row
-  float scr[8 * kRows * 32];       // partial sums of the split layers (parts * rows * N <= 2048)
   float ang[kRows];
   int code[kRows], live[kRows], wipe[kRows];
 };

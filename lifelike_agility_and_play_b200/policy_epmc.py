@@ -278,6 +278,7 @@ class DeviceHierPolicy:
         w = [np.ascontiguousarray(a, np.float32).reshape(-1) for a in weights]
         self.strategic = len(w) == 152
         assert len(w) in (102, 152), "expected an environmental-level (102 arrays) or a strategic-level (152 arrays) model"
+        w = [np.concatenate([a, np.zeros((-a.size) % 4, np.float32)]) for a in w]        # every array starts on a 16-byte boundary (float4 loads)
         starts = np.concatenate([[0], np.cumsum([a.size for a in w])]).astype(np.int64)
         blob = np.concatenate(w)
         off = np.array([starts[i] for i in hier_role_arrays(self.strategic)], np.int32)
