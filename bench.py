@@ -11,7 +11,7 @@ of every environment of the batch.  Contract: see the task statement / DESIGN.md
 
 What the one JSON line holds (N = 1): the PMC headline (`value`, `e2e`, `roofline`, `cpu_baseline`, `on_device_actor_loop`) and
 the other single-GPU configurations of BASELINE.json as sub-objects `epmc_8192` (configs[2]) and `sepmc_4096pairs` (configs[4]),
-each with its own value / e2e / roofline.  N > 1: the PMC shards with the [128, N, 223] trajectory hand-over to rank 0 always
+each with its own value / e2e / roofline / on_device_actor_loop (the environmental- / strategic-level policy kernel in the loop).  N > 1: the PMC shards with the [128, N, 223] trajectory hand-over to rank 0 always
 measured (`gather`), whatever --steps says.
 """
 import argparse
